@@ -1,0 +1,422 @@
+/*
+ * classify_main.c -- `deSAMBA-b200 classify`: drop-in for `deSAMBA classify` (cly_mt.c:482-562) with the per-read
+ * classifier running on B200 GPUs through the C ABI of include/desamba_b200.h.
+ *
+ * Same options (-h -t -l -r -o -s -f), same index directory, same text output in input order, same stderr summary.
+ * What replaces the reference's host (kt_pipeline + kt_for thread pool, cly_mt.c:369-398):
+ *   reader thread   FASTQ(.gz) -> batches in pinned host memory             (read_reads, cly_mt.c:42-56; kseq, utils.c:939-977)
+ *   one thread/GPU  dsb_classify_batch on its own context; batches are dealt in input order
+ *   writer (main)   formats the result records of each batch in input order (output_results, cly_mt.c:350-365)
+ * The index is replicated per GPU, reads are sharded by batch, nothing is exchanged between GPUs.
+ * Extra options: -g INT GPUs to use [all visible], -B INT reads per batch [65536], -M INT Mbases per batch [64].
+ * -t is accepted and ignored (the thread pool it sized no longer exists).
+ *
+ * Classify_buff_pool.max_read_l (cly.c:2958) is the reference's only cross-read state; with -t 1 it is the running maximum
+ * in input order.  It only matters through the test `max_read_l < 510`, so a batch needs its predecessors' value only
+ * when it holds a read < 510 bp while an unfinished earlier batch holds one >= 510 bp; only then does a GPU wait.
+ */
+#define _GNU_SOURCE
+#include "desamba_b200.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <pthread.h>
+#include <sys/time.h>
+#include <sys/resource.h>
+#include <zlib.h>
+
+enum { FMT_SAM = 1, FMT_SAM_FULL = 2, FMT_DES = 3, FMT_DES_FULL = 4 };
+
+typedef struct {
+	int l_min_match, n_threads, max_sec_N, fmt, min_score, n_gpus;
+	uint32_t batch_reads; uint64_t batch_bases;
+	FILE *out;
+} opts_t;
+
+/* ---------------------------------------------------------------- batches */
+enum { SLOT_FREE = 0, SLOT_READY, SLOT_BUSY, SLOT_DONE };
+typedef struct {
+	int state; int rc;
+	uint64_t seq_no;
+	uint32_t n_reads; uint64_t n_bases;
+	char *seqs; size_t m_seqs;              /* pinned */
+	uint64_t *offs; size_t m_offs;          /* pinned, n_reads + 1 */
+	char *quals; size_t m_quals;            /* SAM_FULL only, same offsets as seqs */
+	char *names; size_t n_names, m_names;   /* NUL-terminated, concatenated */
+	uint32_t *name_off; size_t m_name_off;
+	int has_long, has_short;
+	dsb_read_result *rr; size_t m_rr;
+	dsb_hit *hits; size_t m_hits; uint64_t n_hits;
+} slot_t;
+
+typedef struct {
+	opts_t *o;
+	int n_slots; slot_t *slot;
+	pthread_mutex_t mu; pthread_cond_t cv;
+	uint64_t n_filled, n_claimed, n_written; int eof;
+	int32_t known_max;                      /* max_read_l over finished batches */
+	int error; char errmsg[600];
+	int n_files; char **files;
+	uint64_t total_sequences;
+} shared_t;
+
+typedef struct { shared_t *sh; int gpu; dsb_index *ix; dsb_ctx *ctx; } worker_t;
+
+static void fail(shared_t *sh, const char *what, int rc)
+{
+	pthread_mutex_lock(&sh->mu);
+	if (!sh->error) { sh->error = rc ? rc : -1; snprintf(sh->errmsg, sizeof sh->errmsg, "%s: %s", what, dsb_last_error()); }
+	pthread_cond_broadcast(&sh->cv);
+	pthread_mutex_unlock(&sh->mu);
+}
+
+/* ---------------------------------------------------------------- FASTQ reader (kseq_read semantics, utils.c:939-977) */
+typedef struct { gzFile fp; unsigned char *buf; int n, pos, eof; int last_char; } stream_t;
+#define SBUF (1 << 20)
+static inline int st_getc(stream_t *s)
+{
+	if (s->pos >= s->n) {
+		if (s->eof) return -1;
+		s->n = gzread(s->fp, s->buf, SBUF); s->pos = 0;
+		if (s->n <= 0) { s->eof = 1; s->n = 0; return -1; }
+	}
+	return s->buf[s->pos++];
+}
+/* append bytes up to (not including) the next '\n' (or any whitespace if `word`) to *dst; returns the delimiter or -1 */
+static int st_getuntil(stream_t *s, int word, char **dst, size_t *n, size_t *m)
+{
+	for (;;) {
+		if (s->pos >= s->n) {
+			if (s->eof) return -1;
+			s->n = gzread(s->fp, s->buf, SBUF); s->pos = 0;
+			if (s->n <= 0) { s->eof = 1; s->n = 0; return -1; }
+		}
+		int i = s->pos;
+		if (word) { while (i < s->n && s->buf[i] != '\n' && s->buf[i] != ' ' && s->buf[i] != '\t' && s->buf[i] != '\r' && s->buf[i] != '\v' && s->buf[i] != '\f') i++; }
+		else { unsigned char *p = memchr(s->buf + i, '\n', s->n - i); i = p ? (int)(p - s->buf) : s->n; }
+		size_t add = i - s->pos;
+		if (dst) {
+			if (*n + add + 1 > *m) { *m = (*n + add + 1) * 2; *dst = realloc(*dst, *m); }
+			memcpy(*dst + *n, s->buf + s->pos, add); *n += add;
+		}
+		s->pos = i;
+		if (i < s->n) { s->pos++; return s->buf[i]; }
+	}
+}
+
+typedef struct { char *name, *seq, *qual; size_t n_name, m_name, n_seq, m_seq, n_qual, m_qual; } rec_t;
+/* returns seq length >= 0, -1 at end of file, -2 on a truncated quality string (kseq's error codes) */
+static long read_record(stream_t *s, rec_t *r)
+{
+	int c;
+	if (s->last_char == 0) {
+		while ((c = st_getc(s)) != -1 && c != '>' && c != '@');
+		if (c == -1) return -1;
+		s->last_char = c;
+	}
+	r->n_name = r->n_seq = r->n_qual = 0;
+	c = st_getuntil(s, 1, &r->name, &r->n_name, &r->m_name);
+	if (c == -1 && r->n_name == 0) return -1;
+	if (c != '\n' && c != -1) st_getuntil(s, 0, NULL, NULL, NULL);         /* comment */
+	while ((c = st_getc(s)) != -1 && c != '>' && c != '+' && c != '@') {
+		if (c == '\n') continue;
+		if (r->n_seq + 2 > r->m_seq) { r->m_seq = (r->n_seq + 2) * 2; r->seq = realloc(r->seq, r->m_seq); }
+		r->seq[r->n_seq++] = (char)c;
+		st_getuntil(s, 0, &r->seq, &r->n_seq, &r->m_seq);
+		while (r->n_seq && r->seq[r->n_seq - 1] == '\r') r->n_seq--;
+	}
+	s->last_char = (c == '>' || c == '@') ? c : 0;
+	if (c != '+') return (long)r->n_seq;                                     /* FASTA record */
+	st_getuntil(s, 0, NULL, NULL, NULL);                                     /* rest of the '+' line */
+	while (r->n_qual < r->n_seq) {
+		c = st_getuntil(s, 0, &r->qual, &r->n_qual, &r->m_qual);
+		while (r->n_qual && r->qual[r->n_qual - 1] == '\r') r->n_qual--;
+		if (c == -1) break;
+	}
+	s->last_char = 0;
+	if (r->n_qual != r->n_seq) return -2;
+	return (long)r->n_seq;
+}
+
+static int grow_pinned(void **p, size_t *m, size_t need, size_t keep)
+{
+	if (need <= *m) return 0;
+	size_t nm = need + need / 2 + 4096; void *np = NULL;
+	if (dsb_host_alloc(nm, &np) != DSB_OK) return -1;
+	if (*p) { memcpy(np, *p, keep); dsb_host_free(*p); }
+	*p = np; *m = nm;
+	return 0;
+}
+
+static void *reader_main(void *arg)
+{
+	shared_t *sh = (shared_t *)arg; opts_t *o = sh->o;
+	stream_t st; memset(&st, 0, sizeof st); st.buf = malloc(SBUF);
+	rec_t rec; memset(&rec, 0, sizeof rec);
+	int file_i = 0, stream_open = 0, pending = 0;      /* pending: rec holds a record not yet stored */
+	long plen = 0;
+	for (;;) {
+		pthread_mutex_lock(&sh->mu);
+		slot_t *b = &sh->slot[sh->n_filled % sh->n_slots];
+		while (b->state != SLOT_FREE && !sh->error) pthread_cond_wait(&sh->cv, &sh->mu);
+		int err = sh->error;
+		pthread_mutex_unlock(&sh->mu);
+		if (err) break;
+		b->n_reads = 0; b->n_bases = 0; b->n_names = 0; b->has_long = b->has_short = 0;
+		int end_of_input = 0;
+		while (b->n_reads < o->batch_reads && b->n_bases < o->batch_bases) {
+			if (!pending) {
+				if (!stream_open) {
+					if (file_i >= sh->n_files) { end_of_input = 1; break; }
+					st.fp = gzopen(sh->files[file_i], "r");
+					if (!st.fp) { fprintf(stderr, "[xzopen] fail to open file '%s'\n", sh->files[file_i]); fail(sh, "open reads", -2); end_of_input = 1; break; }
+					gzbuffer(st.fp, 1 << 18);
+					st.n = st.pos = st.eof = 0; st.last_char = 0; stream_open = 1;
+					fprintf(stderr, "Processing file: [%s].\n", sh->files[file_i]);
+				}
+				plen = read_record(&st, &rec);
+				if (plen < 0) { gzclose(st.fp); stream_open = 0; file_i++; continue; }   /* -1 end of file; -2 ends the file like the reference ends its run */
+				pending = 1;
+			}
+			size_t L = (size_t)plen;
+			if (grow_pinned((void **)&b->seqs, &b->m_seqs, b->n_bases + L + 16, b->n_bases) ||
+			    grow_pinned((void **)&b->offs, &b->m_offs, ((size_t)b->n_reads + 2) * 8, ((size_t)b->n_reads + 1) * 8)) { fail(sh, "pinned alloc", -4); end_of_input = 1; break; }
+			if (b->n_reads == 0) b->offs[0] = 0;
+			memcpy(b->seqs + b->n_bases, rec.seq, L);
+			if (o->fmt == FMT_SAM_FULL) {
+				if (b->n_bases + L + 1 > b->m_quals) { b->m_quals = (b->n_bases + L + 1) * 2; b->quals = realloc(b->quals, b->m_quals); }
+				if (rec.n_qual == L) memcpy(b->quals + b->n_bases, rec.qual, L); else memset(b->quals + b->n_bases, '*', L);
+			}
+			if ((size_t)b->n_reads + 1 > b->m_name_off) { b->m_name_off = ((size_t)b->n_reads + 1) * 2; b->name_off = realloc(b->name_off, b->m_name_off * 4); }
+			if (b->n_names + rec.n_name + 1 > b->m_names) { b->m_names = (b->n_names + rec.n_name + 1) * 2; b->names = realloc(b->names, b->m_names); }
+			b->name_off[b->n_reads] = (uint32_t)b->n_names;
+			memcpy(b->names + b->n_names, rec.name, rec.n_name); b->names[b->n_names + rec.n_name] = 0; b->n_names += rec.n_name + 1;
+			b->n_bases += L; b->n_reads++; b->offs[b->n_reads] = b->n_bases;
+			if (L >= 510) b->has_long = 1; else b->has_short = 1;
+			pending = 0;
+		}
+		pthread_mutex_lock(&sh->mu);
+		if (b->n_reads) { b->seq_no = sh->n_filled; b->state = SLOT_READY; sh->n_filled++; sh->total_sequences += b->n_reads; }
+		if (end_of_input) sh->eof = 1;
+		pthread_cond_broadcast(&sh->cv);
+		pthread_mutex_unlock(&sh->mu);
+		if (end_of_input) break;
+	}
+	free(st.buf); free(rec.name); free(rec.seq); free(rec.qual);
+	return NULL;
+}
+
+/* ---------------------------------------------------------------- GPU workers */
+static void *worker_main(void *arg)
+{
+	worker_t *w = (worker_t *)arg; shared_t *sh = w->sh;
+	for (;;) {
+		pthread_mutex_lock(&sh->mu);
+		while (!sh->error && sh->n_claimed == sh->n_filled && !sh->eof) pthread_cond_wait(&sh->cv, &sh->mu);
+		if (sh->error || sh->n_claimed == sh->n_filled) { pthread_mutex_unlock(&sh->mu); break; }
+		const uint64_t my = sh->n_claimed++;
+		slot_t *b = &sh->slot[my % sh->n_slots];
+		b->state = SLOT_BUSY;
+		/* the only cross-batch dependency (see the header comment) */
+		if (sh->known_max < 510 && b->has_short) {
+			for (;;) {
+				int earlier_long = 0;
+				for (uint64_t k = sh->n_written; k < my; k++) { slot_t *e = &sh->slot[k % sh->n_slots]; if (e->state == SLOT_BUSY && e->has_long) earlier_long = 1; }
+				if (!earlier_long || sh->known_max >= 510 || sh->error) break;
+				pthread_cond_wait(&sh->cv, &sh->mu);
+			}
+		}
+		const int32_t max_in = sh->known_max;
+		pthread_mutex_unlock(&sh->mu);
+
+		if ((size_t)b->n_reads > b->m_rr) { b->m_rr = (size_t)b->n_reads * 2; b->rr = realloc(b->rr, b->m_rr * sizeof *b->rr); }
+		size_t want = (size_t)b->n_reads * 24 + 4096;
+		int32_t max_out = max_in; int rc;
+		for (;;) {
+			if (want > b->m_hits) { b->m_hits = want; free(b->hits); b->hits = malloc(b->m_hits * sizeof *b->hits); }
+			rc = dsb_classify_batch(w->ctx, b->seqs, b->offs, b->n_reads, max_in, &max_out, b->rr, b->hits, b->m_hits, &b->n_hits);
+			if (rc == DSB_E_CAPACITY && b->n_hits > b->m_hits) { want = b->n_hits; continue; }
+			break;
+		}
+		if (rc != DSB_OK) { fail(sh, "dsb_classify_batch", rc); break; }
+		pthread_mutex_lock(&sh->mu);
+		if (max_out > sh->known_max) sh->known_max = max_out;
+		b->state = SLOT_DONE; b->rc = rc;
+		pthread_cond_broadcast(&sh->cv);
+		pthread_mutex_unlock(&sh->mu);
+	}
+	return NULL;
+}
+
+/* ---------------------------------------------------------------- writers (cly_mt.c:60-344) */
+typedef struct { char *s; size_t n, m; } obuf_t;
+static inline void ob_need(obuf_t *b, size_t add) { if (b->n + add > b->m) { b->m = (b->n + add) * 2 + 4096; b->s = realloc(b->s, b->m); } }
+static const char PRI_STR[3][4] = {"PRI", "SEC", "SUP"};
+
+static void put_hit(obuf_t *ob, const dsb_hit *c, const dsb_ref_info *ri, int rst_cnt)      /* print_hit, cly_mt.c:60-105 */
+{
+	ob_need(ob, 400);
+	ob->n += sprintf(ob->s + ob->n, "%3d %s %s %20s ts:%-10d te:%-10d qs:%-10d qe:%-10d %-5d\t%d\t\n", rst_cnt, PRI_STR[c->primary - 1], c->direction ? "F" : "R",
+	                 ri[c->ref_ID].name, (int)c->t_st, (int)c->t_ed, (int)c->q_st, (int)c->q_ed, (int)c->sum_score, (int)c->indel);
+}
+
+static void format_read(obuf_t *ob, const opts_t *o, const dsb_ref_info *ri, const dsb_read_result *r, const dsb_hit *hits,
+                        const char *name, const char *seq, const char *qual, uint32_t L)
+{
+	const size_t ln = strlen(name);
+	const dsb_hit *c_s = hits + r->hit_off, *c_e = c_s + r->n_hit;
+	if (o->fmt == FMT_DES || o->fmt == FMT_DES_FULL) {              /* output_one_result_des / _full, cly_mt.c:158-246 */
+		ob_need(ob, ln + 200);
+		ob->n += sprintf(ob->s + ob->n, "%s\t%s\t%s\t%ld\tn_rst:[%ld]\tn_anc:[%ld]\t\n", name, r->n_hit ? "CLASSIFY" : "UNCLASSIFY",
+		                 r->fast_classify ? "FAST" : "SLOW", (long)L, (long)r->n_hit, (long)r->n_anchor);
+		int rst_cnt = 0;
+		for (const dsb_hit *c = c_s; c < c_e; c++) if (c->pri_index == 0) put_hit(ob, c, ri, rst_cnt++);
+		for (const dsb_hit *c = c_s; c < c_e; c++)
+			if (c->pri_index > 0 && (o->fmt == FMT_DES_FULL || c->pri_index <= o->max_sec_N)) put_hit(ob, c, ri, rst_cnt++);
+		ob_need(ob, 2); ob->s[ob->n++] = '\n';
+		return;
+	}
+	const int full = o->fmt == FMT_SAM_FULL;                        /* output_one_result_sam, cly_mt.c:248-344 */
+	const size_t lsq = full ? L : 1;
+	ob_need(ob, ln + 2 * lsq + 400);
+	char *p = ob->s + ob->n;
+	#define PUT_SEQ_QUAL() do { if (full) { memcpy(p, seq, L); p += L; *p++ = '\t'; memcpy(p, qual, L); p += L; *p++ = '\t'; } else { memcpy(p, "*\t*\t", 4); p += 4; } } while (0)
+	if (r->n_hit == 0) {
+		p += sprintf(p, "%s\t4\t*\t0\t0\t*\t*\t0\t0\t", name);
+		PUT_SEQ_QUAL();
+		*p++ = '\n';
+		ob->n = p - ob->s;
+		return;
+	}
+	const int flag0 = c_s->direction ? 0 : 0x10;
+	int mapQ_PRI;
+	if (r->n_hit == 1 || (c_s->sum_score - c_s[1].sum_score > 5)) mapQ_PRI = 30;      /* unsigned compare, as in the reference */
+	else mapQ_PRI = (int)((c_s->sum_score - c_s[1].sum_score) << 2);
+	p += sprintf(p, "%s\t%d\t%s\t%d\t%d\t%dS%dM%dS\t*\t0\t0\t", name, flag0, ri[c_s->ref_ID].name, (int)c_s->t_st, mapQ_PRI,
+	             (int)c_s->q_st, (int)(c_s->q_ed - c_s->q_st), (int)(L - c_s->q_ed));
+	PUT_SEQ_QUAL();
+	p += sprintf(p, "AS:i:%d\t\n", (int)c_s->sum_score);
+	ob->n = p - ob->s;
+	for (int loop = 0; loop <= 1; loop++)
+		for (const dsb_hit *c = c_s + 1; c < c_e; c++) {
+			int show = 0, fl = c->direction ? 0 : 0x10, mapQ = 0;
+			if (loop == 0 && c->pri_index == 0) { show = 1; fl += 0x800; mapQ = mapQ_PRI < 30 ? mapQ_PRI : 30; }
+			else if (loop == 1 && c->pri_index > 0 && c->pri_index <= o->max_sec_N) { show = 1; fl += 0x100; }
+			if (!show) continue;
+			ob_need(ob, ln + 400);
+			ob->n += sprintf(ob->s + ob->n, "%s\t%d\t%s\t%d\t%d\t%d%c%dM%d%c\t*\t0\t0\t*\t*\tAS:i:%d\t\n", name, fl, ri[c->ref_ID].name, (int)c->t_st, mapQ,
+			                 (int)c->q_st, loop == 0 ? 'H' : 'S', (int)(c->q_ed - c->q_st), (int)(L - c->q_ed), loop == 0 ? 'H' : 'S', (int)c->sum_score);
+		}
+	#undef PUT_SEQ_QUAL
+}
+
+/* ---------------------------------------------------------------- main */
+static void usage(void)
+{
+	fprintf(stderr, "\nProgram:   deSAMBA-b200 (B200-native classify hot path of deSAMBA)\nVersion:   %s\n\n", dsb_version());
+	fprintf(stderr, "  Usage:     deSAMBA-b200  classify  [Options] <IndexDir> [ReadFiles.fq][...]>\n");
+	fprintf(stderr, "  Basic:   \n    <IndexDir>      FOLDER   the directory contains deSAMBA index\n    [ReadFiles.fq]  FILES    reads files, FASTQ(A) format, separated by space\n");
+	fprintf(stderr, "  Options:\n    -h,             help\n    -t, INT         accepted for compatibility, ignored [4]\n");
+	fprintf(stderr, "    -l, INT         minimum matching length, ignored for NGS reads [170]\n    -r, INT         max Output number of secondary alignments[5]\n");
+	fprintf(stderr, "    -o, FILE        output results into file [stdout]\n    -s, INT         MIN score[64]\n");
+	fprintf(stderr, "    -f, STR         output format, one of: SAM (default), SAM_FULL, DES, DES_FULL\n");
+	fprintf(stderr, "    -g, INT         number of GPUs [all visible]\n    -B, INT         reads per batch [65536]\n    -M, INT         Mbases per batch [64]\n\n");
+}
+
+static double now_s(void) { struct timeval t; gettimeofday(&t, NULL); return t.tv_sec + t.tv_usec * 1e-6; }
+static double cpu_s(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); return r.ru_utime.tv_sec + r.ru_stime.tv_sec + 1e-6 * (r.ru_utime.tv_usec + r.ru_stime.tv_usec); }
+
+static int classify_main(int argc, char **argv)
+{
+	opts_t o = {170, 4, 5, FMT_SAM, 64, 0, 65536, 64ull << 20, stdout};
+	int c;
+	while ((c = getopt(argc, argv, "ht:l:r:f:o:s:g:B:M:")) >= 0) {
+		if (c == 'h') { usage(); return 0; }
+		else if (c == 't') o.n_threads = atoi(optarg);
+		else if (c == 'l') o.l_min_match = atoi(optarg);
+		else if (c == 'r') o.max_sec_N = atoi(optarg);
+		else if (c == 'o') { o.out = fopen(optarg, "w"); if (!o.out) { fprintf(stderr, "[xopen] fail to open file '%s'\n", optarg); return 1; } }
+		else if (c == 's') o.min_score = atoi(optarg);
+		else if (c == 'g') o.n_gpus = atoi(optarg);
+		else if (c == 'B') o.batch_reads = (uint32_t)atol(optarg);
+		else if (c == 'M') o.batch_bases = (uint64_t)atol(optarg) << 20;
+		else if (c == 'f') {
+			if (!strcmp(optarg, "SAM")) o.fmt = FMT_SAM; else if (!strcmp(optarg, "SAM_FULL")) o.fmt = FMT_SAM_FULL;
+			else if (!strcmp(optarg, "DES")) o.fmt = FMT_DES; else if (!strcmp(optarg, "DES_FULL")) o.fmt = FMT_DES_FULL;
+		}
+	}
+	if (optind + 2 > argc) { usage(); return 0; }
+	if (o.batch_reads < 1) o.batch_reads = 1;
+	if (o.batch_bases < 1) o.batch_bases = 1;
+	const char *index_dir = argv[optind++];
+	if (o.n_gpus <= 0) { const char *e = getenv("DSB_GPUS"); o.n_gpus = e ? atoi(e) : 0; }
+	fprintf(stderr, "loading index\t");
+	worker_t *w = calloc(64, sizeof *w);
+	int n_gpus = 0;
+	for (int g = 0; g < (o.n_gpus > 0 ? o.n_gpus : 64); g++) {
+		dsb_index *ix = NULL;
+		int rc = dsb_index_load(index_dir, g, &ix);
+		if (rc != DSB_OK) {
+			if (g == 0 || o.n_gpus > 0) { fprintf(stderr, "\n[deSAMBA-b200] cannot load index on GPU %d: %s\n", g, dsb_last_error()); return 1; }
+			break;                                       /* ran out of visible devices */
+		}
+		w[g].gpu = g; w[g].ix = ix; n_gpus++;
+	}
+	dsb_opts dop; dsb_opts_default(&dop);
+	dop.l_min_match = o.l_min_match; dop.min_score = o.min_score;
+	for (int g = 0; g < n_gpus; g++)
+		if (dsb_ctx_create(w[g].ix, &dop, &w[g].ctx) != DSB_OK) { fprintf(stderr, "\n[deSAMBA-b200] %s\n", dsb_last_error()); return 1; }
+	const dsb_ref_info *ri = dsb_index_ref_info(w[0].ix);
+	const double t0 = now_s(), c0 = cpu_s();
+	fprintf(stderr, "Start classify\n");
+
+	shared_t sh; memset(&sh, 0, sizeof sh);
+	sh.o = &o; sh.n_slots = 2 * n_gpus + 2; sh.slot = calloc(sh.n_slots, sizeof(slot_t));
+	pthread_mutex_init(&sh.mu, NULL); pthread_cond_init(&sh.cv, NULL);
+	sh.n_files = argc - optind; sh.files = argv + optind;
+	pthread_t rd, th[64];
+	pthread_create(&rd, NULL, reader_main, &sh);
+	for (int g = 0; g < n_gpus; g++) { w[g].sh = &sh; pthread_create(&th[g], NULL, worker_main, &w[g]); }
+
+	obuf_t ob = {0};
+	for (;;) {
+		pthread_mutex_lock(&sh.mu);
+		slot_t *b = &sh.slot[sh.n_written % sh.n_slots];
+		while (!sh.error && !(b->state == SLOT_DONE && b->seq_no == sh.n_written) && !(sh.eof && sh.n_written == sh.n_filled)) pthread_cond_wait(&sh.cv, &sh.mu);
+		const int stop = sh.error || !(b->state == SLOT_DONE && b->seq_no == sh.n_written);
+		pthread_mutex_unlock(&sh.mu);
+		if (stop) break;
+		ob.n = 0;
+		for (uint32_t r = 0; r < b->n_reads; r++) {
+			const uint32_t L = (uint32_t)(b->offs[r + 1] - b->offs[r]);
+			format_read(&ob, &o, ri, b->rr + r, b->hits, b->names + b->name_off[r], b->seqs + b->offs[r], b->quals ? b->quals + b->offs[r] : NULL, L);
+			if (ob.n > (8u << 20)) { fwrite(ob.s, 1, ob.n, o.out); ob.n = 0; }
+		}
+		fwrite(ob.s, 1, ob.n, o.out);
+		pthread_mutex_lock(&sh.mu);
+		b->state = SLOT_FREE; sh.n_written++;
+		pthread_cond_broadcast(&sh.cv);
+		pthread_mutex_unlock(&sh.mu);
+	}
+	pthread_join(rd, NULL);
+	for (int g = 0; g < n_gpus; g++) pthread_join(th[g], NULL);
+	fflush(o.out);
+	if (o.out != stdout) fclose(o.out);
+	if (sh.error) { fprintf(stderr, "[deSAMBA-b200] error %d: %s\n", sh.error, sh.errmsg); return 1; }
+	const double sec = now_s() - t0;
+	fprintf(stderr, "%ld sequences processed in %.3fs (%.1f Kseq/m).\n", (long)sh.total_sequences, sec, sh.total_sequences / 1.0e3 / (sec / 60));   /* report_stats, cly_mt.c:439-446 */
+	fprintf(stderr, "Classify CPU: %.3f sec\n", cpu_s() - c0);
+	fprintf(stderr, "GPUs: %d\n", n_gpus);
+	for (int g = 0; g < n_gpus; g++) { dsb_ctx_free(w[g].ctx); dsb_index_free(w[g].ix); }
+	return 0;
+}
+
+int main(int argc, char **argv)
+{
+	if (argc >= 2 && !strcmp(argv[1], "classify")) return classify_main(argc - 1, argv + 1);
+	if (argc >= 2 && (!strcmp(argv[1], "-h") || !strcmp(argv[1], "--help"))) { usage(); return 0; }
+	fprintf(stderr, "deSAMBA-b200: only the `classify` command is implemented here (index construction and analysis stay with the reference)\n");
+	usage();
+	return 1;
+}

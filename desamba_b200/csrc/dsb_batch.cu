@@ -1,0 +1,635 @@
+// dsb_batch.cu -- the batch pipeline behind dsb_classify_batch():
+//   K0 k_encode_probe : ASCII -> 2-bit codes of both strands; every l_ek-mer of the read (both strands) is hashed and
+//                       probed in the two exist-k-mer bit tables (get_exist_kmer, cly.c:956-972) -> membership bit-vectors
+//   K1 k_islands      : replays the reference's island scan + top labelling on the bit-vectors (cly.c:1071-1234) -> seeds
+//   K2 k_classify     : warp per read: FM-index seeding, anchors, chaining, 9-mer sparse-DP scoring (dsb_classify.cuh)
+//   K3 k_finalize     : class filter (needs the running max_read_l of the input order), final sort, primary detection
+// One CUDA stream per context, no host synchronisation between the kernels.
+#include "dsb_internal.h"
+#include "dsb_classify.cuh"
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+
+#define PROBE_TILE 1024
+#define PROBE_THREADS 256
+#define N_BITVEC 5                 // E_fwd, E_rev, T0_fwd, T0_rev, Z (k-mer not masked as low-complexity)
+#define CLASSIFY_WARPS_PER_BLOCK 4
+
+static inline uint32_t bits_words(uint32_t len) { return (len + 31) / 32 + 1; }
+static inline uint32_t seed_slots(uint32_t len) { return len / 2 + 2; }
+
+// ------------------------------------------------------------------------------------------------ K0
+struct ProbeParams {
+	DevIndex ix;
+	const char *seqs; const uint64_t *read_off, *bin_off, *bits_off;
+	const uint2 *tiles;
+	uint8_t *bin; uint32_t *bits;
+};
+
+__device__ __forceinline__ uint32_t cly_bit(char ch)      // CLY_Bit, cly.c:17-35: A0 C1 G2 T3 (either case), everything else 1
+{
+	switch (ch) { case 'A': case 'a': return 0; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 1; }
+}
+
+__device__ __forceinline__ uint64_t revcomp_kmer(uint64_t km, int l)
+{
+	uint64_t x = __brevll(~km);
+	x = ((x & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((x & 0x5555555555555555ull) << 1);
+	return x >> (64 - 2 * l);
+}
+
+__global__ void __launch_bounds__(PROBE_THREADS) k_encode_probe(const __grid_constant__ ProbeParams P)
+{
+	__shared__ uint8_t s_code[PROBE_TILE + 32];
+	const uint2 tile = P.tiles[blockIdx.x];
+	const uint32_t r = tile.x, start = tile.y;
+	const uint64_t off = P.read_off[r];
+	const uint32_t len = (uint32_t)(P.read_off[r + 1] - off);
+	const int l_ek = P.ix.l_ek;
+	const uint32_t n_kmer = len - l_ek + 1;
+	uint8_t *bin_F = P.bin + P.bin_off[r] + DSB_GUARD, *bin_R = bin_F + len;
+	const uint32_t nb = min((uint32_t)(PROBE_TILE + l_ek - 1), len - start);
+	const int tid = threadIdx.x;
+	for (uint32_t k = tid; k < nb; k += PROBE_THREADS) {
+		const uint32_t code = cly_bit(P.seqs[off + start + k]);
+		s_code[k] = (uint8_t)code;
+		if (k < PROBE_TILE) { bin_F[start + k] = (uint8_t)code; bin_R[len - 1 - (start + k)] = (uint8_t)(3 - code); }   // cly.c:1250-1259
+	}
+	if (start == 0 && tid < DSB_GUARD) { bin_F[tid - DSB_GUARD] = 0; bin_R[len + tid] = 0; }      // out-of-buffer policy P3
+	__syncthreads();
+	const uint32_t W = (len + 31) / 32 + 1;
+	uint32_t *bits = P.bits + P.bits_off[r];
+	const int sbm = P.ix.single_base_max;
+	const uint64_t mask = P.ix.ek_mask;
+	#pragma unroll
+	for (int it = 0; it < PROBE_TILE / PROBE_THREADS; it++) {
+		const uint32_t p = it * PROBE_THREADS + tid, i = start + p;
+		const bool valid = i < n_kmer;
+		uint64_t km = 0; uint32_t cnt = 0;
+		if (valid)
+			for (int b = 0; b < l_ek; b++) { const uint32_t c = s_code[p + b]; km = (km << 2) | c; cnt += 1u << (c * 8); }
+		// store_kmers (cly.c:360-398): a k-mer with any base count >= single_base_max is stored as 0 and never exists
+		const bool ok = valid && (int)(cnt & 0xff) < sbm && (int)((cnt >> 8) & 0xff) < sbm && (int)((cnt >> 16) & 0xff) < sbm && (int)(cnt >> 24) < sbm;
+		const uint64_t kr = revcomp_kmer(km, l_ek);
+		uint32_t t0f = 0, t0r = 0, ef = 0, er = 0;
+		if (ok) {
+			const uint64_t hf = dsb_hash64_1(km) & mask, hr = dsb_hash64_1(kr) & mask;
+			const uint32_t bf = __ldg(P.ix.ek0 + (hf >> 3)), br = __ldg(P.ix.ek0 + (hr >> 3));
+			t0f = (bf >> (7 - (hf & 7))) & 1; t0r = (br >> (7 - (hr & 7))) & 1;
+			if (t0f) { const uint64_t h2 = dsb_hash64_2(km) & mask; ef = (__ldg(P.ix.ek1 + (h2 >> 3)) >> (7 - (h2 & 7))) & 1; }
+			if (t0r) { const uint64_t h2 = dsb_hash64_2(kr) & mask; er = (__ldg(P.ix.ek1 + (h2 >> 3)) >> (7 - (h2 & 7))) & 1; }
+		}
+		const uint32_t m_ef = __ballot_sync(DSB_FULL, ef), m_er = __ballot_sync(DSB_FULL, er);
+		const uint32_t m_t0f = __ballot_sync(DSB_FULL, t0f), m_t0r = __ballot_sync(DSB_FULL, t0r), m_z = __ballot_sync(DSB_FULL, ok);
+		const uint32_t w = i >> 5;                     // start and p are multiples of 32 per warp
+		if ((tid & 31) == 0 && w < W) {
+			bits[w] = m_ef; bits[W + w] = m_er; bits[2 * W + w] = m_t0f; bits[3 * W + w] = m_t0r; bits[4 * W + w] = m_z;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+struct IslandParams {
+	int l_ek; uint32_t n_reads;
+	const uint64_t *read_off, *bits_off; const uint32_t *seed_off;
+	const uint32_t *bits;
+	dsb_seed *seeds[2]; uint32_t *n_seeds[2]; uint32_t *total_score[2];
+	unsigned long long *counters;
+};
+
+__device__ __forceinline__ uint32_t bit_at(const uint32_t *v, uint32_t i) { return (__ldg(v + (i >> 5)) >> (i & 31)) & 1; }
+
+// search_exist_kmer_M2 + get_seed_vector_M2 (cly.c:1071-1234).  Both strands run the SAME scan on a bit-vector indexed
+// by forward k-mer position: the reference's right-to-left scan of the reverse strand is the mirror image of its
+// left-to-right scan of the forward strand; only the reported offset is mirrored back.
+__global__ void __launch_bounds__(128) k_islands(const __grid_constant__ IslandParams P)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t r = t >> 1, s = t & 1;
+	uint32_t calls_nz = 0, calls_t0 = 0;
+	if (r < P.n_reads) {
+		const uint32_t len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
+		uint32_t n_seed = 0, total = 0;
+		if (len >= 40) {
+			const uint32_t n = len - P.l_ek + 1, W = (len + 31) / 32 + 1;
+			const uint32_t *E = P.bits + P.bits_off[r] + s * W, *T0 = E + 2 * W, *Z = P.bits + P.bits_off[r] + 4 * W;
+			dsb_seed *out = P.seeds[s] + P.seed_off[r];
+			uint32_t max_index = 0, max_length = 0, index_end = 100;
+			#define PROBE(idx) (calls_nz += bit_at(Z, (idx)), calls_t0 += bit_at(T0, (idx)), bit_at(E, (idx)))
+			for (uint32_t i = 2; i < n; i += 3) {
+				if (!PROBE(i)) continue;
+				uint32_t offset = i, l = 1;
+				for (int j = 1; j < 3; ++j) { if (PROBE(i - j)) { offset--; l++; } else break; }
+				for (uint32_t j = 1; i + j < n; ++j) { if (PROBE(i + j)) { l++; if (l > 60) break; } else break; }
+				dsb_seed sd; sd.offset = s ? (n - offset - l) : offset; sd.len = (uint16_t)l; sd.top = 0; sd.pad = 0;
+				out[n_seed] = sd;
+				// top labelling (cly.c:1174-1226); the window position is the mirrored offset for the reverse strand
+				if (offset < index_end) { if (max_length < l) { max_length = l; max_index = n_seed; } }
+				else { out[max_index].top = 1; index_end += 100; total += max_length; max_index = n_seed; max_length = l; }
+				n_seed++;
+				i = offset + l;
+			}
+			#undef PROBE
+			if (n_seed) out[max_index].top = 1;
+			total += max_length;
+		}
+		P.n_seeds[s][r] = n_seed; P.total_score[s][r] = total;
+	}
+	for (int d = 16; d; d >>= 1) { calls_nz += __shfl_xor_sync(DSB_FULL, calls_nz, d); calls_t0 += __shfl_xor_sync(DSB_FULL, calls_t0, d); }
+	if ((threadIdx.x & 31) == 0 && (calls_nz | calls_t0)) {
+		atomicAdd(P.counters + DSB_CNT_N_BIT0, (unsigned long long)calls_nz);
+		atomicAdd(P.counters + DSB_CNT_N_BIT1, (unsigned long long)calls_t0);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+struct ScratchLayout { uint64_t anc, anc_tmp, chain, chain_tmp, sms, score_v, mem_rst, sc_hash, kstart[2], kent[2], total; };
+static ScratchLayout scratch_layout(uint32_t max_anchors, uint32_t max_matches, uint32_t kidx_bits, uint32_t kidx_len)
+{
+	ScratchLayout L; uint64_t o = 0;
+	auto take = [&](uint64_t bytes) { uint64_t at = o; o += (bytes + 127) & ~127ull; return at; };
+	L.anc = take((uint64_t)max_anchors * sizeof(DevAnchor)); L.anc_tmp = take((uint64_t)max_anchors * sizeof(DevAnchor));
+	L.chain = take((uint64_t)max_anchors * sizeof(DevChain)); L.chain_tmp = take((uint64_t)max_anchors * sizeof(DevChain));
+	L.sms = take((uint64_t)max_matches * sizeof(DevSms));
+	L.score_v = take(1024 * sizeof(int));
+	L.mem_rst = take(512 * sizeof(MemRst));
+	L.sc_hash = take((256 + 2 * 400 + 8) * sizeof(ScHash));
+	for (int s = 0; s < 2; s++) { L.kstart[s] = take(((uint64_t)1 << kidx_bits) * 4 + 128); L.kent[s] = take((uint64_t)kidx_len * sizeof(KEntry) + 128); }
+	L.total = o;
+	return L;
+}
+
+struct ClassifyLaunch { ClassifyParams P; ScratchLayout L; unsigned long long *counters; };
+
+__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_classify(const __grid_constant__ ClassifyLaunch A)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	const int warp = threadIdx.x >> 5;
+	const uint32_t gw = blockIdx.x * CLASSIFY_WARPS_PER_BLOCK + warp;
+	ReadState S;
+	S.ix = &A.P.ix;
+	S.sm = (WarpSmem *)smem_raw + warp;
+	uint8_t *base = A.P.scratch + (uint64_t)gw * A.P.scratch_stride;
+	S.ws.anc = (DevAnchor *)(base + A.L.anc); S.ws.anc_tmp = (DevAnchor *)(base + A.L.anc_tmp);
+	S.ws.chain = (DevChain *)(base + A.L.chain); S.ws.chain_tmp = (DevChain *)(base + A.L.chain_tmp);
+	S.ws.sms = (DevSms *)(base + A.L.sms); S.ws.score_v = (int *)(base + A.L.score_v);
+	S.ws.mem_rst = (MemRst *)(base + A.L.mem_rst); S.ws.sc_hash = (ScHash *)(base + A.L.sc_hash);
+	for (int s = 0; s < 2; s++) { S.ws.kidx_start[s] = (uint32_t *)(base + A.L.kstart[s]); S.ws.kidx_ent[s] = (KEntry *)(base + A.L.kent[s]); }
+	S.max_anchors = A.P.max_anchors; S.max_matches = A.P.max_matches;
+	for (;;) {
+		uint32_t r = 0;
+		if (lane_id() == 0) r = atomicAdd(A.P.work_counter, 1u);
+		r = __shfl_sync(DSB_FULL, r, 0);
+		if (r >= A.P.n_reads) break;
+		classify_read(A.P, S, r);
+		if (lane_id() == 0) {
+			unsigned long long *C = A.counters;
+			const dsb_read_result rr = A.P.rr[r];
+			if (rr.entered_final) {                       // Classify_buff_pool.max_read_l bookkeeping (cly.c:2958), resolved in K3
+				atomicMax(C + DSB_CNT_MAX_READ_L, (unsigned long long)rr.read_len);
+				if (rr.read_len >= 510) atomicMin(C + DSB_CNT_FIRST_LONG, (unsigned long long)r);
+			}
+			if (rr.error) atomicAdd(C + DSB_CNT_N_ERRORS, 1ull);
+			atomicAdd(C + DSB_CNT_N_PREFIX, (unsigned long long)S.c_prefix);
+			atomicAdd(C + DSB_CNT_N_OCC, (unsigned long long)S.c_occ);
+			atomicAdd(C + DSB_CNT_N_LOCATE, (unsigned long long)S.c_locate);
+			atomicAdd(C + DSB_CNT_N_GETREF, (unsigned long long)S.c_getref);
+			atomicAdd(C + DSB_CNT_N_GETREF_BYTES, (unsigned long long)S.c_getref_bytes);
+		}
+		__syncwarp();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+struct FinalizeParams {
+	uint32_t n_reads; int32_t max_read_l_in;
+	int filter_min_length, filter_min_score, filter_min_score_LV3;
+	dsb_read_result *rr; dsb_hit *hits;
+	const unsigned long long *counters;
+};
+
+struct HitCmpByMEMScore {           // chain_cmp_by_MEM_score (cly.c:54-64): asymmetric on ties, as written
+	__device__ int operator()(const dsb_hit &a, const dsb_hit &b) const {
+		const int score_a = (a.sum_score << 5), score_b = (b.sum_score << 5);
+		if (score_a < score_b) return 1;
+		if (score_a > score_b) return -1;
+		return (a.sum_score % 2);
+	}
+};
+
+#define FILTER_MIN_SCORE_SHROT_3G_READ 30
+#define FILTER_MIN_SCORE_2G_READ 26
+// tail of delete_small_score_rst (cly.c:2958-2993) + detect_primary (cly.c:2995-3058); one thread per read
+__global__ void __launch_bounds__(128) k_finalize(const __grid_constant__ FinalizeParams P)
+{
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= P.n_reads) return;
+	dsb_read_result rr = P.rr[r];
+	uint32_t n = rr.n_hit;
+	if (n == 0) return;
+	dsb_hit *hit = P.hits + rr.hit_off, *tmp = hit + n;
+	const uint32_t l_read = rr.read_len;
+	// buff->max_read_l after this read (input order, -t 1 semantics): < 510 iff nothing >= 510 entered before or at r
+	const bool max_small = P.max_read_l_in < 510 && (unsigned long long)r < P.counters[DSB_CNT_FIRST_LONG];
+	for (uint32_t i = 0; i < n; i++) {
+		dsb_hit c = hit[i];
+		const int score = c.sum_score + ((c.q_ed - c.q_st) >> 5);
+		bool kill;
+		if (max_small) kill = score < FILTER_MIN_SCORE_2G_READ;
+		else if (l_read < 310) kill = score < FILTER_MIN_SCORE_SHROT_3G_READ;
+		else kill = score < (P.filter_min_score_LV3) && (c.q_ed - c.q_st < P.filter_min_length || score < P.filter_min_score);
+		if (kill) { c.sum_score = 0; hit[i] = c; }
+	}
+	if (n > 1) glibc_msort(hit, tmp, (int)n, HitCmpByMEMScore());
+	uint32_t k = 0;
+	for (; k < n; k++) if (hit[k].sum_score == 0) break;
+	n = k;
+	rr.n_hit = n;
+	P.rr[r] = rr;
+	if (n == 0) return;
+	// detect_primary
+	int primary_v[400]; uint8_t primary_v_idx[400];      // n <= 400 (cly.c:2897), so the reference's 750 cap is never reached
+	int n_primary_v = 1;
+	primary_v[0] = 0; primary_v_idx[0] = 0;
+	for (uint32_t i = 0; i < n; i++) if (hit[i].q_st > 4294960000u) hit[i].q_st = 0;
+	{ dsb_hit h = hit[0]; h.pri_index = 0; h.primary = 1; hit[0] = h; }
+	for (uint32_t ci = 1; ci < n; ci++) {
+		dsb_hit c_hit = hit[ci];
+		int overlap = 0;
+		for (int i = 0; i < n_primary_v; i++) {
+			const dsb_hit ph = hit[primary_v[i]];
+			int primary_st, primary_ed;
+			if (ph.direction == c_hit.direction) { primary_st = ph.q_st; primary_ed = ph.q_ed; }
+			else { primary_st = l_read - ph.q_ed; primary_ed = l_read - ph.q_st; }
+			const uint32_t overlap_st = DSB_MAX(c_hit.q_st, primary_st);
+			const uint32_t overlap_ed = DSB_MIN(c_hit.q_ed, primary_ed);
+			if ((overlap_st < overlap_ed) && (((overlap_ed - overlap_st) << 1) >= (c_hit.q_ed - c_hit.q_st))) overlap = 1;
+			if (overlap) {
+				c_hit.primary = 2;
+				c_hit.pri_index = ++primary_v_idx[i];
+				const int max_gap = DSB_MAX((ph.sum_score >> 6), 5);
+				if (c_hit.sum_score + max_gap > ph.sum_score) c_hit.pri_index = 1;
+				if (primary_v_idx[i] == 255) primary_v_idx[i] = 254;
+				break;
+			}
+		}
+		if (overlap == 0) {
+			c_hit.primary = 3;
+			c_hit.pri_index = primary_v_idx[n_primary_v] = 0;
+			primary_v[n_primary_v++] = ci;
+		}
+		hit[ci] = c_hit;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int ensure(DevBuf &b, size_t bytes)
+{
+	if (bytes <= b.cap) return DSB_OK;
+	if (b.p) cudaFree(b.p);
+	b.p = nullptr; b.cap = 0;
+	const size_t want = bytes + bytes / 4 + 256;
+	DSB_CUDA(cudaMalloc(&b.p, want));
+	b.cap = want;
+	return DSB_OK;
+}
+
+extern "C" void dsb_opts_default(dsb_opts *o)
+{
+	if (!o) return;
+	o->l_min_match = 170; o->min_score = 64;               // cly_mt.c:486
+	o->max_anchors = 16384; o->max_matches = 16384; o->max_read_len = 1u << 20; o->warps_per_sm = 16;
+}
+
+extern "C" int dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out)
+{
+	if (!ix || !out) { dsb_set_error("dsb_ctx_create: null argument"); return DSB_E_ARG; }
+	*out = nullptr;
+	DSB_CUDA(cudaSetDevice(ix->device));
+	dsb_ctx *c = new dsb_ctx();
+	c->ix = ix;
+	if (o) c->opts = *o; else dsb_opts_default(&c->opts);
+	if (c->opts.max_anchors < 1024) c->opts.max_anchors = 1024;
+	if (c->opts.max_matches < 1024) c->opts.max_matches = 1024;
+	if (c->opts.warps_per_sm < CLASSIFY_WARPS_PER_BLOCK) c->opts.warps_per_sm = CLASSIFY_WARPS_PER_BLOCK;
+	if (c->opts.warps_per_sm > 32) c->opts.warps_per_sm = 32;
+	c->stream = nullptr; c->h_pin = nullptr; c->h_pin_cap = 0; c->ran = false; c->launches = 0;
+	c->n_reads = 0; c->scratch_stride = 0; c->kidx_bits = 0; c->kidx_len = 0; c->hits_cap = 0;
+	memset(c->kernel_ms, 0, sizeof c->kernel_ms);
+	cudaDeviceProp prop;
+	DSB_CUDA(cudaGetDeviceProperties(&prop, ix->device));
+	c->n_sm = prop.multiProcessorCount;
+	c->n_warps = c->n_sm * (int)(c->opts.warps_per_sm / CLASSIFY_WARPS_PER_BLOCK) * CLASSIFY_WARPS_PER_BLOCK;
+	DSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 6; i++) DSB_CUDA(cudaEventCreate(&c->ev[i]));
+	DSB_CUDA(cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CLASSIFY_WARPS_PER_BLOCK * sizeof(WarpSmem))));
+	int rc = ensure(c->counters, DSB_CNT_COUNT * 8);
+	if (rc != DSB_OK) { dsb_ctx_free(c); return rc; }
+	*out = c;
+	return DSB_OK;
+}
+
+extern "C" void dsb_ctx_free(dsb_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->ix->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	DevBuf *bufs[] = {&c->seqs, &c->read_off, &c->bin_off, &c->bits_off, &c->seed_off, &c->tiles, &c->bin, &c->bits, &c->seeds[0], &c->seeds[1],
+	                  &c->n_seeds[0], &c->n_seeds[1], &c->total_score[0], &c->total_score[1], &c->scratch, &c->rr, &c->hits, &c->counters};
+	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+	if (c->h_pin) cudaFreeHost(c->h_pin);
+	for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" void *dsb_ctx_stream(dsb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+extern "C" int dsb_host_alloc(size_t bytes, void **out)
+{
+	if (!out) return DSB_E_ARG;
+	DSB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+	return DSB_OK;
+}
+extern "C" void dsb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *offs, uint32_t n_reads)
+{
+	if (!c || (n_reads && (!seqs || !offs))) { dsb_set_error("dsb_batch_upload: null argument"); return DSB_E_ARG; }
+	DSB_CUDA(cudaSetDevice(c->ix->device));
+	c->ran = false;
+	c->n_reads = n_reads;
+	if (n_reads == 0) { c->n_tiles = 0; c->n_bases = 0; return DSB_OK; }
+	const uint64_t n_bases = offs[n_reads] - offs[0];
+	if (offs[0] != 0) { dsb_set_error("dsb_batch_upload: offs[0] must be 0"); return DSB_E_ARG; }
+	// per-read layout tables (host): bin / bit-vector / seed-slot offsets and the probe tile list
+	const size_t tbl_bytes = (size_t)(n_reads + 1) * 8;
+	uint64_t n_tiles = 0; uint32_t max_len = 0;
+	for (uint32_t r = 0; r < n_reads; r++) {
+		if (offs[r + 1] < offs[r] || offs[r + 1] - offs[r] > c->opts.max_read_len) { dsb_set_error("read %u: bad offsets or longer than max_read_len %u", r, c->opts.max_read_len); return DSB_E_ARG; }
+		const uint32_t len = (uint32_t)(offs[r + 1] - offs[r]);
+		if (len >= 40) n_tiles += (len + PROBE_TILE - 1) / PROBE_TILE;
+		max_len = std::max(max_len, len);
+	}
+	const size_t pin_need = tbl_bytes * 3 + (size_t)(n_reads + 1) * 4 + n_tiles * 8 + 64;
+	if (pin_need > c->h_pin_cap) {
+		if (c->h_pin) cudaFreeHost(c->h_pin);
+		c->h_pin = nullptr; c->h_pin_cap = 0;
+		DSB_CUDA(cudaHostAlloc(&c->h_pin, pin_need + pin_need / 4, cudaHostAllocDefault));
+		c->h_pin_cap = pin_need + pin_need / 4;
+	}
+	uint64_t *h_bin_off = (uint64_t *)c->h_pin, *h_bits_off = h_bin_off + n_reads + 1, *h_tiles64 = h_bits_off + n_reads + 1;
+	uint2 *h_tiles = (uint2 *)h_tiles64;
+	uint32_t *h_seed_off = (uint32_t *)(h_tiles64 + n_tiles);
+	uint64_t bo = 0, wo = 0, so = 0, ti = 0;
+	for (uint32_t r = 0; r < n_reads; r++) {
+		const uint32_t len = (uint32_t)(offs[r + 1] - offs[r]);
+		h_bin_off[r] = bo; h_bits_off[r] = wo; h_seed_off[r] = (uint32_t)so;
+		if (len >= 40) {
+			bo += ((uint64_t)2 * len + 2 * DSB_GUARD + 15) & ~15ull;
+			wo += (uint64_t)N_BITVEC * bits_words(len);
+			so += seed_slots(len);
+			for (uint32_t st = 0; st < len; st += PROBE_TILE) { h_tiles[ti].x = r; h_tiles[ti].y = st; ti++; }
+		}
+	}
+	h_bin_off[n_reads] = bo; h_bits_off[n_reads] = wo; h_seed_off[n_reads] = (uint32_t)so;
+	if (so >= 0xffffffffull) { dsb_set_error("batch too large (seed slots overflow 32 bits): split the batch"); return DSB_E_ARG; }
+	c->n_tiles = (uint32_t)n_tiles; c->n_bases = n_bases; c->bits_words = wo; c->seed_slots = so; c->bin_bytes = bo; c->max_len = max_len;
+	c->h_bits_off.assign(h_bits_off, h_bits_off + n_reads + 1);
+	c->h_seed_off.assign(h_seed_off, h_seed_off + n_reads + 1);
+	c->h_off.assign(offs, offs + n_reads + 1);
+	int rc;
+	if ((rc = ensure(c->seqs, n_bases + 16)) || (rc = ensure(c->read_off, tbl_bytes)) || (rc = ensure(c->bin_off, tbl_bytes)) ||
+	    (rc = ensure(c->bits_off, tbl_bytes)) || (rc = ensure(c->seed_off, (size_t)(n_reads + 1) * 4)) || (rc = ensure(c->tiles, n_tiles * 8 + 8)) ||
+	    (rc = ensure(c->bin, bo + 64)) || (rc = ensure(c->bits, wo * 4 + 64)) ||
+	    (rc = ensure(c->seeds[0], so * sizeof(dsb_seed) + 64)) || (rc = ensure(c->seeds[1], so * sizeof(dsb_seed) + 64)) ||
+	    (rc = ensure(c->n_seeds[0], (size_t)n_reads * 4)) || (rc = ensure(c->n_seeds[1], (size_t)n_reads * 4)) ||
+	    (rc = ensure(c->total_score[0], (size_t)n_reads * 4)) || (rc = ensure(c->total_score[1], (size_t)n_reads * 4)) ||
+	    (rc = ensure(c->rr, (size_t)n_reads * sizeof(dsb_read_result))))
+		return rc;
+	cudaStream_t st = c->stream;
+	DSB_CUDA(cudaMemcpyAsync(c->seqs.p, seqs, n_bases, cudaMemcpyHostToDevice, st));
+	DSB_CUDA(cudaMemcpyAsync(c->read_off.p, offs, tbl_bytes, cudaMemcpyHostToDevice, st));
+	DSB_CUDA(cudaMemcpyAsync(c->bin_off.p, h_bin_off, tbl_bytes, cudaMemcpyHostToDevice, st));
+	DSB_CUDA(cudaMemcpyAsync(c->bits_off.p, h_bits_off, tbl_bytes, cudaMemcpyHostToDevice, st));
+	DSB_CUDA(cudaMemcpyAsync(c->seed_off.p, h_seed_off, (size_t)(n_reads + 1) * 4, cudaMemcpyHostToDevice, st));
+	if (n_tiles) DSB_CUDA(cudaMemcpyAsync(c->tiles.p, h_tiles, n_tiles * 8, cudaMemcpyHostToDevice, st));
+	return DSB_OK;
+}
+
+extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
+{
+	if (!c) return DSB_E_ARG;
+	DSB_CUDA(cudaSetDevice(c->ix->device));
+	cudaStream_t st = c->stream;
+	c->launches = 0;
+	const uint32_t n = c->n_reads;
+	if (n == 0) { c->ran = true; return DSB_OK; }
+	// classify scratch: sized by the batch's longest read (the read's 9-mer index is the large part)
+	uint32_t kb = 10; for (; kb < 18; kb++) if ((1u << kb) >= c->max_len) break;          // hash_size[key_len] >= q_len (cly.c:2196-2198)
+	if (kb > c->kidx_bits || c->max_len + 64 > c->kidx_len || c->scratch_stride == 0) {
+		c->kidx_bits = std::max(c->kidx_bits, kb); c->kidx_len = std::max(c->kidx_len, c->max_len + 64);
+	}
+	const ScratchLayout L = scratch_layout(c->opts.max_anchors, c->opts.max_matches, c->kidx_bits, c->kidx_len);
+	c->scratch_stride = L.total;
+	int rc;
+	if ((rc = ensure(c->scratch, (size_t)L.total * c->n_warps)) != DSB_OK) return rc;
+	// hits: the pre-filter chains of a read use 2 slots each (second half = merge-sort scratch)
+	const uint64_t hits_cap = std::max<uint64_t>(4096, (uint64_t)n * 24);
+	if ((rc = ensure(c->hits, hits_cap * sizeof(dsb_hit))) != DSB_OK) return rc;
+	c->hits_cap = c->hits.cap / sizeof(dsb_hit);
+	unsigned long long *cnt = (unsigned long long *)c->counters.p;
+	DSB_CUDA(cudaMemsetAsync(cnt, 0, DSB_CNT_COUNT * 8, st));
+	DSB_CUDA(cudaMemsetAsync(cnt + DSB_CNT_FIRST_LONG, 0xff, 8, st));
+	DSB_CUDA(cudaEventRecord(c->ev[0], st));
+	if (c->n_tiles) {
+		ProbeParams P;
+		P.ix = c->ix->dev; P.seqs = (const char *)c->seqs.p; P.read_off = (const uint64_t *)c->read_off.p; P.bin_off = (const uint64_t *)c->bin_off.p;
+		P.bits_off = (const uint64_t *)c->bits_off.p; P.tiles = (const uint2 *)c->tiles.p; P.bin = (uint8_t *)c->bin.p; P.bits = (uint32_t *)c->bits.p;
+		k_encode_probe<<<c->n_tiles, PROBE_THREADS, 0, st>>>(P);
+		c->launches++;
+	}
+	DSB_CUDA(cudaEventRecord(c->ev[1], st));
+	{
+		IslandParams P;
+		P.l_ek = c->ix->dev.l_ek; P.n_reads = n; P.read_off = (const uint64_t *)c->read_off.p; P.bits_off = (const uint64_t *)c->bits_off.p;
+		P.seed_off = (const uint32_t *)c->seed_off.p; P.bits = (const uint32_t *)c->bits.p;
+		for (int s = 0; s < 2; s++) { P.seeds[s] = (dsb_seed *)c->seeds[s].p; P.n_seeds[s] = (uint32_t *)c->n_seeds[s].p; P.total_score[s] = (uint32_t *)c->total_score[s].p; }
+		P.counters = cnt;
+		k_islands<<<(2 * n + 127) / 128, 128, 0, st>>>(P);
+		c->launches++;
+	}
+	DSB_CUDA(cudaEventRecord(c->ev[2], st));
+	{
+		ClassifyLaunch A;
+		ClassifyParams &P = A.P;
+		P.ix = c->ix->dev; P.n_reads = n; P.read_off = (const uint64_t *)c->read_off.p; P.bin_off = (const uint64_t *)c->bin_off.p; P.bin = (const uint8_t *)c->bin.p;
+		P.seed_off = (const uint32_t *)c->seed_off.p;
+		for (int s = 0; s < 2; s++) { P.seeds[s] = (const dsb_seed *)c->seeds[s].p; P.n_seeds[s] = (const uint32_t *)c->n_seeds[s].p; P.total_score[s] = (const uint32_t *)c->total_score[s].p; }
+		P.work_counter = (uint32_t *)(cnt + DSB_CNT_WORK);
+		P.scratch = (uint8_t *)c->scratch.p; P.scratch_stride = L.total;
+		P.max_anchors = c->opts.max_anchors; P.max_matches = c->opts.max_matches; P.kidx_bits_max = c->kidx_bits; P.kidx_len_max = c->kidx_len;
+		P.rr = (dsb_read_result *)c->rr.p; P.hits = (dsb_hit *)c->hits.p; P.hits_cap = c->hits_cap; P.hits_cursor = cnt + DSB_CNT_HITS_CURSOR;
+		A.L = L; A.counters = cnt;
+		const int blocks = c->n_warps / CLASSIFY_WARPS_PER_BLOCK;
+		k_classify<<<blocks, CLASSIFY_WARPS_PER_BLOCK * 32, CLASSIFY_WARPS_PER_BLOCK * sizeof(WarpSmem), st>>>(A);
+		c->launches++;
+	}
+	DSB_CUDA(cudaEventRecord(c->ev[3], st));
+	{
+		FinalizeParams P;
+		P.n_reads = n; P.max_read_l_in = max_read_l_in;
+		P.filter_min_length = c->opts.l_min_match; P.filter_min_score = c->opts.min_score; P.filter_min_score_LV3 = c->opts.min_score + 10;   // cly_mt.c:521-523
+		P.rr = (dsb_read_result *)c->rr.p; P.hits = (dsb_hit *)c->hits.p; P.counters = cnt;
+		k_finalize<<<(n + 127) / 128, 128, 0, st>>>(P);
+		c->launches++;
+	}
+	DSB_CUDA(cudaEventRecord(c->ev[4], st));
+	DSB_CUDA(cudaGetLastError());
+	c->ran = true;
+	return DSB_OK;
+}
+
+extern "C" int dsb_batch_sync(dsb_ctx *c)
+{
+	if (!c) return DSB_E_ARG;
+	DSB_CUDA(cudaSetDevice(c->ix->device));
+	DSB_CUDA(cudaStreamSynchronize(c->stream));
+	return DSB_OK;
+}
+
+extern "C" int dsb_batch_download(dsb_ctx *c, int32_t *max_read_l_out, dsb_read_result *rr, dsb_hit *hits, uint64_t hits_cap, uint64_t *n_hits_out)
+{
+	if (!c || !c->ran) { dsb_set_error("dsb_batch_download: no batch has been run"); return DSB_E_ARG; }
+	DSB_CUDA(cudaSetDevice(c->ix->device));
+	if (n_hits_out) *n_hits_out = 0;
+	if (c->n_reads == 0) return DSB_OK;
+	cudaStream_t st = c->stream;
+	unsigned long long h_cnt[DSB_CNT_COUNT];
+	DSB_CUDA(cudaMemcpyAsync(h_cnt, c->counters.p, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+	if (rr) DSB_CUDA(cudaMemcpyAsync(rr, c->rr.p, (size_t)c->n_reads * sizeof(dsb_read_result), cudaMemcpyDeviceToHost, st));
+	DSB_CUDA(cudaStreamSynchronize(st));
+	const uint64_t used = std::min<uint64_t>(h_cnt[DSB_CNT_HITS_CURSOR], c->hits_cap);
+	if (n_hits_out) *n_hits_out = used;
+	if (max_read_l_out) *max_read_l_out = (int32_t)h_cnt[DSB_CNT_MAX_READ_L];
+	if (hits && used) {
+		if (used > hits_cap) { dsb_set_error("hits array too small: %llu needed, %llu given", (unsigned long long)used, (unsigned long long)hits_cap); return DSB_E_CAPACITY; }
+		DSB_CUDA(cudaMemcpyAsync(hits, c->hits.p, used * sizeof(dsb_hit), cudaMemcpyDeviceToHost, st));
+		DSB_CUDA(cudaStreamSynchronize(st));
+	}
+	if (h_cnt[DSB_CNT_N_ERRORS]) {
+		dsb_set_error("%llu read(s) exceeded a per-read capacity (dsb_read_result.error): raise dsb_opts.max_anchors / max_matches", h_cnt[DSB_CNT_N_ERRORS]);
+		return DSB_E_CAPACITY;
+	}
+	return DSB_OK;
+}
+
+extern "C" int dsb_classify_batch(dsb_ctx *c, const char *seqs, const uint64_t *offs, uint32_t n_reads, int32_t max_read_l_in, int32_t *max_read_l_out,
+                                  dsb_read_result *rr, dsb_hit *hits, uint64_t hits_cap, uint64_t *n_hits_out)
+{
+	int rc;
+	if ((rc = dsb_batch_upload(c, seqs, offs, n_reads)) != DSB_OK) return rc;
+	if ((rc = dsb_batch_run(c, max_read_l_in)) != DSB_OK) return rc;
+	rc = dsb_batch_download(c, max_read_l_out, rr, hits, hits_cap, n_hits_out);
+	if (max_read_l_out && (rc == DSB_OK || rc == DSB_E_CAPACITY)) *max_read_l_out = std::max(*max_read_l_out, max_read_l_in);
+	return rc;
+}
+
+extern "C" int dsb_batch_get_seeds(dsb_ctx *c, uint32_t read, int strand, dsb_seed *out, uint32_t cap, uint32_t *n_out, uint32_t *total_score)
+{
+	if (!c || !c->ran || read >= c->n_reads || strand < 0 || strand > 1) return DSB_E_ARG;
+	DSB_CUDA(cudaSetDevice(c->ix->device));
+	DSB_CUDA(cudaStreamSynchronize(c->stream));
+	uint32_t n = 0, ts = 0;
+	DSB_CUDA(cudaMemcpy(&n, (uint32_t *)c->n_seeds[strand].p + read, 4, cudaMemcpyDeviceToHost));
+	DSB_CUDA(cudaMemcpy(&ts, (uint32_t *)c->total_score[strand].p + read, 4, cudaMemcpyDeviceToHost));
+	if (n_out) *n_out = n;
+	if (total_score) *total_score = ts;
+	if (out && n) {
+		if (n > cap) return DSB_E_CAPACITY;
+		DSB_CUDA(cudaMemcpy(out, (dsb_seed *)c->seeds[strand].p + c->h_seed_off[read], (size_t)n * sizeof(dsb_seed), cudaMemcpyDeviceToHost));
+	}
+	return DSB_OK;
+}
+
+extern "C" int dsb_batch_kernel_ms(dsb_ctx *c, float ms[4])
+{
+	if (!c || !c->ran || !ms) return DSB_E_ARG;
+	DSB_CUDA(cudaSetDevice(c->ix->device));
+	DSB_CUDA(cudaStreamSynchronize(c->stream));
+	for (int i = 0; i < 4; i++) { ms[i] = 0; if (c->n_reads) DSB_CUDA(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1])); }
+	return DSB_OK;
+}
+
+extern "C" int dsb_batch_launches(dsb_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int dsb_batch_counters(dsb_ctx *c, uint64_t out[16])
+{
+	if (!c || !c->ran || !out) return DSB_E_ARG;
+	DSB_CUDA(cudaSetDevice(c->ix->device));
+	DSB_CUDA(cudaStreamSynchronize(c->stream));
+	DSB_CUDA(cudaMemcpy(out, c->counters.p, DSB_CNT_COUNT * 8, cudaMemcpyDeviceToHost));
+	return DSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ roofline denominator
+// Random-gather microbenchmark: every thread reads `bytes_each` bytes at pseudo-random aligned positions
+// of a table far larger than L2; the figure reported is sector-granular traffic (max(bytes_each,32) per gather) per second.
+template <int BYTES>
+__global__ void k_gather(const uint8_t *table, uint64_t n_slots, uint64_t n_gathers, uint64_t seed, unsigned long long *sink)
+{
+	const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, nthr = gridDim.x * (uint64_t)blockDim.x;
+	uint64_t acc = 0;
+	for (uint64_t g = tid; g < n_gathers; g += nthr) {
+		const uint64_t slot = dsb_hash64_1(g ^ seed) % n_slots;
+		const uint8_t *p = table + slot * BYTES;
+		if (BYTES == 1) acc += __ldg(p);
+		else if (BYTES == 2) acc += __ldg((const uint16_t *)p);
+		else if (BYTES == 4) acc += __ldg((const uint32_t *)p);
+		else if (BYTES == 8) acc += __ldg((const uint64_t *)p);
+		else { for (int k = 0; k < BYTES / 16; k++) { const uint4 v = __ldg((const uint4 *)p + k); acc += v.x + v.y + v.z + v.w; } }
+	}
+	if (acc == 0x123456789abcdefull) atomicAdd(sink, 1ull);
+}
+
+extern "C" int dsb_gather_bench(int device, uint64_t table_bytes, uint64_t n_gathers, int bytes_each, double *gbs, double *ms_out)
+{
+	if (!gbs || table_bytes < (1u << 20) || n_gathers == 0) return DSB_E_ARG;
+	DSB_CUDA(cudaSetDevice(device));
+	uint8_t *table = nullptr; unsigned long long *sink = nullptr;
+	DSB_CUDA(cudaMalloc(&table, table_bytes));
+	DSB_CUDA(cudaMalloc(&sink, 8));
+	DSB_CUDA(cudaMemset(table, 1, table_bytes));
+	DSB_CUDA(cudaMemset(sink, 0, 8));
+	cudaEvent_t e0, e1;
+	DSB_CUDA(cudaEventCreate(&e0)); DSB_CUDA(cudaEventCreate(&e1));
+	cudaDeviceProp prop; DSB_CUDA(cudaGetDeviceProperties(&prop, device));
+	const int blocks = prop.multiProcessorCount * 8, threads = 256;
+	float best = 1e30f;
+	for (int rep = 0; rep < 4; rep++) {
+		const uint64_t n_slots = table_bytes / bytes_each, seed = 0x9e3779b97f4a7c15ull * (rep + 1);
+		DSB_CUDA(cudaEventRecord(e0));
+		switch (bytes_each) {
+			case 1: k_gather<1><<<blocks, threads>>>(table, n_slots, n_gathers, seed, sink); break;
+			case 2: k_gather<2><<<blocks, threads>>>(table, n_slots, n_gathers, seed, sink); break;
+			case 4: k_gather<4><<<blocks, threads>>>(table, n_slots, n_gathers, seed, sink); break;
+			case 8: k_gather<8><<<blocks, threads>>>(table, n_slots, n_gathers, seed, sink); break;
+			case 16: k_gather<16><<<blocks, threads>>>(table, n_slots, n_gathers, seed, sink); break;
+			case 32: k_gather<32><<<blocks, threads>>>(table, n_slots, n_gathers, seed, sink); break;
+			case 64: k_gather<64><<<blocks, threads>>>(table, n_slots, n_gathers, seed, sink); break;
+			case 128: k_gather<128><<<blocks, threads>>>(table, n_slots, n_gathers, seed, sink); break;
+			default: cudaFree(table); cudaFree(sink); dsb_set_error("bytes_each must be a power of two in 1..128"); return DSB_E_ARG;
+		}
+		DSB_CUDA(cudaEventRecord(e1));
+		DSB_CUDA(cudaEventSynchronize(e1));
+		float ms = 0; DSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+		if (rep > 0 && ms < best) best = ms;
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	cudaFree(table); cudaFree(sink);
+	const double sector_bytes = (double)std::max(bytes_each, 32) * (double)n_gathers;
+	*gbs = sector_bytes / (best * 1e-3) / 1e9;
+	if (ms_out) *ms_out = best;
+	return DSB_OK;
+}

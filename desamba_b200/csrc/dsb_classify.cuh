@@ -1,0 +1,1196 @@
+// dsb_classify.cuh -- the per-read classifier (seeding by FM-index backward search, anchor chaining, 9-mer sparse-DP
+// scoring) as warp-per-read device code.  Behaviour follows the reference function by function (citations inline);
+// structure is this project's own: anchors/chains are index-linked arrays in per-warp HBM scratch, the visited-row
+// set / flank frame / reference window live in shared memory, the read's 9-mer index is a warp-built CSR table.
+#pragma once
+#include "dsb_device.cuh"
+#include "../../include/desamba_b200.h"
+
+#define L_PRE_IDX 13
+#define PRE_IDX_MASK 0x3FFFFFFu
+#define SA_MASK 0x7
+#define SA_OFF 3
+#define MIN_UNI_L 35
+#define LV_L 12
+#define S_A_KEMR_L 9
+#define OVER_SEARCH_M2 50
+#define MIN_SCORE_MEM 12
+#define NO_SA 0xFFFFFFFFFFFFFFFFull
+#define SP_SET_CAP 500
+
+struct DevAnchor {              // Anchor (cly.h:44-61), only the fields read after map_seed
+	uint32_t ref_ID, ref_offset, index_in_read;
+	int32_t  pre;               // chain_anchor_pre as index, -1 = NULL
+	uint16_t mtch_len; int16_t score;
+	uint8_t  direction, useless, duplicate, pad;
+};
+struct DevChain {               // chain_item (cly.h:69-89)
+	uint32_t ref_ID; int32_t q_t_dis; uint32_t sum_score, anchor_number;
+	uint32_t t_st, t_ed, q_st, q_ed, indel;
+	int32_t  cur;               // chain_anchor_cur as index
+	uint8_t  direction, with_top_anchor, primary, pri_index;
+};
+struct DevSms { uint32_t t_pos, q_pos, len, score; };   // spd_match (cly.h:127-133)
+struct MemRst { int match_len; int sa_sp_l; uint64_t sp, sa_sp; int read_offset; int pad; };   // MEM_rst (cly.c:619-627)
+struct KEntry { uint32_t kmer, pos; };
+struct ScHash { uint16_t next; uint16_t seed_ID; uint16_t s_or_e; uint16_t pad; };   // seed_con_hash (cly.h:120-125)
+
+struct WarpSmem {               // per-warp shared memory
+	uint64_t sp_set[SP_SET_CAP];
+	uint8_t  refwin[2176];      // ref[2000] of sdp_middle_M2 / ref[1000] of sdp_right/left_M2 (+ over-read slack)
+	uint8_t  frame[64];         // pad[8] | q_pre[13] | t_pre[13] | t_suf[13]  (policy P2)
+};
+#define FR_A 8
+#define FR_B 21
+#define FR_C 34
+
+struct WarpScratch {            // per-warp HBM scratch
+	DevAnchor *anc, *anc_tmp;
+	DevChain  *chain, *chain_tmp;
+	DevSms    *sms;
+	int       *score_v;         // 1024
+	MemRst    *mem_rst;         // 256
+	ScHash    *sc_hash;         // 256 + 2*400 + 8
+	uint32_t  *kidx_start[2];   // CSR bucket ends of the read's 9-mer index, per strand slot (0 forward, 1 reverse)
+	KEntry    *kidx_ent[2];
+};
+
+struct ClassifyParams {
+	DevIndex ix;
+	uint32_t n_reads;
+	const uint64_t *read_off;   // n_reads+1, offsets into the concatenated ASCII reads
+	const uint64_t *bin_off;    // per read: offset of [GUARD | fwd | rev | GUARD] in bin
+	const uint8_t  *bin;
+	const uint32_t *seed_off;   // per read: first seed slot (per strand array)
+	const dsb_seed *seeds[2];   // [0] forward strand, [1] reverse strand
+	const uint32_t *n_seeds[2];
+	const uint32_t *total_score[2];
+	uint32_t *work_counter;
+	// scratch
+	uint8_t  *scratch; uint64_t scratch_stride;
+	uint32_t max_anchors, max_matches, kidx_bits_max, kidx_len_max;
+	// outputs
+	dsb_read_result *rr;
+	dsb_hit *hits; uint64_t hits_cap; unsigned long long *hits_cursor;
+};
+
+struct SearchDir {              // SEARCH_DIR (cly.c:946-954)
+	const dsb_seed *seed_v; uint32_t l_seed_v;
+	const uint8_t *bin_read;
+	uint32_t direction, total_score;
+};
+
+struct ReadState {
+	const DevIndex *ix;
+	WarpSmem *sm;
+	WarpScratch ws;
+	uint32_t n_anc, n_hit, n_sms;
+	uint32_t max_anchors, max_matches;
+	uint32_t fast_classify;
+	int error;
+	int sp_l;                    // SP_SET.l
+	uint32_t c_prefix, c_occ, c_locate, c_getref, c_getref_bytes;   // algorithmic counters
+};
+#define CNT_GETREF(S, len) do { (S).c_getref++; (S).c_getref_bytes += ((uint32_t)DSB_MAX((int)(len), 0) + 3) >> 2; } while (0)
+
+// ---------------------------------------------------------------- visited-row set (sp_set_insert, cly.c:1286-1298)
+__device__ __forceinline__ int sp_set_insert(ReadState &S, uint64_t node)
+{
+	if (S.sp_l == SP_SET_CAP) S.sp_l = 0;
+	const int lane = lane_id();
+	bool found = false;
+	for (int i = lane; i < S.sp_l; i += 32) found |= (S.sm->sp_set[i] == node);
+	if (__any_sync(DSB_FULL, found)) return 0;
+	S.sm->sp_set[S.sp_l] = node;
+	S.sp_l++;
+	__syncwarp();
+	return 1;
+}
+
+// ---------------------------------------------------------------- FM-index search (cly.c:1344-1447)
+__device__ __noinline__ void bwt_single_search(ReadState &S, uint64_t sp, const uint8_t *string, int max_match_len, MemRst *out)
+{
+	const DevIndex &ix = *S.ix;
+	uint64_t new_sp, sa_sp = NO_SA;
+	int match_len = 0, sa_sp_l = 0;
+	while (1) {
+		if (match_len >= max_match_len) break;
+		if ((sp & SA_MASK) == 0) { sa_sp = sp; sa_sp_l = 0; }
+		else sa_sp_l--;
+		uint32_t c = 0xff;
+		new_sp = occ_one(ix, sp, c) + ix.rank[c];
+		S.c_occ++;
+		if (c != (uint32_t)__ldg(string)) break;
+		match_len++;
+		string--;
+		if (sp_set_insert(S, new_sp) == 0) { out->match_len = -1000; return; }
+		sp = new_sp;
+	}
+	out->sp = sp; out->match_len = match_len; out->sa_sp = sa_sp; out->sa_sp_l = sa_sp_l;
+}
+
+__device__ __noinline__ int bwt_MEM_search(ReadState &S, const uint8_t *string, uint64_t pre_v, int max_rst, int l_min_mth, int l_max_mth, MemRst *mem_rst)
+{
+	const DevIndex &ix = *S.ix;
+	int n_rst = 0;
+	uint64_t sp = __ldg(ix.prefix + pre_v), ep = __ldg(ix.prefix + pre_v + 1), new_sp, new_ep;
+	S.c_prefix++;
+	string -= L_PRE_IDX;
+	int match_len = L_PRE_IDX;
+	while (1) {
+		const uint32_t c = __ldg(string);
+		string--;
+		occ_pair(ix, sp, ep, c, new_sp, new_ep);
+		S.c_occ += 2;
+		new_sp += ix.rank[c]; new_ep += ix.rank[c];
+		if (match_len >= l_min_mth - 1) {
+			if (new_sp + max_rst >= new_ep) break;
+			if (match_len >= l_max_mth) return 0;
+		}
+		if (new_sp + 1 >= new_ep) break;
+		match_len++;
+		sp = new_sp; ep = new_ep;
+	}
+	if (new_sp >= new_ep) return 0;
+	if (new_sp + 1 == new_ep) {
+		if (sp_set_insert(S, new_sp) == 0) return 0;
+		bwt_single_search(S, new_sp, string, DSB_MAX(0, l_max_mth - match_len), mem_rst + n_rst);
+		mem_rst[n_rst].match_len += match_len + 1;
+		if (mem_rst[n_rst].match_len >= l_min_mth) n_rst++;
+	} else {
+		for (uint64_t c_sp = new_sp; c_sp < new_ep; c_sp++) {
+			if (sp_set_insert(S, c_sp) == 0) continue;
+			bwt_single_search(S, c_sp, string, DSB_MAX(0, l_max_mth - match_len), mem_rst + n_rst);
+			mem_rst[n_rst].match_len += match_len + 1;
+			if (mem_rst[n_rst].match_len >= l_min_mth) n_rst++;
+		}
+	}
+	return n_rst;
+}
+
+// ---------------------------------------------------------------- locate + anchors (cly.c:471-496, 629-694, 706-939)
+__device__ __forceinline__ int64_t get_uni(ReadState &S, const DevIndex &ix, uint64_t bwt_pos, int search_l, uint64_t *global_offset, uint32_t *uni_offset_)
+{
+	S.c_locate++;
+	const uint2 sa = __ldg(ix.sa + (bwt_pos >> SA_OFF));
+	int64_t u = sa.x;
+	uint32_t uni_offset = sa.y + search_l + 1;
+	if (search_l > 0)
+		for (;;) { const uint32_t len = __ldg(ix.uni + u).y; if (!(uni_offset >= len) || u >= (int64_t)ix.n_uni) break; uni_offset -= (len + 1); u++; }   // (bound: the reference walks off its table here)
+	const uint64_t rp = __ldg(ix.ref_pos + __ldg(ix.uni + u).x);
+	*global_offset = (rp & 0xFFFFFFFFFFull) + uni_offset;
+	*uni_offset_ = uni_offset;
+	return u;
+}
+
+__device__ __forceinline__ void frame_zero(uint8_t *p13)      // zero one 13-byte flank array (trivial-auto-var-init)
+{
+	if (lane_id() < 13) p13[lane_id()] = 0;
+	__syncwarp();
+}
+
+__device__ __noinline__ void get_new_ed(ReadState &S, uint32_t *e_d, uint32_t *len_, uint32_t *l_mem_ext,
+                                        int32_t q_off, uint64_t t_off, uint32_t l_read, const uint8_t *q_b, bool is_FWD)
+{
+	const DevIndex &ix = *S.ix;
+	uint8_t *fr = S.sm->frame;
+	frame_zero(fr + FR_B); frame_zero(fr + FR_C);
+	const uint8_t *q = fr + FR_B; uint8_t *t = fr + FR_C;
+	uint32_t len, max_len;
+	if (is_FWD) {
+		if (q_off < 0) q_off = 0;
+		max_len = q_off;
+		len = DSB_MIN(12, max_len);
+		if ((uint32_t)lane_id() < len) fr[FR_B + lane_id()] = __ldg(q_b + q_off - lane_id());
+		__syncwarp();
+	} else {
+		max_len = l_read - q_off;
+		len = DSB_MIN(12, max_len);
+		q = q_b + q_off;
+	}
+	CNT_GETREF(S, len); get_ref_coop(ix, t, t_off, len, !is_FWD);
+	if (len > 0 && t[0] == q[0]) {
+		int mtc;
+		do {
+			for (mtc = 0; mtc < len; mtc++) if (t[mtc] != q[mtc]) break;
+			if (mtc > 0) {
+				*l_mem_ext += mtc;
+				max_len -= mtc;
+				len = DSB_MIN(12, max_len);
+				if (is_FWD) {
+					q_off -= mtc; t_off -= mtc;
+					__syncwarp();
+					if ((uint32_t)lane_id() < len) fr[FR_B + lane_id()] = __ldg(q_b + q_off - lane_id());
+					__syncwarp();
+				} else { t_off += mtc; q += mtc; }
+				__syncwarp();
+				CNT_GETREF(S, len); get_ref_coop(ix, t, t_off, len, !is_FWD);
+			}
+		} while (mtc > 0);
+	}
+	*e_d = lv_extd_dev(t, len, q, len);
+	*len_ = len;
+}
+
+struct SeedInfo { const uint8_t *bin_read; uint32_t read_L; uint32_t direction; };
+
+#define MIN_S_1 12
+#define MIN_S_2 20
+__device__ __noinline__ int32_t map_seed(ReadState &S, const MemRst *m_r, const SeedInfo &s_i)
+{
+	const DevIndex &ix = *S.ix;
+	uint64_t b_p = m_r->sp;
+	const int32_t q_off = m_r->read_offset;
+	uint32_t l_m = m_r->match_len;
+	const uint8_t *q_b = s_i.bin_read;
+	int64_t uni = -1;
+	uint32_t u_off = 0;
+	uint64_t t_off = 0;
+	uint32_t l_pre, l_suf = 0, d_pre, d_suf = 0;
+	int32_t s = 0, max_s = 0;
+	uint8_t *fr = S.sm->frame;
+	__syncwarp();
+	if (lane_id() < 16) ((uint32_t *)fr)[lane_id()] = 0;
+	__syncwarp();
+	do {
+		uint8_t *q_pre = fr + FR_A, *t_pre = fr + FR_B, *t_suf = fr + FR_C;
+		const uint8_t *q_suf;
+		l_pre = DSB_MIN(q_off + 1, LV_L);
+		if ((uint32_t)lane_id() < l_pre) q_pre[lane_id()] = __ldg(q_b + q_off - lane_id());
+		__syncwarp();
+		int s_l = 0;
+		if (m_r->sa_sp != NO_SA)
+			uni = get_uni(S, ix, m_r->sa_sp, m_r->sa_sp_l, &t_off, &u_off);
+		else {
+			uint32_t c; uint64_t new_sp;
+			while (1) {
+				if ((b_p & SA_MASK) == 0) break;
+				c = 0xff;
+				new_sp = occ_one(ix, b_p, c) + ix.rank[c];
+				S.c_occ++;
+				if (c == 4) break;
+				t_pre[s_l++] = (uint8_t)c;
+				b_p = new_sp;
+				if (s_l >= l_pre) break;
+			}
+			__syncwarp();
+			if ((b_p & SA_MASK) == 0) uni = get_uni(S, ix, b_p, s_l, &t_off, &u_off);
+			else l_pre = s_l;
+		}
+		if (uni >= 0) {
+			if (__ldg(ix.uni + uni).y < MIN_UNI_L) break;
+			l_pre = DSB_MIN(l_pre, u_off);
+			CNT_GETREF(S, l_pre); get_ref_coop(ix, t_pre, t_off - 1, l_pre, false);
+		}
+		d_pre = lv_extd_dev(t_pre, l_pre, q_pre, l_pre);
+		s = Q_MEM_at(ix, l_m) + Q_LV_at(ix, d_pre, l_pre);
+		if (s < MIN_S_1 && l_pre == LV_L && uni < 0) { s = 0; break; }
+		if (uni < 0) {
+			for (int guard = 0; b_p & SA_MASK; guard++) {
+				if (guard > (1 << 20)) { S.error = 5; return 0; }          // cannot happen on a well-formed index; never hang the GPU
+				uint32_t c = 0xff;
+				b_p = occ_one(ix, b_p, c) + ix.rank[c];
+				S.c_occ++;
+				s_l++;
+			}
+			uni = get_uni(S, ix, b_p, s_l, &t_off, &u_off);
+			if (__ldg(ix.uni + uni).y < MIN_UNI_L) { s = 0; break; }
+		}
+		const int32_t q_off_r = q_off + l_m + 1;
+		uint32_t l_max_suf = DSB_MIN(__ldg(ix.uni + uni).y - u_off - l_m, s_i.read_L - q_off_r);
+		if (l_max_suf != 0) {
+			l_suf = DSB_MIN(l_max_suf, LV_L);
+			q_suf = q_b + q_off_r;
+			CNT_GETREF(S, l_suf); get_ref_coop(ix, t_suf, t_off + l_m, l_suf, true);
+			if (t_suf[0] == __ldg(q_suf)) {
+				int mtc;
+				do {
+					for (mtc = 0; mtc < l_suf; mtc++) if (t_suf[mtc] != __ldg(q_suf + mtc)) break;
+					if (mtc > 0) {
+						l_m += mtc;
+						s = Q_MEM_at(ix, l_m) + Q_LV_at(ix, d_pre, l_pre);
+						l_max_suf -= mtc;
+						l_suf = DSB_MIN(l_max_suf, LV_L);
+						q_suf += mtc;
+						__syncwarp();
+						CNT_GETREF(S, l_suf); get_ref_coop(ix, t_suf, t_off + l_m, l_suf, true);
+					}
+				} while (mtc > 0);
+			}
+			d_suf = lv_extd_dev(t_suf, l_suf, q_suf, l_suf);
+			s += Q_LV_at(ix, d_suf, l_suf);
+		} else
+			l_suf = d_suf = 0;
+		if (s <= MIN_S_2 && l_suf == LV_L) { s = 0; break; }
+	} while (0);
+
+	if (s > 0) {
+		uint16_t am_mtch_len = (uint16_t)l_m; int16_t am_score = (int16_t)s;
+		uint8_t am_left_len = (uint8_t)l_pre, am_left_ED = (uint8_t)d_pre, am_rigt_len = (uint8_t)l_suf, am_rigt_ED = (uint8_t)d_suf;
+		const uint32_t r_p_s = __ldg(ix.uni + uni).x, r_p_e = __ldg(ix.uni + uni + 1).x;
+		const bool ref_search_l = (l_pre < LV_L || d_pre == 0);
+		const bool ref_search_r = (l_suf < LV_L || d_suf == 0);
+		if ((int64_t)r_p_e - (int64_t)r_p_s > 50)
+			if (!((int64_t)r_p_e - (int64_t)r_p_s < 1000)) return 50;
+		for (uint32_t c_r_p = r_p_s; c_r_p < r_p_e; c_r_p++) {
+			const uint64_t rp = __ldg(ix.ref_pos + c_r_p);
+			const uint64_t rp_global = rp & 0xFFFFFFFFFFull; const uint32_t rp_ref = (uint32_t)((rp >> 40) & 0x7FFFFF);
+			uint32_t ed_l, ed_r, len_l, len_r;
+			uint32_t l_m_ext_l = 0, l_m_ext_r;
+			if (ref_search_l || ref_search_r) {
+				if (ref_search_l) {
+					get_new_ed(S, &ed_l, &len_l, &l_m_ext_l, q_off, rp_global + u_off - 1, s_i.read_L, q_b, true);
+					am_left_len = (uint8_t)len_l; am_left_ED = (uint8_t)ed_l;
+				}
+				am_mtch_len = (uint16_t)(l_m + l_m_ext_l);
+				if (ref_search_r) {
+					l_m_ext_r = 0;
+					get_new_ed(S, &ed_r, &len_r, &l_m_ext_r, q_off + l_m + 1, rp_global + u_off + l_m, s_i.read_L, q_b, false);
+					am_rigt_len = (uint8_t)len_r; am_rigt_ED = (uint8_t)ed_r;
+					am_mtch_len = (uint16_t)(am_mtch_len + l_m_ext_r);
+				}
+				am_score = (int16_t)(Q_MEM_at(ix, am_mtch_len) + Q_LV_at(ix, am_left_ED, am_left_len) + Q_LV_at(ix, am_rigt_ED, am_rigt_len));
+				if (am_score < MIN_S_2) continue;
+			}
+			max_s = DSB_MAX(max_s, am_score);
+			if (S.n_anc >= S.max_anchors) { S.error = 1; return max_s; }
+			DevAnchor a;
+			a.direction = (uint8_t)s_i.direction;
+			a.index_in_read = q_off + 1 - l_m_ext_l;
+			const uint64_t g = rp_global + u_off - l_m_ext_l;
+			a.ref_ID = rp_ref;
+			a.ref_offset = (uint32_t)(g - __ldg(ix.ref_info + rp_ref).y);
+			a.mtch_len = am_mtch_len; a.score = am_score;
+			a.pre = -1; a.useless = 0; a.duplicate = 0; a.pad = 0;
+			S.ws.anc[S.n_anc++] = a;
+		}
+	}
+	return max_s;
+}
+
+// ---------------------------------------------------------------- seed scheduling (cly.c:1476-1611)
+__device__ __forceinline__ uint64_t prefix13(const uint8_t *bin_read, int string_index)
+{   // low 26 bits of the l_ek-mer ending at string_index (= kmer[kmer_index] & PRE_IDX_MASK, cly.c:1504; seeds hold only non-zero k-mers)
+	uint64_t v = 0;
+	#pragma unroll
+	for (int k = 12; k >= 0; k--) v = (v << 2) | __ldg(bin_read + string_index - k);
+	return v;
+}
+
+__device__ __forceinline__ void mark_useless(ReadState &S, uint32_t a_b_idx)
+{
+	int top_score = 35;
+	for (uint32_t k = a_b_idx; k < S.n_anc; k++) top_score = DSB_MAX(top_score, S.ws.anc[k].score);
+	for (uint32_t k = a_b_idx; k < S.n_anc; k++) S.ws.anc[k].useless = (S.ws.anc[k].score < top_score) ? 1 : 0;
+}
+
+#define MEM_search_FAST 2
+#define MIN_MEM_LEN_FAST 21
+__device__ __noinline__ void fast_classify(ReadState &S, const SearchDir &s_d, uint32_t read_len)
+{
+	const int l_ek = S.ix->l_ek;
+	const int min_index = MIN_MEM_LEN_FAST - l_ek;
+	const uint8_t *bin_read = s_d.bin_read;
+	MemRst *m_r = S.ws.mem_rst;
+	SeedInfo s_i = {bin_read, read_len, s_d.direction};
+	for (uint32_t si = 0; si < s_d.l_seed_v; si++) {
+		const dsb_seed c_sv = s_d.seed_v[si];
+		if (c_sv.top == 0) continue;
+		S.sp_l = 0;
+		const uint32_t a_b_idx = S.n_anc;
+		for (int j = (int)c_sv.len - 1; j >= min_index;) {
+			const int kmer_index = c_sv.offset + j;
+			const int string_index = kmer_index + l_ek - 1;
+			const uint64_t prefixValue = prefix13(bin_read, string_index);
+			const int n = bwt_MEM_search(S, bin_read + string_index, prefixValue, MEM_search_FAST, MIN_MEM_LEN_FAST - 1, string_index, m_r);
+			if (n == 0) { j -= 2; continue; }
+			j -= 3;
+			int max_score = 0;
+			for (int k = 0; k < n; k++) {
+				m_r[k].read_offset = string_index - m_r[k].match_len;
+				const int c_score = map_seed(S, m_r + k, s_i);
+				max_score = DSB_MAX(c_score, max_score);
+				if (S.error) return;
+			}
+			if (max_score > 35) j -= 7;
+			if (max_score > 256) {
+				if (max_score > 512) si++;
+				break;
+			}
+		}
+		mark_useless(S, a_b_idx);
+	}
+}
+
+struct MemRstCmp { __device__ int operator()(const MemRst &a, const MemRst &b) const { return b.match_len - a.match_len; } };
+
+#define MEM_search_SLOW 8
+#define MIN_MEM_LEN_SLOW 20
+__device__ __noinline__ void slow_classify(ReadState &S, const SearchDir &sd, uint32_t read_len)
+{
+	const int l_ek = S.ix->l_ek;
+	const uint8_t *bin_read = sd.bin_read;
+	const dsb_seed *sv_f = sd.seed_v;
+	MemRst *mem_rst = S.ws.mem_rst;          // <= 31 searches * 8 results per seed
+	SeedInfo seed_info = {bin_read, read_len, sd.direction};
+	const uint8_t top0 = sd.l_seed_v ? sv_f[0].top : 0;
+	for (uint32_t i = 0; i < sd.l_seed_v; i++) {
+		const dsb_seed sv = sv_f[i];
+		if ((int)(sv.len) < 3 && top0 == 0) continue;            // sv_f->top: seed 0's flag, as written (cly.c:1564)
+		const int min_match_len = DSB_MIN(MIN_MEM_LEN_SLOW - 1, l_ek + 1);
+		S.sp_l = 0;
+		int mem_rst_num = 0;
+		for (int j = (int)sv.len - 1; j >= 1; j -= 2) {
+			const int k_idx = sv.offset + j;
+			const int s_idx = k_idx + l_ek - 1;
+			const uint64_t pre_v = prefix13(bin_read, s_idx);
+			const int n = bwt_MEM_search(S, bin_read + s_idx, pre_v, MEM_search_SLOW, min_match_len, s_idx, mem_rst + mem_rst_num);
+			for (int k = mem_rst_num; k < mem_rst_num + n; k++) mem_rst[k].read_offset = k_idx + l_ek - 1 - mem_rst[k].match_len;
+			mem_rst_num += n;
+		}
+		if (mem_rst_num == 0) continue;
+		if (mem_rst_num > 1) glibc_msort(mem_rst, mem_rst + 256, mem_rst_num, MemRstCmp());
+		const uint32_t a_b_idx = S.n_anc;
+		const int max_search = DSB_MIN(mem_rst_num, MEM_search_SLOW);
+		for (int k = 0; k < max_search; k++) { map_seed(S, mem_rst + k, seed_info); if (S.error) return; }
+		mark_useless(S, a_b_idx);
+	}
+	S.fast_classify = 0;
+}
+
+// ---------------------------------------------------------------- chaining (cly.c:38-52, 72-112, 201-349)
+struct ChainCmpByScore {
+	__device__ int operator()(const DevChain &a, const DevChain &b) const {
+		if (a.with_top_anchor != b.with_top_anchor) return (a.with_top_anchor) ? (-1) : (1);
+		int score_a = a.sum_score + ((a.q_ed - a.q_st) << 1);
+		score_a -= (a.indel << 2);
+		int score_b = b.sum_score + ((b.q_ed - b.q_st) << 1);
+		score_b -= (b.indel << 2);
+		if (score_a < score_b) return 1;
+		if (score_a > score_b) return -1;
+		return 0;
+	}
+};
+
+#define MAX_dis_MINUS 30
+#define MAX_waiting_len 400
+__device__ __forceinline__ void chain_insert_M2(ReadState &S, int32_t ai)
+{
+	DevAnchor *A = S.ws.anc; DevChain *C = S.ws.chain;
+	const DevAnchor an = A[ai];
+	const int32_t dis = an.ref_offset - an.index_in_read;
+	const uint32_t ref_l = an.ref_offset, ref_r = ref_l + an.mtch_len;
+	const uint32_t read_l = an.index_in_read, read_r = read_l + an.mtch_len;
+	int dis_minus = 0;
+	for (uint32_t k = 0; k < S.n_hit; k++) {
+		DevChain c = C[k];
+		if (c.direction == an.direction && c.ref_ID == an.ref_ID &&
+		    (dis_minus = DSB_ABS(dis - c.q_t_dis)) < MAX_dis_MINUS &&
+		    DSB_ABS_U(c.t_ed, an.ref_offset) < MAX_waiting_len) {
+			// chain_insert_meta, new_chain == false (cly.c:95-111)
+			c.with_top_anchor |= (!an.useless);
+			if (c.q_ed >= read_r) { C[k] = c; return; }
+			c.t_ed = DSB_MAX(ref_r, c.t_ed);
+			c.q_ed = read_r;
+			A[ai].pre = c.cur;
+			c.cur = ai;
+			c.q_t_dis = an.ref_offset - an.index_in_read;
+			c.indel += dis_minus;
+			c.anchor_number++;
+			c.sum_score += (an.duplicate) ? 1 : an.score;
+			C[k] = c;
+			return;
+		}
+	}
+	DevChain c;                                   // chain_insert_meta, new_chain == true (cly.c:78-94)
+	A[ai].pre = -1;
+	c.ref_ID = an.ref_ID; c.direction = an.direction;
+	c.q_t_dis = an.ref_offset - an.index_in_read;
+	c.t_st = ref_l; c.t_ed = ref_r; c.q_st = read_l; c.q_ed = read_r;
+	c.with_top_anchor = !an.useless;
+	c.anchor_number = 1;
+	c.sum_score = (an.duplicate) ? 1 : an.score;
+	c.indel = 0; c.cur = ai; c.primary = 0; c.pri_index = 0;
+	C[S.n_hit++] = c;
+}
+
+struct AnchorCmp {                                // Anchor_cmp_by_chr_ID_and_pos (cly.c:226-235): a 0/1 comparator
+	__device__ int operator()(const DevAnchor &a, const DevAnchor &b) const {
+		if (a.ref_ID != b.ref_ID) return a.ref_ID > b.ref_ID;
+		if (a.direction != b.direction) return a.direction > b.direction;
+		return a.ref_offset > b.ref_offset;
+	}
+};
+
+#define MAX_ANCHOR_OVERLAP 3
+__device__ __noinline__ void chain_insert_M3(ReadState &S)
+{
+	int *score_v = S.ws.score_v;
+	DevAnchor *A = S.ws.anc; DevChain *C = S.ws.chain;
+	const int32_t n = (int32_t)S.n_anc;
+	glibc_msort(A, S.ws.anc_tmp, n, AnchorCmp());
+	for (int32_t chr_st = 0; chr_st < n;) {
+		int32_t chr_ed = chr_st + 1, c_a;
+		const uint32_t ref_ID = A[chr_st].ref_ID;
+		const uint32_t direction = A[chr_st].direction;
+		for (; chr_ed < n && A[chr_ed].ref_ID == ref_ID && A[chr_ed].direction == direction &&
+		       A[chr_ed].ref_offset - A[chr_ed - 1].ref_offset < 2000; chr_ed++);
+		if (chr_ed - chr_st > 1024) chr_ed = chr_st + 1024;
+		int32_t max_anchor = -1; int max_score = 0, anchor_max_score;
+		for (c_a = chr_st; c_a < chr_ed; c_a++) {
+			const DevAnchor ca = A[c_a];
+			int32_t ca_pre = -1;
+			anchor_max_score = ca.score;
+			const uint32_t max_t = ca.ref_offset + MAX_ANCHOR_OVERLAP;
+			const uint32_t max_q = ca.index_in_read + MAX_ANCHOR_OVERLAP;
+			for (int32_t pre = c_a - 1; pre >= chr_st; pre--) {
+				const DevAnchor pa = A[pre];
+				if (pa.index_in_read + pa.mtch_len > max_q) continue;
+				if (pa.ref_offset + pa.mtch_len > max_t) continue;
+				if (pa.index_in_read + 1000 < max_q) break;
+				if (pa.ref_offset + 1000 < max_t) break;
+				const int indel = pa.index_in_read - pa.ref_offset - (max_q - max_t);
+				const int ABS_indel = DSB_ABS(indel);
+				if (ABS_indel > 200) continue;
+				const int new_score = score_v[pre - chr_st] + ca.mtch_len - (ABS_indel >> 4) - ((max_q - pa.index_in_read) >> 8);
+				if (new_score > anchor_max_score) { anchor_max_score = new_score; ca_pre = pre; }
+			}
+			A[c_a].pre = ca_pre;
+			score_v[c_a - chr_st] = anchor_max_score;
+			if (max_score < anchor_max_score) { max_score = anchor_max_score; max_anchor = c_a; }
+		}
+		int sum_INDEL = 0, anchor_number = 1; int32_t pre = max_anchor;
+		int sum_score = (A[max_anchor].duplicate) ? 1 : A[max_anchor].score;
+		int with_top = !A[max_anchor].useless;
+		for (; A[pre].pre != -1; anchor_number++) {
+			const int32_t pre_ = A[pre].pre;
+			sum_INDEL += (A[pre].index_in_read - A[pre_].index_in_read) - (A[pre].ref_offset - A[pre_].ref_offset);
+			with_top |= (!A[pre].useless);
+			sum_score += (A[pre].duplicate) ? 1 : A[pre].score;
+			pre = pre_;
+		}
+		DevChain c;
+		c.ref_ID = ref_ID; c.direction = (uint8_t)direction;
+		c.q_t_dis = A[max_anchor].ref_offset - A[max_anchor].index_in_read;
+		c.t_st = A[pre].ref_offset;
+		c.t_ed = A[max_anchor].ref_offset + A[max_anchor].mtch_len;
+		c.q_st = A[pre].index_in_read;
+		c.q_ed = A[max_anchor].index_in_read + A[max_anchor].mtch_len;
+		c.with_top_anchor = (uint8_t)with_top;
+		c.anchor_number = anchor_number;
+		c.sum_score = sum_score;
+		c.indel = sum_INDEL;
+		c.cur = max_anchor; c.primary = 0; c.pri_index = 0;
+		C[S.n_hit++] = c;
+		chr_st = chr_ed;
+	}
+}
+
+__device__ __noinline__ void resolve_tree(ReadState &S)     // cly.c:326-349
+{
+	S.n_hit = 0;
+	if (S.n_anc < 50)
+		for (int32_t a = 0; a < (int32_t)S.n_anc; a++) chain_insert_M2(S, a);
+	else
+		chain_insert_M3(S);
+	if (S.n_hit > 1) glibc_msort(S.ws.chain, S.ws.chain_tmp, (int)S.n_hit, ChainCmpByScore());
+	uint32_t rst_num = DSB_MIN(5u, S.n_hit);
+	while (rst_num < S.n_hit && S.ws.chain[rst_num].with_top_anchor == 1) rst_num++;
+	S.n_hit = rst_num;
+}
+
+// ---------------------------------------------------------------- the read's 9-mer index (replaces build_hash_table_M2, cly.c:2173-2224)
+// The reference chains nodes per hash bucket in insertion (= ascending position) order and compares the full 9-mer
+// on lookup.  Equivalent here: a CSR table keyed by the low key_bits of the 9-mer, entries (kmer,pos) in ascending
+// position inside each bucket.  Built by the warp: histogram (RED atomics) -> scan -> ordered fill (__match_any_sync).
+__device__ __forceinline__ uint32_t kmer9_at(const uint8_t *q, uint32_t pos)
+{
+	uint32_t k = 0;
+	#pragma unroll
+	for (int i = 0; i < S_A_KEMR_L; i++) k = (k << 2) | __ldg(q + pos + i);
+	return k;
+}
+
+__device__ __noinline__ void build_kidx(ReadState &S, const uint8_t *q, uint32_t q_len, int slot, int key_bits)
+{
+	uint32_t *start = S.ws.kidx_start[slot];
+	KEntry *ent = S.ws.kidx_ent[slot];
+	const uint32_t nb = 1u << key_bits, kmask = nb - 1;
+	const int lane = lane_id();
+	const uint32_t nk = q_len - S_A_KEMR_L + 1;
+	for (uint32_t b = lane; b < nb; b += 32) start[b] = 0;
+	__syncwarp();
+	for (uint32_t base = 0; base < nk; base += 32) {
+		const uint32_t pos = base + lane;
+		if (pos < nk) atomicAdd(start + (kmer9_at(q, pos) & kmask), 1u);
+	}
+	__syncwarp();
+	__threadfence_block();
+	// exclusive scan over buckets, in place
+	uint32_t carry = 0;
+	for (uint32_t b0 = 0; b0 < nb; b0 += 32) {
+		const uint32_t v = __ldcg(start + b0 + lane);
+		uint32_t x = v;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(DSB_FULL, x, d); if (lane >= d) x += y; }
+		start[b0 + lane] = carry + x - v;
+		carry += __shfl_sync(DSB_FULL, x, 31);
+	}
+	__syncwarp();
+	// ordered fill; afterwards start[b] = END of bucket b, begin = start[b-1] (0 for b == 0)
+	for (uint32_t base = 0; base < nk; base += 32) {
+		const uint32_t pos = base + lane;
+		const bool act = pos < nk;
+		const uint32_t kmer = act ? kmer9_at(q, pos) : 0xffffffffu;
+		const uint32_t key = act ? (kmer & kmask) : (0x80000000u | lane);
+		const uint32_t peers = __match_any_sync(DSB_FULL, key);
+		const int leader = __ffs(peers) - 1;
+		const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+		uint32_t cur = 0;
+		if (act && lane == leader) cur = start[key];
+		cur = __shfl_sync(DSB_FULL, cur, leader);
+		if (act) { KEntry e; e.kmer = kmer; e.pos = pos; ent[cur + rank] = e; }
+		if (act && lane == leader) start[key] = cur + __popc(peers);
+		__syncwarp();
+	}
+	__syncwarp();
+}
+
+struct KIdx { const uint32_t *start; const KEntry *ent; uint32_t kmask; };
+
+// ---------------------------------------------------------------- 9-mer sparse DP scoring (cly.c:1691-1818, 2335-2849)
+__device__ __forceinline__ void sc_hash_idx(ReadState &S)      // cly.c:1691-1710
+{
+	ScHash *sc_hash = S.ws.sc_hash;
+	for (int i = lane_id(); i < 256; i += 32) { ScHash z; z.next = 0; z.seed_ID = 0; z.s_or_e = 0; z.pad = 0; sc_hash[i] = z; }
+	__syncwarp();
+	int sc_con_index = 256;
+	for (uint32_t h = 0; h < S.n_hit; h++) {
+		const DevChain c_h = S.ws.chain[h];
+		for (int i = 1; i >= 0; i--) {
+			uint16_t c_key = ((i == 1) ? (c_h.t_st - c_h.q_st) : (c_h.t_ed - c_h.q_ed)) & 0xff;
+			while (sc_hash[c_key].next != 0) c_key = sc_hash[c_key].next;
+			ScHash e; e.seed_ID = (uint16_t)((h + 1) & 0x7fff); e.s_or_e = (uint16_t)i; e.next = (uint16_t)sc_con_index; e.pad = 0;
+			sc_hash[c_key] = e;
+			ScHash z; z.next = 0; z.seed_ID = 0; z.s_or_e = 0; z.pad = 0;
+			sc_hash[sc_con_index++] = z;
+		}
+	}
+}
+
+__device__ __noinline__ int combine_chain(ReadState &S, int chain_ID, int dis, int isleft, int c_q_pos, int *combined)
+{   // cly.c:1763-1808
+	const ScHash *sc_hash = S.ws.sc_hash;
+	DevChain *c_st = S.ws.chain;
+	uint16_t key = (dis) & 0xff;
+	while (sc_hash[key].next != 0) {
+		const uint16_t seed_ID = sc_hash[key].seed_ID;
+		const int ci = seed_ID - 1;
+		const DevChain c = c_st[ci];
+		const int dis_con = (isleft) ? (c.t_ed - c.q_ed) : (c.t_st - c.q_st);
+		const int q_pos_con = (!isleft) ? (c.q_st) : (c.q_ed - S_A_KEMR_L);
+		if (dis == dis_con && chain_ID != ci && isleft != (int)sc_hash[key].s_or_e && DSB_ABS_U(c_q_pos, q_pos_con) < 8 &&
+		    c_st[chain_ID].ref_ID == c.ref_ID && c_st[chain_ID].direction == c.direction && c.sum_score != 0 && seed_ID - 1 > chain_ID) {
+			DevChain h = c_st[chain_ID];
+			h.sum_score += c.sum_score;
+			h.anchor_number += c.anchor_number;
+			h.indel += c.indel;
+			h.q_st = DSB_MIN(h.q_st, c.q_st);
+			h.t_st = DSB_MIN(h.t_st, c.t_st);
+			h.q_ed = DSB_MAX(h.q_ed, c.q_ed);
+			h.t_ed = DSB_MAX(h.t_ed, c.t_ed);
+			c_st[chain_ID] = h;
+			DevChain z = c;
+			z.sum_score = 0; z.t_st = z.t_ed = z.q_st = z.q_ed = 0;
+			c_st[ci] = z;
+			*combined = ci;
+			return 1;
+		}
+		key = sc_hash[key].next;
+	}
+	return 0;
+}
+
+// MEM_search (cly.c:1810-1818); q in HBM (read strands incl. guards), t in the shared reference window
+__device__ __forceinline__ int MEM_search_fwd(const uint8_t *q, const uint8_t *t, int max)
+{
+	int len = 0;
+	for (; len < max && __ldg(q) == *t; len++, q++, t++);
+	return len;
+}
+__device__ __forceinline__ int MEM_search_bwd(const uint8_t *q, const uint8_t *t, int max)
+{
+	int len = 0;
+	for (; len < max && __ldg(q) == *t; len++, q--, t--);
+	return len;
+}
+
+__device__ __forceinline__ bool sms_push(ReadState &S, uint32_t t_pos, uint32_t q_pos, uint32_t len)
+{
+	if (S.n_sms >= S.max_matches) { S.error = 2; return false; }
+	DevSms *p = S.ws.sms + S.n_sms++;
+	p->t_pos = t_pos; p->q_pos = q_pos; p->len = len;
+	return true;
+}
+
+__device__ __noinline__ void sdp_match(ReadState &S, uint32_t q_bg, uint32_t q_ed, const uint8_t *q_str, const uint8_t *t_str, uint32_t t_len,
+                                       const KIdx &kx, uint32_t t_st, bool isForward)
+{   // cly.c:2335-2440
+	const uint32_t t_kmer_num = t_len - S_A_KEMR_L + 1;
+	const uint32_t MASK = (1u << (2 * S_A_KEMR_L)) - 1;
+	if (isForward) {
+		const uint8_t *c_t_str = t_str + 4;
+		uint32_t kmer = 0;
+		for (int k = 0; k < S_A_KEMR_L - 1; k++) kmer = (kmer << 2) | c_t_str[k];
+		for (int i = 4; (uint32_t)i < t_kmer_num; i++, c_t_str++) {
+			kmer = ((kmer << 2) | c_t_str[S_A_KEMR_L - 1]) & MASK;
+			if ((i & 0x03) != 0) continue;
+			const uint32_t key = kmer & kx.kmask;
+			uint32_t e = key ? kx.start[key - 1] : 0;
+			const uint32_t e_end = kx.start[key];
+			for (; e < e_end; e++) {
+				const KEntry en = kx.ent[e];
+				if (en.kmer != kmer) continue;
+				const uint32_t q_pos = en.pos;
+				if (q_pos >= q_bg && q_pos <= q_ed) {
+					const int back_len = MEM_search_bwd(q_str + q_pos - 1, c_t_str - 1, 4);
+					if (back_len < 4 || i == 4) {
+						uint32_t max_search = q_ed - q_pos - 1;
+						max_search = DSB_MIN(max_search, t_len - i - 1) + OVER_SEARCH_M2;
+						const int forward_len = MEM_search_fwd(q_str + q_pos + S_A_KEMR_L, c_t_str + S_A_KEMR_L, max_search);
+						const int total_len = back_len + forward_len + 1;
+						if (total_len >= 4)
+							if (!sms_push(S, i - back_len + t_st, q_pos - back_len, total_len)) return;
+					}
+				}
+			}
+		}
+	} else {
+		const uint8_t *c_t_str = t_str + t_len - S_A_KEMR_L - 4;
+		uint32_t kmer = 0;
+		for (int k = 0; k < S_A_KEMR_L; k++) kmer = (kmer << 2) | c_t_str[k];
+		uint64_t kmer64 = (uint64_t)kmer << 2;                               // bit2_preKmer_init
+		for (int i = 4; (uint32_t)i < t_kmer_num; i++, c_t_str--) {
+			kmer64 = (kmer64 >> 2) | ((uint64_t)c_t_str[0] << ((S_A_KEMR_L << 1) - 2));
+			if ((i & 0x03) != 0) continue;
+			kmer = (uint32_t)kmer64;
+			const uint32_t key = kmer & kx.kmask;
+			uint32_t e = key ? kx.start[key - 1] : 0;
+			const uint32_t e_end = kx.start[key];
+			for (; e < e_end; e++) {
+				const KEntry en = kx.ent[e];
+				if (en.kmer != kmer) continue;
+				const uint32_t q_pos = en.pos;
+				if (q_pos >= q_bg && q_pos <= q_ed) {
+					const int forward_len = MEM_search_fwd(q_str + q_pos + S_A_KEMR_L, c_t_str + S_A_KEMR_L, 4);
+					if (forward_len < 4 || i == 4) {
+						uint32_t max_search = q_pos;
+						max_search = DSB_MIN((long)max_search, (long)(c_t_str - t_str)) + OVER_SEARCH_M2;
+						const int back_len = MEM_search_bwd(q_str + q_pos - 1, c_t_str - 1, max_search);
+						const int total_len = back_len + forward_len + 1;
+						if (total_len >= 4)
+							if (!sms_push(S, (uint32_t)((long)(c_t_str - t_str) - back_len + t_st), q_pos - back_len, total_len)) return;
+					}
+				}
+			}
+		}
+	}
+}
+
+__device__ __forceinline__ void refwin_zero(ReadState &S, int nbytes)     // zero-initialised stack window (policy P1)
+{
+	__syncwarp();
+	uint32_t *w = (uint32_t *)S.sm->refwin;
+	for (int i = lane_id(); i < (nbytes + 3) / 4; i += 32) w[i] = 0;
+	__syncwarp();
+}
+
+#define MAX_sms_overlap (6)
+#define MAX_sms_overlap_middle (6)
+__device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8_t *q_str, const KIdx &kx)
+{   // cly.c:2444-2530
+	const DevIndex &ix = *S.ix;
+	int score = 10000;
+	const DevAnchor *A = S.ws.anc;
+	const uint64_t t_offset = __ldg(ix.ref_info + A[c_a].ref_ID).y;
+	int32_t pre_a = -1;
+	while (c_a != -1) {
+		const DevAnchor ca = A[c_a];
+		pre_a = ca.pre;
+		if (pre_a != -1) {
+			const DevAnchor pa = A[pre_a];
+			const int pre_mch = pa.mtch_len;
+			const int pre_refoffset = pa.ref_offset - 3;
+			const int total_ref_len = ca.ref_offset - (pre_refoffset + pre_mch) + 3;
+			S.n_sms = 0;
+			DevSms *base = S.ws.sms;
+			base[0].score = score; base[0].q_pos = pa.index_in_read; base[0].t_pos = pa.ref_offset; base[0].len = pa.mtch_len - S_A_KEMR_L + 1;
+			S.n_sms = 1;
+			if (total_ref_len > 12) {
+				if (!(total_ref_len < 2000)) { S.error = 3; return 0; }         // xassert(total_ref_len < 2000) aborts the reference (cly.c:2473)
+				refwin_zero(S, 2128);
+				const uint64_t ref_offset = pre_refoffset + t_offset + pre_mch;
+				CNT_GETREF(S, total_ref_len); get_ref_coop(ix, S.sm->refwin, ref_offset, total_ref_len, true);
+				sdp_match(S, pa.index_in_read + pre_mch - 8, ca.index_in_read - 1, q_str, S.sm->refwin, total_ref_len, kx, pre_refoffset + pre_mch, true);
+				if (S.error) return 0;
+			}
+			if (!sms_push(S, ca.ref_offset, ca.index_in_read, ca.mtch_len - S_A_KEMR_L + 1)) return 0;
+			if (S.n_sms > 1) {
+				for (uint32_t ci = 1; ci < S.n_sms; ci++) {
+					const DevSms c_spd = base[ci];
+					int max_score = c_spd.len;
+					const uint32_t max_q = c_spd.q_pos + MAX_sms_overlap_middle;
+					const uint32_t max_t = c_spd.t_pos + MAX_sms_overlap_middle;
+					for (int pi = (int)ci - 1; pi >= 0; pi--) {
+						const DevSms c_pre = base[pi];
+						const int pre_q_ed = c_pre.q_pos + c_pre.len + S_A_KEMR_L - 1;
+						const int pre_t_ed = c_pre.t_pos + c_pre.len + S_A_KEMR_L - 1;
+						if (pre_q_ed > max_q) continue;
+						if (pre_t_ed > max_t) continue;
+						const int indel = c_pre.q_pos - c_pre.t_pos - (max_q - max_t);
+						const int ABS_indel = DSB_ABS(indel);
+						if (ABS_indel > 200) continue;
+						int new_score = c_pre.score + c_spd.len - (ABS_indel >> 3);
+						if (pre_q_ed > c_spd.q_pos || pre_t_ed > c_spd.t_pos) {
+							const int overlap_q = pre_q_ed - c_spd.q_pos;
+							const int overlap_t = pre_t_ed - c_spd.t_pos;
+							new_score -= DSB_MAX(overlap_q, overlap_t);
+						}
+						max_score = DSB_MAX(max_score, new_score);
+					}
+					score = DSB_MAX(max_score, score);
+					base[ci].score = max_score;
+				}
+			}
+		} else
+			score += ca.mtch_len - S_A_KEMR_L + 1;
+		c_a = pre_a;
+	}
+	return score - 10000;
+}
+
+__device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, const KIdx &kx, int chain_ID, uint32_t l_read, int score_ori)
+{   // cly.c:2532-2677
+	const DevIndex &ix = *S.ix;
+	DevChain *c_st = S.ws.chain;
+	DevSms *sms = S.ws.sms;
+	score_ori += 10000;
+	int total_max_score = score_ori;
+	int max_sms_id = 0;
+	int combined = 0;
+	refwin_zero(S, 1064);
+	{ const DevChain ch = c_st[chain_ID]; sms[0].score = score_ori; sms[0].q_pos = ch.q_ed; sms[0].t_pos = ch.t_ed; sms[0].len = 1 - S_A_KEMR_L; }
+	S.n_sms = 1;
+	uint32_t current_sms = 1;
+	const ulonglong2 ri = __ldg(ix.ref_info + c_st[chain_ID].ref_ID);
+	const uint64_t t_offset_global = ri.y, t_length = ri.x;
+	uint32_t c_t_offset = c_st[chain_ID].t_ed - 3;
+	int last_search = 0;
+	while (1) {
+		if (S.n_sms == current_sms) {
+			const DevChain ch = c_st[chain_ID];
+			const uint32_t next_step = (uint32_t)(t_length - c_t_offset);
+			if (next_step < MIN_SCORE_MEM) break;
+			uint32_t max_search_ref;
+			if (l_read - ch.q_ed < 600) {
+				if (last_search == 1) break;
+				last_search = 1;
+				max_search_ref = l_read - ch.q_ed + 60;
+			} else
+				max_search_ref = (uint32_t)(t_length - c_t_offset);
+			max_search_ref = DSB_MIN(600, max_search_ref);
+			__syncwarp();
+			CNT_GETREF(S, max_search_ref + OVER_SEARCH_M2); get_ref_coop(ix, S.sm->refwin, c_t_offset + t_offset_global, max_search_ref + OVER_SEARCH_M2, true);
+			int search_q_ed = (int)sms[max_sms_id].q_pos + 1000;
+			search_q_ed = DSB_MIN(search_q_ed, l_read);
+			const int search_q_st = DSB_MAX(search_q_ed - 2000, ch.q_st - 8);
+			sdp_match(S, search_q_st, search_q_ed, q_str, S.sm->refwin, max_search_ref, kx, c_t_offset, true);
+			if (S.error) return 0;
+			c_t_offset += max_search_ref - S_A_KEMR_L - 3;
+			if (S.n_sms == current_sms) break;
+			if (sms[current_sms].t_pos > sms[max_sms_id].t_pos + 1000) break;
+		}
+		const uint32_t ci = current_sms++;
+		const DevSms c_sms = sms[ci];
+		int max_score = c_sms.len;
+		const uint32_t max_pre_q = c_sms.q_pos + MAX_sms_overlap;
+		const uint32_t max_pre_t = c_sms.t_pos + MAX_sms_overlap;
+		for (int pi = (int)current_sms - 2; pi >= 0; pi--) {
+			const DevSms c_pre = sms[pi];
+			const int pre_q_ed = c_pre.q_pos + c_pre.len + S_A_KEMR_L - 1;
+			const int pre_t_ed = c_pre.t_pos + c_pre.len + S_A_KEMR_L - 1;
+			if (pre_q_ed > max_pre_q) continue;
+			if (pre_t_ed > max_pre_t) continue;
+			if (c_pre.t_pos + 600 < max_pre_t) break;
+			const int indel = c_pre.q_pos - c_pre.t_pos - (max_pre_q - max_pre_t);
+			const int ABS_indel = DSB_ABS(indel);
+			if (ABS_indel > 200) continue;
+			int new_score = c_pre.score + c_sms.len - (ABS_indel >> 3);
+			if (pre_q_ed > c_sms.q_pos || pre_t_ed > c_sms.t_pos) {
+				const int overlap_q = pre_q_ed - c_sms.q_pos;
+				const int overlap_t = pre_t_ed - c_sms.t_pos;
+				new_score -= DSB_MAX(overlap_q, overlap_t);
+			}
+			max_score = DSB_MAX(max_score, new_score);
+		}
+		sms[ci].score = max_score;
+		if (c_sms.len >= 8 && combine_chain(S, chain_ID, c_sms.t_pos - c_sms.q_pos, 0, c_sms.q_pos, &combined) == 1) {
+			total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2(S, c_st[combined].cur, q_str, kx);
+			if (S.error) return 0;
+			score_ori = total_max_score;
+			max_sms_id = 0;
+			const DevChain ch = c_st[chain_ID];
+			sms[0].score = total_max_score; sms[0].q_pos = ch.q_ed; sms[0].t_pos = ch.t_ed; sms[0].len = -S_A_KEMR_L;
+			S.n_sms = 1;
+			current_sms = 1;
+			c_t_offset = ch.t_ed;
+			continue;
+		}
+		if (total_max_score < max_score) { total_max_score = max_score; max_sms_id = current_sms - 1; }
+		if (c_sms.t_pos > sms[max_sms_id].t_pos + 1000) break;
+	}
+	c_st[chain_ID].q_ed = sms[max_sms_id].q_pos + sms[max_sms_id].len + S_A_KEMR_L;
+	c_st[chain_ID].t_ed = sms[max_sms_id].t_pos + sms[max_sms_id].len + S_A_KEMR_L;
+	return total_max_score - 10000;
+}
+
+__device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, const KIdx &kx, int chain_ID, int score_ori)
+{   // cly.c:2679-2819
+	const DevIndex &ix = *S.ix;
+	DevChain *c_st = S.ws.chain;
+	DevSms *sms = S.ws.sms;
+	score_ori += 10000;
+	int total_max_score = score_ori;
+	int max_sms_id = 0;
+	int combined = 0;
+	refwin_zero(S, 1064);
+	{ const DevChain ch = c_st[chain_ID]; sms[0].score = score_ori; sms[0].q_pos = ch.q_st; sms[0].t_pos = ch.t_st; }
+	S.n_sms = 1;
+	uint32_t current_sms = 1;
+	const uint64_t t_offset_global = __ldg(ix.ref_info + c_st[chain_ID].ref_ID).y;
+	uint32_t c_t_offset = c_st[chain_ID].t_st + 3;
+	int last_search = 0;
+	while (1) {
+		if (S.n_sms == current_sms) {
+			const DevChain ch = c_st[chain_ID];
+			const uint32_t next_step = c_t_offset;
+			if (next_step < MIN_SCORE_MEM) break;
+			uint32_t max_search_ref;
+			if (ch.q_st < 600) {
+				if (last_search == 1) break;
+				last_search = 1;
+				max_search_ref = ch.q_st + 60;
+			} else
+				max_search_ref = c_t_offset;
+			max_search_ref = DSB_MIN(600, max_search_ref);
+			__syncwarp();
+			if (t_offset_global == 0 && c_t_offset < OVER_SEARCH_M2 + max_search_ref)
+				{ CNT_GETREF(S, max_search_ref); get_ref_coop(ix, S.sm->refwin, (int64_t)(c_t_offset + t_offset_global - max_search_ref), max_search_ref, true); }
+			else
+				{ CNT_GETREF(S, max_search_ref + OVER_SEARCH_M2); get_ref_coop(ix, S.sm->refwin, (int64_t)(c_t_offset + t_offset_global - max_search_ref - OVER_SEARCH_M2), max_search_ref + OVER_SEARCH_M2, true); }
+			int search_q_st = (int)sms[max_sms_id].q_pos - 1000;
+			search_q_st = DSB_MAX(search_q_st, 0);
+			const int search_q_ed = DSB_MIN(search_q_st + 2000, ch.q_st - 1);
+			sdp_match(S, search_q_st, search_q_ed, q_str, S.sm->refwin + OVER_SEARCH_M2, max_search_ref, kx, c_t_offset - max_search_ref, false);
+			if (S.error) return 0;
+			c_t_offset = c_t_offset - max_search_ref + S_A_KEMR_L + 3;
+			if (S.n_sms == current_sms) break;
+			if (sms[current_sms].t_pos + 1000 < sms[max_sms_id].t_pos) break;
+		}
+		const uint32_t ci = current_sms++;
+		const DevSms c_sms = sms[ci];
+		int max_score = c_sms.len;
+		const uint32_t min_pre_q = c_sms.q_pos + c_sms.len - MAX_sms_overlap + S_A_KEMR_L - 1;
+		const uint32_t min_pre_t = c_sms.t_pos + c_sms.len - MAX_sms_overlap + S_A_KEMR_L - 1;
+		for (int pi = (int)current_sms - 2; pi >= 0; pi--) {
+			const DevSms c_pre = sms[pi];
+			if (c_pre.q_pos < min_pre_q) continue;
+			if (c_pre.t_pos < min_pre_t) continue;
+			if (min_pre_t + 600 < c_pre.t_pos) break;
+			const int indel = c_pre.q_pos - c_pre.t_pos - (min_pre_q - min_pre_t);
+			const int ABS_indel = DSB_ABS(indel);
+			if (ABS_indel > 200) continue;
+			int new_score = c_pre.score + c_sms.len - (ABS_indel >> 3);
+			if (min_pre_q + MAX_sms_overlap > c_pre.q_pos || min_pre_t + MAX_sms_overlap > c_pre.t_pos) {
+				const int overlap_q = min_pre_q + MAX_sms_overlap - c_pre.q_pos;
+				const int overlap_t = min_pre_t + MAX_sms_overlap - c_pre.t_pos;
+				new_score -= DSB_MAX(overlap_q, overlap_t);
+			}
+			max_score = DSB_MAX(max_score, new_score);
+		}
+		sms[ci].score = max_score;
+		if (c_sms.len >= 8 && combine_chain(S, chain_ID, c_sms.t_pos - c_sms.q_pos, 1, c_sms.q_pos + c_sms.len, &combined) == 1) {
+			total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2(S, c_st[combined].cur, q_str, kx);
+			if (S.error) return 0;
+			score_ori = total_max_score;
+			max_sms_id = 0;
+			const DevChain ch = c_st[chain_ID];
+			sms[0].score = total_max_score; sms[0].q_pos = ch.q_st; sms[0].t_pos = ch.t_st;
+			S.n_sms = 1;
+			current_sms = 1;
+			c_t_offset = ch.t_st;
+			continue;
+		}
+		if (total_max_score < max_score) { total_max_score = max_score; max_sms_id = current_sms - 1; }
+		if (c_sms.t_pos + 1000 < sms[max_sms_id].t_pos) break;
+	}
+	c_st[chain_ID].q_st = sms[max_sms_id].q_pos;
+	c_st[chain_ID].t_st = sms[max_sms_id].t_pos;
+	return total_max_score - 10000;
+}
+
+struct ChainCmpByPos {          // chain_cmp_by_pos (cly.c:2853-2870)
+	__device__ int operator()(const DevChain &a, const DevChain &b) const {
+		if (a.ref_ID > b.ref_ID) return 1;
+		if (a.ref_ID < b.ref_ID) return -1;
+		if (a.t_st > b.t_st) return 1;
+		if (a.t_st < b.t_st) return -1;
+		if (a.sum_score < b.sum_score) return 1;
+		if (a.sum_score > b.sum_score) return -1;
+		return 0;
+	}
+};
+
+// delete_small_score_rst up to (not including) the max_read_l-dependent filter (cly.c:2883-2957)
+__device__ __noinline__ void score_and_merge(ReadState &S, const SearchDir *search_dir, uint32_t l_read, uint32_t kidx_bits_max)
+{
+	if (S.n_hit == 0) return;
+	DevChain *C = S.ws.chain;
+	if (S.n_hit > 200) {
+		uint32_t rst_num = 200;
+		for (; rst_num < S.n_hit && C[rst_num].sum_score > 50; rst_num++);
+		S.n_hit = rst_num;
+	}
+	S.n_hit = DSB_MIN(400u, S.n_hit);
+	sc_hash_idx(S);
+	// get_score_M2 (cly.c:2821-2849)
+	int both_dir = 0;
+	for (uint32_t i = 0; i < S.n_hit; i++) {
+		both_dir |= (C[i].direction == DSB_FORWARD) ? 0x2 : 0x1;
+		if (both_dir == 3) break;
+	}
+	int key_bits = 10;
+	for (; key_bits < 18; key_bits++) if ((1u << key_bits) >= l_read) break;
+	if ((uint32_t)key_bits > kidx_bits_max) key_bits = kidx_bits_max;
+	for (int c_dir = 2; c_dir >= 1; c_dir--) {
+		if ((c_dir & both_dir) == 0) continue;
+		const uint32_t direction = (c_dir == 1) ? DSB_REVERSE : DSB_FORWARD;
+		const SearchDir *c_sd = ((search_dir->direction == direction) ? 0 : 1) + search_dir;
+		build_kidx(S, c_sd->bin_read, l_read, (c_dir == 2) ? 0 : 1, key_bits);
+	}
+	for (uint32_t i = 0; i < S.n_hit; i++) {
+		if (C[i].sum_score == 0) continue;
+		const uint32_t dir = C[i].direction;
+		const SearchDir *c_sd = ((search_dir->direction == dir) ? 0 : 1) + search_dir;
+		const int slot = (dir == DSB_FORWARD) ? 0 : 1;
+		KIdx kx; kx.start = S.ws.kidx_start[slot]; kx.ent = S.ws.kidx_ent[slot]; kx.kmask = (1u << key_bits) - 1;
+		int score = sdp_middle_M2(S, C[i].cur, c_sd->bin_read, kx);
+		if (S.error) return;
+		score = sdp_right_M2(S, c_sd->bin_read, kx, (int)i, l_read, score);
+		if (S.error) return;
+		score = sdp_left_M2(S, c_sd->bin_read, kx, (int)i, score);
+		if (S.error) return;
+		C[i].sum_score = score;
+	}
+	if (S.n_hit > 1) glibc_msort(C, S.ws.chain_tmp, (int)S.n_hit, ChainCmpByPos());
+	const int n = (int)S.n_hit;
+	for (int ci = 0; ci < n - 1; ci++) {
+		if (C[ci].sum_score == 0) continue;
+		DevChain c_c = C[ci];
+		for (int ni = ci + 1; ni < n; ni++) {
+			DevChain next_c = C[ni];
+			if (c_c.ref_ID == next_c.ref_ID) {
+				if (c_c.direction != next_c.direction) continue;
+				if (next_c.sum_score == 0) continue;
+				if (next_c.t_st < c_c.t_st + 5 && next_c.q_st < c_c.q_st + 5 && next_c.sum_score < c_c.sum_score + 5) {
+					next_c.sum_score = 0; next_c.q_ed = next_c.q_st; next_c.t_ed = next_c.t_st;
+					C[ni] = next_c;
+					continue;
+				}
+				const int dis_t = next_c.t_st - c_c.t_ed;
+				const int dis_q = next_c.q_st - c_c.q_ed;
+				const int dis_t_q = DSB_ABS(dis_t - dis_q);
+				if ((dis_t > -20 && dis_t < 1000 && dis_q > -20 && dis_q < 1000) && dis_t_q < 200) {
+					c_c.t_ed = DSB_MAX(c_c.t_ed, next_c.t_ed);
+					c_c.q_ed = DSB_MAX(c_c.q_ed, next_c.q_ed);
+					c_c.sum_score += next_c.sum_score;
+					next_c.sum_score = 0; next_c.q_ed = next_c.q_st; next_c.t_ed = next_c.t_st;
+					C[ni] = next_c;
+				}
+			} else
+				break;
+		}
+		C[ci] = c_c;
+	}
+}
+
+// ---------------------------------------------------------------- classify_seq (cly.c:3064-3132) up to the class filter
+#define MIN_READ_LEN 40
+__device__ void classify_read(const ClassifyParams &P, ReadState &S, uint32_t r)
+{
+	const uint32_t read_len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
+	S.n_anc = 0; S.n_hit = 0; S.n_sms = 0; S.fast_classify = 1; S.error = 0; S.sp_l = 0;
+	S.c_prefix = S.c_occ = S.c_locate = S.c_getref = S.c_getref_bytes = 0;
+	dsb_read_result out;
+	out.hit_off = 0; out.n_hit = 0; out.n_anchor = 0; out.fast_classify = 1; out.entered_final = 0; out.error = 0; out.read_len = read_len;
+	if (read_len >= MIN_READ_LEN) {
+		SearchDir sd[2];
+		const uint8_t *bin_F = P.bin + P.bin_off[r] + DSB_GUARD;
+		for (int s = 0; s < 2; s++) {
+			sd[s].seed_v = P.seeds[s] + P.seed_off[r];
+			sd[s].l_seed_v = P.n_seeds[s][r];
+			sd[s].bin_read = s ? bin_F + read_len : bin_F;
+			sd[s].direction = s ? DSB_REVERSE : DSB_FORWARD;
+			sd[s].total_score = P.total_score[s][r];
+		}
+		if (sd[0].total_score < sd[1].total_score) { SearchDir t = sd[0]; sd[0] = sd[1]; sd[1] = t; }   // cly.c:1261-1266
+		const bool both_direction = ((sd[0].total_score - sd[1].total_score) <= (sd[0].total_score >> 3));
+		const int super_repeat = 0;                                   // always 0 in the reference (cly.c:849-888,1545)
+		fast_classify(S, sd[0], read_len);
+		if (!S.error && both_direction) fast_classify(S, sd[1], read_len);
+		if (!S.error) {
+			resolve_tree(S);
+			bool run_slow_mode = false;
+			if (S.n_hit <= 0) run_slow_mode = true;
+			else if (S.ws.chain[0].anchor_number < 5 && super_repeat < 3) {
+				run_slow_mode = true;
+				if (read_len <= 300 && S.ws.chain[0].sum_score > 200) run_slow_mode = false;
+			}
+			if (run_slow_mode) {
+				S.n_anc = 0;
+				slow_classify(S, sd[0], read_len);
+				if (!S.error) {
+					resolve_tree(S);
+					if (both_direction || S.n_hit <= 0 || (S.ws.chain[0].anchor_number < 5 && super_repeat < 3)) {
+						slow_classify(S, sd[1], read_len);
+						if (!S.error) resolve_tree(S);
+					}
+				}
+			}
+		}
+		if (!S.error) {
+			out.entered_final = (S.n_hit != 0);
+			score_and_merge(S, sd, read_len, P.kidx_bits_max);
+		}
+	}
+	out.n_anchor = S.n_anc;
+	out.fast_classify = (uint8_t)S.fast_classify;
+	if (S.error) { out.error = (uint16_t)S.error; out.n_hit = 0; out.entered_final = 0; S.n_hit = 0; }
+	// hand the pre-filter chains to the finalize kernel: reserve 2*n slots (second half = merge-sort scratch)
+	unsigned long long off = 0;
+	if (S.n_hit) {
+		if (lane_id() == 0) off = atomicAdd(P.hits_cursor, (unsigned long long)(2 * S.n_hit));
+		off = __shfl_sync(DSB_FULL, off, 0);
+		if (off + 2ull * S.n_hit > P.hits_cap) { out.error = 4; S.n_hit = 0; }
+	}
+	out.hit_off = off; out.n_hit = S.n_hit;
+	for (uint32_t i = lane_id(); i < S.n_hit; i += 32) {
+		const DevChain c = S.ws.chain[i];
+		dsb_hit h;
+		h.ref_ID = c.ref_ID; h.t_st = c.t_st; h.t_ed = c.t_ed; h.q_st = c.q_st; h.q_ed = c.q_ed;
+		h.sum_score = c.sum_score; h.indel = c.indel; h.direction = c.direction; h.primary = 0; h.pri_index = 0; h.pad = 0;
+		P.hits[off + i] = h;
+	}
+	if (lane_id() == 0) P.rr[r] = out;
+	__syncwarp();
+}

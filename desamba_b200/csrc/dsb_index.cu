@@ -1,0 +1,212 @@
+// dsb_index.cu -- index loader: reads the reference's unchanged on-disk index (load_idx idx.c:1103-1160, load_bwt
+// bwt.c:68-104, set_ekmer_par idx.c:966-982, calculate_MAPQ_TABLE cly_mt.c:413-437) and makes it resident in one
+// GPU's HBM.  The FM-index blocks are re-cut at load time (see dsb_device.cuh); every other array is uploaded as is.
+#include "dsb_internal.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <cmath>
+
+static thread_local char g_err[512] = "";
+void dsb_set_error(const char *fmt, ...)
+{
+	va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+}
+extern "C" const char *dsb_last_error(void) { return g_err; }
+extern "C" const char *dsb_version(void) { return "desamba_b200 0.1 (sm_100a)"; }
+
+namespace {
+
+struct HostFile {
+	FILE *f; std::string path;
+	HostFile(const char *dir, const char *ext) { path = std::string(dir) + "/deSAMBA" + ext; f = fopen(path.c_str(), "rb"); }
+	~HostFile() { if (f) fclose(f); }
+	bool rd(void *p, size_t n) { return f && fread(p, 1, n, f) == n; }
+};
+
+// upload a host array, remember the allocation; `extra` zero bytes are appended
+int upload(dsb_index *ix, const void *h, size_t bytes, size_t extra, void **d_out)
+{
+	void *d = nullptr;
+	DSB_CUDA(cudaMalloc(&d, bytes + extra + 16));
+	ix->allocs.push_back(d);
+	ix->hbm_bytes += bytes + extra + 16;
+	DSB_CUDA(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice));
+	DSB_CUDA(cudaMemset((char *)d + bytes, 0, extra + 16));
+	*d_out = d;
+	return DSB_OK;
+}
+
+// read `<u64 n> n*elem bytes` (or, with have_n, n*elem bytes without a header) and upload
+int load_array(dsb_index *ix, const char *dir, const char *ext, size_t elem, bool header, uint64_t *n_io, size_t extra,
+               void **d_out, std::vector<uint8_t> *keep = nullptr)
+{
+	HostFile hf(dir, ext);
+	if (!hf.f) { dsb_set_error("cannot open %s", hf.path.c_str()); return DSB_E_IO; }
+	if (header && !hf.rd(n_io, 8)) { dsb_set_error("short read %s", hf.path.c_str()); return DSB_E_IO; }
+	const size_t bytes = (size_t)(*n_io) * elem;
+	std::vector<uint8_t> local;
+	std::vector<uint8_t> &buf = keep ? *keep : local;
+	buf.resize(bytes);
+	if (!hf.rd(buf.data(), bytes)) { dsb_set_error("short read %s", hf.path.c_str()); return DSB_E_IO; }
+	return upload(ix, buf.data(), bytes, extra, d_out);
+}
+
+inline void nib_counts(const uint8_t *p, int nbytes, uint64_t cnt[5])
+{
+	for (int i = 0; i < nbytes; i++) {
+		const uint8_t lo = p[i] & 0xf, hi = p[i] >> 4;
+		if (lo < 5) cnt[lo]++;
+		if (hi < 5) cnt[hi]++;
+	}
+}
+
+} // namespace
+
+extern "C" int dsb_index_load(const char *dir, int device, dsb_index **out)
+{
+	if (!dir || !out) { dsb_set_error("dsb_index_load: null argument"); return DSB_E_ARG; }
+	*out = nullptr;
+	int n_dev = 0;
+	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { dsb_set_error("no CUDA device (there is no CPU fallback)"); return DSB_E_CUDA; }
+	if (device < 0 || device >= n_dev) { dsb_set_error("device %d out of range (%d devices)", device, n_dev); return DSB_E_ARG; }
+	DSB_CUDA(cudaSetDevice(device));
+	dsb_index *ix = new dsb_index();
+	ix->device = device; ix->hbm_bytes = 0;
+	memset(&ix->dev, 0, sizeof ix->dev);
+	int rc = DSB_OK;
+	do {
+		// ---- .bwt: u64 byteLen | occ blocks | u64 rank[5] | u64 hash_index[4^13+1]   (bwt.c:75-85)
+		{
+			HostFile hf(dir, ".bwt");
+			uint64_t byteLen = 0;
+			if (!hf.f || !hf.rd(&byteLen, 8) || byteLen % 168 != 0) { dsb_set_error("cannot read %s", hf.path.c_str()); rc = DSB_E_IO; break; }
+			std::vector<uint8_t> blocks(byteLen);
+			if (!hf.rd(blocks.data(), byteLen)) { dsb_set_error("short read %s", hf.path.c_str()); rc = DSB_E_IO; break; }
+			uint64_t rank[6];
+			if (!hf.rd(rank, 40)) { dsb_set_error("short read %s", hf.path.c_str()); rc = DSB_E_IO; break; }
+			rank[5] = rank[0] - 1;                                     // bwt.c:81
+			memcpy(ix->dev.rank, rank, sizeof rank);
+			const uint64_t nb = byteLen / 168;
+			ix->bwt_len_blocks = nb;
+			// re-cut: 168-B blocks of 256 symbols -> 128-B lines of 128 symbols (+1 trailing line holding the totals,
+			// so that occ(len_bwt, c) is defined when len_bwt % 256 == 0; the reference reads past its array there)
+			const uint64_t n_lines = nb * 2 + 1;
+			std::vector<uint8_t> lines(n_lines * 128, 0);
+			uint64_t tot[5] = {0, 0, 0, 0, 0};
+			for (uint64_t b = 0; b < nb; b++) {
+				const uint8_t *src = blocks.data() + b * 168;
+				uint64_t cnt[5];
+				memcpy(cnt, src, 40);
+				uint8_t *l0 = lines.data() + (2 * b) * 128, *l1 = l0 + 128;
+				memcpy(l0, cnt, 40); memcpy(l0 + 64, src + 40, 64);
+				nib_counts(src + 40, 64, cnt);
+				memcpy(l1, cnt, 40); memcpy(l1 + 64, src + 40 + 64, 64);
+				nib_counts(src + 40 + 64, 64, cnt);
+				memcpy(tot, cnt, 40);
+			}
+			memcpy(lines.data() + (n_lines - 1) * 128, tot, 40);
+			memset(lines.data() + (n_lines - 1) * 128 + 64, 0xff, 64);
+			blocks.clear(); blocks.shrink_to_fit();
+			void *d = nullptr;
+			if ((rc = upload(ix, lines.data(), lines.size(), 128, &d)) != DSB_OK) break;
+			ix->dev.occ = (const uint8_t *)d; ix->dev.n_lines = n_lines;
+			lines.clear(); lines.shrink_to_fit();
+			const uint64_t nh = (1ull << 26) + 1;
+			std::vector<uint64_t> hidx(nh);
+			if (!hf.rd(hidx.data(), nh * 8)) { dsb_set_error("short read %s (prefix table)", hf.path.c_str()); rc = DSB_E_IO; break; }
+			if ((rc = upload(ix, hidx.data(), nh * 8, 0, &d)) != DSB_OK) break;
+			ix->dev.prefix = (const uint64_t *)d;
+		}
+		void *d = nullptr;
+		// ---- .sa (bwt.c:95-98)
+		if ((rc = load_array(ix, dir, ".sa", 8, true, &ix->sa_size, 0, &d)) != DSB_OK) break;
+		ix->dev.sa = (const uint2 *)d;
+		// ---- exist k-mer tables (idx.c:1105-1118) + set_ekmer_par (idx.c:966-982)
+		{
+			HostFile hf(dir, ".exki");
+			if (!hf.f || !hf.rd(&ix->ek_size, 8)) { dsb_set_error("cannot read %s", hf.path.c_str()); rc = DSB_E_IO; break; }
+			uint64_t mask = (1ull << 37) - 1; int l_ek = 20;
+			switch (ix->ek_size >> 27) {
+				case 1:   mask = (1ull << 30) - 1; l_ek = 16; break;
+				case 2:   mask = (1ull << 31) - 1; l_ek = 17; break;
+				case 4:   mask = (1ull << 32) - 1; l_ek = 17; break;
+				case 8:   mask = (1ull << 33) - 1; l_ek = 18; break;
+				case 16:  mask = (1ull << 34) - 1; l_ek = 18; break;
+				case 32:  mask = (1ull << 35) - 1; l_ek = 19; break;
+				case 64:  mask = (1ull << 36) - 1; l_ek = 19; break;
+				case 128: mask = (1ull << 37) - 1; l_ek = 20; break;
+			}
+			ix->dev.ek_mask = mask; ix->dev.l_ek = l_ek;
+			ix->dev.single_base_max = (int)(0.8 * l_ek);
+		}
+		{ uint64_t n = ix->ek_size; if ((rc = load_array(ix, dir, ".exk0", 1, false, &n, 0, &d)) != DSB_OK) break; ix->dev.ek0 = (const uint8_t *)d; }
+		{ uint64_t n = ix->ek_size; if ((rc = load_array(ix, dir, ".exk1", 1, false, &n, 0, &d)) != DSB_OK) break; ix->dev.ek1 = (const uint8_t *)d; }
+		// ---- .unv + fabricated sentinel (idx.c:1123-1129)
+		{
+			HostFile hf(dir, ".unv");
+			if (!hf.f || !hf.rd(&ix->n_uni, 8) || ix->n_uni < 2) { dsb_set_error("cannot read %s", hf.path.c_str()); rc = DSB_E_IO; break; }
+			std::vector<uint32_t> u((ix->n_uni + 1) * 2);
+			if (!hf.rd(u.data(), ix->n_uni * 8)) { dsb_set_error("short read %s", hf.path.c_str()); rc = DSB_E_IO; break; }
+			u[ix->n_uni * 2] = u[(ix->n_uni - 1) * 2] + 1 + u[(ix->n_uni - 1) * 2 + 1];
+			u[ix->n_uni * 2 + 1] = 0;
+			ix->dev.dollar_pos = ix->n_uni - 1 - 1;                    // idx.c:1128
+			if ((rc = upload(ix, u.data(), u.size() * 4, 64, &d)) != DSB_OK) break;
+			ix->dev.uni = (const uint2 *)d; ix->dev.n_uni = ix->n_uni;
+		}
+		// ---- .ref_b (idx.c:1141-1145); 1 KiB of zero slack behind it for windows that run past the last base
+		if ((rc = load_array(ix, dir, ".ref_b", 1, true, &ix->ref_bin_n, 1024, &d)) != DSB_OK) break;
+		ix->dev.ref_bin = (const uint8_t *)d; ix->dev.ref_bin_n = ix->ref_bin_n;
+		// ---- .ref_i (idx.c:1148-1152): host copy for the writers, {seq_l, seq_offset} on the device
+		{
+			HostFile hf(dir, ".ref_i");
+			uint64_t n = 0;
+			if (!hf.f || !hf.rd(&n, 8)) { dsb_set_error("cannot read %s", hf.path.c_str()); rc = DSB_E_IO; break; }
+			ix->ref_info.resize(n);
+			if (!hf.rd(ix->ref_info.data(), n * sizeof(dsb_ref_info))) { dsb_set_error("short read %s", hf.path.c_str()); rc = DSB_E_IO; break; }
+			std::vector<uint64_t> ri(n * 2);
+			for (uint64_t i = 0; i < n; i++) { ix->ref_info[i].name[127] = 0; ri[2 * i] = ix->ref_info[i].seq_l; ri[2 * i + 1] = ix->ref_info[i].seq_offset; }
+			if ((rc = upload(ix, ri.data(), n * 16, 0, &d)) != DSB_OK) break;
+			ix->dev.ref_info = (const ulonglong2 *)d;
+		}
+		// ---- .ref_p (idx.c:1155-1159)
+		if ((rc = load_array(ix, dir, ".ref_p", 8, true, &ix->n_rp, 0, &d)) != DSB_OK) break;
+		ix->dev.ref_pos = (const uint64_t *)d;
+		// ---- MAPQ tables: the reference's expressions evaluated in double and truncated to int (cly_mt.c:413-437),
+		//      P_E = 0.15, L_REF = ref_bin.n * 4 (cly_mt.c:527).  Q_MEM is continued past 2000 entries so that the
+		//      device never indexes outside the table (the reference leaves l_m >= 2000 unchecked).
+		{
+			const double P_E = 0.15; const uint64_t L_REF = ix->ref_bin_n * 4;
+			const double REF_SIZE_PUNALTY = -10 * log(L_REF) / log(10);
+			const double MATCH_SCORE = -10 * log(0.25 / (1 - P_E)) / log(10);
+			const double MISMATCH_PUNALTY = -10 * log(0.75 / (P_E)) / log(10);
+			std::vector<int> q(65536 + 400);
+			for (int i = 0; i < 65536; i++) q[i] = REF_SIZE_PUNALTY + i * MATCH_SCORE + 0.5;
+			int *lv = q.data() + 65536;
+			for (int j = 0; j < 20; j++)
+				for (int i = 0; i < 20; i++) {
+					int v = (j - i) * MATCH_SCORE + i * MISMATCH_PUNALTY + 0.5;
+					if (j < 5) v += 15;
+					lv[i * 20 + j] = v > -8 ? v : -8;
+				}
+			if ((rc = upload(ix, q.data(), q.size() * 4, 0, &d)) != DSB_OK) break;
+			ix->dev.q_mem = (const int *)d; ix->dev.q_lv = (const int *)d + 65536;
+		}
+	} while (0);
+	if (rc != DSB_OK) { dsb_index_free(ix); return rc; }
+	*out = ix;
+	return DSB_OK;
+}
+
+extern "C" void dsb_index_free(dsb_index *ix)
+{
+	if (!ix) return;
+	cudaSetDevice(ix->device);
+	for (void *p : ix->allocs) cudaFree(p);
+	delete ix;
+}
+extern "C" uint64_t dsb_index_n_ref(const dsb_index *ix) { return ix ? ix->ref_info.size() : 0; }
+extern "C" const dsb_ref_info *dsb_index_ref_info(const dsb_index *ix) { return ix ? ix->ref_info.data() : nullptr; }
+extern "C" uint64_t dsb_index_hbm_bytes(const dsb_index *ix) { return ix ? ix->hbm_bytes : 0; }
+extern "C" int dsb_index_l_ek(const dsb_index *ix) { return ix ? ix->dev.l_ek : 0; }

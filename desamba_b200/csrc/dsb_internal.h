@@ -1,0 +1,68 @@
+// dsb_internal.h -- host-side objects behind the C ABI (include/desamba_b200.h).
+#pragma once
+#include "../../include/desamba_b200.h"
+#include "dsb_device.cuh"
+#include <cuda_runtime.h>
+#include <vector>
+#include <string>
+
+void dsb_set_error(const char *fmt, ...);
+#define DSB_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	dsb_set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return DSB_E_CUDA; } } while (0)
+
+struct dsb_index {
+	int device;
+	DevIndex dev;                       // device pointers + scalars, passed to kernels by value
+	std::vector<void *> allocs;         // every cudaMalloc of this index
+	uint64_t hbm_bytes;
+	std::vector<dsb_ref_info> ref_info; // host copy of .ref_i for the writers
+	uint64_t ref_bin_n;                 // bytes of .ref_b (L_REF = 4 * this, cly_mt.c:527)
+	uint64_t bwt_len_blocks;            // reference occ blocks (256 symbols each)
+	uint64_t n_uni, n_rp, sa_size, ek_size;
+};
+
+struct DevBuf {                         // grow-only device buffer
+	void *p; size_t cap;
+	DevBuf() : p(nullptr), cap(0) {}
+};
+
+struct dsb_ctx {
+	dsb_index *ix;
+	dsb_opts opts;
+	cudaStream_t stream;
+	int n_sm, n_warps;                  // resident classify warps = n_sm * warps_per_sm
+	// batch inputs (device)
+	DevBuf seqs, read_off, bin_off, bits_off, seed_off, tiles, bin, bits, seeds[2], n_seeds[2], total_score[2];
+	// classify scratch + outputs
+	DevBuf scratch, rr, hits, counters;
+	uint64_t scratch_stride; uint32_t kidx_bits, kidx_len;
+	uint64_t hits_cap;
+	// pinned staging
+	void *h_pin; size_t h_pin_cap;
+	// batch state
+	uint32_t n_reads, n_tiles; uint64_t n_bases, bits_words, seed_slots, bin_bytes; uint32_t max_len;
+	std::vector<uint64_t> h_off;        // host copies of the per-read offset tables
+	std::vector<uint64_t> h_bits_off;
+	std::vector<uint32_t> h_seed_off;
+	cudaEvent_t ev[6];
+	float kernel_ms[4];
+	int launches;
+	bool ran;
+};
+
+// device-side batch counters (one block of u64 in ctx->counters)
+enum {
+	DSB_CNT_HITS_CURSOR = 0,   // next free slot in hits
+	DSB_CNT_WORK,              // classify work counter
+	DSB_CNT_FIRST_LONG,        // min read index with entered_final && read_len >= 510 (init: ~0)
+	DSB_CNT_MAX_READ_L,        // max read_len over entered_final reads
+	DSB_CNT_N_BIT0,            // algorithmic counters: get_exist_kmer calls with k-mer != 0
+	DSB_CNT_N_BIT1,            //   table-1 probes (table-0 hit)
+	DSB_CNT_N_PREFIX,          //   prefix-table lookups (bwt_MEM_search calls)
+	DSB_CNT_N_OCC,             //   occ calls
+	DSB_CNT_N_LOCATE,          //   get_uni calls
+	DSB_CNT_N_GETREF,          //   get_ref calls
+	DSB_CNT_N_GETREF_BYTES,    //   packed reference bytes those calls cover
+	DSB_CNT_N_ERRORS,          // reads that hit a capacity
+	DSB_CNT_COUNT = 16
+};

@@ -46,7 +46,7 @@
 #define MIN_SCORE_MEM 12
 #define NO_SA 0xFFFFFFFFFFFFFFFFull
 
-orc_counters orc_cnt;
+__thread orc_counters orc_cnt;   /* per thread: the multi-threaded timing run must not share a counter cache line */
 
 /* ------------------------------------------------------------------ index loading (idx.c:1103-1160, bwt.c:68-104) */
 static void *slurp(const char *dir, const char *ext, size_t skip_hdr, uint64_t *hdr, size_t elem, size_t extra_elems)

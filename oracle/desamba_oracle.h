@@ -83,7 +83,7 @@ typedef struct orc_buff orc_buff;   /* per-thread scratch (Classify_buff_pool, c
 typedef struct {
 	uint64_t n_bit0, n_bit1, n_prefix, n_occ, n_locate, n_getref, n_getref_bytes, n_reads, n_bases, n_hits;
 } orc_counters;
-extern orc_counters orc_cnt;
+extern __thread orc_counters orc_cnt;
 
 int  orc_index_load(orc_index *ix, const char *dir);          /* idx.c:1103-1160 + bwt.c:68-104 */
 void orc_index_free(orc_index *ix);

@@ -1,0 +1,31 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE (oracle).  Regenerates tests/golden/*: outputs of the UNMODIFIED reference (oracle/_ref/deSAMBA_zero =
+# reference sources + -ftrivial-auto-var-init=zero, run -t 1: the parity oracle O_def of SURVEY.md 8c; and deSAMBA_stock -t 4
+# for the demo) on the demo reads and on small deterministic synthetic sets (desamba_b200/bin/simreads, seeds below).
+# Needs oracle/_ref (oracle/build_ref.sh + oracle/build_index.sh, i.e. /root/reference present).  Outputs are gzip'd text.
+set -euo pipefail
+HERE=$(cd "$(dirname "$0")" && pwd); ROOT=$(dirname "$HERE")
+R=$HERE/_ref; G=$ROOT/tests/golden; SIM=$ROOT/desamba_b200/bin/simreads
+IDX=$R/demo/idx; FA=$R/demo/viral-gs.fa
+mkdir -p "$G" "$R/sets"
+[ -s "$IDX/deSAMBA.bwt" ] || "$HERE/build_index.sh" "$FA" "$IDX"
+# name mode n err seed
+gen() { [ -s "$R/sets/$1.fq" ] || "$SIM" "$2" "$FA" "$3" "$4" "$5" "$R/sets/$1.fq"; }
+gen long10  long  300  0.10 20261020
+gen long30  long  300  0.30 20261021
+gen short1  short 5000 0.01 20261022
+[ -s "$R/sets/mixed.fq" ] || "$SIM" mixed "$FA" 150 1500 20261024 "$R/sets/mixed.fq"
+run() { # set fmt extra-opts tag
+  "$R/deSAMBA_zero" classify -t 1 -f "$2" $3 "$IDX" "$R/sets/$1.fq" -o "$G/$1$4.$2" 2>/dev/null; gzip -9nf "$G/$1$4.$2"; }
+for s in long10 long30 short1 mixed; do run $s DES_FULL "" ""; run $s SAM "" ""; done
+run long10 SAM "-l 100 -s 40 -r 2" ".l100s40r2"
+for f in SAM SAM_FULL DES DES_FULL; do
+  "$R/deSAMBA_stock" classify -t 4 -f $f "$IDX" "$R/demo/ERR1050068.fastq" -o "$G/demo.$f" 2>/dev/null
+  "$R/deSAMBA_zero" classify -t 1 -f $f "$IDX" "$R/demo/ERR1050068.fastq" -o "$G/demo.zero.$f" 2>/dev/null
+  cmp "$G/demo.$f" "$G/demo.zero.$f"; rm "$G/demo.zero.$f"
+done
+md5sum "$G"/demo.* | sed "s#$G/##" > "$G/demo.md5"
+rm "$G/demo.SAM_FULL" "$G/demo.DES"           # md5 only (SAM_FULL repeats the 2 MB of reads; DES == DES_FULL on this set)
+gzip -9nf "$G/demo.SAM" "$G/demo.DES_FULL"
+md5sum "$R"/sets/*.fq "$R/demo/ERR1050068.fastq" "$FA" | sed "s#$R/##" > "$G/inputs.md5"
+ls -la "$G"
