@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(128) k_islands(const __grid_constant__ IslandP
 				dsb_seed sd; sd.offset = s ? (n - offset - l) : offset; sd.len = (uint16_t)l; sd.top = 0; sd.pad = 0;
 				out[n_seed] = sd;
 				// top labelling (cly.c:1174-1226); the window position is the mirrored offset for the reverse strand
-				if (offset < index_end) { if (max_length < l) { max_length = l; max_index = n_seed; } }
+				if (offset < index_end) { if (max_length < l) { max_length = l; max_index = n_seed; } out[max_index].top = 0; }   // (un-marks seed 0 when it was marked as its own predecessor)
 				else { out[max_index].top = 1; index_end += 100; total += max_length; max_index = n_seed; max_length = l; }
 				n_seed++;
 				i = offset + l;

@@ -17,3 +17,5 @@ rm -f "$OUT/database.jdb"
 "$R/deSAMBA_stock" index "$OUT/kmer.srt" "$FA" "$OUT" >&2
 rm -f "$OUT/kmer.srt"
 ls -la "$OUT" >&2
+# the raw index directory is git- and gpurun-ignored (0.8 GB); the GPU box gets this archive (tests/oracle_binding.py unpacks it)
+[ "$(basename "$OUT")" = idx ] && (cd "$(dirname "$OUT")" && tar cf - idx | gzip -1 > idx.tgz) || true

@@ -29,6 +29,18 @@ def build():
     subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True)
 
 
+def ensure_demo_index():
+    """The demo index (built by the unmodified reference, oracle/build_index.sh) travels to the GPU box as
+    oracle/_ref/demo/idx.tgz (the raw directory is 0.8 GB, mostly the fixed 512 MiB prefix table); unpack on first use."""
+    if os.path.exists(os.path.join(DEMO_IDX, "deSAMBA.bwt")):
+        return DEMO_IDX
+    tgz = os.path.join(REF_DIR, "demo", "idx.tgz")
+    if not os.path.exists(tgz):
+        raise FileNotFoundError(f"{DEMO_IDX} and {tgz} are both missing: run oracle/build_ref.sh + oracle/build_index.sh where /root/reference exists")
+    subprocess.run(["tar", "xzf", tgz, "-C", os.path.join(REF_DIR, "demo")], check=True)
+    return DEMO_IDX
+
+
 _lib = None
 
 
@@ -57,6 +69,8 @@ COUNTER_NAMES = ["n_hits", "n_reads", "_2", "_3", "n_bit0", "n_bit1", "n_prefix"
 
 class Oracle:
     def __init__(self, index_dir=DEMO_IDX, l_min_match=170, min_score=64):
+        if index_dir == DEMO_IDX:
+            ensure_demo_index()
         self._h = lib().orc_capi_open(os.fsencode(index_dir), l_min_match, min_score)
         if not self._h:
             raise RuntimeError(f"oracle: cannot load index {index_dir}")

@@ -19,6 +19,7 @@ def main():
     def say(*a):
         s = " ".join(str(x) for x in a)
         print(s, flush=True); log.write(s + "\n"); log.flush()
+    ob.ensure_demo_index()
     t0 = time.time()
     ix = dsb.Index(ob.DEMO_IDX, 0)
     say(f"index loaded in {time.time()-t0:.1f}s, HBM {ix.hbm_bytes/1e6:.0f} MB, l_ek {ix.l_ek}")
