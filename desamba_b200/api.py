@@ -201,6 +201,15 @@ class Context:
             self.n_reads = n
             return BatchResult(rr, hits[:used.value], mx.value)
 
+    def classify_into(self, cat, offs, rr, hits, max_read_l_in=0):
+        """dsb_classify_batch with caller-owned (ideally pinned) input and output arrays; returns (n_hit_slots, max_read_l)"""
+        n = len(offs) - 1
+        mx, used = C.c_int32(0), C.c_uint64(0)
+        _check(lib.dsb_classify_batch(self._h, cat.ctypes.data, offs.ctypes.data, n, max_read_l_in, C.byref(mx), rr.ctypes.data,
+                                      hits.ctypes.data, len(hits), C.byref(used)), "dsb_classify_batch")
+        self.n_reads = n
+        return used.value, mx.value
+
     def classify_reads(self, seqs, max_read_l_in=0):
         cat, offs = pack_reads(seqs)
         return self.classify(cat, offs, max_read_l_in)

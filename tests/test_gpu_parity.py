@@ -1,0 +1,199 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C ABI with HOST buffers, against the
+oracle on the same inputs (bit-exact: all arithmetic on the path is integer), against the golden text of the unmodified
+reference through the `deSAMBA-b200 classify` driver, on edge cases, and through size-independent properties."""
+import gzip
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+DRIVER = os.path.join(ROOT, "desamba_b200", "bin", "deSAMBA-b200")
+SETS = {"demo": None, "long10": ("long", 300, 0.10, 20261020), "long30": ("long", 300, 0.30, 20261021),
+        "short1": ("short", 5000, 0.01, 20261022), "mixed": ("mixed", (150, 1500), 0, 20261024)}
+CNT = ("n_bit0", "n_bit1", "n_prefix", "n_occ", "n_locate", "n_getref", "n_getref_bytes")
+
+
+def _set_path(ob, name):
+    return ob.DEMO_FQ if name == "demo" else ob.sim_set(name, *SETS[name])
+
+
+def _assert_same(ob, res, rr_o, hits_o, names=None):
+    bad = ob.compare_results(res.rr, res.hits, rr_o, hits_o, names, max_report=5)
+    assert not bad, "\n".join(bad)
+
+
+def test_native_library_is_loaded(gpu):
+    dsb, ix, ctx = gpu
+    assert any("libdesamba_b200.so" in l for l in open("/proc/self/maps"))
+    assert ix.hbm_bytes > 500e6 and ix.l_ek == 16
+
+
+@pytest.mark.parametrize("name", list(SETS))
+def test_set_parity_against_oracle(gpu, ob, oracle, name):
+    dsb, ix, ctx = gpu
+    names, seqs, _ = ob.read_fastq(_set_path(ob, name))
+    cat, offs = ob.pack(seqs)
+    oracle.counters(reset=True)
+    rr_o, hits_o, mx_o = oracle.classify(cat, offs)
+    cnt_o = oracle.counters()
+    res = ctx.classify(cat, offs)
+    _assert_same(ob, res, rr_o, hits_o, names)
+    assert res.max_read_l == mx_o
+    # kernel-level parity: island seeds of both strands, and the algorithmic counters of every stage
+    for i in range(0, len(seqs), max(1, len(seqs) // 100)):
+        for s in (0, 1):
+            sg, tg = ctx.seeds(i, s)
+            so, to = oracle.seeds(seqs[i], s)
+            assert tg == to and sg.tobytes() == so.tobytes(), (name, i, s)
+    cnt_g = ctx.counters()
+    assert {k: cnt_g[k] for k in CNT} == {k: cnt_o[k] for k in CNT}
+    assert ctx.launches() == 4
+
+
+def _run_driver(args):
+    r = subprocess.run([DRIVER, "classify"] + args, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    return r.stdout
+
+
+@pytest.mark.parametrize("fmt", ["SAM", "SAM_FULL", "DES", "DES_FULL"])
+def test_driver_demo_md5(gpu, ob, demo_index, fmt):
+    # config #1: identical text to `deSAMBA classify -t 4 -f <fmt>` of the unmodified reference
+    want = dict((l.split()[1], l.split()[0]) for l in open(os.path.join(GOLD, "demo.md5")) if len(l.split()) == 2)
+    out = _run_driver(["-t", "4", "-f", fmt, demo_index, ob.DEMO_FQ])
+    assert hashlib.md5(out).hexdigest() == want["demo." + fmt]
+
+
+@pytest.mark.parametrize("name", ["long10", "long30", "short1", "mixed"])
+@pytest.mark.parametrize("fmt,batch", [("SAM", "65536"), ("DES_FULL", "97")])
+def test_driver_sets_text(gpu, ob, demo_index, name, fmt, batch):
+    # small batches (-B 97) exercise the carry of max_read_l between batches (mixed set: short reads after long ones)
+    out = _run_driver(["-f", fmt, "-B", batch, demo_index, _set_path(ob, name)])
+    assert out == gzip.open(os.path.join(GOLD, f"{name}.{fmt}.gz")).read()
+
+
+def test_driver_options_and_gz_input(gpu, ob, demo_index, tmp_path):
+    path = _set_path(ob, "long10")
+    gz = tmp_path / "long10.fq.gz"
+    with open(path, "rb") as f, gzip.open(gz, "wb", compresslevel=1) as g:
+        g.write(f.read())
+    out = _run_driver(["-l", "100", "-s", "40", "-r", "2", "-o", str(tmp_path / "o.sam"), demo_index, str(gz)])
+    assert out == b""
+    assert open(tmp_path / "o.sam", "rb").read() == gzip.open(os.path.join(GOLD, "long10.l100s40r2.SAM.gz")).read()
+
+
+def test_edge_cases(gpu, ob, oracle):
+    dsb, ix, ctx = gpu
+    _, demo, _ = ob.read_fastq(ob.DEMO_FQ, 40)
+    long_read = b"".join(demo)[:5000]
+    rng = np.random.default_rng(11)
+    rnd = lambda n: bytes(rng.choice(list(b"ACGT"), n).tolist())
+    reads = [b"", b"A", rnd(39), rnd(40), rnd(41), b"N" * 200, b"A" * 300, b"ACGT" * 100, demo[0].lower(), demo[1][:55],
+             long_read[:1023], long_read[:1024], long_read[:1025], long_read[:2048], long_read[:2049], long_read[:1039], long_read[:1040],
+             demo[2].replace(b"A", b"N"), demo[3][::-1], rnd(3000)] + demo[4:12]
+    cat, offs = ob.pack(reads)
+    rr_o, hits_o, mx_o = oracle.classify(cat, offs)
+    res = ctx.classify(cat, offs)
+    _assert_same(ob, res, rr_o, hits_o)
+    assert res.max_read_l == mx_o
+    assert int(res.rr["n_hit"][0]) == 0 and int(res.rr["fast_classify"][0]) == 1      # < 40 bp: untouched result (cly.c:3089)
+    # empty batch and a single read
+    e = ctx.classify(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64))
+    assert len(e.rr) == 0 and len(e.hits) == 0
+    one = ctx.classify(*ob.pack([demo[0]]))
+    r1, h1, _ = oracle.classify(*ob.pack([demo[0]]))
+    _assert_same(ob, one, r1, h1)
+
+
+def test_max_read_l_state(gpu, ob, oracle):
+    # Classify_buff_pool.max_read_l (cly.c:2958): short reads are filtered differently once a read >= 510 bp has reached the
+    # filter -- inside a batch (input order) and across batches (max_read_l_in / max_read_l_out)
+    dsb, ix, ctx = gpu
+    _, short, _ = ob.read_fastq(_set_path(ob, "short1"), 300)
+    _, long_, _ = ob.read_fastq(_set_path(ob, "long10"), 3)
+    reads = short[:100] + long_[:1] + short[100:200] + long_[1:] + short[200:]
+    cat, offs = ob.pack(reads)
+    for mx_in in (0, 509, 510, 30000):
+        rr_o, hits_o, mx_o = oracle.classify(cat, offs, mx_in)
+        res = ctx.classify(cat, offs, mx_in)
+        _assert_same(ob, res, rr_o, hits_o)
+        assert res.max_read_l == mx_o
+    # chained batches == one batch
+    whole_rr, whole_hits, _ = oracle.classify(cat, offs, 0)
+    mx, got = 0, []
+    for lo in range(0, len(reads), 64):
+        res = ctx.classify(*ob.pack(reads[lo:lo + 64]), mx)
+        mx = res.max_read_l
+        got += [res.read_hits(i).tobytes() for i in range(len(res.rr))]
+    want = [whole_hits[int(o):int(o) + int(n)].tobytes() for o, n in zip(whole_rr["hit_off"], whole_rr["n_hit"])]
+    assert got == want
+
+
+def test_upload_run_download_equals_classify_batch(gpu, ob):
+    dsb, ix, ctx = gpu
+    _, seqs, _ = ob.read_fastq(_set_path(ob, "long30"), 120)
+    cat, offs = ob.pack(seqs)
+    a = ctx.classify(cat, offs)
+    ctx.upload(cat, offs)
+    for _ in range(2):                        # re-running on inputs resident in HBM is idempotent
+        ctx.run(0)
+        b = ctx.download()
+        assert b.rr.tobytes() != b"" and [b.read_hits(i).tobytes() for i in range(len(seqs))] == [a.read_hits(i).tobytes() for i in range(len(seqs))]
+        assert b.rr["n_anchor"].tolist() == a.rr["n_anchor"].tolist()
+    ms = ctx.kernel_ms()
+    assert all(m >= 0 for m in ms) and ms[2] > 0
+
+
+def test_batch_composition_invariance_large(gpu, ob):
+    # property at a larger size (no oracle): per-read results do not depend on batch composition, order or repetition
+    dsb, ix, ctx = gpu
+    path = ob.sim_set("long10_4k", "long", 4000, 0.10, 20261030)
+    _, seqs, _ = ob.read_fastq(path)
+    cat, offs = ob.pack(seqs)
+    a = ctx.classify(cat, offs, 10**6)
+    ha = [a.read_hits(i).tobytes() for i in range(len(seqs))]
+    assert sum(int(x) for x in a.rr["n_hit"]) > 3000 and not a.rr["error"].any()
+    perm = np.random.default_rng(2).permutation(len(seqs))
+    b = ctx.classify(*ob.pack([seqs[i] for i in perm]), 10**6)
+    assert [b.read_hits(k).tobytes() for k in range(len(seqs))] == [ha[i] for i in perm]
+    assert b.rr["n_anchor"].tolist() == a.rr["n_anchor"][perm].tolist()
+    c = ctx.classify(*ob.pack(seqs[1000:1500]), 10**6)
+    assert [c.read_hits(k).tobytes() for k in range(500)] == ha[1000:1500]
+
+
+def test_sample_of_large_batch_against_oracle(gpu, ob, oracle):
+    dsb, ix, ctx = gpu
+    path = ob.sim_set("short1_50k", "short", 50000, 0.01, 20261031)
+    names, seqs, _ = ob.read_fastq(path)
+    res = ctx.classify(*ob.pack(seqs))
+    idx = list(range(0, len(seqs), 25))
+    rr_o, hits_o, _ = oracle.classify(*ob.pack([seqs[i] for i in idx]))
+    for k, i in enumerate(idx):
+        assert res.read_hits(i).tobytes() == hits_o[int(rr_o["hit_off"][k]):int(rr_o["hit_off"][k]) + int(rr_o["n_hit"][k])].tobytes(), i
+        assert int(res.rr["n_anchor"][i]) == int(rr_o["n_anchor"][k])
+
+
+def test_capacity_is_reported_not_fatal(gpu, ob):
+    dsb, ix, _ = gpu
+    small = dsb.Context(ix, max_anchors=1024, max_matches=1024)
+    _, seqs, _ = ob.read_fastq(_set_path(ob, "long10"), 300)
+    big = max(seqs, key=len)
+    try:
+        res = small.classify(*ob.pack([big * 3]))
+        assert not res.rr["error"].any()
+    except dsb.DsbError as e:
+        assert e.code == -5 and "capacity" in str(e)
+    finally:
+        small.close()
+
+
+def test_gather_microbenchmark(gpu):
+    dsb, _, _ = gpu
+    gbs, ms = dsb.gather_bench(0, 2 << 30, 1 << 26, 1)
+    assert 100 < gbs < 20000 and ms > 0
