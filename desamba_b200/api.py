@@ -61,6 +61,7 @@ _sig("dsb_batch_get_seeds", C.c_int, _vp, C.c_uint32, C.c_int, _vp, C.c_uint32, 
 _sig("dsb_batch_kernel_ms", C.c_int, _vp, C.POINTER(C.c_float * 4))
 _sig("dsb_batch_launches", C.c_int, _vp)
 _sig("dsb_batch_counters", C.c_int, _vp, C.POINTER(C.c_uint64 * 16))
+_sig("dsb_batch_profile", C.c_int, _vp, _vp)
 _sig("dsb_ctx_stream", _vp, _vp)
 _sig("dsb_host_alloc", C.c_int, C.c_size_t, C.POINTER(_vp))
 _sig("dsb_host_free", None, _vp)
@@ -257,6 +258,12 @@ class Context:
         out = (C.c_uint64 * 16)()
         _check(lib.dsb_batch_counters(self._h, C.byref(out)), "dsb_batch_counters")
         return dict(zip(COUNTER_NAMES, list(out)))
+
+    def profile(self):
+        """per-read phase times [n_reads, 8] in units of 1024 SM cycles (fast, chain, slow, kidx, middle, right, left, total)"""
+        out = np.zeros((self.n_reads, 8), dtype=np.uint32)
+        _check(lib.dsb_batch_profile(self._h, out.ctypes.data), "dsb_batch_profile")
+        return out
 
     def stream(self):
         return lib.dsb_ctx_stream(self._h)

@@ -336,7 +336,7 @@ extern "C" void dsb_ctx_free(dsb_ctx *c)
 	cudaSetDevice(c->ix->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = {&c->seqs, &c->read_off, &c->bin_off, &c->bits_off, &c->seed_off, &c->tiles, &c->bin, &c->bits, &c->seeds[0], &c->seeds[1],
-	                  &c->n_seeds[0], &c->n_seeds[1], &c->total_score[0], &c->total_score[1], &c->scratch, &c->rr, &c->hits, &c->counters};
+	                  &c->n_seeds[0], &c->n_seeds[1], &c->total_score[0], &c->total_score[1], &c->scratch, &c->rr, &c->hits, &c->counters, &c->prof};
 	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
 	if (c->h_pin) cudaFreeHost(c->h_pin);
 	for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -438,6 +438,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 	// hits: the pre-filter chains of a read use 2 slots each (second half = merge-sort scratch)
 	const uint64_t hits_cap = std::max<uint64_t>(4096, (uint64_t)n * 24);
 	if ((rc = ensure(c->hits, hits_cap * sizeof(dsb_hit))) != DSB_OK) return rc;
+	if ((rc = ensure(c->prof, (size_t)n * 32)) != DSB_OK) return rc;
 	c->hits_cap = c->hits.cap / sizeof(dsb_hit);
 	unsigned long long *cnt = (unsigned long long *)c->counters.p;
 	DSB_CUDA(cudaMemsetAsync(cnt, 0, DSB_CNT_COUNT * 8, st));
@@ -468,6 +469,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		P.seed_off = (const uint32_t *)c->seed_off.p;
 		for (int s = 0; s < 2; s++) { P.seeds[s] = (const dsb_seed *)c->seeds[s].p; P.n_seeds[s] = (const uint32_t *)c->n_seeds[s].p; P.total_score[s] = (const uint32_t *)c->total_score[s].p; }
 		P.work_counter = (uint32_t *)(cnt + DSB_CNT_WORK);
+		P.prof = (uint32_t *)c->prof.p;
 		P.scratch = (uint8_t *)c->scratch.p; P.scratch_stride = L.total;
 		P.max_anchors = c->opts.max_anchors; P.max_matches = c->opts.max_matches; P.kidx_bits_max = c->kidx_bits; P.kidx_len_max = c->kidx_len;
 		P.rr = (dsb_read_result *)c->rr.p; P.hits = (dsb_hit *)c->hits.p; P.hits_cap = c->hits_cap; P.hits_cursor = cnt + DSB_CNT_HITS_CURSOR;
@@ -559,6 +561,15 @@ extern "C" int dsb_batch_kernel_ms(dsb_ctx *c, float ms[4])
 	DSB_CUDA(cudaSetDevice(c->ix->device));
 	DSB_CUDA(cudaStreamSynchronize(c->stream));
 	for (int i = 0; i < 4; i++) { ms[i] = 0; if (c->n_reads) DSB_CUDA(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1])); }
+	return DSB_OK;
+}
+
+extern "C" int dsb_batch_profile(dsb_ctx *c, uint32_t *out)
+{
+	if (!c || !c->ran || !out) return DSB_E_ARG;
+	DSB_CUDA(cudaSetDevice(c->ix->device));
+	DSB_CUDA(cudaStreamSynchronize(c->stream));
+	if (c->n_reads) DSB_CUDA(cudaMemcpy(out, c->prof.p, (size_t)c->n_reads * 32, cudaMemcpyDeviceToHost));
 	return DSB_OK;
 }
 

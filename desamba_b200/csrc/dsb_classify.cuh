@@ -4,6 +4,7 @@
 // set / flank frame / reference window live in shared memory, the read's 9-mer index is a warp-built CSR table.
 #pragma once
 #include "dsb_device.cuh"
+#include <climits>
 #include "../../include/desamba_b200.h"
 
 #define L_PRE_IDX 13
@@ -66,6 +67,7 @@ struct ClassifyParams {
 	const uint32_t *n_seeds[2];
 	const uint32_t *total_score[2];
 	uint32_t *work_counter;
+	uint32_t *prof;             // per read: 8 x u32 phase times in units of 1024 cycles (fast, chain, slow, kidx, middle, right, left, total)
 	// scratch
 	uint8_t  *scratch; uint64_t scratch_stride;
 	uint32_t max_anchors, max_matches, kidx_bits_max, kidx_len_max;
@@ -90,7 +92,10 @@ struct ReadState {
 	int error;
 	int sp_l;                    // SP_SET.l
 	uint32_t c_prefix, c_occ, c_locate, c_getref, c_getref_bytes;   // algorithmic counters
+	long long t_phase[8];       // clock64 per phase
 };
+#define PH_BEGIN() const long long ph_t0_ = clock64()
+#define PH_END(S, k) (S).t_phase[k] += clock64() - ph_t0_
 #define CNT_GETREF(S, len) do { (S).c_getref++; (S).c_getref_bytes += ((uint32_t)DSB_MAX((int)(len), 0) + 3) >> 2; } while (0)
 
 // ---------------------------------------------------------------- visited-row set (sp_set_insert, cly.c:1286-1298)
@@ -543,20 +548,38 @@ __device__ __noinline__ void chain_insert_M3(ReadState &S)
 			anchor_max_score = ca.score;
 			const uint32_t max_t = ca.ref_offset + MAX_ANCHOR_OVERLAP;
 			const uint32_t max_q = ca.index_in_read + MAX_ANCHOR_OVERLAP;
-			for (int32_t pre = c_a - 1; pre >= chr_st; pre--) {
-				const DevAnchor pa = A[pre];
-				if (pa.index_in_read + pa.mtch_len > max_q) continue;
-				if (pa.ref_offset + pa.mtch_len > max_t) continue;
-				if (pa.index_in_read + 1000 < max_q) break;
-				if (pa.ref_offset + 1000 < max_t) break;
-				const int indel = pa.index_in_read - pa.ref_offset - (max_q - max_t);
-				const int ABS_indel = DSB_ABS(indel);
-				if (ABS_indel > 200) continue;
-				const int new_score = score_v[pre - chr_st] + ca.mtch_len - (ABS_indel >> 4) - ((max_q - pa.index_in_read) >> 8);
-				if (new_score > anchor_max_score) { anchor_max_score = new_score; ca_pre = pre; }
+			// look-back over earlier anchors of the group, 32 per step (lane 0 = nearest); the reference's sequential loop takes
+			// the first maximum it meets walking backwards and stops at the first `break` (cly.c:283-303)
+			int best_score = INT_MIN, best_pre = -1;
+			for (int32_t base = c_a - 1; base >= chr_st; base -= 32) {
+				const int32_t pre = base - lane_id();
+				const bool act = pre >= chr_st;
+				DevAnchor pa; pa.index_in_read = 0; pa.ref_offset = 0; pa.mtch_len = 0;
+				if (act) pa = A[pre];
+				const bool pass = act && !(pa.index_in_read + pa.mtch_len > max_q) && !(pa.ref_offset + pa.mtch_len > max_t);
+				const bool brk = pass && ((pa.index_in_read + 1000 < max_q) || (pa.ref_offset + 1000 < max_t));
+				const uint32_t bm = __ballot_sync(DSB_FULL, brk);
+				const int first = bm ? (__ffs(bm) - 1) : 32;
+				if (pass && lane_id() < first) {
+					const int indel = pa.index_in_read - pa.ref_offset - (max_q - max_t);
+					const int ABS_indel = DSB_ABS(indel);
+					if (!(ABS_indel > 200)) {
+						const int new_score = score_v[pre - chr_st] + ca.mtch_len - (ABS_indel >> 4) - ((max_q - pa.index_in_read) >> 8);
+						if (new_score > best_score) { best_score = new_score; best_pre = pre; }      // lanes walk downwards: first maximum = highest pre
+					}
+				}
+				if (bm) break;
 			}
-			A[c_a].pre = ca_pre;
-			score_v[c_a - chr_st] = anchor_max_score;
+			{	// arg-max over lanes: highest score, ties -> highest pre
+				#pragma unroll
+				for (int d = 16; d; d >>= 1) {
+					const int os = __shfl_xor_sync(DSB_FULL, best_score, d), op = __shfl_xor_sync(DSB_FULL, best_pre, d);
+					if (os > best_score || (os == best_score && op > best_pre)) { best_score = os; best_pre = op; }
+				}
+				if (best_pre >= 0 && best_score > anchor_max_score) { anchor_max_score = best_score; ca_pre = best_pre; }
+			}
+			if (lane_id() == 0) { A[c_a].pre = ca_pre; score_v[c_a - chr_st] = anchor_max_score; }
+			__syncwarp();
 			if (max_score < anchor_max_score) { max_score = anchor_max_score; max_anchor = c_a; }
 		}
 		int sum_INDEL = 0, anchor_number = 1; int32_t pre = max_anchor;
@@ -805,6 +828,19 @@ __device__ __forceinline__ void refwin_zero(ReadState &S, int nbytes)     // zer
 	__syncwarp();
 }
 
+__device__ __forceinline__ int warp_max(int v)
+{
+	#pragma unroll
+	for (int d = 16; d; d >>= 1) v = max(v, __shfl_xor_sync(DSB_FULL, v, d));
+	return v;
+}
+__device__ __forceinline__ DevSms load_sms(const DevSms *p)
+{
+	const uint4 v = *(const uint4 *)p;
+	DevSms r; r.t_pos = v.x; r.q_pos = v.y; r.len = v.z; r.score = v.w;
+	return r;
+}
+
 #define MAX_sms_overlap (6)
 #define MAX_sms_overlap_middle (6)
 __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8_t *q_str, const KIdx &kx)
@@ -841,8 +877,10 @@ __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8
 					int max_score = c_spd.len;
 					const uint32_t max_q = c_spd.q_pos + MAX_sms_overlap_middle;
 					const uint32_t max_t = c_spd.t_pos + MAX_sms_overlap_middle;
-					for (int pi = (int)ci - 1; pi >= 0; pi--) {
-						const DevSms c_pre = base[pi];
+					for (int pbase = (int)ci - 1; pbase >= 0; pbase -= 32) {
+						const int pi = pbase - lane_id();
+						if (pi < 0) continue;
+						const DevSms c_pre = load_sms(base + pi);
 						const int pre_q_ed = c_pre.q_pos + c_pre.len + S_A_KEMR_L - 1;
 						const int pre_t_ed = c_pre.t_pos + c_pre.len + S_A_KEMR_L - 1;
 						if (pre_q_ed > max_q) continue;
@@ -858,8 +896,11 @@ __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8
 						}
 						max_score = DSB_MAX(max_score, new_score);
 					}
+					__syncwarp();
+					max_score = warp_max(max_score);
 					score = DSB_MAX(max_score, score);
-					base[ci].score = max_score;
+					if (lane_id() == 0) base[ci].score = max_score;
+					__syncwarp();
 				}
 			}
 		} else
@@ -915,25 +956,35 @@ __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, con
 		int max_score = c_sms.len;
 		const uint32_t max_pre_q = c_sms.q_pos + MAX_sms_overlap;
 		const uint32_t max_pre_t = c_sms.t_pos + MAX_sms_overlap;
-		for (int pi = (int)current_sms - 2; pi >= 0; pi--) {
-			const DevSms c_pre = sms[pi];
+		for (int pbase = (int)current_sms - 2; pbase >= 0; pbase -= 32) {
+			const int pi = pbase - lane_id();
+			const bool act = pi >= 0;
+			DevSms c_pre; c_pre.t_pos = c_pre.q_pos = c_pre.len = c_pre.score = 0;
+			if (act) c_pre = load_sms(sms + pi);
 			const int pre_q_ed = c_pre.q_pos + c_pre.len + S_A_KEMR_L - 1;
 			const int pre_t_ed = c_pre.t_pos + c_pre.len + S_A_KEMR_L - 1;
-			if (pre_q_ed > max_pre_q) continue;
-			if (pre_t_ed > max_pre_t) continue;
-			if (c_pre.t_pos + 600 < max_pre_t) break;
-			const int indel = c_pre.q_pos - c_pre.t_pos - (max_pre_q - max_pre_t);
-			const int ABS_indel = DSB_ABS(indel);
-			if (ABS_indel > 200) continue;
-			int new_score = c_pre.score + c_sms.len - (ABS_indel >> 3);
-			if (pre_q_ed > c_sms.q_pos || pre_t_ed > c_sms.t_pos) {
-				const int overlap_q = pre_q_ed - c_sms.q_pos;
-				const int overlap_t = pre_t_ed - c_sms.t_pos;
-				new_score -= DSB_MAX(overlap_q, overlap_t);
+			const bool pass = act && !(pre_q_ed > max_pre_q) && !(pre_t_ed > max_pre_t);
+			const bool brk = pass && (c_pre.t_pos + 600 < max_pre_t);
+			const uint32_t bm = __ballot_sync(DSB_FULL, brk);
+			const int first = bm ? (__ffs(bm) - 1) : 32;
+			if (pass && lane_id() < first) {
+				const int indel = c_pre.q_pos - c_pre.t_pos - (max_pre_q - max_pre_t);
+				const int ABS_indel = DSB_ABS(indel);
+				if (!(ABS_indel > 200)) {
+					int new_score = c_pre.score + c_sms.len - (ABS_indel >> 3);
+					if (pre_q_ed > c_sms.q_pos || pre_t_ed > c_sms.t_pos) {
+						const int overlap_q = pre_q_ed - c_sms.q_pos;
+						const int overlap_t = pre_t_ed - c_sms.t_pos;
+						new_score -= DSB_MAX(overlap_q, overlap_t);
+					}
+					max_score = DSB_MAX(max_score, new_score);
+				}
 			}
-			max_score = DSB_MAX(max_score, new_score);
+			if (bm) break;
 		}
-		sms[ci].score = max_score;
+		max_score = warp_max(max_score);
+		if (lane_id() == 0) sms[ci].score = max_score;
+		__syncwarp();
 		if (c_sms.len >= 8 && combine_chain(S, chain_ID, c_sms.t_pos - c_sms.q_pos, 0, c_sms.q_pos, &combined) == 1) {
 			total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2(S, c_st[combined].cur, q_str, kx);
 			if (S.error) return 0;
@@ -1002,23 +1053,33 @@ __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, cons
 		int max_score = c_sms.len;
 		const uint32_t min_pre_q = c_sms.q_pos + c_sms.len - MAX_sms_overlap + S_A_KEMR_L - 1;
 		const uint32_t min_pre_t = c_sms.t_pos + c_sms.len - MAX_sms_overlap + S_A_KEMR_L - 1;
-		for (int pi = (int)current_sms - 2; pi >= 0; pi--) {
-			const DevSms c_pre = sms[pi];
-			if (c_pre.q_pos < min_pre_q) continue;
-			if (c_pre.t_pos < min_pre_t) continue;
-			if (min_pre_t + 600 < c_pre.t_pos) break;
-			const int indel = c_pre.q_pos - c_pre.t_pos - (min_pre_q - min_pre_t);
-			const int ABS_indel = DSB_ABS(indel);
-			if (ABS_indel > 200) continue;
-			int new_score = c_pre.score + c_sms.len - (ABS_indel >> 3);
-			if (min_pre_q + MAX_sms_overlap > c_pre.q_pos || min_pre_t + MAX_sms_overlap > c_pre.t_pos) {
-				const int overlap_q = min_pre_q + MAX_sms_overlap - c_pre.q_pos;
-				const int overlap_t = min_pre_t + MAX_sms_overlap - c_pre.t_pos;
-				new_score -= DSB_MAX(overlap_q, overlap_t);
+		for (int pbase = (int)current_sms - 2; pbase >= 0; pbase -= 32) {
+			const int pi = pbase - lane_id();
+			const bool act = pi >= 0;
+			DevSms c_pre; c_pre.t_pos = c_pre.q_pos = c_pre.len = c_pre.score = 0;
+			if (act) c_pre = load_sms(sms + pi);
+			const bool pass = act && !(c_pre.q_pos < min_pre_q) && !(c_pre.t_pos < min_pre_t);
+			const bool brk = pass && (min_pre_t + 600 < c_pre.t_pos);
+			const uint32_t bm = __ballot_sync(DSB_FULL, brk);
+			const int first = bm ? (__ffs(bm) - 1) : 32;
+			if (pass && lane_id() < first) {
+				const int indel = c_pre.q_pos - c_pre.t_pos - (min_pre_q - min_pre_t);
+				const int ABS_indel = DSB_ABS(indel);
+				if (!(ABS_indel > 200)) {
+					int new_score = c_pre.score + c_sms.len - (ABS_indel >> 3);
+					if (min_pre_q + MAX_sms_overlap > c_pre.q_pos || min_pre_t + MAX_sms_overlap > c_pre.t_pos) {
+						const int overlap_q = min_pre_q + MAX_sms_overlap - c_pre.q_pos;
+						const int overlap_t = min_pre_t + MAX_sms_overlap - c_pre.t_pos;
+						new_score -= DSB_MAX(overlap_q, overlap_t);
+					}
+					max_score = DSB_MAX(max_score, new_score);
+				}
 			}
-			max_score = DSB_MAX(max_score, new_score);
+			if (bm) break;
 		}
-		sms[ci].score = max_score;
+		max_score = warp_max(max_score);
+		if (lane_id() == 0) sms[ci].score = max_score;
+		__syncwarp();
 		if (c_sms.len >= 8 && combine_chain(S, chain_ID, c_sms.t_pos - c_sms.q_pos, 1, c_sms.q_pos + c_sms.len, &combined) == 1) {
 			total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2(S, c_st[combined].cur, q_str, kx);
 			if (S.error) return 0;
@@ -1076,7 +1137,7 @@ __device__ __noinline__ void score_and_merge(ReadState &S, const SearchDir *sear
 		if ((c_dir & both_dir) == 0) continue;
 		const uint32_t direction = (c_dir == 1) ? DSB_REVERSE : DSB_FORWARD;
 		const SearchDir *c_sd = ((search_dir->direction == direction) ? 0 : 1) + search_dir;
-		build_kidx(S, c_sd->bin_read, l_read, (c_dir == 2) ? 0 : 1, key_bits);
+		{ PH_BEGIN(); build_kidx(S, c_sd->bin_read, l_read, (c_dir == 2) ? 0 : 1, key_bits); PH_END(S, 3); }
 	}
 	for (uint32_t i = 0; i < S.n_hit; i++) {
 		if (C[i].sum_score == 0) continue;
@@ -1084,11 +1145,11 @@ __device__ __noinline__ void score_and_merge(ReadState &S, const SearchDir *sear
 		const SearchDir *c_sd = ((search_dir->direction == dir) ? 0 : 1) + search_dir;
 		const int slot = (dir == DSB_FORWARD) ? 0 : 1;
 		KIdx kx; kx.start = S.ws.kidx_start[slot]; kx.ent = S.ws.kidx_ent[slot]; kx.kmask = (1u << key_bits) - 1;
-		int score = sdp_middle_M2(S, C[i].cur, c_sd->bin_read, kx);
+		int score; { PH_BEGIN(); score = sdp_middle_M2(S, C[i].cur, c_sd->bin_read, kx); PH_END(S, 4); }
 		if (S.error) return;
-		score = sdp_right_M2(S, c_sd->bin_read, kx, (int)i, l_read, score);
+		{ PH_BEGIN(); score = sdp_right_M2(S, c_sd->bin_read, kx, (int)i, l_read, score); PH_END(S, 5); }
 		if (S.error) return;
-		score = sdp_left_M2(S, c_sd->bin_read, kx, (int)i, score);
+		{ PH_BEGIN(); score = sdp_left_M2(S, c_sd->bin_read, kx, (int)i, score); PH_END(S, 6); }
 		if (S.error) return;
 		C[i].sum_score = score;
 	}
@@ -1131,6 +1192,8 @@ __device__ void classify_read(const ClassifyParams &P, ReadState &S, uint32_t r)
 	const uint32_t read_len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
 	S.n_anc = 0; S.n_hit = 0; S.n_sms = 0; S.fast_classify = 1; S.error = 0; S.sp_l = 0;
 	S.c_prefix = S.c_occ = S.c_locate = S.c_getref = S.c_getref_bytes = 0;
+	for (int k = 0; k < 8; k++) S.t_phase[k] = 0;
+	const long long t_read0 = clock64();
 	dsb_read_result out;
 	out.hit_off = 0; out.n_hit = 0; out.n_anchor = 0; out.fast_classify = 1; out.entered_final = 0; out.error = 0; out.read_len = read_len;
 	if (read_len >= MIN_READ_LEN) {
@@ -1146,10 +1209,10 @@ __device__ void classify_read(const ClassifyParams &P, ReadState &S, uint32_t r)
 		if (sd[0].total_score < sd[1].total_score) { SearchDir t = sd[0]; sd[0] = sd[1]; sd[1] = t; }   // cly.c:1261-1266
 		const bool both_direction = ((sd[0].total_score - sd[1].total_score) <= (sd[0].total_score >> 3));
 		const int super_repeat = 0;                                   // always 0 in the reference (cly.c:849-888,1545)
-		fast_classify(S, sd[0], read_len);
-		if (!S.error && both_direction) fast_classify(S, sd[1], read_len);
+		{ PH_BEGIN(); fast_classify(S, sd[0], read_len); PH_END(S, 0); }
+		if (!S.error && both_direction) { PH_BEGIN(); fast_classify(S, sd[1], read_len); PH_END(S, 0); }
 		if (!S.error) {
-			resolve_tree(S);
+			{ PH_BEGIN(); resolve_tree(S); PH_END(S, 1); }
 			bool run_slow_mode = false;
 			if (S.n_hit <= 0) run_slow_mode = true;
 			else if (S.ws.chain[0].anchor_number < 5 && super_repeat < 3) {
@@ -1158,12 +1221,12 @@ __device__ void classify_read(const ClassifyParams &P, ReadState &S, uint32_t r)
 			}
 			if (run_slow_mode) {
 				S.n_anc = 0;
-				slow_classify(S, sd[0], read_len);
+				{ PH_BEGIN(); slow_classify(S, sd[0], read_len); PH_END(S, 2); }
 				if (!S.error) {
-					resolve_tree(S);
+					{ PH_BEGIN(); resolve_tree(S); PH_END(S, 1); }
 					if (both_direction || S.n_hit <= 0 || (S.ws.chain[0].anchor_number < 5 && super_repeat < 3)) {
-						slow_classify(S, sd[1], read_len);
-						if (!S.error) resolve_tree(S);
+						{ PH_BEGIN(); slow_classify(S, sd[1], read_len); PH_END(S, 2); }
+						if (!S.error) { PH_BEGIN(); resolve_tree(S); PH_END(S, 1); }
 					}
 				}
 			}
@@ -1192,5 +1255,7 @@ __device__ void classify_read(const ClassifyParams &P, ReadState &S, uint32_t r)
 		P.hits[off + i] = h;
 	}
 	if (lane_id() == 0) P.rr[r] = out;
+	S.t_phase[7] = clock64() - t_read0;
+	if (P.prof && lane_id() < 8) P.prof[(uint64_t)r * 8 + lane_id()] = (uint32_t)(S.t_phase[lane_id()] >> 10);
 	__syncwarp();
 }

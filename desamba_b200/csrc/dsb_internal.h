@@ -34,7 +34,7 @@ struct dsb_ctx {
 	// batch inputs (device)
 	DevBuf seqs, read_off, bin_off, bits_off, seed_off, tiles, bin, bits, seeds[2], n_seeds[2], total_score[2];
 	// classify scratch + outputs
-	DevBuf scratch, rr, hits, counters;
+	DevBuf scratch, rr, hits, counters, prof;
 	uint64_t scratch_stride; uint32_t kidx_bits, kidx_len;
 	uint64_t hits_cap;
 	// pinned staging

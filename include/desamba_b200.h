@@ -121,6 +121,10 @@ void *dsb_ctx_stream(dsb_ctx *ctx);
  * [8] SA/unitig/ref_pos locates, [9] get_ref calls, [10] packed reference bytes they cover, [11] reads that hit a capacity */
 int dsb_batch_counters(dsb_ctx *ctx, uint64_t out[16]);
 
+/* per-read device time of the last run, out[n_reads][8] in units of 1024 SM cycles:
+ * fast seeding, chaining, slow seeding, 9-mer index build, sdp middle, sdp right, sdp left, whole read */
+int dsb_batch_profile(dsb_ctx *ctx, uint32_t *out);
+
 /* pinned host memory for the caller's batch buffers (the driver batches reads into these; cly_mt.c:42-56 equivalent) */
 int  dsb_host_alloc(size_t bytes, void **out);
 void dsb_host_free(void *p);
