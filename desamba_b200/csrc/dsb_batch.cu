@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(128) k_islands(const __grid_constant__ IslandP
 }
 
 // ------------------------------------------------------------------------------------------------ K2
-struct ScratchLayout { uint64_t anc, anc_tmp, chain, chain_tmp, sms, score_v, mem_rst, sc_hash, kstart[2], kent[2], total; };
+struct ScratchLayout { uint64_t anc, anc_tmp, chain, chain_tmp, sms, score_v, sc_hash, kstart[2], kent[2], sp_set, lane_mem, seed_rec, chunk_next, total; };
 static ScratchLayout scratch_layout(uint32_t max_anchors, uint32_t max_matches, uint32_t kidx_bits, uint32_t kidx_len)
 {
 	ScratchLayout L; uint64_t o = 0;
@@ -153,9 +153,12 @@ static ScratchLayout scratch_layout(uint32_t max_anchors, uint32_t max_matches, 
 	L.chain = take((uint64_t)max_anchors * sizeof(DevChain)); L.chain_tmp = take((uint64_t)max_anchors * sizeof(DevChain));
 	L.sms = take((uint64_t)max_matches * sizeof(DevSms));
 	L.score_v = take(1024 * sizeof(int));
-	L.mem_rst = take(512 * sizeof(MemRst));
 	L.sc_hash = take((256 + 2 * 400 + 8) * sizeof(ScHash));
 	for (int s = 0; s < 2; s++) { L.kstart[s] = take(((uint64_t)1 << kidx_bits) * 4 + 128); L.kent[s] = take((uint64_t)kidx_len * sizeof(KEntry) + 128); }
+	L.sp_set = take(32 * 512 * 8);
+	L.lane_mem = take(32 * 512 * sizeof(MemRst));
+	L.seed_rec = take(((uint64_t)kidx_len / 2 + 8) * sizeof(SeedRec));
+	L.chunk_next = take(((uint64_t)max_anchors / ANCHOR_CHUNK + 8) * 4);
 	L.total = o;
 	return L;
 }
@@ -174,7 +177,9 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_classify(cons
 	S.ws.anc = (DevAnchor *)(base + A.L.anc); S.ws.anc_tmp = (DevAnchor *)(base + A.L.anc_tmp);
 	S.ws.chain = (DevChain *)(base + A.L.chain); S.ws.chain_tmp = (DevChain *)(base + A.L.chain_tmp);
 	S.ws.sms = (DevSms *)(base + A.L.sms); S.ws.score_v = (int *)(base + A.L.score_v);
-	S.ws.mem_rst = (MemRst *)(base + A.L.mem_rst); S.ws.sc_hash = (ScHash *)(base + A.L.sc_hash);
+	S.ws.sc_hash = (ScHash *)(base + A.L.sc_hash);
+	S.ws.sp_set = (uint64_t *)(base + A.L.sp_set); S.ws.lane_mem = (MemRst *)(base + A.L.lane_mem);
+	S.ws.seed_rec = (SeedRec *)(base + A.L.seed_rec); S.ws.chunk_next = (uint32_t *)(base + A.L.chunk_next);
 	for (int s = 0; s < 2; s++) { S.ws.kidx_start[s] = (uint32_t *)(base + A.L.kstart[s]); S.ws.kidx_ent[s] = (KEntry *)(base + A.L.kent[s]); }
 	S.max_anchors = A.P.max_anchors; S.max_matches = A.P.max_matches;
 	for (;;) {

@@ -37,23 +37,28 @@ struct KEntry { uint32_t kmer, pos; };
 struct ScHash { uint16_t next; uint16_t seed_ID; uint16_t s_or_e; uint16_t pad; };   // seed_con_hash (cly.h:120-125)
 
 struct WarpSmem {               // per-warp shared memory
-	uint64_t sp_set[SP_SET_CAP];
 	uint8_t  refwin[2176];      // ref[2000] of sdp_middle_M2 / ref[1000] of sdp_right/left_M2 (+ over-read slack)
-	uint8_t  frame[64];         // pad[8] | q_pre[13] | t_pre[13] | t_suf[13]  (policy P2)
+	uint32_t next_seed;         // seed_pass: work counter of the lanes
+	uint32_t chunk_cursor;      // seed_pass: next free chunk of the anchor staging pool
+	uint32_t pad[2];
 };
 #define FR_A 8
 #define FR_B 21
 #define FR_C 34
 
+struct SeedRec;
 struct WarpScratch {            // per-warp HBM scratch
-	DevAnchor *anc, *anc_tmp;
+	DevAnchor *anc, *anc_tmp;   // anc_tmp: staging pool of seed_pass, then merge-sort scratch of chain_insert_M3
 	DevChain  *chain, *chain_tmp;
 	DevSms    *sms;
 	int       *score_v;         // 1024
-	MemRst    *mem_rst;         // 256
 	ScHash    *sc_hash;         // 256 + 2*400 + 8
 	uint32_t  *kidx_start[2];   // CSR bucket ends of the read's 9-mer index, per strand slot (0 forward, 1 reverse)
 	KEntry    *kidx_ent[2];
+	uint64_t  *sp_set;          // 32 lanes x 512 visited rows, interleaved
+	MemRst    *lane_mem;        // 32 lanes x 512
+	SeedRec   *seed_rec;        // one per island seed of a strand
+	uint32_t  *chunk_next;      // max_anchors / ANCHOR_CHUNK links
 };
 
 struct ClassifyParams {
@@ -98,370 +103,7 @@ struct ReadState {
 #define PH_END(S, k) (S).t_phase[k] += clock64() - ph_t0_
 #define CNT_GETREF(S, len) do { (S).c_getref++; (S).c_getref_bytes += ((uint32_t)DSB_MAX((int)(len), 0) + 3) >> 2; } while (0)
 
-// ---------------------------------------------------------------- visited-row set (sp_set_insert, cly.c:1286-1298)
-__device__ __forceinline__ int sp_set_insert(ReadState &S, uint64_t node)
-{
-	if (S.sp_l == SP_SET_CAP) S.sp_l = 0;
-	const int lane = lane_id();
-	bool found = false;
-	for (int i = lane; i < S.sp_l; i += 32) found |= (S.sm->sp_set[i] == node);
-	if (__any_sync(DSB_FULL, found)) return 0;
-	S.sm->sp_set[S.sp_l] = node;
-	S.sp_l++;
-	__syncwarp();
-	return 1;
-}
-
-// ---------------------------------------------------------------- FM-index search (cly.c:1344-1447)
-__device__ __noinline__ void bwt_single_search(ReadState &S, uint64_t sp, const uint8_t *string, int max_match_len, MemRst *out)
-{
-	const DevIndex &ix = *S.ix;
-	uint64_t new_sp, sa_sp = NO_SA;
-	int match_len = 0, sa_sp_l = 0;
-	while (1) {
-		if (match_len >= max_match_len) break;
-		if ((sp & SA_MASK) == 0) { sa_sp = sp; sa_sp_l = 0; }
-		else sa_sp_l--;
-		uint32_t c = 0xff;
-		new_sp = occ_one(ix, sp, c) + ix.rank[c];
-		S.c_occ++;
-		if (c != (uint32_t)__ldg(string)) break;
-		match_len++;
-		string--;
-		if (sp_set_insert(S, new_sp) == 0) { out->match_len = -1000; return; }
-		sp = new_sp;
-	}
-	out->sp = sp; out->match_len = match_len; out->sa_sp = sa_sp; out->sa_sp_l = sa_sp_l;
-}
-
-__device__ __noinline__ int bwt_MEM_search(ReadState &S, const uint8_t *string, uint64_t pre_v, int max_rst, int l_min_mth, int l_max_mth, MemRst *mem_rst)
-{
-	const DevIndex &ix = *S.ix;
-	int n_rst = 0;
-	uint64_t sp = __ldg(ix.prefix + pre_v), ep = __ldg(ix.prefix + pre_v + 1), new_sp, new_ep;
-	S.c_prefix++;
-	string -= L_PRE_IDX;
-	int match_len = L_PRE_IDX;
-	while (1) {
-		const uint32_t c = __ldg(string);
-		string--;
-		occ_pair(ix, sp, ep, c, new_sp, new_ep);
-		S.c_occ += 2;
-		new_sp += ix.rank[c]; new_ep += ix.rank[c];
-		if (match_len >= l_min_mth - 1) {
-			if (new_sp + max_rst >= new_ep) break;
-			if (match_len >= l_max_mth) return 0;
-		}
-		if (new_sp + 1 >= new_ep) break;
-		match_len++;
-		sp = new_sp; ep = new_ep;
-	}
-	if (new_sp >= new_ep) return 0;
-	if (new_sp + 1 == new_ep) {
-		if (sp_set_insert(S, new_sp) == 0) return 0;
-		bwt_single_search(S, new_sp, string, DSB_MAX(0, l_max_mth - match_len), mem_rst + n_rst);
-		mem_rst[n_rst].match_len += match_len + 1;
-		if (mem_rst[n_rst].match_len >= l_min_mth) n_rst++;
-	} else {
-		for (uint64_t c_sp = new_sp; c_sp < new_ep; c_sp++) {
-			if (sp_set_insert(S, c_sp) == 0) continue;
-			bwt_single_search(S, c_sp, string, DSB_MAX(0, l_max_mth - match_len), mem_rst + n_rst);
-			mem_rst[n_rst].match_len += match_len + 1;
-			if (mem_rst[n_rst].match_len >= l_min_mth) n_rst++;
-		}
-	}
-	return n_rst;
-}
-
-// ---------------------------------------------------------------- locate + anchors (cly.c:471-496, 629-694, 706-939)
-__device__ __forceinline__ int64_t get_uni(ReadState &S, const DevIndex &ix, uint64_t bwt_pos, int search_l, uint64_t *global_offset, uint32_t *uni_offset_)
-{
-	S.c_locate++;
-	const uint2 sa = __ldg(ix.sa + (bwt_pos >> SA_OFF));
-	int64_t u = sa.x;
-	uint32_t uni_offset = sa.y + search_l + 1;
-	if (search_l > 0)
-		for (;;) { const uint32_t len = __ldg(ix.uni + u).y; if (!(uni_offset >= len) || u >= (int64_t)ix.n_uni) break; uni_offset -= (len + 1); u++; }   // (bound: the reference walks off its table here)
-	const uint64_t rp = __ldg(ix.ref_pos + __ldg(ix.uni + u).x);
-	*global_offset = (rp & 0xFFFFFFFFFFull) + uni_offset;
-	*uni_offset_ = uni_offset;
-	return u;
-}
-
-__device__ __forceinline__ void frame_zero(uint8_t *p13)      // zero one 13-byte flank array (trivial-auto-var-init)
-{
-	if (lane_id() < 13) p13[lane_id()] = 0;
-	__syncwarp();
-}
-
-__device__ __noinline__ void get_new_ed(ReadState &S, uint32_t *e_d, uint32_t *len_, uint32_t *l_mem_ext,
-                                        int32_t q_off, uint64_t t_off, uint32_t l_read, const uint8_t *q_b, bool is_FWD)
-{
-	const DevIndex &ix = *S.ix;
-	uint8_t *fr = S.sm->frame;
-	frame_zero(fr + FR_B); frame_zero(fr + FR_C);
-	const uint8_t *q = fr + FR_B; uint8_t *t = fr + FR_C;
-	uint32_t len, max_len;
-	if (is_FWD) {
-		if (q_off < 0) q_off = 0;
-		max_len = q_off;
-		len = DSB_MIN(12, max_len);
-		if ((uint32_t)lane_id() < len) fr[FR_B + lane_id()] = __ldg(q_b + q_off - lane_id());
-		__syncwarp();
-	} else {
-		max_len = l_read - q_off;
-		len = DSB_MIN(12, max_len);
-		q = q_b + q_off;
-	}
-	CNT_GETREF(S, len); get_ref_coop(ix, t, t_off, len, !is_FWD);
-	if (len > 0 && t[0] == q[0]) {
-		int mtc;
-		do {
-			for (mtc = 0; mtc < len; mtc++) if (t[mtc] != q[mtc]) break;
-			if (mtc > 0) {
-				*l_mem_ext += mtc;
-				max_len -= mtc;
-				len = DSB_MIN(12, max_len);
-				if (is_FWD) {
-					q_off -= mtc; t_off -= mtc;
-					__syncwarp();
-					if ((uint32_t)lane_id() < len) fr[FR_B + lane_id()] = __ldg(q_b + q_off - lane_id());
-					__syncwarp();
-				} else { t_off += mtc; q += mtc; }
-				__syncwarp();
-				CNT_GETREF(S, len); get_ref_coop(ix, t, t_off, len, !is_FWD);
-			}
-		} while (mtc > 0);
-	}
-	*e_d = lv_extd_dev(t, len, q, len);
-	*len_ = len;
-}
-
-struct SeedInfo { const uint8_t *bin_read; uint32_t read_L; uint32_t direction; };
-
-#define MIN_S_1 12
-#define MIN_S_2 20
-__device__ __noinline__ int32_t map_seed(ReadState &S, const MemRst *m_r, const SeedInfo &s_i)
-{
-	const DevIndex &ix = *S.ix;
-	uint64_t b_p = m_r->sp;
-	const int32_t q_off = m_r->read_offset;
-	uint32_t l_m = m_r->match_len;
-	const uint8_t *q_b = s_i.bin_read;
-	int64_t uni = -1;
-	uint32_t u_off = 0;
-	uint64_t t_off = 0;
-	uint32_t l_pre, l_suf = 0, d_pre, d_suf = 0;
-	int32_t s = 0, max_s = 0;
-	uint8_t *fr = S.sm->frame;
-	__syncwarp();
-	if (lane_id() < 16) ((uint32_t *)fr)[lane_id()] = 0;
-	__syncwarp();
-	do {
-		uint8_t *q_pre = fr + FR_A, *t_pre = fr + FR_B, *t_suf = fr + FR_C;
-		const uint8_t *q_suf;
-		l_pre = DSB_MIN(q_off + 1, LV_L);
-		if ((uint32_t)lane_id() < l_pre) q_pre[lane_id()] = __ldg(q_b + q_off - lane_id());
-		__syncwarp();
-		int s_l = 0;
-		if (m_r->sa_sp != NO_SA)
-			uni = get_uni(S, ix, m_r->sa_sp, m_r->sa_sp_l, &t_off, &u_off);
-		else {
-			uint32_t c; uint64_t new_sp;
-			while (1) {
-				if ((b_p & SA_MASK) == 0) break;
-				c = 0xff;
-				new_sp = occ_one(ix, b_p, c) + ix.rank[c];
-				S.c_occ++;
-				if (c == 4) break;
-				t_pre[s_l++] = (uint8_t)c;
-				b_p = new_sp;
-				if (s_l >= l_pre) break;
-			}
-			__syncwarp();
-			if ((b_p & SA_MASK) == 0) uni = get_uni(S, ix, b_p, s_l, &t_off, &u_off);
-			else l_pre = s_l;
-		}
-		if (uni >= 0) {
-			if (__ldg(ix.uni + uni).y < MIN_UNI_L) break;
-			l_pre = DSB_MIN(l_pre, u_off);
-			CNT_GETREF(S, l_pre); get_ref_coop(ix, t_pre, t_off - 1, l_pre, false);
-		}
-		d_pre = lv_extd_dev(t_pre, l_pre, q_pre, l_pre);
-		s = Q_MEM_at(ix, l_m) + Q_LV_at(ix, d_pre, l_pre);
-		if (s < MIN_S_1 && l_pre == LV_L && uni < 0) { s = 0; break; }
-		if (uni < 0) {
-			for (int guard = 0; b_p & SA_MASK; guard++) {
-				if (guard > (1 << 20)) { S.error = 5; return 0; }          // cannot happen on a well-formed index; never hang the GPU
-				uint32_t c = 0xff;
-				b_p = occ_one(ix, b_p, c) + ix.rank[c];
-				S.c_occ++;
-				s_l++;
-			}
-			uni = get_uni(S, ix, b_p, s_l, &t_off, &u_off);
-			if (__ldg(ix.uni + uni).y < MIN_UNI_L) { s = 0; break; }
-		}
-		const int32_t q_off_r = q_off + l_m + 1;
-		uint32_t l_max_suf = DSB_MIN(__ldg(ix.uni + uni).y - u_off - l_m, s_i.read_L - q_off_r);
-		if (l_max_suf != 0) {
-			l_suf = DSB_MIN(l_max_suf, LV_L);
-			q_suf = q_b + q_off_r;
-			CNT_GETREF(S, l_suf); get_ref_coop(ix, t_suf, t_off + l_m, l_suf, true);
-			if (t_suf[0] == __ldg(q_suf)) {
-				int mtc;
-				do {
-					for (mtc = 0; mtc < l_suf; mtc++) if (t_suf[mtc] != __ldg(q_suf + mtc)) break;
-					if (mtc > 0) {
-						l_m += mtc;
-						s = Q_MEM_at(ix, l_m) + Q_LV_at(ix, d_pre, l_pre);
-						l_max_suf -= mtc;
-						l_suf = DSB_MIN(l_max_suf, LV_L);
-						q_suf += mtc;
-						__syncwarp();
-						CNT_GETREF(S, l_suf); get_ref_coop(ix, t_suf, t_off + l_m, l_suf, true);
-					}
-				} while (mtc > 0);
-			}
-			d_suf = lv_extd_dev(t_suf, l_suf, q_suf, l_suf);
-			s += Q_LV_at(ix, d_suf, l_suf);
-		} else
-			l_suf = d_suf = 0;
-		if (s <= MIN_S_2 && l_suf == LV_L) { s = 0; break; }
-	} while (0);
-
-	if (s > 0) {
-		uint16_t am_mtch_len = (uint16_t)l_m; int16_t am_score = (int16_t)s;
-		uint8_t am_left_len = (uint8_t)l_pre, am_left_ED = (uint8_t)d_pre, am_rigt_len = (uint8_t)l_suf, am_rigt_ED = (uint8_t)d_suf;
-		const uint32_t r_p_s = __ldg(ix.uni + uni).x, r_p_e = __ldg(ix.uni + uni + 1).x;
-		const bool ref_search_l = (l_pre < LV_L || d_pre == 0);
-		const bool ref_search_r = (l_suf < LV_L || d_suf == 0);
-		if ((int64_t)r_p_e - (int64_t)r_p_s > 50)
-			if (!((int64_t)r_p_e - (int64_t)r_p_s < 1000)) return 50;
-		for (uint32_t c_r_p = r_p_s; c_r_p < r_p_e; c_r_p++) {
-			const uint64_t rp = __ldg(ix.ref_pos + c_r_p);
-			const uint64_t rp_global = rp & 0xFFFFFFFFFFull; const uint32_t rp_ref = (uint32_t)((rp >> 40) & 0x7FFFFF);
-			uint32_t ed_l, ed_r, len_l, len_r;
-			uint32_t l_m_ext_l = 0, l_m_ext_r;
-			if (ref_search_l || ref_search_r) {
-				if (ref_search_l) {
-					get_new_ed(S, &ed_l, &len_l, &l_m_ext_l, q_off, rp_global + u_off - 1, s_i.read_L, q_b, true);
-					am_left_len = (uint8_t)len_l; am_left_ED = (uint8_t)ed_l;
-				}
-				am_mtch_len = (uint16_t)(l_m + l_m_ext_l);
-				if (ref_search_r) {
-					l_m_ext_r = 0;
-					get_new_ed(S, &ed_r, &len_r, &l_m_ext_r, q_off + l_m + 1, rp_global + u_off + l_m, s_i.read_L, q_b, false);
-					am_rigt_len = (uint8_t)len_r; am_rigt_ED = (uint8_t)ed_r;
-					am_mtch_len = (uint16_t)(am_mtch_len + l_m_ext_r);
-				}
-				am_score = (int16_t)(Q_MEM_at(ix, am_mtch_len) + Q_LV_at(ix, am_left_ED, am_left_len) + Q_LV_at(ix, am_rigt_ED, am_rigt_len));
-				if (am_score < MIN_S_2) continue;
-			}
-			max_s = DSB_MAX(max_s, am_score);
-			if (S.n_anc >= S.max_anchors) { S.error = 1; return max_s; }
-			DevAnchor a;
-			a.direction = (uint8_t)s_i.direction;
-			a.index_in_read = q_off + 1 - l_m_ext_l;
-			const uint64_t g = rp_global + u_off - l_m_ext_l;
-			a.ref_ID = rp_ref;
-			a.ref_offset = (uint32_t)(g - __ldg(ix.ref_info + rp_ref).y);
-			a.mtch_len = am_mtch_len; a.score = am_score;
-			a.pre = -1; a.useless = 0; a.duplicate = 0; a.pad = 0;
-			S.ws.anc[S.n_anc++] = a;
-		}
-	}
-	return max_s;
-}
-
-// ---------------------------------------------------------------- seed scheduling (cly.c:1476-1611)
-__device__ __forceinline__ uint64_t prefix13(const uint8_t *bin_read, int string_index)
-{   // low 26 bits of the l_ek-mer ending at string_index (= kmer[kmer_index] & PRE_IDX_MASK, cly.c:1504; seeds hold only non-zero k-mers)
-	uint64_t v = 0;
-	#pragma unroll
-	for (int k = 12; k >= 0; k--) v = (v << 2) | __ldg(bin_read + string_index - k);
-	return v;
-}
-
-__device__ __forceinline__ void mark_useless(ReadState &S, uint32_t a_b_idx)
-{
-	int top_score = 35;
-	for (uint32_t k = a_b_idx; k < S.n_anc; k++) top_score = DSB_MAX(top_score, S.ws.anc[k].score);
-	for (uint32_t k = a_b_idx; k < S.n_anc; k++) S.ws.anc[k].useless = (S.ws.anc[k].score < top_score) ? 1 : 0;
-}
-
-#define MEM_search_FAST 2
-#define MIN_MEM_LEN_FAST 21
-__device__ __noinline__ void fast_classify(ReadState &S, const SearchDir &s_d, uint32_t read_len)
-{
-	const int l_ek = S.ix->l_ek;
-	const int min_index = MIN_MEM_LEN_FAST - l_ek;
-	const uint8_t *bin_read = s_d.bin_read;
-	MemRst *m_r = S.ws.mem_rst;
-	SeedInfo s_i = {bin_read, read_len, s_d.direction};
-	for (uint32_t si = 0; si < s_d.l_seed_v; si++) {
-		const dsb_seed c_sv = s_d.seed_v[si];
-		if (c_sv.top == 0) continue;
-		S.sp_l = 0;
-		const uint32_t a_b_idx = S.n_anc;
-		for (int j = (int)c_sv.len - 1; j >= min_index;) {
-			const int kmer_index = c_sv.offset + j;
-			const int string_index = kmer_index + l_ek - 1;
-			const uint64_t prefixValue = prefix13(bin_read, string_index);
-			const int n = bwt_MEM_search(S, bin_read + string_index, prefixValue, MEM_search_FAST, MIN_MEM_LEN_FAST - 1, string_index, m_r);
-			if (n == 0) { j -= 2; continue; }
-			j -= 3;
-			int max_score = 0;
-			for (int k = 0; k < n; k++) {
-				m_r[k].read_offset = string_index - m_r[k].match_len;
-				const int c_score = map_seed(S, m_r + k, s_i);
-				max_score = DSB_MAX(c_score, max_score);
-				if (S.error) return;
-			}
-			if (max_score > 35) j -= 7;
-			if (max_score > 256) {
-				if (max_score > 512) si++;
-				break;
-			}
-		}
-		mark_useless(S, a_b_idx);
-	}
-}
-
-struct MemRstCmp { __device__ int operator()(const MemRst &a, const MemRst &b) const { return b.match_len - a.match_len; } };
-
-#define MEM_search_SLOW 8
-#define MIN_MEM_LEN_SLOW 20
-__device__ __noinline__ void slow_classify(ReadState &S, const SearchDir &sd, uint32_t read_len)
-{
-	const int l_ek = S.ix->l_ek;
-	const uint8_t *bin_read = sd.bin_read;
-	const dsb_seed *sv_f = sd.seed_v;
-	MemRst *mem_rst = S.ws.mem_rst;          // <= 31 searches * 8 results per seed
-	SeedInfo seed_info = {bin_read, read_len, sd.direction};
-	const uint8_t top0 = sd.l_seed_v ? sv_f[0].top : 0;
-	for (uint32_t i = 0; i < sd.l_seed_v; i++) {
-		const dsb_seed sv = sv_f[i];
-		if ((int)(sv.len) < 3 && top0 == 0) continue;            // sv_f->top: seed 0's flag, as written (cly.c:1564)
-		const int min_match_len = DSB_MIN(MIN_MEM_LEN_SLOW - 1, l_ek + 1);
-		S.sp_l = 0;
-		int mem_rst_num = 0;
-		for (int j = (int)sv.len - 1; j >= 1; j -= 2) {
-			const int k_idx = sv.offset + j;
-			const int s_idx = k_idx + l_ek - 1;
-			const uint64_t pre_v = prefix13(bin_read, s_idx);
-			const int n = bwt_MEM_search(S, bin_read + s_idx, pre_v, MEM_search_SLOW, min_match_len, s_idx, mem_rst + mem_rst_num);
-			for (int k = mem_rst_num; k < mem_rst_num + n; k++) mem_rst[k].read_offset = k_idx + l_ek - 1 - mem_rst[k].match_len;
-			mem_rst_num += n;
-		}
-		if (mem_rst_num == 0) continue;
-		if (mem_rst_num > 1) glibc_msort(mem_rst, mem_rst + 256, mem_rst_num, MemRstCmp());
-		const uint32_t a_b_idx = S.n_anc;
-		const int max_search = DSB_MIN(mem_rst_num, MEM_search_SLOW);
-		for (int k = 0; k < max_search; k++) { map_seed(S, mem_rst + k, seed_info); if (S.error) return; }
-		mark_useless(S, a_b_idx);
-	}
-	S.fast_classify = 0;
-}
+#include "dsb_seed.cuh"
 
 // ---------------------------------------------------------------- chaining (cly.c:38-52, 72-112, 201-349)
 struct ChainCmpByScore {
@@ -1209,8 +851,8 @@ __device__ void classify_read(const ClassifyParams &P, ReadState &S, uint32_t r)
 		if (sd[0].total_score < sd[1].total_score) { SearchDir t = sd[0]; sd[0] = sd[1]; sd[1] = t; }   // cly.c:1261-1266
 		const bool both_direction = ((sd[0].total_score - sd[1].total_score) <= (sd[0].total_score >> 3));
 		const int super_repeat = 0;                                   // always 0 in the reference (cly.c:849-888,1545)
-		{ PH_BEGIN(); fast_classify(S, sd[0], read_len); PH_END(S, 0); }
-		if (!S.error && both_direction) { PH_BEGIN(); fast_classify(S, sd[1], read_len); PH_END(S, 0); }
+		{ PH_BEGIN(); seed_pass(S, sd[0], read_len, false); PH_END(S, 0); }
+		if (!S.error && both_direction) { PH_BEGIN(); seed_pass(S, sd[1], read_len, false); PH_END(S, 0); }
 		if (!S.error) {
 			{ PH_BEGIN(); resolve_tree(S); PH_END(S, 1); }
 			bool run_slow_mode = false;
@@ -1221,11 +863,11 @@ __device__ void classify_read(const ClassifyParams &P, ReadState &S, uint32_t r)
 			}
 			if (run_slow_mode) {
 				S.n_anc = 0;
-				{ PH_BEGIN(); slow_classify(S, sd[0], read_len); PH_END(S, 2); }
+				{ PH_BEGIN(); seed_pass(S, sd[0], read_len, true); PH_END(S, 2); }
 				if (!S.error) {
 					{ PH_BEGIN(); resolve_tree(S); PH_END(S, 1); }
 					if (both_direction || S.n_hit <= 0 || (S.ws.chain[0].anchor_number < 5 && super_repeat < 3)) {
-						{ PH_BEGIN(); slow_classify(S, sd[1], read_len); PH_END(S, 2); }
+						{ PH_BEGIN(); seed_pass(S, sd[1], read_len, true); PH_END(S, 2); }
 						if (!S.error) { PH_BEGIN(); resolve_tree(S); PH_END(S, 1); }
 					}
 				}

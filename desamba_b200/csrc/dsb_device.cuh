@@ -24,8 +24,10 @@
 
 // ---- HBM layout of the index -------------------------------------------------------------------------------------
 // FM index: the reference's 168-byte blocks (5 x u64 counts + 256 nibbles, bwt.c:32-41) are re-cut at load time into
-// 128-byte lines of 128 symbols: u64 cnt[5] (A,C,G,T,#) | 24 B pad | 64 B nibbles (low nibble first).  One occ() is
-// one aligned 128-byte line = one L2/HBM request for the warp.
+// 128-byte lines of 128 symbols:  u64 cnt[5] (A,C,G,T,# before the line) at byte 0 | pad | bit-plane 0 at byte 48 |
+// bit-plane 1 at byte 64 | bit-plane 2 at byte 80 | pad.  Plane k holds bit k of the symbol code (A0 C1 G2 T3 #4 $5,
+// padding 7); symbol i of the line is bit i of the 128-bit little-endian plane.  occ() = 1 count word + 3 x 16 B =
+// 3 sectors of one aligned line, counted with and/xor/popc.
 struct DevIndex {
 	const uint8_t  *occ;        // n_lines * 128 B
 	uint64_t        n_lines;
@@ -75,61 +77,6 @@ __device__ __forceinline__ uint64_t dsb_hash64_2(uint64_t key)
 	key += ~(key << 27);
 	key ^= (key >> 31);
 	return key;
-}
-
-// number of nibbles equal to c among the first nv (0..16) nibbles of w
-__device__ __forceinline__ int nib_eq_count(uint64_t w, int nv, uint32_t c)
-{
-	uint64_t x = w ^ (0x1111111111111111ull * c);
-	x |= x >> 1; x |= x >> 2;
-	uint64_t m = ~x & 0x1111111111111111ull;
-	if (nv < 16) m &= (nv <= 0) ? 0ull : ((1ull << (nv * 4)) - 1);
-	return __popcll(m);
-}
-
-// occ(sp,c) and occ(ep,c) in one step (bwt.c:43-65 semantics: #c in BWT[0,r)).  Lanes 0-15 read the line of sp,
-// lanes 16-31 the line of ep (8 B each, two 128-B requests in one load instruction); counts are reduced inside
-// each half with xor-shuffles.  All lanes return the same pair.
-__device__ __forceinline__ void occ_pair(const DevIndex &ix, uint64_t sp, uint64_t ep, uint32_t c, uint64_t &o_sp, uint64_t &o_ep)
-{
-	const int lane = lane_id(), half = lane >> 4, h = lane & 15;
-	const uint64_t r = half ? ep : sp;
-	const uint64_t *line = (const uint64_t *)(ix.occ + (r >> 7) * 128);
-	const uint64_t w = __ldg(line + h);
-	const int in = (int)(r & 127);
-	int cnt = 0;
-	if (h >= 8) cnt = nib_eq_count(w, in - (h - 8) * 16, c);
-	cnt += __shfl_xor_sync(DSB_FULL, cnt, 8);
-	cnt += __shfl_xor_sync(DSB_FULL, cnt, 4);
-	cnt += __shfl_xor_sync(DSB_FULL, cnt, 2);
-	cnt += __shfl_xor_sync(DSB_FULL, cnt, 1);
-	const uint64_t base = __shfl_sync(DSB_FULL, w, (half << 4) + (int)c);
-	const uint64_t res = base + (uint64_t)cnt;
-	o_sp = __shfl_sync(DSB_FULL, res, 0);
-	o_ep = __shfl_sync(DSB_FULL, res, 16);
-}
-
-// occ(r, c) with the reference's "*c == 0xff -> take c = BWT[r]" mode (bwt.c:50-56).  Returns DOLLOR_POS for '$'.
-__device__ __forceinline__ uint64_t occ_one(const DevIndex &ix, uint64_t r, uint32_t &c)
-{
-	const int lane = lane_id(), h = lane & 15;
-	const uint64_t *line = (const uint64_t *)(ix.occ + (r >> 7) * 128);
-	const uint64_t w = __ldg(line + h);
-	const int in = (int)(r & 127);
-	if (c == 0xff) {
-		const uint64_t ww = __shfl_sync(DSB_FULL, w, 8 + (in >> 4));
-		c = (uint32_t)(ww >> ((in & 15) << 2)) & 0xf;
-		if (c == 5) return ix.dollar_pos;
-	}
-	int cnt = 0;
-	if (lane >= 8 && lane < 16) cnt = nib_eq_count(w, in - (h - 8) * 16, c);
-	cnt += __shfl_xor_sync(DSB_FULL, cnt, 8);
-	cnt += __shfl_xor_sync(DSB_FULL, cnt, 4);
-	cnt += __shfl_xor_sync(DSB_FULL, cnt, 2);
-	cnt += __shfl_xor_sync(DSB_FULL, cnt, 1);
-	cnt = __shfl_sync(DSB_FULL, cnt, 8);           // total of lanes 8..15 (xor tree keeps it inside aligned groups of 16)
-	const uint64_t base = __shfl_sync(DSB_FULL, w, (int)(c > 4 ? 4 : c));
-	return base + (uint64_t)cnt;
 }
 
 __device__ __forceinline__ uint32_t ref_base_at(const DevIndex &ix, uint64_t o)

@@ -53,15 +53,6 @@ int load_array(dsb_index *ix, const char *dir, const char *ext, size_t elem, boo
 	return upload(ix, buf.data(), bytes, extra, d_out);
 }
 
-inline void nib_counts(const uint8_t *p, int nbytes, uint64_t cnt[5])
-{
-	for (int i = 0; i < nbytes; i++) {
-		const uint8_t lo = p[i] & 0xf, hi = p[i] >> 4;
-		if (lo < 5) cnt[lo]++;
-		if (hi < 5) cnt[hi]++;
-	}
-}
-
 } // namespace
 
 extern "C" int dsb_index_load(const char *dir, int device, dsb_index **out)
@@ -90,8 +81,9 @@ extern "C" int dsb_index_load(const char *dir, int device, dsb_index **out)
 			memcpy(ix->dev.rank, rank, sizeof rank);
 			const uint64_t nb = byteLen / 168;
 			ix->bwt_len_blocks = nb;
-			// re-cut: 168-B blocks of 256 symbols -> 128-B lines of 128 symbols (+1 trailing line holding the totals,
-			// so that occ(len_bwt, c) is defined when len_bwt % 256 == 0; the reference reads past its array there)
+			// re-cut: 168-B blocks of 256 nibble symbols -> 128-B lines of 128 symbols as three bit-planes (dsb_device.cuh),
+			// +1 trailing line holding the totals so that occ(len_bwt, c) is defined when len_bwt % 256 == 0 (the reference
+			// reads past its array there)
 			const uint64_t n_lines = nb * 2 + 1;
 			std::vector<uint8_t> lines(n_lines * 128, 0);
 			uint64_t tot[5] = {0, 0, 0, 0, 0};
@@ -99,15 +91,26 @@ extern "C" int dsb_index_load(const char *dir, int device, dsb_index **out)
 				const uint8_t *src = blocks.data() + b * 168;
 				uint64_t cnt[5];
 				memcpy(cnt, src, 40);
-				uint8_t *l0 = lines.data() + (2 * b) * 128, *l1 = l0 + 128;
-				memcpy(l0, cnt, 40); memcpy(l0 + 64, src + 40, 64);
-				nib_counts(src + 40, 64, cnt);
-				memcpy(l1, cnt, 40); memcpy(l1 + 64, src + 40 + 64, 64);
-				nib_counts(src + 40 + 64, 64, cnt);
+				for (int half = 0; half < 2; half++) {
+					uint8_t *l = lines.data() + (2 * b + half) * 128;
+					const uint8_t *nib = src + 40 + 64 * half;
+					memcpy(l, cnt, 40);
+					uint64_t pl[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+					for (int i = 0; i < 128; i++) {
+						uint8_t v = (nib[i >> 1] >> ((i & 1) << 2)) & 0xf;
+						if (v < 5) cnt[v]++;
+						if (v > 5) v = 7;                                  // padding never equals a countable symbol
+						for (int k = 0; k < 3; k++) if ((v >> k) & 1) pl[k][i >> 6] |= 1ull << (i & 63);
+					}
+					memcpy(l + 48, pl[0], 16); memcpy(l + 64, pl[1], 16); memcpy(l + 80, pl[2], 16);
+				}
 				memcpy(tot, cnt, 40);
 			}
-			memcpy(lines.data() + (n_lines - 1) * 128, tot, 40);
-			memset(lines.data() + (n_lines - 1) * 128 + 64, 0xff, 64);
+			{
+				uint8_t *l = lines.data() + (n_lines - 1) * 128;
+				memcpy(l, tot, 40);
+				memset(l + 48, 0xff, 48);
+			}
 			blocks.clear(); blocks.shrink_to_fit();
 			void *d = nullptr;
 			if ((rc = upload(ix, lines.data(), lines.size(), 128, &d)) != DSB_OK) break;
