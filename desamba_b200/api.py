@@ -58,7 +58,9 @@ _sig("dsb_batch_run", C.c_int, _vp, C.c_int32)
 _sig("dsb_batch_download", C.c_int, _vp, _i32p, _vp, _vp, C.c_uint64, _u64p)
 _sig("dsb_batch_sync", C.c_int, _vp)
 _sig("dsb_batch_get_seeds", C.c_int, _vp, C.c_uint32, C.c_int, _vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32))
-_sig("dsb_batch_kernel_ms", C.c_int, _vp, C.POINTER(C.c_float * 4))
+_sig("dsb_batch_kernel_ms", C.c_int, _vp, C.POINTER(C.c_float * 10), C.c_int)
+_sig("dsb_ctx_mark", C.c_int, _vp, C.c_int)
+_sig("dsb_ctx_elapsed_ms", C.c_int, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_float))
 _sig("dsb_batch_launches", C.c_int, _vp)
 _sig("dsb_batch_counters", C.c_int, _vp, C.POINTER(C.c_uint64 * 16))
 _sig("dsb_batch_profile", C.c_int, _vp, _vp)
@@ -68,8 +70,10 @@ _sig("dsb_host_free", None, _vp)
 _sig("dsb_gather_bench", C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double))
 
 DSB_E_CAPACITY = -5
+KERNEL_NAMES = ["k_encode_probe", "k_islands", "k_seed(fast)", "k_chain(fast)", "k_seed(slow0)", "k_chain(slow0)", "k_seed(slow1)", "k_chain(slow1)",
+                "k_score", "k_finalize"]
 COUNTER_NAMES = ["hit_slots", "reads_taken", "first_long", "max_read_l", "n_bit0", "n_bit1", "n_prefix", "n_occ", "n_locate",
-                 "n_getref", "n_getref_bytes", "n_errors"]
+                 "n_getref_seed", "n_getref_bytes_seed", "n_errors", "n_getref_score", "n_getref_bytes_score"]
 
 
 class DsbError(RuntimeError):
@@ -247,9 +251,18 @@ class Context:
         return out, ts.value
 
     def kernel_ms(self):
-        ms = (C.c_float * 4)()
-        _check(lib.dsb_batch_kernel_ms(self._h, C.byref(ms)), "dsb_batch_kernel_ms")
+        """device ms of the 10 kernels of the last run (KERNEL_NAMES)"""
+        ms = (C.c_float * 10)()
+        _check(lib.dsb_batch_kernel_ms(self._h, C.byref(ms), 10), "dsb_batch_kernel_ms")
         return list(ms)
+
+    def mark(self, which):
+        _check(lib.dsb_ctx_mark(self._h, which), "dsb_ctx_mark")
+
+    def elapsed_ms(self, mark_a, other, mark_b):
+        ms = C.c_float(0)
+        _check(lib.dsb_ctx_elapsed_ms(self._h, mark_a, other._h, mark_b, C.byref(ms)), "dsb_ctx_elapsed_ms")
+        return ms.value
 
     def launches(self):
         return lib.dsb_batch_launches(self._h)
@@ -257,7 +270,10 @@ class Context:
     def counters(self):
         out = (C.c_uint64 * 16)()
         _check(lib.dsb_batch_counters(self._h, C.byref(out)), "dsb_batch_counters")
-        return dict(zip(COUNTER_NAMES, list(out)))
+        d = dict(zip(COUNTER_NAMES, list(out)))
+        d["n_getref"] = d["n_getref_seed"] + d["n_getref_score"]
+        d["n_getref_bytes"] = d["n_getref_bytes_seed"] + d["n_getref_bytes_score"]
+        return d
 
     def profile(self):
         """per-read phase times [n_reads, 8] in units of 1024 SM cycles (fast, chain, slow, kidx, middle, right, left, total)"""

@@ -163,14 +163,14 @@ static ScratchLayout scratch_layout(uint32_t max_anchors, uint32_t max_matches, 
 	return L;
 }
 
-struct ClassifyLaunch { ClassifyParams P; ScratchLayout L; unsigned long long *counters; };
+struct ClassifyLaunch { ClassifyParams P; ScratchLayout L; };
 
-__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_classify(const __grid_constant__ ClassifyLaunch A)
+// Persistent phase kernels: every warp pulls read ids from a work list (first seeding pass: all reads, longest first; later
+// phases: the lists the chain kernel fills) and runs one phase of classify_seq for that read in its own scratch.
+__device__ __forceinline__ void warp_setup(const ClassifyLaunch &A, ReadState &S, uint8_t *smem_raw)
 {
-	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int warp = threadIdx.x >> 5;
 	const uint32_t gw = blockIdx.x * CLASSIFY_WARPS_PER_BLOCK + warp;
-	ReadState S;
 	S.ix = &A.P.ix;
 	S.sm = (WarpSmem *)smem_raw + warp;
 	uint8_t *base = A.P.scratch + (uint64_t)gw * A.P.scratch_stride;
@@ -182,28 +182,41 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_classify(cons
 	S.ws.seed_rec = (SeedRec *)(base + A.L.seed_rec); S.ws.chunk_next = (uint32_t *)(base + A.L.chunk_next);
 	for (int s = 0; s < 2; s++) { S.ws.kidx_start[s] = (uint32_t *)(base + A.L.kstart[s]); S.ws.kidx_ent[s] = (KEntry *)(base + A.L.kent[s]); }
 	S.max_anchors = A.P.max_anchors; S.max_matches = A.P.max_matches;
-	for (;;) {
-		uint32_t r = 0;
-		if (lane_id() == 0) r = atomicAdd(A.P.work_counter, 1u);
-		r = __shfl_sync(DSB_FULL, r, 0);
-		if (r >= A.P.n_reads) break;
-		classify_read(A.P, S, r);
-		if (lane_id() == 0) {
-			unsigned long long *C = A.counters;
-			const dsb_read_result rr = A.P.rr[r];
-			if (rr.entered_final) {                       // Classify_buff_pool.max_read_l bookkeeping (cly.c:2958), resolved in K3
-				atomicMax(C + DSB_CNT_MAX_READ_L, (unsigned long long)rr.read_len);
-				if (rr.read_len >= 510) atomicMin(C + DSB_CNT_FIRST_LONG, (unsigned long long)r);
-			}
-			if (rr.error) atomicAdd(C + DSB_CNT_N_ERRORS, 1ull);
-			atomicAdd(C + DSB_CNT_N_PREFIX, (unsigned long long)S.c_prefix);
-			atomicAdd(C + DSB_CNT_N_OCC, (unsigned long long)S.c_occ);
-			atomicAdd(C + DSB_CNT_N_LOCATE, (unsigned long long)S.c_locate);
-			atomicAdd(C + DSB_CNT_N_GETREF, (unsigned long long)S.c_getref);
-			atomicAdd(C + DSB_CNT_N_GETREF_BYTES, (unsigned long long)S.c_getref_bytes);
-		}
-		__syncwarp();
-	}
+}
+// next read of the launch's work list, or 0xffffffff; list < 0: all reads in `order`
+__device__ __forceinline__ uint32_t next_read(const ClassifyParams &P, int list, int cursor)
+{
+	uint32_t i = 0;
+	if (lane_id() == 0) i = atomicAdd(P.ctl + CTL_CURSOR + cursor, 1u);
+	i = __shfl_sync(DSB_FULL, i, 0);
+	const uint32_t n = (list < 0) ? P.n_reads : P.ctl[CTL_LIST_N + list];
+	if (i >= n) return 0xffffffffu;
+	return (list < 0) ? P.order[i] : P.list[list][i];
+}
+
+__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_seed(const __grid_constant__ ClassifyLaunch A, int pass, int list, int cursor)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	ReadState S;
+	warp_setup(A, S, smem_raw);
+	DevAnchor *scratch_anc = S.ws.anc;
+	for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_seed(A.P, S, r, pass, scratch_anc);
+}
+
+__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_chain(const __grid_constant__ ClassifyLaunch A, int pass, int list, int cursor)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	ReadState S;
+	warp_setup(A, S, smem_raw);
+	for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_chain(A.P, S, r, pass);
+}
+
+__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_score(const __grid_constant__ ClassifyLaunch A, int list, int cursor)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	ReadState S;
+	warp_setup(A, S, smem_raw);
+	for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_score(A.P, S, r);
 }
 
 // ------------------------------------------------------------------------------------------------ K3
@@ -321,14 +334,12 @@ extern "C" int dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out)
 	if (c->opts.warps_per_sm > 32) c->opts.warps_per_sm = 32;
 	c->stream = nullptr; c->h_pin = nullptr; c->h_pin_cap = 0; c->ran = false; c->launches = 0;
 	c->n_reads = 0; c->scratch_stride = 0; c->kidx_bits = 0; c->kidx_len = 0; c->hits_cap = 0;
-	memset(c->kernel_ms, 0, sizeof c->kernel_ms);
 	cudaDeviceProp prop;
 	DSB_CUDA(cudaGetDeviceProperties(&prop, ix->device));
 	c->n_sm = prop.multiProcessorCount;
 	c->n_warps = c->n_sm * (int)(c->opts.warps_per_sm / CLASSIFY_WARPS_PER_BLOCK) * CLASSIFY_WARPS_PER_BLOCK;
 	DSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-	for (int i = 0; i < 6; i++) DSB_CUDA(cudaEventCreate(&c->ev[i]));
-	DSB_CUDA(cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CLASSIFY_WARPS_PER_BLOCK * sizeof(WarpSmem))));
+	for (int i = 0; i < DSB_N_EV; i++) DSB_CUDA(cudaEventCreate(&c->ev[i]));
 	int rc = ensure(c->counters, DSB_CNT_COUNT * 8);
 	if (rc != DSB_OK) { dsb_ctx_free(c); return rc; }
 	*out = c;
@@ -341,10 +352,11 @@ extern "C" void dsb_ctx_free(dsb_ctx *c)
 	cudaSetDevice(c->ix->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = {&c->seqs, &c->read_off, &c->bin_off, &c->bits_off, &c->seed_off, &c->tiles, &c->bin, &c->bits, &c->seeds[0], &c->seeds[1],
-	                  &c->n_seeds[0], &c->n_seeds[1], &c->total_score[0], &c->total_score[1], &c->scratch, &c->rr, &c->hits, &c->counters, &c->prof};
+	                  &c->n_seeds[0], &c->n_seeds[1], &c->total_score[0], &c->total_score[1], &c->scratch, &c->rr, &c->hits, &c->counters, &c->prof, &c->work, &c->anc_pool, &c->chain_pool,
+	                  &c->lists[0], &c->lists[1], &c->lists[2], &c->ctl, &c->order};
 	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
 	if (c->h_pin) cudaFreeHost(c->h_pin);
-	for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	for (int i = 0; i < DSB_N_EV; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -377,7 +389,7 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 		if (len >= 40) n_tiles += (len + PROBE_TILE - 1) / PROBE_TILE;
 		max_len = std::max(max_len, len);
 	}
-	const size_t pin_need = tbl_bytes * 3 + (size_t)(n_reads + 1) * 4 + n_tiles * 8 + 64;
+	const size_t pin_need = tbl_bytes * 3 + (size_t)(n_reads + 1) * 8 + n_tiles * 8 + 64;
 	if (pin_need > c->h_pin_cap) {
 		if (c->h_pin) cudaFreeHost(c->h_pin);
 		c->h_pin = nullptr; c->h_pin_cap = 0;
@@ -399,6 +411,10 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 		}
 	}
 	h_bin_off[n_reads] = bo; h_bits_off[n_reads] = wo; h_seed_off[n_reads] = (uint32_t)so;
+	// work order of the first seeding pass: longest reads first (the expensive tail starts early)
+	uint32_t *h_order = h_seed_off + n_reads + 1;
+	for (uint32_t r = 0; r < n_reads; r++) h_order[r] = r;
+	std::stable_sort(h_order, h_order + n_reads, [&](uint32_t a, uint32_t b) { return offs[a + 1] - offs[a] > offs[b + 1] - offs[b]; });
 	if (so >= 0xffffffffull) { dsb_set_error("batch too large (seed slots overflow 32 bits): split the batch"); return DSB_E_ARG; }
 	c->n_tiles = (uint32_t)n_tiles; c->n_bases = n_bases; c->bits_words = wo; c->seed_slots = so; c->bin_bytes = bo; c->max_len = max_len;
 	c->h_bits_off.assign(h_bits_off, h_bits_off + n_reads + 1);
@@ -411,7 +427,7 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 	    (rc = ensure(c->seeds[0], so * sizeof(dsb_seed) + 64)) || (rc = ensure(c->seeds[1], so * sizeof(dsb_seed) + 64)) ||
 	    (rc = ensure(c->n_seeds[0], (size_t)n_reads * 4)) || (rc = ensure(c->n_seeds[1], (size_t)n_reads * 4)) ||
 	    (rc = ensure(c->total_score[0], (size_t)n_reads * 4)) || (rc = ensure(c->total_score[1], (size_t)n_reads * 4)) ||
-	    (rc = ensure(c->rr, (size_t)n_reads * sizeof(dsb_read_result))))
+	    (rc = ensure(c->rr, (size_t)n_reads * sizeof(dsb_read_result))) || (rc = ensure(c->order, (size_t)n_reads * 4)))
 		return rc;
 	cudaStream_t st = c->stream;
 	DSB_CUDA(cudaMemcpyAsync(c->seqs.p, seqs, n_bases, cudaMemcpyHostToDevice, st));
@@ -420,6 +436,7 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 	DSB_CUDA(cudaMemcpyAsync(c->bits_off.p, h_bits_off, tbl_bytes, cudaMemcpyHostToDevice, st));
 	DSB_CUDA(cudaMemcpyAsync(c->seed_off.p, h_seed_off, (size_t)(n_reads + 1) * 4, cudaMemcpyHostToDevice, st));
 	if (n_tiles) DSB_CUDA(cudaMemcpyAsync(c->tiles.p, h_tiles, n_tiles * 8, cudaMemcpyHostToDevice, st));
+	DSB_CUDA(cudaMemcpyAsync(c->order.p, h_order, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
 	return DSB_OK;
 }
 
@@ -444,6 +461,14 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 	const uint64_t hits_cap = std::max<uint64_t>(4096, (uint64_t)n * 24);
 	if ((rc = ensure(c->hits, hits_cap * sizeof(dsb_hit))) != DSB_OK) return rc;
 	if ((rc = ensure(c->prof, (size_t)n * 32)) != DSB_OK) return rc;
+	// state between the phase kernels: per-read records, anchor / chain pools (bump-allocated per read), work lists
+	const uint64_t anc_cap = c->n_bases / 8 + 64ull * n + (1u << 16), chain_cap = c->n_bases / 32 + 16ull * n + (1u << 14);
+	if ((rc = ensure(c->work, (size_t)n * sizeof(ReadWork))) || (rc = ensure(c->anc_pool, anc_cap * sizeof(DevAnchor))) ||
+	    (rc = ensure(c->chain_pool, chain_cap * sizeof(DevChain))) || (rc = ensure(c->ctl, CTL_WORDS * 4)))
+		return rc;
+	for (int l = 0; l < N_LISTS; l++) if ((rc = ensure(c->lists[l], (size_t)n * 4)) != DSB_OK) return rc;
+	DSB_CUDA(cudaMemsetAsync(c->ctl.p, 0, CTL_WORDS * 4, st));
+	DSB_CUDA(cudaMemsetAsync(c->prof.p, 0, (size_t)n * 32, st));
 	c->hits_cap = c->hits.cap / sizeof(dsb_hit);
 	unsigned long long *cnt = (unsigned long long *)c->counters.p;
 	DSB_CUDA(cudaMemsetAsync(cnt, 0, DSB_CNT_COUNT * 8, st));
@@ -473,17 +498,29 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		P.ix = c->ix->dev; P.n_reads = n; P.read_off = (const uint64_t *)c->read_off.p; P.bin_off = (const uint64_t *)c->bin_off.p; P.bin = (const uint8_t *)c->bin.p;
 		P.seed_off = (const uint32_t *)c->seed_off.p;
 		for (int s = 0; s < 2; s++) { P.seeds[s] = (const dsb_seed *)c->seeds[s].p; P.n_seeds[s] = (const uint32_t *)c->n_seeds[s].p; P.total_score[s] = (const uint32_t *)c->total_score[s].p; }
-		P.work_counter = (uint32_t *)(cnt + DSB_CNT_WORK);
-		P.prof = (uint32_t *)c->prof.p;
+		P.order = (const uint32_t *)c->order.p; P.prof = (uint32_t *)c->prof.p;
+		P.work = (ReadWork *)c->work.p;
+		P.anc_pool = (DevAnchor *)c->anc_pool.p; P.anc_pool_cap = (uint32_t)std::min<uint64_t>(c->anc_pool.cap / sizeof(DevAnchor), 0xfffffff0u);
+		P.chain_pool = (DevChain *)c->chain_pool.p; P.chain_pool_cap = (uint32_t)std::min<uint64_t>(c->chain_pool.cap / sizeof(DevChain), 0xfffffff0u);
+		for (int l = 0; l < N_LISTS; l++) P.list[l] = (uint32_t *)c->lists[l].p;
+		P.ctl = (uint32_t *)c->ctl.p;
 		P.scratch = (uint8_t *)c->scratch.p; P.scratch_stride = L.total;
 		P.max_anchors = c->opts.max_anchors; P.max_matches = c->opts.max_matches; P.kidx_bits_max = c->kidx_bits; P.kidx_len_max = c->kidx_len;
 		P.rr = (dsb_read_result *)c->rr.p; P.hits = (dsb_hit *)c->hits.p; P.hits_cap = c->hits_cap; P.hits_cursor = cnt + DSB_CNT_HITS_CURSOR;
-		A.L = L; A.counters = cnt;
-		const int blocks = c->n_warps / CLASSIFY_WARPS_PER_BLOCK;
-		k_classify<<<blocks, CLASSIFY_WARPS_PER_BLOCK * 32, CLASSIFY_WARPS_PER_BLOCK * sizeof(WarpSmem), st>>>(A);
-		c->launches++;
+		P.counters = cnt;
+		A.L = L;
+		const int blocks = c->n_warps / CLASSIFY_WARPS_PER_BLOCK, threads = CLASSIFY_WARPS_PER_BLOCK * 32;
+		const size_t smem = CLASSIFY_WARPS_PER_BLOCK * sizeof(WarpSmem);
+		// classify_seq's control flow (cly.c:3098-3131) as a sequence of phase kernels over work lists
+		k_seed <<<blocks, threads, smem, st>>>(A, PASS_FAST, -1, 0);            DSB_CUDA(cudaEventRecord(c->ev[3], st));
+		k_chain<<<blocks, threads, smem, st>>>(A, PASS_FAST, -1, 1);            DSB_CUDA(cudaEventRecord(c->ev[4], st));
+		k_seed <<<blocks, threads, smem, st>>>(A, PASS_SLOW0, LIST_SLOW0, 2);   DSB_CUDA(cudaEventRecord(c->ev[5], st));
+		k_chain<<<blocks, threads, smem, st>>>(A, PASS_SLOW0, LIST_SLOW0, 3);   DSB_CUDA(cudaEventRecord(c->ev[6], st));
+		k_seed <<<blocks, threads, smem, st>>>(A, PASS_SLOW1, LIST_SLOW1, 4);   DSB_CUDA(cudaEventRecord(c->ev[7], st));
+		k_chain<<<blocks, threads, smem, st>>>(A, PASS_SLOW1, LIST_SLOW1, 5);   DSB_CUDA(cudaEventRecord(c->ev[8], st));
+		k_score<<<blocks, threads, smem, st>>>(A, LIST_SCORE, 6);               DSB_CUDA(cudaEventRecord(c->ev[9], st));
+		c->launches += 7;
 	}
-	DSB_CUDA(cudaEventRecord(c->ev[3], st));
 	{
 		FinalizeParams P;
 		P.n_reads = n; P.max_read_l_in = max_read_l_in;
@@ -492,7 +529,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		k_finalize<<<(n + 127) / 128, 128, 0, st>>>(P);
 		c->launches++;
 	}
-	DSB_CUDA(cudaEventRecord(c->ev[4], st));
+	DSB_CUDA(cudaEventRecord(c->ev[10], st));
 	DSB_CUDA(cudaGetLastError());
 	c->ran = true;
 	return DSB_OK;
@@ -560,12 +597,29 @@ extern "C" int dsb_batch_get_seeds(dsb_ctx *c, uint32_t read, int strand, dsb_se
 	return DSB_OK;
 }
 
-extern "C" int dsb_batch_kernel_ms(dsb_ctx *c, float ms[4])
+extern "C" int dsb_batch_kernel_ms(dsb_ctx *c, float *ms, int cap)
 {
 	if (!c || !c->ran || !ms) return DSB_E_ARG;
 	DSB_CUDA(cudaSetDevice(c->ix->device));
 	DSB_CUDA(cudaStreamSynchronize(c->stream));
-	for (int i = 0; i < 4; i++) { ms[i] = 0; if (c->n_reads) DSB_CUDA(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1])); }
+	for (int i = 0; i < DSB_N_KERNELS && i < cap; i++) { ms[i] = 0; if (c->n_reads) DSB_CUDA(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1])); }
+	return DSB_OK;
+}
+
+// stream marks for timing several batches in flight: mark 0/1 = events on this context's stream; elapsed = b.mark_b - a.mark_a
+extern "C" int dsb_ctx_mark(dsb_ctx *c, int which)
+{
+	if (!c || which < 0 || which > 1) return DSB_E_ARG;
+	DSB_CUDA(cudaSetDevice(c->ix->device));
+	DSB_CUDA(cudaEventRecord(c->ev[DSB_N_KERNELS + 1 + which], c->stream));
+	return DSB_OK;
+}
+extern "C" int dsb_ctx_elapsed_ms(dsb_ctx *a, int mark_a, dsb_ctx *b, int mark_b, float *ms)
+{
+	if (!a || !b || !ms || (mark_a | mark_b) < 0 || mark_a > 1 || mark_b > 1) return DSB_E_ARG;
+	DSB_CUDA(cudaSetDevice(a->ix->device));
+	DSB_CUDA(cudaEventSynchronize(b->ev[DSB_N_KERNELS + 1 + mark_b]));
+	DSB_CUDA(cudaEventElapsedTime(ms, a->ev[DSB_N_KERNELS + 1 + mark_a], b->ev[DSB_N_KERNELS + 1 + mark_b]));
 	return DSB_OK;
 }
 

@@ -61,6 +61,17 @@ struct WarpScratch {            // per-warp HBM scratch
 	uint32_t  *chunk_next;      // max_anchors / ANCHOR_CHUNK links
 };
 
+// per-read state that lives in HBM between the phase kernels
+struct ReadWork {
+	uint32_t anc_off, n_anc;      // the read's anchors in the anchor pool (cly_r.anchor_v)
+	uint32_t chain_off, n_chain;  // chains kept by resolve_tree, in the chain pool
+	uint16_t error; uint8_t fast_classify, pad;
+};
+enum { LIST_SLOW0 = 0, LIST_SLOW1 = 1, LIST_SCORE = 2, N_LISTS = 3 };
+enum { PASS_FAST = 0, PASS_SLOW0 = 1, PASS_SLOW1 = 2 };
+// control block (u32): [0..2] list lengths, [3] anchor pool cursor, [4] chain pool cursor, [8..15] work cursors of the launches
+enum { CTL_LIST_N = 0, CTL_ANC_CURSOR = 3, CTL_CHAIN_CURSOR = 4, CTL_CURSOR = 8, CTL_WORDS = 32 };
+
 struct ClassifyParams {
 	DevIndex ix;
 	uint32_t n_reads;
@@ -71,14 +82,21 @@ struct ClassifyParams {
 	const dsb_seed *seeds[2];   // [0] forward strand, [1] reverse strand
 	const uint32_t *n_seeds[2];
 	const uint32_t *total_score[2];
-	uint32_t *work_counter;
+	const uint32_t *order;      // read ids, longest first (work order of the first seeding pass)
 	uint32_t *prof;             // per read: 8 x u32 phase times in units of 1024 cycles (fast, chain, slow, kidx, middle, right, left, total)
-	// scratch
+	// state between the phase kernels
+	ReadWork *work;
+	DevAnchor *anc_pool; uint32_t anc_pool_cap;
+	DevChain *chain_pool; uint32_t chain_pool_cap;
+	uint32_t *list[N_LISTS];
+	uint32_t *ctl;
+	// per-warp scratch
 	uint8_t  *scratch; uint64_t scratch_stride;
 	uint32_t max_anchors, max_matches, kidx_bits_max, kidx_len_max;
 	// outputs
 	dsb_read_result *rr;
 	dsb_hit *hits; uint64_t hits_cap; unsigned long long *hits_cursor;
+	unsigned long long *counters;
 };
 
 struct SearchDir {              // SEARCH_DIR (cly.c:946-954)
@@ -398,68 +416,89 @@ __device__ __forceinline__ bool sms_push(ReadState &S, uint32_t t_pos, uint32_t 
 	return true;
 }
 
-__device__ __noinline__ void sdp_match(ReadState &S, uint32_t q_bg, uint32_t q_ed, const uint8_t *q_str, const uint8_t *t_str, uint32_t t_len,
-                                       const KIdx &kx, uint32_t t_st, bool isForward)
-{   // cly.c:2335-2440
-	const uint32_t t_kmer_num = t_len - S_A_KEMR_L + 1;
-	const uint32_t MASK = (1u << (2 * S_A_KEMR_L)) - 1;
-	if (isForward) {
-		const uint8_t *c_t_str = t_str + 4;
-		uint32_t kmer = 0;
-		for (int k = 0; k < S_A_KEMR_L - 1; k++) kmer = (kmer << 2) | c_t_str[k];
-		for (int i = 4; (uint32_t)i < t_kmer_num; i++, c_t_str++) {
-			kmer = ((kmer << 2) | c_t_str[S_A_KEMR_L - 1]) & MASK;
-			if ((i & 0x03) != 0) continue;
-			const uint32_t key = kmer & kx.kmask;
-			uint32_t e = key ? kx.start[key - 1] : 0;
-			const uint32_t e_end = kx.start[key];
-			for (; e < e_end; e++) {
-				const KEntry en = kx.ent[e];
-				if (en.kmer != kmer) continue;
-				const uint32_t q_pos = en.pos;
-				if (q_pos >= q_bg && q_pos <= q_ed) {
-					const int back_len = MEM_search_bwd(q_str + q_pos - 1, c_t_str - 1, 4);
-					if (back_len < 4 || i == 4) {
-						uint32_t max_search = q_ed - q_pos - 1;
-						max_search = DSB_MIN(max_search, t_len - i - 1) + OVER_SEARCH_M2;
-						const int forward_len = MEM_search_fwd(q_str + q_pos + S_A_KEMR_L, c_t_str + S_A_KEMR_L, max_search);
-						const int total_len = back_len + forward_len + 1;
-						if (total_len >= 4)
-							if (!sms_push(S, i - back_len + t_st, q_pos - back_len, total_len)) return;
-					}
+// sdp_match (cly.c:2335-2440): 9-mer matches between a reference window and the read, one LANE per scanned target position
+// (every 4th).  The reference pushes matches in (target scan order, ascending read position) order; lanes keep that order by
+// an ordered compaction of each round of 32 positions.  kmer(i) is rebuilt from the window instead of rolled.
+struct SdpArgs { uint32_t q_bg, q_ed; const uint8_t *q_str, *t_str; uint32_t t_len, t_st; KIdx kx; };
+
+template <bool FWD>
+__device__ __forceinline__ uint32_t sdp_scan_pos(const SdpArgs &A, int i, DevSms *out, uint32_t cap)
+{   // all matches of target position i; writes the first `cap` of them to out[], returns their number
+	const uint8_t *c_t_str = FWD ? (A.t_str + i) : (A.t_str + A.t_len - S_A_KEMR_L - i);
+	uint32_t kmer = 0;
+	#pragma unroll
+	for (int k = 0; k < S_A_KEMR_L; k++) kmer = (kmer << 2) | c_t_str[k];
+	const uint32_t key = kmer & A.kx.kmask;
+	uint32_t e = key ? A.kx.start[key - 1] : 0;
+	const uint32_t e_end = A.kx.start[key];
+	uint32_t n = 0;
+	for (; e < e_end; e++) {
+		const KEntry en = A.kx.ent[e];
+		if (en.kmer != kmer) continue;
+		const uint32_t q_pos = en.pos;
+		if (!(q_pos >= A.q_bg && q_pos <= A.q_ed)) continue;
+		if (FWD) {
+			const int back_len = MEM_search_bwd(A.q_str + q_pos - 1, c_t_str - 1, 4);
+			if (back_len < 4 || i == 4) {
+				uint32_t max_search = A.q_ed - q_pos - 1;
+				max_search = DSB_MIN(max_search, A.t_len - i - 1) + OVER_SEARCH_M2;
+				const int forward_len = MEM_search_fwd(A.q_str + q_pos + S_A_KEMR_L, c_t_str + S_A_KEMR_L, max_search);
+				const int total_len = back_len + forward_len + 1;
+				if (total_len >= 4) {
+					if (n < cap) { out[n].t_pos = i - back_len + A.t_st; out[n].q_pos = q_pos - back_len; out[n].len = total_len; }
+					n++;
 				}
 			}
-		}
-	} else {
-		const uint8_t *c_t_str = t_str + t_len - S_A_KEMR_L - 4;
-		uint32_t kmer = 0;
-		for (int k = 0; k < S_A_KEMR_L; k++) kmer = (kmer << 2) | c_t_str[k];
-		uint64_t kmer64 = (uint64_t)kmer << 2;                               // bit2_preKmer_init
-		for (int i = 4; (uint32_t)i < t_kmer_num; i++, c_t_str--) {
-			kmer64 = (kmer64 >> 2) | ((uint64_t)c_t_str[0] << ((S_A_KEMR_L << 1) - 2));
-			if ((i & 0x03) != 0) continue;
-			kmer = (uint32_t)kmer64;
-			const uint32_t key = kmer & kx.kmask;
-			uint32_t e = key ? kx.start[key - 1] : 0;
-			const uint32_t e_end = kx.start[key];
-			for (; e < e_end; e++) {
-				const KEntry en = kx.ent[e];
-				if (en.kmer != kmer) continue;
-				const uint32_t q_pos = en.pos;
-				if (q_pos >= q_bg && q_pos <= q_ed) {
-					const int forward_len = MEM_search_fwd(q_str + q_pos + S_A_KEMR_L, c_t_str + S_A_KEMR_L, 4);
-					if (forward_len < 4 || i == 4) {
-						uint32_t max_search = q_pos;
-						max_search = DSB_MIN((long)max_search, (long)(c_t_str - t_str)) + OVER_SEARCH_M2;
-						const int back_len = MEM_search_bwd(q_str + q_pos - 1, c_t_str - 1, max_search);
-						const int total_len = back_len + forward_len + 1;
-						if (total_len >= 4)
-							if (!sms_push(S, (uint32_t)((long)(c_t_str - t_str) - back_len + t_st), q_pos - back_len, total_len)) return;
-					}
+		} else {
+			const int forward_len = MEM_search_fwd(A.q_str + q_pos + S_A_KEMR_L, c_t_str + S_A_KEMR_L, 4);
+			if (forward_len < 4 || i == 4) {
+				uint32_t max_search = q_pos;
+				max_search = DSB_MIN((long)max_search, (long)(c_t_str - A.t_str)) + OVER_SEARCH_M2;
+				const int back_len = MEM_search_bwd(A.q_str + q_pos - 1, c_t_str - 1, max_search);
+				const int total_len = back_len + forward_len + 1;
+				if (total_len >= 4) {
+					if (n < cap) { out[n].t_pos = (uint32_t)((long)(c_t_str - A.t_str) - back_len + A.t_st); out[n].q_pos = q_pos - back_len; out[n].len = total_len; }
+					n++;
 				}
 			}
 		}
 	}
+	return n;
+}
+
+template <bool FWD>
+__device__ __forceinline__ void sdp_match_warp(ReadState &S, const SdpArgs &A)
+{
+	if (A.t_len < S_A_KEMR_L + 4) return;
+	const uint32_t t_kmer_num = A.t_len - S_A_KEMR_L + 1;
+	const uint32_t n_pos = (t_kmer_num > 4) ? (t_kmer_num - 4 + 3) / 4 : 0;       // i = 4, 8, ... < t_kmer_num
+	const int lane = lane_id();
+	for (uint32_t base = 0; base < n_pos; base += 32) {
+		const uint32_t k = base + lane;
+		const int i = 4 + 4 * (int)k;
+		DevSms loc[2];
+		const uint32_t cnt = (k < n_pos) ? sdp_scan_pos<FWD>(A, i, loc, 2) : 0;
+		uint32_t x = cnt;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(DSB_FULL, x, d); if (lane >= d) x += y; }
+		const uint32_t total = __shfl_sync(DSB_FULL, x, 31);
+		if (total == 0) continue;
+		if (S.n_sms + total > S.max_matches) { S.error = 2; return; }
+		DevSms *dst = S.ws.sms + S.n_sms + (x - cnt);
+		if (cnt <= 2) { for (uint32_t m = 0; m < cnt; m++) { dst[m].t_pos = loc[m].t_pos; dst[m].q_pos = loc[m].q_pos; dst[m].len = loc[m].len; } }
+		else sdp_scan_pos<FWD>(A, i, dst, cnt);
+		S.n_sms += total;
+		__syncwarp();
+	}
+}
+
+__device__ __noinline__ void sdp_match(ReadState &S, uint32_t q_bg, uint32_t q_ed, const uint8_t *q_str, const uint8_t *t_str, uint32_t t_len,
+                                       const KIdx &kx, uint32_t t_st, bool isForward)
+{
+	SdpArgs A; A.q_bg = q_bg; A.q_ed = q_ed; A.q_str = q_str; A.t_str = t_str; A.t_len = t_len; A.t_st = t_st; A.kx = kx;
+	__syncwarp();
+	if (isForward) sdp_match_warp<true>(S, A); else sdp_match_warp<false>(S, A);
+	__syncwarp();
 }
 
 __device__ __forceinline__ void refwin_zero(ReadState &S, int nbytes)     // zero-initialised stack window (policy P1)
@@ -519,24 +558,32 @@ __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8
 					int max_score = c_spd.len;
 					const uint32_t max_q = c_spd.q_pos + MAX_sms_overlap_middle;
 					const uint32_t max_t = c_spd.t_pos + MAX_sms_overlap_middle;
-					for (int pbase = (int)ci - 1; pbase >= 0; pbase -= 32) {
-						const int pi = pbase - lane_id();
-						if (pi < 0) continue;
-						const DevSms c_pre = load_sms(base + pi);
-						const int pre_q_ed = c_pre.q_pos + c_pre.len + S_A_KEMR_L - 1;
-						const int pre_t_ed = c_pre.t_pos + c_pre.len + S_A_KEMR_L - 1;
-						if (pre_q_ed > max_q) continue;
-						if (pre_t_ed > max_t) continue;
-						const int indel = c_pre.q_pos - c_pre.t_pos - (max_q - max_t);
-						const int ABS_indel = DSB_ABS(indel);
-						if (ABS_indel > 200) continue;
-						int new_score = c_pre.score + c_spd.len - (ABS_indel >> 3);
-						if (pre_q_ed > c_spd.q_pos || pre_t_ed > c_spd.t_pos) {
-							const int overlap_q = pre_q_ed - c_spd.q_pos;
-							const int overlap_t = pre_t_ed - c_spd.t_pos;
-							new_score -= DSB_MAX(overlap_q, overlap_t);
+					for (int pbase = (int)ci - 1; pbase >= 0; pbase -= 128) {
+						DevSms e[4];
+						#pragma unroll
+						for (int u = 0; u < 4; u++) {                     // 4 independent 16-byte loads in flight per lane
+							const int pi = pbase - 32 * u - lane_id();
+							e[u].t_pos = e[u].q_pos = e[u].len = e[u].score = 0;
+							if (pi >= 0) e[u] = load_sms(base + pi);
 						}
-						max_score = DSB_MAX(max_score, new_score);
+						#pragma unroll
+						for (int u = 0; u < 4; u++) {
+							const int pi = pbase - 32 * u - lane_id();
+							const DevSms c_pre = e[u];
+							const int pre_q_ed = c_pre.q_pos + c_pre.len + S_A_KEMR_L - 1;
+							const int pre_t_ed = c_pre.t_pos + c_pre.len + S_A_KEMR_L - 1;
+							const int indel = c_pre.q_pos - c_pre.t_pos - (max_q - max_t);
+							const int ABS_indel = DSB_ABS(indel);
+							if (pi >= 0 && !(pre_q_ed > max_q) && !(pre_t_ed > max_t) && !(ABS_indel > 200)) {
+								int new_score = c_pre.score + c_spd.len - (ABS_indel >> 3);
+								if (pre_q_ed > c_spd.q_pos || pre_t_ed > c_spd.t_pos) {
+									const int overlap_q = pre_q_ed - c_spd.q_pos;
+									const int overlap_t = pre_t_ed - c_spd.t_pos;
+									new_score -= DSB_MAX(overlap_q, overlap_t);
+								}
+								max_score = DSB_MAX(max_score, new_score);
+							}
+						}
 					}
 					__syncwarp();
 					max_score = warp_max(max_score);
@@ -598,31 +645,42 @@ __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, con
 		int max_score = c_sms.len;
 		const uint32_t max_pre_q = c_sms.q_pos + MAX_sms_overlap;
 		const uint32_t max_pre_t = c_sms.t_pos + MAX_sms_overlap;
-		for (int pbase = (int)current_sms - 2; pbase >= 0; pbase -= 32) {
-			const int pi = pbase - lane_id();
-			const bool act = pi >= 0;
-			DevSms c_pre; c_pre.t_pos = c_pre.q_pos = c_pre.len = c_pre.score = 0;
-			if (act) c_pre = load_sms(sms + pi);
-			const int pre_q_ed = c_pre.q_pos + c_pre.len + S_A_KEMR_L - 1;
-			const int pre_t_ed = c_pre.t_pos + c_pre.len + S_A_KEMR_L - 1;
-			const bool pass = act && !(pre_q_ed > max_pre_q) && !(pre_t_ed > max_pre_t);
-			const bool brk = pass && (c_pre.t_pos + 600 < max_pre_t);
-			const uint32_t bm = __ballot_sync(DSB_FULL, brk);
-			const int first = bm ? (__ffs(bm) - 1) : 32;
-			if (pass && lane_id() < first) {
-				const int indel = c_pre.q_pos - c_pre.t_pos - (max_pre_q - max_pre_t);
-				const int ABS_indel = DSB_ABS(indel);
-				if (!(ABS_indel > 200)) {
-					int new_score = c_pre.score + c_sms.len - (ABS_indel >> 3);
-					if (pre_q_ed > c_sms.q_pos || pre_t_ed > c_sms.t_pos) {
-						const int overlap_q = pre_q_ed - c_sms.q_pos;
-						const int overlap_t = pre_t_ed - c_sms.t_pos;
-						new_score -= DSB_MAX(overlap_q, overlap_t);
-					}
-					max_score = DSB_MAX(max_score, new_score);
-				}
+		for (int pbase = (int)current_sms - 2; pbase >= 0; pbase -= 128) {
+			DevSms e[4];
+			#pragma unroll
+			for (int u = 0; u < 4; u++) {                                 // 4 independent 16-byte loads in flight per lane
+				const int pi = pbase - 32 * u - lane_id();
+				e[u].t_pos = e[u].q_pos = e[u].len = e[u].score = 0;
+				if (pi >= 0) e[u] = load_sms(sms + pi);
 			}
-			if (bm) break;
+			bool stop = false;
+			#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				if (stop) continue;                                       // warp-uniform
+				const bool act = (pbase - 32 * u - lane_id()) >= 0;
+				const DevSms c_pre = e[u];
+				const int pre_q_ed = c_pre.q_pos + c_pre.len + S_A_KEMR_L - 1;
+				const int pre_t_ed = c_pre.t_pos + c_pre.len + S_A_KEMR_L - 1;
+				const bool pass = act && !(pre_q_ed > max_pre_q) && !(pre_t_ed > max_pre_t);
+				const bool brk = pass && (c_pre.t_pos + 600 < max_pre_t);
+				const uint32_t bm = __ballot_sync(DSB_FULL, brk);
+				const int first = bm ? (__ffs(bm) - 1) : 32;
+				if (pass && lane_id() < first) {
+					const int indel = c_pre.q_pos - c_pre.t_pos - (max_pre_q - max_pre_t);
+					const int ABS_indel = DSB_ABS(indel);
+					if (!(ABS_indel > 200)) {
+						int new_score = c_pre.score + c_sms.len - (ABS_indel >> 3);
+						if (pre_q_ed > c_sms.q_pos || pre_t_ed > c_sms.t_pos) {
+							const int overlap_q = pre_q_ed - c_sms.q_pos;
+							const int overlap_t = pre_t_ed - c_sms.t_pos;
+							new_score -= DSB_MAX(overlap_q, overlap_t);
+						}
+						max_score = DSB_MAX(max_score, new_score);
+					}
+				}
+				if (bm) stop = true;
+			}
+			if (stop) break;
 		}
 		max_score = warp_max(max_score);
 		if (lane_id() == 0) sms[ci].score = max_score;
@@ -695,29 +753,40 @@ __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, cons
 		int max_score = c_sms.len;
 		const uint32_t min_pre_q = c_sms.q_pos + c_sms.len - MAX_sms_overlap + S_A_KEMR_L - 1;
 		const uint32_t min_pre_t = c_sms.t_pos + c_sms.len - MAX_sms_overlap + S_A_KEMR_L - 1;
-		for (int pbase = (int)current_sms - 2; pbase >= 0; pbase -= 32) {
-			const int pi = pbase - lane_id();
-			const bool act = pi >= 0;
-			DevSms c_pre; c_pre.t_pos = c_pre.q_pos = c_pre.len = c_pre.score = 0;
-			if (act) c_pre = load_sms(sms + pi);
-			const bool pass = act && !(c_pre.q_pos < min_pre_q) && !(c_pre.t_pos < min_pre_t);
-			const bool brk = pass && (min_pre_t + 600 < c_pre.t_pos);
-			const uint32_t bm = __ballot_sync(DSB_FULL, brk);
-			const int first = bm ? (__ffs(bm) - 1) : 32;
-			if (pass && lane_id() < first) {
-				const int indel = c_pre.q_pos - c_pre.t_pos - (min_pre_q - min_pre_t);
-				const int ABS_indel = DSB_ABS(indel);
-				if (!(ABS_indel > 200)) {
-					int new_score = c_pre.score + c_sms.len - (ABS_indel >> 3);
-					if (min_pre_q + MAX_sms_overlap > c_pre.q_pos || min_pre_t + MAX_sms_overlap > c_pre.t_pos) {
-						const int overlap_q = min_pre_q + MAX_sms_overlap - c_pre.q_pos;
-						const int overlap_t = min_pre_t + MAX_sms_overlap - c_pre.t_pos;
-						new_score -= DSB_MAX(overlap_q, overlap_t);
-					}
-					max_score = DSB_MAX(max_score, new_score);
-				}
+		for (int pbase = (int)current_sms - 2; pbase >= 0; pbase -= 128) {
+			DevSms e[4];
+			#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int pi = pbase - 32 * u - lane_id();
+				e[u].t_pos = e[u].q_pos = e[u].len = e[u].score = 0;
+				if (pi >= 0) e[u] = load_sms(sms + pi);
 			}
-			if (bm) break;
+			bool stop = false;
+			#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				if (stop) continue;                                       // warp-uniform
+				const bool act = (pbase - 32 * u - lane_id()) >= 0;
+				const DevSms c_pre = e[u];
+				const bool pass = act && !(c_pre.q_pos < min_pre_q) && !(c_pre.t_pos < min_pre_t);
+				const bool brk = pass && (min_pre_t + 600 < c_pre.t_pos);
+				const uint32_t bm = __ballot_sync(DSB_FULL, brk);
+				const int first = bm ? (__ffs(bm) - 1) : 32;
+				if (pass && lane_id() < first) {
+					const int indel = c_pre.q_pos - c_pre.t_pos - (min_pre_q - min_pre_t);
+					const int ABS_indel = DSB_ABS(indel);
+					if (!(ABS_indel > 200)) {
+						int new_score = c_pre.score + c_sms.len - (ABS_indel >> 3);
+						if (min_pre_q + MAX_sms_overlap > c_pre.q_pos || min_pre_t + MAX_sms_overlap > c_pre.t_pos) {
+							const int overlap_q = min_pre_q + MAX_sms_overlap - c_pre.q_pos;
+							const int overlap_t = min_pre_t + MAX_sms_overlap - c_pre.t_pos;
+							new_score -= DSB_MAX(overlap_q, overlap_t);
+						}
+						max_score = DSB_MAX(max_score, new_score);
+					}
+				}
+				if (bm) stop = true;
+			}
+			if (stop) break;
 		}
 		max_score = warp_max(max_score);
 		if (lane_id() == 0) sms[ci].score = max_score;
@@ -829,64 +898,177 @@ __device__ __noinline__ void score_and_merge(ReadState &S, const SearchDir *sear
 
 // ---------------------------------------------------------------- classify_seq (cly.c:3064-3132) up to the class filter
 #define MIN_READ_LEN 40
-__device__ void classify_read(const ClassifyParams &P, ReadState &S, uint32_t r)
+// ================================================================ the phases of classify_seq (cly.c:3064-3132)
+// classify_seq is cut at its decision points into three kinds of work, each run by its own kernel over a list of reads
+// (so that all warps of the GPU execute the same code at the same time):
+//   seed   fast_classify / slow_classify of the strand(s)            -> anchors appended to the read's anchor vector
+//   chain  resolve_tree + the run_slow_mode decisions (cly.c:3101-3127) -> next list: slow pass 0, slow pass 1 or scoring
+//   score  delete_small_score_rst up to the class filter (cly.c:2883-2957) -> pre-filter hits for the finalize kernel
+__device__ __forceinline__ bool setup_dirs(const ClassifyParams &P, uint32_t r, uint32_t read_len, SearchDir sd[2])
 {
-	const uint32_t read_len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
+	const uint8_t *bin_F = P.bin + P.bin_off[r] + DSB_GUARD;
+	for (int s = 0; s < 2; s++) {
+		sd[s].seed_v = P.seeds[s] + P.seed_off[r];
+		sd[s].l_seed_v = P.n_seeds[s][r];
+		sd[s].bin_read = s ? bin_F + read_len : bin_F;
+		sd[s].direction = s ? DSB_REVERSE : DSB_FORWARD;
+		sd[s].total_score = P.total_score[s][r];
+	}
+	if (sd[0].total_score < sd[1].total_score) { SearchDir t = sd[0]; sd[0] = sd[1]; sd[1] = t; }   // cly.c:1261-1266
+	return ((sd[0].total_score - sd[1].total_score) <= (sd[0].total_score >> 3));                   // both_direction, cly.c:3095
+}
+
+__device__ __forceinline__ void read_begin(ReadState &S)
+{
 	S.n_anc = 0; S.n_hit = 0; S.n_sms = 0; S.fast_classify = 1; S.error = 0; S.sp_l = 0;
 	S.c_prefix = S.c_occ = S.c_locate = S.c_getref = S.c_getref_bytes = 0;
 	for (int k = 0; k < 8; k++) S.t_phase[k] = 0;
-	const long long t_read0 = clock64();
-	dsb_read_result out;
-	out.hit_off = 0; out.n_hit = 0; out.n_anchor = 0; out.fast_classify = 1; out.entered_final = 0; out.error = 0; out.read_len = read_len;
-	if (read_len >= MIN_READ_LEN) {
-		SearchDir sd[2];
-		const uint8_t *bin_F = P.bin + P.bin_off[r] + DSB_GUARD;
-		for (int s = 0; s < 2; s++) {
-			sd[s].seed_v = P.seeds[s] + P.seed_off[r];
-			sd[s].l_seed_v = P.n_seeds[s][r];
-			sd[s].bin_read = s ? bin_F + read_len : bin_F;
-			sd[s].direction = s ? DSB_REVERSE : DSB_FORWARD;
-			sd[s].total_score = P.total_score[s][r];
+}
+
+__device__ __forceinline__ void read_end(const ClassifyParams &P, ReadState &S, uint32_t r, long long t0)
+{
+	S.t_phase[7] = clock64() - t0;
+	if (P.prof && lane_id() < 8) P.prof[(uint64_t)r * 8 + lane_id()] += (uint32_t)(S.t_phase[lane_id()] >> 10);
+	__syncwarp();
+}
+
+__device__ __forceinline__ void list_push(const ClassifyParams &P, int list, uint32_t r)
+{
+	if (lane_id() == 0) { const uint32_t i = atomicAdd(P.ctl + CTL_LIST_N + list, 1u); P.list[list][i] = r; }
+}
+
+// a read that ends without hits (or with an error): its result record is final
+__device__ __forceinline__ void write_empty_result(const ClassifyParams &P, uint32_t r, uint32_t read_len, uint32_t n_anchor, uint32_t fast, int error)
+{
+	if (lane_id() == 0) {
+		dsb_read_result out;
+		out.hit_off = 0; out.n_hit = 0; out.n_anchor = n_anchor; out.fast_classify = (uint8_t)fast; out.entered_final = 0; out.error = (uint16_t)error; out.read_len = read_len;
+		P.rr[r] = out;
+		if (error) atomicAdd(P.counters + DSB_CNT_N_ERRORS, 1ull);
+	}
+}
+
+__device__ void phase_seed(const ClassifyParams &P, ReadState &S, uint32_t r, int pass, DevAnchor *scratch_anc)
+{
+	const long long t0 = clock64();
+	const uint32_t read_len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
+	read_begin(S);
+	ReadWork w;
+	if (pass == PASS_FAST) {
+		w.anc_off = w.n_anc = w.chain_off = w.n_chain = 0; w.error = 0; w.fast_classify = 1; w.pad = 0;
+		if (read_len < MIN_READ_LEN) {                                 // cly.c:3089: untouched (unmapped) result
+			if (lane_id() == 0) P.work[r] = w;
+			write_empty_result(P, r, read_len, 0, 1, 0);
+			return;
 		}
-		if (sd[0].total_score < sd[1].total_score) { SearchDir t = sd[0]; sd[0] = sd[1]; sd[1] = t; }   // cly.c:1261-1266
-		const bool both_direction = ((sd[0].total_score - sd[1].total_score) <= (sd[0].total_score >> 3));
-		const int super_repeat = 0;                                   // always 0 in the reference (cly.c:849-888,1545)
+	} else
+		w = P.work[r];
+	SearchDir sd[2];
+	const bool both_direction = setup_dirs(P, r, read_len, sd);
+	S.ws.anc = scratch_anc;
+	if (pass == PASS_SLOW1) {                                          // the third pass appends to the (re-ordered) anchors of the second (cly.c:3121-3125)
+		const uint64_t *src = (const uint64_t *)(P.anc_pool + w.anc_off); uint64_t *dst = (uint64_t *)scratch_anc;
+		for (uint32_t i = lane_id(); i < w.n_anc * 3; i += 32) dst[i] = src[i];
+		__syncwarp();
+		S.n_anc = w.n_anc;
+	}
+	if (pass == PASS_FAST) {
 		{ PH_BEGIN(); seed_pass(S, sd[0], read_len, false); PH_END(S, 0); }
 		if (!S.error && both_direction) { PH_BEGIN(); seed_pass(S, sd[1], read_len, false); PH_END(S, 0); }
-		if (!S.error) {
-			{ PH_BEGIN(); resolve_tree(S); PH_END(S, 1); }
-			bool run_slow_mode = false;
-			if (S.n_hit <= 0) run_slow_mode = true;
-			else if (S.ws.chain[0].anchor_number < 5 && super_repeat < 3) {
-				run_slow_mode = true;
-				if (read_len <= 300 && S.ws.chain[0].sum_score > 200) run_slow_mode = false;
-			}
-			if (run_slow_mode) {
-				S.n_anc = 0;
-				{ PH_BEGIN(); seed_pass(S, sd[0], read_len, true); PH_END(S, 2); }
-				if (!S.error) {
-					{ PH_BEGIN(); resolve_tree(S); PH_END(S, 1); }
-					if (both_direction || S.n_hit <= 0 || (S.ws.chain[0].anchor_number < 5 && super_repeat < 3)) {
-						{ PH_BEGIN(); seed_pass(S, sd[1], read_len, true); PH_END(S, 2); }
-						if (!S.error) { PH_BEGIN(); resolve_tree(S); PH_END(S, 1); }
-					}
-				}
-			}
-		}
-		if (!S.error) {
-			out.entered_final = (S.n_hit != 0);
-			score_and_merge(S, sd, read_len, P.kidx_bits_max);
+	} else {
+		PH_BEGIN(); seed_pass(S, sd[pass == PASS_SLOW0 ? 0 : 1], read_len, true); PH_END(S, 2);
+		w.fast_classify = 0;
+	}
+	// move the anchors to the read's own region of the pool
+	uint32_t off = 0;
+	if (!S.error && S.n_anc) {
+		if (lane_id() == 0) off = atomicAdd(P.ctl + CTL_ANC_CURSOR, S.n_anc);
+		off = __shfl_sync(DSB_FULL, off, 0);
+		if ((uint64_t)off + S.n_anc > P.anc_pool_cap) S.error = 1;
+		else {
+			const uint64_t *src = (const uint64_t *)scratch_anc; uint64_t *dst = (uint64_t *)(P.anc_pool + off);
+			for (uint32_t i = lane_id(); i < S.n_anc * 3; i += 32) dst[i] = src[i];
 		}
 	}
-	out.n_anchor = S.n_anc;
-	out.fast_classify = (uint8_t)S.fast_classify;
-	if (S.error) { out.error = (uint16_t)S.error; out.n_hit = 0; out.entered_final = 0; S.n_hit = 0; }
+	w.anc_off = off; w.n_anc = S.n_anc; w.error = (uint16_t)S.error;
+	if (lane_id() == 0) {
+		P.work[r] = w;
+		unsigned long long *C = P.counters;
+		atomicAdd(C + DSB_CNT_N_PREFIX, (unsigned long long)S.c_prefix);
+		atomicAdd(C + DSB_CNT_N_OCC, (unsigned long long)S.c_occ);
+		atomicAdd(C + DSB_CNT_N_LOCATE, (unsigned long long)S.c_locate);
+		atomicAdd(C + DSB_CNT_N_GETREF, (unsigned long long)S.c_getref);
+		atomicAdd(C + DSB_CNT_N_GETREF_BYTES, (unsigned long long)S.c_getref_bytes);
+	}
+	read_end(P, S, r, t0);
+}
+
+__device__ void phase_chain(const ClassifyParams &P, ReadState &S, uint32_t r, int pass)
+{
+	const long long t0 = clock64();
+	const uint32_t read_len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
+	if (read_len < MIN_READ_LEN) return;
+	read_begin(S);
+	ReadWork w = P.work[r];
+	if (w.error) { write_empty_result(P, r, read_len, w.n_anc, w.fast_classify, w.error); return; }
+	SearchDir sd[2];
+	const bool both_direction = setup_dirs(P, r, read_len, sd);
+	const int super_repeat = 0;                                        // always 0 in the reference (cly.c:849-888,1545)
+	S.ws.anc = P.anc_pool + w.anc_off; S.n_anc = w.n_anc;
+	{ PH_BEGIN(); resolve_tree(S); PH_END(S, 1); }
+	int next;                                                           // -1: finished without hits
+	if (pass == PASS_FAST) {                                            // cly.c:3101-3112
+		bool run_slow_mode = false;
+		if (S.n_hit <= 0) run_slow_mode = true;
+		else if (S.ws.chain[0].anchor_number < 5 && super_repeat < 3) {
+			run_slow_mode = true;
+			if (read_len <= 300 && S.ws.chain[0].sum_score > 200) run_slow_mode = false;
+		}
+		next = run_slow_mode ? LIST_SLOW0 : LIST_SCORE;
+	} else if (pass == PASS_SLOW0)                                      // cly.c:3119-3121
+		next = (both_direction || S.n_hit <= 0 || (S.ws.chain[0].anchor_number < 5 && super_repeat < 3)) ? LIST_SLOW1 : LIST_SCORE;
+	else
+		next = S.n_hit ? LIST_SCORE : -1;
+	if (next == LIST_SCORE) {
+		uint32_t off = 0;
+		if (lane_id() == 0) off = atomicAdd(P.ctl + CTL_CHAIN_CURSOR, S.n_hit);
+		off = __shfl_sync(DSB_FULL, off, 0);
+		if ((uint64_t)off + S.n_hit > P.chain_pool_cap) { write_empty_result(P, r, read_len, w.n_anc, w.fast_classify, 1); read_end(P, S, r, t0); return; }
+		const uint32_t *src = (const uint32_t *)S.ws.chain; uint32_t *dst = (uint32_t *)(P.chain_pool + off);
+		for (uint32_t i = lane_id(); i < S.n_hit * (uint32_t)(sizeof(DevChain) / 4); i += 32) dst[i] = src[i];
+		w.chain_off = off; w.n_chain = S.n_hit;
+		if (lane_id() == 0) P.work[r] = w;
+	}
+	if (next >= 0) list_push(P, next, r);
+	else write_empty_result(P, r, read_len, w.n_anc, w.fast_classify, 0);
+	read_end(P, S, r, t0);
+}
+
+__device__ void phase_score(const ClassifyParams &P, ReadState &S, uint32_t r)
+{
+	const long long t0 = clock64();
+	const uint32_t read_len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
+	read_begin(S);
+	const ReadWork w = P.work[r];
+	SearchDir sd[2];
+	setup_dirs(P, r, read_len, sd);
+	S.ws.anc = P.anc_pool + w.anc_off; S.n_anc = w.n_anc;
+	{
+		const uint32_t *src = (const uint32_t *)(P.chain_pool + w.chain_off); uint32_t *dst = (uint32_t *)S.ws.chain;
+		for (uint32_t i = lane_id(); i < w.n_chain * (uint32_t)(sizeof(DevChain) / 4); i += 32) dst[i] = src[i];
+		__syncwarp();
+		S.n_hit = w.n_chain;
+	}
+	dsb_read_result out;
+	out.hit_off = 0; out.n_hit = 0; out.n_anchor = w.n_anc; out.fast_classify = w.fast_classify; out.entered_final = 1; out.error = 0; out.read_len = read_len;
+	score_and_merge(S, sd, read_len, P.kidx_bits_max);
+	if (S.error) { out.error = (uint16_t)S.error; out.entered_final = 0; S.n_hit = 0; }
 	// hand the pre-filter chains to the finalize kernel: reserve 2*n slots (second half = merge-sort scratch)
 	unsigned long long off = 0;
 	if (S.n_hit) {
 		if (lane_id() == 0) off = atomicAdd(P.hits_cursor, (unsigned long long)(2 * S.n_hit));
 		off = __shfl_sync(DSB_FULL, off, 0);
-		if (off + 2ull * S.n_hit > P.hits_cap) { out.error = 4; S.n_hit = 0; }
+		if (off + 2ull * S.n_hit > P.hits_cap) { out.error = 4; out.entered_final = 0; S.n_hit = 0; }
 	}
 	out.hit_off = off; out.n_hit = S.n_hit;
 	for (uint32_t i = lane_id(); i < S.n_hit; i += 32) {
@@ -896,8 +1078,16 @@ __device__ void classify_read(const ClassifyParams &P, ReadState &S, uint32_t r)
 		h.sum_score = c.sum_score; h.indel = c.indel; h.direction = c.direction; h.primary = 0; h.pri_index = 0; h.pad = 0;
 		P.hits[off + i] = h;
 	}
-	if (lane_id() == 0) P.rr[r] = out;
-	S.t_phase[7] = clock64() - t_read0;
-	if (P.prof && lane_id() < 8) P.prof[(uint64_t)r * 8 + lane_id()] = (uint32_t)(S.t_phase[lane_id()] >> 10);
-	__syncwarp();
+	if (lane_id() == 0) {
+		P.rr[r] = out;
+		unsigned long long *C = P.counters;
+		if (out.entered_final) {                          // Classify_buff_pool.max_read_l bookkeeping (cly.c:2958), resolved in k_finalize
+			atomicMax(C + DSB_CNT_MAX_READ_L, (unsigned long long)read_len);
+			if (read_len >= 510) atomicMin(C + DSB_CNT_FIRST_LONG, (unsigned long long)r);
+		}
+		if (out.error) atomicAdd(C + DSB_CNT_N_ERRORS, 1ull);
+		atomicAdd(C + DSB_CNT_N_GETREF_SCORE, (unsigned long long)S.c_getref);
+		atomicAdd(C + DSB_CNT_N_GETREF_BYTES_SCORE, (unsigned long long)S.c_getref_bytes);
+	}
+	read_end(P, S, r, t0);
 }

@@ -26,6 +26,9 @@ struct DevBuf {                         // grow-only device buffer
 	DevBuf() : p(nullptr), cap(0) {}
 };
 
+#define DSB_N_KERNELS 10               // launches of one dsb_batch_run
+#define DSB_N_EV (DSB_N_KERNELS + 3)   // kernel boundaries + 2 user marks
+
 struct dsb_ctx {
 	dsb_index *ix;
 	dsb_opts opts;
@@ -34,7 +37,7 @@ struct dsb_ctx {
 	// batch inputs (device)
 	DevBuf seqs, read_off, bin_off, bits_off, seed_off, tiles, bin, bits, seeds[2], n_seeds[2], total_score[2];
 	// classify scratch + outputs
-	DevBuf scratch, rr, hits, counters, prof;
+	DevBuf scratch, rr, hits, counters, prof, work, anc_pool, chain_pool, lists[3], ctl, order;
 	uint64_t scratch_stride; uint32_t kidx_bits, kidx_len;
 	uint64_t hits_cap;
 	// pinned staging
@@ -44,8 +47,7 @@ struct dsb_ctx {
 	std::vector<uint64_t> h_off;        // host copies of the per-read offset tables
 	std::vector<uint64_t> h_bits_off;
 	std::vector<uint32_t> h_seed_off;
-	cudaEvent_t ev[6];
-	float kernel_ms[4];
+	cudaEvent_t ev[DSB_N_EV];
 	int launches;
 	bool ran;
 };
@@ -61,8 +63,10 @@ enum {
 	DSB_CNT_N_PREFIX,          //   prefix-table lookups (bwt_MEM_search calls)
 	DSB_CNT_N_OCC,             //   occ calls
 	DSB_CNT_N_LOCATE,          //   get_uni calls
-	DSB_CNT_N_GETREF,          //   get_ref calls
+	DSB_CNT_N_GETREF,          //   get_ref calls of the seeding phase (map_seed / get_new_ed flanks)
 	DSB_CNT_N_GETREF_BYTES,    //   packed reference bytes those calls cover
 	DSB_CNT_N_ERRORS,          // reads that hit a capacity
+	DSB_CNT_N_GETREF_SCORE,    //   get_ref calls of the scoring phase (sdp windows)
+	DSB_CNT_N_GETREF_BYTES_SCORE,
 	DSB_CNT_COUNT = 16
 };

@@ -109,8 +109,14 @@ int dsb_batch_sync(dsb_ctx *ctx);
 
 /* introspection for tests / profiling (valid after dsb_batch_run + dsb_batch_sync) */
 int dsb_batch_get_seeds(dsb_ctx *ctx, uint32_t read, int strand /*0 fwd,1 rev*/, dsb_seed *out, uint32_t cap, uint32_t *n_out, uint32_t *total_score);
-/* per-kernel device time of the last dsb_batch_run in ms: [0] encode+probe, [1] islands, [2] classify (seed+chain+score), [3] finalize */
-int dsb_batch_kernel_ms(dsb_ctx *ctx, float ms[4]);
+/* device time of each kernel of the last dsb_batch_run in ms (CUDA events on the context's stream), up to `cap` values:
+ * [0] encode+probe, [1] islands, [2] seed fast, [3] chain, [4] seed slow (strand 0), [5] chain, [6] seed slow (strand 1),
+ * [7] chain, [8] score, [9] finalize */
+int dsb_batch_kernel_ms(dsb_ctx *ctx, float *ms, int cap);
+/* stream marks for timing several contexts (batches) in flight on one GPU: dsb_ctx_mark records mark 0 or 1 on the
+ * context's stream; dsb_ctx_elapsed_ms waits for b's mark and returns b.mark_b - a.mark_a in ms */
+int dsb_ctx_mark(dsb_ctx *ctx, int which);
+int dsb_ctx_elapsed_ms(dsb_ctx *a, int mark_a, dsb_ctx *b, int mark_b, float *ms);
 /* number of kernel launches issued by the last dsb_batch_run */
 int dsb_batch_launches(dsb_ctx *ctx);
 /* CUDA stream handle (cudaStream_t) the context launches on */
@@ -118,7 +124,8 @@ void *dsb_ctx_stream(dsb_ctx *ctx);
 /* device-side counters of the last dsb_batch_run (algorithmic-byte model):
  * [0] hit slots used, [1] reads taken, [2] first read >= 510 bp that reached the filter, [3] max_read_l of the batch,
  * [4] get_exist_kmer calls on unmasked k-mers (table-0 probes), [5] table-1 probes, [6] prefix-table lookups, [7] occ calls,
- * [8] SA/unitig/ref_pos locates, [9] get_ref calls, [10] packed reference bytes they cover, [11] reads that hit a capacity */
+ * [8] SA/unitig/ref_pos locates, [9] get_ref calls while seeding, [10] packed reference bytes they cover, [11] reads that hit a
+ * capacity, [12] get_ref calls while scoring, [13] their packed bytes */
 int dsb_batch_counters(dsb_ctx *ctx, uint64_t out[16]);
 
 /* per-read device time of the last run, out[n_reads][8] in units of 1024 SM cycles:

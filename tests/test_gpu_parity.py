@@ -53,7 +53,7 @@ def test_set_parity_against_oracle(gpu, ob, oracle, name):
             assert tg == to and sg.tobytes() == so.tobytes(), (name, i, s)
     cnt_g = ctx.counters()
     assert {k: cnt_g[k] for k in CNT} == {k: cnt_o[k] for k in CNT}
-    assert ctx.launches() == 4
+    assert ctx.launches() == 10      # probe, islands, 3 x (seed, chain), score, finalize
 
 
 def _run_driver(args):
@@ -147,7 +147,7 @@ def test_upload_run_download_equals_classify_batch(gpu, ob):
         assert b.rr.tobytes() != b"" and [b.read_hits(i).tobytes() for i in range(len(seqs))] == [a.read_hits(i).tobytes() for i in range(len(seqs))]
         assert b.rr["n_anchor"].tolist() == a.rr["n_anchor"].tolist()
     ms = ctx.kernel_ms()
-    assert all(m >= 0 for m in ms) and ms[2] > 0
+    assert len(ms) == 10 and all(m >= 0 for m in ms) and ms[2] > 0 and ms[8] > 0
 
 
 def test_batch_composition_invariance_large(gpu, ob):

@@ -57,7 +57,7 @@ def main():
         bad = ob.compare_results(res.rr, res.hits, rr_o, hits_o, names, max_report=8)
         n_bad_total = len(ob.compare_results(res.rr, res.hits, rr_o, hits_o, names, max_report=10**9))
         cnt_g = ctx.counters()
-        say(f"[{name}] reads={len(seqs)} bases={len(cat)} oracle {t_o:.2f}s gpu(e2e) {t_g:.3f}s kernels_ms={['%.2f' % x for x in ctx.kernel_ms()]} "
+        say(f"[{name}] reads={len(seqs)} bases={len(cat)} oracle {t_o:.2f}s gpu(e2e) {t_g:.3f}s kernels_ms={['%.2f' % x for x in ctx.kernel_ms()]} sum={sum(ctx.kernel_ms()):.2f} "
             f"seed_mismatch={n_seed_bad} read_mismatch={n_bad_total} max_read_l gpu={res.max_read_l} oracle={mx_o}")
         say(f"    counters gpu: " + " ".join(f"{k}={cnt_g[k]}" for k in ("n_bit0", "n_bit1", "n_prefix", "n_occ", "n_locate", "n_getref", "n_getref_bytes")))
         say(f"    counters orc: " + " ".join(f"{k}={cnt_o[k]}" for k in ("n_bit0", "n_bit1", "n_prefix", "n_occ", "n_locate", "n_getref", "n_getref_bytes")))

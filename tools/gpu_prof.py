@@ -16,7 +16,7 @@ ix = dsb.Index(ob.DEMO_IDX, 0); ctx = dsb.Context(ix)
 ctx.upload(cat, offs)
 for _ in range(2):
     ctx.run(10**6); ctx.sync()
-print("kernel ms", ctx.kernel_ms())
+print("kernel ms", dict(zip(dsb.KERNEL_NAMES, [round(x, 2) for x in ctx.kernel_ms()])))
 res = ctx.download()
 P = ctx.profile().astype(np.float64) * 1024 / 1.965e6     # ms at 1965 MHz
 names = ["fast", "chain", "slow", "kidx", "middle", "right", "left", "total"]
