@@ -15,6 +15,7 @@
 #define PROBE_THREADS 256
 #define N_BITVEC 5                 // E_fwd, E_rev, T0_fwd, T0_rev, Z (k-mer not masked as low-complexity)
 #define CLASSIFY_WARPS_PER_BLOCK 4
+#define HEAVY_BLOCKS 148              // CTAs of k_score_heavy (one heavy read at a time each)
 
 static inline uint32_t bits_words(uint32_t len) { return (len + 31) / 32 + 1; }
 static inline uint32_t seed_slots(uint32_t len) { return len / 2 + 2; }
@@ -182,6 +183,7 @@ __device__ __forceinline__ void warp_setup(const ClassifyLaunch &A, ReadState &S
 	S.ws.seed_rec = (SeedRec *)(base + A.L.seed_rec); S.ws.chunk_next = (uint32_t *)(base + A.L.chunk_next);
 	for (int s = 0; s < 2; s++) { S.ws.kidx_start[s] = (uint32_t *)(base + A.L.kstart[s]); S.ws.kidx_ent[s] = (KEntry *)(base + A.L.kent[s]); }
 	S.max_anchors = A.P.max_anchors; S.max_matches = A.P.max_matches;
+	S.team = nullptr;
 }
 // next read of the launch's work list, or 0xffffffff; list < 0: all reads in `order`
 __device__ __forceinline__ uint32_t next_read(const ClassifyParams &P, int list, int cursor)
@@ -217,6 +219,33 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_score(const _
 	ReadState S;
 	warp_setup(A, S, smem_raw);
 	for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_score(A.P, S, r);
+}
+
+// Reads with many anchors (repeats) carry the long tail of a batch: their sparse DP looks back over thousands of matches.
+// They get a whole CTA each: warp 0 runs phase_score, the other warps serve its DP look-backs (dp_team_helper_loop).
+// Runs on a second stream next to k_score.
+__global__ void __launch_bounds__(TEAM_WARPS * 32) k_score_heavy(const __grid_constant__ ClassifyLaunch A, int list, int cursor, uint32_t slot0)
+{
+	__shared__ __align__(16) WarpSmem wsm;
+	__shared__ DpTeam team;
+	const int warp = threadIdx.x >> 5;
+	if (warp == 0) {
+		ReadState S;
+		S.ix = &A.P.ix; S.sm = &wsm; S.team = &team;
+		uint8_t *base = A.P.scratch + (uint64_t)(slot0 + blockIdx.x) * A.P.scratch_stride;       // scratch slots of their own
+		S.ws.anc = (DevAnchor *)(base + A.L.anc); S.ws.anc_tmp = (DevAnchor *)(base + A.L.anc_tmp);
+		S.ws.chain = (DevChain *)(base + A.L.chain); S.ws.chain_tmp = (DevChain *)(base + A.L.chain_tmp);
+		S.ws.sms = (DevSms *)(base + A.L.sms); S.ws.score_v = (int *)(base + A.L.score_v);
+		S.ws.sc_hash = (ScHash *)(base + A.L.sc_hash);
+		S.ws.sp_set = (uint64_t *)(base + A.L.sp_set); S.ws.lane_mem = (MemRst *)(base + A.L.lane_mem);
+		S.ws.seed_rec = (SeedRec *)(base + A.L.seed_rec); S.ws.chunk_next = (uint32_t *)(base + A.L.chunk_next);
+		for (int s = 0; s < 2; s++) { S.ws.kidx_start[s] = (uint32_t *)(base + A.L.kstart[s]); S.ws.kidx_ent[s] = (KEntry *)(base + A.L.kent[s]); }
+		S.max_anchors = A.P.max_anchors; S.max_matches = A.P.max_matches;
+		for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_score(A.P, S, r);
+		if (lane_id() == 0) team.cmd = -1;
+		__syncthreads();                                 // releases the helpers
+	} else
+		dp_team_helper_loop(&team, warp);
 }
 
 // ------------------------------------------------------------------------------------------------ K3
@@ -332,13 +361,16 @@ extern "C" int dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out)
 	if (c->opts.max_matches < 1024) c->opts.max_matches = 1024;
 	if (c->opts.warps_per_sm < CLASSIFY_WARPS_PER_BLOCK) c->opts.warps_per_sm = CLASSIFY_WARPS_PER_BLOCK;
 	if (c->opts.warps_per_sm > 32) c->opts.warps_per_sm = 32;
-	c->stream = nullptr; c->h_pin = nullptr; c->h_pin_cap = 0; c->ran = false; c->launches = 0;
+	c->stream = nullptr; c->stream2 = nullptr; c->ev_fork = nullptr; c->ev_join = nullptr; c->h_pin = nullptr; c->h_pin_cap = 0; c->ran = false; c->launches = 0;
 	c->n_reads = 0; c->scratch_stride = 0; c->kidx_bits = 0; c->kidx_len = 0; c->hits_cap = 0;
 	cudaDeviceProp prop;
 	DSB_CUDA(cudaGetDeviceProperties(&prop, ix->device));
 	c->n_sm = prop.multiProcessorCount;
 	c->n_warps = c->n_sm * (int)(c->opts.warps_per_sm / CLASSIFY_WARPS_PER_BLOCK) * CLASSIFY_WARPS_PER_BLOCK;
 	DSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	DSB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+	DSB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+	DSB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 	for (int i = 0; i < DSB_N_EV; i++) DSB_CUDA(cudaEventCreate(&c->ev[i]));
 	int rc = ensure(c->counters, DSB_CNT_COUNT * 8);
 	if (rc != DSB_OK) { dsb_ctx_free(c); return rc; }
@@ -353,10 +385,13 @@ extern "C" void dsb_ctx_free(dsb_ctx *c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = {&c->seqs, &c->read_off, &c->bin_off, &c->bits_off, &c->seed_off, &c->tiles, &c->bin, &c->bits, &c->seeds[0], &c->seeds[1],
 	                  &c->n_seeds[0], &c->n_seeds[1], &c->total_score[0], &c->total_score[1], &c->scratch, &c->rr, &c->hits, &c->counters, &c->prof, &c->work, &c->anc_pool, &c->chain_pool,
-	                  &c->lists[0], &c->lists[1], &c->lists[2], &c->ctl, &c->order};
+	                  &c->lists[0], &c->lists[1], &c->lists[2], &c->lists[3], &c->ctl, &c->order};
 	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
 	if (c->h_pin) cudaFreeHost(c->h_pin);
 	for (int i = 0; i < DSB_N_EV; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+	if (c->ev_join) cudaEventDestroy(c->ev_join);
+	if (c->stream2) cudaStreamDestroy(c->stream2);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -456,7 +491,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 	const ScratchLayout L = scratch_layout(c->opts.max_anchors, c->opts.max_matches, c->kidx_bits, c->kidx_len);
 	c->scratch_stride = L.total;
 	int rc;
-	if ((rc = ensure(c->scratch, (size_t)L.total * c->n_warps)) != DSB_OK) return rc;
+	if ((rc = ensure(c->scratch, (size_t)L.total * (c->n_warps + HEAVY_BLOCKS))) != DSB_OK) return rc;
 	// hits: the pre-filter chains of a read use 2 slots each (second half = merge-sort scratch)
 	const uint64_t hits_cap = std::max<uint64_t>(4096, (uint64_t)n * 24);
 	if ((rc = ensure(c->hits, hits_cap * sizeof(dsb_hit))) != DSB_OK) return rc;
@@ -518,8 +553,15 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		k_chain<<<blocks, threads, smem, st>>>(A, PASS_SLOW0, LIST_SLOW0, 3);   DSB_CUDA(cudaEventRecord(c->ev[6], st));
 		k_seed <<<blocks, threads, smem, st>>>(A, PASS_SLOW1, LIST_SLOW1, 4);   DSB_CUDA(cudaEventRecord(c->ev[7], st));
 		k_chain<<<blocks, threads, smem, st>>>(A, PASS_SLOW1, LIST_SLOW1, 5);   DSB_CUDA(cudaEventRecord(c->ev[8], st));
-		k_score<<<blocks, threads, smem, st>>>(A, LIST_SCORE, 6);               DSB_CUDA(cudaEventRecord(c->ev[9], st));
-		c->launches += 7;
+		// scoring: the heavy reads (a CTA each) on the second stream, next to everybody else's warp-per-read kernel
+		DSB_CUDA(cudaEventRecord(c->ev_fork, st));
+		DSB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+		k_score_heavy<<<HEAVY_BLOCKS, TEAM_WARPS * 32, 0, c->stream2>>>(A, LIST_SCORE_HEAVY, 7, (uint32_t)c->n_warps);
+		DSB_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+		k_score<<<blocks, threads, smem, st>>>(A, LIST_SCORE, 6);
+		DSB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+		DSB_CUDA(cudaEventRecord(c->ev[9], st));
+		c->launches += 8;
 	}
 	{
 		FinalizeParams P;

@@ -67,10 +67,14 @@ struct ReadWork {
 	uint32_t chain_off, n_chain;  // chains kept by resolve_tree, in the chain pool
 	uint16_t error; uint8_t fast_classify, pad;
 };
-enum { LIST_SLOW0 = 0, LIST_SLOW1 = 1, LIST_SCORE = 2, N_LISTS = 3 };
+enum { LIST_SLOW0 = 0, LIST_SLOW1 = 1, LIST_SCORE = 2, LIST_SCORE_HEAVY = 3, N_LISTS = 4 };   // HEAVY: reads with many anchors, scored first
+#define HEAVY_ANCHORS 256
+#ifndef KIDX_LOAD_SHIFT
+#define KIDX_LOAD_SHIFT 2
+#endif
 enum { PASS_FAST = 0, PASS_SLOW0 = 1, PASS_SLOW1 = 2 };
-// control block (u32): [0..2] list lengths, [3] anchor pool cursor, [4] chain pool cursor, [8..15] work cursors of the launches
-enum { CTL_LIST_N = 0, CTL_ANC_CURSOR = 3, CTL_CHAIN_CURSOR = 4, CTL_CURSOR = 8, CTL_WORDS = 32 };
+// control block (u32): [0..3] list lengths, [4] anchor pool cursor, [5] chain pool cursor, [8..15] work cursors of the launches
+enum { CTL_LIST_N = 0, CTL_ANC_CURSOR = 4, CTL_CHAIN_CURSOR = 5, CTL_CURSOR = 8, CTL_WORDS = 32 };
 
 struct ClassifyParams {
 	DevIndex ix;
@@ -105,9 +109,11 @@ struct SearchDir {              // SEARCH_DIR (cly.c:946-954)
 	uint32_t direction, total_score;
 };
 
+struct DpTeam;
 struct ReadState {
 	const DevIndex *ix;
 	WarpSmem *sm;
+	DpTeam *team;                // helper warps of the CTA for the sparse DP of heavy reads (k_score_heavy), else nullptr
 	WarpScratch ws;
 	uint32_t n_anc, n_hit, n_sms;
 	uint32_t max_anchors, max_matches;
@@ -286,12 +292,36 @@ __device__ __noinline__ void resolve_tree(ReadState &S)     // cly.c:326-349
 // The reference chains nodes per hash bucket in insertion (= ascending position) order and compares the full 9-mer
 // on lookup.  Equivalent here: a CSR table keyed by the low key_bits of the 9-mer, entries (kmer,pos) in ascending
 // position inside each bucket.  Built by the warp: histogram (RED atomics) -> scan -> ordered fill (__match_any_sync).
-__device__ __forceinline__ uint32_t kmer9_at(const uint8_t *q, uint32_t pos)
+// 128 read positions per step: every lane loads one aligned 4-byte word of the strand (4 bases), packs it to 8 bits, and the
+// 9-mers are cut out of three neighbouring packed words fetched by shuffle -- no per-position byte loads.
+struct KmerTile {
+	uint32_t p0, p1;     // packed words lane and lane + 32 of the tile (first base in the high bits of the byte)
+	int a;               // byte offset of the tile's position 0 inside its first word
+};
+__device__ __forceinline__ uint32_t pack4(uint32_t w) { return ((w & 3) << 6) | (((w >> 8) & 3) << 4) | (((w >> 16) & 3) << 2) | ((w >> 24) & 3); }
+__device__ __forceinline__ KmerTile load_kmer_tile(const uint8_t *q, uint32_t base)
+{   // q + base need not be aligned; guard bytes around the strands make the two extra words readable
+	KmerTile T;
+	const uintptr_t addr = (uintptr_t)(q + base);
+	T.a = (int)(addr & 3);
+	const uint32_t *w = (const uint32_t *)(addr - T.a);
+	const int lane = lane_id();
+	T.p0 = pack4(w[lane]);
+	T.p1 = (lane < 3) ? pack4(w[32 + lane]) : 0;
+	return T;
+}
+// 9-mer at tile position p (0..127); warp-collective (shuffles), every lane may ask for a different p
+__device__ __forceinline__ uint32_t tile_kmer(const KmerTile &T, uint32_t p)
 {
-	uint32_t k = 0;
+	const uint32_t bi = p + T.a, wi = bi >> 2, o = bi & 3;
+	uint32_t P = 0;
 	#pragma unroll
-	for (int i = 0; i < S_A_KEMR_L; i++) k = (k << 2) | __ldg(q + pos + i);
-	return k;
+	for (int k = 0; k < 3; k++) {
+		const uint32_t idx = wi + k;
+		const uint32_t lo = __shfl_sync(DSB_FULL, T.p0, idx & 31), hi = __shfl_sync(DSB_FULL, T.p1, idx & 31);
+		P = (P << 8) | ((idx < 32) ? lo : hi);
+	}
+	return (P >> (6 - 2 * o)) & 0x3ffffu;
 }
 
 __device__ __noinline__ void build_kidx(ReadState &S, const uint8_t *q, uint32_t q_len, int slot, int key_bits)
@@ -301,40 +331,53 @@ __device__ __noinline__ void build_kidx(ReadState &S, const uint8_t *q, uint32_t
 	const uint32_t nb = 1u << key_bits, kmask = nb - 1;
 	const int lane = lane_id();
 	const uint32_t nk = q_len - S_A_KEMR_L + 1;
-	for (uint32_t b = lane; b < nb; b += 32) start[b] = 0;
+	for (uint32_t b = lane * 4; b < nb; b += 128) *(uint4 *)(start + b) = make_uint4(0, 0, 0, 0);
 	__syncwarp();
-	for (uint32_t base = 0; base < nk; base += 32) {
-		const uint32_t pos = base + lane;
-		if (pos < nk) atomicAdd(start + (kmer9_at(q, pos) & kmask), 1u);
+	// histogram
+	for (uint32_t base = 0; base < nk; base += 128) {
+		const KmerTile T = load_kmer_tile(q, base);
+		#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const uint32_t p = 32 * j + lane;
+			const uint32_t kmer = tile_kmer(T, p);
+			if (base + p < nk) atomicAdd(start + (kmer & kmask), 1u);
+		}
 	}
 	__syncwarp();
 	__threadfence_block();
-	// exclusive scan over buckets, in place
+	// exclusive scan over buckets, in place, 4 buckets per lane
 	uint32_t carry = 0;
-	for (uint32_t b0 = 0; b0 < nb; b0 += 32) {
-		const uint32_t v = __ldcg(start + b0 + lane);
-		uint32_t x = v;
+	for (uint32_t b0 = 0; b0 < nb; b0 += 128) {
+		uint4 v = __ldcg((const uint4 *)(start + b0) + lane);
+		const uint32_t sum = v.x + v.y + v.z + v.w;
+		uint32_t x = sum;
 		#pragma unroll
 		for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(DSB_FULL, x, d); if (lane >= d) x += y; }
-		start[b0 + lane] = carry + x - v;
+		uint32_t e = carry + x - sum;
+		uint4 o; o.x = e; e += v.x; o.y = e; e += v.y; o.z = e; e += v.z; o.w = e;
+		*((uint4 *)(start + b0) + lane) = o;
 		carry += __shfl_sync(DSB_FULL, x, 31);
 	}
 	__syncwarp();
 	// ordered fill; afterwards start[b] = END of bucket b, begin = start[b-1] (0 for b == 0)
-	for (uint32_t base = 0; base < nk; base += 32) {
-		const uint32_t pos = base + lane;
-		const bool act = pos < nk;
-		const uint32_t kmer = act ? kmer9_at(q, pos) : 0xffffffffu;
-		const uint32_t key = act ? (kmer & kmask) : (0x80000000u | lane);
-		const uint32_t peers = __match_any_sync(DSB_FULL, key);
-		const int leader = __ffs(peers) - 1;
-		const uint32_t rank = __popc(peers & ((1u << lane) - 1));
-		uint32_t cur = 0;
-		if (act && lane == leader) cur = start[key];
-		cur = __shfl_sync(DSB_FULL, cur, leader);
-		if (act) { KEntry e; e.kmer = kmer; e.pos = pos; ent[cur + rank] = e; }
-		if (act && lane == leader) start[key] = cur + __popc(peers);
-		__syncwarp();
+	for (uint32_t base = 0; base < nk; base += 128) {
+		const KmerTile T = load_kmer_tile(q, base);
+		#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const uint32_t pos = base + 32 * j + lane;
+			const bool act = pos < nk;
+			const uint32_t kmer = tile_kmer(T, 32 * j + lane);
+			const uint32_t key = act ? (kmer & kmask) : (0x80000000u | lane);
+			const uint32_t peers = __match_any_sync(DSB_FULL, key);
+			const int leader = __ffs(peers) - 1;
+			const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+			uint32_t cur = 0;
+			if (act && lane == leader) cur = start[key];
+			cur = __shfl_sync(DSB_FULL, cur, leader);
+			if (act) { KEntry e; e.kmer = kmer; e.pos = pos; ent[cur + rank] = e; }
+			if (act && lane == leader) start[key] = cur + __popc(peers);
+			__syncwarp();
+		}
 	}
 	__syncwarp();
 }
@@ -524,6 +567,164 @@ __device__ __forceinline__ DevSms load_sms(const DevSms *p)
 
 #define MAX_sms_overlap (6)
 #define MAX_sms_overlap_middle (6)
+// ---------------------------------------------------------------- sparse DP over 9-mer matches, one LANE per match
+// The reference scores the matches of a window one after the other; each looks back over ALL earlier matches (walking
+// backwards, stopping at its first `break`) and takes the best predecessor (cly.c:2480-2528, 2621-2652, 2765-2797).  Here
+// a block of <= 32 consecutive matches is scored at once: lane j owns match first+j.  Earlier blocks are final, so every
+// lane walks them in the same order (one broadcast load per predecessor serves 32 matches); the dependencies inside the
+// block are resolved by a short sequential pass.  pass / break / candidate score are the reference's own expressions.
+enum { DP_MIDDLE = 0, DP_RIGHT = 1, DP_LEFT = 2 };
+
+template <int KIND>
+__device__ __forceinline__ void dp_eval(const DevSms &c, const DevSms &p, bool &pass, bool &brk, bool &has, int &cand)
+{
+	has = false; brk = false; cand = 0;
+	if (KIND == DP_LEFT) {
+		const uint32_t min_pre_q = c.q_pos + c.len - MAX_sms_overlap + S_A_KEMR_L - 1;
+		const uint32_t min_pre_t = c.t_pos + c.len - MAX_sms_overlap + S_A_KEMR_L - 1;
+		pass = !(p.q_pos < min_pre_q) && !(p.t_pos < min_pre_t);
+		if (!pass) return;
+		if (min_pre_t + 600 < p.t_pos) { brk = true; return; }
+		const int indel = p.q_pos - p.t_pos - (min_pre_q - min_pre_t);
+		const int ABS_indel = DSB_ABS(indel);
+		if (ABS_indel > 200) return;
+		int new_score = p.score + c.len - (ABS_indel >> 3);
+		if (min_pre_q + MAX_sms_overlap > p.q_pos || min_pre_t + MAX_sms_overlap > p.t_pos) {
+			const int overlap_q = min_pre_q + MAX_sms_overlap - p.q_pos;
+			const int overlap_t = min_pre_t + MAX_sms_overlap - p.t_pos;
+			new_score -= DSB_MAX(overlap_q, overlap_t);
+		}
+		has = true; cand = new_score;
+	} else {
+		const uint32_t max_q = c.q_pos + MAX_sms_overlap;
+		const uint32_t max_t = c.t_pos + MAX_sms_overlap;
+		const int pre_q_ed = p.q_pos + p.len + S_A_KEMR_L - 1;
+		const int pre_t_ed = p.t_pos + p.len + S_A_KEMR_L - 1;
+		pass = !(pre_q_ed > max_q) && !(pre_t_ed > max_t);
+		if (!pass) return;
+		if (KIND == DP_RIGHT && (p.t_pos + 600 < max_t)) { brk = true; return; }
+		const int indel = p.q_pos - p.t_pos - (max_q - max_t);
+		const int ABS_indel = DSB_ABS(indel);
+		if (ABS_indel > 200) return;
+		int new_score = p.score + c.len - (ABS_indel >> 3);
+		if (pre_q_ed > c.q_pos || pre_t_ed > c.t_pos) {
+			const int overlap_q = pre_q_ed - c.q_pos;
+			const int overlap_t = pre_t_ed - c.t_pos;
+			new_score -= DSB_MAX(overlap_q, overlap_t);
+		}
+		has = true; cand = new_score;
+	}
+}
+
+// Heavy reads (repeats: thousands of matches per window) are scored by k_score_heavy with a whole CTA: warp 0 runs the
+// read, the other warps only help with phase (A) below -- each takes a contiguous range of the earlier matches.
+#define TEAM_WARPS 16
+#define TEAM_MIN_FIRST 512
+struct DpTeam {
+	int cmd;                          // >= 0: job posted, < 0: exit
+	int kind; uint32_t first, nb;
+	const DevSms *sms;
+	DevSms item[32]; int stopped0[32];
+	int best[TEAM_WARPS][32]; int brk[TEAM_WARPS][32];
+};
+
+// phase (A) over the predecessors [lo, hi), walked downwards: best candidate per lane and whether the lane's walk hit its break
+template <int KIND>
+__device__ __forceinline__ void dp_range(const DevSms *sms, int lo, int hi, const DevSms &my, bool stopped, int &best, bool &brk_out)
+{
+	for (int pi = hi - 1; pi >= lo; ) {
+		if (__all_sync(DSB_FULL, stopped)) break;
+		DevSms e[4];
+		#pragma unroll
+		for (int u = 0; u < 4; u++) { e[u].t_pos = e[u].q_pos = e[u].len = e[u].score = 0; if (pi - u >= lo) e[u] = load_sms(sms + pi - u); }
+		#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			if (pi - u >= lo && !stopped) {
+				bool pass, brk, has; int cand;
+				dp_eval<KIND>(my, e[u], pass, brk, has, cand);
+				if (brk) { stopped = true; brk_out = true; }
+				else if (has) best = DSB_MAX(best, cand);
+			}
+		}
+		pi -= 4;
+	}
+}
+
+__device__ __forceinline__ void dp_team_range(DpTeam *T, int w)
+{   // the share of warp w (0 = the range nearest to the block) of the posted job
+	const int lane = lane_id();
+	const int first = (int)T->first, chunk = (first + TEAM_WARPS - 1) / TEAM_WARPS;
+	const int hi = first - w * chunk, lo = max(0, hi - chunk);
+	const DevSms my = T->item[lane];
+	int best = INT_MIN; bool brk = false;
+	const bool stopped = T->stopped0[lane] != 0;
+	if (hi > 0) {
+		if (T->kind == DP_RIGHT) dp_range<DP_RIGHT>(T->sms, lo, hi, my, stopped, best, brk);
+		else if (T->kind == DP_LEFT) dp_range<DP_LEFT>(T->sms, lo, hi, my, stopped, best, brk);
+		else dp_range<DP_MIDDLE>(T->sms, lo, hi, my, stopped, best, brk);
+	}
+	T->best[w][lane] = best; T->brk[w][lane] = brk ? 1 : 0;
+}
+
+__device__ __forceinline__ void dp_team_helper_loop(DpTeam *T, int w)
+{
+	for (;;) {
+		__syncthreads();                                 // job posted
+		if (T->cmd < 0) break;
+		dp_team_range(T, w);
+		__syncthreads();                                 // results ready
+	}
+}
+
+// scores of the matches [first, first + nb), nb <= 32; lane j holds match first+j in `my` and receives its score.
+template <int KIND>
+__device__ __forceinline__ int dp_block(const DevSms *sms, uint32_t first, uint32_t nb, DevSms my, DpTeam *team)
+{
+	const int lane = lane_id();
+	const bool mine = (uint32_t)lane < nb;
+	// (0) inside the block, positions only: does my walk stop (break) before it leaves the block, and at which lane?
+	int stop_at = -1;                                    // highest k < lane whose predecessor test says `break`
+	if (KIND != DP_MIDDLE) {
+		for (int k = (int)nb - 2; k >= 0; k--) {
+			DevSms p;
+			p.t_pos = __shfl_sync(DSB_FULL, my.t_pos, k); p.q_pos = __shfl_sync(DSB_FULL, my.q_pos, k); p.len = __shfl_sync(DSB_FULL, my.len, k); p.score = 0;
+			if (mine && k < lane && stop_at < 0) { bool pass, brk, has; int cand; dp_eval<KIND>(my, p, pass, brk, has, cand); if (brk) stop_at = k; }
+		}
+	}
+	// (A) predecessors in earlier blocks: all lanes walk first-1 .. 0 together, each with its own stop
+	int best = (int)my.len;
+	const bool stopped = !mine || stop_at >= 0;
+	if (team && first >= TEAM_MIN_FIRST) {
+		team->item[lane] = my; team->stopped0[lane] = stopped ? 1 : 0;
+		if (lane == 0) { team->kind = KIND; team->first = first; team->nb = nb; team->sms = sms; team->cmd = 1; }
+		__syncthreads();                                 // job posted: the helper warps wake up
+		dp_team_range(team, 0);
+		__syncthreads();                                 // results ready
+		if (!stopped)
+			for (int w = 0; w < TEAM_WARPS; w++) { best = DSB_MAX(best, team->best[w][lane]); if (team->brk[w][lane]) break; }
+		__syncwarp();
+	} else {
+		bool brk = false;
+		dp_range<KIND>(sms, 0, (int)first, my, stopped, best, brk);
+	}
+	// (B) predecessors inside the block, in order: match j needs the final scores of the matches before it
+	int my_score = best;
+	for (uint32_t j = 1; j < nb; j++) {
+		DevSms c;
+		c.t_pos = __shfl_sync(DSB_FULL, my.t_pos, j); c.q_pos = __shfl_sync(DSB_FULL, my.q_pos, j); c.len = __shfl_sync(DSB_FULL, my.len, j); c.score = 0;
+		const int c_stop = __shfl_sync(DSB_FULL, stop_at, j);
+		int cand_max = INT_MIN;
+		if ((uint32_t)lane < j && lane > c_stop) {
+			DevSms p = my; p.score = (uint32_t)my_score;
+			bool pass, brk, has; int cand;
+			dp_eval<KIND>(c, p, pass, brk, has, cand);
+			if (has) cand_max = cand;
+		}
+		cand_max = warp_max(cand_max);
+		if ((uint32_t)lane == j && cand_max > my_score) my_score = cand_max;
+	}
+	return my_score;
+}
 __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8_t *q_str, const KIdx &kx)
 {   // cly.c:2444-2530
 	const DevIndex &ix = *S.ix;
@@ -553,43 +754,15 @@ __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8
 			}
 			if (!sms_push(S, ca.ref_offset, ca.index_in_read, ca.mtch_len - S_A_KEMR_L + 1)) return 0;
 			if (S.n_sms > 1) {
-				for (uint32_t ci = 1; ci < S.n_sms; ci++) {
-					const DevSms c_spd = base[ci];
-					int max_score = c_spd.len;
-					const uint32_t max_q = c_spd.q_pos + MAX_sms_overlap_middle;
-					const uint32_t max_t = c_spd.t_pos + MAX_sms_overlap_middle;
-					for (int pbase = (int)ci - 1; pbase >= 0; pbase -= 128) {
-						DevSms e[4];
-						#pragma unroll
-						for (int u = 0; u < 4; u++) {                     // 4 independent 16-byte loads in flight per lane
-							const int pi = pbase - 32 * u - lane_id();
-							e[u].t_pos = e[u].q_pos = e[u].len = e[u].score = 0;
-							if (pi >= 0) e[u] = load_sms(base + pi);
-						}
-						#pragma unroll
-						for (int u = 0; u < 4; u++) {
-							const int pi = pbase - 32 * u - lane_id();
-							const DevSms c_pre = e[u];
-							const int pre_q_ed = c_pre.q_pos + c_pre.len + S_A_KEMR_L - 1;
-							const int pre_t_ed = c_pre.t_pos + c_pre.len + S_A_KEMR_L - 1;
-							const int indel = c_pre.q_pos - c_pre.t_pos - (max_q - max_t);
-							const int ABS_indel = DSB_ABS(indel);
-							if (pi >= 0 && !(pre_q_ed > max_q) && !(pre_t_ed > max_t) && !(ABS_indel > 200)) {
-								int new_score = c_pre.score + c_spd.len - (ABS_indel >> 3);
-								if (pre_q_ed > c_spd.q_pos || pre_t_ed > c_spd.t_pos) {
-									const int overlap_q = pre_q_ed - c_spd.q_pos;
-									const int overlap_t = pre_t_ed - c_spd.t_pos;
-									new_score -= DSB_MAX(overlap_q, overlap_t);
-								}
-								max_score = DSB_MAX(max_score, new_score);
-							}
-						}
-					}
+				__syncwarp();
+				for (uint32_t first = 1; first < S.n_sms; first += 32) {
+					const uint32_t nb = DSB_MIN(32u, S.n_sms - first);
+					DevSms my; my.t_pos = my.q_pos = my.len = my.score = 0;
+					if ((uint32_t)lane_id() < nb) my = load_sms(base + first + lane_id());
+					const int sc = dp_block<DP_MIDDLE>(base, first, nb, my, S.team);
+					if ((uint32_t)lane_id() < nb) base[first + lane_id()].score = sc;
 					__syncwarp();
-					max_score = warp_max(max_score);
-					score = DSB_MAX(max_score, score);
-					if (lane_id() == 0) base[ci].score = max_score;
-					__syncwarp();
+					score = DSB_MAX(warp_max(((uint32_t)lane_id() < nb) ? sc : INT_MIN), score);
 				}
 			}
 		} else
@@ -615,6 +788,7 @@ __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, con
 	const ulonglong2 ri = __ldg(ix.ref_info + c_st[chain_ID].ref_ID);
 	const uint64_t t_offset_global = ri.y, t_length = ri.x;
 	uint32_t c_t_offset = c_st[chain_ID].t_ed - 3;
+	uint32_t best_t = c_st[chain_ID].t_ed;               // sms[max_sms_id].t_pos
 	int last_search = 0;
 	while (1) {
 		if (S.n_sms == current_sms) {
@@ -640,66 +814,45 @@ __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, con
 			if (S.n_sms == current_sms) break;
 			if (sms[current_sms].t_pos > sms[max_sms_id].t_pos + 1000) break;
 		}
-		const uint32_t ci = current_sms++;
-		const DevSms c_sms = sms[ci];
-		int max_score = c_sms.len;
-		const uint32_t max_pre_q = c_sms.q_pos + MAX_sms_overlap;
-		const uint32_t max_pre_t = c_sms.t_pos + MAX_sms_overlap;
-		for (int pbase = (int)current_sms - 2; pbase >= 0; pbase -= 128) {
-			DevSms e[4];
-			#pragma unroll
-			for (int u = 0; u < 4; u++) {                                 // 4 independent 16-byte loads in flight per lane
-				const int pi = pbase - 32 * u - lane_id();
-				e[u].t_pos = e[u].q_pos = e[u].len = e[u].score = 0;
-				if (pi >= 0) e[u] = load_sms(sms + pi);
-			}
-			bool stop = false;
-			#pragma unroll
-			for (int u = 0; u < 4; u++) {
-				if (stop) continue;                                       // warp-uniform
-				const bool act = (pbase - 32 * u - lane_id()) >= 0;
-				const DevSms c_pre = e[u];
-				const int pre_q_ed = c_pre.q_pos + c_pre.len + S_A_KEMR_L - 1;
-				const int pre_t_ed = c_pre.t_pos + c_pre.len + S_A_KEMR_L - 1;
-				const bool pass = act && !(pre_q_ed > max_pre_q) && !(pre_t_ed > max_pre_t);
-				const bool brk = pass && (c_pre.t_pos + 600 < max_pre_t);
-				const uint32_t bm = __ballot_sync(DSB_FULL, brk);
-				const int first = bm ? (__ffs(bm) - 1) : 32;
-				if (pass && lane_id() < first) {
-					const int indel = c_pre.q_pos - c_pre.t_pos - (max_pre_q - max_pre_t);
-					const int ABS_indel = DSB_ABS(indel);
-					if (!(ABS_indel > 200)) {
-						int new_score = c_pre.score + c_sms.len - (ABS_indel >> 3);
-						if (pre_q_ed > c_sms.q_pos || pre_t_ed > c_sms.t_pos) {
-							const int overlap_q = pre_q_ed - c_sms.q_pos;
-							const int overlap_t = pre_t_ed - c_sms.t_pos;
-							new_score -= DSB_MAX(overlap_q, overlap_t);
-						}
-						max_score = DSB_MAX(max_score, new_score);
-					}
-				}
-				if (bm) stop = true;
-			}
-			if (stop) break;
-		}
-		max_score = warp_max(max_score);
-		if (lane_id() == 0) sms[ci].score = max_score;
+		// score the pending matches in blocks of 32 (dp_block), then replay the reference's per-match control flow
+		const uint32_t first = current_sms, nb = DSB_MIN(32u, S.n_sms - current_sms);
+		DevSms my; my.t_pos = my.q_pos = my.len = my.score = 0;
+		if ((uint32_t)lane_id() < nb) my = load_sms(sms + first + lane_id());
+		const int my_score = dp_block<DP_RIGHT>(sms, first, nb, my, S.team);
+		if ((uint32_t)lane_id() < nb) sms[first + lane_id()].score = my_score;
 		__syncwarp();
-		if (c_sms.len >= 8 && combine_chain(S, chain_ID, c_sms.t_pos - c_sms.q_pos, 0, c_sms.q_pos, &combined) == 1) {
-			total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2(S, c_st[combined].cur, q_str, kx);
-			if (S.error) return 0;
-			score_ori = total_max_score;
-			max_sms_id = 0;
-			const DevChain ch = c_st[chain_ID];
-			sms[0].score = total_max_score; sms[0].q_pos = ch.q_ed; sms[0].t_pos = ch.t_ed; sms[0].len = -S_A_KEMR_L;
-			S.n_sms = 1;
-			current_sms = 1;
-			c_t_offset = ch.t_ed;
-			continue;
+		// combine_chain returns 0 at once when the bucket of the match's diagonal is empty (cly.c:1771)
+		const bool need = (uint32_t)lane_id() < nb && my.len >= 8 && S.ws.sc_hash[(my.t_pos - my.q_pos) & 0xff].next != 0;
+		const uint32_t cm = __ballot_sync(DSB_FULL, need);
+		bool restarted = false, done = false;
+		for (uint32_t j = 0; j < nb; j++) {
+			DevSms c_sms;
+			c_sms.t_pos = __shfl_sync(DSB_FULL, my.t_pos, j); c_sms.q_pos = __shfl_sync(DSB_FULL, my.q_pos, j); c_sms.len = __shfl_sync(DSB_FULL, my.len, j);
+			const int max_score = __shfl_sync(DSB_FULL, my_score, j);
+			current_sms = first + j + 1;
+			if (((cm >> j) & 1) && combine_chain(S, chain_ID, c_sms.t_pos - c_sms.q_pos, 0, c_sms.q_pos, &combined) == 1) {
+				total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2(S, c_st[combined].cur, q_str, kx);
+				if (S.error) return 0;
+				score_ori = total_max_score;
+				max_sms_id = 0;
+				const DevChain ch = c_st[chain_ID];
+				__syncwarp();
+				if (lane_id() == 0) { sms[0].score = total_max_score; sms[0].q_pos = ch.q_ed; sms[0].t_pos = ch.t_ed; sms[0].len = -S_A_KEMR_L; }
+				__syncwarp();
+				best_t = ch.t_ed;
+				S.n_sms = 1;
+				current_sms = 1;
+				c_t_offset = ch.t_ed;
+				restarted = true;
+				break;
+			}
+			if (total_max_score < max_score) { total_max_score = max_score; max_sms_id = first + j; best_t = c_sms.t_pos; }
+			if (c_sms.t_pos > best_t + 1000) { done = true; break; }
 		}
-		if (total_max_score < max_score) { total_max_score = max_score; max_sms_id = current_sms - 1; }
-		if (c_sms.t_pos > sms[max_sms_id].t_pos + 1000) break;
+		if (restarted) continue;
+		if (done) break;
 	}
+	__syncwarp();
 	c_st[chain_ID].q_ed = sms[max_sms_id].q_pos + sms[max_sms_id].len + S_A_KEMR_L;
 	c_st[chain_ID].t_ed = sms[max_sms_id].t_pos + sms[max_sms_id].len + S_A_KEMR_L;
 	return total_max_score - 10000;
@@ -720,6 +873,7 @@ __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, cons
 	uint32_t current_sms = 1;
 	const uint64_t t_offset_global = __ldg(ix.ref_info + c_st[chain_ID].ref_ID).y;
 	uint32_t c_t_offset = c_st[chain_ID].t_st + 3;
+	uint32_t best_t = c_st[chain_ID].t_st;               // sms[max_sms_id].t_pos
 	int last_search = 0;
 	while (1) {
 		if (S.n_sms == current_sms) {
@@ -748,64 +902,44 @@ __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, cons
 			if (S.n_sms == current_sms) break;
 			if (sms[current_sms].t_pos + 1000 < sms[max_sms_id].t_pos) break;
 		}
-		const uint32_t ci = current_sms++;
-		const DevSms c_sms = sms[ci];
-		int max_score = c_sms.len;
-		const uint32_t min_pre_q = c_sms.q_pos + c_sms.len - MAX_sms_overlap + S_A_KEMR_L - 1;
-		const uint32_t min_pre_t = c_sms.t_pos + c_sms.len - MAX_sms_overlap + S_A_KEMR_L - 1;
-		for (int pbase = (int)current_sms - 2; pbase >= 0; pbase -= 128) {
-			DevSms e[4];
-			#pragma unroll
-			for (int u = 0; u < 4; u++) {
-				const int pi = pbase - 32 * u - lane_id();
-				e[u].t_pos = e[u].q_pos = e[u].len = e[u].score = 0;
-				if (pi >= 0) e[u] = load_sms(sms + pi);
-			}
-			bool stop = false;
-			#pragma unroll
-			for (int u = 0; u < 4; u++) {
-				if (stop) continue;                                       // warp-uniform
-				const bool act = (pbase - 32 * u - lane_id()) >= 0;
-				const DevSms c_pre = e[u];
-				const bool pass = act && !(c_pre.q_pos < min_pre_q) && !(c_pre.t_pos < min_pre_t);
-				const bool brk = pass && (min_pre_t + 600 < c_pre.t_pos);
-				const uint32_t bm = __ballot_sync(DSB_FULL, brk);
-				const int first = bm ? (__ffs(bm) - 1) : 32;
-				if (pass && lane_id() < first) {
-					const int indel = c_pre.q_pos - c_pre.t_pos - (min_pre_q - min_pre_t);
-					const int ABS_indel = DSB_ABS(indel);
-					if (!(ABS_indel > 200)) {
-						int new_score = c_pre.score + c_sms.len - (ABS_indel >> 3);
-						if (min_pre_q + MAX_sms_overlap > c_pre.q_pos || min_pre_t + MAX_sms_overlap > c_pre.t_pos) {
-							const int overlap_q = min_pre_q + MAX_sms_overlap - c_pre.q_pos;
-							const int overlap_t = min_pre_t + MAX_sms_overlap - c_pre.t_pos;
-							new_score -= DSB_MAX(overlap_q, overlap_t);
-						}
-						max_score = DSB_MAX(max_score, new_score);
-					}
-				}
-				if (bm) stop = true;
-			}
-			if (stop) break;
-		}
-		max_score = warp_max(max_score);
-		if (lane_id() == 0) sms[ci].score = max_score;
+		// score the pending matches in blocks of 32 (dp_block), then replay the reference's per-match control flow
+		const uint32_t first = current_sms, nb = DSB_MIN(32u, S.n_sms - current_sms);
+		DevSms my; my.t_pos = my.q_pos = my.len = my.score = 0;
+		if ((uint32_t)lane_id() < nb) my = load_sms(sms + first + lane_id());
+		const int my_score = dp_block<DP_LEFT>(sms, first, nb, my, S.team);
+		if ((uint32_t)lane_id() < nb) sms[first + lane_id()].score = my_score;
 		__syncwarp();
-		if (c_sms.len >= 8 && combine_chain(S, chain_ID, c_sms.t_pos - c_sms.q_pos, 1, c_sms.q_pos + c_sms.len, &combined) == 1) {
-			total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2(S, c_st[combined].cur, q_str, kx);
-			if (S.error) return 0;
-			score_ori = total_max_score;
-			max_sms_id = 0;
-			const DevChain ch = c_st[chain_ID];
-			sms[0].score = total_max_score; sms[0].q_pos = ch.q_st; sms[0].t_pos = ch.t_st;
-			S.n_sms = 1;
-			current_sms = 1;
-			c_t_offset = ch.t_st;
-			continue;
+		const bool need = (uint32_t)lane_id() < nb && my.len >= 8 && S.ws.sc_hash[(my.t_pos - my.q_pos) & 0xff].next != 0;
+		const uint32_t cm = __ballot_sync(DSB_FULL, need);
+		bool restarted = false, done = false;
+		for (uint32_t j = 0; j < nb; j++) {
+			DevSms c_sms;
+			c_sms.t_pos = __shfl_sync(DSB_FULL, my.t_pos, j); c_sms.q_pos = __shfl_sync(DSB_FULL, my.q_pos, j); c_sms.len = __shfl_sync(DSB_FULL, my.len, j);
+			const int max_score = __shfl_sync(DSB_FULL, my_score, j);
+			current_sms = first + j + 1;
+			if (((cm >> j) & 1) && combine_chain(S, chain_ID, c_sms.t_pos - c_sms.q_pos, 1, c_sms.q_pos + c_sms.len, &combined) == 1) {
+				total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2(S, c_st[combined].cur, q_str, kx);
+				if (S.error) return 0;
+				score_ori = total_max_score;
+				max_sms_id = 0;
+				const DevChain ch = c_st[chain_ID];
+				__syncwarp();
+				if (lane_id() == 0) { sms[0].score = total_max_score; sms[0].q_pos = ch.q_st; sms[0].t_pos = ch.t_st; }
+				__syncwarp();
+				best_t = ch.t_st;
+				S.n_sms = 1;
+				current_sms = 1;
+				c_t_offset = ch.t_st;
+				restarted = true;
+				break;
+			}
+			if (total_max_score < max_score) { total_max_score = max_score; max_sms_id = first + j; best_t = c_sms.t_pos; }
+			if (c_sms.t_pos + 1000 < best_t) { done = true; break; }
 		}
-		if (total_max_score < max_score) { total_max_score = max_score; max_sms_id = current_sms - 1; }
-		if (c_sms.t_pos + 1000 < sms[max_sms_id].t_pos) break;
+		if (restarted) continue;
+		if (done) break;
 	}
+	__syncwarp();
 	c_st[chain_ID].q_st = sms[max_sms_id].q_pos;
 	c_st[chain_ID].t_st = sms[max_sms_id].t_pos;
 	return total_max_score - 10000;
@@ -841,8 +975,10 @@ __device__ __noinline__ void score_and_merge(ReadState &S, const SearchDir *sear
 		both_dir |= (C[i].direction == DSB_FORWARD) ? 0x2 : 0x1;
 		if (both_dir == 3) break;
 	}
-	int key_bits = 10;
-	for (; key_bits < 18; key_bits++) if ((1u << key_bits) >= l_read) break;
+	// the reference sizes its chained hash at >= l_read buckets (cly.c:2196-2198); the CSR table here only has to be a
+	// superset filter (entries carry the full 9-mer), so it is kept 2^KIDX_LOAD_SHIFT times smaller: cheaper build passes
+	int key_bits = 7;
+	for (; key_bits < 17; key_bits++) if (((1u << KIDX_LOAD_SHIFT) << key_bits) >= l_read) break;
 	if ((uint32_t)key_bits > kidx_bits_max) key_bits = kidx_bits_max;
 	for (int c_dir = 2; c_dir >= 1; c_dir--) {
 		if ((c_dir & both_dir) == 0) continue;
@@ -1039,7 +1175,7 @@ __device__ void phase_chain(const ClassifyParams &P, ReadState &S, uint32_t r, i
 		w.chain_off = off; w.n_chain = S.n_hit;
 		if (lane_id() == 0) P.work[r] = w;
 	}
-	if (next >= 0) list_push(P, next, r);
+	if (next >= 0) list_push(P, (next == LIST_SCORE && w.n_anc >= HEAVY_ANCHORS) ? LIST_SCORE_HEAVY : next, r);
 	else write_empty_result(P, r, read_len, w.n_anc, w.fast_classify, 0);
 	read_end(P, S, r, t0);
 }

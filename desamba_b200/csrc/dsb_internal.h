@@ -32,12 +32,13 @@ struct DevBuf {                         // grow-only device buffer
 struct dsb_ctx {
 	dsb_index *ix;
 	dsb_opts opts;
-	cudaStream_t stream;
+	cudaStream_t stream, stream2;       // stream2: k_score_heavy next to k_score
+	cudaEvent_t ev_fork, ev_join;
 	int n_sm, n_warps;                  // resident classify warps = n_sm * warps_per_sm
 	// batch inputs (device)
 	DevBuf seqs, read_off, bin_off, bits_off, seed_off, tiles, bin, bits, seeds[2], n_seeds[2], total_score[2];
 	// classify scratch + outputs
-	DevBuf scratch, rr, hits, counters, prof, work, anc_pool, chain_pool, lists[3], ctl, order;
+	DevBuf scratch, rr, hits, counters, prof, work, anc_pool, chain_pool, lists[4], ctl, order;
 	uint64_t scratch_stride; uint32_t kidx_bits, kidx_len;
 	uint64_t hits_cap;
 	// pinned staging

@@ -24,7 +24,7 @@ print("sum over reads (warp-ms):", {k: round(float(P[:, i].sum()), 1) for i, k i
 print("mean per read (ms):", {k: round(float(P[:, i].mean()), 3) for i, k in enumerate(names)})
 order = np.argsort(-P[:, 7])
 print("worst reads:")
-for i in order[:12]:
+for i in order[:int(os.environ.get("PROF_WORST", "12"))]:
     print(f"  read {i} len={len(seqs[i])} n_anc={res.rr['n_anchor'][i]} n_hit={res.rr['n_hit'][i]} fast={res.rr['fast_classify'][i]} " + " ".join(f"{k}={P[i, j]:.1f}" for j, k in enumerate(names)))
 q = np.percentile(P[:, 7], [50, 90, 99, 99.9, 100])
 print("total ms percentiles 50/90/99/99.9/100:", [round(float(x), 2) for x in q])
