@@ -193,13 +193,42 @@ struct AnchorCmp {                                // Anchor_cmp_by_chr_ID_and_po
 	}
 };
 
+// The reference sorts with qsort (= glibc merge sort, taking the left run while cmp <= 0).  For a comparator that is a
+// consistent ordering, that is THE stable sort by the comparator's key, so it can be computed any way: here each element's
+// final position is counted directly (elements with a smaller key, or an equal key and a smaller index), 32 elements at a
+// time, and the array is permuted through scratch.  (chain_cmp_by_MEM_score is NOT consistent: k_finalize keeps the
+// explicit merge emulation for it.)
+template <typename T>
+__device__ __forceinline__ void warp_stable_sort_by_key(T *a, T *tmp, uint32_t n, uint64_t *key)
+{
+	const int lane = lane_id();
+	__syncwarp();
+	for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+		const uint32_t i = i0 + lane;
+		const uint64_t ki = (i < n) ? key[i] : 0;
+		uint32_t r = 0;
+		for (uint32_t j = 0; j < n; j++) { const uint64_t kj = key[j]; r += (kj < ki || (kj == ki && j < i)) ? 1u : 0u; }
+		if (i < n) tmp[r] = a[i];
+	}
+	__syncwarp();
+	for (uint32_t i = lane; i < n; i += 32) a[i] = tmp[i];
+	__syncwarp();
+}
+
 #define MAX_ANCHOR_OVERLAP 3
 __device__ __noinline__ void chain_insert_M3(ReadState &S)
 {
 	int *score_v = S.ws.score_v;
 	DevAnchor *A = S.ws.anc; DevChain *C = S.ws.chain;
 	const int32_t n = (int32_t)S.n_anc;
-	glibc_msort(A, S.ws.anc_tmp, n, AnchorCmp());
+	{	// qsort by (ref_ID, direction, ref_offset), cly.c:226-243
+		uint64_t *key = (uint64_t *)S.ws.sms;                  // the match buffer is idle while chaining
+		if ((uint64_t)n * 8 <= (uint64_t)S.max_matches * sizeof(DevSms)) {
+			for (int32_t i = lane_id(); i < n; i += 32) { const DevAnchor a = A[i]; key[i] = ((uint64_t)a.ref_ID << 33) | ((uint64_t)(a.direction ? 1 : 0) << 32) | a.ref_offset; }
+			warp_stable_sort_by_key(A, S.ws.anc_tmp, (uint32_t)n, key);
+		} else
+			glibc_msort(A, S.ws.anc_tmp, n, AnchorCmp());
+	}
 	for (int32_t chr_st = 0; chr_st < n;) {
 		int32_t chr_ed = chr_st + 1, c_a;
 		const uint32_t ref_ID = A[chr_st].ref_ID;
@@ -282,7 +311,17 @@ __device__ __noinline__ void resolve_tree(ReadState &S)     // cly.c:326-349
 		for (int32_t a = 0; a < (int32_t)S.n_anc; a++) chain_insert_M2(S, a);
 	else
 		chain_insert_M3(S);
-	if (S.n_hit > 1) glibc_msort(S.ws.chain, S.ws.chain_tmp, (int)S.n_hit, ChainCmpByScore());
+	if (S.n_hit > 32 && (uint64_t)S.n_hit * 8 <= (uint64_t)S.max_matches * sizeof(DevSms)) {       // chain_cmp_by_score (cly.c:38-52) as a key
+		uint64_t *key = (uint64_t *)S.ws.sms;
+		__syncwarp();
+		for (uint32_t i = lane_id(); i < S.n_hit; i += 32) {
+			const DevChain c = S.ws.chain[i];
+			int score = c.sum_score + ((c.q_ed - c.q_st) << 1);
+			score -= (c.indel << 2);
+			key[i] = ((uint64_t)(c.with_top_anchor ? 0 : 1) << 32) | (uint32_t)~((uint32_t)score ^ 0x80000000u);   // with_top first, then descending (signed) score
+		}
+		warp_stable_sort_by_key(S.ws.chain, S.ws.chain_tmp, S.n_hit, key);
+	} else if (S.n_hit > 1) glibc_msort(S.ws.chain, S.ws.chain_tmp, (int)S.n_hit, ChainCmpByScore());
 	uint32_t rst_num = DSB_MIN(5u, S.n_hit);
 	while (rst_num < S.n_hit && S.ws.chain[rst_num].with_top_anchor == 1) rst_num++;
 	S.n_hit = rst_num;
