@@ -196,7 +196,10 @@ __device__ __forceinline__ uint32_t next_read(const ClassifyParams &P, int list,
 	return (list < 0) ? P.order[i] : P.list[list][i];
 }
 
-__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_seed(const __grid_constant__ ClassifyLaunch A, int pass, int list, int cursor)
+#ifndef SEED_MIN_BLOCKS
+#define SEED_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SEED_MIN_BLOCKS) k_seed(const __grid_constant__ ClassifyLaunch A, int pass, int list, int cursor)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	ReadState S;
