@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128) k_islands(const __grid_constant__ IslandP
 }
 
 // ------------------------------------------------------------------------------------------------ K2
-struct ScratchLayout { uint64_t anc, anc_tmp, chain, chain_tmp, sms, score_v, sc_hash, kstart[2], kent[2], sp_set, lane_mem, seed_rec, chunk_next, total; };
+struct ScratchLayout { uint64_t anc, anc_tmp, chain, chain_tmp, sms, score_v, sc_hash, kstart[2], kent[2], sp_set, sp_gen, lane_mem, seed_rec, chunk_next, total; };
 static ScratchLayout scratch_layout(uint32_t max_anchors, uint32_t max_matches, uint32_t kidx_bits, uint32_t kidx_len)
 {
 	ScratchLayout L; uint64_t o = 0;
@@ -156,7 +156,8 @@ static ScratchLayout scratch_layout(uint32_t max_anchors, uint32_t max_matches, 
 	L.score_v = take(1024 * sizeof(int));
 	L.sc_hash = take((256 + 2 * 400 + 8) * sizeof(ScHash));
 	for (int s = 0; s < 2; s++) { L.kstart[s] = take(((uint64_t)1 << kidx_bits) * 4 + 128); L.kent[s] = take((uint64_t)kidx_len * sizeof(KEntry) + 128); }
-	L.sp_set = take(32 * 512 * 8);
+	L.sp_set = take(32 * SP_TAB * 8);
+	L.sp_gen = take(32 * 4);
 	L.lane_mem = take(32 * 512 * sizeof(MemRst));
 	L.seed_rec = take(((uint64_t)kidx_len / 2 + 8) * sizeof(SeedRec));
 	L.chunk_next = take(((uint64_t)max_anchors / ANCHOR_CHUNK + 8) * 4);
@@ -179,7 +180,7 @@ __device__ __forceinline__ void warp_setup(const ClassifyLaunch &A, ReadState &S
 	S.ws.chain = (DevChain *)(base + A.L.chain); S.ws.chain_tmp = (DevChain *)(base + A.L.chain_tmp);
 	S.ws.sms = (DevSms *)(base + A.L.sms); S.ws.score_v = (int *)(base + A.L.score_v);
 	S.ws.sc_hash = (ScHash *)(base + A.L.sc_hash);
-	S.ws.sp_set = (uint64_t *)(base + A.L.sp_set); S.ws.lane_mem = (MemRst *)(base + A.L.lane_mem);
+	S.ws.sp_set = (uint64_t *)(base + A.L.sp_set); S.ws.sp_gen = (uint32_t *)(base + A.L.sp_gen); S.ws.lane_mem = (MemRst *)(base + A.L.lane_mem);
 	S.ws.seed_rec = (SeedRec *)(base + A.L.seed_rec); S.ws.chunk_next = (uint32_t *)(base + A.L.chunk_next);
 	for (int s = 0; s < 2; s++) { S.ws.kidx_start[s] = (uint32_t *)(base + A.L.kstart[s]); S.ws.kidx_ent[s] = (KEntry *)(base + A.L.kent[s]); }
 	S.max_anchors = A.P.max_anchors; S.max_matches = A.P.max_matches;
@@ -205,7 +206,26 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SEED_MIN_BLOCKS
 	ReadState S;
 	warp_setup(A, S, smem_raw);
 	DevAnchor *scratch_anc = S.ws.anc;
-	for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_seed(A.P, S, r, pass, scratch_anc);
+	if (list >= 0) {
+		for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_seed(A.P, S, r, pass, scratch_anc);
+		return;
+	}
+	// first pass over all reads in `order` (longest first): the long ones a warp each, the short tail 32 reads per warp
+	for (;;) {
+		uint32_t i = 0;
+		if (lane_id() == 0) i = atomicAdd(A.P.ctl + CTL_CURSOR + cursor, 1u);
+		i = __shfl_sync(DSB_FULL, i, 0);
+		if (i >= A.P.n_long) break;
+		phase_seed(A.P, S, A.P.order[i], pass, scratch_anc);
+	}
+	const uint32_t n_short = A.P.n_reads - A.P.n_long;
+	for (;;) {
+		uint32_t i0 = 0;
+		if (lane_id() == 0) i0 = atomicAdd(A.P.ctl + CTL_CURSOR + 11, 32u);
+		i0 = __shfl_sync(DSB_FULL, i0, 0);
+		if (i0 >= n_short) break;
+		phase_seed_group(A.P, S, A.P.n_long + i0, min(32u, n_short - i0), scratch_anc);
+	}
 }
 
 __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_chain(const __grid_constant__ ClassifyLaunch A, int pass, int list, int cursor)
@@ -240,7 +260,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) k_score_heavy(const __grid_co
 		S.ws.chain = (DevChain *)(base + A.L.chain); S.ws.chain_tmp = (DevChain *)(base + A.L.chain_tmp);
 		S.ws.sms = (DevSms *)(base + A.L.sms); S.ws.score_v = (int *)(base + A.L.score_v);
 		S.ws.sc_hash = (ScHash *)(base + A.L.sc_hash);
-		S.ws.sp_set = (uint64_t *)(base + A.L.sp_set); S.ws.lane_mem = (MemRst *)(base + A.L.lane_mem);
+		S.ws.sp_set = (uint64_t *)(base + A.L.sp_set); S.ws.sp_gen = (uint32_t *)(base + A.L.sp_gen); S.ws.lane_mem = (MemRst *)(base + A.L.lane_mem);
 		S.ws.seed_rec = (SeedRec *)(base + A.L.seed_rec); S.ws.chunk_next = (uint32_t *)(base + A.L.chunk_next);
 		for (int s = 0; s < 2; s++) { S.ws.kidx_start[s] = (uint32_t *)(base + A.L.kstart[s]); S.ws.kidx_ent[s] = (KEntry *)(base + A.L.kent[s]); }
 		S.max_anchors = A.P.max_anchors; S.max_matches = A.P.max_matches;
@@ -360,12 +380,12 @@ extern "C" int dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out)
 	dsb_ctx *c = new dsb_ctx();
 	c->ix = ix;
 	if (o) c->opts = *o; else dsb_opts_default(&c->opts);
-	if (c->opts.max_anchors < 1024) c->opts.max_anchors = 1024;
+	if (c->opts.max_anchors < 32 * SHORT_LANE_ANCHORS) c->opts.max_anchors = 32 * SHORT_LANE_ANCHORS;   // the lane-per-read path cuts the buffer in 32
 	if (c->opts.max_matches < 1024) c->opts.max_matches = 1024;
 	if (c->opts.warps_per_sm < CLASSIFY_WARPS_PER_BLOCK) c->opts.warps_per_sm = CLASSIFY_WARPS_PER_BLOCK;
 	if (c->opts.warps_per_sm > 32) c->opts.warps_per_sm = 32;
 	c->stream = nullptr; c->stream2 = nullptr; c->ev_fork = nullptr; c->ev_join = nullptr; c->h_pin = nullptr; c->h_pin_cap = 0; c->ran = false; c->launches = 0;
-	c->n_reads = 0; c->scratch_stride = 0; c->kidx_bits = 0; c->kidx_len = 0; c->hits_cap = 0;
+	c->n_reads = 0; c->scratch_zeroed_stride = 0; c->scratch_stride = 0; c->kidx_bits = 0; c->kidx_len = 0; c->hits_cap = 0;
 	cudaDeviceProp prop;
 	DSB_CUDA(cudaGetDeviceProperties(&prop, ix->device));
 	c->n_sm = prop.multiProcessorCount;
@@ -388,7 +408,7 @@ extern "C" void dsb_ctx_free(dsb_ctx *c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = {&c->seqs, &c->read_off, &c->bin_off, &c->bits_off, &c->seed_off, &c->tiles, &c->bin, &c->bits, &c->seeds[0], &c->seeds[1],
 	                  &c->n_seeds[0], &c->n_seeds[1], &c->total_score[0], &c->total_score[1], &c->scratch, &c->rr, &c->hits, &c->counters, &c->prof, &c->work, &c->anc_pool, &c->chain_pool,
-	                  &c->lists[0], &c->lists[1], &c->lists[2], &c->lists[3], &c->ctl, &c->order};
+	                  &c->lists[0], &c->lists[1], &c->lists[2], &c->lists[3], &c->lists[4], &c->ctl, &c->order};
 	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
 	if (c->h_pin) cudaFreeHost(c->h_pin);
 	for (int i = 0; i < DSB_N_EV; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -453,6 +473,8 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 	uint32_t *h_order = h_seed_off + n_reads + 1;
 	for (uint32_t r = 0; r < n_reads; r++) h_order[r] = r;
 	std::stable_sort(h_order, h_order + n_reads, [&](uint32_t a, uint32_t b) { return offs[a + 1] - offs[a] > offs[b + 1] - offs[b]; });
+	c->n_long = 0;
+	for (uint32_t r = 0; r < n_reads; r++) if (offs[r + 1] - offs[r] > SHORT_READ_MAX) c->n_long++;
 	if (so >= 0xffffffffull) { dsb_set_error("batch too large (seed slots overflow 32 bits): split the batch"); return DSB_E_ARG; }
 	c->n_tiles = (uint32_t)n_tiles; c->n_bases = n_bases; c->bits_words = wo; c->seed_slots = so; c->bin_bytes = bo; c->max_len = max_len;
 	c->h_bits_off.assign(h_bits_off, h_bits_off + n_reads + 1);
@@ -494,7 +516,12 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 	const ScratchLayout L = scratch_layout(c->opts.max_anchors, c->opts.max_matches, c->kidx_bits, c->kidx_len);
 	c->scratch_stride = L.total;
 	int rc;
-	if ((rc = ensure(c->scratch, (size_t)L.total * (c->n_warps + HEAVY_BLOCKS))) != DSB_OK) return rc;
+	{
+		const void *before = c->scratch.p;
+		if ((rc = ensure(c->scratch, (size_t)L.total * (c->n_warps + HEAVY_BLOCKS))) != DSB_OK) return rc;
+		// the visited-row hash sets (and their generation counters) must start zeroed; a changed layout moves them
+		if (c->scratch.p != before || L.total != c->scratch_zeroed_stride) { DSB_CUDA(cudaMemsetAsync(c->scratch.p, 0, c->scratch.cap, st)); c->scratch_zeroed_stride = L.total; }
+	}
 	// hits: the pre-filter chains of a read use 2 slots each (second half = merge-sort scratch)
 	const uint64_t hits_cap = std::max<uint64_t>(4096, (uint64_t)n * 24);
 	if ((rc = ensure(c->hits, hits_cap * sizeof(dsb_hit))) != DSB_OK) return rc;
@@ -536,7 +563,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		P.ix = c->ix->dev; P.n_reads = n; P.read_off = (const uint64_t *)c->read_off.p; P.bin_off = (const uint64_t *)c->bin_off.p; P.bin = (const uint8_t *)c->bin.p;
 		P.seed_off = (const uint32_t *)c->seed_off.p;
 		for (int s = 0; s < 2; s++) { P.seeds[s] = (const dsb_seed *)c->seeds[s].p; P.n_seeds[s] = (const uint32_t *)c->n_seeds[s].p; P.total_score[s] = (const uint32_t *)c->total_score[s].p; }
-		P.order = (const uint32_t *)c->order.p; P.prof = (uint32_t *)c->prof.p;
+		P.order = (const uint32_t *)c->order.p; P.n_long = c->n_long; P.prof = (uint32_t *)c->prof.p;
 		P.work = (ReadWork *)c->work.p;
 		P.anc_pool = (DevAnchor *)c->anc_pool.p; P.anc_pool_cap = (uint32_t)std::min<uint64_t>(c->anc_pool.cap / sizeof(DevAnchor), 0xfffffff0u);
 		P.chain_pool = (DevChain *)c->chain_pool.p; P.chain_pool_cap = (uint32_t)std::min<uint64_t>(c->chain_pool.cap / sizeof(DevChain), 0xfffffff0u);
@@ -550,7 +577,9 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		const int blocks = c->n_warps / CLASSIFY_WARPS_PER_BLOCK, threads = CLASSIFY_WARPS_PER_BLOCK * 32;
 		const size_t smem = CLASSIFY_WARPS_PER_BLOCK * sizeof(WarpSmem);
 		// classify_seq's control flow (cly.c:3098-3131) as a sequence of phase kernels over work lists
-		k_seed <<<blocks, threads, smem, st>>>(A, PASS_FAST, -1, 0);            DSB_CUDA(cudaEventRecord(c->ev[3], st));
+		k_seed <<<blocks, threads, smem, st>>>(A, PASS_FAST, -1, 0);
+		k_seed <<<blocks, threads, smem, st>>>(A, PASS_FAST, LIST_SEED_REDO, 10);    // short reads whose lane buffer overflowed
+		DSB_CUDA(cudaEventRecord(c->ev[3], st));
 		k_chain<<<blocks, threads, smem, st>>>(A, PASS_FAST, -1, 1);            DSB_CUDA(cudaEventRecord(c->ev[4], st));
 		k_seed <<<blocks, threads, smem, st>>>(A, PASS_SLOW0, LIST_SLOW0, 2);   DSB_CUDA(cudaEventRecord(c->ev[5], st));
 		k_chain<<<blocks, threads, smem, st>>>(A, PASS_SLOW0, LIST_SLOW0, 3);   DSB_CUDA(cudaEventRecord(c->ev[6], st));
@@ -564,7 +593,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		k_score<<<blocks, threads, smem, st>>>(A, LIST_SCORE, 6);
 		DSB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
 		DSB_CUDA(cudaEventRecord(c->ev[9], st));
-		c->launches += 8;
+		c->launches += 9;
 	}
 	{
 		FinalizeParams P;

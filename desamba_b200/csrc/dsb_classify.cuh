@@ -55,7 +55,8 @@ struct WarpScratch {            // per-warp HBM scratch
 	ScHash    *sc_hash;         // 256 + 2*400 + 8
 	uint32_t  *kidx_start[2];   // CSR bucket ends of the read's 9-mer index, per strand slot (0 forward, 1 reverse)
 	KEntry    *kidx_ent[2];
-	uint64_t  *sp_set;          // 32 lanes x 512 visited rows, interleaved
+	uint64_t  *sp_set;          // 32 lanes x SP_TAB slots of the visited-row hash sets, interleaved (zeroed when the scratch is allocated)
+	uint32_t  *sp_gen;          // 32 generation counters of those sets
 	MemRst    *lane_mem;        // 32 lanes x 512
 	SeedRec   *seed_rec;        // one per island seed of a strand
 	uint32_t  *chunk_next;      // max_anchors / ANCHOR_CHUNK links
@@ -67,14 +68,16 @@ struct ReadWork {
 	uint32_t chain_off, n_chain;  // chains kept by resolve_tree, in the chain pool
 	uint16_t error; uint8_t fast_classify, pad;
 };
-enum { LIST_SLOW0 = 0, LIST_SLOW1 = 1, LIST_SCORE = 2, LIST_SCORE_HEAVY = 3, N_LISTS = 4 };   // HEAVY: reads with many anchors, scored first
+enum { LIST_SLOW0 = 0, LIST_SLOW1 = 1, LIST_SCORE = 2, LIST_SCORE_HEAVY = 3, LIST_SEED_REDO = 4, N_LISTS = 5 };   // HEAVY: reads with many anchors, scored first
 #define HEAVY_ANCHORS 256
 #ifndef KIDX_LOAD_SHIFT
 #define KIDX_LOAD_SHIFT 2
 #endif
 enum { PASS_FAST = 0, PASS_SLOW0 = 1, PASS_SLOW1 = 2 };
-// control block (u32): [0..3] list lengths, [4] anchor pool cursor, [5] chain pool cursor, [8..15] work cursors of the launches
-enum { CTL_LIST_N = 0, CTL_ANC_CURSOR = 4, CTL_CHAIN_CURSOR = 5, CTL_CURSOR = 8, CTL_WORDS = 32 };
+// control block (u32): [0..4] list lengths, [5] anchor pool cursor, [6] chain pool cursor, [8..19] work cursors of the launches
+enum { CTL_LIST_N = 0, CTL_ANC_CURSOR = 5, CTL_CHAIN_CURSOR = 6, CTL_CURSOR = 8, CTL_WORDS = 32 };
+#define SHORT_READ_MAX 600          // reads up to this length are seeded one LANE per read in the fast pass
+#define SHORT_LANE_ANCHORS 256      // their lane-private anchor buffer; a read that needs more is redone warp-per-read
 
 struct ClassifyParams {
 	DevIndex ix;
@@ -87,6 +90,7 @@ struct ClassifyParams {
 	const uint32_t *n_seeds[2];
 	const uint32_t *total_score[2];
 	const uint32_t *order;      // read ids, longest first (work order of the first seeding pass)
+	uint32_t n_long;            // the first n_long entries of `order` are longer than SHORT_READ_MAX
 	uint32_t *prof;             // per read: 8 x u32 phase times in units of 1024 cycles (fast, chain, slow, kidx, middle, right, left, total)
 	// state between the phase kernels
 	ReadWork *work;
@@ -1176,6 +1180,103 @@ __device__ void phase_seed(const ClassifyParams &P, ReadState &S, uint32_t r, in
 		atomicAdd(C + DSB_CNT_N_GETREF_BYTES, (unsigned long long)S.c_getref_bytes);
 	}
 	read_end(P, S, r, t0);
+}
+
+// Fast pass for SHORT reads (<= SHORT_READ_MAX bp: a handful of island seeds each), one LANE per READ: lane l runs
+// fast_classify of read order[i0 + l] start to end -- seeds in order, so the "> 512 skips the next seed" rule is applied as
+// the reference writes it (cly.c:1530-1531) -- with the same lane-private search code as seed_pass.  No warp collective
+// is used between the first and the last line of the per-lane part.
+__device__ void phase_seed_group(const ClassifyParams &P, ReadState &S, uint32_t i0, uint32_t count, DevAnchor *scratch_anc)
+{
+	const long long t0 = clock64();
+	const int lane = lane_id();
+	const bool act = (uint32_t)lane < count;
+	uint32_t c_prefix = 0, c_occ = 0, c_locate = 0, c_getref = 0, c_getref_bytes = 0;
+	uint32_t r = 0, read_len = 0;
+	ReadWork w;
+	w.anc_off = w.n_anc = w.chain_off = w.n_chain = 0; w.error = 0; w.fast_classify = 1; w.pad = 0;
+	SearchDir sd[2];
+	LaneCtx L;
+	L.ix = S.ix; L.sp_set = S.ws.sp_set + lane; L.sp_l = 0; L.sp_gen = S.ws.sp_gen[lane]; L.mem = S.ws.lane_mem + lane * 512;
+	L.pool = nullptr; L.chunk_next = nullptr; L.chunk_cursor = nullptr; L.n_chunks = 0; L.first_chunk = L.cur_chunk = 0;
+	L.lin = scratch_anc + (uint32_t)lane * SHORT_LANE_ANCHORS; L.lin_cap = SHORT_LANE_ANCHORS;
+	L.n_out = 0; L.top_score = 35; L.error = 0;
+	L.c_prefix = L.c_occ = L.c_locate = L.c_getref = L.c_getref_bytes = 0;
+	// lane state: strand pass d, next seed k of it, the running seed task
+	int n_dir = 0, d = 0; uint32_t k = 0, seed_start = 0;
+	SeedTask T; T.stage = 2;
+	bool busy = false, running = false;
+	SeedInfo s_i = {nullptr, 0, 0};
+	if (act) {
+		r = P.order[i0 + lane];
+		read_len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
+		if (read_len < MIN_READ_LEN) {                                 // cly.c:3089: untouched (unmapped) result
+			dsb_read_result out;
+			out.hit_off = 0; out.n_hit = 0; out.n_anchor = 0; out.fast_classify = 1; out.entered_final = 0; out.error = 0; out.read_len = read_len;
+			P.rr[r] = out; P.work[r] = w;
+		} else {
+			n_dir = setup_dirs(P, r, read_len, sd) ? 2 : 1;
+			s_i.bin_read = sd[0].bin_read; s_i.read_L = read_len; s_i.direction = sd[0].direction;
+			busy = true;
+		}
+	}
+	for (;;) {
+		// a busy lane without a running seed advances to its next top seed (or finishes its read)
+		while (busy && !running) {
+			if (k >= sd[d].l_seed_v) {
+				d++; k = 0;
+				if (d >= n_dir) { busy = false; break; }
+				s_i.bin_read = sd[d].bin_read; s_i.direction = sd[d].direction;
+				continue;
+			}
+			const dsb_seed sv = sd[d].seed_v[k];
+			if (sv.top == 0) { k++; continue; }
+			sp_set_clear_t(L); L.top_score = 35; seed_start = L.n_out;
+			seed_task_begin(T, sv, false, L.ix->l_ek);
+			running = true;
+		}
+		if (__all_sync(DSB_FULL, !busy)) break;
+		if (running) {
+			if (T.stage != 2) fast_seed_step(L, T, s_i);
+			if (L.error) { busy = false; running = false; }
+			else if (T.stage == 2) {
+				for (uint32_t a = seed_start; a < L.n_out; a++) L.lin[a].useless = (L.lin[a].score < L.top_score) ? 1 : 0;      // cly.c:1536-1542
+				k += T.flag512 ? 2 : 1;                                  // "> 512": c_sv++ skips the next seed (cly.c:1530-1531)
+				running = false;
+			}
+		}
+		__syncwarp();
+	}
+	S.ws.sp_gen[lane] = L.sp_gen;
+	if (act && read_len >= MIN_READ_LEN) {
+		if (L.error == 6) {                                            // too many anchors for the lane buffer: redo warp-per-read
+			const uint32_t i = atomicAdd(P.ctl + CTL_LIST_N + LIST_SEED_REDO, 1u);
+			P.list[LIST_SEED_REDO][i] = r;
+		} else {
+			uint32_t off = 0;
+			if (!L.error && L.n_out) {
+				off = atomicAdd(P.ctl + CTL_ANC_CURSOR, L.n_out);
+				if ((uint64_t)off + L.n_out > P.anc_pool_cap) L.error = 1;
+				else for (uint32_t a = 0; a < L.n_out; a++) P.anc_pool[off + a] = L.lin[a];
+			}
+			w.anc_off = off; w.n_anc = L.n_out; w.error = (uint16_t)L.error;
+			P.work[r] = w;
+			c_prefix = L.c_prefix; c_occ = L.c_occ; c_locate = L.c_locate; c_getref = L.c_getref; c_getref_bytes = L.c_getref_bytes;
+		}
+	}
+	__syncwarp();
+	c_prefix = __reduce_add_sync(DSB_FULL, c_prefix); c_occ = __reduce_add_sync(DSB_FULL, c_occ); c_locate = __reduce_add_sync(DSB_FULL, c_locate);
+	c_getref = __reduce_add_sync(DSB_FULL, c_getref); c_getref_bytes = __reduce_add_sync(DSB_FULL, c_getref_bytes);
+	if (lane == 0) {
+		unsigned long long *C = P.counters;
+		atomicAdd(C + DSB_CNT_N_PREFIX, (unsigned long long)c_prefix);
+		atomicAdd(C + DSB_CNT_N_OCC, (unsigned long long)c_occ);
+		atomicAdd(C + DSB_CNT_N_LOCATE, (unsigned long long)c_locate);
+		atomicAdd(C + DSB_CNT_N_GETREF, (unsigned long long)c_getref);
+		atomicAdd(C + DSB_CNT_N_GETREF_BYTES, (unsigned long long)c_getref_bytes);
+	}
+	if (act && P.prof) { const uint32_t dt = (uint32_t)((clock64() - t0) >> 10); P.prof[(uint64_t)r * 8 + 0] += dt; P.prof[(uint64_t)r * 8 + 7] += dt; }
+	__syncwarp();
 }
 
 __device__ void phase_chain(const ClassifyParams &P, ReadState &S, uint32_t r, int pass)

@@ -15,11 +15,13 @@ struct SeedRec { uint32_t first_chunk, count; int32_t top_score; uint32_t flag51
 
 struct LaneCtx {
 	const DevIndex *ix;
-	uint64_t *sp_set;              // visited-row set, interleaved across lanes: element i at sp_set[i * 32]
-	int sp_l;
+	uint64_t *sp_set;              // visited-row set: open-addressing table of SP_TAB slots, interleaved across lanes (slot i at sp_set[i * 32])
+	int sp_l;                      // SP_SET.l: rows in the set
+	uint32_t sp_gen;               // generation tag of the live entries (clearing the set = a new generation)
 	MemRst *mem;                   // 256 results + 256 merge-sort scratch (slow mode)
 	DevAnchor *pool; uint32_t *chunk_next; uint32_t *chunk_cursor; uint32_t n_chunks;
 	uint32_t first_chunk, cur_chunk, n_out; int top_score;
+	DevAnchor *lin; uint32_t lin_cap;   // lane-per-READ mode (short reads): anchors go to a lane-private linear buffer instead
 	int error;
 	uint32_t c_prefix, c_occ, c_locate, c_getref, c_getref_bytes;
 	uint8_t fr[64];                // pad[8] | q_pre[13] | t_pre[13] | t_suf[13]  (frame layout policy P2 of the oracle)
@@ -72,13 +74,30 @@ __device__ __forceinline__ uint64_t occ_char_t(const DevIndex &ix, uint64_t r, u
 }
 
 // ---------------------------------------------------------------- visited-row set (sp_set_insert, cly.c:1286-1298)
+// The reference keeps <= 500 rows in an array and scans it linearly on every insert; the set is emptied when it is full
+// and at the start of every seed.  Same semantics here with a hash table: slot = (generation << 40) | row (rows of a
+// BWT are < 2^40, like REF_POS.global_offset), 0 = never used; emptying the set = next generation, stale slots read as
+// free.  (The linear scan was 69 % of the instructions of the seeding kernel on short reads, profiles/r1d_*.)
+#define SP_TAB 1024
+__device__ __forceinline__ void sp_set_clear_t(LaneCtx &L)
+{
+	L.sp_l = 0;
+	if (++L.sp_gen >= (1u << 24)) {
+		for (int i = 0; i < SP_TAB; i++) L.sp_set[i * 32] = 0;
+		L.sp_gen = 1;
+	}
+}
 __device__ __forceinline__ int sp_set_insert_t(LaneCtx &L, uint64_t node)
 {
-	if (L.sp_l == SP_SET_CAP) L.sp_l = 0;
-	for (int i = 0; i < L.sp_l; i++) if (L.sp_set[i * 32] == node) return 0;
-	L.sp_set[L.sp_l * 32] = node;
-	L.sp_l++;
-	return 1;
+	if (L.sp_l == SP_SET_CAP) sp_set_clear_t(L);
+	const uint64_t key = ((uint64_t)L.sp_gen << 40) | (node & 0xFFFFFFFFFFull);
+	uint32_t h = (uint32_t)((node * 0x9E3779B97F4A7C15ull) >> 54);          // top 10 bits
+	for (;;) {
+		const uint64_t v = L.sp_set[h * 32];
+		if (v == key) return 0;
+		if ((uint32_t)(v >> 40) != L.sp_gen) { L.sp_set[h * 32] = key; L.sp_l++; return 1; }
+		h = (h + 1) & (SP_TAB - 1);
+	}
 }
 
 // ---------------------------------------------------------------- FM-index search (cly.c:1344-1447)
@@ -209,6 +228,12 @@ __device__ __noinline__ void get_new_ed_t(LaneCtx &L, uint32_t *e_d, uint32_t *l
 
 __device__ __forceinline__ bool anchor_push_t(LaneCtx &L, const DevAnchor &a)
 {
+	if (L.lin) {
+		if (L.n_out >= L.lin_cap) { L.error = 6; return false; }      // the read is redone by the warp-per-read path
+		L.lin[L.n_out++] = a;
+		L.top_score = DSB_MAX(L.top_score, (int)a.score);
+		return true;
+	}
 	if ((L.n_out & (ANCHOR_CHUNK - 1)) == 0) {
 		const uint32_t c = atomicAdd(L.chunk_cursor, 1u);
 		if (c >= L.n_chunks) { L.error = 1; return false; }
@@ -364,61 +389,86 @@ __device__ __forceinline__ uint64_t prefix13(const uint8_t *bin_read, int string
 
 #define MEM_search_FAST 2
 #define MIN_MEM_LEN_FAST 21
-// one top seed of fast_classify (cly.c:1494-1543); returns 1 when the seed scored > 512 (the next seed is then skipped)
-__device__ __noinline__ uint32_t fast_seed_t(LaneCtx &L, const dsb_seed c_sv, const SeedInfo &s_i)
+#define MEM_search_SLOW 8
+#define MIN_MEM_LEN_SLOW 20
+struct MemRstCmp { __device__ int operator()(const MemRst &a, const MemRst &b) const { return b.match_len - a.match_len; } };
+
+// The per-seed schedules of fast_classify (cly.c:1494-1543) and slow_classify (cly.c:1563-1608) as step functions: the
+// lanes of a warp work on different seeds, but a warp-uniform outer loop makes every busy lane do ONE step at a time
+// (one k-mer search, or one map_seed), so that lanes enter bwt_MEM_search_t / map_seed_t together and their dependent
+// loads are in flight at the same time, instead of 32 private instruction streams.
+struct SeedTask {
+	dsb_seed sv;
+	int j;                   // k-mer index inside the island (counts down)
+	int stage;               // 0: searching, 1: slow mode -- mapping the sorted MEM results, 2: done
+	int n_mem, i_mem;        // slow mode: results collected / next one to map
+	uint32_t flag512;
+};
+
+__device__ __forceinline__ void seed_task_begin(SeedTask &T, const dsb_seed sv, bool slow, int l_ek)
+{
+	T.sv = sv; T.j = (int)sv.len - 1; T.stage = 0; T.n_mem = 0; T.i_mem = 0; T.flag512 = 0;
+	if (!slow && T.j < MIN_MEM_LEN_FAST - l_ek) T.stage = 2;
+	if (slow && T.j < 1) T.stage = 2;
+}
+
+// one step of a top seed in fast mode = one iteration of the k-mer loop (cly.c:1500-1534)
+__device__ __forceinline__ void fast_seed_step(LaneCtx &L, SeedTask &T, const SeedInfo &s_i)
 {
 	const int l_ek = L.ix->l_ek;
 	const int min_index = MIN_MEM_LEN_FAST - l_ek;
 	const uint8_t *bin_read = s_i.bin_read;
 	MemRst m_r[MEM_search_FAST];
-	uint32_t flag512 = 0;
-	for (int j = (int)c_sv.len - 1; j >= min_index;) {
-		const int kmer_index = c_sv.offset + j;
-		const int string_index = kmer_index + l_ek - 1;
-		const uint64_t prefixValue = prefix13(bin_read, string_index);
-		const int n = bwt_MEM_search_t(L, bin_read + string_index, prefixValue, MEM_search_FAST, MIN_MEM_LEN_FAST - 1, string_index, m_r);
-		if (n == 0) { j -= 2; continue; }
-		j -= 3;
+	const int kmer_index = T.sv.offset + T.j;
+	const int string_index = kmer_index + l_ek - 1;
+	const uint64_t prefixValue = prefix13(bin_read, string_index);
+	const int n = bwt_MEM_search_t(L, bin_read + string_index, prefixValue, MEM_search_FAST, MIN_MEM_LEN_FAST - 1, string_index, m_r);
+	if (n == 0) T.j -= 2;
+	else {
+		T.j -= 3;
 		int max_score = 0;
 		for (int k = 0; k < n; k++) {
 			m_r[k].read_offset = string_index - m_r[k].match_len;
 			const int c_score = map_seed_t(L, m_r + k, s_i);
 			max_score = DSB_MAX(c_score, max_score);
-			if (L.error) return 0;
+			if (L.error) { T.stage = 2; return; }
 		}
-		if (max_score > 35) j -= 7;
+		if (max_score > 35) T.j -= 7;
 		if (max_score > 256) {
-			if (max_score > 512) flag512 = 1;
-			break;
+			if (max_score > 512) T.flag512 = 1;
+			T.stage = 2;
+			return;
 		}
 	}
-	return flag512;
+	if (T.j < min_index) T.stage = 2;
 }
 
-struct MemRstCmp { __device__ int operator()(const MemRst &a, const MemRst &b) const { return b.match_len - a.match_len; } };
-
-#define MEM_search_SLOW 8
-#define MIN_MEM_LEN_SLOW 20
-// one seed of slow_classify (cly.c:1563-1608)
-__device__ __noinline__ void slow_seed_t(LaneCtx &L, const dsb_seed sv, const SeedInfo &s_i)
+// one step of a seed in slow mode: one k-mer search (cly.c:1570-1591), then -- after the sort by match length -- one
+// map_seed of the at most 8 longest results (cly.c:1595-1600)
+__device__ __forceinline__ void slow_seed_step(LaneCtx &L, SeedTask &T, const SeedInfo &s_i)
 {
 	const int l_ek = L.ix->l_ek;
-	const uint8_t *bin_read = s_i.bin_read;
 	MemRst *mem_rst = L.mem;                                    // <= 30 searches * 8 results per seed (len <= 61)
-	const int min_match_len = DSB_MIN(MIN_MEM_LEN_SLOW - 1, l_ek + 1);
-	int mem_rst_num = 0;
-	for (int j = (int)sv.len - 1; j >= 1; j -= 2) {
-		const int k_idx = sv.offset + j;
+	if (T.stage == 0) {
+		const int min_match_len = DSB_MIN(MIN_MEM_LEN_SLOW - 1, l_ek + 1);
+		const int k_idx = T.sv.offset + T.j;
 		const int s_idx = k_idx + l_ek - 1;
-		const uint64_t pre_v = prefix13(bin_read, s_idx);
-		const int n = bwt_MEM_search_t(L, bin_read + s_idx, pre_v, MEM_search_SLOW, min_match_len, s_idx, mem_rst + mem_rst_num);
-		for (int k = mem_rst_num; k < mem_rst_num + n; k++) mem_rst[k].read_offset = k_idx + l_ek - 1 - mem_rst[k].match_len;
-		mem_rst_num += n;
+		const uint64_t pre_v = prefix13(s_i.bin_read, s_idx);
+		const int n = bwt_MEM_search_t(L, s_i.bin_read + s_idx, pre_v, MEM_search_SLOW, min_match_len, s_idx, mem_rst + T.n_mem);
+		for (int k = T.n_mem; k < T.n_mem + n; k++) mem_rst[k].read_offset = k_idx + l_ek - 1 - mem_rst[k].match_len;
+		T.n_mem += n;
+		T.j -= 2;
+		if (T.j < 1) {
+			if (T.n_mem == 0) { T.stage = 2; return; }
+			if (T.n_mem > 1) glibc_msort(mem_rst, mem_rst + 256, T.n_mem, MemRstCmp());
+			T.n_mem = DSB_MIN(T.n_mem, MEM_search_SLOW);
+			T.stage = 1;
+		}
+		return;
 	}
-	if (mem_rst_num == 0) return;
-	if (mem_rst_num > 1) glibc_msort(mem_rst, mem_rst + 256, mem_rst_num, MemRstCmp());
-	const int max_search = DSB_MIN(mem_rst_num, MEM_search_SLOW);
-	for (int k = 0; k < max_search; k++) { map_seed_t(L, mem_rst + k, s_i); if (L.error) return; }
+	map_seed_t(L, mem_rst + T.i_mem, s_i);
+	T.i_mem++;
+	if (L.error || T.i_mem >= T.n_mem) T.stage = 2;
 }
 
 // ================================================================ warp level
@@ -434,30 +484,47 @@ __device__ __noinline__ void seed_pass(ReadState &S, const SearchDir &sd, uint32
 	if (lane == 0) { sm->next_seed = 0; sm->chunk_cursor = 0; }
 	__syncwarp();
 	LaneCtx L;
-	L.ix = S.ix; L.sp_set = S.ws.sp_set + lane; L.sp_l = 0; L.mem = S.ws.lane_mem + lane * 512;
+	L.ix = S.ix; L.sp_set = S.ws.sp_set + lane; L.sp_l = 0; L.sp_gen = S.ws.sp_gen[lane]; L.mem = S.ws.lane_mem + lane * 512;
 	L.pool = S.ws.anc_tmp; L.chunk_next = S.ws.chunk_next; L.chunk_cursor = &sm->chunk_cursor; L.n_chunks = S.max_anchors / ANCHOR_CHUNK;
-	L.error = 0; L.c_prefix = L.c_occ = L.c_locate = L.c_getref = L.c_getref_bytes = 0;
+	L.error = 0; L.c_prefix = L.c_occ = L.c_locate = L.c_getref = L.c_getref_bytes = 0; L.lin = nullptr; L.lin_cap = 0;
 	const SeedInfo s_i = {sd.bin_read, read_len, sd.direction};
 	const uint8_t top0 = sd.seed_v[0].top;
 	SeedRec *rec = S.ws.seed_rec;
+	SeedTask T; T.stage = 2;
+	int my_k = -1; bool exhausted = false;
 	for (;;) {
-		const uint32_t k = atomicAdd(&sm->next_seed, 1u);
-		if (k >= n_seed) break;
-		const dsb_seed sv = sd.seed_v[k];
-		SeedRec r; r.first_chunk = 0xffffffffu; r.count = 0; r.top_score = 35; r.flag512 = 0;
-		r.c_prefix = r.c_occ = r.c_locate = r.c_getref = r.c_getref_bytes = 0;
-		const bool eligible = slow ? !((int)(sv.len) < 3 && top0 == 0)              // sv_f->top: seed 0's flag, as written (cly.c:1564)
-		                           : (sv.top != 0);
-		if (eligible && !L.error) {
-			L.sp_l = 0; L.n_out = 0; L.first_chunk = 0xffffffffu; L.cur_chunk = 0; L.top_score = 35;
-			L.c_prefix = L.c_occ = L.c_locate = L.c_getref = L.c_getref_bytes = 0;
-			if (slow) slow_seed_t(L, sv, s_i);
-			else r.flag512 = fast_seed_t(L, sv, s_i);
-			r.first_chunk = L.first_chunk; r.count = L.n_out; r.top_score = L.top_score;
-			r.c_prefix = L.c_prefix; r.c_occ = L.c_occ; r.c_locate = L.c_locate; r.c_getref = L.c_getref; r.c_getref_bytes = L.c_getref_bytes;
+		// lanes without a seed pull the next eligible one (ineligible seeds get an empty record on the way)
+		while (my_k < 0 && !exhausted) {
+			const uint32_t k = atomicAdd(&sm->next_seed, 1u);
+			if (k >= n_seed) { exhausted = true; break; }
+			const dsb_seed sv = sd.seed_v[k];
+			const bool eligible = slow ? !((int)(sv.len) < 3 && top0 == 0)              // sv_f->top: seed 0's flag, as written (cly.c:1564)
+			                           : (sv.top != 0);
+			if (eligible && !L.error) {
+				my_k = (int)k;
+				sp_set_clear_t(L); L.n_out = 0; L.first_chunk = 0xffffffffu; L.cur_chunk = 0; L.top_score = 35;
+				L.c_prefix = L.c_occ = L.c_locate = L.c_getref = L.c_getref_bytes = 0;
+				seed_task_begin(T, sv, slow, L.ix->l_ek);
+			} else {
+				SeedRec r; r.first_chunk = 0xffffffffu; r.count = 0; r.top_score = 35; r.flag512 = 0;
+				r.c_prefix = r.c_occ = r.c_locate = r.c_getref = r.c_getref_bytes = 0; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+				rec[k] = r;
+			}
 		}
-		rec[k] = r;
+		if (__all_sync(DSB_FULL, my_k < 0)) break;
+		if (my_k >= 0) {
+			if (T.stage != 2) { if (slow) slow_seed_step(L, T, s_i); else fast_seed_step(L, T, s_i); }
+			if (T.stage == 2) {
+				SeedRec r; r.first_chunk = L.first_chunk; r.count = L.n_out; r.top_score = L.top_score; r.flag512 = T.flag512;
+				r.c_prefix = L.c_prefix; r.c_occ = L.c_occ; r.c_locate = L.c_locate; r.c_getref = L.c_getref; r.c_getref_bytes = L.c_getref_bytes;
+				r.pad[0] = r.pad[1] = r.pad[2] = 0;
+				rec[my_k] = r;
+				my_k = -1;
+			}
+		}
+		__syncwarp();
 	}
+	S.ws.sp_gen[lane] = L.sp_gen;
 	__syncwarp();
 	L.error = __reduce_max_sync(DSB_FULL, L.error);
 	if (L.error) { S.error = L.error; return; }
