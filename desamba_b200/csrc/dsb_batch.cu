@@ -15,7 +15,7 @@
 #define PROBE_THREADS 256
 #define N_BITVEC 5                 // E_fwd, E_rev, T0_fwd, T0_rev, Z (k-mer not masked as low-complexity)
 #define CLASSIFY_WARPS_PER_BLOCK 4
-#define HEAVY_BLOCKS 148              // CTAs of k_score_heavy (one heavy read at a time each)
+#define HEAVY_BLOCKS 32               // CTAs of k_score_heavy (one heavy read at a time each; a handful of reads per batch)
 
 static inline uint32_t bits_words(uint32_t len) { return (len + 31) / 32 + 1; }
 static inline uint32_t seed_slots(uint32_t len) { return len / 2 + 2; }
@@ -585,13 +585,9 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		k_chain<<<blocks, threads, smem, st>>>(A, PASS_SLOW0, LIST_SLOW0, 3);   DSB_CUDA(cudaEventRecord(c->ev[6], st));
 		k_seed <<<blocks, threads, smem, st>>>(A, PASS_SLOW1, LIST_SLOW1, 4);   DSB_CUDA(cudaEventRecord(c->ev[7], st));
 		k_chain<<<blocks, threads, smem, st>>>(A, PASS_SLOW1, LIST_SLOW1, 5);   DSB_CUDA(cudaEventRecord(c->ev[8], st));
-		// scoring: the heavy reads (a CTA each) on the second stream, next to everybody else's warp-per-read kernel
-		DSB_CUDA(cudaEventRecord(c->ev_fork, st));
-		DSB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-		k_score_heavy<<<HEAVY_BLOCKS, TEAM_WARPS * 32, 0, c->stream2>>>(A, LIST_SCORE_HEAVY, 7, (uint32_t)c->n_warps);
-		DSB_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+		// scoring: a warp per read; the few reads that give up there (ERR_DEFER) then get a CTA each
 		k_score<<<blocks, threads, smem, st>>>(A, LIST_SCORE, 6);
-		DSB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+		k_score_heavy<<<HEAVY_BLOCKS, TEAM_WARPS * 32, 0, st>>>(A, LIST_SCORE_HEAVY, 7, (uint32_t)c->n_warps);
 		DSB_CUDA(cudaEventRecord(c->ev[9], st));
 		c->launches += 9;
 	}

@@ -68,8 +68,11 @@ struct ReadWork {
 	uint32_t chain_off, n_chain;  // chains kept by resolve_tree, in the chain pool
 	uint16_t error; uint8_t fast_classify, pad;
 };
-enum { LIST_SLOW0 = 0, LIST_SLOW1 = 1, LIST_SCORE = 2, LIST_SCORE_HEAVY = 3, LIST_SEED_REDO = 4, N_LISTS = 5 };   // HEAVY: reads with many anchors, scored first
-#define HEAVY_ANCHORS 256
+enum { LIST_SLOW0 = 0, LIST_SLOW1 = 1, LIST_SCORE = 2, LIST_SCORE_HEAVY = 3, LIST_SEED_REDO = 4, N_LISTS = 5 };
+// HEAVY: a read whose sparse DP collects more than DEFER_SMS matches in one extension (repeats) gives up in k_score and is
+// re-scored from its (untouched) pool chains by k_score_heavy, a whole CTA per read
+#define DEFER_SMS 1024
+#define ERR_DEFER 7
 #ifndef KIDX_LOAD_SHIFT
 #define KIDX_LOAD_SHIFT 2
 #endif
@@ -794,6 +797,7 @@ __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8
 				CNT_GETREF(S, total_ref_len); get_ref_coop(ix, S.sm->refwin, ref_offset, total_ref_len, true);
 				sdp_match(S, pa.index_in_read + pre_mch - 8, ca.index_in_read - 1, q_str, S.sm->refwin, total_ref_len, kx, pre_refoffset + pre_mch, true);
 				if (S.error) return 0;
+				if (!S.team && S.n_sms > DEFER_SMS) { S.error = ERR_DEFER; return 0; }
 			}
 			if (!sms_push(S, ca.ref_offset, ca.index_in_read, ca.mtch_len - S_A_KEMR_L + 1)) return 0;
 			if (S.n_sms > 1) {
@@ -853,6 +857,7 @@ __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, con
 			const int search_q_st = DSB_MAX(search_q_ed - 2000, ch.q_st - 8);
 			sdp_match(S, search_q_st, search_q_ed, q_str, S.sm->refwin, max_search_ref, kx, c_t_offset, true);
 			if (S.error) return 0;
+			if (!S.team && S.n_sms > DEFER_SMS) { S.error = ERR_DEFER; return 0; }
 			c_t_offset += max_search_ref - S_A_KEMR_L - 3;
 			if (S.n_sms == current_sms) break;
 			if (sms[current_sms].t_pos > sms[max_sms_id].t_pos + 1000) break;
@@ -941,6 +946,7 @@ __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, cons
 			const int search_q_ed = DSB_MIN(search_q_st + 2000, ch.q_st - 1);
 			sdp_match(S, search_q_st, search_q_ed, q_str, S.sm->refwin + OVER_SEARCH_M2, max_search_ref, kx, c_t_offset - max_search_ref, false);
 			if (S.error) return 0;
+			if (!S.team && S.n_sms > DEFER_SMS) { S.error = ERR_DEFER; return 0; }
 			c_t_offset = c_t_offset - max_search_ref + S_A_KEMR_L + 3;
 			if (S.n_sms == current_sms) break;
 			if (sms[current_sms].t_pos + 1000 < sms[max_sms_id].t_pos) break;
@@ -1315,7 +1321,7 @@ __device__ void phase_chain(const ClassifyParams &P, ReadState &S, uint32_t r, i
 		w.chain_off = off; w.n_chain = S.n_hit;
 		if (lane_id() == 0) P.work[r] = w;
 	}
-	if (next >= 0) list_push(P, (next == LIST_SCORE && w.n_anc >= HEAVY_ANCHORS) ? LIST_SCORE_HEAVY : next, r);
+	if (next >= 0) list_push(P, next, r);
 	else write_empty_result(P, r, read_len, w.n_anc, w.fast_classify, 0);
 	read_end(P, S, r, t0);
 }
@@ -1338,6 +1344,11 @@ __device__ void phase_score(const ClassifyParams &P, ReadState &S, uint32_t r)
 	dsb_read_result out;
 	out.hit_off = 0; out.n_hit = 0; out.n_anchor = w.n_anc; out.fast_classify = w.fast_classify; out.entered_final = 1; out.error = 0; out.read_len = read_len;
 	score_and_merge(S, sd, read_len, P.kidx_bits_max);
+	if (S.error == ERR_DEFER) {                          // too heavy for one warp: k_score_heavy starts over from the pool chains
+		list_push(P, LIST_SCORE_HEAVY, r);
+		read_end(P, S, r, t0);
+		return;
+	}
 	if (S.error) { out.error = (uint16_t)S.error; out.entered_final = 0; S.n_hit = 0; }
 	// hand the pre-filter chains to the finalize kernel: reserve 2*n slots (second half = merge-sort scratch)
 	unsigned long long off = 0;
