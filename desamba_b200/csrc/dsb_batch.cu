@@ -717,18 +717,24 @@ extern "C" int dsb_batch_counters(dsb_ctx *c, uint64_t out[16])
 // Random-gather microbenchmark: every thread reads `bytes_each` bytes at pseudo-random aligned positions
 // of a table far larger than L2; the figure reported is sector-granular traffic (max(bytes_each,32) per gather) per second.
 template <int BYTES>
-__global__ void k_gather(const uint8_t *table, uint64_t n_slots, uint64_t n_gathers, uint64_t seed, unsigned long long *sink)
+__global__ void __launch_bounds__(256) k_gather(const uint8_t *table, uint64_t n_slots, uint64_t n_gathers, uint64_t seed, unsigned long long *sink)
 {
 	const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, nthr = gridDim.x * (uint64_t)blockDim.x;
 	uint64_t acc = 0;
-	for (uint64_t g = tid; g < n_gathers; g += nthr) {
-		const uint64_t slot = dsb_hash64_1(g ^ seed) % n_slots;
-		const uint8_t *p = table + slot * BYTES;
-		if (BYTES == 1) acc += __ldg(p);
-		else if (BYTES == 2) acc += __ldg((const uint16_t *)p);
-		else if (BYTES == 4) acc += __ldg((const uint32_t *)p);
-		else if (BYTES == 8) acc += __ldg((const uint64_t *)p);
-		else { for (int k = 0; k < BYTES / 16; k++) { const uint4 v = __ldg((const uint4 *)p + k); acc += v.x + v.y + v.z + v.w; } }
+	constexpr int U = (BYTES <= 16) ? 8 : 4;             // independent gathers in flight per thread
+	for (uint64_t g = tid; g < n_gathers; g += nthr * U) {
+		const uint8_t *p[U];
+		#pragma unroll
+		for (int u = 0; u < U; u++) p[u] = table + (dsb_hash64_1((g + u * nthr) ^ seed) % n_slots) * BYTES;
+		#pragma unroll
+		for (int u = 0; u < U; u++) {
+			if (g + u * nthr >= n_gathers) break;
+			if (BYTES == 1) acc += __ldg(p[u]);
+			else if (BYTES == 2) acc += __ldg((const uint16_t *)p[u]);
+			else if (BYTES == 4) acc += __ldg((const uint32_t *)p[u]);
+			else if (BYTES == 8) acc += __ldg((const uint64_t *)p[u]);
+			else { for (int k = 0; k < BYTES / 16; k++) { const uint4 v = __ldg((const uint4 *)p[u] + k); acc += v.x + v.y + v.z + v.w; } }
+		}
 	}
 	if (acc == 0x123456789abcdefull) atomicAdd(sink, 1ull);
 }
@@ -745,7 +751,7 @@ extern "C" int dsb_gather_bench(int device, uint64_t table_bytes, uint64_t n_gat
 	cudaEvent_t e0, e1;
 	DSB_CUDA(cudaEventCreate(&e0)); DSB_CUDA(cudaEventCreate(&e1));
 	cudaDeviceProp prop; DSB_CUDA(cudaGetDeviceProperties(&prop, device));
-	const int blocks = prop.multiProcessorCount * 8, threads = 256;
+	const int blocks = prop.multiProcessorCount * 8, threads = 256;      // 2048 threads per SM x 4-8 gathers in flight each
 	float best = 1e30f;
 	for (int rep = 0; rep < 4; rep++) {
 		const uint64_t n_slots = table_bytes / bytes_each, seed = 0x9e3779b97f4a7c15ull * (rep + 1);

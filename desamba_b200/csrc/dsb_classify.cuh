@@ -382,7 +382,7 @@ __device__ __noinline__ void build_kidx(ReadState &S, const uint8_t *q, uint32_t
 	// histogram
 	for (uint32_t base = 0; base < nk; base += 128) {
 		const KmerTile T = load_kmer_tile(q, base);
-		#pragma unroll
+		#pragma unroll 1
 		for (int j = 0; j < 4; j++) {
 			const uint32_t p = 32 * j + lane;
 			const uint32_t kmer = tile_kmer(T, p);
@@ -408,7 +408,7 @@ __device__ __noinline__ void build_kidx(ReadState &S, const uint8_t *q, uint32_t
 	// ordered fill; afterwards start[b] = END of bucket b, begin = start[b-1] (0 for b == 0)
 	for (uint32_t base = 0; base < nk; base += 128) {
 		const KmerTile T = load_kmer_tile(q, base);
-		#pragma unroll
+		#pragma unroll 1
 		for (int j = 0; j < 4; j++) {
 			const uint32_t pos = base + 32 * j + lane;
 			const bool act = pos < nk;
@@ -676,7 +676,7 @@ struct DpTeam {
 
 // phase (A) over the predecessors [lo, hi), walked downwards: best candidate per lane and whether the lane's walk hit its break
 template <int KIND>
-__device__ __forceinline__ void dp_range(const DevSms *sms, int lo, int hi, const DevSms &my, bool stopped, int &best, bool &brk_out)
+__device__ __noinline__ void dp_range(const DevSms *sms, int lo, int hi, const DevSms &my, bool stopped, int &best, bool &brk_out)
 {
 	for (int pi = hi - 1; pi >= lo; ) {
 		if (__all_sync(DSB_FULL, stopped)) break;

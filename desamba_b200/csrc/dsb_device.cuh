@@ -115,9 +115,11 @@ static __device__ __noinline__ int32_t lv_extd_dev(const uint8_t *ref, int32_t r
 	int32_t best_score = query_length;
 	#define DSB_R(idx) (((idx) == ref_length) ? (uint32_t)'#' : (uint32_t)ref[(idx)])
 	#define DSB_Q(idx) (((idx) == query_length) ? (uint32_t)'$' : (uint32_t)query[(idx)])
+	#pragma unroll 1
 	for (int i = 0; i <= 4; i++) {
 		int32_t prev_mn = -1, cur_mn = (i - 1), next_mn = mn[-i + 1];
 		int32_t prev_ed = i + 1, cur_ed = i, next_ed = ed[-i + 1];
+		#pragma unroll 1
 		for (int j = -i; j <= 4; j++) {
 			int32_t m, e;
 			if (cur_mn + j < ref_length - 1) {

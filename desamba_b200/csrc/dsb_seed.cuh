@@ -41,7 +41,7 @@ __device__ __forceinline__ uint32_t plane_count(const uint4 &p0, const uint4 &p1
 	return __popcll((a0 ^ x0) & (b0 ^ x1) & (c0 ^ x2) & m_lo) + __popcll((a1 ^ x0) & (b1 ^ x1) & (c1 ^ x2) & m_hi);
 }
 // occ(r, c) for a known symbol c (0..4)
-__device__ __forceinline__ uint64_t occ_t(const DevIndex &ix, uint64_t r, uint32_t c)
+__device__ __noinline__ uint64_t occ_t(const DevIndex &ix, uint64_t r, uint32_t c)
 {
 	const uint4 *line = (const uint4 *)(ix.occ + (r >> 7) * 128);
 	const uint64_t base = __ldg((const uint64_t *)line + c);
@@ -49,7 +49,7 @@ __device__ __forceinline__ uint64_t occ_t(const DevIndex &ix, uint64_t r, uint32
 	return base + plane_count(p0, p1, p2, (int)(r & 127), c);
 }
 // occ(r, *c) with *c == 0xff: takes c = BWT[r] first; '$' (5) returns DOLLOR_POS (bwt.c:50-56)
-__device__ __forceinline__ uint64_t occ_char_t(const DevIndex &ix, uint64_t r, uint32_t &c)
+__device__ __noinline__ uint64_t occ_char_t(const DevIndex &ix, uint64_t r, uint32_t &c)
 {
 	const uint4 *line = (const uint4 *)(ix.occ + (r >> 7) * 128);
 	const uint4 h0 = __ldg(line), h1 = __ldg(line + 1);
@@ -87,7 +87,7 @@ __device__ __forceinline__ void sp_set_clear_t(LaneCtx &L)
 		L.sp_gen = 1;
 	}
 }
-__device__ __forceinline__ int sp_set_insert_t(LaneCtx &L, uint64_t node)
+__device__ __noinline__ int sp_set_insert_t(LaneCtx &L, uint64_t node)
 {
 	if (L.sp_l == SP_SET_CAP) sp_set_clear_t(L);
 	const uint64_t key = ((uint64_t)L.sp_gen << 40) | (node & 0xFFFFFFFFFFull);
@@ -101,7 +101,7 @@ __device__ __forceinline__ int sp_set_insert_t(LaneCtx &L, uint64_t node)
 }
 
 // ---------------------------------------------------------------- FM-index search (cly.c:1344-1447)
-__device__ __forceinline__ void bwt_single_search_t(LaneCtx &L, uint64_t sp, const uint8_t *string, int max_match_len, MemRst *out)
+__device__ __noinline__ void bwt_single_search_t(LaneCtx &L, uint64_t sp, const uint8_t *string, int max_match_len, MemRst *out)
 {
 	const DevIndex &ix = *L.ix;
 	uint64_t new_sp, sa_sp = NO_SA;
@@ -164,7 +164,7 @@ __device__ __noinline__ int bwt_MEM_search_t(LaneCtx &L, const uint8_t *string, 
 }
 
 // ---------------------------------------------------------------- locate + anchors (cly.c:435-496, 629-694, 706-939)
-__device__ __forceinline__ void get_ref_t(LaneCtx &L, uint8_t *out, int64_t off, int32_t length, bool forward)
+__device__ __noinline__ void get_ref_t(LaneCtx &L, uint8_t *out, int64_t off, int32_t length, bool forward)
 {   // get_ref, cly.c:435-466
 	if (off < 0) off = 0;
 	if (length < 0) length = 0;
@@ -173,7 +173,7 @@ __device__ __forceinline__ void get_ref_t(LaneCtx &L, uint8_t *out, int64_t off,
 	for (uint32_t k = 0; k < (uint32_t)length; k++) out[k] = (uint8_t)ref_base_at(*L.ix, forward ? o + k : o - k);
 }
 
-__device__ __forceinline__ int64_t get_uni_t(LaneCtx &L, uint64_t bwt_pos, int search_l, uint64_t *global_offset, uint32_t *uni_offset_)
+__device__ __noinline__ int64_t get_uni_t(LaneCtx &L, uint64_t bwt_pos, int search_l, uint64_t *global_offset, uint32_t *uni_offset_)
 {   // get_uni, cly.c:471-496
 	const DevIndex &ix = *L.ix;
 	L.c_locate++;
