@@ -8,7 +8,8 @@
  *   one thread/GPU  dsb_classify_batch on its own context; batches are dealt in input order
  *   writer (main)   formats the result records of each batch in input order (output_results, cly_mt.c:350-365)
  * The index is replicated per GPU, reads are sharded by batch, nothing is exchanged between GPUs.
- * Extra options: -g INT GPUs to use [all visible], -B INT reads per batch [65536], -M INT Mbases per batch [64].
+ * Extra options: -g INT GPUs to use [all visible], -c INT contexts (batches in flight) per GPU [3], -B INT reads per batch
+ * [262144], -M INT Mbases per batch [256].
  * -t is accepted and ignored (the thread pool it sized no longer exists).
  *
  * Classify_buff_pool.max_read_l (cly.c:2958) is the reference's only cross-read state; with -t 1 it is the running maximum
@@ -29,7 +30,7 @@
 enum { FMT_SAM = 1, FMT_SAM_FULL = 2, FMT_DES = 3, FMT_DES_FULL = 4 };
 
 typedef struct {
-	int l_min_match, n_threads, max_sec_N, fmt, min_score, n_gpus;
+	int l_min_match, n_threads, max_sec_N, fmt, min_score, n_gpus, ctx_per_gpu;
 	uint32_t batch_reads; uint64_t batch_bases;
 	FILE *out;
 } opts_t;
@@ -321,7 +322,7 @@ static void usage(void)
 	fprintf(stderr, "    -l, INT         minimum matching length, ignored for NGS reads [170]\n    -r, INT         max Output number of secondary alignments[5]\n");
 	fprintf(stderr, "    -o, FILE        output results into file [stdout]\n    -s, INT         MIN score[64]\n");
 	fprintf(stderr, "    -f, STR         output format, one of: SAM (default), SAM_FULL, DES, DES_FULL\n");
-	fprintf(stderr, "    -g, INT         number of GPUs [all visible]\n    -B, INT         reads per batch [65536]\n    -M, INT         Mbases per batch [64]\n\n");
+	fprintf(stderr, "    -g, INT         number of GPUs [all visible]\n    -c, INT         batches in flight per GPU [3]\n    -B, INT         reads per batch [262144]\n    -M, INT         Mbases per batch [256]\n\n");
 }
 
 static double now_s(void) { struct timeval t; gettimeofday(&t, NULL); return t.tv_sec + t.tv_usec * 1e-6; }
@@ -329,9 +330,9 @@ static double cpu_s(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); return 
 
 static int classify_main(int argc, char **argv)
 {
-	opts_t o = {170, 4, 5, FMT_SAM, 64, 0, 65536, 64ull << 20, stdout};
+	opts_t o = {170, 4, 5, FMT_SAM, 64, 0, 3, 262144, 256ull << 20, stdout};
 	int c;
-	while ((c = getopt(argc, argv, "ht:l:r:f:o:s:g:B:M:")) >= 0) {
+	while ((c = getopt(argc, argv, "ht:l:r:f:o:s:g:B:M:c:")) >= 0) {
 		if (c == 'h') { usage(); return 0; }
 		else if (c == 't') o.n_threads = atoi(optarg);
 		else if (c == 'l') o.l_min_match = atoi(optarg);
@@ -339,6 +340,7 @@ static int classify_main(int argc, char **argv)
 		else if (c == 'o') { o.out = fopen(optarg, "w"); if (!o.out) { fprintf(stderr, "[xopen] fail to open file '%s'\n", optarg); return 1; } }
 		else if (c == 's') o.min_score = atoi(optarg);
 		else if (c == 'g') o.n_gpus = atoi(optarg);
+		else if (c == 'c') o.ctx_per_gpu = atoi(optarg);
 		else if (c == 'B') o.batch_reads = (uint32_t)atol(optarg);
 		else if (c == 'M') o.batch_bases = (uint64_t)atol(optarg) << 20;
 		else if (c == 'f') {
@@ -352,7 +354,9 @@ static int classify_main(int argc, char **argv)
 	const char *index_dir = argv[optind++];
 	if (o.n_gpus <= 0) { const char *e = getenv("DSB_GPUS"); o.n_gpus = e ? atoi(e) : 0; }
 	fprintf(stderr, "loading index\t");
-	worker_t *w = calloc(64, sizeof *w);
+	if (o.ctx_per_gpu < 1) o.ctx_per_gpu = 1;
+	if (o.ctx_per_gpu > 8) o.ctx_per_gpu = 8;
+	dsb_index *gix[64];
 	int n_gpus = 0;
 	for (int g = 0; g < (o.n_gpus > 0 ? o.n_gpus : 64); g++) {
 		dsb_index *ix = NULL;
@@ -361,23 +365,28 @@ static int classify_main(int argc, char **argv)
 			if (g == 0 || o.n_gpus > 0) { fprintf(stderr, "\n[deSAMBA-b200] cannot load index on GPU %d: %s\n", g, dsb_last_error()); return 1; }
 			break;                                       /* ran out of visible devices */
 		}
-		w[g].gpu = g; w[g].ix = ix; n_gpus++;
+		gix[g] = ix; n_gpus++;
 	}
+	/* several contexts (streams) per GPU: the expensive tail reads of one batch overlap the next batch */
+	const int n_workers = n_gpus * o.ctx_per_gpu;
+	worker_t *w = calloc(n_workers, sizeof *w);
 	dsb_opts dop; dsb_opts_default(&dop);
 	dop.l_min_match = o.l_min_match; dop.min_score = o.min_score;
-	for (int g = 0; g < n_gpus; g++)
-		if (dsb_ctx_create(w[g].ix, &dop, &w[g].ctx) != DSB_OK) { fprintf(stderr, "\n[deSAMBA-b200] %s\n", dsb_last_error()); return 1; }
+	for (int k = 0; k < n_workers; k++) {
+		w[k].gpu = k % n_gpus; w[k].ix = gix[k % n_gpus];
+		if (dsb_ctx_create(w[k].ix, &dop, &w[k].ctx) != DSB_OK) { fprintf(stderr, "\n[deSAMBA-b200] %s\n", dsb_last_error()); return 1; }
+	}
 	const dsb_ref_info *ri = dsb_index_ref_info(w[0].ix);
 	const double t0 = now_s(), c0 = cpu_s();
 	fprintf(stderr, "Start classify\n");
 
 	shared_t sh; memset(&sh, 0, sizeof sh);
-	sh.o = &o; sh.n_slots = 2 * n_gpus + 2; sh.slot = calloc(sh.n_slots, sizeof(slot_t));
+	sh.o = &o; sh.n_slots = 2 * n_workers + 2; sh.slot = calloc(sh.n_slots, sizeof(slot_t));
 	pthread_mutex_init(&sh.mu, NULL); pthread_cond_init(&sh.cv, NULL);
 	sh.n_files = argc - optind; sh.files = argv + optind;
-	pthread_t rd, th[64];
+	pthread_t rd, *th = calloc(n_workers, sizeof *th);
 	pthread_create(&rd, NULL, reader_main, &sh);
-	for (int g = 0; g < n_gpus; g++) { w[g].sh = &sh; pthread_create(&th[g], NULL, worker_main, &w[g]); }
+	for (int k = 0; k < n_workers; k++) { w[k].sh = &sh; pthread_create(&th[k], NULL, worker_main, &w[k]); }
 
 	obuf_t ob = {0};
 	for (;;) {
@@ -400,15 +409,16 @@ static int classify_main(int argc, char **argv)
 		pthread_mutex_unlock(&sh.mu);
 	}
 	pthread_join(rd, NULL);
-	for (int g = 0; g < n_gpus; g++) pthread_join(th[g], NULL);
+	for (int k = 0; k < n_workers; k++) pthread_join(th[k], NULL);
 	fflush(o.out);
 	if (o.out != stdout) fclose(o.out);
 	if (sh.error) { fprintf(stderr, "[deSAMBA-b200] error %d: %s\n", sh.error, sh.errmsg); return 1; }
 	const double sec = now_s() - t0;
 	fprintf(stderr, "%ld sequences processed in %.3fs (%.1f Kseq/m).\n", (long)sh.total_sequences, sec, sh.total_sequences / 1.0e3 / (sec / 60));   /* report_stats, cly_mt.c:439-446 */
 	fprintf(stderr, "Classify CPU: %.3f sec\n", cpu_s() - c0);
-	fprintf(stderr, "GPUs: %d\n", n_gpus);
-	for (int g = 0; g < n_gpus; g++) { dsb_ctx_free(w[g].ctx); dsb_index_free(w[g].ix); }
+	fprintf(stderr, "GPUs: %d (%d contexts each)\n", n_gpus, o.ctx_per_gpu);
+	for (int k = 0; k < n_workers; k++) dsb_ctx_free(w[k].ctx);
+	for (int g = 0; g < n_gpus; g++) dsb_index_free(gix[g]);
 	return 0;
 }
 

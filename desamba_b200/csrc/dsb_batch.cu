@@ -15,7 +15,7 @@
 #define PROBE_THREADS 256
 #define N_BITVEC 5                 // E_fwd, E_rev, T0_fwd, T0_rev, Z (k-mer not masked as low-complexity)
 #define CLASSIFY_WARPS_PER_BLOCK 4
-#define HEAVY_BLOCKS 32               // CTAs of k_score_heavy (one heavy read at a time each; a handful of reads per batch)
+#define HEAVY_BLOCKS 24               // CTAs of k_score_heavy (one heavy read at a time each; a handful of reads per batch)
 
 static inline uint32_t bits_words(uint32_t len) { return (len + 31) / 32 + 1; }
 static inline uint32_t seed_slots(uint32_t len) { return len / 2 + 2; }
@@ -207,7 +207,12 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SEED_MIN_BLOCKS
 	warp_setup(A, S, smem_raw);
 	DevAnchor *scratch_anc = S.ws.anc;
 	if (list >= 0) {
-		for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_seed(A.P, S, r, pass, scratch_anc);
+		// the work lists are in no particular order: take the long reads of the list first (their seeding is the tail of the pass)
+		for (int sweep = 0; sweep < 2; sweep++)
+			for (uint32_t r; (r = next_read(A.P, list, cursor + 12 * sweep)) != 0xffffffffu;) {
+				const bool is_long = (A.P.read_off[r + 1] - A.P.read_off[r]) > 12000;
+				if (is_long == (sweep == 0)) phase_seed(A.P, S, r, pass, scratch_anc);
+			}
 		return;
 	}
 	// first pass over all reads in `order` (longest first): the long ones a warp each, the short tail 32 reads per warp

@@ -674,25 +674,34 @@ struct DpTeam {
 	int best[TEAM_WARPS][32]; int brk[TEAM_WARPS][32];
 };
 
-// phase (A) over the predecessors [lo, hi), walked downwards: best candidate per lane and whether the lane's walk hit its break
+// phase (A) over the predecessors [lo, hi), walked downwards: best candidate per lane and whether the lane's walk hit its break.
+// The predecessors are fetched 32 at a time (one coalesced 512-byte request, the next tile already in flight) and handed
+// to all lanes by shuffle, highest index first.
 template <int KIND>
 __device__ __noinline__ void dp_range(const DevSms *sms, int lo, int hi, const DevSms &my, bool stopped, int &best, bool &brk_out)
 {
-	for (int pi = hi - 1; pi >= lo; ) {
+	const int lane = lane_id();
+	int top = hi - 1;                                    // tile = entries top, top-1, ..., top-31 (lane l holds entry top - l)
+	DevSms cur; cur.t_pos = cur.q_pos = cur.len = cur.score = 0;
+	if (top - lane >= lo) cur = load_sms(sms + top - lane);
+	while (top >= lo) {
 		if (__all_sync(DSB_FULL, stopped)) break;
-		DevSms e[4];
-		#pragma unroll
-		for (int u = 0; u < 4; u++) { e[u].t_pos = e[u].q_pos = e[u].len = e[u].score = 0; if (pi - u >= lo) e[u] = load_sms(sms + pi - u); }
-		#pragma unroll
-		for (int u = 0; u < 4; u++) {
-			if (pi - u >= lo && !stopped) {
+		DevSms nxt; nxt.t_pos = nxt.q_pos = nxt.len = nxt.score = 0;
+		if (top - 32 - lane >= lo) nxt = load_sms(sms + top - 32 - lane);
+		const int n_here = min(32, top - lo + 1);
+		#pragma unroll 4
+		for (int k = 0; k < n_here; k++) {
+			DevSms p;
+			p.t_pos = __shfl_sync(DSB_FULL, cur.t_pos, k); p.q_pos = __shfl_sync(DSB_FULL, cur.q_pos, k);
+			p.len = __shfl_sync(DSB_FULL, cur.len, k); p.score = __shfl_sync(DSB_FULL, cur.score, k);
+			if (!stopped) {
 				bool pass, brk, has; int cand;
-				dp_eval<KIND>(my, e[u], pass, brk, has, cand);
+				dp_eval<KIND>(my, p, pass, brk, has, cand);
 				if (brk) { stopped = true; brk_out = true; }
 				else if (has) best = DSB_MAX(best, cand);
 			}
 		}
-		pi -= 4;
+		cur = nxt; top -= 32;
 	}
 }
 

@@ -26,6 +26,9 @@ order = np.argsort(-P[:, 7])
 print("worst reads:")
 for i in order[:int(os.environ.get("PROF_WORST", "12"))]:
     print(f"  read {i} len={len(seqs[i])} n_anc={res.rr['n_anchor'][i]} n_hit={res.rr['n_hit'][i]} fast={res.rr['fast_classify'][i]} " + " ".join(f"{k}={P[i, j]:.1f}" for j, k in enumerate(names)))
+for j, k in enumerate(names[:7]):
+    i = int(np.argmax(P[:, j]))
+    print(f"max {k}: read {i} len={len(seqs[i])} n_anc={res.rr['n_anchor'][i]} " + " ".join(f"{kk}={P[i, jj]:.1f}" for jj, kk in enumerate(names)))
 q = np.percentile(P[:, 7], [50, 90, 99, 99.9, 100])
 print("total ms percentiles 50/90/99/99.9/100:", [round(float(x), 2) for x in q])
 lens = np.array([len(s) for s in seqs])
