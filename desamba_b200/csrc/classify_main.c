@@ -26,6 +26,7 @@
 #include <sys/time.h>
 #include <sys/resource.h>
 #include <zlib.h>
+#include <fcntl.h>
 
 enum { FMT_SAM = 1, FMT_SAM_FULL = 2, FMT_DES = 3, FMT_DES_FULL = 4 };
 
@@ -73,14 +74,20 @@ static void fail(shared_t *sh, const char *what, int rc)
 }
 
 /* ---------------------------------------------------------------- FASTQ reader (kseq_read semantics, utils.c:939-977) */
-typedef struct { gzFile fp; unsigned char *buf; int n, pos, eof; int last_char; } stream_t;
-#define SBUF (1 << 20)
+typedef struct { gzFile fp; int fd; unsigned char *buf; int n, pos, eof; int last_char; int need_qual; } stream_t;
+#define SBUF (4 << 20)
+/* plain files are read with read(2) (zlib's transparent mode costs an extra copy of every byte); .gz through zlib */
+static inline int st_fill(stream_t *s)
+{
+	s->n = s->fp ? gzread(s->fp, s->buf, SBUF) : (int)read(s->fd, s->buf, SBUF);
+	s->pos = 0;
+	if (s->n <= 0) { s->eof = 1; s->n = 0; return -1; }
+	return 0;
+}
 static inline int st_getc(stream_t *s)
 {
 	if (s->pos >= s->n) {
-		if (s->eof) return -1;
-		s->n = gzread(s->fp, s->buf, SBUF); s->pos = 0;
-		if (s->n <= 0) { s->eof = 1; s->n = 0; return -1; }
+		if (s->eof || st_fill(s)) return -1;
 	}
 	return s->buf[s->pos++];
 }
@@ -89,9 +96,7 @@ static int st_getuntil(stream_t *s, int word, char **dst, size_t *n, size_t *m)
 {
 	for (;;) {
 		if (s->pos >= s->n) {
-			if (s->eof) return -1;
-			s->n = gzread(s->fp, s->buf, SBUF); s->pos = 0;
-			if (s->n <= 0) { s->eof = 1; s->n = 0; return -1; }
+			if (s->eof || st_fill(s)) return -1;
 		}
 		int i = s->pos;
 		if (word) { while (i < s->n && s->buf[i] != '\n' && s->buf[i] != ' ' && s->buf[i] != '\t' && s->buf[i] != '\r' && s->buf[i] != '\v' && s->buf[i] != '\f') i++; }
@@ -130,6 +135,11 @@ static long read_record(stream_t *s, rec_t *r)
 	s->last_char = (c == '>' || c == '@') ? c : 0;
 	if (c != '+') return (long)r->n_seq;                                     /* FASTA record */
 	st_getuntil(s, 0, NULL, NULL, NULL);                                     /* rest of the '+' line */
+	/* fast path (4-line FASTQ, quality not printed): the quality line is exactly as long as the sequence */
+	if (!s->need_qual && r->n_seq && (size_t)(s->n - s->pos) > r->n_seq && s->buf[s->pos + r->n_seq] == '\n') {
+		s->pos += (int)r->n_seq + 1; s->last_char = 0;
+		return (long)r->n_seq;
+	}
 	while (r->n_qual < r->n_seq) {
 		c = st_getuntil(s, 0, &r->qual, &r->n_qual, &r->m_qual);
 		while (r->n_qual && r->qual[r->n_qual - 1] == '\r') r->n_qual--;
@@ -140,10 +150,16 @@ static long read_record(stream_t *s, rec_t *r)
 	return (long)r->n_seq;
 }
 
-static int grow_pinned(void **p, size_t *m, size_t need, size_t keep)
+/* pinned batch buffers: cudaHostAlloc is slow (tens of ms per 100 MB), so a buffer goes to its final size in at most
+ * a few steps: 32 MB, then straight to `full` (the batch limit), beyond that by doubling */
+static int grow_pinned(void **p, size_t *m, size_t need, size_t keep, size_t full)
 {
 	if (need <= *m) return 0;
-	size_t nm = need + need / 2 + 4096; void *np = NULL;
+	size_t nm = (size_t)32 << 20;
+	if (nm > full) nm = full;
+	if (need > nm) nm = full;
+	while (need > nm) nm *= 2;
+	void *np = NULL;
 	if (dsb_host_alloc(nm, &np) != DSB_OK) return -1;
 	if (*p) { memcpy(np, *p, keep); dsb_host_free(*p); }
 	*p = np; *m = nm;
@@ -170,19 +186,26 @@ static void *reader_main(void *arg)
 			if (!pending) {
 				if (!stream_open) {
 					if (file_i >= sh->n_files) { end_of_input = 1; break; }
-					st.fp = gzopen(sh->files[file_i], "r");
-					if (!st.fp) { fprintf(stderr, "[xzopen] fail to open file '%s'\n", sh->files[file_i]); fail(sh, "open reads", -2); end_of_input = 1; break; }
-					gzbuffer(st.fp, 1 << 18);
+					st.fp = NULL;
+					st.fd = open(sh->files[file_i], O_RDONLY);
+					if (st.fd < 0) { fprintf(stderr, "[xzopen] fail to open file '%s'\n", sh->files[file_i]); fail(sh, "open reads", -2); end_of_input = 1; break; }
+					unsigned char magic[2] = {0, 0};
+					if (pread(st.fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+						st.fp = gzdopen(st.fd, "r");
+						if (!st.fp) { fail(sh, "gzdopen", -2); end_of_input = 1; break; }
+						gzbuffer(st.fp, 1 << 20);
+					}
+					st.need_qual = (o->fmt == FMT_SAM_FULL);
 					st.n = st.pos = st.eof = 0; st.last_char = 0; stream_open = 1;
 					fprintf(stderr, "Processing file: [%s].\n", sh->files[file_i]);
 				}
 				plen = read_record(&st, &rec);
-				if (plen < 0) { gzclose(st.fp); stream_open = 0; file_i++; continue; }   /* -1 end of file; -2 ends the file like the reference ends its run */
+				if (plen < 0) { if (st.fp) gzclose(st.fp); else close(st.fd); stream_open = 0; file_i++; continue; }   /* -1 end of file; -2 ends the file like the reference ends its run */
 				pending = 1;
 			}
 			size_t L = (size_t)plen;
-			if (grow_pinned((void **)&b->seqs, &b->m_seqs, b->n_bases + L + 16, b->n_bases) ||
-			    grow_pinned((void **)&b->offs, &b->m_offs, ((size_t)b->n_reads + 2) * 8, ((size_t)b->n_reads + 1) * 8)) { fail(sh, "pinned alloc", -4); end_of_input = 1; break; }
+			if (grow_pinned((void **)&b->seqs, &b->m_seqs, b->n_bases + L + 16, b->n_bases, o->batch_bases + ((size_t)4 << 20)) ||
+			    grow_pinned((void **)&b->offs, &b->m_offs, ((size_t)b->n_reads + 2) * 8, ((size_t)b->n_reads + 1) * 8, ((size_t)o->batch_reads + 2) * 8)) { fail(sh, "pinned alloc", -4); end_of_input = 1; break; }
 			if (b->n_reads == 0) b->offs[0] = 0;
 			memcpy(b->seqs + b->n_bases, rec.seq, L);
 			if (o->fmt == FMT_SAM_FULL) {

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <cstdarg>
 #include <cmath>
+#include <chrono>
 
 static thread_local char g_err[512] = "";
 void dsb_set_error(const char *fmt, ...)
@@ -62,7 +63,12 @@ extern "C" int dsb_index_load(const char *dir, int device, dsb_index **out)
 	int n_dev = 0;
 	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { dsb_set_error("no CUDA device (there is no CPU fallback)"); return DSB_E_CUDA; }
 	if (device < 0 || device >= n_dev) { dsb_set_error("device %d out of range (%d devices)", device, n_dev); return DSB_E_ARG; }
+	const bool verbose = getenv("DSB_VERBOSE") != nullptr;
+	auto t_prev = std::chrono::steady_clock::now();
+	auto lap = [&](const char *what) { if (!verbose) return; auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[dsb_index_load] %-28s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count()); t_prev = t; };
 	DSB_CUDA(cudaSetDevice(device));
+	DSB_CUDA(cudaFree(0));
+	lap("CUDA context");
 	dsb_index *ix = new dsb_index();
 	ix->device = device; ix->hbm_bytes = 0;
 	memset(&ix->dev, 0, sizeof ix->dev);
@@ -75,6 +81,7 @@ extern "C" int dsb_index_load(const char *dir, int device, dsb_index **out)
 			if (!hf.f || !hf.rd(&byteLen, 8) || byteLen % 168 != 0) { dsb_set_error("cannot read %s", hf.path.c_str()); rc = DSB_E_IO; break; }
 			std::vector<uint8_t> blocks(byteLen);
 			if (!hf.rd(blocks.data(), byteLen)) { dsb_set_error("short read %s", hf.path.c_str()); rc = DSB_E_IO; break; }
+			lap("read FM blocks");
 			uint64_t rank[6];
 			if (!hf.rd(rank, 40)) { dsb_set_error("short read %s", hf.path.c_str()); rc = DSB_E_IO; break; }
 			rank[5] = rank[0] - 1;                                     // bwt.c:81
@@ -111,21 +118,26 @@ extern "C" int dsb_index_load(const char *dir, int device, dsb_index **out)
 				memcpy(l, tot, 40);
 				memset(l + 48, 0xff, 48);
 			}
+			lap("re-cut FM blocks (host)");
 			blocks.clear(); blocks.shrink_to_fit();
 			void *d = nullptr;
 			if ((rc = upload(ix, lines.data(), lines.size(), 128, &d)) != DSB_OK) break;
 			ix->dev.occ = (const uint8_t *)d; ix->dev.n_lines = n_lines;
 			lines.clear(); lines.shrink_to_fit();
+			lap("upload FM lines");
 			const uint64_t nh = (1ull << 26) + 1;
 			std::vector<uint64_t> hidx(nh);
 			if (!hf.rd(hidx.data(), nh * 8)) { dsb_set_error("short read %s (prefix table)", hf.path.c_str()); rc = DSB_E_IO; break; }
+			lap("read prefix table");
 			if ((rc = upload(ix, hidx.data(), nh * 8, 0, &d)) != DSB_OK) break;
 			ix->dev.prefix = (const uint64_t *)d;
+			lap("upload prefix table");
 		}
 		void *d = nullptr;
 		// ---- .sa (bwt.c:95-98)
 		if ((rc = load_array(ix, dir, ".sa", 8, true, &ix->sa_size, 0, &d)) != DSB_OK) break;
 		ix->dev.sa = (const uint2 *)d;
+		lap("SA");
 		// ---- exist k-mer tables (idx.c:1105-1118) + set_ekmer_par (idx.c:966-982)
 		{
 			HostFile hf(dir, ".exki");
@@ -146,6 +158,7 @@ extern "C" int dsb_index_load(const char *dir, int device, dsb_index **out)
 		}
 		{ uint64_t n = ix->ek_size; if ((rc = load_array(ix, dir, ".exk0", 1, false, &n, 0, &d)) != DSB_OK) break; ix->dev.ek0 = (const uint8_t *)d; }
 		{ uint64_t n = ix->ek_size; if ((rc = load_array(ix, dir, ".exk1", 1, false, &n, 0, &d)) != DSB_OK) break; ix->dev.ek1 = (const uint8_t *)d; }
+		lap("exist k-mer tables");
 		// ---- .unv + fabricated sentinel (idx.c:1123-1129)
 		{
 			HostFile hf(dir, ".unv");
@@ -197,6 +210,7 @@ extern "C" int dsb_index_load(const char *dir, int device, dsb_index **out)
 			ix->dev.q_mem = (const int *)d; ix->dev.q_lv = (const int *)d + 65536;
 		}
 	} while (0);
+	lap("unitigs, ref, tables");
 	if (rc != DSB_OK) { dsb_index_free(ix); return rc; }
 	*out = ix;
 	return DSB_OK;
