@@ -64,6 +64,8 @@ _sig("dsb_ctx_elapsed_ms", C.c_int, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_fl
 _sig("dsb_batch_launches", C.c_int, _vp)
 _sig("dsb_batch_counters", C.c_int, _vp, C.POINTER(C.c_uint64 * 16))
 _sig("dsb_batch_profile", C.c_int, _vp, _vp)
+_sig("dsb_ctx_set_bin_capacity", C.c_int, _vp, C.c_uint32)
+_sig("dsb_ctx_bin_capacity", C.c_uint32, _vp)
 _sig("dsb_ctx_stream", _vp, _vp)
 _sig("dsb_host_alloc", C.c_int, C.c_size_t, C.POINTER(_vp))
 _sig("dsb_host_free", None, _vp)
@@ -188,7 +190,9 @@ class Context:
             pass
 
     # -- the end-to-end call with host buffers
-    def classify(self, cat, offs, max_read_l_in=0):
+    def classify(self, cat, offs, max_read_l_in=0, m_bin_read_in=0):
+        """one batch; both cross-read states of the reference are given explicitly (0, 0 = first batch of a run)"""
+        lib.dsb_ctx_set_bin_capacity(self._h, m_bin_read_in)
         cat = np.ascontiguousarray(cat, dtype=np.uint8)
         offs = np.ascontiguousarray(offs, dtype=np.uint64)
         n = len(offs) - 1
@@ -215,12 +219,13 @@ class Context:
         self.n_reads = n
         return used.value, mx.value
 
-    def classify_reads(self, seqs, max_read_l_in=0):
+    def classify_reads(self, seqs, max_read_l_in=0, m_bin_read_in=0):
         cat, offs = pack_reads(seqs)
-        return self.classify(cat, offs, max_read_l_in)
+        return self.classify(cat, offs, max_read_l_in, m_bin_read_in)
 
     # -- the three steps separately (run works on inputs resident in HBM)
-    def upload(self, cat, offs):
+    def upload(self, cat, offs, m_bin_read_in=0):
+        lib.dsb_ctx_set_bin_capacity(self._h, m_bin_read_in)
         cat = np.ascontiguousarray(cat, dtype=np.uint8)
         offs = np.ascontiguousarray(offs, dtype=np.uint64)
         self.n_reads = len(offs) - 1
@@ -280,6 +285,13 @@ class Context:
         out = np.zeros((self.n_reads, 8), dtype=np.uint32)
         _check(lib.dsb_batch_profile(self._h, out.ctypes.data), "dsb_batch_profile")
         return out
+
+    def set_bin_capacity(self, m):
+        """cross-read state #2 of the reference (capacity of its bin_read buffer); see include/desamba_b200.h"""
+        _check(lib.dsb_ctx_set_bin_capacity(self._h, m), "dsb_ctx_set_bin_capacity")
+
+    def bin_capacity(self):
+        return lib.dsb_ctx_bin_capacity(self._h)
 
     def stream(self):
         return lib.dsb_ctx_stream(self._h)

@@ -48,6 +48,7 @@ typedef struct {
 	char *names; size_t n_names, m_names;   /* NUL-terminated, concatenated */
 	uint32_t *name_off; size_t m_name_off;
 	int has_long, has_short;
+	uint32_t m_bin_read_in;                 /* capacity of the reference's bin_read buffer before this batch (dsb_ctx_set_bin_capacity) */
 	dsb_read_result *rr; size_t m_rr;
 	dsb_hit *hits; size_t m_hits; uint64_t n_hits;
 } slot_t;
@@ -172,6 +173,7 @@ static void *reader_main(void *arg)
 	stream_t st; memset(&st, 0, sizeof st); st.buf = malloc(SBUF);
 	rec_t rec; memset(&rec, 0, sizeof rec);
 	int file_i = 0, stream_open = 0, pending = 0;      /* pending: rec holds a record not yet stored */
+	uint32_t m_bin_read = 0;                           /* running BUFF_REALLOC capacity over all reads, in input order */
 	long plen = 0;
 	for (;;) {
 		pthread_mutex_lock(&sh->mu);
@@ -180,7 +182,7 @@ static void *reader_main(void *arg)
 		int err = sh->error;
 		pthread_mutex_unlock(&sh->mu);
 		if (err) break;
-		b->n_reads = 0; b->n_bases = 0; b->n_names = 0; b->has_long = b->has_short = 0;
+		b->n_reads = 0; b->n_bases = 0; b->n_names = 0; b->has_long = b->has_short = 0; b->m_bin_read_in = m_bin_read;
 		int end_of_input = 0;
 		while (b->n_reads < o->batch_reads && b->n_bases < o->batch_bases) {
 			if (!pending) {
@@ -218,6 +220,7 @@ static void *reader_main(void *arg)
 			memcpy(b->names + b->n_names, rec.name, rec.n_name); b->names[b->n_names + rec.n_name] = 0; b->n_names += rec.n_name + 1;
 			b->n_bases += L; b->n_reads++; b->offs[b->n_reads] = b->n_bases;
 			if (L >= 510) b->has_long = 1; else b->has_short = 1;
+			if (L >= 40 && 2 * L > m_bin_read) m_bin_read = (uint32_t)(2 * L + 20);
 			pending = 0;
 		}
 		pthread_mutex_lock(&sh->mu);
@@ -259,6 +262,7 @@ static void *worker_main(void *arg)
 		int32_t max_out = max_in; int rc;
 		for (;;) {
 			if (want > b->m_hits) { b->m_hits = want; free(b->hits); b->hits = malloc(b->m_hits * sizeof *b->hits); }
+			dsb_ctx_set_bin_capacity(w->ctx, b->m_bin_read_in);
 			rc = dsb_classify_batch(w->ctx, b->seqs, b->offs, b->n_reads, max_in, &max_out, b->rr, b->hits, b->m_hits, &b->n_hits);
 			if (rc == DSB_E_CAPACITY && b->n_hits > b->m_hits) { want = b->n_hits; continue; }
 			break;

@@ -25,6 +25,7 @@ struct ProbeParams {
 	DevIndex ix;
 	const char *seqs; const uint64_t *read_off, *bin_off, *bits_off;
 	const uint2 *tiles;
+	const uint8_t *hdr7;       // per read: the byte 7 before the forward strand (oracle policy P3: the reference's malloc chunk header)
 	uint8_t *bin; uint32_t *bits;
 };
 
@@ -57,7 +58,10 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_encode_probe(const __grid_con
 		s_code[k] = (uint8_t)code;
 		if (k < PROBE_TILE) { bin_F[start + k] = (uint8_t)code; bin_R[len - 1 - (start + k)] = (uint8_t)(3 - code); }   // cly.c:1250-1259
 	}
-	if (start == 0 && tid < DSB_GUARD) { bin_F[tid - DSB_GUARD] = 0; bin_R[len + tid] = 0; }      // out-of-buffer policy P3
+	if (start == 0 && tid < DSB_GUARD) {                          // out-of-buffer policy P3 (oracle/desamba_oracle.c)
+		bin_F[tid - DSB_GUARD] = (tid == DSB_GUARD - 7) ? P.hdr7[r] : (tid == DSB_GUARD - 8) ? (uint8_t)0xff : (uint8_t)0;
+		bin_R[len + tid] = 0;
+	}
 	__syncthreads();
 	const uint32_t W = (len + 31) / 32 + 1;
 	uint32_t *bits = P.bits + P.bits_off[r];
@@ -390,7 +394,7 @@ extern "C" int dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out)
 	if (c->opts.warps_per_sm < CLASSIFY_WARPS_PER_BLOCK) c->opts.warps_per_sm = CLASSIFY_WARPS_PER_BLOCK;
 	if (c->opts.warps_per_sm > 32) c->opts.warps_per_sm = 32;
 	c->stream = nullptr; c->stream2 = nullptr; c->ev_fork = nullptr; c->ev_join = nullptr; c->h_pin = nullptr; c->h_pin_cap = 0; c->ran = false; c->launches = 0;
-	c->n_reads = 0; c->scratch_zeroed_stride = 0; c->scratch_stride = 0; c->kidx_bits = 0; c->kidx_len = 0; c->hits_cap = 0;
+	c->n_reads = 0; c->m_bin_read = 0; c->scratch_zeroed_stride = 0; c->scratch_stride = 0; c->kidx_bits = 0; c->kidx_len = 0; c->hits_cap = 0;
 	cudaDeviceProp prop;
 	DSB_CUDA(cudaGetDeviceProperties(&prop, ix->device));
 	c->n_sm = prop.multiProcessorCount;
@@ -413,7 +417,7 @@ extern "C" void dsb_ctx_free(dsb_ctx *c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = {&c->seqs, &c->read_off, &c->bin_off, &c->bits_off, &c->seed_off, &c->tiles, &c->bin, &c->bits, &c->seeds[0], &c->seeds[1],
 	                  &c->n_seeds[0], &c->n_seeds[1], &c->total_score[0], &c->total_score[1], &c->scratch, &c->rr, &c->hits, &c->counters, &c->prof, &c->work, &c->anc_pool, &c->chain_pool,
-	                  &c->lists[0], &c->lists[1], &c->lists[2], &c->lists[3], &c->lists[4], &c->ctl, &c->order};
+	                  &c->lists[0], &c->lists[1], &c->lists[2], &c->lists[3], &c->lists[4], &c->ctl, &c->order, &c->hdr7};
 	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
 	if (c->h_pin) cudaFreeHost(c->h_pin);
 	for (int i = 0; i < DSB_N_EV; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -423,6 +427,9 @@ extern "C" void dsb_ctx_free(dsb_ctx *c)
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
+
+extern "C" int dsb_ctx_set_bin_capacity(dsb_ctx *c, uint32_t m_bin_read) { if (!c) return DSB_E_ARG; c->m_bin_read = m_bin_read; return DSB_OK; }
+extern "C" uint32_t dsb_ctx_bin_capacity(dsb_ctx *c) { return c ? c->m_bin_read : 0; }
 
 extern "C" void *dsb_ctx_stream(dsb_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
@@ -452,7 +459,7 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 		if (len >= 40) n_tiles += (len + PROBE_TILE - 1) / PROBE_TILE;
 		max_len = std::max(max_len, len);
 	}
-	const size_t pin_need = tbl_bytes * 3 + (size_t)(n_reads + 1) * 8 + n_tiles * 8 + 64;
+	const size_t pin_need = tbl_bytes * 3 + (size_t)(n_reads + 1) * 8 + n_tiles * 8 + n_reads + 64;
 	if (pin_need > c->h_pin_cap) {
 		if (c->h_pin) cudaFreeHost(c->h_pin);
 		c->h_pin = nullptr; c->h_pin_cap = 0;
@@ -480,6 +487,16 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 	std::stable_sort(h_order, h_order + n_reads, [&](uint32_t a, uint32_t b) { return offs[a + 1] - offs[a] > offs[b + 1] - offs[b]; });
 	c->n_long = 0;
 	for (uint32_t r = 0; r < n_reads; r++) if (offs[r + 1] - offs[r] > SHORT_READ_MAX) c->n_long++;
+	// policy P3: the capacity of the reference's bin_read buffer (BUFF_REALLOC, utils.h:117-122) in input order decides the
+	// chunk-header byte an alignment that runs 7 bases off the start of a read compares with
+	uint8_t *h_hdr7 = (uint8_t *)(h_order + n_reads);
+	for (uint32_t r = 0; r < n_reads; r++) {
+		const uint32_t len = (uint32_t)(offs[r + 1] - offs[r]);
+		if (len >= 40 && 2 * len > c->m_bin_read) c->m_bin_read = 2 * len + 20;
+		uint32_t chunk = (c->m_bin_read + 8 + 15) & ~15u;
+		if (chunk < 32) chunk = 32;
+		h_hdr7[r] = (uint8_t)((chunk >> 8) & 0xff);
+	}
 	if (so >= 0xffffffffull) { dsb_set_error("batch too large (seed slots overflow 32 bits): split the batch"); return DSB_E_ARG; }
 	c->n_tiles = (uint32_t)n_tiles; c->n_bases = n_bases; c->bits_words = wo; c->seed_slots = so; c->bin_bytes = bo; c->max_len = max_len;
 	c->h_bits_off.assign(h_bits_off, h_bits_off + n_reads + 1);
@@ -492,7 +509,7 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 	    (rc = ensure(c->seeds[0], so * sizeof(dsb_seed) + 64)) || (rc = ensure(c->seeds[1], so * sizeof(dsb_seed) + 64)) ||
 	    (rc = ensure(c->n_seeds[0], (size_t)n_reads * 4)) || (rc = ensure(c->n_seeds[1], (size_t)n_reads * 4)) ||
 	    (rc = ensure(c->total_score[0], (size_t)n_reads * 4)) || (rc = ensure(c->total_score[1], (size_t)n_reads * 4)) ||
-	    (rc = ensure(c->rr, (size_t)n_reads * sizeof(dsb_read_result))) || (rc = ensure(c->order, (size_t)n_reads * 4)))
+	    (rc = ensure(c->rr, (size_t)n_reads * sizeof(dsb_read_result))) || (rc = ensure(c->order, (size_t)n_reads * 4)) || (rc = ensure(c->hdr7, (size_t)n_reads + 16)))
 		return rc;
 	cudaStream_t st = c->stream;
 	DSB_CUDA(cudaMemcpyAsync(c->seqs.p, seqs, n_bases, cudaMemcpyHostToDevice, st));
@@ -502,6 +519,7 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 	DSB_CUDA(cudaMemcpyAsync(c->seed_off.p, h_seed_off, (size_t)(n_reads + 1) * 4, cudaMemcpyHostToDevice, st));
 	if (n_tiles) DSB_CUDA(cudaMemcpyAsync(c->tiles.p, h_tiles, n_tiles * 8, cudaMemcpyHostToDevice, st));
 	DSB_CUDA(cudaMemcpyAsync(c->order.p, h_order, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+	DSB_CUDA(cudaMemcpyAsync(c->hdr7.p, h_hdr7, (size_t)n_reads, cudaMemcpyHostToDevice, st));
 	return DSB_OK;
 }
 
@@ -547,7 +565,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 	if (c->n_tiles) {
 		ProbeParams P;
 		P.ix = c->ix->dev; P.seqs = (const char *)c->seqs.p; P.read_off = (const uint64_t *)c->read_off.p; P.bin_off = (const uint64_t *)c->bin_off.p;
-		P.bits_off = (const uint64_t *)c->bits_off.p; P.tiles = (const uint2 *)c->tiles.p; P.bin = (uint8_t *)c->bin.p; P.bits = (uint32_t *)c->bits.p;
+		P.bits_off = (const uint64_t *)c->bits_off.p; P.tiles = (const uint2 *)c->tiles.p; P.hdr7 = (const uint8_t *)c->hdr7.p; P.bin = (uint8_t *)c->bin.p; P.bits = (uint32_t *)c->bits.p;
 		k_encode_probe<<<c->n_tiles, PROBE_THREADS, 0, st>>>(P);
 		c->launches++;
 	}

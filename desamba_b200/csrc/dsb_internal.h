@@ -38,12 +38,13 @@ struct dsb_ctx {
 	// batch inputs (device)
 	DevBuf seqs, read_off, bin_off, bits_off, seed_off, tiles, bin, bits, seeds[2], n_seeds[2], total_score[2];
 	// classify scratch + outputs
-	DevBuf scratch, rr, hits, counters, prof, work, anc_pool, chain_pool, lists[5], ctl, order;
+	DevBuf scratch, rr, hits, counters, prof, work, anc_pool, chain_pool, lists[5], ctl, order, hdr7;
 	uint64_t scratch_stride, scratch_zeroed_stride; uint32_t kidx_bits, kidx_len;
 	uint64_t hits_cap;
 	// pinned staging
 	void *h_pin; size_t h_pin_cap;
 	// batch state
+	uint32_t m_bin_read;                // capacity of the reference's bin_read buffer after the batches seen so far (policy P3)
 	uint32_t n_long;                    // reads longer than SHORT_READ_MAX (prefix of the length-sorted order)
 	uint32_t n_reads, n_tiles; uint64_t n_bases, bits_words, seed_slots, bin_bytes; uint32_t max_len;
 	std::vector<uint64_t> h_off;        // host copies of the per-read offset tables

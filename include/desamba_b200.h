@@ -103,6 +103,13 @@ int dsb_classify_batch(dsb_ctx *ctx, const char *seqs, const uint64_t *offs, uin
                        int32_t max_read_l_in, int32_t *max_read_l_out,
                        dsb_read_result *rr, dsb_hit *hits, uint64_t hits_cap, uint64_t *n_hits_out);
 int dsb_batch_upload(dsb_ctx *ctx, const char *seqs, const uint64_t *offs, uint32_t n_reads);
+/* Second (and last) piece of cross-read state of the reference: the capacity of Classify_buff_pool.bin_read (BUFF_REALLOC,
+ * utils.h:117-122, cly.c:1241): an alignment that runs 7 bases off the START of a read compares with a byte of that buffer's
+ * malloc header, which depends on the capacity.  A context carries the value from batch to batch by itself (= one thread of
+ * the reference); a caller that deals consecutive batches to several contexts sets the value valid before the batch
+ * (it depends on the read lengths only: capacity = 2*len+20 whenever 2*len exceeds it, for reads >= 40 bp). */
+int dsb_ctx_set_bin_capacity(dsb_ctx *ctx, uint32_t m_bin_read);
+uint32_t dsb_ctx_bin_capacity(dsb_ctx *ctx);
 int dsb_batch_run(dsb_ctx *ctx, int32_t max_read_l_in);
 int dsb_batch_download(dsb_ctx *ctx, int32_t *max_read_l_out, dsb_read_result *rr, dsb_hit *hits, uint64_t hits_cap, uint64_t *n_hits_out);
 int dsb_batch_sync(dsb_ctx *ctx);

@@ -14,10 +14,13 @@
  *   P2  the three 13-byte flank arrays of map_seed are adjacent in the order q_pre, t_pre, t_suf and get_new_ed's
  *       q_buff/t_buff reuse the t_pre/t_suf slots (frame layout of the O_def binary, objdump of map_seed);
  *       the 5 padding bytes below q_pre read 0.
- *   P3  the two read strands are contiguous (forward, then reverse complement: cly.c:1247-1259); bytes before
- *       the forward strand and after the reverse strand read ORC_OOB (0 = 'A': what the reference most often
- *       sees there, malloc-header high bytes / untouched realloc slack).  Inputs used for parity keep
- *       alignments away from read ends (adapter padding), so P3 is rarely exercised; the tests quantify it.
+ *   P3  the two read strands are contiguous (forward, then reverse complement: cly.c:1247-1259).  Bytes after the
+ *       reverse strand read ORC_OOB (0 = 'A': untouched realloc slack).  Bytes BEFORE the forward strand are the
+ *       glibc chunk header of the reference's bin_read buffer (BUFF_REALLOC, utils.h:117-122): [-1..-6] = 0 (high
+ *       bytes of the size field), [-7] = (chunk_size >> 8) & 0xff -- a base code 0..3 for buffers of 256..1023 bytes,
+ *       i.e. for short reads -- and [-8] = low size byte | flags, never a base.  chunk_size follows from the running
+ *       capacity m_bin_read of the buffer (grows to 2*len+20 whenever 2*len exceeds it), which is carried over the
+ *       reads in input order (-t 1).  Pinned by tests/golden/syn_short1 (a read starting right of a 7-A run).
  */
 #include "desamba_oracle.h"
 #include <stdlib.h>
@@ -267,6 +270,7 @@ struct orc_buff {
 	sc_hash_t *sc_hash; size_t m_sc_hash;
 	spd_match *sms; size_t n_sms, m_sms;
 	int max_read_l;
+	uint32_t m_bin_read;                      /* capacity of the reference's bin_read buffer (policy P3) */
 };
 
 orc_buff *orc_buff_new(void) { return (orc_buff *)calloc(1, sizeof(orc_buff)); }
@@ -424,6 +428,13 @@ static void get_island(const orc_index *ix, const char *seq, uint32_t read_len, 
 	uint8_t *bin_F = buff->bin_base + GUARD, *bin_R = bin_F + read_len;
 	memset(buff->bin_base, ORC_OOB, GUARD);
 	memset(bin_R + read_len, ORC_OOB, GUARD);
+	{	/* policy P3: the chunk header in front of the reference's buffer */
+		if (2 * read_len > buff->m_bin_read) buff->m_bin_read = 2 * read_len + 20;          /* BUFF_REALLOC */
+		uint32_t chunk = (buff->m_bin_read + 8 + 15) & ~15u;
+		if (chunk < 32) chunk = 32;
+		bin_F[-7] = (uint8_t)((chunk >> 8) & 0xff);
+		bin_F[-8] = 0xff;
+	}
 	for (uint32_t k = 0; k < read_len; ++k) bin_F[k] = cly_bit(seq[k]);
 	seed_vector(ix, bin_F, buff->kmer, l_kmer_buff, res->seeds[0], FORWARD, sd);
 	for (uint32_t k = 0; k < read_len; ++k) bin_R[read_len - k - 1] = 3 - bin_F[k];

@@ -27,5 +27,16 @@ done
 md5sum "$G"/demo.* | sed "s#$G/##" > "$G/demo.md5"
 rm "$G/demo.SAM_FULL" "$G/demo.DES"           # md5 only (SAM_FULL repeats the 2 MB of reads; DES == DES_FULL on this set)
 gzip -9nf "$G/demo.SAM" "$G/demo.DES_FULL"
-md5sum "$R"/sets/*.fq "$R/demo/ERR1050068.fastq" "$FA" | sed "s#$R/##" > "$G/inputs.md5"
+# second index: synthetic multi-strain reference (tools/gen_synth_ref.py 3 species x 4 strains x 300 kb, seed 7): unitigs with
+# several reference positions, many secondary hits
+SYN=$R/syn
+mkdir -p "$SYN"
+[ -s "$SYN/syn.fa" ] || python3 "$ROOT/tools/gen_synth_ref.py" "$SYN/syn.fa" 3 4 300000 7
+[ -s "$SYN/idx/deSAMBA.bwt" ] || "$HERE/build_index.sh" "$SYN/syn.fa" "$SYN/idx"
+[ -s "$R/sets/syn_long10.fq" ] || "$SIM" long "$SYN/syn.fa" 400 0.10 20261025 "$R/sets/syn_long10.fq"
+[ -s "$R/sets/syn_short1.fq" ] || "$SIM" short "$SYN/syn.fa" 4000 0.01 20261026 "$R/sets/syn_short1.fq"
+for s in syn_long10 syn_short1; do
+  "$R/deSAMBA_zero" classify -t 1 -f DES_FULL "$SYN/idx" "$R/sets/$s.fq" -o "$G/$s.DES_FULL" 2>/dev/null; gzip -9nf "$G/$s.DES_FULL"
+done
+md5sum "$R"/sets/*.fq "$R/demo/ERR1050068.fastq" "$FA" "$SYN/syn.fa" | sed "s#$R/##" > "$G/inputs.md5"
 ls -la "$G"

@@ -23,12 +23,18 @@ void *orc_capi_open(const char *dir, int l_min_match, int min_score)
 void orc_capi_close(void *h_) { capi_handle *h = (capi_handle *)h_; if (h) { orc_index_free(&h->ix); free(h); } }
 int orc_capi_l_ek(void *h_) { return ((capi_handle *)h_)->ix.l_ek; }
 
+/* m_bin_read carried between calls (policy P3 of the oracle): set before / read after orc_capi_classify */
+static __thread uint32_t g_m_bin_read = 0;
+void orc_capi_set_m_bin_read(uint32_t m) { g_m_bin_read = m; }
+uint32_t orc_capi_get_m_bin_read(void) { return g_m_bin_read; }
+
 int64_t orc_capi_classify(void *h_, const char *seqs, const uint64_t *offs, uint32_t n, int32_t max_read_l_in, int32_t *max_read_l_out,
                           capi_rr *rr, capi_hit *hits, uint64_t cap)
 {
 	capi_handle *h = (capi_handle *)h_;
 	orc_buff *buff = orc_buff_new();
 	buff->max_read_l = max_read_l_in;
+	buff->m_bin_read = g_m_bin_read;
 	orc_result res; memset(&res, 0, sizeof res);
 	uint64_t used = 0; int64_t ret = 0;
 	for (uint32_t r = 0; r < n; r++) {
@@ -45,6 +51,7 @@ int64_t orc_capi_classify(void *h_, const char *seqs, const uint64_t *offs, uint
 		used += res.n_hit;
 	}
 	if (max_read_l_out) *max_read_l_out = buff->max_read_l;
+	g_m_bin_read = buff->m_bin_read;
 	orc_result_free(&res); orc_buff_free(buff);
 	return ret < 0 ? ret : (int64_t)used;
 }

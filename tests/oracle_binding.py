@@ -16,6 +16,8 @@ DEMO_IDX = os.path.join(REF_DIR, "demo", "idx")
 DEMO_FQ = os.path.join(REF_DIR, "demo", "ERR1050068.fastq")
 DEMO_FA = os.path.join(REF_DIR, "demo", "viral-gs.fa")
 SETS_DIR = os.path.join(REF_DIR, "sets")
+SYN_IDX = os.path.join(REF_DIR, "syn", "idx")      # second index: synthetic 3 species x 4 strains x 300 kb (oracle/make_golden.sh)
+SYN_FA = os.path.join(REF_DIR, "syn", "syn.fa")
 SIMREADS = os.path.join(ROOT, "desamba_b200", "bin", "simreads")
 
 HIT_DTYPE = np.dtype([("ref_ID", "<u4"), ("t_st", "<u4"), ("t_ed", "<u4"), ("q_st", "<u4"), ("q_ed", "<u4"), ("sum_score", "<u4"),
@@ -41,6 +43,17 @@ def ensure_demo_index():
     return DEMO_IDX
 
 
+def ensure_syn_index():
+    """the synthetic multi-strain index (built by the unmodified reference), shipped as oracle/_ref/syn/idx.tgz"""
+    if os.path.exists(os.path.join(SYN_IDX, "deSAMBA.bwt")):
+        return SYN_IDX
+    tgz = os.path.join(REF_DIR, "syn", "idx.tgz")
+    if not os.path.exists(tgz):
+        raise FileNotFoundError(f"{SYN_IDX} and {tgz} are both missing: run oracle/make_golden.sh where /root/reference exists")
+    subprocess.run(["tar", "xzf", tgz, "-C", os.path.join(REF_DIR, "syn")], check=True)
+    return SYN_IDX
+
+
 _lib = None
 
 
@@ -61,6 +74,8 @@ def lib():
         _lib.orc_capi_classify_mt.restype = C.c_uint64
         _lib.orc_capi_classify_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
         _lib.orc_capi_l_ek.argtypes = [C.c_void_p]
+        _lib.orc_capi_set_m_bin_read.argtypes = [C.c_uint32]
+        _lib.orc_capi_get_m_bin_read.restype = C.c_uint32
     return _lib
 
 
@@ -80,7 +95,8 @@ class Oracle:
             lib().orc_capi_close(self._h)
             self._h = None
 
-    def classify(self, cat, offs, max_read_l_in=0):
+    def classify(self, cat, offs, max_read_l_in=0, m_bin_read_in=0):
+        """one batch with a fresh scratch buffer (both cross-read states of the reference given explicitly)"""
         cat = np.ascontiguousarray(cat, dtype=np.uint8)
         offs = np.ascontiguousarray(offs, dtype=np.uint64)
         n = len(offs) - 1
@@ -89,6 +105,7 @@ class Oracle:
         while True:
             hits = np.zeros(cap, dtype=HIT_DTYPE)
             mx = C.c_int32(0)
+            lib().orc_capi_set_m_bin_read(m_bin_read_in)
             used = lib().orc_capi_classify(self._h, cat.ctypes.data, offs.ctypes.data, n, max_read_l_in, C.byref(mx), rr.ctypes.data, hits.ctypes.data, cap)
             if used < 0:
                 cap *= 4

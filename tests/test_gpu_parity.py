@@ -88,6 +88,33 @@ def test_driver_options_and_gz_input(gpu, ob, demo_index, tmp_path):
     assert open(tmp_path / "o.sam", "rb").read() == gzip.open(os.path.join(GOLD, "long10.l100s40r2.SAM.gz")).read()
 
 
+@pytest.mark.parametrize("name,spec", [("syn_long10", ("long", 400, 0.10, 20261025)), ("syn_short1", ("short", 4000, 0.01, 20261026))])
+def test_second_index_multi_strain(gpu, ob, name, spec):
+    # another index (synthetic, 4 strains per species: several REF_POS per unitig, many secondaries): records against the
+    # oracle, driver text against the golden output of the unmodified reference
+    dsb, _, _ = gpu
+    idx = ob.ensure_syn_index()
+    path = ob.sim_set(name, *spec, fasta=ob.SYN_FA)
+    names, seqs, _ = ob.read_fastq(path)
+    cat, offs = ob.pack(seqs)
+    orc = ob.Oracle(idx)
+    orc.counters(reset=True)
+    rr_o, hits_o, mx_o = orc.classify(cat, offs)
+    cnt_o = orc.counters()
+    ix2 = dsb.Index(idx, 0)
+    ctx2 = dsb.Context(ix2)
+    try:
+        res = ctx2.classify(cat, offs)
+        _assert_same(ob, res, rr_o, hits_o, names)
+        cnt_g = ctx2.counters()
+        assert {k: cnt_g[k] for k in CNT} == {k: cnt_o[k] for k in CNT}
+        assert int((res.hits["primary"] == 2).sum()) > 500           # secondaries exist on this index
+    finally:
+        ctx2.close(); ix2.close(); orc.close()
+    out = _run_driver(["-f", "DES_FULL", "-B", "1000", idx, path])
+    assert out == gzip.open(os.path.join(GOLD, f"{name}.DES_FULL.gz")).read()
+
+
 def test_edge_cases(gpu, ob, oracle):
     dsb, ix, ctx = gpu
     _, demo, _ = ob.read_fastq(ob.DEMO_FQ, 40)
@@ -126,10 +153,10 @@ def test_max_read_l_state(gpu, ob, oracle):
         assert res.max_read_l == mx_o
     # chained batches == one batch
     whole_rr, whole_hits, _ = oracle.classify(cat, offs, 0)
-    mx, got = 0, []
+    mx, cap, got = 0, 0, []
     for lo in range(0, len(reads), 64):
-        res = ctx.classify(*ob.pack(reads[lo:lo + 64]), mx)
-        mx = res.max_read_l
+        res = ctx.classify(*ob.pack(reads[lo:lo + 64]), mx, cap)
+        mx, cap = res.max_read_l, ctx.bin_capacity()
         got += [res.read_hits(i).tobytes() for i in range(len(res.rr))]
     want = [whole_hits[int(o):int(o) + int(n)].tobytes() for o, n in zip(whole_rr["hit_off"], whole_rr["n_hit"])]
     assert got == want

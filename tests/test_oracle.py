@@ -50,6 +50,19 @@ def test_synthetic_sets_match_reference(ob, demo_index, name, fmt):
     assert out == gzip.open(os.path.join(GOLD, f"{name}.{fmt}.gz")).read()
 
 
+@pytest.mark.parametrize("name,spec", [("syn_long10", ("long", 400, 0.10, 20261025)), ("syn_short1", ("short", 4000, 0.01, 20261026))])
+def test_second_index_multi_strain(ob, name, spec):
+    # synthetic multi-strain reference: unitigs with several reference positions, thousands of secondary hits
+    try:
+        idx = ob.ensure_syn_index()
+    except FileNotFoundError as e:
+        pytest.skip(str(e))
+    path = ob.sim_set(name, *spec, fasta=ob.SYN_FA)
+    out = _orc_cli(ob, ["-f", "DES_FULL", idx, path])
+    gold = gzip.open(os.path.join(GOLD, f"{name}.DES_FULL.gz")).read()
+    assert out == gold and gold.count(b" SEC ") > 1000
+
+
 def test_options_l_s_r(ob, demo_index):
     path = ob.sim_set("long10", *SETS["long10"])
     out = _orc_cli(ob, ["-l", "100", "-s", "40", "-r", "2", demo_index, path])
