@@ -33,7 +33,7 @@ struct DevChain {               // chain_item (cly.h:69-89)
 };
 struct DevSms { uint32_t t_pos, q_pos, len, score; };   // spd_match (cly.h:127-133)
 struct MemRst { int match_len; int sa_sp_l; uint64_t sp, sa_sp; int read_offset; int pad; };   // MEM_rst (cly.c:619-627)
-struct KEntry { uint32_t kmer, pos; };
+struct KEntry { uint32_t kmer, prev; };   // the read's 9-mer index: entry p = 9-mer at position p + the previous (smaller) position of the same bucket
 struct ScHash { uint16_t next; uint16_t seed_ID; uint16_t s_or_e; uint16_t pad; };   // seed_con_hash (cly.h:120-125)
 
 struct WarpSmem {               // per-warp shared memory
@@ -73,9 +73,6 @@ enum { LIST_SLOW0 = 0, LIST_SLOW1 = 1, LIST_SCORE = 2, LIST_SCORE_HEAVY = 3, LIS
 // re-scored from its (untouched) pool chains by k_score_heavy, a whole CTA per read
 #define DEFER_SMS 1024
 #define ERR_DEFER 7
-#ifndef KIDX_LOAD_SHIFT
-#define KIDX_LOAD_SHIFT 2
-#endif
 enum { PASS_FAST = 0, PASS_SLOW0 = 1, PASS_SLOW1 = 2 };
 // control block (u32): [0..4] list lengths, [5] anchor pool cursor, [6] chain pool cursor, [8..19] work cursors of the launches
 enum { CTL_LIST_N = 0, CTL_ANC_CURSOR = 5, CTL_CHAIN_CURSOR = 6, CTL_CURSOR = 8, CTL_WORDS = 32 };
@@ -370,65 +367,43 @@ __device__ __forceinline__ uint32_t tile_kmer(const KmerTile &T, uint32_t p)
 	return (P >> (6 - 2 * o)) & 0x3ffffu;
 }
 
+#define KIDX_NIL 0xffffffffu
+// The read's 9-mer index (replaces build_hash_table_M2, cly.c:2173-2224).  The reference chains the positions of a bucket
+// in ascending order and compares the full 9-mer on lookup.  Here: ent[p] = {9-mer at p, previous position of the same
+// bucket} written SEQUENTIALLY (coalesced; scattered 8-byte entry stores cost 100 B/base of DRAM traffic, profiles/r1f),
+// head[bucket] = last position.  A lookup walks a bucket from its last position downwards (and can stop below the query
+// range); sdp_scan_pos turns the order around again.
 __device__ __noinline__ void build_kidx(ReadState &S, const uint8_t *q, uint32_t q_len, int slot, int key_bits)
 {
-	uint32_t *start = S.ws.kidx_start[slot];
+	uint32_t *head = S.ws.kidx_start[slot];
 	KEntry *ent = S.ws.kidx_ent[slot];
 	const uint32_t nb = 1u << key_bits, kmask = nb - 1;
 	const int lane = lane_id();
 	const uint32_t nk = q_len - S_A_KEMR_L + 1;
-	for (uint32_t b = lane * 4; b < nb; b += 128) *(uint4 *)(start + b) = make_uint4(0, 0, 0, 0);
+	for (uint32_t b = lane * 4; b < nb; b += 128) *(uint4 *)(head + b) = make_uint4(KIDX_NIL, KIDX_NIL, KIDX_NIL, KIDX_NIL);
 	__syncwarp();
-	// histogram
 	for (uint32_t base = 0; base < nk; base += 128) {
 		const KmerTile T = load_kmer_tile(q, base);
 		#pragma unroll 1
 		for (int j = 0; j < 4; j++) {
-			const uint32_t p = 32 * j + lane;
-			const uint32_t kmer = tile_kmer(T, p);
-			if (base + p < nk) atomicAdd(start + (kmer & kmask), 1u);
-		}
-	}
-	__syncwarp();
-	__threadfence_block();
-	// exclusive scan over buckets, in place, 4 buckets per lane
-	uint32_t carry = 0;
-	for (uint32_t b0 = 0; b0 < nb; b0 += 128) {
-		uint4 v = __ldcg((const uint4 *)(start + b0) + lane);
-		const uint32_t sum = v.x + v.y + v.z + v.w;
-		uint32_t x = sum;
-		#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(DSB_FULL, x, d); if (lane >= d) x += y; }
-		uint32_t e = carry + x - sum;
-		uint4 o; o.x = e; e += v.x; o.y = e; e += v.y; o.z = e; e += v.z; o.w = e;
-		*((uint4 *)(start + b0) + lane) = o;
-		carry += __shfl_sync(DSB_FULL, x, 31);
-	}
-	__syncwarp();
-	// ordered fill; afterwards start[b] = END of bucket b, begin = start[b-1] (0 for b == 0)
-	for (uint32_t base = 0; base < nk; base += 128) {
-		const KmerTile T = load_kmer_tile(q, base);
-		#pragma unroll 1
-		for (int j = 0; j < 4; j++) {
-			const uint32_t pos = base + 32 * j + lane;
+			const uint32_t pos0 = base + 32 * j, pos = pos0 + lane;
 			const bool act = pos < nk;
 			const uint32_t kmer = tile_kmer(T, 32 * j + lane);
 			const uint32_t key = act ? (kmer & kmask) : (0x80000000u | lane);
 			const uint32_t peers = __match_any_sync(DSB_FULL, key);
-			const int leader = __ffs(peers) - 1;
-			const uint32_t rank = __popc(peers & ((1u << lane) - 1));
-			uint32_t cur = 0;
-			if (act && lane == leader) cur = start[key];
-			cur = __shfl_sync(DSB_FULL, cur, leader);
-			if (act) { KEntry e; e.kmer = kmer; e.pos = pos; ent[cur + rank] = e; }
-			if (act && lane == leader) start[key] = cur + __popc(peers);
+			const uint32_t below = peers & ((1u << lane) - 1);
+			uint32_t prev;
+			if (below) prev = pos0 + (31 - __clz(below));                 // an earlier position of this round in the same bucket
+			else prev = act ? head[key] : KIDX_NIL;
+			if (act) { KEntry e; e.kmer = kmer; e.prev = prev; ent[pos] = e; }
+			if (act && (peers >> lane) == 1u) head[key] = pos;           // the last position of the bucket in this round
 			__syncwarp();
 		}
 	}
 	__syncwarp();
 }
 
-struct KIdx { const uint32_t *start; const KEntry *ent; uint32_t kmask; };
+struct KIdx { const uint32_t *start; const KEntry *ent; uint32_t kmask; };   // start = head[]
 
 // ---------------------------------------------------------------- 9-mer sparse DP scoring (cly.c:1691-1818, 2335-2849)
 __device__ __forceinline__ void sc_hash_idx(ReadState &S)      // cly.c:1691-1710
@@ -510,46 +485,48 @@ __device__ __forceinline__ bool sms_push(ReadState &S, uint32_t t_pos, uint32_t 
 // an ordered compaction of each round of 32 positions.  kmer(i) is rebuilt from the window instead of rolled.
 struct SdpArgs { uint32_t q_bg, q_ed; const uint8_t *q_str, *t_str; uint32_t t_len, t_st; KIdx kx; };
 
+// all matches of target position i.  The bucket is walked from its highest read position downwards, the reference emits
+// ascending read positions: with total == 0 (first pass) the k-th match found goes to out[k] for k < cap; with the number of
+// matches known (second pass) it goes to out[total - 1 - k].  Returns the number of matches.
 template <bool FWD>
-__device__ __forceinline__ uint32_t sdp_scan_pos(const SdpArgs &A, int i, DevSms *out, uint32_t cap)
-{   // all matches of target position i; writes the first `cap` of them to out[], returns their number
+__device__ __forceinline__ uint32_t sdp_scan_pos(const SdpArgs &A, int i, DevSms *out, uint32_t cap, uint32_t total)
+{
 	const uint8_t *c_t_str = FWD ? (A.t_str + i) : (A.t_str + A.t_len - S_A_KEMR_L - i);
 	uint32_t kmer = 0;
 	#pragma unroll
 	for (int k = 0; k < S_A_KEMR_L; k++) kmer = (kmer << 2) | c_t_str[k];
-	const uint32_t key = kmer & A.kx.kmask;
-	uint32_t e = key ? A.kx.start[key - 1] : 0;
-	const uint32_t e_end = A.kx.start[key];
 	uint32_t n = 0;
-	for (; e < e_end; e++) {
-		const KEntry en = A.kx.ent[e];
-		if (en.kmer != kmer) continue;
-		const uint32_t q_pos = en.pos;
-		if (!(q_pos >= A.q_bg && q_pos <= A.q_ed)) continue;
+	for (uint32_t q_pos = A.kx.start[kmer & A.kx.kmask]; q_pos != KIDX_NIL; ) {
+		if (q_pos < A.q_bg) break;                                     // positions only get smaller from here
+		const KEntry en = A.kx.ent[q_pos];
+		const uint32_t cur = q_pos;
+		q_pos = en.prev;
+		if (en.kmer != kmer || cur > A.q_ed) continue;
+		DevSms m; m.score = 0;
+		bool hit = false;
 		if (FWD) {
-			const int back_len = MEM_search_bwd(A.q_str + q_pos - 1, c_t_str - 1, 4);
+			const int back_len = MEM_search_bwd(A.q_str + cur - 1, c_t_str - 1, 4);
 			if (back_len < 4 || i == 4) {
-				uint32_t max_search = A.q_ed - q_pos - 1;
+				uint32_t max_search = A.q_ed - cur - 1;
 				max_search = DSB_MIN(max_search, A.t_len - i - 1) + OVER_SEARCH_M2;
-				const int forward_len = MEM_search_fwd(A.q_str + q_pos + S_A_KEMR_L, c_t_str + S_A_KEMR_L, max_search);
+				const int forward_len = MEM_search_fwd(A.q_str + cur + S_A_KEMR_L, c_t_str + S_A_KEMR_L, max_search);
 				const int total_len = back_len + forward_len + 1;
-				if (total_len >= 4) {
-					if (n < cap) { out[n].t_pos = i - back_len + A.t_st; out[n].q_pos = q_pos - back_len; out[n].len = total_len; }
-					n++;
-				}
+				if (total_len >= 4) { hit = true; m.t_pos = i - back_len + A.t_st; m.q_pos = cur - back_len; m.len = total_len; }
 			}
 		} else {
-			const int forward_len = MEM_search_fwd(A.q_str + q_pos + S_A_KEMR_L, c_t_str + S_A_KEMR_L, 4);
+			const int forward_len = MEM_search_fwd(A.q_str + cur + S_A_KEMR_L, c_t_str + S_A_KEMR_L, 4);
 			if (forward_len < 4 || i == 4) {
-				uint32_t max_search = q_pos;
+				uint32_t max_search = cur;
 				max_search = DSB_MIN((long)max_search, (long)(c_t_str - A.t_str)) + OVER_SEARCH_M2;
-				const int back_len = MEM_search_bwd(A.q_str + q_pos - 1, c_t_str - 1, max_search);
+				const int back_len = MEM_search_bwd(A.q_str + cur - 1, c_t_str - 1, max_search);
 				const int total_len = back_len + forward_len + 1;
-				if (total_len >= 4) {
-					if (n < cap) { out[n].t_pos = (uint32_t)((long)(c_t_str - A.t_str) - back_len + A.t_st); out[n].q_pos = q_pos - back_len; out[n].len = total_len; }
-					n++;
-				}
+				if (total_len >= 4) { hit = true; m.t_pos = (uint32_t)((long)(c_t_str - A.t_str) - back_len + A.t_st); m.q_pos = cur - back_len; m.len = total_len; }
 			}
+		}
+		if (hit) {
+			if (total) { DevSms *o = out + (total - 1 - n); o->t_pos = m.t_pos; o->q_pos = m.q_pos; o->len = m.len; }
+			else if (n < cap) out[n] = m;
+			n++;
 		}
 	}
 	return n;
@@ -566,7 +543,7 @@ __device__ __forceinline__ void sdp_match_warp(ReadState &S, const SdpArgs &A)
 		const uint32_t k = base + lane;
 		const int i = 4 + 4 * (int)k;
 		DevSms loc[2];
-		const uint32_t cnt = (k < n_pos) ? sdp_scan_pos<FWD>(A, i, loc, 2) : 0;
+		const uint32_t cnt = (k < n_pos) ? sdp_scan_pos<FWD>(A, i, loc, 2, 0) : 0;
 		uint32_t x = cnt;
 		#pragma unroll
 		for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(DSB_FULL, x, d); if (lane >= d) x += y; }
@@ -574,8 +551,8 @@ __device__ __forceinline__ void sdp_match_warp(ReadState &S, const SdpArgs &A)
 		if (total == 0) continue;
 		if (S.n_sms + total > S.max_matches) { S.error = 2; return; }
 		DevSms *dst = S.ws.sms + S.n_sms + (x - cnt);
-		if (cnt <= 2) { for (uint32_t m = 0; m < cnt; m++) { dst[m].t_pos = loc[m].t_pos; dst[m].q_pos = loc[m].q_pos; dst[m].len = loc[m].len; } }
-		else sdp_scan_pos<FWD>(A, i, dst, cnt);
+		if (cnt <= 2) { for (uint32_t m = 0; m < cnt; m++) { const DevSms &l = loc[cnt - 1 - m]; dst[m].t_pos = l.t_pos; dst[m].q_pos = l.q_pos; dst[m].len = l.len; } }   // found in descending order
+		else sdp_scan_pos<FWD>(A, i, dst, cnt, cnt);
 		S.n_sms += total;
 		__syncwarp();
 	}
@@ -1033,10 +1010,8 @@ __device__ __noinline__ void score_and_merge(ReadState &S, const SearchDir *sear
 		both_dir |= (C[i].direction == DSB_FORWARD) ? 0x2 : 0x1;
 		if (both_dir == 3) break;
 	}
-	// the reference sizes its chained hash at >= l_read buckets (cly.c:2196-2198); the CSR table here only has to be a
-	// superset filter (entries carry the full 9-mer), so it is kept 2^KIDX_LOAD_SHIFT times smaller: cheaper build passes
-	int key_bits = 7;
-	for (; key_bits < 17; key_bits++) if (((1u << KIDX_LOAD_SHIFT) << key_bits) >= l_read) break;
+	int key_bits = 10;                                             // hash_size[key_len] >= q_len, cly.c:2196-2198
+	for (; key_bits < 18; key_bits++) if ((1u << key_bits) >= l_read) break;
 	if ((uint32_t)key_bits > kidx_bits_max) key_bits = kidx_bits_max;
 	for (int c_dir = 2; c_dir >= 1; c_dir--) {
 		if ((c_dir & both_dir) == 0) continue;
