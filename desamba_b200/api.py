@@ -206,8 +206,12 @@ class Context:
             if rc == DSB_E_CAPACITY and used.value > cap:
                 cap = int(used.value)
                 continue
-            _check(rc, "dsb_classify_batch")
             self.n_reads = n
+            if rc != 0:
+                e = DsbError(rc, "dsb_classify_batch")
+                if rc == DSB_E_CAPACITY:                 # per-read capacity: the other reads' records are valid (dsb_read_result.error)
+                    e.result = BatchResult(rr, hits[:min(used.value, cap)], mx.value)
+                raise e
             return BatchResult(rr, hits[:used.value], mx.value)
 
     def classify_into(self, cat, offs, rr, hits, max_read_l_in=0):

@@ -219,6 +219,53 @@ __device__ __forceinline__ void warp_stable_sort_by_key(T *a, T *tmp, uint32_t n
 	__syncwarp();
 }
 
+// The same stable sort for large n (thousands of anchors of a repeat-rich read; counting ranks is O(n^2)): chunks of
+// SORT_CHUNK keys are rank-sorted, then merged pairwise -- every element finds its place in the other run by binary search
+// (left run wins ties, which keeps the sort stable).  key0/key1 and idx0/idx1 are ping-pong buffers of n entries each.
+#define SORT_CHUNK 1024
+template <typename T>
+__device__ __noinline__ void warp_stable_sort_large(T *a, T *tmp, uint32_t n, uint64_t *key0, uint64_t *key1, uint32_t *idx0, uint32_t *idx1)
+{
+	const int lane = lane_id();
+	__syncwarp();
+	for (uint32_t c0 = 0; c0 < n; c0 += SORT_CHUNK) {                    // chunk sort: (key0, identity) -> (key1, idx1)
+		const uint32_t cn = DSB_MIN((uint32_t)SORT_CHUNK, n - c0);
+		for (uint32_t i0 = 0; i0 < cn; i0 += 32) {
+			const uint32_t i = i0 + lane;
+			const uint64_t ki = (i < cn) ? key0[c0 + i] : 0;
+			uint32_t r = 0;
+			for (uint32_t j = 0; j < cn; j++) { const uint64_t kj = key0[c0 + j]; r += (kj < ki || (kj == ki && j < i)) ? 1u : 0u; }
+			if (i < cn) { key1[c0 + r] = ki; idx1[c0 + r] = c0 + i; }
+		}
+	}
+	__syncwarp();
+	uint64_t *ks = key1, *kd = key0; uint32_t *is = idx1, *id = idx0;
+	for (uint32_t w = SORT_CHUNK; w < n; w <<= 1) {                      // merge runs of width w
+		for (uint32_t p = lane; p < n; p += 32) {
+			const uint32_t pair = p / (2 * w) * (2 * w), l0 = pair, l1 = DSB_MIN(pair + w, n), r1 = DSB_MIN(pair + 2 * w, n);
+			const uint64_t k = ks[p];
+			uint32_t dst;
+			if (p < l1) {                                                // left run: elements of the right run that are < k come first
+				uint32_t lo = l1, hi = r1;
+				while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ks[mid] < k) lo = mid + 1; else hi = mid; }
+				dst = p + (lo - l1);
+			} else {                                                     // right run: elements of the left run that are <= k come first
+				uint32_t lo = l0, hi = l1;
+				while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ks[mid] <= k) lo = mid + 1; else hi = mid; }
+				dst = (p - l1) + lo;
+			}
+			kd[dst] = k; id[dst] = is[p];
+		}
+		__syncwarp();
+		uint64_t *tk = ks; ks = kd; kd = tk;
+		uint32_t *ti = is; is = id; id = ti;
+	}
+	for (uint32_t i = lane; i < n; i += 32) tmp[i] = a[is[i]];
+	__syncwarp();
+	for (uint32_t i = lane; i < n; i += 32) a[i] = tmp[i];
+	__syncwarp();
+}
+
 #define MAX_ANCHOR_OVERLAP 3
 __device__ __noinline__ void chain_insert_M3(ReadState &S)
 {
@@ -229,7 +276,10 @@ __device__ __noinline__ void chain_insert_M3(ReadState &S)
 		uint64_t *key = (uint64_t *)S.ws.sms;                  // the match buffer is idle while chaining
 		if ((uint64_t)n * 8 <= (uint64_t)S.max_matches * sizeof(DevSms)) {
 			for (int32_t i = lane_id(); i < n; i += 32) { const DevAnchor a = A[i]; key[i] = ((uint64_t)a.ref_ID << 33) | ((uint64_t)(a.direction ? 1 : 0) << 32) | a.ref_offset; }
-			warp_stable_sort_by_key(A, S.ws.anc_tmp, (uint32_t)n, key);
+			if (n <= 2 * SORT_CHUNK) warp_stable_sort_by_key(A, S.ws.anc_tmp, (uint32_t)n, key);
+			else if ((uint64_t)n * 16 <= (uint64_t)S.max_matches * sizeof(DevSms) && (uint64_t)n * 8 <= (uint64_t)S.max_anchors * sizeof(DevChain))
+				warp_stable_sort_large(A, S.ws.anc_tmp, (uint32_t)n, key, key + n, (uint32_t *)S.ws.chain_tmp, (uint32_t *)S.ws.chain_tmp + n);   // chain_tmp is idle here
+			else warp_stable_sort_by_key(A, S.ws.anc_tmp, (uint32_t)n, key);
 		} else
 			glibc_msort(A, S.ws.anc_tmp, n, AnchorCmp());
 	}

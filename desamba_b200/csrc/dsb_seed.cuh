@@ -481,8 +481,6 @@ __device__ __noinline__ void seed_pass(ReadState &S, const SearchDir &sd, uint32
 	const uint32_t n_seed = sd.l_seed_v;
 	if (slow) S.fast_classify = 0;
 	if (n_seed == 0) return;
-	if (lane == 0) { sm->next_seed = 0; sm->chunk_cursor = 0; }
-	__syncwarp();
 	LaneCtx L;
 	L.ix = S.ix; L.sp_set = S.ws.sp_set + lane; L.sp_l = 0; L.sp_gen = S.ws.sp_gen[lane]; L.mem = S.ws.lane_mem + lane * 512;
 	L.pool = S.ws.anc_tmp; L.chunk_next = S.ws.chunk_next; L.chunk_cursor = &sm->chunk_cursor; L.n_chunks = S.max_anchors / ANCHOR_CHUNK;
@@ -491,12 +489,23 @@ __device__ __noinline__ void seed_pass(ReadState &S, const SearchDir &sd, uint32
 	const uint8_t top0 = sd.seed_v[0].top;
 	SeedRec *rec = S.ws.seed_rec;
 	SeedTask T; T.stage = 2;
+	uint32_t carry = 0;                                          // 1: the next seed in array order is skipped
+	uint32_t n_anc = S.n_anc;
+	uint32_t c_prefix = 0, c_occ = 0, c_locate = 0, c_getref = 0, c_getref_bytes = 0;      // counters of the seeds the reference would have run
+	// Every seed that yields an anchor holds at least one chunk of the staging pool, so the seeds are taken in windows small
+	// enough for the pool (one window for all but reads of several 100 kb): search the window's seeds, append, reuse the pool.
+	const uint32_t win = DSB_MAX(32u, (L.n_chunks / 2) & ~31u);
+	for (uint32_t w0 = 0; w0 < n_seed; w0 += win) {
+	const uint32_t w1 = DSB_MIN(n_seed, w0 + win);
+	__syncwarp();
+	if (lane == 0) { sm->next_seed = w0; sm->chunk_cursor = 0; }
+	__syncwarp();
 	int my_k = -1; bool exhausted = false;
 	for (;;) {
 		// lanes without a seed pull the next eligible one (ineligible seeds get an empty record on the way)
 		while (my_k < 0 && !exhausted) {
 			const uint32_t k = atomicAdd(&sm->next_seed, 1u);
-			if (k >= n_seed) { exhausted = true; break; }
+			if (k >= w1) { exhausted = true; break; }
 			const dsb_seed sv = sd.seed_v[k];
 			const bool eligible = slow ? !((int)(sv.len) < 3 && top0 == 0)              // sv_f->top: seed 0's flag, as written (cly.c:1564)
 			                           : (sv.top != 0);
@@ -529,14 +538,11 @@ __device__ __noinline__ void seed_pass(ReadState &S, const SearchDir &sd, uint32
 	L.error = __reduce_max_sync(DSB_FULL, L.error);
 	if (L.error) { S.error = L.error; return; }
 	// ordered append: drop the seeds removed by the "> 512 skips the next seed" rule (cly.c:1530-1531), prefix-sum, copy
-	uint32_t carry = 0;                                          // 1: the next seed in array order is skipped
-	uint32_t n_anc = S.n_anc;
-	uint32_t c_prefix = 0, c_occ = 0, c_locate = 0, c_getref = 0, c_getref_bytes = 0;      // counters of the seeds the reference would have run
-	for (uint32_t base = 0; base < n_seed; base += 32) {
+	for (uint32_t base = w0; base < w1; base += 32) {
 		const uint32_t k = base + lane;
 		SeedRec r; r.first_chunk = 0xffffffffu; r.count = 0; r.top_score = 35; r.flag512 = 0;
 		r.c_prefix = r.c_occ = r.c_locate = r.c_getref = r.c_getref_bytes = 0;
-		if (k < n_seed) r = rec[k];
+		if (k < w1) r = rec[k];
 		const uint32_t F = __ballot_sync(DSB_FULL, r.flag512 != 0);
 		uint32_t skipped = 0;
 		#pragma unroll
@@ -562,6 +568,7 @@ __device__ __noinline__ void seed_pass(ReadState &S, const SearchDir &sd, uint32
 			S.ws.anc[dst + i] = a;
 		}
 		n_anc += total;
+	}
 	}
 	__syncwarp();
 	S.n_anc = n_anc;

@@ -138,6 +138,20 @@ def test_edge_cases(gpu, ob, oracle):
     _assert_same(ob, one, r1, h1)
 
 
+def test_very_long_reads_many_anchors(gpu, ob, oracle):
+    # reads of 150-400 kb built from many simulated reads: thousands of anchors (merge-sort path of the anchor sort, many
+    # chain groups, 18-bit 9-mer index) -- the reference handles these through realloc'd vectors
+    dsb, ix, ctx = gpu
+    _, seqs, _ = ob.read_fastq(_set_path(ob, "long10"), 120)
+    reads = [b"".join(seqs[0:20]), b"".join(seqs[20:70]), b"".join(seqs[70:120])[:400000], seqs[3]]
+    cat, offs = ob.pack(reads)
+    rr_o, hits_o, mx_o = oracle.classify(cat, offs)
+    assert int(rr_o["n_anchor"].max()) > 2500
+    res = ctx.classify(cat, offs)
+    _assert_same(ob, res, rr_o, hits_o)
+    assert res.max_read_l == mx_o
+
+
 def test_max_read_l_state(gpu, ob, oracle):
     # Classify_buff_pool.max_read_l (cly.c:2958): short reads are filtered differently once a read >= 510 bp has reached the
     # filter -- inside a batch (input order) and across batches (max_read_l_in / max_read_l_out)
