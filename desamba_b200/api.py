@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "lib", "libdesamba_b200.so")
+lib_path = os.environ.get("DSB_LIB") or os.path.join(_HERE, "lib", "libdesamba_b200.so")   # DSB_LIB: developer override (kernel variants)
 if not os.path.exists(lib_path):
     raise ImportError(
         f"{lib_path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -123,6 +123,16 @@ __global__ void __launch_bounds__(128) k_islands(const __grid_constant__ IslandP
 			uint32_t max_index = 0, max_length = 0, index_end = 100;
 			#define PROBE(idx) (calls_nz += bit_at(Z, (idx)), calls_t0 += bit_at(T0, (idx)), bit_at(E, (idx)))
 			for (uint32_t i = 2; i < n; i += 3) {
+				{   // the probes i, i+3, ... that fall into the current 32-bit word and miss are taken in one step
+					const uint32_t w = i >> 5, b = i & 31, left = n - (w << 5);
+					uint32_t pm = ((b % 3 == 0) ? 0x49249249u : (b % 3 == 1) ? 0x92492492u : 0x24924924u) & (0xffffffffu << b);
+					if (left < 32) pm &= (1u << left) - 1;
+					const uint32_t e = __ldg(E + w) & pm;
+					const uint32_t miss = e ? (pm & ((1u << (__ffs(e) - 1)) - 1)) : pm;
+					if (miss) { calls_nz += __popc(__ldg(Z + w) & miss); calls_t0 += __popc(__ldg(T0 + w) & miss); }
+					if (!e) { i = (w << 5) + (31 - __clz(pm)); continue; }
+					i = (w << 5) + __ffs(e) - 1;
+				}
 				if (!PROBE(i)) continue;
 				uint32_t offset = i, l = 1;
 				for (int j = 1; j < 3; ++j) { if (PROBE(i - j)) { offset--; l++; } else break; }
@@ -149,8 +159,8 @@ __global__ void __launch_bounds__(128) k_islands(const __grid_constant__ IslandP
 }
 
 // ------------------------------------------------------------------------------------------------ K2
-struct ScratchLayout { uint64_t anc, anc_tmp, chain, chain_tmp, sms, score_v, sc_hash, kstart[2], kent[2], sp_set, sp_gen, lane_mem, seed_rec, chunk_next, total; };
-static ScratchLayout scratch_layout(uint32_t max_anchors, uint32_t max_matches, uint32_t kidx_bits, uint32_t kidx_len)
+struct ScratchLayout { uint64_t anc, anc_tmp, chain, chain_tmp, sms, sms_tmp, cand, sort_key[2], sort_idx[2], score_v, sc_hash, sp_set, sp_gen, lane_mem, seed_rec, chunk_next, total; };
+static ScratchLayout scratch_layout(uint32_t max_anchors, uint32_t max_matches, uint32_t max_len)
 {
 	ScratchLayout L; uint64_t o = 0;
 	auto take = [&](uint64_t bytes) { uint64_t at = o; o += (bytes + 127) & ~127ull; return at; };
@@ -159,11 +169,12 @@ static ScratchLayout scratch_layout(uint32_t max_anchors, uint32_t max_matches, 
 	L.sms = take((uint64_t)max_matches * sizeof(DevSms));
 	L.score_v = take(1024 * sizeof(int));
 	L.sc_hash = take((256 + 2 * 400 + 8) * sizeof(ScHash));
-	for (int s = 0; s < 2; s++) { L.kstart[s] = take(((uint64_t)1 << kidx_bits) * 4 + 128); L.kent[s] = take((uint64_t)kidx_len * sizeof(KEntry) + 128); }
+	L.sms_tmp = take((uint64_t)max_matches * sizeof(DevSms)); L.cand = take((uint64_t)CAND_CAP * sizeof(uint2));
+	for (int s = 0; s < 2; s++) { L.sort_key[s] = take((uint64_t)max_matches * 8); L.sort_idx[s] = take((uint64_t)max_matches * 4); }
 	L.sp_set = take(32 * SP_TAB * 8);
 	L.sp_gen = take(32 * 4);
 	L.lane_mem = take(32 * 512 * sizeof(MemRst));
-	L.seed_rec = take(((uint64_t)kidx_len / 2 + 8) * sizeof(SeedRec));
+	L.seed_rec = take(((uint64_t)max_len / 2 + 8) * sizeof(SeedRec));
 	L.chunk_next = take(((uint64_t)max_anchors / ANCHOR_CHUNK + 8) * 4);
 	L.total = o;
 	return L;
@@ -186,9 +197,10 @@ __device__ __forceinline__ void warp_setup(const ClassifyLaunch &A, ReadState &S
 	S.ws.sc_hash = (ScHash *)(base + A.L.sc_hash);
 	S.ws.sp_set = (uint64_t *)(base + A.L.sp_set); S.ws.sp_gen = (uint32_t *)(base + A.L.sp_gen); S.ws.lane_mem = (MemRst *)(base + A.L.lane_mem);
 	S.ws.seed_rec = (SeedRec *)(base + A.L.seed_rec); S.ws.chunk_next = (uint32_t *)(base + A.L.chunk_next);
-	for (int s = 0; s < 2; s++) { S.ws.kidx_start[s] = (uint32_t *)(base + A.L.kstart[s]); S.ws.kidx_ent[s] = (KEntry *)(base + A.L.kent[s]); }
+	S.ws.sms_tmp = (DevSms *)(base + A.L.sms_tmp); S.ws.cand = (uint2 *)(base + A.L.cand);
+	for (int s = 0; s < 2; s++) { S.ws.sort_key[s] = (uint64_t *)(base + A.L.sort_key[s]); S.ws.sort_idx[s] = (uint32_t *)(base + A.L.sort_idx[s]); }
 	S.max_anchors = A.P.max_anchors; S.max_matches = A.P.max_matches;
-	S.team = nullptr;
+	S.team = nullptr; S.mt = nullptr; S.l_read = 0;
 }
 // next read of the launch's work list, or 0xffffffff; list < 0: all reads in `order`
 __device__ __forceinline__ uint32_t next_read(const ClassifyParams &P, int list, int cursor)
@@ -250,6 +262,7 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_score(const _
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	ReadState S;
 	warp_setup(A, S, smem_raw);
+	S.mt = (MatchSmem *)(smem_raw + CLASSIFY_WARPS_PER_BLOCK * sizeof(WarpSmem)) + (threadIdx.x >> 5);
 	for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_score(A.P, S, r);
 }
 
@@ -259,6 +272,7 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_score(const _
 __global__ void __launch_bounds__(TEAM_WARPS * 32) k_score_heavy(const __grid_constant__ ClassifyLaunch A, int list, int cursor, uint32_t slot0)
 {
 	__shared__ __align__(16) WarpSmem wsm;
+	__shared__ __align__(16) MatchSmem msm;
 	__shared__ DpTeam team;
 	const int warp = threadIdx.x >> 5;
 	if (warp == 0) {
@@ -271,8 +285,9 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) k_score_heavy(const __grid_co
 		S.ws.sc_hash = (ScHash *)(base + A.L.sc_hash);
 		S.ws.sp_set = (uint64_t *)(base + A.L.sp_set); S.ws.sp_gen = (uint32_t *)(base + A.L.sp_gen); S.ws.lane_mem = (MemRst *)(base + A.L.lane_mem);
 		S.ws.seed_rec = (SeedRec *)(base + A.L.seed_rec); S.ws.chunk_next = (uint32_t *)(base + A.L.chunk_next);
-		for (int s = 0; s < 2; s++) { S.ws.kidx_start[s] = (uint32_t *)(base + A.L.kstart[s]); S.ws.kidx_ent[s] = (KEntry *)(base + A.L.kent[s]); }
-		S.max_anchors = A.P.max_anchors; S.max_matches = A.P.max_matches;
+		S.ws.sms_tmp = (DevSms *)(base + A.L.sms_tmp); S.ws.cand = (uint2 *)(base + A.L.cand);
+		for (int s = 0; s < 2; s++) { S.ws.sort_key[s] = (uint64_t *)(base + A.L.sort_key[s]); S.ws.sort_idx[s] = (uint32_t *)(base + A.L.sort_idx[s]); }
+		S.max_anchors = A.P.max_anchors; S.max_matches = A.P.max_matches; S.mt = &msm; S.l_read = 0;
 		for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_score(A.P, S, r);
 		if (lane_id() == 0) team.cmd = -1;
 		__syncthreads();                                 // releases the helpers
@@ -531,12 +546,9 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 	c->launches = 0;
 	const uint32_t n = c->n_reads;
 	if (n == 0) { c->ran = true; return DSB_OK; }
-	// classify scratch: sized by the batch's longest read (the read's 9-mer index is the large part)
-	uint32_t kb = 10; for (; kb < 18; kb++) if ((1u << kb) >= c->max_len) break;          // hash_size[key_len] >= q_len (cly.c:2196-2198)
-	if (kb > c->kidx_bits || c->max_len + 64 > c->kidx_len || c->scratch_stride == 0) {
-		c->kidx_bits = std::max(c->kidx_bits, kb); c->kidx_len = std::max(c->kidx_len, c->max_len + 64);
-	}
-	const ScratchLayout L = scratch_layout(c->opts.max_anchors, c->opts.max_matches, c->kidx_bits, c->kidx_len);
+	// classify scratch: the per-seed records are sized by the longest read seen
+	if (c->max_len + 64 > c->kidx_len || c->scratch_stride == 0) c->kidx_len = std::max(c->kidx_len, c->max_len + 64);
+	const ScratchLayout L = scratch_layout(c->opts.max_anchors, c->opts.max_matches, c->kidx_len);
 	c->scratch_stride = L.total;
 	int rc;
 	{
@@ -593,7 +605,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		for (int l = 0; l < N_LISTS; l++) P.list[l] = (uint32_t *)c->lists[l].p;
 		P.ctl = (uint32_t *)c->ctl.p;
 		P.scratch = (uint8_t *)c->scratch.p; P.scratch_stride = L.total;
-		P.max_anchors = c->opts.max_anchors; P.max_matches = c->opts.max_matches; P.kidx_bits_max = c->kidx_bits; P.kidx_len_max = c->kidx_len;
+		P.max_anchors = c->opts.max_anchors; P.max_matches = c->opts.max_matches;
 		P.rr = (dsb_read_result *)c->rr.p; P.hits = (dsb_hit *)c->hits.p; P.hits_cap = c->hits_cap; P.hits_cursor = cnt + DSB_CNT_HITS_CURSOR;
 		P.counters = cnt;
 		A.L = L;
@@ -609,7 +621,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		k_seed <<<blocks, threads, smem, st>>>(A, PASS_SLOW1, LIST_SLOW1, 4);   DSB_CUDA(cudaEventRecord(c->ev[7], st));
 		k_chain<<<blocks, threads, smem, st>>>(A, PASS_SLOW1, LIST_SLOW1, 5);   DSB_CUDA(cudaEventRecord(c->ev[8], st));
 		// scoring: a warp per read; the few reads that give up there (ERR_DEFER) then get a CTA each
-		k_score<<<blocks, threads, smem, st>>>(A, LIST_SCORE, 6);
+		k_score<<<blocks, threads, smem + CLASSIFY_WARPS_PER_BLOCK * sizeof(MatchSmem), st>>>(A, LIST_SCORE, 6);
 		k_score_heavy<<<HEAVY_BLOCKS, TEAM_WARPS * 32, 0, st>>>(A, LIST_SCORE_HEAVY, 7, (uint32_t)c->n_warps);
 		DSB_CUDA(cudaEventRecord(c->ev[9], st));
 		c->launches += 9;

@@ -33,7 +33,6 @@ struct DevChain {               // chain_item (cly.h:69-89)
 };
 struct DevSms { uint32_t t_pos, q_pos, len, score; };   // spd_match (cly.h:127-133)
 struct MemRst { int match_len; int sa_sp_l; uint64_t sp, sa_sp; int read_offset; int pad; };   // MEM_rst (cly.c:619-627)
-struct KEntry { uint32_t kmer, prev; };   // the read's 9-mer index: entry p = 9-mer at position p + the previous (smaller) position of the same bucket
 struct ScHash { uint16_t next; uint16_t seed_ID; uint16_t s_or_e; uint16_t pad; };   // seed_con_hash (cly.h:120-125)
 
 struct WarpSmem {               // per-warp shared memory
@@ -41,6 +40,14 @@ struct WarpSmem {               // per-warp shared memory
 	uint32_t next_seed;         // seed_pass: work counter of the lanes
 	uint32_t chunk_cursor;      // seed_pass: next free chunk of the anchor staging pool
 	uint32_t pad[2];
+};
+// per-warp shared memory of the scoring kernels: hash table of the 9-mers of the scanned TARGET positions of one sdp_match
+#define TT_SLOTS 1024           // >= 2 x the scanned positions of a window (t_len < 2000 -> at most 497)
+#define TT_EMPTY 0xffffffffu
+struct MatchSmem {
+	uint32_t tslot[TT_SLOTS];   // open addressing: (9-mer << 9) | scanned position index, or TT_EMPTY
+	uint32_t bloom[512];        // one hash bit per scanned 9-mer (16 bits per table slot): the streaming loop tests this first
+	uint32_t n_cand, n_tmp, pad[2];
 };
 #define FR_A 8
 #define FR_B 21
@@ -53,8 +60,10 @@ struct WarpScratch {            // per-warp HBM scratch
 	DevSms    *sms;
 	int       *score_v;         // 1024
 	ScHash    *sc_hash;         // 256 + 2*400 + 8
-	uint32_t  *kidx_start[2];   // CSR bucket ends of the read's 9-mer index, per strand slot (0 forward, 1 reverse)
-	KEntry    *kidx_ent[2];
+	DevSms    *sms_tmp;         // sdp_match: matches of the current window before they are ordered (max_matches)
+	uint2     *cand;            // sdp_match: (scanned target index, read position) pairs with equal 9-mers (CAND_CAP)
+	uint64_t  *sort_key[2];     // sdp_match: order keys of sms_tmp + merge-sort ping-pong (max_matches each)
+	uint32_t  *sort_idx[2];     // merge-sort permutation ping-pong (max_matches each)
 	uint64_t  *sp_set;          // 32 lanes x SP_TAB slots of the visited-row hash sets, interleaved (zeroed when the scratch is allocated)
 	uint32_t  *sp_gen;          // 32 generation counters of those sets
 	MemRst    *lane_mem;        // 32 lanes x 512
@@ -91,7 +100,7 @@ struct ClassifyParams {
 	const uint32_t *total_score[2];
 	const uint32_t *order;      // read ids, longest first (work order of the first seeding pass)
 	uint32_t n_long;            // the first n_long entries of `order` are longer than SHORT_READ_MAX
-	uint32_t *prof;             // per read: 8 x u32 phase times in units of 1024 cycles (fast, chain, slow, kidx, middle, right, left, total)
+	uint32_t *prof;             // per read: 8 x u32 phase times in units of 1024 cycles (fast, chain, slow, sdp_match [part of the next three], middle, right, left, total)
 	// state between the phase kernels
 	ReadWork *work;
 	DevAnchor *anc_pool; uint32_t anc_pool_cap;
@@ -100,7 +109,7 @@ struct ClassifyParams {
 	uint32_t *ctl;
 	// per-warp scratch
 	uint8_t  *scratch; uint64_t scratch_stride;
-	uint32_t max_anchors, max_matches, kidx_bits_max, kidx_len_max;
+	uint32_t max_anchors, max_matches;
 	// outputs
 	dsb_read_result *rr;
 	dsb_hit *hits; uint64_t hits_cap; unsigned long long *hits_cursor;
@@ -117,6 +126,8 @@ struct DpTeam;
 struct ReadState {
 	const DevIndex *ix;
 	WarpSmem *sm;
+	MatchSmem *mt;               // scoring kernels only
+	uint32_t l_read;             // scoring: length of the read (positions that have a 9-mer: 0 .. l_read - 9)
 	DpTeam *team;                // helper warps of the CTA for the sparse DP of heavy reads (k_score_heavy), else nullptr
 	WarpScratch ws;
 	uint32_t n_anc, n_hit, n_sms;
@@ -219,17 +230,17 @@ __device__ __forceinline__ void warp_stable_sort_by_key(T *a, T *tmp, uint32_t n
 	__syncwarp();
 }
 
-// The same stable sort for large n (thousands of anchors of a repeat-rich read; counting ranks is O(n^2)): chunks of
-// SORT_CHUNK keys are rank-sorted, then merged pairwise -- every element finds its place in the other run by binary search
-// (left run wins ties, which keeps the sort stable).  key0/key1 and idx0/idx1 are ping-pong buffers of n entries each.
-#define SORT_CHUNK 1024
-template <typename T>
-__device__ __noinline__ void warp_stable_sort_large(T *a, T *tmp, uint32_t n, uint64_t *key0, uint64_t *key1, uint32_t *idx0, uint32_t *idx1)
+// Sorted permutation of n 64-bit keys by a warp, for large n (counting ranks is O(n^2)): chunks of CHUNK keys are rank-sorted, then merged pairwise (every
+// element finds its place in the other run by binary search; the left run wins ties, so the order is stable).  key0 holds the
+// keys; key0/key1 and idx0/idx1 are ping-pong buffers of n entries.  Returns the index array: result[i] = index of the i-th
+// smallest key.
+template <uint32_t CHUNK>
+__device__ __noinline__ const uint32_t *warp_sort_perm(uint32_t n, uint64_t *key0, uint64_t *key1, uint32_t *idx0, uint32_t *idx1)
 {
 	const int lane = lane_id();
 	__syncwarp();
-	for (uint32_t c0 = 0; c0 < n; c0 += SORT_CHUNK) {                    // chunk sort: (key0, identity) -> (key1, idx1)
-		const uint32_t cn = DSB_MIN((uint32_t)SORT_CHUNK, n - c0);
+	for (uint32_t c0 = 0; c0 < n; c0 += CHUNK) {                         // chunk sort: (key0, identity) -> (key1, idx1)
+		const uint32_t cn = DSB_MIN((uint32_t)CHUNK, n - c0);
 		for (uint32_t i0 = 0; i0 < cn; i0 += 32) {
 			const uint32_t i = i0 + lane;
 			const uint64_t ki = (i < cn) ? key0[c0 + i] : 0;
@@ -240,7 +251,7 @@ __device__ __noinline__ void warp_stable_sort_large(T *a, T *tmp, uint32_t n, ui
 	}
 	__syncwarp();
 	uint64_t *ks = key1, *kd = key0; uint32_t *is = idx1, *id = idx0;
-	for (uint32_t w = SORT_CHUNK; w < n; w <<= 1) {                      // merge runs of width w
+	for (uint32_t w = CHUNK; w < n; w <<= 1) {                           // merge runs of width w
 		for (uint32_t p = lane; p < n; p += 32) {
 			const uint32_t pair = p / (2 * w) * (2 * w), l0 = pair, l1 = DSB_MIN(pair + w, n), r1 = DSB_MIN(pair + 2 * w, n);
 			const uint64_t k = ks[p];
@@ -260,9 +271,17 @@ __device__ __noinline__ void warp_stable_sort_large(T *a, T *tmp, uint32_t n, ui
 		uint64_t *tk = ks; ks = kd; kd = tk;
 		uint32_t *ti = is; is = id; id = ti;
 	}
-	for (uint32_t i = lane; i < n; i += 32) tmp[i] = a[is[i]];
+	return is;
+}
+
+#define SORT_CHUNK 1024
+template <typename T>
+__device__ __noinline__ void warp_stable_sort_large(T *a, T *tmp, uint32_t n, uint64_t *key0, uint64_t *key1, uint32_t *idx0, uint32_t *idx1)
+{
+	const uint32_t *is = warp_sort_perm<SORT_CHUNK>(n, key0, key1, idx0, idx1);
+	for (uint32_t i = lane_id(); i < n; i += 32) tmp[i] = a[is[i]];
 	__syncwarp();
-	for (uint32_t i = lane; i < n; i += 32) a[i] = tmp[i];
+	for (uint32_t i = lane_id(); i < n; i += 32) a[i] = tmp[i];
 	__syncwarp();
 }
 
@@ -381,80 +400,6 @@ __device__ __noinline__ void resolve_tree(ReadState &S)     // cly.c:326-349
 	S.n_hit = rst_num;
 }
 
-// ---------------------------------------------------------------- the read's 9-mer index (replaces build_hash_table_M2, cly.c:2173-2224)
-// The reference chains nodes per hash bucket in insertion (= ascending position) order and compares the full 9-mer
-// on lookup.  Equivalent here: a CSR table keyed by the low key_bits of the 9-mer, entries (kmer,pos) in ascending
-// position inside each bucket.  Built by the warp: histogram (RED atomics) -> scan -> ordered fill (__match_any_sync).
-// 128 read positions per step: every lane loads one aligned 4-byte word of the strand (4 bases), packs it to 8 bits, and the
-// 9-mers are cut out of three neighbouring packed words fetched by shuffle -- no per-position byte loads.
-struct KmerTile {
-	uint32_t p0, p1;     // packed words lane and lane + 32 of the tile (first base in the high bits of the byte)
-	int a;               // byte offset of the tile's position 0 inside its first word
-};
-__device__ __forceinline__ uint32_t pack4(uint32_t w) { return ((w & 3) << 6) | (((w >> 8) & 3) << 4) | (((w >> 16) & 3) << 2) | ((w >> 24) & 3); }
-__device__ __forceinline__ KmerTile load_kmer_tile(const uint8_t *q, uint32_t base)
-{   // q + base need not be aligned; guard bytes around the strands make the two extra words readable
-	KmerTile T;
-	const uintptr_t addr = (uintptr_t)(q + base);
-	T.a = (int)(addr & 3);
-	const uint32_t *w = (const uint32_t *)(addr - T.a);
-	const int lane = lane_id();
-	T.p0 = pack4(w[lane]);
-	T.p1 = (lane < 3) ? pack4(w[32 + lane]) : 0;
-	return T;
-}
-// 9-mer at tile position p (0..127); warp-collective (shuffles), every lane may ask for a different p
-__device__ __forceinline__ uint32_t tile_kmer(const KmerTile &T, uint32_t p)
-{
-	const uint32_t bi = p + T.a, wi = bi >> 2, o = bi & 3;
-	uint32_t P = 0;
-	#pragma unroll
-	for (int k = 0; k < 3; k++) {
-		const uint32_t idx = wi + k;
-		const uint32_t lo = __shfl_sync(DSB_FULL, T.p0, idx & 31), hi = __shfl_sync(DSB_FULL, T.p1, idx & 31);
-		P = (P << 8) | ((idx < 32) ? lo : hi);
-	}
-	return (P >> (6 - 2 * o)) & 0x3ffffu;
-}
-
-#define KIDX_NIL 0xffffffffu
-// The read's 9-mer index (replaces build_hash_table_M2, cly.c:2173-2224).  The reference chains the positions of a bucket
-// in ascending order and compares the full 9-mer on lookup.  Here: ent[p] = {9-mer at p, previous position of the same
-// bucket} written SEQUENTIALLY (coalesced; scattered 8-byte entry stores cost 100 B/base of DRAM traffic, profiles/r1f),
-// head[bucket] = last position.  A lookup walks a bucket from its last position downwards (and can stop below the query
-// range); sdp_scan_pos turns the order around again.
-__device__ __noinline__ void build_kidx(ReadState &S, const uint8_t *q, uint32_t q_len, int slot, int key_bits)
-{
-	uint32_t *head = S.ws.kidx_start[slot];
-	KEntry *ent = S.ws.kidx_ent[slot];
-	const uint32_t nb = 1u << key_bits, kmask = nb - 1;
-	const int lane = lane_id();
-	const uint32_t nk = q_len - S_A_KEMR_L + 1;
-	for (uint32_t b = lane * 4; b < nb; b += 128) *(uint4 *)(head + b) = make_uint4(KIDX_NIL, KIDX_NIL, KIDX_NIL, KIDX_NIL);
-	__syncwarp();
-	for (uint32_t base = 0; base < nk; base += 128) {
-		const KmerTile T = load_kmer_tile(q, base);
-		#pragma unroll 1
-		for (int j = 0; j < 4; j++) {
-			const uint32_t pos0 = base + 32 * j, pos = pos0 + lane;
-			const bool act = pos < nk;
-			const uint32_t kmer = tile_kmer(T, 32 * j + lane);
-			const uint32_t key = act ? (kmer & kmask) : (0x80000000u | lane);
-			const uint32_t peers = __match_any_sync(DSB_FULL, key);
-			const uint32_t below = peers & ((1u << lane) - 1);
-			uint32_t prev;
-			if (below) prev = pos0 + (31 - __clz(below));                 // an earlier position of this round in the same bucket
-			else prev = act ? head[key] : KIDX_NIL;
-			if (act) { KEntry e; e.kmer = kmer; e.prev = prev; ent[pos] = e; }
-			if (act && (peers >> lane) == 1u) head[key] = pos;           // the last position of the bucket in this round
-			__syncwarp();
-		}
-	}
-	__syncwarp();
-}
-
-struct KIdx { const uint32_t *start; const KEntry *ent; uint32_t kmask; };   // start = head[]
-
 // ---------------------------------------------------------------- 9-mer sparse DP scoring (cly.c:1691-1818, 2335-2849)
 __device__ __forceinline__ void sc_hash_idx(ReadState &S)      // cly.c:1691-1710
 {
@@ -530,91 +475,191 @@ __device__ __forceinline__ bool sms_push(ReadState &S, uint32_t t_pos, uint32_t 
 	return true;
 }
 
-// sdp_match (cly.c:2335-2440): 9-mer matches between a reference window and the read, one LANE per scanned target position
-// (every 4th).  The reference pushes matches in (target scan order, ascending read position) order; lanes keep that order by
-// an ordered compaction of each round of 32 positions.  kmer(i) is rebuilt from the window instead of rolled.
-struct SdpArgs { uint32_t q_bg, q_ed; const uint8_t *q_str, *t_str; uint32_t t_len, t_st; KIdx kx; };
+// ---------------------------------------------------------------- sdp_match (cly.c:2335-2440) without a per-read index
+// The reference hashes all 9-mers of the READ once (build_hash_table_M2, cly.c:2173-2224) and looks up every 4th 9-mer of a
+// reference window; only read positions inside [q_bg, q_ed] (<= 2000 wide) count.  A per-read index is ~100 KB of scattered
+// per-warp scratch (it was 100 B/base of DRAM traffic and the top stall of k_score, profiles/r1f).  Here the roles are
+// swapped: the <= 497 scanned TARGET 9-mers of the window go into a small hash table in shared memory, and the warp streams
+// the read range [q_bg, q_ed] through it -- 16 consecutive positions per lane from one coalesced 16-byte load, the 9-mers cut
+// out of a 48-bit register.  Equal 9-mers give (target index, read position) candidates; each candidate then runs the
+// reference's own test + extension on a lane of its own (sdp_extend), and the surviving matches are put into the
+// reference's push order: target scan order, ascending read position (the order the hash chains are walked in).
+struct SdpArgs { uint32_t q_bg, q_ed; const uint8_t *q_str, *t_str; uint32_t t_len, t_st; bool fwd; };
+#define CAND_CAP (32 * 512 + 4096)
+// The per-warp shared structures are reached through pointers kept in ReadState, which the compiler can only treat as
+// generic addresses (LD.E / generic atomics); these wrappers keep the accesses in the shared window (LDS / STS / ATOMS).
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u32_ro(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }   // table is read-only while streaming
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t atoms_cas(uint32_t a, uint32_t cmp, uint32_t v) { uint32_t o; asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(o) : "r"(a), "r"(cmp), "r"(v) : "memory"); return o; }
+__device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
+__device__ __forceinline__ void reds_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 
-// all matches of target position i.  The bucket is walked from its highest read position downwards, the reference emits
-// ascending read positions: with total == 0 (first pass) the k-th match found goes to out[k] for k < cap; with the number of
-// matches known (second pass) it goes to out[total - 1 - k].  Returns the number of matches.
-template <bool FWD>
-__device__ __forceinline__ uint32_t sdp_scan_pos(const SdpArgs &A, int i, DevSms *out, uint32_t cap, uint32_t total)
+__device__ __forceinline__ uint32_t pack4(uint32_t w) { return ((w & 0x03030303u) * 0x40100401u) >> 24; }   // 4 base codes (first in the low byte) -> 8 bits, first base in the high bits
+__device__ __forceinline__ uint32_t tt_hash(uint32_t kmer, uint32_t tbits) { return (kmer * 0x9E3779B1u) >> (32 - tbits); }
+
+// the per-(scanned target position, read position) body of sdp_match (cly.c:2353-2384 / 2402-2433)
+__device__ __forceinline__ bool sdp_extend(const SdpArgs &A, uint32_t k, uint32_t cur, DevSms &m)
 {
-	const uint8_t *c_t_str = FWD ? (A.t_str + i) : (A.t_str + A.t_len - S_A_KEMR_L - i);
-	uint32_t kmer = 0;
-	#pragma unroll
-	for (int k = 0; k < S_A_KEMR_L; k++) kmer = (kmer << 2) | c_t_str[k];
-	uint32_t n = 0;
-	for (uint32_t q_pos = A.kx.start[kmer & A.kx.kmask]; q_pos != KIDX_NIL; ) {
-		if (q_pos < A.q_bg) break;                                     // positions only get smaller from here
-		const KEntry en = A.kx.ent[q_pos];
-		const uint32_t cur = q_pos;
-		q_pos = en.prev;
-		if (en.kmer != kmer || cur > A.q_ed) continue;
-		DevSms m; m.score = 0;
-		bool hit = false;
-		if (FWD) {
-			const int back_len = MEM_search_bwd(A.q_str + cur - 1, c_t_str - 1, 4);
-			if (back_len < 4 || i == 4) {
-				uint32_t max_search = A.q_ed - cur - 1;
-				max_search = DSB_MIN(max_search, A.t_len - i - 1) + OVER_SEARCH_M2;
-				const int forward_len = MEM_search_fwd(A.q_str + cur + S_A_KEMR_L, c_t_str + S_A_KEMR_L, max_search);
-				const int total_len = back_len + forward_len + 1;
-				if (total_len >= 4) { hit = true; m.t_pos = i - back_len + A.t_st; m.q_pos = cur - back_len; m.len = total_len; }
-			}
-		} else {
-			const int forward_len = MEM_search_fwd(A.q_str + cur + S_A_KEMR_L, c_t_str + S_A_KEMR_L, 4);
-			if (forward_len < 4 || i == 4) {
-				uint32_t max_search = cur;
-				max_search = DSB_MIN((long)max_search, (long)(c_t_str - A.t_str)) + OVER_SEARCH_M2;
-				const int back_len = MEM_search_bwd(A.q_str + cur - 1, c_t_str - 1, max_search);
-				const int total_len = back_len + forward_len + 1;
-				if (total_len >= 4) { hit = true; m.t_pos = (uint32_t)((long)(c_t_str - A.t_str) - back_len + A.t_st); m.q_pos = cur - back_len; m.len = total_len; }
-			}
+	const int i = 4 + 4 * (int)k;
+	const uint8_t *c_t_str = A.fwd ? (A.t_str + i) : (A.t_str + A.t_len - S_A_KEMR_L - i);
+	if (A.fwd) {
+		const int back_len = MEM_search_bwd(A.q_str + cur - 1, c_t_str - 1, 4);
+		if (back_len < 4 || i == 4) {
+			uint32_t max_search = A.q_ed - cur - 1;
+			max_search = DSB_MIN(max_search, A.t_len - i - 1) + OVER_SEARCH_M2;
+			const int forward_len = MEM_search_fwd(A.q_str + cur + S_A_KEMR_L, c_t_str + S_A_KEMR_L, max_search);
+			const int total_len = back_len + forward_len + 1;
+			if (total_len >= 4) { m.t_pos = i - back_len + A.t_st; m.q_pos = cur - back_len; m.len = total_len; return true; }
 		}
-		if (hit) {
-			if (total) { DevSms *o = out + (total - 1 - n); o->t_pos = m.t_pos; o->q_pos = m.q_pos; o->len = m.len; }
-			else if (n < cap) out[n] = m;
-			n++;
+	} else {
+		const int forward_len = MEM_search_fwd(A.q_str + cur + S_A_KEMR_L, c_t_str + S_A_KEMR_L, 4);
+		if (forward_len < 4 || i == 4) {
+			uint32_t max_search = cur;
+			max_search = DSB_MIN((long)max_search, (long)(c_t_str - A.t_str)) + OVER_SEARCH_M2;
+			const int back_len = MEM_search_bwd(A.q_str + cur - 1, c_t_str - 1, max_search);
+			const int total_len = back_len + forward_len + 1;
+			if (total_len >= 4) { m.t_pos = (uint32_t)((long)(c_t_str - A.t_str) - back_len + A.t_st); m.q_pos = cur - back_len; m.len = total_len; return true; }
 		}
 	}
-	return n;
+	return false;
 }
 
-template <bool FWD>
-__device__ __forceinline__ void sdp_match_warp(ReadState &S, const SdpArgs &A)
+// the collected candidates, 32 at a time: test + extension; a surviving match goes (unordered) into sms_tmp with its order
+// key (target index, read position of the 9-mer)
+__device__ __noinline__ void sdp_flush_cand(ReadState &S, const SdpArgs &A)
 {
+	MatchSmem *M = S.mt;
+	__syncwarp();
+	const uint32_t a_ntmp = smem_addr(&M->n_tmp), a_ncand = smem_addr(&M->n_cand);
+	const uint32_t nc = DSB_MIN(lds_u32(a_ncand), (uint32_t)CAND_CAP);
+	for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
+		const uint32_t c = c0 + lane_id();
+		if (c < nc) {
+			const uint2 cd = S.ws.cand[c];
+			DevSms m; m.score = 0;
+			if (sdp_extend(A, cd.x, cd.y, m)) {
+				const uint32_t slot = atoms_add(a_ntmp, 1u);
+				if (S.n_sms + slot < S.max_matches) { S.ws.sms_tmp[slot] = m; S.ws.sort_key[0][slot] = ((uint64_t)cd.x << 32) | cd.y; }
+			}
+		}
+	}
+	__syncwarp();
+	if (lane_id() == 0) sts_u32(a_ncand, 0);
+	__syncwarp();
+}
+
+// Sorted permutation of n 64-bit keys by a warp, for large n: see warp_sort_perm above.
+
+__device__ __noinline__ void sdp_match(ReadState &S, uint32_t q_bg, uint32_t q_ed, const uint8_t *q_str, const uint8_t *t_str, uint32_t t_len,
+                                       uint32_t t_st, bool isForward)
+{
+	SdpArgs A; A.q_bg = q_bg; A.q_ed = q_ed; A.q_str = q_str; A.t_str = t_str; A.t_len = t_len; A.t_st = t_st; A.fwd = isForward;
+	PH_BEGIN();
+	__syncwarp();
 	if (A.t_len < S_A_KEMR_L + 4) return;
 	const uint32_t t_kmer_num = A.t_len - S_A_KEMR_L + 1;
 	const uint32_t n_pos = (t_kmer_num > 4) ? (t_kmer_num - 4 + 3) / 4 : 0;       // i = 4, 8, ... < t_kmer_num
+	if (n_pos == 0 || S.l_read < S_A_KEMR_L) return;
+	if (n_pos > 511) { S.error = 3; return; }                                      // (windows are < 2000 bases everywhere)
+	const uint32_t lo = A.q_bg, hi = DSB_MIN(A.q_ed, S.l_read - S_A_KEMR_L);       // read positions that have a 9-mer and lie in [q_bg, q_ed]
+	if (lo > hi) return;
+	MatchSmem *M = S.mt;
 	const int lane = lane_id();
-	for (uint32_t base = 0; base < n_pos; base += 32) {
-		const uint32_t k = base + lane;
+#ifdef DSB_PROF_SDP
+	long long pt_ = clock64();
+	#define SDP_PT(k) do { const long long n_ = clock64(); S.t_phase[k] += n_ - pt_; pt_ = n_; } while (0)
+#else
+	#define SDP_PT(k) do { } while (0)
+#endif
+	// (1) the scanned target 9-mers -> shared hash table (open addressing, equal 9-mers take slots of their own) + filter bits
+	uint32_t tbits = 6;
+	while ((1u << tbits) < 2 * n_pos) tbits++;
+	const uint32_t tmask = (1u << tbits) - 1;
+	const uint32_t fbits = tbits + 4;                                              // filter bits = 16 x table slots (<= 16384)
+	const uint32_t a_tslot = smem_addr(M->tslot), a_bloom = smem_addr(M->bloom), a_ncand = smem_addr(&M->n_cand);
+	for (uint32_t s = lane; s <= tmask; s += 32) sts_u32(a_tslot + 4 * s, TT_EMPTY);
+	for (uint32_t s = lane; s < (1u << (fbits - 5)); s += 32) sts_u32(a_bloom + 4 * s, 0);
+	if (lane == 0) { sts_u32(a_ncand, 0); sts_u32(smem_addr(&M->n_tmp), 0); }
+	__syncwarp();
+	for (uint32_t k = lane; k < n_pos; k += 32) {
 		const int i = 4 + 4 * (int)k;
-		DevSms loc[2];
-		const uint32_t cnt = (k < n_pos) ? sdp_scan_pos<FWD>(A, i, loc, 2, 0) : 0;
-		uint32_t x = cnt;
+		const uint8_t *c_t_str = A.fwd ? (A.t_str + i) : (A.t_str + A.t_len - S_A_KEMR_L - i);
+		uint32_t kmer = 0;
 		#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(DSB_FULL, x, d); if (lane >= d) x += y; }
-		const uint32_t total = __shfl_sync(DSB_FULL, x, 31);
-		if (total == 0) continue;
-		if (S.n_sms + total > S.max_matches) { S.error = 2; return; }
-		DevSms *dst = S.ws.sms + S.n_sms + (x - cnt);
-		if (cnt <= 2) { for (uint32_t m = 0; m < cnt; m++) { const DevSms &l = loc[cnt - 1 - m]; dst[m].t_pos = l.t_pos; dst[m].q_pos = l.q_pos; dst[m].len = l.len; } }   // found in descending order
-		else sdp_scan_pos<FWD>(A, i, dst, cnt, cnt);
-		S.n_sms += total;
-		__syncwarp();
+		for (int b = 0; b < S_A_KEMR_L; b++) kmer = (kmer << 2) | c_t_str[b];
+		const uint32_t f = tt_hash(kmer, fbits);
+		reds_or(a_bloom + 4 * (f >> 5), 1u << (f & 31));
+		uint32_t h = tt_hash(kmer, tbits);
+		while (atoms_cas(a_tslot + 4 * h, TT_EMPTY, (kmer << 9) | k) != TT_EMPTY) h = (h + 1) & tmask;
 	}
-}
-
-__device__ __noinline__ void sdp_match(ReadState &S, uint32_t q_bg, uint32_t q_ed, const uint8_t *q_str, const uint8_t *t_str, uint32_t t_len,
-                                       const KIdx &kx, uint32_t t_st, bool isForward)
-{
-	SdpArgs A; A.q_bg = q_bg; A.q_ed = q_ed; A.q_str = q_str; A.t_str = t_str; A.t_len = t_len; A.t_st = t_st; A.kx = kx;
 	__syncwarp();
-	if (isForward) sdp_match_warp<true>(S, A); else sdp_match_warp<false>(S, A);
+	SDP_PT(0);
+	// (2) stream the read range, 512 positions per round (the loads of the next round are in flight while this one is looked
+	// up): filter bits of 16 consecutive 9-mers per lane, then the table for the few that pass.  A candidate is a (scanned
+	// target index, read position) pair with equal 9-mers.
+	const uintptr_t a_lo = (uintptr_t)(A.q_str + lo) & ~(uintptr_t)15;
+	const int64_t p_first = (int64_t)(a_lo - (uintptr_t)A.q_str);                  // read position of byte 0 of the first 16-byte chunk (<= lo)
+	uint4 a = make_uint4(0, 0, 0, 0); uint2 b = make_uint2(0, 0);
+	{ const int64_t p0 = p_first + 16 * lane; if (p0 <= (int64_t)hi) { a = __ldg((const uint4 *)(A.q_str + p0)); b = __ldg((const uint2 *)(A.q_str + p0 + 16)); } }
+	for (int64_t pb = p_first; pb <= (int64_t)hi; pb += 512) {
+		const int64_t p0 = pb + 16 * lane;
+		const uint4 ca = a; const uint2 cb = b;
+		{ const int64_t pn = p0 + 512; if (pn <= (int64_t)hi) { a = __ldg((const uint4 *)(A.q_str + pn)); b = __ldg((const uint2 *)(A.q_str + pn + 16)); } }
+		uint32_t maybe = 0;                                                        // bit j: the 9-mer at p0 + j passes the filter
+		uint64_t bits = 0;
+		if (p0 <= (int64_t)hi && p0 + 15 >= (int64_t)lo) {
+			bits = ((uint64_t)pack4(ca.x) << 40) | ((uint64_t)pack4(ca.y) << 32) | ((uint64_t)pack4(ca.z) << 24) |
+			       ((uint64_t)pack4(ca.w) << 16) | ((uint64_t)pack4(cb.x) << 8) | (uint64_t)pack4(cb.y);   // base t of the chunk at bits 47-2t, 46-2t
+			#pragma unroll 4
+			for (int j = 0; j < 16; j++) {
+				const uint32_t kmer = (uint32_t)(bits >> (30 - 2 * j)) & 0x3ffffu;
+				const uint32_t f = tt_hash(kmer, fbits);
+				maybe |= ((lds_u32_ro(a_bloom + 4 * (f >> 5)) >> (f & 31)) & 1u) << j;
+			}
+			const int j_min = (int)DSB_MAX((int64_t)lo - p0, (int64_t)0), j_max = (int)DSB_MIN((int64_t)hi - p0, (int64_t)15);
+			maybe &= (0xffffu >> (15 - j_max)) & (0xffffu << j_min);
+		}
+		while (__any_sync(DSB_FULL, maybe != 0)) {                                  // one position per lane and turn
+			if (lds_u32(a_ncand) + 32 * n_pos > CAND_CAP) sdp_flush_cand(S, A);     // room for every scanned position on every lane
+			if (maybe) {
+				const int j = __ffs(maybe) - 1;
+				maybe &= maybe - 1;
+				const uint32_t p = (uint32_t)(p0 + j);
+				const uint32_t kmer = (uint32_t)(bits >> (30 - 2 * j)) & 0x3ffffu;
+				uint32_t h = tt_hash(kmer, tbits), slot;
+				for (; (slot = lds_u32_ro(a_tslot + 4 * h)) != TT_EMPTY; h = (h + 1) & tmask)     // every scanned target position with this 9-mer
+					if ((slot >> 9) == kmer) S.ws.cand[atoms_add(a_ncand, 1u)] = make_uint2(slot & 0x1ff, p);
+			}
+		}
+	}
+	SDP_PT(1);
+	sdp_flush_cand(S, A);
+	SDP_PT(2);
+	// (3) order: target scan order, then ascending read position (unique keys), appended to the match array
+	const uint32_t total = lds_u32(smem_addr(&M->n_tmp));
+	if (total) {
+		if (S.n_sms + total > S.max_matches) { S.error = 2; return; }
+		DevSms *dst = S.ws.sms + S.n_sms;
+		const DevSms *src = S.ws.sms_tmp;
+		const uint64_t *key = S.ws.sort_key[0];
+		if (total <= 256) {
+			for (uint32_t i0 = 0; i0 < total; i0 += 32) {
+				const uint32_t i = i0 + lane;
+				const uint64_t ki = (i < total) ? key[i] : 0;
+				uint32_t r = 0;
+				for (uint32_t j = 0; j < total; j++) r += (key[j] < ki) ? 1u : 0u;
+				if (i < total) { const DevSms m = src[i]; dst[r].t_pos = m.t_pos; dst[r].q_pos = m.q_pos; dst[r].len = m.len; }
+			}
+		} else {
+			const uint32_t *perm = warp_sort_perm<128>(total, S.ws.sort_key[0], S.ws.sort_key[1], S.ws.sort_idx[0], S.ws.sort_idx[1]);
+			for (uint32_t i = lane; i < total; i += 32) { const DevSms m = src[perm[i]]; dst[i].t_pos = m.t_pos; dst[i].q_pos = m.q_pos; dst[i].len = m.len; }
+		}
+		S.n_sms += total;
+	}
 	__syncwarp();
+	PH_END(S, 3);
 }
 
 __device__ __forceinline__ void refwin_zero(ReadState &S, int nbytes)     // zero-initialised stack window (policy P1)
@@ -648,8 +693,9 @@ __device__ __forceinline__ DevSms load_sms(const DevSms *p)
 // block are resolved by a short sequential pass.  pass / break / candidate score are the reference's own expressions.
 enum { DP_MIDDLE = 0, DP_RIGHT = 1, DP_LEFT = 2 };
 
-template <int KIND>
-__device__ __forceinline__ void dp_eval(const DevSms &c, const DevSms &p, bool &pass, bool &brk, bool &has, int &cand)
+// (KIND is a run-time value: one copy of the DP code keeps the scoring kernel inside the instruction cache -- with three
+// template instances of every routine `no instruction` was the top stall, profiles/r1j)
+__device__ __forceinline__ void dp_eval(const int KIND, const DevSms &c, const DevSms &p, bool &pass, bool &brk, bool &has, int &cand)
 {
 	has = false; brk = false; cand = 0;
 	if (KIND == DP_LEFT) {
@@ -699,37 +745,41 @@ struct DpTeam {
 	const DevSms *sms;
 	DevSms item[32]; int stopped0[32];
 	int best[TEAM_WARPS][32]; int brk[TEAM_WARPS][32];
+	uint4 tile[TEAM_WARPS][64];       // predecessor tiles of dp_range, two per warp
 };
 
 // phase (A) over the predecessors [lo, hi), walked downwards: best candidate per lane and whether the lane's walk hit its break.
-// The predecessors are fetched 32 at a time (one coalesced 512-byte request, the next tile already in flight) and handed
-// to all lanes by shuffle, highest index first.
-template <int KIND>
-__device__ __noinline__ void dp_range(const DevSms *sms, int lo, int hi, const DevSms &my, bool stopped, int &best, bool &brk_out)
+// The predecessors are fetched 32 at a time (one coalesced 512-byte request, the next tile already in flight), parked in a
+// shared-memory tile (two tiles, used alternately) and read back by all lanes as broadcasts, highest index first.
+__device__ __noinline__ void dp_range(const int KIND, const DevSms *sms, int lo, int hi, const DevSms &my, bool stopped, int &best, bool &brk_out, uint32_t a_tile)
 {
 	const int lane = lane_id();
 	int top = hi - 1;                                    // tile = entries top, top-1, ..., top-31 (lane l holds entry top - l)
-	DevSms cur; cur.t_pos = cur.q_pos = cur.len = cur.score = 0;
-	if (top - lane >= lo) cur = load_sms(sms + top - lane);
+	uint4 cur = make_uint4(0, 0, 0, 0);
+	if (top - lane >= lo) cur = *(const uint4 *)(sms + top - lane);
+	uint32_t buf = 0;
 	while (top >= lo) {
 		if (__all_sync(DSB_FULL, stopped)) break;
-		DevSms nxt; nxt.t_pos = nxt.q_pos = nxt.len = nxt.score = 0;
-		if (top - 32 - lane >= lo) nxt = load_sms(sms + top - 32 - lane);
+		const uint32_t a_buf = a_tile + buf * 512;
+		asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a_buf + 16 * lane), "r"(cur.x), "r"(cur.y), "r"(cur.z), "r"(cur.w) : "memory");
+		uint4 nxt = make_uint4(0, 0, 0, 0);
+		if (top - 32 - lane >= lo) nxt = *(const uint4 *)(sms + top - 32 - lane);
+		__syncwarp();
 		const int n_here = min(32, top - lo + 1);
-		#pragma unroll 4
-		for (int k = 0; k < n_here; k++) {
-			DevSms p;
-			p.t_pos = __shfl_sync(DSB_FULL, cur.t_pos, k); p.q_pos = __shfl_sync(DSB_FULL, cur.q_pos, k);
-			p.len = __shfl_sync(DSB_FULL, cur.len, k); p.score = __shfl_sync(DSB_FULL, cur.score, k);
-			if (!stopped) {
+		if (!stopped) {
+			#pragma unroll 2
+			for (int k = 0; k < n_here; k++) {
+				DevSms p;
+				asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(p.t_pos), "=r"(p.q_pos), "=r"(p.len), "=r"(p.score) : "r"(a_buf + 16 * k) : "memory");
 				bool pass, brk, has; int cand;
-				dp_eval<KIND>(my, p, pass, brk, has, cand);
-				if (brk) { stopped = true; brk_out = true; }
-				else if (has) best = DSB_MAX(best, cand);
+				dp_eval(KIND, my, p, pass, brk, has, cand);
+				if (brk) { stopped = true; brk_out = true; break; }
+				if (has) best = DSB_MAX(best, cand);
 			}
 		}
-		cur = nxt; top -= 32;
+		cur = nxt; top -= 32; buf ^= 1;
 	}
+	__syncwarp();
 }
 
 __device__ __forceinline__ void dp_team_range(DpTeam *T, int w)
@@ -740,11 +790,7 @@ __device__ __forceinline__ void dp_team_range(DpTeam *T, int w)
 	const DevSms my = T->item[lane];
 	int best = INT_MIN; bool brk = false;
 	const bool stopped = T->stopped0[lane] != 0;
-	if (hi > 0) {
-		if (T->kind == DP_RIGHT) dp_range<DP_RIGHT>(T->sms, lo, hi, my, stopped, best, brk);
-		else if (T->kind == DP_LEFT) dp_range<DP_LEFT>(T->sms, lo, hi, my, stopped, best, brk);
-		else dp_range<DP_MIDDLE>(T->sms, lo, hi, my, stopped, best, brk);
-	}
+	if (hi > 0) dp_range(T->kind, T->sms, lo, hi, my, stopped, best, brk, smem_addr(T->tile[w]));
 	T->best[w][lane] = best; T->brk[w][lane] = brk ? 1 : 0;
 }
 
@@ -759,8 +805,7 @@ __device__ __forceinline__ void dp_team_helper_loop(DpTeam *T, int w)
 }
 
 // scores of the matches [first, first + nb), nb <= 32; lane j holds match first+j in `my` and receives its score.
-template <int KIND>
-__device__ __forceinline__ int dp_block(const DevSms *sms, uint32_t first, uint32_t nb, DevSms my, DpTeam *team)
+__device__ __noinline__ int dp_block(const int KIND, const DevSms *sms, uint32_t first, uint32_t nb, DevSms my, DpTeam *team, uint32_t a_tile)
 {
 	const int lane = lane_id();
 	const bool mine = (uint32_t)lane < nb;
@@ -770,7 +815,7 @@ __device__ __forceinline__ int dp_block(const DevSms *sms, uint32_t first, uint3
 		for (int k = (int)nb - 2; k >= 0; k--) {
 			DevSms p;
 			p.t_pos = __shfl_sync(DSB_FULL, my.t_pos, k); p.q_pos = __shfl_sync(DSB_FULL, my.q_pos, k); p.len = __shfl_sync(DSB_FULL, my.len, k); p.score = 0;
-			if (mine && k < lane && stop_at < 0) { bool pass, brk, has; int cand; dp_eval<KIND>(my, p, pass, brk, has, cand); if (brk) stop_at = k; }
+			if (mine && k < lane && stop_at < 0) { bool pass, brk, has; int cand; dp_eval(KIND, my, p, pass, brk, has, cand); if (brk) stop_at = k; }
 		}
 	}
 	// (A) predecessors in earlier blocks: all lanes walk first-1 .. 0 together, each with its own stop
@@ -787,7 +832,7 @@ __device__ __forceinline__ int dp_block(const DevSms *sms, uint32_t first, uint3
 		__syncwarp();
 	} else {
 		bool brk = false;
-		dp_range<KIND>(sms, 0, (int)first, my, stopped, best, brk);
+		dp_range(KIND, sms, 0, (int)first, my, stopped, best, brk, a_tile);
 	}
 	// (B) predecessors inside the block, in order: match j needs the final scores of the matches before it
 	int my_score = best;
@@ -799,7 +844,7 @@ __device__ __forceinline__ int dp_block(const DevSms *sms, uint32_t first, uint3
 		if ((uint32_t)lane < j && lane > c_stop) {
 			DevSms p = my; p.score = (uint32_t)my_score;
 			bool pass, brk, has; int cand;
-			dp_eval<KIND>(c, p, pass, brk, has, cand);
+			dp_eval(KIND, c, p, pass, brk, has, cand);
 			if (has) cand_max = cand;
 		}
 		cand_max = warp_max(cand_max);
@@ -807,7 +852,7 @@ __device__ __forceinline__ int dp_block(const DevSms *sms, uint32_t first, uint3
 	}
 	return my_score;
 }
-__device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8_t *q_str, const KIdx &kx)
+__device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8_t *q_str)
 {   // cly.c:2444-2530
 	const DevIndex &ix = *S.ix;
 	int score = 10000;
@@ -831,7 +876,7 @@ __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8
 				refwin_zero(S, 2128);
 				const uint64_t ref_offset = pre_refoffset + t_offset + pre_mch;
 				CNT_GETREF(S, total_ref_len); get_ref_coop(ix, S.sm->refwin, ref_offset, total_ref_len, true);
-				sdp_match(S, pa.index_in_read + pre_mch - 8, ca.index_in_read - 1, q_str, S.sm->refwin, total_ref_len, kx, pre_refoffset + pre_mch, true);
+				sdp_match(S, pa.index_in_read + pre_mch - 8, ca.index_in_read - 1, q_str, S.sm->refwin, total_ref_len, pre_refoffset + pre_mch, true);
 				if (S.error) return 0;
 				if (!S.team && S.n_sms > DEFER_SMS) { S.error = ERR_DEFER; return 0; }
 			}
@@ -842,7 +887,7 @@ __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8
 					const uint32_t nb = DSB_MIN(32u, S.n_sms - first);
 					DevSms my; my.t_pos = my.q_pos = my.len = my.score = 0;
 					if ((uint32_t)lane_id() < nb) my = load_sms(base + first + lane_id());
-					const int sc = dp_block<DP_MIDDLE>(base, first, nb, my, S.team);
+					const int sc = dp_block(DP_MIDDLE, base, first, nb, my, S.team, smem_addr(S.mt->tslot));
 					if ((uint32_t)lane_id() < nb) base[first + lane_id()].score = sc;
 					__syncwarp();
 					score = DSB_MAX(warp_max(((uint32_t)lane_id() < nb) ? sc : INT_MIN), score);
@@ -855,7 +900,7 @@ __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8
 	return score - 10000;
 }
 
-__device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, const KIdx &kx, int chain_ID, uint32_t l_read, int score_ori)
+__device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, int chain_ID, uint32_t l_read, int score_ori)
 {   // cly.c:2532-2677
 	const DevIndex &ix = *S.ix;
 	DevChain *c_st = S.ws.chain;
@@ -891,7 +936,7 @@ __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, con
 			int search_q_ed = (int)sms[max_sms_id].q_pos + 1000;
 			search_q_ed = DSB_MIN(search_q_ed, l_read);
 			const int search_q_st = DSB_MAX(search_q_ed - 2000, ch.q_st - 8);
-			sdp_match(S, search_q_st, search_q_ed, q_str, S.sm->refwin, max_search_ref, kx, c_t_offset, true);
+			sdp_match(S, search_q_st, search_q_ed, q_str, S.sm->refwin, max_search_ref, c_t_offset, true);
 			if (S.error) return 0;
 			if (!S.team && S.n_sms > DEFER_SMS) { S.error = ERR_DEFER; return 0; }
 			c_t_offset += max_search_ref - S_A_KEMR_L - 3;
@@ -902,7 +947,7 @@ __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, con
 		const uint32_t first = current_sms, nb = DSB_MIN(32u, S.n_sms - current_sms);
 		DevSms my; my.t_pos = my.q_pos = my.len = my.score = 0;
 		if ((uint32_t)lane_id() < nb) my = load_sms(sms + first + lane_id());
-		const int my_score = dp_block<DP_RIGHT>(sms, first, nb, my, S.team);
+		const int my_score = dp_block(DP_RIGHT, sms, first, nb, my, S.team, smem_addr(S.mt->tslot));
 		if ((uint32_t)lane_id() < nb) sms[first + lane_id()].score = my_score;
 		__syncwarp();
 		// combine_chain returns 0 at once when the bucket of the match's diagonal is empty (cly.c:1771)
@@ -915,7 +960,7 @@ __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, con
 			const int max_score = __shfl_sync(DSB_FULL, my_score, j);
 			current_sms = first + j + 1;
 			if (((cm >> j) & 1) && combine_chain(S, chain_ID, c_sms.t_pos - c_sms.q_pos, 0, c_sms.q_pos, &combined) == 1) {
-				total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2(S, c_st[combined].cur, q_str, kx);
+				total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2(S, c_st[combined].cur, q_str);
 				if (S.error) return 0;
 				score_ori = total_max_score;
 				max_sms_id = 0;
@@ -942,7 +987,7 @@ __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, con
 	return total_max_score - 10000;
 }
 
-__device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, const KIdx &kx, int chain_ID, int score_ori)
+__device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, int chain_ID, int score_ori)
 {   // cly.c:2679-2819
 	const DevIndex &ix = *S.ix;
 	DevChain *c_st = S.ws.chain;
@@ -980,7 +1025,7 @@ __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, cons
 			int search_q_st = (int)sms[max_sms_id].q_pos - 1000;
 			search_q_st = DSB_MAX(search_q_st, 0);
 			const int search_q_ed = DSB_MIN(search_q_st + 2000, ch.q_st - 1);
-			sdp_match(S, search_q_st, search_q_ed, q_str, S.sm->refwin + OVER_SEARCH_M2, max_search_ref, kx, c_t_offset - max_search_ref, false);
+			sdp_match(S, search_q_st, search_q_ed, q_str, S.sm->refwin + OVER_SEARCH_M2, max_search_ref, c_t_offset - max_search_ref, false);
 			if (S.error) return 0;
 			if (!S.team && S.n_sms > DEFER_SMS) { S.error = ERR_DEFER; return 0; }
 			c_t_offset = c_t_offset - max_search_ref + S_A_KEMR_L + 3;
@@ -991,7 +1036,7 @@ __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, cons
 		const uint32_t first = current_sms, nb = DSB_MIN(32u, S.n_sms - current_sms);
 		DevSms my; my.t_pos = my.q_pos = my.len = my.score = 0;
 		if ((uint32_t)lane_id() < nb) my = load_sms(sms + first + lane_id());
-		const int my_score = dp_block<DP_LEFT>(sms, first, nb, my, S.team);
+		const int my_score = dp_block(DP_LEFT, sms, first, nb, my, S.team, smem_addr(S.mt->tslot));
 		if ((uint32_t)lane_id() < nb) sms[first + lane_id()].score = my_score;
 		__syncwarp();
 		const bool need = (uint32_t)lane_id() < nb && my.len >= 8 && S.ws.sc_hash[(my.t_pos - my.q_pos) & 0xff].next != 0;
@@ -1003,7 +1048,7 @@ __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, cons
 			const int max_score = __shfl_sync(DSB_FULL, my_score, j);
 			current_sms = first + j + 1;
 			if (((cm >> j) & 1) && combine_chain(S, chain_ID, c_sms.t_pos - c_sms.q_pos, 1, c_sms.q_pos + c_sms.len, &combined) == 1) {
-				total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2(S, c_st[combined].cur, q_str, kx);
+				total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2(S, c_st[combined].cur, q_str);
 				if (S.error) return 0;
 				score_ori = total_max_score;
 				max_sms_id = 0;
@@ -1043,7 +1088,7 @@ struct ChainCmpByPos {          // chain_cmp_by_pos (cly.c:2853-2870)
 };
 
 // delete_small_score_rst up to (not including) the max_read_l-dependent filter (cly.c:2883-2957)
-__device__ __noinline__ void score_and_merge(ReadState &S, const SearchDir *search_dir, uint32_t l_read, uint32_t kidx_bits_max)
+__device__ __noinline__ void score_and_merge(ReadState &S, const SearchDir *search_dir, uint32_t l_read)
 {
 	if (S.n_hit == 0) return;
 	DevChain *C = S.ws.chain;
@@ -1055,35 +1100,29 @@ __device__ __noinline__ void score_and_merge(ReadState &S, const SearchDir *sear
 	S.n_hit = DSB_MIN(400u, S.n_hit);
 	sc_hash_idx(S);
 	// get_score_M2 (cly.c:2821-2849)
-	int both_dir = 0;
-	for (uint32_t i = 0; i < S.n_hit; i++) {
-		both_dir |= (C[i].direction == DSB_FORWARD) ? 0x2 : 0x1;
-		if (both_dir == 3) break;
-	}
-	int key_bits = 10;                                             // hash_size[key_len] >= q_len, cly.c:2196-2198
-	for (; key_bits < 18; key_bits++) if ((1u << key_bits) >= l_read) break;
-	if ((uint32_t)key_bits > kidx_bits_max) key_bits = kidx_bits_max;
-	for (int c_dir = 2; c_dir >= 1; c_dir--) {
-		if ((c_dir & both_dir) == 0) continue;
-		const uint32_t direction = (c_dir == 1) ? DSB_REVERSE : DSB_FORWARD;
-		const SearchDir *c_sd = ((search_dir->direction == direction) ? 0 : 1) + search_dir;
-		{ PH_BEGIN(); build_kidx(S, c_sd->bin_read, l_read, (c_dir == 2) ? 0 : 1, key_bits); PH_END(S, 3); }
-	}
+	S.l_read = l_read;                                             // (build_hash_table_M2, cly.c:2173-2224, is not needed: see sdp_match)
 	for (uint32_t i = 0; i < S.n_hit; i++) {
 		if (C[i].sum_score == 0) continue;
 		const uint32_t dir = C[i].direction;
 		const SearchDir *c_sd = ((search_dir->direction == dir) ? 0 : 1) + search_dir;
-		const int slot = (dir == DSB_FORWARD) ? 0 : 1;
-		KIdx kx; kx.start = S.ws.kidx_start[slot]; kx.ent = S.ws.kidx_ent[slot]; kx.kmask = (1u << key_bits) - 1;
-		int score; { PH_BEGIN(); score = sdp_middle_M2(S, C[i].cur, c_sd->bin_read, kx); PH_END(S, 4); }
+		int score; { PH_BEGIN(); score = sdp_middle_M2(S, C[i].cur, c_sd->bin_read); PH_END(S, 4); }
 		if (S.error) return;
-		{ PH_BEGIN(); score = sdp_right_M2(S, c_sd->bin_read, kx, (int)i, l_read, score); PH_END(S, 5); }
+		{ PH_BEGIN(); score = sdp_right_M2(S, c_sd->bin_read, (int)i, l_read, score); PH_END(S, 5); }
 		if (S.error) return;
-		{ PH_BEGIN(); score = sdp_left_M2(S, c_sd->bin_read, kx, (int)i, score); PH_END(S, 6); }
+		{ PH_BEGIN(); score = sdp_left_M2(S, c_sd->bin_read, (int)i, score); PH_END(S, 6); }
 		if (S.error) return;
 		C[i].sum_score = score;
 	}
-	if (S.n_hit > 1) glibc_msort(C, S.ws.chain_tmp, (int)S.n_hit, ChainCmpByPos());
+	if (S.n_hit > 1) {
+		// qsort by chain_cmp_by_pos (cly.c:2853-2870): a consistent order (ref_ID, t_st ascending, sum_score descending), so the
+		// reference's merge sort is THE stable sort by that key -- two stable passes, least significant field first
+		uint64_t *key = S.ws.sort_key[0];
+		__syncwarp();
+		for (uint32_t i = lane_id(); i < S.n_hit; i += 32) key[i] = (uint32_t)~C[i].sum_score;
+		warp_stable_sort_by_key(C, S.ws.chain_tmp, S.n_hit, key);
+		for (uint32_t i = lane_id(); i < S.n_hit; i += 32) key[i] = ((uint64_t)C[i].ref_ID << 32) | C[i].t_st;
+		warp_stable_sort_by_key(C, S.ws.chain_tmp, S.n_hit, key);
+	}
 	const int n = (int)S.n_hit;
 	for (int ci = 0; ci < n - 1; ci++) {
 		if (C[ci].sum_score == 0) continue;
@@ -1377,7 +1416,7 @@ __device__ void phase_score(const ClassifyParams &P, ReadState &S, uint32_t r)
 	}
 	dsb_read_result out;
 	out.hit_off = 0; out.n_hit = 0; out.n_anchor = w.n_anc; out.fast_classify = w.fast_classify; out.entered_final = 1; out.error = 0; out.read_len = read_len;
-	score_and_merge(S, sd, read_len, P.kidx_bits_max);
+	score_and_merge(S, sd, read_len);
 	if (S.error == ERR_DEFER) {                          // too heavy for one warp: k_score_heavy starts over from the pool chains
 		list_push(P, LIST_SCORE_HEAVY, r);
 		read_end(P, S, r, t0);

@@ -170,7 +170,20 @@ __device__ __noinline__ void get_ref_t(LaneCtx &L, uint8_t *out, int64_t off, in
 	if (length < 0) length = 0;
 	L.c_getref++; L.c_getref_bytes += ((uint32_t)length + 3) >> 2;
 	const uint64_t o = (uint64_t)off;
-	for (uint32_t k = 0; k < (uint32_t)length; k++) out[k] = (uint8_t)ref_base_at(*L.ix, forward ? o + k : o - k);
+	const DevIndex &ix = *L.ix;
+	if (length == 0) return;
+	// <= 16 bases well inside the packed reference (every call of the seeding path): two aligned words instead of a load per base
+	const uint64_t x_hi = forward ? o + (uint32_t)(length - 1) : o;
+	if (length <= 16 && (forward || o >= (uint64_t)(length - 1)) && (x_hi >> 2) + 8 < ix.ref_bin_n + 1024) {
+		const uint64_t x_lo = forward ? o : o - (uint32_t)(length - 1);
+		const uint64_t w = (x_lo >> 2) & ~3ull;                          // byte offset of the first word
+		const uint32_t w0 = __ldg((const uint32_t *)(ix.ref_bin + w)), w1 = __ldg((const uint32_t *)(ix.ref_bin + w + 4));
+		const uint64_t v = ((uint64_t)__byte_perm(w0, 0, 0x0123) << 32) | __byte_perm(w1, 0, 0x0123);   // base 4w + d at bits 63-2d, 62-2d
+		const uint32_t d0 = (uint32_t)(o - 4 * w);
+		for (int k = 0; k < length; k++) { const uint32_t d = forward ? d0 + k : d0 - k; out[k] = (uint8_t)((v >> (62 - 2 * d)) & 3); }
+		return;
+	}
+	for (uint32_t k = 0; k < (uint32_t)length; k++) out[k] = (uint8_t)ref_base_at(ix, forward ? o + k : o - k);
 }
 
 __device__ __noinline__ int64_t get_uni_t(LaneCtx &L, uint64_t bwt_pos, int search_l, uint64_t *global_offset, uint32_t *uni_offset_)
@@ -490,8 +503,6 @@ __device__ __noinline__ void seed_pass(ReadState &S, const SearchDir &sd, uint32
 	SeedRec *rec = S.ws.seed_rec;
 	SeedTask T; T.stage = 2;
 	uint32_t carry = 0;                                          // 1: the next seed in array order is skipped
-	uint32_t n_anc = S.n_anc;
-	uint32_t c_prefix = 0, c_occ = 0, c_locate = 0, c_getref = 0, c_getref_bytes = 0;      // counters of the seeds the reference would have run
 	// Every seed that yields an anchor holds at least one chunk of the staging pool, so the seeds are taken in windows small
 	// enough for the pool (one window for all but reads of several 100 kb): search the window's seeds, append, reuse the pool.
 	const uint32_t win = DSB_MAX(32u, (L.n_chunks / 2) & ~31u);
@@ -538,6 +549,8 @@ __device__ __noinline__ void seed_pass(ReadState &S, const SearchDir &sd, uint32
 	L.error = __reduce_max_sync(DSB_FULL, L.error);
 	if (L.error) { S.error = L.error; return; }
 	// ordered append: drop the seeds removed by the "> 512 skips the next seed" rule (cly.c:1530-1531), prefix-sum, copy
+	uint32_t n_anc = S.n_anc;
+	uint32_t c_prefix = 0, c_occ = 0, c_locate = 0, c_getref = 0, c_getref_bytes = 0;      // counters of the seeds the reference would have run
 	for (uint32_t base = w0; base < w1; base += 32) {
 		const uint32_t k = base + lane;
 		SeedRec r; r.first_chunk = 0xffffffffu; r.count = 0; r.top_score = 35; r.flag512 = 0;
@@ -569,9 +582,9 @@ __device__ __noinline__ void seed_pass(ReadState &S, const SearchDir &sd, uint32
 		}
 		n_anc += total;
 	}
-	}
 	__syncwarp();
 	S.n_anc = n_anc;
 	S.c_prefix += __reduce_add_sync(DSB_FULL, c_prefix); S.c_occ += __reduce_add_sync(DSB_FULL, c_occ); S.c_locate += __reduce_add_sync(DSB_FULL, c_locate);
 	S.c_getref += __reduce_add_sync(DSB_FULL, c_getref); S.c_getref_bytes += __reduce_add_sync(DSB_FULL, c_getref_bytes);
+	}
 }

@@ -12,14 +12,14 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 ob.ensure_demo_index()
 _, seqs = bench.make_batch(ob, n, 0, 0, "/tmp")
 cat, offs = ob.pack(seqs)
-ix = dsb.Index(ob.DEMO_IDX, 0); ctx = dsb.Context(ix)
+ix = dsb.Index(ob.DEMO_IDX, 0); ctx = dsb.Context(ix, warps_per_sm=int(os.environ.get("PROF_WARPS", "0")) or None)
 ctx.upload(cat, offs)
 for _ in range(2):
     ctx.run(10**6); ctx.sync()
 print("kernel ms", dict(zip(dsb.KERNEL_NAMES, [round(x, 2) for x in ctx.kernel_ms()])))
 res = ctx.download()
 P = ctx.profile().astype(np.float64) * 1024 / 1.965e6     # ms at 1965 MHz
-names = ["fast", "chain", "slow", "kidx", "middle", "right", "left", "total"]
+names = ["fast", "chain", "slow", "match", "middle", "right", "left", "total"]
 print("sum over reads (warp-ms):", {k: round(float(P[:, i].sum()), 1) for i, k in enumerate(names)})
 print("mean per read (ms):", {k: round(float(P[:, i].mean()), 3) for i, k in enumerate(names)})
 order = np.argsort(-P[:, 7])
