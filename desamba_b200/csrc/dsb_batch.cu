@@ -14,7 +14,9 @@
 #define PROBE_TILE 1024
 #define PROBE_THREADS 256
 #define N_BITVEC 5                 // E_fwd, E_rev, T0_fwd, T0_rev, Z (k-mer not masked as low-complexity)
-#define CLASSIFY_WARPS_PER_BLOCK 4
+#ifndef CLASSIFY_WARPS_PER_BLOCK
+#define CLASSIFY_WARPS_PER_BLOCK 2      // small blocks release their SM share early in the tail of a launch (batches in flight overlap better)
+#endif
 #define HEAVY_BLOCKS 24               // CTAs of k_score_heavy (one heavy read at a time each; a handful of reads per batch)
 
 static inline uint32_t bits_words(uint32_t len) { return (len + 31) / 32 + 1; }
@@ -171,10 +173,10 @@ static ScratchLayout scratch_layout(uint32_t max_anchors, uint32_t max_matches, 
 	L.sc_hash = take((256 + 2 * 400 + 8) * sizeof(ScHash));
 	L.sms_tmp = take((uint64_t)max_matches * sizeof(DevSms)); L.cand = take((uint64_t)CAND_CAP * sizeof(uint2));
 	for (int s = 0; s < 2; s++) { L.sort_key[s] = take((uint64_t)max_matches * 8); L.sort_idx[s] = take((uint64_t)max_matches * 4); }
-	L.sp_set = take(32 * SP_TAB * 8);
+	L.sp_set = take(32 * (SP_SMALL + SP_TAB) * 8);
 	L.sp_gen = take(32 * 4);
 	L.lane_mem = take(32 * 512 * sizeof(MemRst));
-	L.seed_rec = take(((uint64_t)max_len / 2 + 8) * sizeof(SeedRec));
+	L.seed_rec = take((std::max<uint64_t>(2 * (uint64_t)max_len / 3, GROUP_SEEDS) + 16) * sizeof(SeedRec));   // island seeds of both strands of a read / of a group
 	L.chunk_next = take(((uint64_t)max_anchors / ANCHOR_CHUNK + 8) * 4);
 	L.total = o;
 	return L;
@@ -213,31 +215,51 @@ __device__ __forceinline__ uint32_t next_read(const ClassifyParams &P, int list,
 	return (list < 0) ? P.order[i] : P.list[list][i];
 }
 
-#ifndef SEED_MIN_BLOCKS
-#define SEED_MIN_BLOCKS 4
+#ifndef CLASSIFY_WARPS_PER_SM
+#define CLASSIFY_WARPS_PER_SM 16          // resident classify warps per SM the phase kernels are compiled for (register budget 65536 / (32 * this))
 #endif
+#define SEED_MIN_BLOCKS (CLASSIFY_WARPS_PER_SM / CLASSIFY_WARPS_PER_BLOCK)
 __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SEED_MIN_BLOCKS) k_seed(const __grid_constant__ ClassifyLaunch A, int pass, int list, int cursor)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	ReadState S;
 	warp_setup(A, S, smem_raw);
 	DevAnchor *scratch_anc = S.ws.anc;
+	WarpSmem *sm = S.sm;
 	if (list >= 0) {
 		// the work lists are in no particular order: take the long reads of the list first (their seeding is the tail of the pass)
 		for (int sweep = 0; sweep < 2; sweep++)
 			for (uint32_t r; (r = next_read(A.P, list, cursor + 12 * sweep)) != 0xffffffffu;) {
 				const bool is_long = (A.P.read_off[r + 1] - A.P.read_off[r]) > 12000;
-				if (is_long == (sweep == 0)) phase_seed(A.P, S, r, pass, scratch_anc);
+				if (is_long != (sweep == 0)) continue;
+				__syncwarp();
+				if (lane_id() == 0) { sm->grp_read[0] = r; sm->grp_n = 1; }
+				phase_seed(A.P, S, pass, scratch_anc);
 			}
 		return;
 	}
-	// first pass over all reads in `order` (longest first): the long ones a warp each, the short tail 32 reads per warp
+	// first pass over all reads in `order` (longest first): the long ones SEED_GROUP at a time -- as one group of jobs while
+	// their island seeds stay below GROUP_SEEDS, else in smaller groups -- the short tail 32 reads per warp
 	for (;;) {
-		uint32_t i = 0;
-		if (lane_id() == 0) i = atomicAdd(A.P.ctl + CTL_CURSOR + cursor, 1u);
-		i = __shfl_sync(DSB_FULL, i, 0);
-		if (i >= A.P.n_long) break;
-		phase_seed(A.P, S, A.P.order[i], pass, scratch_anc);
+		uint32_t i0 = 0;
+		if (lane_id() == 0) i0 = atomicAdd(A.P.ctl + CTL_CURSOR + cursor, (uint32_t)SEED_GROUP);
+		i0 = __shfl_sync(DSB_FULL, i0, 0);
+		if (i0 >= A.P.n_long) break;
+		const uint32_t cnt = min((uint32_t)SEED_GROUP, A.P.n_long - i0);
+		for (uint32_t q = 0; q < cnt;) {
+			uint32_t g = 0, tot = 0;
+			__syncwarp();
+			while (q + g < cnt) {
+				const uint32_t r = A.P.order[i0 + q + g];
+				const uint32_t ns = A.P.n_seeds[0][r] + A.P.n_seeds[1][r];
+				if (g > 0 && tot + ns > GROUP_SEEDS) break;
+				if (lane_id() == 0) sm->grp_read[g] = r;
+				g++; tot += ns;
+			}
+			if (lane_id() == 0) sm->grp_n = g;
+			phase_seed(A.P, S, pass, scratch_anc);
+			q += g;
+		}
 	}
 	const uint32_t n_short = A.P.n_reads - A.P.n_long;
 	for (;;) {
@@ -249,7 +271,7 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SEED_MIN_BLOCKS
 	}
 }
 
-__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_chain(const __grid_constant__ ClassifyLaunch A, int pass, int list, int cursor)
+__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SEED_MIN_BLOCKS) k_chain(const __grid_constant__ ClassifyLaunch A, int pass, int list, int cursor)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	ReadState S;
@@ -257,13 +279,18 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_chain(const _
 	for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_chain(A.P, S, r, pass);
 }
 
-__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32) k_score(const __grid_constant__ ClassifyLaunch A, int list, int cursor)
+__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SEED_MIN_BLOCKS) k_score(const __grid_constant__ ClassifyLaunch A, int list, int cursor)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	ReadState S;
 	warp_setup(A, S, smem_raw);
 	S.mt = (MatchSmem *)(smem_raw + CLASSIFY_WARPS_PER_BLOCK * sizeof(WarpSmem)) + (threadIdx.x >> 5);
-	for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_score(A.P, S, r);
+	// the list is in no particular order: reads with many anchors or many bases (the expensive ones) are scored first
+	for (int sweep = 0; sweep < 2; sweep++)
+		for (uint32_t r; (r = next_read(A.P, list, cursor + 12 * sweep)) != 0xffffffffu;) {
+			const bool is_big = A.P.work[r].n_anc > 200 || (A.P.read_off[r + 1] - A.P.read_off[r]) > 16000;
+			if (is_big == (sweep == 0)) phase_score(A.P, S, r);
+		}
 }
 
 // Reads with many anchors (repeats) carry the long tail of a batch: their sparse DP looks back over thousands of matches.
@@ -393,7 +420,7 @@ extern "C" void dsb_opts_default(dsb_opts *o)
 {
 	if (!o) return;
 	o->l_min_match = 170; o->min_score = 64;               // cly_mt.c:486
-	o->max_anchors = 16384; o->max_matches = 16384; o->max_read_len = 1u << 20; o->warps_per_sm = 16;
+	o->max_anchors = 16384; o->max_matches = 16384; o->max_read_len = 1u << 20; o->warps_per_sm = CLASSIFY_WARPS_PER_SM;
 }
 
 extern "C" int dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out)

@@ -35,11 +35,34 @@ struct DevSms { uint32_t t_pos, q_pos, len, score; };   // spd_match (cly.h:127-
 struct MemRst { int match_len; int sa_sp_l; uint64_t sp, sa_sp; int read_offset; int pad; };   // MEM_rst (cly.c:619-627)
 struct ScHash { uint16_t next; uint16_t seed_ID; uint16_t s_or_e; uint16_t pad; };   // seed_con_hash (cly.h:120-125)
 
+// a seeding job = one strand pass of one read (fast_classify / slow_classify over its island seeds); a warp runs the jobs of
+// up to SEED_GROUP reads at once.  Measured (gpurun_out/bench_vg*.json): groups of 4 / 8 reads take exactly as long as the
+// reads one after the other -- lanes on different seeds are in different code most of the time and a warp has ONE
+// scoreboard, so their latencies do not overlap -- and the coarser work units lengthen the tail of the launch
+// (fast pass 11.5 -> 19.6 -> 27.3 ms).  Hence 1: both strand passes of one read form the set of jobs.
+#ifndef SEED_GROUP
+#define SEED_GROUP 1
+#endif
+#define MAX_SEED_JOBS (2 * SEED_GROUP)
+#ifndef GROUP_SEEDS
+#define GROUP_SEEDS 384
+#endif
+//                              seeds (both strands) of the reads of a group: more and the next read starts a group of its own
+struct SeedJob {
+	const dsb_seed *seed_v; const uint8_t *bin_read;
+	uint32_t l_seed_v, read_len, direction;
+	uint32_t base;              // index of the job's first seed in the combined numbering of the group
+	uint32_t anc_end;           // anchors of the group up to and including this job
+	uint32_t pad;
+};
 struct WarpSmem {               // per-warp shared memory
 	uint8_t  refwin[2176];      // ref[2000] of sdp_middle_M2 / ref[1000] of sdp_right/left_M2 (+ over-read slack)
 	uint32_t next_seed;         // seed_pass: work counter of the lanes
 	uint32_t chunk_cursor;      // seed_pass: next free chunk of the anchor staging pool
-	uint32_t pad[2];
+	uint32_t grp_n;             // reads of the current seeding group
+	uint32_t pad;
+	uint32_t grp_read[SEED_GROUP], grp_job0[SEED_GROUP + 4];   // read ids, first job of each read (+ end)
+	SeedJob  job[MAX_SEED_JOBS];
 };
 // per-warp shared memory of the scoring kernels: hash table of the 9-mers of the scanned TARGET positions of one sdp_match
 #define TT_SLOTS 1024           // >= 2 x the scanned positions of a window (t_len < 2000 -> at most 497)
@@ -64,7 +87,7 @@ struct WarpScratch {            // per-warp HBM scratch
 	uint2     *cand;            // sdp_match: (scanned target index, read position) pairs with equal 9-mers (CAND_CAP)
 	uint64_t  *sort_key[2];     // sdp_match: order keys of sms_tmp + merge-sort ping-pong (max_matches each)
 	uint32_t  *sort_idx[2];     // merge-sort permutation ping-pong (max_matches each)
-	uint64_t  *sp_set;          // 32 lanes x SP_TAB slots of the visited-row hash sets, interleaved (zeroed when the scratch is allocated)
+	uint64_t  *sp_set;          // 32 lanes x (SP_SMALL + SP_TAB) slots of the visited-row hash sets, interleaved (zeroed when the scratch is allocated)
 	uint32_t  *sp_gen;          // 32 generation counters of those sets
 	MemRst    *lane_mem;        // 32 lanes x 512
 	SeedRec   *seed_rec;        // one per island seed of a strand
@@ -1206,51 +1229,88 @@ __device__ __forceinline__ void write_empty_result(const ClassifyParams &P, uint
 	}
 }
 
-__device__ void phase_seed(const ClassifyParams &P, ReadState &S, uint32_t r, int pass, DevAnchor *scratch_anc)
+// One seeding pass (fast / slow strand 0 / slow strand 1) of the reads S.sm->grp_read[0 .. grp_n): all their strand passes
+// run as one set of jobs (seed_pass); more than one read only in the fast pass.  A group that runs into a capacity is
+// taken apart again: its reads go to the redo list and are seeded one by one.
+__device__ void phase_seed(const ClassifyParams &P, ReadState &S, int pass, DevAnchor *scratch_anc)
 {
 	const long long t0 = clock64();
-	const uint32_t read_len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
+	WarpSmem *sm = S.sm;
+	const int lane = lane_id();
+	__syncwarp();
+	const int g = (int)sm->grp_n;
 	read_begin(S);
-	ReadWork w;
-	if (pass == PASS_FAST) {
-		w.anc_off = w.n_anc = w.chain_off = w.n_chain = 0; w.error = 0; w.fast_classify = 1; w.pad = 0;
-		if (read_len < MIN_READ_LEN) {                                 // cly.c:3089: untouched (unmapped) result
-			if (lane_id() == 0) P.work[r] = w;
-			write_empty_result(P, r, read_len, 0, 1, 0);
-			return;
-		}
-	} else
-		w = P.work[r];
-	SearchDir sd[2];
-	const bool both_direction = setup_dirs(P, r, read_len, sd);
 	S.ws.anc = scratch_anc;
-	if (pass == PASS_SLOW1) {                                          // the third pass appends to the (re-ordered) anchors of the second (cly.c:3121-3125)
-		const uint64_t *src = (const uint64_t *)(P.anc_pool + w.anc_off); uint64_t *dst = (uint64_t *)scratch_anc;
-		for (uint32_t i = lane_id(); i < w.n_anc * 3; i += 32) dst[i] = src[i];
+	ReadWork w;
+	w.anc_off = w.n_anc = w.chain_off = w.n_chain = 0; w.error = 0; w.fast_classify = 1; w.pad = 0;
+	// jobs
+	int n_jobs = 0; uint32_t base = 0;
+	for (int q = 0; q < g; q++) {
+		const uint32_t r = sm->grp_read[q];
+		const uint32_t read_len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
 		__syncwarp();
-		S.n_anc = w.n_anc;
-	}
-	if (pass == PASS_FAST) {
-		{ PH_BEGIN(); seed_pass(S, sd[0], read_len, false); PH_END(S, 0); }
-		if (!S.error && both_direction) { PH_BEGIN(); seed_pass(S, sd[1], read_len, false); PH_END(S, 0); }
-	} else {
-		PH_BEGIN(); seed_pass(S, sd[pass == PASS_SLOW0 ? 0 : 1], read_len, true); PH_END(S, 2);
-		w.fast_classify = 0;
-	}
-	// move the anchors to the read's own region of the pool
-	uint32_t off = 0;
-	if (!S.error && S.n_anc) {
-		if (lane_id() == 0) off = atomicAdd(P.ctl + CTL_ANC_CURSOR, S.n_anc);
-		off = __shfl_sync(DSB_FULL, off, 0);
-		if ((uint64_t)off + S.n_anc > P.anc_pool_cap) S.error = 1;
-		else {
-			const uint64_t *src = (const uint64_t *)scratch_anc; uint64_t *dst = (uint64_t *)(P.anc_pool + off);
-			for (uint32_t i = lane_id(); i < S.n_anc * 3; i += 32) dst[i] = src[i];
+		if (lane == 0) sm->grp_job0[q] = (uint32_t)n_jobs;
+		if (read_len < MIN_READ_LEN) continue;                         // cly.c:3089: untouched (unmapped) result, written below
+		SearchDir sd[2];
+		const bool both_direction = setup_dirs(P, r, read_len, sd);
+		const int d0 = (pass == PASS_SLOW1) ? 1 : 0, d1 = (pass == PASS_FAST && both_direction) ? 1 : d0;
+		for (int d = d0; d <= d1; d++) {
+			if (lane == 0) {
+				SeedJob J; J.seed_v = sd[d].seed_v; J.bin_read = sd[d].bin_read; J.l_seed_v = sd[d].l_seed_v; J.read_len = read_len;
+				J.direction = sd[d].direction; J.base = base; J.anc_end = 0; J.pad = 0;
+				sm->job[n_jobs] = J;
+			}
+			base += sd[d].l_seed_v; n_jobs++;
 		}
 	}
-	w.anc_off = off; w.n_anc = S.n_anc; w.error = (uint16_t)S.error;
-	if (lane_id() == 0) {
-		P.work[r] = w;
+	__syncwarp();
+	if (lane == 0) sm->grp_job0[g] = (uint32_t)n_jobs;
+	__syncwarp();
+	if (pass != PASS_FAST) {                                           // (one read)
+		w = P.work[sm->grp_read[0]];
+		w.fast_classify = 0;
+		if (pass == PASS_SLOW1) {                                      // the third pass appends to the (re-ordered) anchors of the second (cly.c:3121-3125)
+			const uint64_t *src = (const uint64_t *)(P.anc_pool + w.anc_off); uint64_t *dst = (uint64_t *)scratch_anc;
+			for (uint32_t i = lane; i < w.n_anc * 3; i += 32) dst[i] = src[i];
+			__syncwarp();
+			S.n_anc = w.n_anc;
+		}
+	}
+	if (n_jobs) { PH_BEGIN(); seed_pass(S, n_jobs, pass != PASS_FAST); PH_END(S, pass == PASS_FAST ? 0 : 2); }
+	if (S.error && g > 1) {                                            // take the group apart
+		if (lane == 0) for (int q = 0; q < g; q++) { const uint32_t i = atomicAdd(P.ctl + CTL_LIST_N + LIST_SEED_REDO, 1u); P.list[LIST_SEED_REDO][i] = sm->grp_read[q]; }
+		__syncwarp();
+		return;
+	}
+	// move the anchors of every read to its own region of the pool
+	for (int q = 0; q < g; q++) {
+		const uint32_t r = sm->grp_read[q];
+		const uint32_t read_len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
+		const int j0 = (int)sm->grp_job0[q], j1 = (int)sm->grp_job0[q + 1];
+		if (j0 == j1) {                                                // too short (fast pass only)
+			if (lane == 0) P.work[r] = w;
+			write_empty_result(P, r, read_len, 0, 1, 0);
+			continue;
+		}
+		const uint32_t a0 = (g == 1) ? 0u : ((j0 > 0) ? sm->job[j0 - 1].anc_end : 0u);
+		const uint32_t a1 = (g == 1) ? S.n_anc : sm->job[j1 - 1].anc_end;
+		const uint32_t n = S.error ? 0u : a1 - a0;
+		uint32_t off = 0; int err = S.error;
+		if (n) {
+			if (lane == 0) off = atomicAdd(P.ctl + CTL_ANC_CURSOR, n);
+			off = __shfl_sync(DSB_FULL, off, 0);
+			if ((uint64_t)off + n > P.anc_pool_cap) err = 1;
+			else {
+				const uint64_t *src = (const uint64_t *)(scratch_anc + a0); uint64_t *dst = (uint64_t *)(P.anc_pool + off);
+				for (uint32_t i = lane; i < n * 3; i += 32) dst[i] = src[i];
+			}
+		}
+		ReadWork wr = w;
+		wr.anc_off = off; wr.n_anc = err ? ((g == 1) ? S.n_anc : 0u) : n; wr.error = (uint16_t)err;
+		if (lane == 0) P.work[r] = wr;
+		if (P.prof && lane == 0) { const uint32_t dt = (uint32_t)(((clock64() - t0) / g) >> 10); P.prof[(uint64_t)r * 8 + (pass == PASS_FAST ? 0 : 2)] += dt; P.prof[(uint64_t)r * 8 + 7] += dt; }
+	}
+	if (lane == 0) {
 		unsigned long long *C = P.counters;
 		atomicAdd(C + DSB_CNT_N_PREFIX, (unsigned long long)S.c_prefix);
 		atomicAdd(C + DSB_CNT_N_OCC, (unsigned long long)S.c_occ);
@@ -1258,7 +1318,7 @@ __device__ void phase_seed(const ClassifyParams &P, ReadState &S, uint32_t r, in
 		atomicAdd(C + DSB_CNT_N_GETREF, (unsigned long long)S.c_getref);
 		atomicAdd(C + DSB_CNT_N_GETREF_BYTES, (unsigned long long)S.c_getref_bytes);
 	}
-	read_end(P, S, r, t0);
+	__syncwarp();
 }
 
 // Fast pass for SHORT reads (<= SHORT_READ_MAX bp: a handful of island seeds each), one LANE per READ: lane l runs

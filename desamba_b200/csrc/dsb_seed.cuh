@@ -79,11 +79,13 @@ __device__ __noinline__ uint64_t occ_char_t(const DevIndex &ix, uint64_t r, uint
 // BWT are < 2^40, like REF_POS.global_offset), 0 = never used; emptying the set = next generation, stale slots read as
 // free.  (The linear scan was 69 % of the instructions of the seeding kernel on short reads, profiles/r1d_*.)
 #define SP_TAB 1024
+#define SP_SMALL 128            // the first SP_SMALL / 2 rows of a set live in a table of this size (1 KB per lane, cache
+                                // resident; most seeds never need more) -- only later rows go to the SP_TAB-slot table behind it
 __device__ __forceinline__ void sp_set_clear_t(LaneCtx &L)
 {
 	L.sp_l = 0;
 	if (++L.sp_gen >= (1u << 24)) {
-		for (int i = 0; i < SP_TAB; i++) L.sp_set[i * 32] = 0;
+		for (int i = 0; i < SP_SMALL + SP_TAB; i++) L.sp_set[i * 32] = 0;
 		L.sp_gen = 1;
 	}
 }
@@ -91,11 +93,21 @@ __device__ __noinline__ int sp_set_insert_t(LaneCtx &L, uint64_t node)
 {
 	if (L.sp_l == SP_SET_CAP) sp_set_clear_t(L);
 	const uint64_t key = ((uint64_t)L.sp_gen << 40) | (node & 0xFFFFFFFFFFull);
-	uint32_t h = (uint32_t)((node * 0x9E3779B97F4A7C15ull) >> 54);          // top 10 bits
-	for (;;) {
+	const uint64_t hh = node * 0x9E3779B97F4A7C15ull;
+	uint32_t h = (uint32_t)(hh >> 57);                                       // top 7 bits
+	for (;;) {                                                               // (at most SP_SMALL / 2 live slots: a free one exists)
 		const uint64_t v = L.sp_set[h * 32];
 		if (v == key) return 0;
-		if ((uint32_t)(v >> 40) != L.sp_gen) { L.sp_set[h * 32] = key; L.sp_l++; return 1; }
+		if ((uint32_t)(v >> 40) != L.sp_gen) break;
+		h = (h + 1) & (SP_SMALL - 1);
+	}
+	if (L.sp_l < SP_SMALL / 2) { L.sp_set[h * 32] = key; L.sp_l++; return 1; }
+	uint64_t *big = L.sp_set + SP_SMALL * 32;
+	h = (uint32_t)(hh >> 54);                                                // top 10 bits
+	for (;;) {
+		const uint64_t v = big[h * 32];
+		if (v == key) return 0;
+		if ((uint32_t)(v >> 40) != L.sp_gen) { big[h * 32] = key; L.sp_l++; return 1; }
 		h = (h + 1) & (SP_TAB - 1);
 	}
 }
@@ -117,6 +129,7 @@ __device__ __noinline__ void bwt_single_search_t(LaneCtx &L, uint64_t sp, const 
 		if (c != (uint32_t)__ldg(string)) break;
 		match_len++;
 		string--;
+		asm volatile("prefetch.global.L1 [%0];" :: "l"(ix.occ + (new_sp >> 7) * 128));   // the next step's FM line, while the set is probed
 		if (sp_set_insert_t(L, new_sp) == 0) { out->match_len = -1000; return; }
 		sp = new_sp;
 	}
@@ -485,21 +498,32 @@ __device__ __forceinline__ void slow_seed_step(LaneCtx &L, SeedTask &T, const Se
 }
 
 // ================================================================ warp level
-// One seeding pass over a strand = fast_classify (cly.c:1476-1546) or slow_classify (cly.c:1548-1611): lanes pull seeds,
-// then the anchors are appended to S.ws.anc in seed order with anchor_useless set per seed (cly.c:1536-1542, 1601-1607).
-__device__ __noinline__ void seed_pass(ReadState &S, const SearchDir &sd, uint32_t read_len, bool slow)
+// The seeding jobs in S.sm->job[0 .. n_jobs) (strand passes of one or several reads: fast_classify, cly.c:1476-1546, or
+// slow_classify, cly.c:1548-1611): the lanes pull seeds from the combined numbering of all jobs, then the anchors are appended
+// to S.ws.anc job by job in seed order with anchor_useless set per seed (cly.c:1536-1542, 1601-1607); job[j].anc_end
+// receives S.n_anc after job j.
+__device__ __forceinline__ int seed_job_of(const WarpSmem *sm, int n_jobs, uint32_t k)
+{
+	int j = 0;
+	while (j + 1 < n_jobs && k >= sm->job[j + 1].base) j++;
+	return j;
+}
+
+__device__ __noinline__ void seed_pass(ReadState &S, int n_jobs, bool slow)
 {
 	WarpSmem *sm = S.sm;
 	const int lane = lane_id();
-	const uint32_t n_seed = sd.l_seed_v;
+	__syncwarp();
+	const uint32_t n_seed = sm->job[n_jobs - 1].base + sm->job[n_jobs - 1].l_seed_v;
 	if (slow) S.fast_classify = 0;
+	if (lane < n_jobs) sm->job[lane].anc_end = S.n_anc;              // (jobs without seeds keep the count of their predecessor, fixed below)
+	__syncwarp();
 	if (n_seed == 0) return;
 	LaneCtx L;
 	L.ix = S.ix; L.sp_set = S.ws.sp_set + lane; L.sp_l = 0; L.sp_gen = S.ws.sp_gen[lane]; L.mem = S.ws.lane_mem + lane * 512;
 	L.pool = S.ws.anc_tmp; L.chunk_next = S.ws.chunk_next; L.chunk_cursor = &sm->chunk_cursor; L.n_chunks = S.max_anchors / ANCHOR_CHUNK;
 	L.error = 0; L.c_prefix = L.c_occ = L.c_locate = L.c_getref = L.c_getref_bytes = 0; L.lin = nullptr; L.lin_cap = 0;
-	const SeedInfo s_i = {sd.bin_read, read_len, sd.direction};
-	const uint8_t top0 = sd.seed_v[0].top;
+	SeedInfo s_i = {nullptr, 0, 0};
 	SeedRec *rec = S.ws.seed_rec;
 	SeedTask T; T.stage = 2;
 	uint32_t carry = 0;                                          // 1: the next seed in array order is skipped
@@ -517,11 +541,13 @@ __device__ __noinline__ void seed_pass(ReadState &S, const SearchDir &sd, uint32
 		while (my_k < 0 && !exhausted) {
 			const uint32_t k = atomicAdd(&sm->next_seed, 1u);
 			if (k >= w1) { exhausted = true; break; }
-			const dsb_seed sv = sd.seed_v[k];
-			const bool eligible = slow ? !((int)(sv.len) < 3 && top0 == 0)              // sv_f->top: seed 0's flag, as written (cly.c:1564)
+			const SeedJob &J = sm->job[seed_job_of(sm, n_jobs, k)];
+			const dsb_seed sv = J.seed_v[k - J.base];
+			const bool eligible = slow ? !((int)(sv.len) < 3 && J.seed_v[0].top == 0)   // sv_f->top: seed 0's flag, as written (cly.c:1564)
 			                           : (sv.top != 0);
 			if (eligible && !L.error) {
 				my_k = (int)k;
+				s_i.bin_read = J.bin_read; s_i.read_L = J.read_len; s_i.direction = J.direction;
 				sp_set_clear_t(L); L.n_out = 0; L.first_chunk = 0xffffffffu; L.cur_chunk = 0; L.top_score = 35;
 				L.c_prefix = L.c_occ = L.c_locate = L.c_getref = L.c_getref_bytes = 0;
 				seed_task_begin(T, sv, slow, L.ix->l_ek);
@@ -548,19 +574,25 @@ __device__ __noinline__ void seed_pass(ReadState &S, const SearchDir &sd, uint32
 	__syncwarp();
 	L.error = __reduce_max_sync(DSB_FULL, L.error);
 	if (L.error) { S.error = L.error; return; }
-	// ordered append: drop the seeds removed by the "> 512 skips the next seed" rule (cly.c:1530-1531), prefix-sum, copy
+	// ordered append: drop the seeds removed by the "> 512 skips the next seed" rule (cly.c:1530-1531; it does not reach into
+	// the next strand pass), prefix-sum, copy
 	uint32_t n_anc = S.n_anc;
 	uint32_t c_prefix = 0, c_occ = 0, c_locate = 0, c_getref = 0, c_getref_bytes = 0;      // counters of the seeds the reference would have run
 	for (uint32_t base = w0; base < w1; base += 32) {
 		const uint32_t k = base + lane;
 		SeedRec r; r.first_chunk = 0xffffffffu; r.count = 0; r.top_score = 35; r.flag512 = 0;
 		r.c_prefix = r.c_occ = r.c_locate = r.c_getref = r.c_getref_bytes = 0;
-		if (k < w1) r = rec[k];
-		const uint32_t F = __ballot_sync(DSB_FULL, r.flag512 != 0);
+		int jk = 0; bool job_first = false, job_last = false;
+		if (k < w1) {
+			r = rec[k];
+			jk = seed_job_of(sm, n_jobs, k);
+			job_first = (k == sm->job[jk].base); job_last = (k + 1 == sm->job[jk].base + sm->job[jk].l_seed_v);
+		}
+		const uint32_t F = __ballot_sync(DSB_FULL, r.flag512 != 0), J1 = __ballot_sync(DSB_FULL, job_first);
 		uint32_t skipped = 0;
 		#pragma unroll
 		for (int b = 0; b < 32; b++) {
-			const uint32_t sk = carry;
+			const uint32_t sk = ((J1 >> b) & 1) ? 0u : carry;
 			skipped |= sk << b;
 			carry = (!sk && ((F >> b) & 1)) ? 1u : 0u;
 		}
@@ -572,6 +604,7 @@ __device__ __noinline__ void seed_pass(ReadState &S, const SearchDir &sd, uint32
 		for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(DSB_FULL, x, d); if (lane >= d) x += y; }
 		const uint32_t total = __shfl_sync(DSB_FULL, x, 31);
 		if (n_anc + total > S.max_anchors) { S.error = 1; return; }
+		if (job_last) sm->job[jk].anc_end = n_anc + x;
 		uint32_t dst = n_anc + x - cnt;
 		uint32_t ch = r.first_chunk;
 		for (uint32_t i = 0; i < cnt; i++) {
@@ -587,4 +620,8 @@ __device__ __noinline__ void seed_pass(ReadState &S, const SearchDir &sd, uint32
 	S.c_prefix += __reduce_add_sync(DSB_FULL, c_prefix); S.c_occ += __reduce_add_sync(DSB_FULL, c_occ); S.c_locate += __reduce_add_sync(DSB_FULL, c_locate);
 	S.c_getref += __reduce_add_sync(DSB_FULL, c_getref); S.c_getref_bytes += __reduce_add_sync(DSB_FULL, c_getref_bytes);
 	}
+	__syncwarp();
+	if (lane == 0)
+		for (int j = 0; j < n_jobs; j++) if (sm->job[j].l_seed_v == 0 && j > 0) sm->job[j].anc_end = sm->job[j - 1].anc_end;
+	__syncwarp();
 }
