@@ -58,7 +58,7 @@ _sig("dsb_batch_run", C.c_int, _vp, C.c_int32)
 _sig("dsb_batch_download", C.c_int, _vp, _i32p, _vp, _vp, C.c_uint64, _u64p)
 _sig("dsb_batch_sync", C.c_int, _vp)
 _sig("dsb_batch_get_seeds", C.c_int, _vp, C.c_uint32, C.c_int, _vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32))
-_sig("dsb_batch_kernel_ms", C.c_int, _vp, C.POINTER(C.c_float * 10), C.c_int)
+_sig("dsb_batch_kernel_ms", C.c_int, _vp, C.POINTER(C.c_float * 11), C.c_int)
 _sig("dsb_ctx_mark", C.c_int, _vp, C.c_int)
 _sig("dsb_ctx_elapsed_ms", C.c_int, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_float))
 _sig("dsb_batch_launches", C.c_int, _vp)
@@ -73,7 +73,7 @@ _sig("dsb_gather_bench", C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.PO
 
 DSB_E_CAPACITY = -5
 KERNEL_NAMES = ["k_encode_probe", "k_islands", "k_seed(fast)", "k_chain(fast)", "k_seed(slow0)", "k_chain(slow0)", "k_seed(slow1)", "k_chain(slow1)",
-                "k_score", "k_finalize"]
+                "k_score", "k_score_heavy", "k_finalize"]
 COUNTER_NAMES = ["hit_slots", "reads_taken", "first_long", "max_read_l", "n_bit0", "n_bit1", "n_prefix", "n_occ", "n_locate",
                  "n_getref_seed", "n_getref_bytes_seed", "n_errors", "n_getref_score", "n_getref_bytes_score"]
 
@@ -260,9 +260,9 @@ class Context:
         return out, ts.value
 
     def kernel_ms(self):
-        """device ms of the 10 kernels of the last run (KERNEL_NAMES)"""
-        ms = (C.c_float * 10)()
-        _check(lib.dsb_batch_kernel_ms(self._h, C.byref(ms), 10), "dsb_batch_kernel_ms")
+        """device ms of the 11 kernel groups of the last run (KERNEL_NAMES)"""
+        ms = (C.c_float * 11)()
+        _check(lib.dsb_batch_kernel_ms(self._h, C.byref(ms), 11), "dsb_batch_kernel_ms")
         return list(ms)
 
     def mark(self, which):

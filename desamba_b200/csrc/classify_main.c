@@ -9,7 +9,7 @@
  *   writer (main)   formats the result records of each batch in input order (output_results, cly_mt.c:350-365)
  * The index is replicated per GPU, reads are sharded by batch, nothing is exchanged between GPUs.
  * Extra options: -g INT GPUs to use [all visible], -c INT contexts (batches in flight) per GPU [3], -B INT reads per batch
- * [262144], -M INT Mbases per batch [256].
+ * [262144], -M INT Mbases per batch [512].
  * -t is accepted and ignored (the thread pool it sized no longer exists).
  *
  * Classify_buff_pool.max_read_l (cly.c:2958) is the reference's only cross-read state; with -t 1 it is the running maximum
@@ -349,7 +349,7 @@ static void usage(void)
 	fprintf(stderr, "    -l, INT         minimum matching length, ignored for NGS reads [170]\n    -r, INT         max Output number of secondary alignments[5]\n");
 	fprintf(stderr, "    -o, FILE        output results into file [stdout]\n    -s, INT         MIN score[64]\n");
 	fprintf(stderr, "    -f, STR         output format, one of: SAM (default), SAM_FULL, DES, DES_FULL\n");
-	fprintf(stderr, "    -g, INT         number of GPUs [all visible]\n    -c, INT         batches in flight per GPU [3]\n    -B, INT         reads per batch [262144]\n    -M, INT         Mbases per batch [256]\n\n");
+	fprintf(stderr, "    -g, INT         number of GPUs [all visible]\n    -c, INT         batches in flight per GPU [3]\n    -B, INT         reads per batch [262144]\n    -M, INT         Mbases per batch [512]\n\n");
 }
 
 static double now_s(void) { struct timeval t; gettimeofday(&t, NULL); return t.tv_sec + t.tv_usec * 1e-6; }
@@ -357,7 +357,7 @@ static double cpu_s(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); return 
 
 static int classify_main(int argc, char **argv)
 {
-	opts_t o = {170, 4, 5, FMT_SAM, 64, 0, 3, 262144, 256ull << 20, stdout};
+	opts_t o = {170, 4, 5, FMT_SAM, 64, 0, 3, 262144, 512ull << 20, stdout};
 	int c;
 	while ((c = getopt(argc, argv, "ht:l:r:f:o:s:g:B:M:c:")) >= 0) {
 		if (c == 'h') { usage(); return 0; }

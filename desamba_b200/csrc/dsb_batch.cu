@@ -218,7 +218,11 @@ __device__ __forceinline__ uint32_t next_read(const ClassifyParams &P, int list,
 #ifndef CLASSIFY_WARPS_PER_SM
 #define CLASSIFY_WARPS_PER_SM 16          // resident classify warps per SM the phase kernels are compiled for (register budget 65536 / (32 * this))
 #endif
-#define SEED_MIN_BLOCKS (CLASSIFY_WARPS_PER_SM / CLASSIFY_WARPS_PER_BLOCK)
+#ifndef SEED_REG_WARPS
+#define SEED_REG_WARPS CLASSIFY_WARPS_PER_SM    // warps per SM the register budget of k_seed / k_chain is cut for (>= the launched number: launches of several contexts can then share an SM)
+#endif
+#define SEED_MIN_BLOCKS (SEED_REG_WARPS / CLASSIFY_WARPS_PER_BLOCK)
+#define SCORE_MIN_BLOCKS (CLASSIFY_WARPS_PER_SM / CLASSIFY_WARPS_PER_BLOCK)
 __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SEED_MIN_BLOCKS) k_seed(const __grid_constant__ ClassifyLaunch A, int pass, int list, int cursor)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -279,7 +283,7 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SEED_MIN_BLOCKS
 	for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_chain(A.P, S, r, pass);
 }
 
-__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SEED_MIN_BLOCKS) k_score(const __grid_constant__ ClassifyLaunch A, int list, int cursor)
+__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SCORE_MIN_BLOCKS) k_score(const __grid_constant__ ClassifyLaunch A, int list, int cursor)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	ReadState S;
@@ -525,8 +529,15 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 	h_bin_off[n_reads] = bo; h_bits_off[n_reads] = wo; h_seed_off[n_reads] = (uint32_t)so;
 	// work order of the first seeding pass: longest reads first (the expensive tail starts early)
 	uint32_t *h_order = h_seed_off + n_reads + 1;
-	for (uint32_t r = 0; r < n_reads; r++) h_order[r] = r;
-	std::stable_sort(h_order, h_order + n_reads, [&](uint32_t a, uint32_t b) { return offs[a + 1] - offs[a] > offs[b + 1] - offs[b]; });
+	// (a stable counting sort by length: a comparison sort of a million 150-bp reads cost more host time than their kernels)
+	{
+		std::vector<uint32_t> &first = c->h_len_first;
+		first.assign((size_t)max_len + 2, 0);
+		for (uint32_t r = 0; r < n_reads; r++) first[(uint32_t)(offs[r + 1] - offs[r])]++;
+		uint32_t run = 0;
+		for (uint32_t l = max_len + 1; l-- > 0;) { const uint32_t n_l = first[l]; first[l] = run; run += n_l; }   // first[l] = reads longer than l
+		for (uint32_t r = 0; r < n_reads; r++) h_order[first[(uint32_t)(offs[r + 1] - offs[r])]++] = r;
+	}
 	c->n_long = 0;
 	for (uint32_t r = 0; r < n_reads; r++) if (offs[r + 1] - offs[r] > SHORT_READ_MAX) c->n_long++;
 	// policy P3: the capacity of the reference's bin_read buffer (BUFF_REALLOC, utils.h:117-122) in input order decides the
@@ -649,8 +660,9 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		k_chain<<<blocks, threads, smem, st>>>(A, PASS_SLOW1, LIST_SLOW1, 5);   DSB_CUDA(cudaEventRecord(c->ev[8], st));
 		// scoring: a warp per read; the few reads that give up there (ERR_DEFER) then get a CTA each
 		k_score<<<blocks, threads, smem + CLASSIFY_WARPS_PER_BLOCK * sizeof(MatchSmem), st>>>(A, LIST_SCORE, 6);
-		k_score_heavy<<<HEAVY_BLOCKS, TEAM_WARPS * 32, 0, st>>>(A, LIST_SCORE_HEAVY, 7, (uint32_t)c->n_warps);
 		DSB_CUDA(cudaEventRecord(c->ev[9], st));
+		k_score_heavy<<<HEAVY_BLOCKS, TEAM_WARPS * 32, 0, st>>>(A, LIST_SCORE_HEAVY, 7, (uint32_t)c->n_warps);
+		DSB_CUDA(cudaEventRecord(c->ev[10], st));
 		c->launches += 9;
 	}
 	{
@@ -661,7 +673,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		k_finalize<<<(n + 127) / 128, 128, 0, st>>>(P);
 		c->launches++;
 	}
-	DSB_CUDA(cudaEventRecord(c->ev[10], st));
+	DSB_CUDA(cudaEventRecord(c->ev[11], st));
 	DSB_CUDA(cudaGetLastError());
 	c->ran = true;
 	return DSB_OK;

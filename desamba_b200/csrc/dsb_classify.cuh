@@ -237,7 +237,7 @@ struct AnchorCmp {                                // Anchor_cmp_by_chr_ID_and_po
 // time, and the array is permuted through scratch.  (chain_cmp_by_MEM_score is NOT consistent: k_finalize keeps the
 // explicit merge emulation for it.)
 template <typename T>
-__device__ __forceinline__ void warp_stable_sort_by_key(T *a, T *tmp, uint32_t n, uint64_t *key)
+__device__ __noinline__ void warp_stable_sort_by_key(T *a, T *tmp, uint32_t n, uint64_t *key)
 {
 	const int lane = lane_id();
 	__syncwarp();
@@ -245,6 +245,7 @@ __device__ __forceinline__ void warp_stable_sort_by_key(T *a, T *tmp, uint32_t n
 		const uint32_t i = i0 + lane;
 		const uint64_t ki = (i < n) ? key[i] : 0;
 		uint32_t r = 0;
+		#pragma unroll 4
 		for (uint32_t j = 0; j < n; j++) { const uint64_t kj = key[j]; r += (kj < ki || (kj == ki && j < i)) ? 1u : 0u; }
 		if (i < n) tmp[r] = a[i];
 	}
@@ -695,9 +696,7 @@ __device__ __forceinline__ void refwin_zero(ReadState &S, int nbytes)     // zer
 
 __device__ __forceinline__ int warp_max(int v)
 {
-	#pragma unroll
-	for (int d = 16; d; d >>= 1) v = max(v, __shfl_xor_sync(DSB_FULL, v, d));
-	return v;
+	return __reduce_max_sync(DSB_FULL, v);
 }
 __device__ __forceinline__ DevSms load_sms(const DevSms *p)
 {
@@ -760,30 +759,29 @@ __device__ __forceinline__ void dp_eval(const int KIND, const DevSms &c, const D
 
 // Heavy reads (repeats: thousands of matches per window) are scored by k_score_heavy with a whole CTA: warp 0 runs the
 // read, the other warps only help with phase (A) below -- each takes a contiguous range of the earlier matches.
-#define TEAM_WARPS 16
-#define TEAM_MIN_FIRST 512
+#define TEAM_WARPS 32
+#define TEAM_MIN_FIRST 128
 struct DpTeam {
 	int cmd;                          // >= 0: job posted, < 0: exit
 	int kind; uint32_t first, nb;
 	const DevSms *sms;
 	DevSms item[32]; int stopped0[32];
 	int best[TEAM_WARPS][32]; int brk[TEAM_WARPS][32];
-	uint4 tile[TEAM_WARPS][64];       // predecessor tiles of dp_range, two per warp
+	uint4 tile[TEAM_WARPS][32];       // predecessor tile of dp_range, one per warp
 };
 
 // phase (A) over the predecessors [lo, hi), walked downwards: best candidate per lane and whether the lane's walk hit its break.
 // The predecessors are fetched 32 at a time (one coalesced 512-byte request, the next tile already in flight), parked in a
-// shared-memory tile (two tiles, used alternately) and read back by all lanes as broadcasts, highest index first.
+// shared-memory tile and read back by all lanes as broadcasts, highest index first.
 __device__ __noinline__ void dp_range(const int KIND, const DevSms *sms, int lo, int hi, const DevSms &my, bool stopped, int &best, bool &brk_out, uint32_t a_tile)
 {
 	const int lane = lane_id();
 	int top = hi - 1;                                    // tile = entries top, top-1, ..., top-31 (lane l holds entry top - l)
 	uint4 cur = make_uint4(0, 0, 0, 0);
 	if (top - lane >= lo) cur = *(const uint4 *)(sms + top - lane);
-	uint32_t buf = 0;
 	while (top >= lo) {
-		if (__all_sync(DSB_FULL, stopped)) break;
-		const uint32_t a_buf = a_tile + buf * 512;
+		if (__all_sync(DSB_FULL, stopped)) break;                                  // (also: every lane is done with the previous tile)
+		const uint32_t a_buf = a_tile;
 		asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a_buf + 16 * lane), "r"(cur.x), "r"(cur.y), "r"(cur.z), "r"(cur.w) : "memory");
 		uint4 nxt = make_uint4(0, 0, 0, 0);
 		if (top - 32 - lane >= lo) nxt = *(const uint4 *)(sms + top - 32 - lane);
@@ -800,7 +798,7 @@ __device__ __noinline__ void dp_range(const int KIND, const DevSms *sms, int lo,
 				if (has) best = DSB_MAX(best, cand);
 			}
 		}
-		cur = nxt; top -= 32; buf ^= 1;
+		cur = nxt; top -= 32;
 	}
 	__syncwarp();
 }
@@ -832,12 +830,17 @@ __device__ __noinline__ int dp_block(const int KIND, const DevSms *sms, uint32_t
 {
 	const int lane = lane_id();
 	const bool mine = (uint32_t)lane < nb;
+	// the block's matches, parked in shared memory behind the predecessor tile: read back as broadcasts in (0) and (B)
+	const uint32_t a_blk = a_tile + 512;
+	__syncwarp();
+	asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a_blk + 16 * lane), "r"(my.t_pos), "r"(my.q_pos), "r"(my.len), "r"(0u) : "memory");
+	__syncwarp();
 	// (0) inside the block, positions only: does my walk stop (break) before it leaves the block, and at which lane?
 	int stop_at = -1;                                    // highest k < lane whose predecessor test says `break`
 	if (KIND != DP_MIDDLE) {
 		for (int k = (int)nb - 2; k >= 0; k--) {
 			DevSms p;
-			p.t_pos = __shfl_sync(DSB_FULL, my.t_pos, k); p.q_pos = __shfl_sync(DSB_FULL, my.q_pos, k); p.len = __shfl_sync(DSB_FULL, my.len, k); p.score = 0;
+			asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(p.t_pos), "=r"(p.q_pos), "=r"(p.len), "=r"(p.score) : "r"(a_blk + 16 * k) : "memory");
 			if (mine && k < lane && stop_at < 0) { bool pass, brk, has; int cand; dp_eval(KIND, my, p, pass, brk, has, cand); if (brk) stop_at = k; }
 		}
 	}
@@ -861,7 +864,7 @@ __device__ __noinline__ int dp_block(const int KIND, const DevSms *sms, uint32_t
 	int my_score = best;
 	for (uint32_t j = 1; j < nb; j++) {
 		DevSms c;
-		c.t_pos = __shfl_sync(DSB_FULL, my.t_pos, j); c.q_pos = __shfl_sync(DSB_FULL, my.q_pos, j); c.len = __shfl_sync(DSB_FULL, my.len, j); c.score = 0;
+		asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c.t_pos), "=r"(c.q_pos), "=r"(c.len), "=r"(c.score) : "r"(a_blk + 16 * j) : "memory");
 		const int c_stop = __shfl_sync(DSB_FULL, stop_at, j);
 		int cand_max = INT_MIN;
 		if ((uint32_t)lane < j && lane > c_stop) {
@@ -870,7 +873,7 @@ __device__ __noinline__ int dp_block(const int KIND, const DevSms *sms, uint32_t
 			dp_eval(KIND, c, p, pass, brk, has, cand);
 			if (has) cand_max = cand;
 		}
-		cand_max = warp_max(cand_max);
+		cand_max = __reduce_max_sync(DSB_FULL, cand_max);
 		if ((uint32_t)lane == j && cand_max > my_score) my_score = cand_max;
 	}
 	return my_score;
@@ -1232,7 +1235,7 @@ __device__ __forceinline__ void write_empty_result(const ClassifyParams &P, uint
 // One seeding pass (fast / slow strand 0 / slow strand 1) of the reads S.sm->grp_read[0 .. grp_n): all their strand passes
 // run as one set of jobs (seed_pass); more than one read only in the fast pass.  A group that runs into a capacity is
 // taken apart again: its reads go to the redo list and are seeded one by one.
-__device__ void phase_seed(const ClassifyParams &P, ReadState &S, int pass, DevAnchor *scratch_anc)
+__device__ __noinline__ void phase_seed(const ClassifyParams &P, ReadState &S, int pass, DevAnchor *scratch_anc)
 {
 	const long long t0 = clock64();
 	WarpSmem *sm = S.sm;

@@ -26,7 +26,7 @@ struct DevBuf {                         // grow-only device buffer
 	DevBuf() : p(nullptr), cap(0) {}
 };
 
-#define DSB_N_KERNELS 10               // launches of one dsb_batch_run
+#define DSB_N_KERNELS 11               // timed kernel groups of one dsb_batch_run
 #define DSB_N_EV (DSB_N_KERNELS + 3)   // kernel boundaries + 2 user marks
 
 struct dsb_ctx {
@@ -50,6 +50,7 @@ struct dsb_ctx {
 	std::vector<uint64_t> h_off;        // host copies of the per-read offset tables
 	std::vector<uint64_t> h_bits_off;
 	std::vector<uint32_t> h_seed_off;
+	std::vector<uint32_t> h_len_first;  // counting sort of the reads by length (work order)
 	cudaEvent_t ev[DSB_N_EV];
 	int launches;
 	bool ran;

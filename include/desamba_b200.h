@@ -118,7 +118,7 @@ int dsb_batch_sync(dsb_ctx *ctx);
 int dsb_batch_get_seeds(dsb_ctx *ctx, uint32_t read, int strand /*0 fwd,1 rev*/, dsb_seed *out, uint32_t cap, uint32_t *n_out, uint32_t *total_score);
 /* device time of each kernel of the last dsb_batch_run in ms (CUDA events on the context's stream), up to `cap` values:
  * [0] encode+probe, [1] islands, [2] seed fast, [3] chain, [4] seed slow (strand 0), [5] chain, [6] seed slow (strand 1),
- * [7] chain, [8] score, [9] finalize */
+ * [7] chain, [8] score (warp per read), [9] score of the deferred repeat-rich reads (CTA per read), [10] finalize */
 int dsb_batch_kernel_ms(dsb_ctx *ctx, float *ms, int cap);
 /* stream marks for timing several contexts (batches) in flight on one GPU: dsb_ctx_mark records mark 0 or 1 on the
  * context's stream; dsb_ctx_elapsed_ms waits for b's mark and returns b.mark_b - a.mark_a in ms */

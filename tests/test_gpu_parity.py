@@ -188,7 +188,7 @@ def test_upload_run_download_equals_classify_batch(gpu, ob):
         assert b.rr.tobytes() != b"" and [b.read_hits(i).tobytes() for i in range(len(seqs))] == [a.read_hits(i).tobytes() for i in range(len(seqs))]
         assert b.rr["n_anchor"].tolist() == a.rr["n_anchor"].tolist()
     ms = ctx.kernel_ms()
-    assert len(ms) == 10 and all(m >= 0 for m in ms) and ms[2] > 0 and ms[8] > 0
+    assert len(ms) == 11 and all(m >= 0 for m in ms) and ms[2] > 0 and ms[8] > 0
 
 
 def test_batch_composition_invariance_large(gpu, ob):
