@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_encode_probe(const __grid_con
 		s_code[k] = (uint8_t)code;
 		if (k < PROBE_TILE) { bin_F[start + k] = (uint8_t)code; bin_R[len - 1 - (start + k)] = (uint8_t)(3 - code); }   // cly.c:1250-1259
 	}
-	if (start == 0 && tid < DSB_GUARD) {                          // out-of-buffer policy P3 (oracle/desamba_oracle.c)
+	if (start == 0 && tid < DSB_GUARD) {                          // out-of-buffer policy P3
 		bin_F[tid - DSB_GUARD] = (tid == DSB_GUARD - 7) ? P.hdr7[r] : (tid == DSB_GUARD - 8) ? (uint8_t)0xff : (uint8_t)0;
 		bin_R[len + tid] = 0;
 	}
