@@ -9,7 +9,7 @@
  *   writer (main)   formats the result records of each batch in input order (output_results, cly_mt.c:350-365)
  * The index is replicated per GPU, reads are sharded by batch, nothing is exchanged between GPUs.
  * Extra options: -g INT GPUs to use [all visible], -c INT contexts (batches in flight) per GPU [3], -B INT reads per batch
- * [262144], -M INT Mbases per batch [512].
+ * [262144], -M INT Mbases per batch [512], -P INT helper threads of the FASTQ reader [8 on >= 16 cores; 0 = serial reader].
  * -t is accepted and ignored (the thread pool it sized no longer exists).
  *
  * Classify_buff_pool.max_read_l (cly.c:2958) is the reference's only cross-read state; with -t 1 it is the running maximum
@@ -27,6 +27,8 @@
 #include <sys/resource.h>
 #include <zlib.h>
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 
 enum { FMT_SAM = 1, FMT_SAM_FULL = 2, FMT_DES = 3, FMT_DES_FULL = 4 };
 
@@ -34,6 +36,7 @@ typedef struct {
 	int l_min_match, n_threads, max_sec_N, fmt, min_score, n_gpus, ctx_per_gpu;
 	uint32_t batch_reads; uint64_t batch_bases;
 	FILE *out;
+	int n_parse_threads;                    /* helper threads of the FASTQ reader (0: serial reader only) */
 } opts_t;
 
 /* ---------------------------------------------------------------- batches */
@@ -62,6 +65,8 @@ typedef struct {
 	int error; char errmsg[600];
 	int n_files; char **files;
 	uint64_t total_sequences;
+	int max_ahead;                          /* batches the reader may be ahead of the writer (small until the GPUs are ready) */
+	int started; char early_msg[4096];      /* "Processing file" lines of the time before "Start classify" */
 } shared_t;
 
 typedef struct { shared_t *sh; int gpu; dsb_index *ix; dsb_ctx *ctx; } worker_t;
@@ -74,82 +79,7 @@ static void fail(shared_t *sh, const char *what, int rc)
 	pthread_mutex_unlock(&sh->mu);
 }
 
-/* ---------------------------------------------------------------- FASTQ reader (kseq_read semantics, utils.c:939-977) */
-typedef struct { gzFile fp; int fd; unsigned char *buf; int n, pos, eof; int last_char; int need_qual; } stream_t;
-#define SBUF (4 << 20)
-/* plain files are read with read(2) (zlib's transparent mode costs an extra copy of every byte); .gz through zlib */
-static inline int st_fill(stream_t *s)
-{
-	s->n = s->fp ? gzread(s->fp, s->buf, SBUF) : (int)read(s->fd, s->buf, SBUF);
-	s->pos = 0;
-	if (s->n <= 0) { s->eof = 1; s->n = 0; return -1; }
-	return 0;
-}
-static inline int st_getc(stream_t *s)
-{
-	if (s->pos >= s->n) {
-		if (s->eof || st_fill(s)) return -1;
-	}
-	return s->buf[s->pos++];
-}
-/* append bytes up to (not including) the next '\n' (or any whitespace if `word`) to *dst; returns the delimiter or -1 */
-static int st_getuntil(stream_t *s, int word, char **dst, size_t *n, size_t *m)
-{
-	for (;;) {
-		if (s->pos >= s->n) {
-			if (s->eof || st_fill(s)) return -1;
-		}
-		int i = s->pos;
-		if (word) { while (i < s->n && s->buf[i] != '\n' && s->buf[i] != ' ' && s->buf[i] != '\t' && s->buf[i] != '\r' && s->buf[i] != '\v' && s->buf[i] != '\f') i++; }
-		else { unsigned char *p = memchr(s->buf + i, '\n', s->n - i); i = p ? (int)(p - s->buf) : s->n; }
-		size_t add = i - s->pos;
-		if (dst) {
-			if (*n + add + 1 > *m) { *m = (*n + add + 1) * 2; *dst = realloc(*dst, *m); }
-			memcpy(*dst + *n, s->buf + s->pos, add); *n += add;
-		}
-		s->pos = i;
-		if (i < s->n) { s->pos++; return s->buf[i]; }
-	}
-}
-
-typedef struct { char *name, *seq, *qual; size_t n_name, m_name, n_seq, m_seq, n_qual, m_qual; } rec_t;
-/* returns seq length >= 0, -1 at end of file, -2 on a truncated quality string (kseq's error codes) */
-static long read_record(stream_t *s, rec_t *r)
-{
-	int c;
-	if (s->last_char == 0) {
-		while ((c = st_getc(s)) != -1 && c != '>' && c != '@');
-		if (c == -1) return -1;
-		s->last_char = c;
-	}
-	r->n_name = r->n_seq = r->n_qual = 0;
-	c = st_getuntil(s, 1, &r->name, &r->n_name, &r->m_name);
-	if (c == -1 && r->n_name == 0) return -1;
-	if (c != '\n' && c != -1) st_getuntil(s, 0, NULL, NULL, NULL);         /* comment */
-	while ((c = st_getc(s)) != -1 && c != '>' && c != '+' && c != '@') {
-		if (c == '\n') continue;
-		if (r->n_seq + 2 > r->m_seq) { r->m_seq = (r->n_seq + 2) * 2; r->seq = realloc(r->seq, r->m_seq); }
-		r->seq[r->n_seq++] = (char)c;
-		st_getuntil(s, 0, &r->seq, &r->n_seq, &r->m_seq);
-		while (r->n_seq && r->seq[r->n_seq - 1] == '\r') r->n_seq--;
-	}
-	s->last_char = (c == '>' || c == '@') ? c : 0;
-	if (c != '+') return (long)r->n_seq;                                     /* FASTA record */
-	st_getuntil(s, 0, NULL, NULL, NULL);                                     /* rest of the '+' line */
-	/* fast path (4-line FASTQ, quality not printed): the quality line is exactly as long as the sequence */
-	if (!s->need_qual && r->n_seq && (size_t)(s->n - s->pos) > r->n_seq && s->buf[s->pos + r->n_seq] == '\n') {
-		s->pos += (int)r->n_seq + 1; s->last_char = 0;
-		return (long)r->n_seq;
-	}
-	while (r->n_qual < r->n_seq) {
-		c = st_getuntil(s, 0, &r->qual, &r->n_qual, &r->m_qual);
-		while (r->n_qual && r->qual[r->n_qual - 1] == '\r') r->n_qual--;
-		if (c == -1) break;
-	}
-	s->last_char = 0;
-	if (r->n_qual != r->n_seq) return -2;
-	return (long)r->n_seq;
-}
+#include "fastq_reader.h"
 
 /* pinned batch buffers: cudaHostAlloc is slow (tens of ms per 100 MB), so a buffer goes to its final size in at most
  * a few steps: 32 MB, then straight to `full` (the batch limit), beyond that by doubling */
@@ -167,6 +97,82 @@ static int grow_pinned(void **p, size_t *m, size_t need, size_t keep, size_t ful
 	return 0;
 }
 
+/* one record into the batch (serial path) */
+static int slot_add(shared_t *sh, slot_t *b, const char *name, size_t n_name, const char *seq, const char *qual, size_t n_qual, size_t L)
+{
+	opts_t *o = sh->o;
+	if (grow_pinned((void **)&b->seqs, &b->m_seqs, b->n_bases + L + 16, b->n_bases, o->batch_bases + ((size_t)4 << 20)) ||
+	    grow_pinned((void **)&b->offs, &b->m_offs, ((size_t)b->n_reads + 2) * 8, ((size_t)b->n_reads + 1) * 8, ((size_t)o->batch_reads + 2) * 8)) return -1;
+	if (b->n_reads == 0) b->offs[0] = 0;
+	memcpy(b->seqs + b->n_bases, seq, L);
+	if (o->fmt == FMT_SAM_FULL) {
+		if (b->n_bases + L + 1 > b->m_quals) { b->m_quals = (b->n_bases + L + 1) * 2; b->quals = realloc(b->quals, b->m_quals); }
+		if (n_qual == L) memcpy(b->quals + b->n_bases, qual, L); else memset(b->quals + b->n_bases, '*', L);
+	}
+	if ((size_t)b->n_reads + 1 > b->m_name_off) { b->m_name_off = ((size_t)b->n_reads + 1) * 2; b->name_off = realloc(b->name_off, b->m_name_off * 4); }
+	if (b->n_names + n_name + 1 > b->m_names) { b->m_names = (b->n_names + n_name + 1) * 2; b->names = realloc(b->names, b->m_names); }
+	b->name_off[b->n_reads] = (uint32_t)b->n_names;
+	memcpy(b->names + b->n_names, name, n_name); b->names[b->n_names + n_name] = 0; b->n_names += n_name + 1;
+	b->n_bases += L; b->n_reads++; b->offs[b->n_reads] = b->n_bases;
+	if (L >= 510) b->has_long = 1; else b->has_short = 1;
+	return 0;
+}
+
+/* records [i0, i1) of an indexed block into the batch: offsets serially, bytes by the helper threads */
+typedef struct { const char *map; const fq_rec_t *r; size_t i0, i1; slot_t *b; uint32_t first_read; int quals; } copy_job_t;
+static void *copy_thread(void *a)
+{
+	copy_job_t *j = (copy_job_t *)a; slot_t *b = j->b;
+	for (size_t i = j->i0; i < j->i1; i++) {
+		const fq_rec_t *r = j->r + i;
+		const uint32_t k = j->first_read + (uint32_t)(i - j->i0);
+		memcpy(b->seqs + b->offs[k], j->map + r->seq, r->n_seq);
+		if (j->quals) memcpy(b->quals + b->offs[k], j->map + r->qual, r->n_seq);
+		char *nm = b->names + b->name_off[k];
+		memcpy(nm, j->map + r->name, r->n_name); nm[r->n_name] = 0;
+	}
+	return NULL;
+}
+static int slot_add_block(shared_t *sh, slot_t *b, const char *map, const fq_rec_t *r, size_t i0, size_t i1, int n_thr)
+{
+	opts_t *o = sh->o;
+	uint64_t bases = 0, names = 0;
+	for (size_t i = i0; i < i1; i++) { bases += r[i].n_seq; names += r[i].n_name + 1; }
+	const size_t n = i1 - i0;
+	if (grow_pinned((void **)&b->seqs, &b->m_seqs, b->n_bases + bases + 16, b->n_bases, o->batch_bases + ((size_t)4 << 20)) ||
+	    grow_pinned((void **)&b->offs, &b->m_offs, ((size_t)b->n_reads + n + 2) * 8, ((size_t)b->n_reads + 1) * 8, ((size_t)o->batch_reads + 2) * 8)) return -1;
+	if (o->fmt == FMT_SAM_FULL && b->n_bases + bases + 1 > b->m_quals) { b->m_quals = (b->n_bases + bases + 1) * 2; b->quals = realloc(b->quals, b->m_quals); }
+	if ((size_t)b->n_reads + n > b->m_name_off) { b->m_name_off = ((size_t)b->n_reads + n) * 2; b->name_off = realloc(b->name_off, b->m_name_off * 4); }
+	if (b->n_names + names > b->m_names) { b->m_names = (b->n_names + names) * 2; b->names = realloc(b->names, b->m_names); }
+	if (b->n_reads == 0) b->offs[0] = 0;
+	const uint32_t first = b->n_reads;
+	for (size_t i = i0; i < i1; i++) {
+		const uint32_t L = r[i].n_seq;
+		b->name_off[b->n_reads] = (uint32_t)b->n_names; b->n_names += r[i].n_name + 1;
+		b->n_bases += L; b->n_reads++; b->offs[b->n_reads] = b->n_bases;
+		if (L >= 510) b->has_long = 1; else b->has_short = 1;
+	}
+	if (n_thr > 64) n_thr = 64;
+	if ((size_t)n_thr > n) n_thr = (int)n;
+	if (n_thr < 1) n_thr = 1;
+	copy_job_t job[64]; pthread_t th[64];
+	/* shares of about the same number of bases */
+	size_t at = i0; uint64_t done = 0;
+	for (int t = 0; t < n_thr; t++) {
+		const uint64_t upto = bases * (uint64_t)(t + 1) / (uint64_t)n_thr;
+		size_t e = at;
+		while (e < i1 && (done < upto || t == n_thr - 1)) { done += r[e].n_seq; e++; }
+		if (t == n_thr - 1) e = i1;
+		job[t].map = map; job[t].r = r; job[t].i0 = at; job[t].i1 = e; job[t].b = b; job[t].first_read = first + (uint32_t)(at - i0); job[t].quals = (o->fmt == FMT_SAM_FULL);
+		at = e;
+	}
+	for (int t = 1; t < n_thr; t++) pthread_create(&th[t], NULL, copy_thread, &job[t]);
+	copy_thread(&job[0]);
+	for (int t = 1; t < n_thr; t++) pthread_join(th[t], NULL);
+	return 0;
+}
+
+#define FQ_BLOCK ((uint64_t)256 << 20)     /* bytes of a plain FASTQ file indexed at a time */
 static void *reader_main(void *arg)
 {
 	shared_t *sh = (shared_t *)arg; opts_t *o = sh->o;
@@ -175,16 +181,45 @@ static void *reader_main(void *arg)
 	int file_i = 0, stream_open = 0, pending = 0;      /* pending: rec holds a record not yet stored */
 	uint32_t m_bin_read = 0;                           /* running BUFF_REALLOC capacity over all reads, in input order */
 	long plen = 0;
+	/* plain 4-line FASTQ: mapped, indexed a block at a time by the helper threads (fastq_reader.h) */
+	const char *map = NULL; uint64_t map_size = 0, map_pos = 0;
+	fq_list_t lists[64]; memset(lists, 0, sizeof lists);
+	fq_rec_t *recs = NULL; size_t m_recs = 0, n_recs = 0, i_rec = 0;
+	const int n_thr = o->n_parse_threads;
 	for (;;) {
 		pthread_mutex_lock(&sh->mu);
 		slot_t *b = &sh->slot[sh->n_filled % sh->n_slots];
-		while (b->state != SLOT_FREE && !sh->error) pthread_cond_wait(&sh->cv, &sh->mu);
+		while ((b->state != SLOT_FREE || sh->n_filled - sh->n_written >= (uint64_t)sh->max_ahead) && !sh->error) pthread_cond_wait(&sh->cv, &sh->mu);
 		int err = sh->error;
 		pthread_mutex_unlock(&sh->mu);
 		if (err) break;
 		b->n_reads = 0; b->n_bases = 0; b->n_names = 0; b->has_long = b->has_short = 0; b->m_bin_read_in = m_bin_read;
 		int end_of_input = 0;
 		while (b->n_reads < o->batch_reads && b->n_bases < o->batch_bases) {
+			if (map) {
+				if (i_rec < n_recs) {                   /* as many indexed records as the batch takes */
+					size_t e = i_rec; uint32_t nr = b->n_reads; uint64_t nb = b->n_bases;
+					while (e < n_recs && nr < o->batch_reads && nb < o->batch_bases) { nb += recs[e].n_seq; nr++; e++; }
+					if (slot_add_block(sh, b, map, recs, i_rec, e, n_thr)) { fail(sh, "pinned alloc", -4); end_of_input = 1; break; }
+					for (size_t i = i_rec; i < e; i++) { const size_t L = recs[i].n_seq; if (L >= 40 && 2 * L > m_bin_read) m_bin_read = (uint32_t)(2 * L + 20); }
+					i_rec = e;
+					continue;
+				}
+				if (map_pos < map_size) {               /* next block */
+					uint64_t next = map_pos;
+					const long n = fq_index_block(map, map_size, map_pos, map_pos + FQ_BLOCK, n_thr, lists, &recs, &m_recs, &next);
+					if (n >= 0) { n_recs = (size_t)n; i_rec = 0; map_pos = next; continue; }
+					/* not strict 4-line FASTQ from here on: the serial reader takes over at the start of the block */
+					munmap((void *)map, map_size); map = NULL;
+					lseek(st.fd, (off_t)map_pos, SEEK_SET);
+					st.n = st.pos = st.eof = 0; st.last_char = 0;
+					n_recs = i_rec = 0;
+					continue;
+				}
+				munmap((void *)map, map_size); map = NULL; n_recs = i_rec = 0;
+				close(st.fd); stream_open = 0; file_i++;
+				continue;
+			}
 			if (!pending) {
 				if (!stream_open) {
 					if (file_i >= sh->n_files) { end_of_input = 1; break; }
@@ -192,34 +227,34 @@ static void *reader_main(void *arg)
 					st.fd = open(sh->files[file_i], O_RDONLY);
 					if (st.fd < 0) { fprintf(stderr, "[xzopen] fail to open file '%s'\n", sh->files[file_i]); fail(sh, "open reads", -2); end_of_input = 1; break; }
 					unsigned char magic[2] = {0, 0};
-					if (pread(st.fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+					const int got = (int)pread(st.fd, magic, 2, 0);
+					if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
 						st.fp = gzdopen(st.fd, "r");
 						if (!st.fp) { fail(sh, "gzdopen", -2); end_of_input = 1; break; }
 						gzbuffer(st.fp, 1 << 20);
 					}
 					st.need_qual = (o->fmt == FMT_SAM_FULL);
 					st.n = st.pos = st.eof = 0; st.last_char = 0; stream_open = 1;
-					fprintf(stderr, "Processing file: [%s].\n", sh->files[file_i]);
+					pthread_mutex_lock(&sh->mu);             /* (the reader starts while the index is still loading) */
+					if (sh->started) fprintf(stderr, "Processing file: [%s].\n", sh->files[file_i]);
+					else { const size_t l = strlen(sh->early_msg); snprintf(sh->early_msg + l, sizeof sh->early_msg - l, "Processing file: [%s].\n", sh->files[file_i]); }
+					pthread_mutex_unlock(&sh->mu);
+					struct stat sb;
+					if (!st.fp && n_thr > 0 && got >= 1 && magic[0] == '@' && fstat(st.fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+						void *m = mmap(NULL, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, st.fd, 0);
+						if (m != MAP_FAILED) {
+							madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
+							map = (const char *)m; map_size = (uint64_t)sb.st_size; map_pos = 0; n_recs = i_rec = 0;
+							continue;
+						}
+					}
 				}
 				plen = read_record(&st, &rec);
 				if (plen < 0) { if (st.fp) gzclose(st.fp); else close(st.fd); stream_open = 0; file_i++; continue; }   /* -1 end of file; -2 ends the file like the reference ends its run */
 				pending = 1;
 			}
-			size_t L = (size_t)plen;
-			if (grow_pinned((void **)&b->seqs, &b->m_seqs, b->n_bases + L + 16, b->n_bases, o->batch_bases + ((size_t)4 << 20)) ||
-			    grow_pinned((void **)&b->offs, &b->m_offs, ((size_t)b->n_reads + 2) * 8, ((size_t)b->n_reads + 1) * 8, ((size_t)o->batch_reads + 2) * 8)) { fail(sh, "pinned alloc", -4); end_of_input = 1; break; }
-			if (b->n_reads == 0) b->offs[0] = 0;
-			memcpy(b->seqs + b->n_bases, rec.seq, L);
-			if (o->fmt == FMT_SAM_FULL) {
-				if (b->n_bases + L + 1 > b->m_quals) { b->m_quals = (b->n_bases + L + 1) * 2; b->quals = realloc(b->quals, b->m_quals); }
-				if (rec.n_qual == L) memcpy(b->quals + b->n_bases, rec.qual, L); else memset(b->quals + b->n_bases, '*', L);
-			}
-			if ((size_t)b->n_reads + 1 > b->m_name_off) { b->m_name_off = ((size_t)b->n_reads + 1) * 2; b->name_off = realloc(b->name_off, b->m_name_off * 4); }
-			if (b->n_names + rec.n_name + 1 > b->m_names) { b->m_names = (b->n_names + rec.n_name + 1) * 2; b->names = realloc(b->names, b->m_names); }
-			b->name_off[b->n_reads] = (uint32_t)b->n_names;
-			memcpy(b->names + b->n_names, rec.name, rec.n_name); b->names[b->n_names + rec.n_name] = 0; b->n_names += rec.n_name + 1;
-			b->n_bases += L; b->n_reads++; b->offs[b->n_reads] = b->n_bases;
-			if (L >= 510) b->has_long = 1; else b->has_short = 1;
+			const size_t L = (size_t)plen;
+			if (slot_add(sh, b, rec.name, rec.n_name, rec.seq, rec.qual, rec.n_qual, L)) { fail(sh, "pinned alloc", -4); end_of_input = 1; break; }
 			if (L >= 40 && 2 * L > m_bin_read) m_bin_read = (uint32_t)(2 * L + 20);
 			pending = 0;
 		}
@@ -230,6 +265,9 @@ static void *reader_main(void *arg)
 		pthread_mutex_unlock(&sh->mu);
 		if (end_of_input) break;
 	}
+	if (map) munmap((void *)map, map_size);
+	for (int t = 0; t < 64; t++) free(lists[t].r);
+	free(recs);
 	free(st.buf); free(rec.name); free(rec.seq); free(rec.qual);
 	return NULL;
 }
@@ -349,7 +387,7 @@ static void usage(void)
 	fprintf(stderr, "    -l, INT         minimum matching length, ignored for NGS reads [170]\n    -r, INT         max Output number of secondary alignments[5]\n");
 	fprintf(stderr, "    -o, FILE        output results into file [stdout]\n    -s, INT         MIN score[64]\n");
 	fprintf(stderr, "    -f, STR         output format, one of: SAM (default), SAM_FULL, DES, DES_FULL\n");
-	fprintf(stderr, "    -g, INT         number of GPUs [all visible]\n    -c, INT         batches in flight per GPU [3]\n    -B, INT         reads per batch [262144]\n    -M, INT         Mbases per batch [512]\n\n");
+	fprintf(stderr, "    -g, INT         number of GPUs [all visible]\n    -c, INT         batches in flight per GPU [3]\n    -B, INT         reads per batch [262144]\n    -M, INT         Mbases per batch [512]\n    -P, INT         FASTQ reader threads [8 on >= 16 cores; 0: serial]\n\n");
 }
 
 static double now_s(void) { struct timeval t; gettimeofday(&t, NULL); return t.tv_sec + t.tv_usec * 1e-6; }
@@ -357,9 +395,9 @@ static double cpu_s(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); return 
 
 static int classify_main(int argc, char **argv)
 {
-	opts_t o = {170, 4, 5, FMT_SAM, 64, 0, 3, 262144, 512ull << 20, stdout};
+	opts_t o = {170, 4, 5, FMT_SAM, 64, 0, 3, 262144, 512ull << 20, stdout, -1};
 	int c;
-	while ((c = getopt(argc, argv, "ht:l:r:f:o:s:g:B:M:c:")) >= 0) {
+	while ((c = getopt(argc, argv, "ht:l:r:f:o:s:g:B:M:c:P:")) >= 0) {
 		if (c == 'h') { usage(); return 0; }
 		else if (c == 't') o.n_threads = atoi(optarg);
 		else if (c == 'l') o.l_min_match = atoi(optarg);
@@ -367,6 +405,7 @@ static int classify_main(int argc, char **argv)
 		else if (c == 'o') { o.out = fopen(optarg, "w"); if (!o.out) { fprintf(stderr, "[xopen] fail to open file '%s'\n", optarg); return 1; } }
 		else if (c == 's') o.min_score = atoi(optarg);
 		else if (c == 'g') o.n_gpus = atoi(optarg);
+		else if (c == 'P') o.n_parse_threads = atoi(optarg);
 		else if (c == 'c') o.ctx_per_gpu = atoi(optarg);
 		else if (c == 'B') o.batch_reads = (uint32_t)atol(optarg);
 		else if (c == 'M') o.batch_bases = (uint64_t)atol(optarg) << 20;
@@ -383,6 +422,16 @@ static int classify_main(int argc, char **argv)
 	fprintf(stderr, "loading index\t");
 	if (o.ctx_per_gpu < 1) o.ctx_per_gpu = 1;
 	if (o.ctx_per_gpu > 8) o.ctx_per_gpu = 8;
+	if (o.n_parse_threads < 0) { long nc = sysconf(_SC_NPROCESSORS_ONLN); o.n_parse_threads = nc >= 16 ? 8 : nc >= 8 ? 4 : nc >= 4 ? 2 : 1; }
+	if (o.n_parse_threads > 64) o.n_parse_threads = 64;
+	/* the reader starts at once: the first batches are parsed into pinned memory while the index is loaded into HBM */
+	shared_t sh; memset(&sh, 0, sizeof sh);
+	sh.o = &o; sh.n_slots = 2 * ((o.n_gpus > 0 ? o.n_gpus : 8) * o.ctx_per_gpu) + 2; sh.slot = calloc(sh.n_slots, sizeof(slot_t));
+	sh.max_ahead = 3;
+	pthread_mutex_init(&sh.mu, NULL); pthread_cond_init(&sh.cv, NULL);
+	sh.n_files = argc - optind; sh.files = argv + optind;
+	pthread_t rd;
+	pthread_create(&rd, NULL, reader_main, &sh);
 	dsb_index *gix[64];
 	int n_gpus = 0;
 	for (int g = 0; g < (o.n_gpus > 0 ? o.n_gpus : 64); g++) {
@@ -406,13 +455,13 @@ static int classify_main(int argc, char **argv)
 	const dsb_ref_info *ri = dsb_index_ref_info(w[0].ix);
 	const double t0 = now_s(), c0 = cpu_s();
 	fprintf(stderr, "Start classify\n");
-
-	shared_t sh; memset(&sh, 0, sizeof sh);
-	sh.o = &o; sh.n_slots = 2 * n_workers + 2; sh.slot = calloc(sh.n_slots, sizeof(slot_t));
-	pthread_mutex_init(&sh.mu, NULL); pthread_cond_init(&sh.cv, NULL);
-	sh.n_files = argc - optind; sh.files = argv + optind;
-	pthread_t rd, *th = calloc(n_workers, sizeof *th);
-	pthread_create(&rd, NULL, reader_main, &sh);
+	pthread_mutex_lock(&sh.mu);
+	sh.started = 1; fputs(sh.early_msg, stderr);
+	sh.max_ahead = 2 * n_workers + 2;
+	if (sh.max_ahead > sh.n_slots) sh.max_ahead = sh.n_slots;
+	pthread_cond_broadcast(&sh.cv);
+	pthread_mutex_unlock(&sh.mu);
+	pthread_t *th = calloc(n_workers, sizeof *th);
 	for (int k = 0; k < n_workers; k++) { w[k].sh = &sh; pthread_create(&th[k], NULL, worker_main, &w[k]); }
 
 	obuf_t ob = {0};

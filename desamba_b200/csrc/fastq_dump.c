@@ -1,0 +1,49 @@
+/* fastq_dump -- test tool for fastq_reader.h: prints the records of a FASTA/FASTQ file as  name \t sequence \t quality-length
+ * usage: fastq_dump serial|parallel FILE [block_bytes] [threads]   (parallel falls back to the serial reader exactly like the
+ * driver does; exit code 3 when it had to) */
+#define _GNU_SOURCE
+#include "fastq_reader.h"
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+
+static int dump_serial(int fd, uint64_t from)
+{
+	stream_t st; memset(&st, 0, sizeof st); st.buf = malloc(SBUF); st.fd = fd; st.need_qual = 1;
+	lseek(fd, (off_t)from, SEEK_SET);
+	rec_t rec; memset(&rec, 0, sizeof rec);
+	long L;
+	while ((L = read_record(&st, &rec)) >= 0) {
+		fwrite(rec.name, 1, rec.n_name, stdout); putchar('\t'); fwrite(rec.seq, 1, (size_t)L, stdout); printf("\t%zu\n", rec.n_qual);
+	}
+	return 0;
+}
+
+int main(int argc, char **argv)
+{
+	if (argc < 3) return 2;
+	int fd = open(argv[2], O_RDONLY);
+	if (fd < 0) return 2;
+	if (!strcmp(argv[1], "serial")) return dump_serial(fd, 0);
+	const uint64_t block = argc > 3 ? strtoull(argv[3], 0, 10) : (64u << 20);
+	const int thr = argc > 4 ? atoi(argv[4]) : 4;
+	struct stat sb; fstat(fd, &sb);
+	const uint64_t size = (uint64_t)sb.st_size;
+	if (size == 0) return 0;
+	const char *map = mmap(NULL, size, PROT_READ, MAP_PRIVATE, fd, 0);
+	if (map == MAP_FAILED) return dump_serial(fd, 0);
+	fq_list_t lists[64]; memset(lists, 0, sizeof lists);
+	fq_rec_t *recs = NULL; size_t m_recs = 0;
+	uint64_t pos = 0;
+	if (map[0] != '@') { dump_serial(fd, 0); return 3; }
+	while (pos < size) {
+		uint64_t next;
+		const long n = fq_index_block(map, size, pos, pos + block, thr, lists, &recs, &m_recs, &next);
+		if (n < 0) { fflush(stdout); dump_serial(fd, pos); return 3; }
+		for (long i = 0; i < n; i++) {
+			fwrite(map + recs[i].name, 1, recs[i].n_name, stdout); putchar('\t'); fwrite(map + recs[i].seq, 1, recs[i].n_seq, stdout); printf("\t%u\n", recs[i].n_seq);
+		}
+		pos = next;
+	}
+	return 0;
+}

@@ -78,6 +78,27 @@ def test_driver_sets_text(gpu, ob, demo_index, name, fmt, batch):
     assert out == gzip.open(os.path.join(GOLD, f"{name}.{fmt}.gz")).read()
 
 
+@pytest.mark.parametrize("extra", [["-P", "0"], ["-P", "3", "-B", "50"], ["-f", "SAM_FULL", "-P", "5"]])
+def test_driver_reader_modes(gpu, ob, demo_index, tmp_path, extra):
+    # serial FASTQ reader (-P 0) and the parallel indexer with other thread counts / batch sizes: same text; SAM_FULL prints
+    # the bases and qualities the reader handed on; a file that is not 4-line FASTQ half way falls back to the serial reader
+    path = _set_path(ob, "mixed")
+    want = _run_driver(["-f", "SAM_FULL" if "SAM_FULL" in extra else "SAM", "-P", "0", demo_index, path])
+    if "SAM_FULL" not in extra:
+        assert want == gzip.open(os.path.join(GOLD, "mixed.SAM.gz")).read()
+    assert _run_driver(extra + [demo_index, path]) == want
+    if extra == ["-P", "0"]:
+        txt = open(path, "rb").read()
+        recs = txt.split(b"\n@")
+        k = len(recs) // 2
+        seq = recs[k].split(b"\n")                       # wrap one record's sequence and quality over two lines each
+        seq[1] = seq[1][:7] + b"\n" + seq[1][7:]; seq[3] = seq[3][:7] + b"\n" + seq[3][7:]
+        recs[k] = b"\n".join(seq)
+        wrapped = tmp_path / "wrapped.fq"
+        wrapped.write_bytes(b"\n@".join(recs))
+        assert _run_driver(["-P", "4", demo_index, str(wrapped)]) == want
+
+
 def test_driver_options_and_gz_input(gpu, ob, demo_index, tmp_path):
     path = _set_path(ob, "long10")
     gz = tmp_path / "long10.fq.gz"
@@ -150,6 +171,47 @@ def test_very_long_reads_many_anchors(gpu, ob, oracle):
     res = ctx.classify(cat, offs)
     _assert_same(ob, res, rr_o, hits_o)
     assert res.max_read_l == mx_o
+
+
+def test_repeat_rich_reads_heavy_path(gpu, ob, oracle):
+    # tandem copies of a read segment: every scanned 9-mer of a reference window matches many read positions, so sdp_match
+    # collects thousands of candidates (candidate flushes, merge-sort ordering of > 256 matches) and the read is deferred to
+    # the CTA-per-read kernel (> 1024 matches in one extension); plus low-complexity reads that yield no seeds at all
+    dsb, ix, ctx = gpu
+    _, seqs, _ = ob.read_fastq(_set_path(ob, "long10"), 12)
+    long_ = [s for s in seqs if len(s) > 3000]
+    reads = [long_[0][200:500] * 25, long_[1][100:160] * 120, long_[2][300:1300] * 6, long_[0][:2000] + long_[0][200:500] * 15 + long_[0][2000:3000],
+             b"AC" * 3000, b"ACG" * 2000, b"A" * 5000 + long_[1][:1500], long_[3]]
+    # reads from the (TAACCC)n telomeric repeats of HHV-7 (NC_001716.2: ~143-146 kb and the terminal repeat at 1-3 kb): repeats in
+    # the reference AND the read -- the reads the bench workload defers to k_score_heavy
+    c, on = [], False
+    for l in open(ob.DEMO_FA):
+        if l.startswith(">"):
+            if on:
+                break
+            on = l[1:].split()[0] == "tid|10372|ref|NC_001716.2"
+        elif on:
+            c.append(l.strip().upper())
+    c = "".join(c).encode()
+    assert len(c) == 153080
+    rng = np.random.default_rng(5)
+
+    def mutate(seq, rate):
+        a = np.frombuffer(seq, dtype=np.uint8).copy()
+        m = rng.random(len(a)) < rate
+        a[m] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), int(m.sum()))
+        return a.tobytes()
+
+    rnd = lambda n: bytes(rng.choice(list(b"ACGT"), n).tolist())
+    reads += [rnd(80) + mutate(c[142500:147500], 0.05) + rnd(80), rnd(80) + mutate(c[800:3800], 0.08) + rnd(80), rnd(80) + mutate(c[143000:146000], 0.02) + rnd(80)]
+    cat, offs = ob.pack(reads)
+    rr_o, hits_o, mx_o = oracle.classify(cat, offs)
+    res = ctx.classify(cat, offs)
+    _assert_same(ob, res, rr_o, hits_o)
+    assert res.max_read_l == mx_o
+    assert int(rr_o["n_hit"].sum()) > 0
+    ms = ctx.kernel_ms()
+    assert ms[9] > 0.05, ms                     # k_score_heavy had work (its empty launch takes a few microseconds)
 
 
 def test_max_read_l_state(gpu, ob, oracle):

@@ -1,0 +1,90 @@
+"""The driver's FASTQ input (desamba_b200/csrc/fastq_reader.h): the parallel indexer for plain 4-line FASTQ hands on exactly the
+records of the serial kseq-style reader (kseq_read, utils.c:939-977) -- for every block size and thread count, and by falling
+back to the serial reader on anything that is not strict 4-line FASTQ."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DUMP = os.path.join(ROOT, "desamba_b200", "bin", "fastq_dump")
+
+
+def _dump(mode, path, *args):
+    r = subprocess.run([DUMP, mode, path] + [str(a) for a in args], capture_output=True)
+    assert r.returncode in (0, 3), r.stderr
+    return r.stdout, r.returncode
+
+
+def _rand_fastq(rng, n, lo, hi, qual_at=False, crlf=False, comment=False, last_newline=True):
+    out = []
+    for i in range(n):
+        L = int(rng.integers(lo, hi + 1))
+        seq = bytes(rng.choice(list(b"ACGTN"), L).tolist())
+        qual = bytes(rng.choice(list(b"@+>I5#"), L).tolist()) if qual_at else b"I" * L
+        name = b"@r%d" % i + (b" some comment\twith tabs" if comment and i % 2 else b"")
+        nl = b"\r\n" if crlf else b"\n"
+        out.append(name + nl + seq + nl + (b"+r%d" % i if i % 3 == 0 else b"+") + nl + qual + nl)
+    txt = b"".join(out)
+    return txt if last_newline else txt.rstrip(b"\r\n")
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import oracle_binding
+    oracle_binding.build()                       # builds the product too (make -C desamba_b200/csrc)
+    assert os.path.exists(DUMP)
+    return oracle_binding
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(qual_at=True), dict(crlf=True), dict(comment=True), dict(last_newline=False),
+                                dict(qual_at=True, crlf=True, comment=True, last_newline=False)])
+def test_parallel_equals_serial_on_4_line_fastq(ob, tmp_path, kw):
+    rng = np.random.default_rng(7)
+    p = str(tmp_path / "a.fq")
+    open(p, "wb").write(_rand_fastq(rng, 400, 1, 700, **kw))
+    want, _ = _dump("serial", p)
+    assert want.count(b"\n") == 400
+    for block, thr in ((1 << 26, 4), (5000, 7), (997, 3), (200, 16), (64, 2), (1, 1)):
+        got, rc = _dump("parallel", p, block, thr)
+        assert got == want, (kw, block, thr)
+        assert rc == 0, (kw, block, thr)         # handled by the parallel indexer, no fallback
+
+
+def test_long_records_span_several_shares(ob, tmp_path):
+    rng = np.random.default_rng(8)
+    p = str(tmp_path / "long.fq")
+    open(p, "wb").write(_rand_fastq(rng, 30, 20000, 90000, qual_at=True))
+    want, _ = _dump("serial", p)
+    for block, thr in ((1 << 20, 8), (30000, 8), (100000, 64)):
+        got, rc = _dump("parallel", p, block, thr)
+        assert got == want and rc == 0
+
+
+@pytest.mark.parametrize("name,text", [
+    ("fasta", b">a\nACGT\nACGT\n>b desc\nGGGG\n"),
+    ("wrapped", b"@a\nACGT\nACGT\n+\nIIII\nIIII\n@b\nAC\n+\nII\n"),
+    ("truncated_quality", b"@a\nACGTACGT\n+\nIIII\n"),
+    ("cut_off", b"@a\nACGT\n+\nIIII\n@b\nACG"),
+    ("junk_between", b"@a\nACGT\n+\nIIII\n\n\n@b\nAC\n+\nII\n"),
+    ("leading_junk", b"\n\n@a\nACGT\n+\nIIII\n"),
+    ("empty_sequence", b"@a\n\n+\n\n@b\nAC\n+\nII\n"),
+    ("fasta_after_fastq", b"@a\nACGT\n+\nIIII\n>b\nACGT\n"),
+    ("empty", b""),
+])
+def test_everything_else_falls_back_to_the_serial_reader(ob, tmp_path, name, text):
+    p = str(tmp_path / (name + ".fq"))
+    open(p, "wb").write(text)
+    want, _ = _dump("serial", p)
+    for block, thr in ((1 << 20, 4), (8, 3)):
+        got, rc = _dump("parallel", p, block, thr)
+        assert got == want, (name, block, thr)
+
+
+def test_demo_and_simulated_sets(ob):
+    ob.ensure_demo_index()
+    for path in (ob.DEMO_FQ, ob.sim_set("short1", "short", 5000, 0.01, 20261022), ob.sim_set("long10", "long", 300, 0.10, 20261020)):
+        want, _ = _dump("serial", path)
+        got, rc = _dump("parallel", path, 1 << 18, 8)
+        assert got == want and rc == 0
