@@ -424,6 +424,9 @@ static int classify_main(int argc, char **argv)
 	if (o.ctx_per_gpu > 8) o.ctx_per_gpu = 8;
 	if (o.n_parse_threads < 0) { long nc = sysconf(_SC_NPROCESSORS_ONLN); o.n_parse_threads = nc >= 16 ? 8 : nc >= 8 ? 4 : nc >= 4 ? 2 : 1; }
 	if (o.n_parse_threads > 64) o.n_parse_threads = 64;
+	const int verbose = getenv("DSB_VERBOSE") != NULL;
+	const double t_start = now_s();
+	#define STAMP(what) do { if (verbose) fprintf(stderr, "[deSAMBA-b200] %-34s at %7.3f s\n", what, now_s() - t_start); } while (0)
 	/* the reader starts at once: the first batches are parsed into pinned memory while the index is loaded into HBM */
 	shared_t sh; memset(&sh, 0, sizeof sh);
 	sh.o = &o; sh.n_slots = 2 * ((o.n_gpus > 0 ? o.n_gpus : 8) * o.ctx_per_gpu) + 2; sh.slot = calloc(sh.n_slots, sizeof(slot_t));
@@ -443,6 +446,7 @@ static int classify_main(int argc, char **argv)
 		}
 		gix[g] = ix; n_gpus++;
 	}
+	STAMP("index resident in HBM");
 	/* several contexts (streams) per GPU: the expensive tail reads of one batch overlap the next batch */
 	const int n_workers = n_gpus * o.ctx_per_gpu;
 	worker_t *w = calloc(n_workers, sizeof *w);
@@ -452,6 +456,7 @@ static int classify_main(int argc, char **argv)
 		w[k].gpu = k % n_gpus; w[k].ix = gix[k % n_gpus];
 		if (dsb_ctx_create(w[k].ix, &dop, &w[k].ctx) != DSB_OK) { fprintf(stderr, "\n[deSAMBA-b200] %s\n", dsb_last_error()); return 1; }
 	}
+	STAMP("contexts created");
 	const dsb_ref_info *ri = dsb_index_ref_info(w[0].ix);
 	const double t0 = now_s(), c0 = cpu_s();
 	fprintf(stderr, "Start classify\n");
@@ -486,6 +491,7 @@ static int classify_main(int argc, char **argv)
 	}
 	pthread_join(rd, NULL);
 	for (int k = 0; k < n_workers; k++) pthread_join(th[k], NULL);
+	STAMP("last record written");
 	fflush(o.out);
 	if (o.out != stdout) fclose(o.out);
 	if (sh.error) { fprintf(stderr, "[deSAMBA-b200] error %d: %s\n", sh.error, sh.errmsg); return 1; }
@@ -495,6 +501,7 @@ static int classify_main(int argc, char **argv)
 	fprintf(stderr, "GPUs: %d (%d contexts each)\n", n_gpus, o.ctx_per_gpu);
 	for (int k = 0; k < n_workers; k++) dsb_ctx_free(w[k].ctx);
 	for (int g = 0; g < n_gpus; g++) dsb_index_free(gix[g]);
+	STAMP("device memory released");
 	return 0;
 }
 

@@ -82,8 +82,15 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_encode_probe(const __grid_con
 		uint32_t t0f = 0, t0r = 0, ef = 0, er = 0;
 		if (ok) {
 			const uint64_t hf = dsb_hash64_1(km) & mask, hr = dsb_hash64_1(kr) & mask;
-			const uint32_t bf = __ldg(P.ix.ek0 + (hf >> 3)), br = __ldg(P.ix.ek0 + (hr >> 3));
-			t0f = (bf >> (7 - (hf & 7))) & 1; t0r = (br >> (7 - (hr & 7))) & 1;
+			if (P.ix.ek0_sum) {                            // summary bit (L2) first; the table byte only where it is set
+				const uint64_t yf = hf >> 3, yr = hr >> 3;
+				const uint32_t sf = (__ldg(P.ix.ek0_sum + (yf >> 5)) >> (yf & 31)) & 1, sr = (__ldg(P.ix.ek0_sum + (yr >> 5)) >> (yr & 31)) & 1;
+				if (sf) t0f = (__ldg(P.ix.ek0 + yf) >> (7 - (hf & 7))) & 1;
+				if (sr) t0r = (__ldg(P.ix.ek0 + yr) >> (7 - (hr & 7))) & 1;
+			} else {
+				const uint32_t bf = __ldg(P.ix.ek0 + (hf >> 3)), br = __ldg(P.ix.ek0 + (hr >> 3));
+				t0f = (bf >> (7 - (hf & 7))) & 1; t0r = (br >> (7 - (hr & 7))) & 1;
+			}
 			if (t0f) { const uint64_t h2 = dsb_hash64_2(km) & mask; ef = (__ldg(P.ix.ek1 + (h2 >> 3)) >> (7 - (h2 & 7))) & 1; }
 			if (t0r) { const uint64_t h2 = dsb_hash64_2(kr) & mask; er = (__ldg(P.ix.ek1 + (h2 >> 3)) >> (7 - (h2 & 7))) & 1; }
 		}

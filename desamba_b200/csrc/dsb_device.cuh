@@ -42,6 +42,7 @@ struct DevIndex {
 	uint64_t        ref_bin_n;  // bytes in ref_bin; 1 KiB of zero slack follows, anything further reads as base 0
 	const ulonglong2 *ref_info; // {seq_l, seq_offset}, idx.h:13-17
 	const uint8_t  *ek0, *ek1;  // exist-k-mer bit tables, MSB-first, idx.c:1018-1021
+	const uint32_t *ek0_sum;    // one bit per BYTE of ek0 (byte != 0), or null: 1/8 of the table, L2-resident for small indexes
 	uint64_t        ek_mask;
 	int             l_ek;
 	int             single_base_max;

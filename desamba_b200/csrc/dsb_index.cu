@@ -17,6 +17,47 @@ void dsb_set_error(const char *fmt, ...)
 extern "C" const char *dsb_last_error(void) { return g_err; }
 extern "C" const char *dsb_version(void) { return "desamba_b200 0.1 (sm_100a)"; }
 
+// FM-index re-cut (see dsb_index_load): thread b turns block b (u64 cnt[5] + 256 nibble symbols) into lines 2b and 2b+1
+__global__ void __launch_bounds__(128) k_recut_fm(const uint8_t *blocks, uint64_t nb, uint8_t *lines)
+{
+	const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nb) return;
+	const uint8_t *src = blocks + b * 168;
+	uint64_t cnt[5];
+	for (int k = 0; k < 5; k++) cnt[k] = ((const uint64_t *)src)[k];
+	for (int half = 0; half < 2; half++) {
+		uint64_t *l = (uint64_t *)(lines + (2 * b + half) * 128);
+		const uint8_t *nib = src + 40 + 64 * half;
+		for (int k = 0; k < 5; k++) l[k] = cnt[k];
+		uint64_t pl[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+		for (int i = 0; i < 128; i++) {
+			uint32_t v = (nib[i >> 1] >> ((i & 1) << 2)) & 0xf;
+			if (v < 5) cnt[v]++;
+			if (v > 5) v = 7;                                          // padding never equals a countable symbol
+			for (int k = 0; k < 3; k++) if ((v >> k) & 1) pl[k][i >> 6] |= 1ull << (i & 63);
+		}
+		l[6] = pl[0][0]; l[7] = pl[0][1]; l[8] = pl[1][0]; l[9] = pl[1][1]; l[10] = pl[2][0]; l[11] = pl[2][1];   // bytes 48 / 64 / 80
+	}
+	if (b == nb - 1) {                                                 // trailing line: the totals, every symbol = padding
+		uint64_t *l = (uint64_t *)(lines + 2 * nb * 128);
+		for (int k = 0; k < 5; k++) l[k] = cnt[k];
+		for (int k = 6; k < 12; k++) l[k] = ~0ull;
+	}
+}
+
+// summary of a bit table: bit j of word w = (byte 32 w + j of the table != 0)
+__global__ void __launch_bounds__(256) k_byte_summary(const uint8_t *table, uint64_t n_words, uint32_t *sum)
+{
+	const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= n_words) return;
+	const uint4 a = ((const uint4 *)table)[2 * w], b = ((const uint4 *)table)[2 * w + 1];
+	const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+	uint32_t m = 0;
+	for (int i = 0; i < 8; i++)
+		for (int k = 0; k < 4; k++) if ((v[i] >> (8 * k)) & 0xff) m |= 1u << (4 * i + k);
+	sum[w] = m;
+}
+
 namespace {
 
 struct HostFile {
@@ -88,43 +129,25 @@ extern "C" int dsb_index_load(const char *dir, int device, dsb_index **out)
 			memcpy(ix->dev.rank, rank, sizeof rank);
 			const uint64_t nb = byteLen / 168;
 			ix->bwt_len_blocks = nb;
-			// re-cut: 168-B blocks of 256 nibble symbols -> 128-B lines of 128 symbols as three bit-planes (dsb_device.cuh),
-			// +1 trailing line holding the totals so that occ(len_bwt, c) is defined when len_bwt % 256 == 0 (the reference
-			// reads past its array there)
+			// re-cut ON THE GPU: 168-B blocks of 256 nibble symbols -> 128-B lines of 128 symbols as three bit-planes
+			// (dsb_device.cuh), +1 trailing line holding the totals so that occ(len_bwt, c) is defined when len_bwt % 256 == 0
+			// (the reference reads past its array there).  One thread per block; a host loop took ~10 ns per symbol, which is
+			// half a minute for a bacteria-scale index.
 			const uint64_t n_lines = nb * 2 + 1;
-			std::vector<uint8_t> lines(n_lines * 128, 0);
-			uint64_t tot[5] = {0, 0, 0, 0, 0};
-			for (uint64_t b = 0; b < nb; b++) {
-				const uint8_t *src = blocks.data() + b * 168;
-				uint64_t cnt[5];
-				memcpy(cnt, src, 40);
-				for (int half = 0; half < 2; half++) {
-					uint8_t *l = lines.data() + (2 * b + half) * 128;
-					const uint8_t *nib = src + 40 + 64 * half;
-					memcpy(l, cnt, 40);
-					uint64_t pl[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-					for (int i = 0; i < 128; i++) {
-						uint8_t v = (nib[i >> 1] >> ((i & 1) << 2)) & 0xf;
-						if (v < 5) cnt[v]++;
-						if (v > 5) v = 7;                                  // padding never equals a countable symbol
-						for (int k = 0; k < 3; k++) if ((v >> k) & 1) pl[k][i >> 6] |= 1ull << (i & 63);
-					}
-					memcpy(l + 48, pl[0], 16); memcpy(l + 64, pl[1], 16); memcpy(l + 80, pl[2], 16);
-				}
-				memcpy(tot, cnt, 40);
-			}
-			{
-				uint8_t *l = lines.data() + (n_lines - 1) * 128;
-				memcpy(l, tot, 40);
-				memset(l + 48, 0xff, 48);
-			}
-			lap("re-cut FM blocks (host)");
+			void *d_blocks = nullptr, *d = nullptr;
+			DSB_CUDA(cudaMalloc(&d_blocks, byteLen + 16));
+			DSB_CUDA(cudaMemcpy(d_blocks, blocks.data(), byteLen, cudaMemcpyHostToDevice));
 			blocks.clear(); blocks.shrink_to_fit();
-			void *d = nullptr;
-			if ((rc = upload(ix, lines.data(), lines.size(), 128, &d)) != DSB_OK) break;
+			DSB_CUDA(cudaMalloc(&d, n_lines * 128 + 128 + 16));
+			ix->allocs.push_back(d);
+			ix->hbm_bytes += n_lines * 128 + 128 + 16;
+			DSB_CUDA(cudaMemset(d, 0, n_lines * 128 + 128 + 16));
+			k_recut_fm<<<(unsigned)((nb + 127) / 128), 128>>>((const uint8_t *)d_blocks, nb, (uint8_t *)d);
+			DSB_CUDA(cudaGetLastError());
+			DSB_CUDA(cudaDeviceSynchronize());
+			DSB_CUDA(cudaFree(d_blocks));
 			ix->dev.occ = (const uint8_t *)d; ix->dev.n_lines = n_lines;
-			lines.clear(); lines.shrink_to_fit();
-			lap("upload FM lines");
+			lap("upload + re-cut FM blocks (GPU)");
 			const uint64_t nh = (1ull << 26) + 1;
 			std::vector<uint64_t> hidx(nh);
 			if (!hf.rd(hidx.data(), nh * 8)) { dsb_set_error("short read %s (prefix table)", hf.path.c_str()); rc = DSB_E_IO; break; }
@@ -158,6 +181,19 @@ extern "C" int dsb_index_load(const char *dir, int device, dsb_index **out)
 		}
 		{ uint64_t n = ix->ek_size; if ((rc = load_array(ix, dir, ".exk0", 1, false, &n, 0, &d)) != DSB_OK) break; ix->dev.ek0 = (const uint8_t *)d; }
 		{ uint64_t n = ix->ek_size; if ((rc = load_array(ix, dir, ".exk1", 1, false, &n, 0, &d)) != DSB_OK) break; ix->dev.ek1 = (const uint8_t *)d; }
+		// A sparse table 0 (viral-scale index: 1 % of the bits, 8 % of the bytes set) gets a summary with one bit per byte: it
+		// stays in L2 and answers most probes without a DRAM access (k_encode_probe is DRAM-bound on these probes).
+		ix->dev.ek0_sum = nullptr;
+		if (ix->ek_size <= (1ull << 28) && ix->ek_size % 32 == 0) {
+			void *ds = nullptr;
+			DSB_CUDA(cudaMalloc(&ds, ix->ek_size / 8 + 16));
+			ix->allocs.push_back(ds);
+			ix->hbm_bytes += ix->ek_size / 8 + 16;
+			k_byte_summary<<<(unsigned)((ix->ek_size / 32 + 255) / 256), 256>>>(ix->dev.ek0, ix->ek_size / 32, (uint32_t *)ds);
+			DSB_CUDA(cudaGetLastError());
+			DSB_CUDA(cudaDeviceSynchronize());
+			ix->dev.ek0_sum = (const uint32_t *)ds;
+		}
 		lap("exist k-mer tables");
 		// ---- .unv + fabricated sentinel (idx.c:1123-1129)
 		{
