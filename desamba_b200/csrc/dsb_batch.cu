@@ -17,7 +17,9 @@
 #ifndef CLASSIFY_WARPS_PER_BLOCK
 #define CLASSIFY_WARPS_PER_BLOCK 2      // small blocks release their SM share early in the tail of a launch (batches in flight overlap better)
 #endif
+#ifndef HEAVY_BLOCKS
 #define HEAVY_BLOCKS 24               // CTAs of k_score_heavy (one heavy read at a time each; a handful of reads per batch)
+#endif
 
 static inline uint32_t bits_words(uint32_t len) { return (len + 31) / 32 + 1; }
 static inline uint32_t seed_slots(uint32_t len) { return len / 2 + 2; }

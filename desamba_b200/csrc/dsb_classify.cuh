@@ -759,7 +759,9 @@ __device__ __forceinline__ void dp_eval(const int KIND, const DevSms &c, const D
 
 // Heavy reads (repeats: thousands of matches per window) are scored by k_score_heavy with a whole CTA: warp 0 runs the
 // read, the other warps only help with phase (A) below -- each takes a contiguous range of the earlier matches.
+#ifndef TEAM_WARPS
 #define TEAM_WARPS 32
+#endif
 #define TEAM_MIN_FIRST 128
 struct DpTeam {
 	int cmd;                          // >= 0: job posted, < 0: exit
