@@ -763,12 +763,11 @@ __device__ __forceinline__ void dp_eval(const int KIND, const DevSms &c, const D
 #define TEAM_WARPS 32
 #endif
 #define TEAM_MIN_FIRST 128
-#define TEAM_PRE 64                 // predecessors nearest to the block that warp 0 takes before the team is called
 struct DpTeam {
 	int cmd;                          // >= 0: job posted, < 0: exit
 	int kind; uint32_t first, nb;
 	const DevSms *sms;
-	DevSms item[32]; int stopped0[32]; int floor[32];
+	DevSms item[32]; int stopped0[32];
 	int best[TEAM_WARPS][32]; int brk[TEAM_WARPS][32];
 	uint4 tile[TEAM_WARPS][32];       // predecessor tile of dp_range, one per warp
 };
@@ -776,41 +775,25 @@ struct DpTeam {
 // phase (A) over the predecessors [lo, hi), walked downwards: best candidate per lane and whether the lane's walk hit its break.
 // The predecessors are fetched 32 at a time (one coalesced 512-byte request, the next tile already in flight), parked in a
 // shared-memory tile and read back by all lanes as broadcasts, highest index first.
-// A tile is SKIPPED when it can change nothing for any lane: no candidate from it can beat what the lane already has
-// (candidate <= predecessor score + own length: the indel and overlap terms only subtract) and none of its entries can
-// trigger the lane's break (by the tile's smallest / largest target position).  Scores grow along a repeat, so in windows
-// with thousands of matches only the nearest tiles are evaluated.  `floor` = a score the lane is already known to reach
-// from elsewhere (team mode: the share nearest to the block); it only widens the skip test, `best` stays exact.
-__device__ __noinline__ void dp_range(const int KIND, const DevSms *sms, int lo, int hi, const DevSms &my, bool stopped, int &best, bool &brk_out, uint32_t a_tile, int floor)
+__device__ __noinline__ void dp_range(const int KIND, const DevSms *sms, int lo, int hi, const DevSms &my, bool stopped, int &best, bool &brk_out, uint32_t a_tile)
 {
 	const int lane = lane_id();
 	int top = hi - 1;                                    // tile = entries top, top-1, ..., top-31 (lane l holds entry top - l)
 	uint4 cur = make_uint4(0, 0, 0, 0);
 	if (top - lane >= lo) cur = *(const uint4 *)(sms + top - lane);
-	const uint32_t brk_ref = (KIND == DP_LEFT) ? (my.t_pos + my.len - MAX_sms_overlap + S_A_KEMR_L - 1) : (my.t_pos + MAX_sms_overlap);   // min_pre_t / max_t of dp_eval
 	while (top >= lo) {
 		if (__all_sync(DSB_FULL, stopped)) break;                                  // (also: every lane is done with the previous tile)
+		const uint32_t a_buf = a_tile;
+		asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a_buf + 16 * lane), "r"(cur.x), "r"(cur.y), "r"(cur.z), "r"(cur.w) : "memory");
 		uint4 nxt = make_uint4(0, 0, 0, 0);
 		if (top - 32 - lane >= lo) nxt = *(const uint4 *)(sms + top - 32 - lane);
-		{
-			const bool have = top - lane >= lo;
-			const int t_score = __reduce_max_sync(DSB_FULL, have ? (int)cur.w : INT_MIN);
-			const uint32_t t_min = __reduce_min_sync(DSB_FULL, have ? cur.x : 0xffffffffu), t_max = __reduce_max_sync(DSB_FULL, have ? cur.x : 0u);
-			bool can_skip = stopped;
-			if (!stopped) {
-				const bool no_brk = (KIND == DP_MIDDLE) || ((KIND == DP_RIGHT) ? !(t_min + 600 < brk_ref) : !(brk_ref + 600 < t_max));
-				can_skip = no_brk && (int)((uint32_t)t_score + my.len) <= DSB_MAX(best, floor);
-			}
-			if (__all_sync(DSB_FULL, can_skip)) { cur = nxt; top -= 32; continue; }
-		}
-		asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a_tile + 16 * lane), "r"(cur.x), "r"(cur.y), "r"(cur.z), "r"(cur.w) : "memory");
 		__syncwarp();
 		const int n_here = min(32, top - lo + 1);
 		if (!stopped) {
 			#pragma unroll 2
 			for (int k = 0; k < n_here; k++) {
 				DevSms p;
-				asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(p.t_pos), "=r"(p.q_pos), "=r"(p.len), "=r"(p.score) : "r"(a_tile + 16 * k) : "memory");
+				asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(p.t_pos), "=r"(p.q_pos), "=r"(p.len), "=r"(p.score) : "r"(a_buf + 16 * k) : "memory");
 				bool pass, brk, has; int cand;
 				dp_eval(KIND, my, p, pass, brk, has, cand);
 				if (brk) { stopped = true; brk_out = true; break; }
@@ -823,14 +806,14 @@ __device__ __noinline__ void dp_range(const int KIND, const DevSms *sms, int lo,
 }
 
 __device__ __forceinline__ void dp_team_range(DpTeam *T, int w)
-{   // the share of warp w (0 = the range nearest to the block) of the posted job over the predecessors [0, T->first)
+{   // the share of warp w (0 = the range nearest to the block) of the posted job
 	const int lane = lane_id();
 	const int first = (int)T->first, chunk = (first + TEAM_WARPS - 1) / TEAM_WARPS;
 	const int hi = first - w * chunk, lo = max(0, hi - chunk);
 	const DevSms my = T->item[lane];
 	int best = INT_MIN; bool brk = false;
 	const bool stopped = T->stopped0[lane] != 0;
-	if (hi > 0) dp_range(T->kind, T->sms, lo, hi, my, stopped, best, brk, smem_addr(T->tile[w]), T->floor[lane]);
+	if (hi > 0) dp_range(T->kind, T->sms, lo, hi, my, stopped, best, brk, smem_addr(T->tile[w]));
 	T->best[w][lane] = best; T->brk[w][lane] = brk ? 1 : 0;
 }
 
@@ -867,22 +850,17 @@ __device__ __noinline__ int dp_block(const int KIND, const DevSms *sms, uint32_t
 	int best = (int)my.len;
 	const bool stopped = !mine || stop_at >= 0;
 	if (team && first >= TEAM_MIN_FIRST) {
-		// the nearest TEAM_PRE predecessors first, by this warp alone: what a lane reaches there is the floor the whole team
-		// prunes with (and a lane that hits its break there needs nothing from further back)
-		bool brk0 = false;
-		const int pre_lo = (int)first - TEAM_PRE;
-		dp_range(KIND, sms, pre_lo, (int)first, my, stopped, best, brk0, a_tile, INT_MIN);
-		team->item[lane] = my; team->stopped0[lane] = (stopped || brk0) ? 1 : 0; team->floor[lane] = best;
-		if (lane == 0) { team->kind = KIND; team->first = (uint32_t)pre_lo; team->nb = nb; team->sms = sms; team->cmd = 1; }
+		team->item[lane] = my; team->stopped0[lane] = stopped ? 1 : 0;
+		if (lane == 0) { team->kind = KIND; team->first = first; team->nb = nb; team->sms = sms; team->cmd = 1; }
 		__syncthreads();                                 // job posted: the helper warps wake up
 		dp_team_range(team, 0);
 		__syncthreads();                                 // results ready
-		if (!stopped && !brk0)
+		if (!stopped)
 			for (int w = 0; w < TEAM_WARPS; w++) { best = DSB_MAX(best, team->best[w][lane]); if (team->brk[w][lane]) break; }
 		__syncwarp();
 	} else {
 		bool brk = false;
-		dp_range(KIND, sms, 0, (int)first, my, stopped, best, brk, a_tile, INT_MIN);
+		dp_range(KIND, sms, 0, (int)first, my, stopped, best, brk, a_tile);
 	}
 	// (B) predecessors inside the block, in order: match j needs the final scores of the matches before it
 	int my_score = best;
