@@ -390,6 +390,17 @@ static void usage(void)
 	fprintf(stderr, "    -g, INT         number of GPUs [all visible]\n    -c, INT         batches in flight per GPU [3]\n    -B, INT         reads per batch [262144]\n    -M, INT         Mbases per batch [512]\n    -P, INT         FASTQ reader threads [8 on >= 16 cores; 0: serial]\n\n");
 }
 
+typedef struct { const opts_t *o; const dsb_ref_info *ri; slot_t *b; uint32_t r0, r1; obuf_t ob; } fmt_job_t;
+static void *fmt_thread(void *a)
+{
+	fmt_job_t *j = (fmt_job_t *)a; slot_t *b = j->b;
+	for (uint32_t r = j->r0; r < j->r1; r++) {
+		const uint32_t L = (uint32_t)(b->offs[r + 1] - b->offs[r]);
+		format_read(&j->ob, j->o, j->ri, b->rr + r, b->hits, b->names + b->name_off[r], b->seqs + b->offs[r], b->quals ? b->quals + b->offs[r] : NULL, L);
+	}
+	return NULL;
+}
+
 static double now_s(void) { struct timeval t; gettimeofday(&t, NULL); return t.tv_sec + t.tv_usec * 1e-6; }
 static double cpu_s(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); return r.ru_utime.tv_sec + r.ru_stime.tv_sec + 1e-6 * (r.ru_utime.tv_usec + r.ru_stime.tv_usec); }
 
@@ -469,6 +480,9 @@ static int classify_main(int argc, char **argv)
 	pthread_t *th = calloc(n_workers, sizeof *th);
 	for (int k = 0; k < n_workers; k++) { w[k].sh = &sh; pthread_create(&th[k], NULL, worker_main, &w[k]); }
 
+	/* the text of a batch is formatted by helper threads (contiguous shares of the batch's reads, written in order) */
+	const int n_fmt = o.n_parse_threads > 1 ? (o.n_parse_threads > 16 ? 16 : o.n_parse_threads) : 1;
+	fmt_job_t fj[16]; memset(fj, 0, sizeof fj);
 	obuf_t ob = {0};
 	for (;;) {
 		pthread_mutex_lock(&sh.mu);
@@ -477,13 +491,25 @@ static int classify_main(int argc, char **argv)
 		const int stop = sh.error || !(b->state == SLOT_DONE && b->seq_no == sh.n_written);
 		pthread_mutex_unlock(&sh.mu);
 		if (stop) break;
-		ob.n = 0;
-		for (uint32_t r = 0; r < b->n_reads; r++) {
-			const uint32_t L = (uint32_t)(b->offs[r + 1] - b->offs[r]);
-			format_read(&ob, &o, ri, b->rr + r, b->hits, b->names + b->name_off[r], b->seqs + b->offs[r], b->quals ? b->quals + b->offs[r] : NULL, L);
-			if (ob.n > (8u << 20)) { fwrite(ob.s, 1, ob.n, o.out); ob.n = 0; }
+		if (n_fmt > 1 && b->n_reads >= 4096) {
+			pthread_t ft[16];
+			for (int t = 0; t < n_fmt; t++) {
+				fj[t].o = &o; fj[t].ri = ri; fj[t].b = b; fj[t].ob.n = 0;
+				fj[t].r0 = (uint32_t)((uint64_t)b->n_reads * t / n_fmt); fj[t].r1 = (uint32_t)((uint64_t)b->n_reads * (t + 1) / n_fmt);
+			}
+			for (int t = 1; t < n_fmt; t++) pthread_create(&ft[t], NULL, fmt_thread, &fj[t]);
+			fmt_thread(&fj[0]);
+			for (int t = 1; t < n_fmt; t++) pthread_join(ft[t], NULL);
+			for (int t = 0; t < n_fmt; t++) fwrite(fj[t].ob.s, 1, fj[t].ob.n, o.out);
+		} else {
+			ob.n = 0;
+			for (uint32_t r = 0; r < b->n_reads; r++) {
+				const uint32_t L = (uint32_t)(b->offs[r + 1] - b->offs[r]);
+				format_read(&ob, &o, ri, b->rr + r, b->hits, b->names + b->name_off[r], b->seqs + b->offs[r], b->quals ? b->quals + b->offs[r] : NULL, L);
+				if (ob.n > (8u << 20)) { fwrite(ob.s, 1, ob.n, o.out); ob.n = 0; }
+			}
+			fwrite(ob.s, 1, ob.n, o.out);
 		}
-		fwrite(ob.s, 1, ob.n, o.out);
 		pthread_mutex_lock(&sh.mu);
 		b->state = SLOT_FREE; sh.n_written++;
 		pthread_cond_broadcast(&sh.cv);
