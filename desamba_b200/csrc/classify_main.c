@@ -27,7 +27,6 @@
 #include <sys/resource.h>
 #include <zlib.h>
 #include <fcntl.h>
-#include <sys/mman.h>
 #include <sys/stat.h>
 
 enum { FMT_SAM = 1, FMT_SAM_FULL = 2, FMT_DES = 3, FMT_DES_FULL = 4 };
@@ -65,11 +64,13 @@ typedef struct {
 	int error; char errmsg[600];
 	int n_files; char **files;
 	uint64_t total_sequences;
+	double t_reader_wait, t_reader_work, t_worker_call, t_worker_wait, t_writer_wait, t_writer_fmt;   /* DSB_VERBOSE: where the host time goes */
 	int max_ahead;                          /* batches the reader may be ahead of the writer (small until the GPUs are ready) */
 	int started; char early_msg[4096];      /* "Processing file" lines of the time before "Start classify" */
 } shared_t;
 
 typedef struct { shared_t *sh; int gpu; dsb_index *ix; dsb_ctx *ctx; } worker_t;
+static double now_s(void);
 
 static void fail(shared_t *sh, const char *what, int rc)
 {
@@ -81,15 +82,14 @@ static void fail(shared_t *sh, const char *what, int rc)
 
 #include "fastq_reader.h"
 
-/* pinned batch buffers: cudaHostAlloc is slow (tens of ms per 100 MB), so a buffer goes to its final size in at most
- * a few steps: 32 MB, then straight to `full` (the batch limit), beyond that by doubling */
+/* pinned batch buffers: cudaHostAlloc is slow (tens of ms per 100 MB), so a buffer grows by doubling from 32 MB, up to `full`
+ * (the batch limit) -- a batch of short reads never pins the 512 MB a batch of long reads needs */
 static int grow_pinned(void **p, size_t *m, size_t need, size_t keep, size_t full)
 {
 	if (need <= *m) return 0;
 	size_t nm = (size_t)32 << 20;
-	if (nm > full) nm = full;
-	if (need > nm) nm = full;
 	while (need > nm) nm *= 2;
+	if (nm > full && need <= full) nm = full;
 	void *np = NULL;
 	if (dsb_host_alloc(nm, &np) != DSB_OK) return -1;
 	if (*p) { memcpy(np, *p, keep); dsb_host_free(*p); }
@@ -173,6 +173,7 @@ static int slot_add_block(shared_t *sh, slot_t *b, const char *map, const fq_rec
 }
 
 #define FQ_BLOCK ((uint64_t)256 << 20)     /* bytes of a plain FASTQ file indexed at a time */
+#define FQ_MARGIN ((uint64_t)16 << 20)     /* read beyond the block: the records that start in it must be complete */
 static void *reader_main(void *arg)
 {
 	shared_t *sh = (shared_t *)arg; opts_t *o = sh->o;
@@ -181,18 +182,22 @@ static void *reader_main(void *arg)
 	int file_i = 0, stream_open = 0, pending = 0;      /* pending: rec holds a record not yet stored */
 	uint32_t m_bin_read = 0;                           /* running BUFF_REALLOC capacity over all reads, in input order */
 	long plen = 0;
-	/* plain 4-line FASTQ: mapped, indexed a block at a time by the helper threads (fastq_reader.h) */
-	const char *map = NULL; uint64_t map_size = 0, map_pos = 0;
+	/* plain 4-line FASTQ: read and indexed a block at a time by the helper threads (fastq_reader.h) */
+	const char *map = NULL; uint64_t map_size = 0, map_pos = 0;           /* map = blockbuf - (offset of the block): file offsets index it */
+	char *blockbuf = NULL;
 	fq_list_t lists[64]; memset(lists, 0, sizeof lists);
 	fq_rec_t *recs = NULL; size_t m_recs = 0, n_recs = 0, i_rec = 0;
 	const int n_thr = o->n_parse_threads;
 	for (;;) {
+		const double tw0 = now_s();
 		pthread_mutex_lock(&sh->mu);
 		slot_t *b = &sh->slot[sh->n_filled % sh->n_slots];
 		while ((b->state != SLOT_FREE || sh->n_filled - sh->n_written >= (uint64_t)sh->max_ahead) && !sh->error) pthread_cond_wait(&sh->cv, &sh->mu);
 		int err = sh->error;
 		pthread_mutex_unlock(&sh->mu);
 		if (err) break;
+		const double tw1 = now_s();
+		sh->t_reader_wait += tw1 - tw0;
 		b->n_reads = 0; b->n_bases = 0; b->n_names = 0; b->has_long = b->has_short = 0; b->m_bin_read_in = m_bin_read;
 		int end_of_input = 0;
 		while (b->n_reads < o->batch_reads && b->n_bases < o->batch_bases) {
@@ -207,16 +212,21 @@ static void *reader_main(void *arg)
 				}
 				if (map_pos < map_size) {               /* next block */
 					uint64_t next = map_pos;
-					const long n = fq_index_block(map, map_size, map_pos, map_pos + FQ_BLOCK, n_thr, lists, &recs, &m_recs, &next);
+					const uint64_t len = (map_size - map_pos < FQ_BLOCK + FQ_MARGIN) ? map_size - map_pos : FQ_BLOCK + FQ_MARGIN;
+					long n = -1;
+					if (fq_read_block(st.fd, map_pos, len, blockbuf, n_thr) == 0) {
+						map = blockbuf - map_pos;
+						n = fq_index_block(map, map_pos + len, map_pos + len == map_size, map_pos, map_pos + FQ_BLOCK, n_thr, lists, &recs, &m_recs, &next);
+					}
 					if (n >= 0) { n_recs = (size_t)n; i_rec = 0; map_pos = next; continue; }
 					/* not strict 4-line FASTQ from here on: the serial reader takes over at the start of the block */
-					munmap((void *)map, map_size); map = NULL;
+					map = NULL;
 					lseek(st.fd, (off_t)map_pos, SEEK_SET);
 					st.n = st.pos = st.eof = 0; st.last_char = 0;
 					n_recs = i_rec = 0;
 					continue;
 				}
-				munmap((void *)map, map_size); map = NULL; n_recs = i_rec = 0;
+				map = NULL; n_recs = i_rec = 0;
 				close(st.fd); stream_open = 0; file_i++;
 				continue;
 			}
@@ -241,10 +251,9 @@ static void *reader_main(void *arg)
 					pthread_mutex_unlock(&sh->mu);
 					struct stat sb;
 					if (!st.fp && n_thr > 0 && got >= 1 && magic[0] == '@' && fstat(st.fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
-						void *m = mmap(NULL, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, st.fd, 0);
-						if (m != MAP_FAILED) {
-							madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
-							map = (const char *)m; map_size = (uint64_t)sb.st_size; map_pos = 0; n_recs = i_rec = 0;
+						if (!blockbuf) blockbuf = malloc(FQ_BLOCK + FQ_MARGIN + 16);
+						if (blockbuf) {
+							map = blockbuf; map_size = (uint64_t)sb.st_size; map_pos = 0; n_recs = i_rec = 0;
 							continue;
 						}
 					}
@@ -258,6 +267,7 @@ static void *reader_main(void *arg)
 			if (L >= 40 && 2 * L > m_bin_read) m_bin_read = (uint32_t)(2 * L + 20);
 			pending = 0;
 		}
+		sh->t_reader_work += now_s() - tw1;
 		pthread_mutex_lock(&sh->mu);
 		if (b->n_reads) { b->seq_no = sh->n_filled; b->state = SLOT_READY; sh->n_filled++; sh->total_sequences += b->n_reads; }
 		if (end_of_input) sh->eof = 1;
@@ -265,7 +275,7 @@ static void *reader_main(void *arg)
 		pthread_mutex_unlock(&sh->mu);
 		if (end_of_input) break;
 	}
-	if (map) munmap((void *)map, map_size);
+	free(blockbuf);
 	for (int t = 0; t < 64; t++) free(lists[t].r);
 	free(recs);
 	free(st.buf); free(rec.name); free(rec.seq); free(rec.qual);
@@ -298,6 +308,7 @@ static void *worker_main(void *arg)
 		if ((size_t)b->n_reads > b->m_rr) { b->m_rr = (size_t)b->n_reads * 2; b->rr = realloc(b->rr, b->m_rr * sizeof *b->rr); }
 		size_t want = (size_t)b->n_reads * 24 + 4096;
 		int32_t max_out = max_in; int rc;
+		const double tc0 = now_s();
 		for (;;) {
 			if (want > b->m_hits) { b->m_hits = want; free(b->hits); b->hits = malloc(b->m_hits * sizeof *b->hits); }
 			dsb_ctx_set_bin_capacity(w->ctx, b->m_bin_read_in);
@@ -307,6 +318,7 @@ static void *worker_main(void *arg)
 		}
 		if (rc != DSB_OK) { fail(sh, "dsb_classify_batch", rc); break; }
 		pthread_mutex_lock(&sh->mu);
+		sh->t_worker_call += now_s() - tc0;
 		if (max_out > sh->known_max) sh->known_max = max_out;
 		b->state = SLOT_DONE; b->rc = rc;
 		pthread_cond_broadcast(&sh->cv);
@@ -485,12 +497,15 @@ static int classify_main(int argc, char **argv)
 	fmt_job_t fj[16]; memset(fj, 0, sizeof fj);
 	obuf_t ob = {0};
 	for (;;) {
+		const double tq0 = now_s();
 		pthread_mutex_lock(&sh.mu);
 		slot_t *b = &sh.slot[sh.n_written % sh.n_slots];
 		while (!sh.error && !(b->state == SLOT_DONE && b->seq_no == sh.n_written) && !(sh.eof && sh.n_written == sh.n_filled)) pthread_cond_wait(&sh.cv, &sh.mu);
 		const int stop = sh.error || !(b->state == SLOT_DONE && b->seq_no == sh.n_written);
 		pthread_mutex_unlock(&sh.mu);
 		if (stop) break;
+		const double tq1 = now_s();
+		sh.t_writer_wait += tq1 - tq0;
 		if (n_fmt > 1 && b->n_reads >= 4096) {
 			pthread_t ft[16];
 			for (int t = 0; t < n_fmt; t++) {
@@ -510,6 +525,7 @@ static int classify_main(int argc, char **argv)
 			}
 			fwrite(ob.s, 1, ob.n, o.out);
 		}
+		sh.t_writer_fmt += now_s() - tq1;
 		pthread_mutex_lock(&sh.mu);
 		b->state = SLOT_FREE; sh.n_written++;
 		pthread_cond_broadcast(&sh.cv);
@@ -518,6 +534,8 @@ static int classify_main(int argc, char **argv)
 	pthread_join(rd, NULL);
 	for (int k = 0; k < n_workers; k++) pthread_join(th[k], NULL);
 	STAMP("last record written");
+	if (verbose) fprintf(stderr, "[deSAMBA-b200] host time: reader %.3f s work + %.3f s waiting for a free batch; GPU calls %.3f s (sum over %d worker threads); writer %.3f s formatting + %.3f s waiting\n",
+	                     sh.t_reader_work, sh.t_reader_wait, sh.t_worker_call, n_workers, sh.t_writer_fmt, sh.t_writer_wait);
 	fflush(o.out);
 	if (o.out != stdout) fclose(o.out);
 	if (sh.error) { fprintf(stderr, "[deSAMBA-b200] error %d: %s\n", sh.error, sh.errmsg); return 1; }

@@ -1,10 +1,9 @@
 /* fastq_dump -- test tool for fastq_reader.h: prints the records of a FASTA/FASTQ file as  name \t sequence \t quality-length
- * usage: fastq_dump serial|parallel FILE [block_bytes] [threads]   (parallel falls back to the serial reader exactly like the
- * driver does; exit code 3 when it had to) */
+ * usage: fastq_dump serial|parallel FILE [block_bytes] [threads] [margin_bytes]   (parallel falls back to the serial reader exactly
+ * like the driver does; exit code 3 when it had to) */
 #define _GNU_SOURCE
 #include "fastq_reader.h"
 #include <fcntl.h>
-#include <sys/mman.h>
 #include <sys/stat.h>
 
 static int dump_serial(int fd, uint64_t from)
@@ -27,18 +26,23 @@ int main(int argc, char **argv)
 	if (!strcmp(argv[1], "serial")) return dump_serial(fd, 0);
 	const uint64_t block = argc > 3 ? strtoull(argv[3], 0, 10) : (64u << 20);
 	const int thr = argc > 4 ? atoi(argv[4]) : 4;
+	const uint64_t margin = argc > 5 ? strtoull(argv[5], 0, 10) : (16u << 20);
 	struct stat sb; fstat(fd, &sb);
 	const uint64_t size = (uint64_t)sb.st_size;
 	if (size == 0) return 0;
-	const char *map = mmap(NULL, size, PROT_READ, MAP_PRIVATE, fd, 0);
-	if (map == MAP_FAILED) return dump_serial(fd, 0);
+	char *buf = malloc(block + margin + 16);
 	fq_list_t lists[64]; memset(lists, 0, sizeof lists);
 	fq_rec_t *recs = NULL; size_t m_recs = 0;
 	uint64_t pos = 0;
-	if (map[0] != '@') { dump_serial(fd, 0); return 3; }
+	char first = 0;
+	if (pread(fd, &first, 1, 0) != 1 || first != '@') { dump_serial(fd, 0); return 3; }
 	while (pos < size) {
+		/* like the driver: block + margin bytes into the buffer, records that start inside the block are indexed */
+		const uint64_t len = (size - pos < block + margin) ? size - pos : block + margin;
+		if (fq_read_block(fd, pos, len, buf, thr)) return 2;
+		const char *map = buf - pos;
 		uint64_t next;
-		const long n = fq_index_block(map, size, pos, pos + block, thr, lists, &recs, &m_recs, &next);
+		const long n = fq_index_block(map, pos + len, pos + len == size, pos, pos + block, thr, lists, &recs, &m_recs, &next);
 		if (n < 0) { fflush(stdout); dump_serial(fd, pos); return 3; }
 		for (long i = 0; i < n; i++) {
 			fwrite(map + recs[i].name, 1, recs[i].n_name, stdout); putchar('\t'); fwrite(map + recs[i].seq, 1, recs[i].n_seq, stdout); printf("\t%u\n", recs[i].n_seq);

@@ -104,7 +104,7 @@ typedef struct { fq_rec_t *r; size_t n, m; int bad; uint64_t first, next; } fq_l
 static inline int fq_is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
 
 /* the record starting at p: fills *o and *next (start of the following record); 0 ok, -1 not strict 4-line FASTQ / cut off */
-static inline int fq_parse_at(const char *map, uint64_t size, uint64_t p, fq_rec_t *o, uint64_t *next)
+static inline int fq_parse_at(const char *map, uint64_t size, int at_eof, uint64_t p, fq_rec_t *o, uint64_t *next)
 {
 	if (p >= size || map[p] != '@') return -1;
 	const char *e1 = memchr(map + p, '\n', size - p);
@@ -128,19 +128,21 @@ static inline int fq_parse_at(const char *map, uint64_t size, uint64_t p, fq_rec
 	const uint64_t q0 = (uint64_t)(e3 - map) + 1;
 	if (q0 > size) return -1;
 	const char *e4 = (q0 < size) ? memchr(map + q0, '\n', size - q0) : NULL;
+	if (!e4 && !at_eof) return -1;                                   /* ran into the end of the buffered part, not of the file */
 	uint64_t q1 = e4 ? (uint64_t)(e4 - map) : size;
 	const uint64_t nx = e4 ? q1 + 1 : size;
 	while (q1 > q0 && map[q1 - 1] == '\r') q1--;
 	if (q1 - q0 != o->n_seq) return -1;
 	o->qual = q0;
 	if (nx < size && map[nx] != '@') return -1;
+	if (nx >= size && !at_eof) return -1;
 	*next = nx;
 	return 0;
 }
 
 /* the records that START in [lo, hi); lo == 0 or any offset (the first record start at or after lo is looked for: a line
  * starting with '@' that parses as a record whose successor parses too).  out->next = start of the first record >= hi. */
-static void fq_index_range(const char *map, uint64_t size, uint64_t lo, uint64_t hi, int lo_is_start, fq_list_t *out)
+static void fq_index_range(const char *map, uint64_t size, int at_eof, uint64_t lo, uint64_t hi, int lo_is_start, fq_list_t *out)
 {
 	out->n = 0; out->bad = 0; out->first = out->next = lo;
 	uint64_t p = lo;
@@ -150,16 +152,16 @@ static void fq_index_range(const char *map, uint64_t size, uint64_t lo, uint64_t
 		if (p > 0) { const char *e = memchr(map + p - 1, '\n', size - (p - 1)); p = e ? (uint64_t)(e - map) + 1 : size; }
 		for (int tries = 0; tries < 64 && p < size && p < hi + (1u << 20); tries++) {
 			fq_rec_t r2; uint64_t nx2;
-			if (map[p] == '@' && fq_parse_at(map, size, p, &r, &nx) == 0 && (nx >= size || fq_parse_at(map, size, nx, &r2, &nx2) == 0)) { found = 1; break; }
+			if (map[p] == '@' && fq_parse_at(map, size, at_eof, p, &r, &nx) == 0 && (nx >= size || fq_parse_at(map, size, at_eof, nx, &r2, &nx2) == 0)) { found = 1; break; }
 			const char *e = memchr(map + p, '\n', size - p);
 			p = e ? (uint64_t)(e - map) + 1 : size;
 		}
-		if (p >= size) { out->first = out->next = size; return; }
+		if (p >= size) { if (at_eof) out->first = out->next = size; else out->bad = 1; return; }
 		if (!found) { out->bad = 1; return; }
 		out->first = p;
 	}
 	while (p < hi && p < size) {
-		if (fq_parse_at(map, size, p, &r, &nx) != 0) { out->bad = 1; return; }
+		if (fq_parse_at(map, size, at_eof, p, &r, &nx) != 0) { out->bad = 1; return; }
 		if (out->n == out->m) { out->m = out->m ? out->m * 2 : 4096; out->r = (fq_rec_t *)realloc(out->r, out->m * sizeof(fq_rec_t)); }
 		out->r[out->n++] = r;
 		p = nx;
@@ -167,13 +169,14 @@ static void fq_index_range(const char *map, uint64_t size, uint64_t lo, uint64_t
 	out->next = p;
 }
 
-typedef struct { const char *map; uint64_t size, lo, hi; int lo_is_start; fq_list_t *out; } fq_index_job_t;
-static void *fq_index_thread(void *a) { fq_index_job_t *j = (fq_index_job_t *)a; fq_index_range(j->map, j->size, j->lo, j->hi, j->lo_is_start, j->out); return NULL; }
+typedef struct { const char *map; uint64_t size, lo, hi; int at_eof, lo_is_start; fq_list_t *out; } fq_index_job_t;
+static void *fq_index_thread(void *a) { fq_index_job_t *j = (fq_index_job_t *)a; fq_index_range(j->map, j->size, j->at_eof, j->lo, j->hi, j->lo_is_start, j->out); return NULL; }
 
 /* index the records that start in the block [lo, hi) of the mapping with n_thr threads; lo must be a record start.
- * Returns the number of records (appended to *recs in file order) and the start of the next block in *next, or -1 when the
- * block is not strict 4-line FASTQ (nothing is appended). */
-static long fq_index_block(const char *map, uint64_t size, uint64_t lo, uint64_t hi, int n_thr, fq_list_t *lists, fq_rec_t **recs, size_t *m_recs, uint64_t *next)
+ * map[0, size) need only be readable from lo on; at_eof = size is the end of the file (else: of the buffered part, and a
+ * record that runs into it makes the block fail).  Returns the number of records (written to *recs in file order) and the
+ * start of the next block in *next, or -1 when the block is not strict 4-line FASTQ. */
+static long fq_index_block(const char *map, uint64_t size, int at_eof, uint64_t lo, uint64_t hi, int n_thr, fq_list_t *lists, fq_rec_t **recs, size_t *m_recs, uint64_t *next)
 {
 	if (hi > size) hi = size;
 	if (n_thr < 1) n_thr = 1;
@@ -181,7 +184,7 @@ static long fq_index_block(const char *map, uint64_t size, uint64_t lo, uint64_t
 	const uint64_t span = (hi - lo + n_thr - 1) / n_thr;
 	fq_index_job_t job[64]; pthread_t th[64];
 	for (int t = 0; t < n_thr; t++) {
-		job[t].map = map; job[t].size = size; job[t].lo = lo + t * span; job[t].hi = (t == n_thr - 1) ? hi : lo + (t + 1) * span;
+		job[t].map = map; job[t].size = size; job[t].at_eof = at_eof; job[t].lo = lo + t * span; job[t].hi = (t == n_thr - 1) ? hi : lo + (t + 1) * span;
 		if (job[t].lo > hi) job[t].lo = hi;
 		if (job[t].hi > hi) job[t].hi = hi;
 		job[t].lo_is_start = (t == 0); job[t].out = &lists[t];
@@ -201,5 +204,35 @@ static long fq_index_block(const char *map, uint64_t size, uint64_t lo, uint64_t
 	for (int t = 0; t < n_thr; t++) { if (lists[t].n) memcpy(*recs + k, lists[t].r, lists[t].n * sizeof(fq_rec_t)); k += lists[t].n; }
 	*next = expect;
 	return (long)n;
+}
+
+/* ---- block input: the file is read (not mapped: a page fault per 4 KB under one mm lock is slower than the serial reader)
+ * into a reusable buffer, FQ_MARGIN bytes beyond the block so that the records starting in the block are complete */
+typedef struct { int fd; char *dst; uint64_t off, len; long got; } fq_read_job_t;
+static void *fq_read_thread(void *a)
+{
+	fq_read_job_t *j = (fq_read_job_t *)a; uint64_t done = 0;
+	while (done < j->len) {
+		const ssize_t n = pread(j->fd, j->dst + done, j->len - done, (off_t)(j->off + done));
+		if (n <= 0) break;
+		done += (uint64_t)n;
+	}
+	j->got = (long)done;
+	return NULL;
+}
+/* bytes [pos, pos + len) of fd into buf with n_thr threads; returns 0 when all of them arrived */
+static int fq_read_block(int fd, uint64_t pos, uint64_t len, char *buf, int n_thr)
+{
+	if (n_thr < 1) n_thr = 1;
+	if (n_thr > 64) n_thr = 64;
+	fq_read_job_t job[64]; pthread_t th[64];
+	const uint64_t span = ((len + n_thr - 1) / n_thr + 4095) & ~4095ull;
+	int n = 0;
+	for (uint64_t o = 0; o < len && n < 64; o += span, n++) { job[n].fd = fd; job[n].dst = buf + o; job[n].off = pos + o; job[n].len = (o + span <= len) ? span : len - o; job[n].got = 0; }
+	for (int t = 1; t < n; t++) pthread_create(&th[t], NULL, fq_read_thread, &job[t]);
+	if (n) fq_read_thread(&job[0]);
+	for (int t = 1; t < n; t++) pthread_join(th[t], NULL);
+	for (int t = 0; t < n; t++) if ((uint64_t)job[t].got != job[t].len) return -1;
+	return 0;
 }
 #endif

@@ -46,10 +46,13 @@ def test_parallel_equals_serial_on_4_line_fastq(ob, tmp_path, kw):
     open(p, "wb").write(_rand_fastq(rng, 400, 1, 700, **kw))
     want, _ = _dump("serial", p)
     assert want.count(b"\n") == 400
-    for block, thr in ((1 << 26, 4), (5000, 7), (997, 3), (200, 16), (64, 2), (1, 1)):
-        got, rc = _dump("parallel", p, block, thr)
-        assert got == want, (kw, block, thr)
-        assert rc == 0, (kw, block, thr)         # handled by the parallel indexer, no fallback
+    for block, thr, margin in ((1 << 26, 4, 1 << 24), (5000, 7, 6000), (997, 3, 6000), (200, 16, 1 << 20), (64, 2, 6000), (1, 1, 6000)):
+        got, rc = _dump("parallel", p, block, thr, margin)
+        assert got == want, (kw, block, thr, margin)
+        assert rc == 0, (kw, block, thr, margin)         # handled by the parallel indexer, no fallback (margin > 3 records)
+    for block, thr, margin in ((5000, 4, 100), (300, 3, 0), (64, 2, 700)):
+        got, rc = _dump("parallel", p, block, thr, margin)   # margin smaller than a record: the block fails, the serial reader takes over
+        assert got == want, (kw, block, thr, margin)
 
 
 def test_long_records_span_several_shares(ob, tmp_path):
@@ -57,8 +60,8 @@ def test_long_records_span_several_shares(ob, tmp_path):
     p = str(tmp_path / "long.fq")
     open(p, "wb").write(_rand_fastq(rng, 30, 20000, 90000, qual_at=True))
     want, _ = _dump("serial", p)
-    for block, thr in ((1 << 20, 8), (30000, 8), (100000, 64)):
-        got, rc = _dump("parallel", p, block, thr)
+    for block, thr, margin in ((1 << 20, 8, 1 << 20), (30000, 8, 1 << 20), (100000, 64, 1 << 20)):
+        got, rc = _dump("parallel", p, block, thr, margin)
         assert got == want and rc == 0
 
 
