@@ -4,7 +4,7 @@
  *
  * Same options (-h -t -l -r -o -s -f), same index directory, same text output in input order, same stderr summary.
  * What replaces the reference's host (kt_pipeline + kt_for thread pool, cly_mt.c:369-398):
- *   reader thread   FASTQ(.gz) -> batches in pinned host memory             (read_reads, cly_mt.c:42-56; kseq, utils.c:939-977)
+ *   reader thread   FASTQ(.gz) -> batches in host memory (parallel indexer for plain FASTQ) (read_reads, cly_mt.c:42-56; kseq, utils.c:939-977)
  *   one thread/GPU  dsb_classify_batch on its own context; batches are dealt in input order
  *   writer (main)   formats the result records of each batch in input order (output_results, cly_mt.c:350-365)
  * The index is replicated per GPU, reads are sharded by batch, nothing is exchanged between GPUs.
@@ -28,6 +28,7 @@
 #include <zlib.h>
 #include <fcntl.h>
 #include <sys/stat.h>
+#include <sys/mman.h>
 
 enum { FMT_SAM = 1, FMT_SAM_FULL = 2, FMT_DES = 3, FMT_DES_FULL = 4 };
 
@@ -82,18 +83,24 @@ static void fail(shared_t *sh, const char *what, int rc)
 
 #include "fastq_reader.h"
 
-/* pinned batch buffers: cudaHostAlloc is slow (tens of ms per 100 MB), so a buffer grows by doubling from 32 MB, up to `full`
- * (the batch limit) -- a batch of short reads never pins the 512 MB a batch of long reads needs */
+/* batch buffers grow by doubling from 32 MB, and from 128 MB straight to `full` (the batch limit) */
+/* The batch buffers are ordinary (huge-page) memory by default: cudaHostAlloc costs ~1 s per GB on an 8-GPU box (19 allocations
+ * = 6.9 s for a 4 GB input, more than reading, classifying and writing it), and the H2D copy of a batch from pageable memory
+ * was not slower in the driver (3 contexts per GPU overlap it).  DSB_PINNED=1 pins them (long multi-GPU runs). */
+static double g_t_pinned = 0; static int g_n_pinned = 0; static int g_pageable = 1;
 static int grow_pinned(void **p, size_t *m, size_t need, size_t keep, size_t full)
 {
 	if (need <= *m) return 0;
+	const double t0 = now_s();
 	size_t nm = (size_t)32 << 20;
 	while (need > nm) nm *= 2;
-	if (nm > full && need <= full) nm = full;
+	if ((nm > full || nm >= ((size_t)128 << 20)) && need <= full) nm = full;       /* a batch of long reads will fill up: no more copies */
 	void *np = NULL;
-	if (dsb_host_alloc(nm, &np) != DSB_OK) return -1;
-	if (*p) { memcpy(np, *p, keep); dsb_host_free(*p); }
+	if (g_pageable) { if (posix_memalign(&np, (size_t)2 << 20, nm)) return -1; madvise(np, nm, MADV_HUGEPAGE); }
+	else if (dsb_host_alloc(nm, &np) != DSB_OK) return -1;
+	if (*p) { memcpy(np, *p, keep); if (g_pageable) free(*p); else dsb_host_free(*p); }
 	*p = np; *m = nm;
+	g_t_pinned += now_s() - t0; g_n_pinned++;
 	return 0;
 }
 
@@ -448,6 +455,7 @@ static int classify_main(int argc, char **argv)
 	if (o.n_parse_threads < 0) { long nc = sysconf(_SC_NPROCESSORS_ONLN); o.n_parse_threads = nc >= 16 ? 8 : nc >= 8 ? 4 : nc >= 4 ? 2 : 1; }
 	if (o.n_parse_threads > 64) o.n_parse_threads = 64;
 	const int verbose = getenv("DSB_VERBOSE") != NULL;
+	g_pageable = getenv("DSB_PINNED") == NULL;
 	const double t_start = now_s();
 	#define STAMP(what) do { if (verbose) fprintf(stderr, "[deSAMBA-b200] %-34s at %7.3f s\n", what, now_s() - t_start); } while (0)
 	/* the reader starts at once: the first batches are parsed into pinned memory while the index is loaded into HBM */
@@ -534,6 +542,7 @@ static int classify_main(int argc, char **argv)
 	pthread_join(rd, NULL);
 	for (int k = 0; k < n_workers; k++) pthread_join(th[k], NULL);
 	STAMP("last record written");
+	if (verbose) fprintf(stderr, "[deSAMBA-b200] batch buffers: %d allocations, %.3f s (%s)\n", g_n_pinned, g_t_pinned, g_pageable ? "pageable" : "pinned");
 	if (verbose) fprintf(stderr, "[deSAMBA-b200] host time: reader %.3f s work + %.3f s waiting for a free batch; GPU calls %.3f s (sum over %d worker threads); writer %.3f s formatting + %.3f s waiting\n",
 	                     sh.t_reader_work, sh.t_reader_wait, sh.t_worker_call, n_workers, sh.t_writer_fmt, sh.t_writer_wait);
 	fflush(o.out);

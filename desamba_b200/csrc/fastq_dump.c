@@ -24,6 +24,8 @@ int main(int argc, char **argv)
 	int fd = open(argv[2], O_RDONLY);
 	if (fd < 0) return 2;
 	if (!strcmp(argv[1], "serial")) return dump_serial(fd, 0);
+	const int count_only = !strcmp(argv[1], "count");             /* timing aid: index only, print the totals */
+	uint64_t n_rec = 0, n_base = 0;
 	const uint64_t block = argc > 3 ? strtoull(argv[3], 0, 10) : (64u << 20);
 	const int thr = argc > 4 ? atoi(argv[4]) : 4;
 	const uint64_t margin = argc > 5 ? strtoull(argv[5], 0, 10) : (16u << 20);
@@ -44,10 +46,12 @@ int main(int argc, char **argv)
 		uint64_t next;
 		const long n = fq_index_block(map, pos + len, pos + len == size, pos, pos + block, thr, lists, &recs, &m_recs, &next);
 		if (n < 0) { fflush(stdout); dump_serial(fd, pos); return 3; }
-		for (long i = 0; i < n; i++) {
+		if (count_only) { for (long i = 0; i < n; i++) { n_rec++; n_base += recs[i].n_seq; } }
+		else for (long i = 0; i < n; i++) {
 			fwrite(map + recs[i].name, 1, recs[i].n_name, stdout); putchar('\t'); fwrite(map + recs[i].seq, 1, recs[i].n_seq, stdout); printf("\t%u\n", recs[i].n_seq);
 		}
 		pos = next;
 	}
+	if (count_only) printf("%llu records %llu bases\n", (unsigned long long)n_rec, (unsigned long long)n_base);
 	return 0;
 }
