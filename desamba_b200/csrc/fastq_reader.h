@@ -2,9 +2,9 @@
  * fastq_reader.h -- FASTA/FASTQ(.gz) input of `deSAMBA-b200 classify`.
  *
  * (1) the serial reader: kseq_read semantics (utils.c:939-977) over read(2) / zlib, one record at a time;
- * (2) a parallel indexer for plain (uncompressed) 4-line FASTQ, the format sequencers write: the file is mapped, helper
- *     threads find and check the records that start in their share of a block, and the driver copies the bases of a whole
- *     batch into pinned memory with the same helpers.  Anything that is not strict 4-line FASTQ (FASTA, wrapped lines, a
+ * (2) a parallel indexer for plain (uncompressed) 4-line FASTQ, the format sequencers write: helper threads read a block of
+ *     the file into a buffer, find and check the records that start in their share of it, and the driver copies the bases of
+ *     a whole batch into the batch buffer with the same helpers.  Anything that is not strict 4-line FASTQ (FASTA, wrapped lines, a
  *     truncated or inconsistent record, junk between records) makes the indexer give up at the start of the block and the
  *     serial reader takes over from there, so the records handed on are the same in every case (tests/test_reader.py).
  * A single-threaded parser feeds ~0.8 Gbases/s; one B200 classifies 6.
