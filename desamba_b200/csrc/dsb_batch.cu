@@ -147,7 +147,27 @@ __global__ void __launch_bounds__(128) k_islands(const __grid_constant__ IslandP
 				if (!PROBE(i)) continue;
 				uint32_t offset = i, l = 1;
 				for (int j = 1; j < 3; ++j) { if (PROBE(i - j)) { offset--; l++; } else break; }
-				for (uint32_t j = 1; i + j < n; ++j) { if (PROBE(i + j)) { l++; if (l > 60) break; } else break; }
+				{   // right extension (cly.c:1118-1130) a word at a time: the run of existing k-mers behind i, cut at l = 61 and at n;
+					// every probed position counts for the probe counters -- the hits, and the miss that ends the run if there is one
+					const uint32_t want = 61 - l;                          // hits after which `l > 60` stops the loop
+					uint32_t run = 0;
+					for (uint32_t p = i + 1; p < n && run < want;) {
+						const uint32_t b = p & 31, avail = min(32 - b, n - p);
+						const uint32_t x = ~(__ldg(E + (p >> 5)) >> b);
+						const uint32_t ones = x ? min((uint32_t)(__ffs(x) - 1), avail) : avail;
+						run += ones; p += ones;
+						if (ones < avail) break;
+					}
+					const uint32_t hits = min(run, want);
+					const uint32_t probes = hits + ((hits == run && i + run + 1 < n && run < want) ? 1u : 0u);
+					for (uint32_t p = i + 1, left = probes; left;) {        // probe counters over [i + 1, i + probes]
+						const uint32_t b = p & 31, take = min(32 - b, left);
+						const uint32_t m = ((take == 32) ? 0xffffffffu : ((1u << take) - 1)) << b;
+						calls_nz += __popc(__ldg(Z + (p >> 5)) & m); calls_t0 += __popc(__ldg(T0 + (p >> 5)) & m);
+						p += take; left -= take;
+					}
+					l += hits;
+				}
 				dsb_seed sd; sd.offset = s ? (n - offset - l) : offset; sd.len = (uint16_t)l; sd.top = 0; sd.pad = 0;
 				out[n_seed] = sd;
 				// top labelling (cly.c:1174-1226); the window position is the mirrored offset for the reverse strand
