@@ -469,7 +469,7 @@ extern "C" int dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out)
 	if (c->opts.warps_per_sm < CLASSIFY_WARPS_PER_BLOCK) c->opts.warps_per_sm = CLASSIFY_WARPS_PER_BLOCK;
 	if (c->opts.warps_per_sm > 32) c->opts.warps_per_sm = 32;
 	c->stream = nullptr; c->stream2 = nullptr; c->ev_fork = nullptr; c->ev_join = nullptr; c->h_pin = nullptr; c->h_pin_cap = 0; c->ran = false; c->launches = 0;
-	c->n_reads = 0; c->m_bin_read = 0; c->scratch_zeroed_stride = 0; c->scratch_stride = 0; c->kidx_bits = 0; c->kidx_len = 0; c->hits_cap = 0;
+	c->n_reads = 0; c->m_bin_read = 0; c->scratch_zeroed_stride = 0; c->scratch_stride = 0; c->rec_len = 0; c->hits_cap = 0;
 	cudaDeviceProp prop;
 	DSB_CUDA(cudaGetDeviceProperties(&prop, ix->device));
 	c->n_sm = prop.multiProcessorCount;
@@ -614,8 +614,8 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 	const uint32_t n = c->n_reads;
 	if (n == 0) { c->ran = true; return DSB_OK; }
 	// classify scratch: the per-seed records are sized by the longest read seen
-	if (c->max_len + 64 > c->kidx_len || c->scratch_stride == 0) c->kidx_len = std::max(c->kidx_len, c->max_len + 64);
-	const ScratchLayout L = scratch_layout(c->opts.max_anchors, c->opts.max_matches, c->kidx_len);
+	if (c->max_len + 64 > c->rec_len || c->scratch_stride == 0) c->rec_len = std::max(c->rec_len, c->max_len + 64);
+	const ScratchLayout L = scratch_layout(c->opts.max_anchors, c->opts.max_matches, c->rec_len);
 	c->scratch_stride = L.total;
 	int rc;
 	{

@@ -1103,18 +1103,6 @@ __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, int 
 	return total_max_score - 10000;
 }
 
-struct ChainCmpByPos {          // chain_cmp_by_pos (cly.c:2853-2870)
-	__device__ int operator()(const DevChain &a, const DevChain &b) const {
-		if (a.ref_ID > b.ref_ID) return 1;
-		if (a.ref_ID < b.ref_ID) return -1;
-		if (a.t_st > b.t_st) return 1;
-		if (a.t_st < b.t_st) return -1;
-		if (a.sum_score < b.sum_score) return 1;
-		if (a.sum_score > b.sum_score) return -1;
-		return 0;
-	}
-};
-
 // delete_small_score_rst up to (not including) the max_read_l-dependent filter (cly.c:2883-2957)
 __device__ __noinline__ void score_and_merge(ReadState &S, const SearchDir *search_dir, uint32_t l_read)
 {

@@ -39,7 +39,7 @@ struct dsb_ctx {
 	DevBuf seqs, read_off, bin_off, bits_off, seed_off, tiles, bin, bits, seeds[2], n_seeds[2], total_score[2];
 	// classify scratch + outputs
 	DevBuf scratch, rr, hits, counters, prof, work, anc_pool, chain_pool, lists[5], ctl, order, hdr7;
-	uint64_t scratch_stride, scratch_zeroed_stride; uint32_t kidx_bits, kidx_len;
+	uint64_t scratch_stride, scratch_zeroed_stride; uint32_t rec_len;   /* rec_len: longest read seen (+64), sizes the per-seed records */
 	uint64_t hits_cap;
 	// pinned staging
 	void *h_pin; size_t h_pin_cap;
