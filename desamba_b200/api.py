@@ -26,7 +26,7 @@ assert HIT_DTYPE.itemsize == 32 and RR_DTYPE.itemsize == 24 and SEED_DTYPE.items
 
 class Opts(C.Structure):
     _fields_ = [("l_min_match", C.c_int32), ("min_score", C.c_int32), ("max_anchors", C.c_uint32), ("max_matches", C.c_uint32),
-                ("max_read_len", C.c_uint32), ("warps_per_sm", C.c_uint32)]
+                ("max_read_len", C.c_uint32), ("warps_per_sm", C.c_uint32), ("pool_scale_pct", C.c_uint32)]
 
 
 class RefInfo(C.Structure):
@@ -161,7 +161,7 @@ def pack_reads(seqs):
 class Context:
     """Stream + scratch for batches on one GPU (replaces Classify_buff_pool, cly.h:137-158)."""
 
-    def __init__(self, index, l_min_match=170, min_score=64, max_anchors=None, max_matches=None, warps_per_sm=None, max_read_len=None):
+    def __init__(self, index, l_min_match=170, min_score=64, max_anchors=None, max_matches=None, warps_per_sm=None, max_read_len=None, pool_scale_pct=None):
         self.index = index
         o = Opts()
         lib.dsb_opts_default(C.byref(o))
@@ -174,6 +174,8 @@ class Context:
             o.warps_per_sm = warps_per_sm
         if max_read_len:
             o.max_read_len = max_read_len
+        if pool_scale_pct:
+            o.pool_scale_pct = pool_scale_pct
         self._h = _vp()
         _check(lib.dsb_ctx_create(index._h, C.byref(o), C.byref(self._h)), "dsb_ctx_create")
         self.n_reads = 0
@@ -188,6 +190,10 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def retries(self):
+        """re-runs of the last batch after a pool overflow (dsb_batch_retries)"""
+        return int(lib.dsb_batch_retries(self._h))
 
     # -- the end-to-end call with host buffers
     def classify(self, cat, offs, max_read_l_in=0, m_bin_read_in=0):

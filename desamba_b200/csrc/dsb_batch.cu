@@ -1,8 +1,12 @@
 // dsb_batch.cu -- the batch pipeline behind dsb_classify_batch():
-//   K0 k_encode_probe : ASCII -> 2-bit codes of both strands; every l_ek-mer of the read (both strands) is hashed and
-//                       probed in the two exist-k-mer bit tables (get_exist_kmer, cly.c:956-972) -> membership bit-vectors
-//   K1 k_islands      : replays the reference's island scan + top labelling on the bit-vectors (cly.c:1071-1234) -> seeds
-//   K2 k_classify     : warp per read: FM-index seeding, anchors, chaining, 9-mer sparse-DP scoring (dsb_classify.cuh)
+//   K0 k_encode_probe : ASCII -> 2-bit codes of both strands (bytes for the scoring kernels, packed words for seeding); every
+//                       l_ek-mer of the read (both strands) is hashed and probed in the two exist-k-mer bit tables
+//                       (get_exist_kmer, cly.c:956-972) -> membership bit-vectors
+//   K1 k_islands      : replays the reference's island scan + top labelling on the bit-vectors (cly.c:1071-1234) -> seeds,
+//                       and the seed-task list of the fast pass
+//   K2 k_seed x3      : lane per island seed over a flat task list (dsb_seedcore.h): FM-index search, locate, flanks -> anchors
+//      k_chain x3     : warp per read: ordered gather of the anchors, resolve_tree, which pass comes next (cly.c:3098-3127)
+//      k_score, k_score_heavy : warp / CTA per read: 9-mer sparse-DP scoring (dsb_classify.cuh)
 //   K3 k_finalize     : class filter (needs the running max_read_l of the input order), final sort, primary detection
 // One CUDA stream per context, no host synchronisation between the kernels.
 #include "dsb_internal.h"
@@ -31,6 +35,7 @@ struct ProbeParams {
 	const uint2 *tiles;
 	const uint8_t *hdr7;       // per read: the byte 7 before the forward strand (oracle policy P3: the reference's malloc chunk header)
 	uint8_t *bin; uint32_t *bits;
+	uint64_t *pk;              // 2-bit packed forward strands for the seeding engine (layout: SeedEnv.pk, dsb_seedcore.h)
 };
 
 __device__ __forceinline__ uint32_t cly_bit(char ch)      // CLY_Bit, cly.c:17-35: A0 C1 G2 T3 (either case), everything else 1
@@ -47,7 +52,7 @@ __device__ __forceinline__ uint64_t revcomp_kmer(uint64_t km, int l)
 
 __global__ void __launch_bounds__(PROBE_THREADS) k_encode_probe(const __grid_constant__ ProbeParams P)
 {
-	__shared__ uint8_t s_code[PROBE_TILE + 32];
+	__shared__ __align__(16) uint8_t s_code[PROBE_TILE + 32];
 	const uint2 tile = P.tiles[blockIdx.x];
 	const uint32_t r = tile.x, start = tile.y;
 	const uint64_t off = P.read_off[r];
@@ -67,6 +72,15 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_encode_probe(const __grid_con
 		bin_R[len + tid] = 0;
 	}
 	__syncthreads();
+	if (tid < 32 && start + 32 * tid < len) {                     // 32 packed words of 32 bases, first base in the top bits
+		const uint32_t *w4 = (const uint32_t *)(s_code + 32 * tid);
+		uint64_t v = 0;
+		#pragma unroll
+		for (int k = 0; k < 8; k++) v = (v << 8) | (((w4[k] & 0x03030303u) * 0x40100401u) >> 24);
+		const uint32_t valid = min(32u, len - (start + 32 * tid));
+		if (valid < 32) v &= ~0ull << (64 - 2 * valid);
+		P.pk[P.bits_off[r] / N_BITVEC + 1 + (start >> 5) + tid] = v;
+	}
 	const uint32_t W = (len + 31) / 32 + 1;
 	uint32_t *bits = P.bits + P.bits_off[r];
 	const int sbm = P.ix.single_base_max;
@@ -112,6 +126,7 @@ struct IslandParams {
 	const uint32_t *bits;
 	dsb_seed *seeds[2]; uint32_t *n_seeds[2]; uint32_t *total_score[2];
 	unsigned long long *counters;
+	SeedTaskRef *tasks; uint32_t task_cap; uint32_t *ctl; uint32_t *task_first[2], *task_cnt[2];
 };
 
 __device__ __forceinline__ uint32_t bit_at(const uint32_t *v, uint32_t i) { return (__ldg(v + (i >> 5)) >> (i & 31)) & 1; }
@@ -182,6 +197,30 @@ __global__ void __launch_bounds__(128) k_islands(const __grid_constant__ IslandP
 		}
 		P.n_seeds[s][r] = n_seed; P.total_score[s][r] = total;
 	}
+	{	// seed tasks of the fast pass: the top seeds of the strand with the larger total score, of both strands when the scores are
+		// close (cly.c:1261-1266, 3095-3099, 1494-1496).  Threads 2r and 2r + 1 are neighbours in the warp.
+		uint32_t n_seed = 0, total = 0;
+		if (r < P.n_reads) { n_seed = P.n_seeds[s][r]; total = P.total_score[s][r]; }
+		const uint32_t other = __shfl_xor_sync(DSB_FULL, total, 1);
+		if (r < P.n_reads) {
+			const bool first = s ? (total > other) : (total >= other);                    // search_dir[0] after the swap
+			const uint32_t t0 = first ? total : other, t1 = first ? other : total;
+			const bool both = (t0 - t1) <= (t0 >> 3);
+			const dsb_seed *sv = P.seeds[s] + P.seed_off[r];
+			uint32_t n_top = 0;
+			if (first || both) for (uint32_t k = 0; k < n_seed; k++) n_top += sv[k].top ? 1u : 0u;
+			uint32_t base = 0;
+			if (n_top) {
+				base = atomicAdd(P.ctl + CTL_TASK_N + PASS_FAST, n_top);
+				if ((uint64_t)base + n_top > P.task_cap) { atomicOr(P.ctl + CTL_OVERFLOW, OVF_TASKS); n_top = 0; }
+			}
+			P.task_first[s][r] = base; P.task_cnt[s][r] = n_top;
+			if (n_top) {
+				SeedTaskRef *out = P.tasks + base;
+				for (uint32_t k = 0, at = 0; k < n_seed; k++) if (sv[k].top) { SeedTaskRef t; t.read = r; t.sk = (s << 31) | k; out[at++] = t; }
+			}
+		}
+	}
 	for (int d = 16; d; d >>= 1) { calls_nz += __shfl_xor_sync(DSB_FULL, calls_nz, d); calls_t0 += __shfl_xor_sync(DSB_FULL, calls_t0, d); }
 	if ((threadIdx.x & 31) == 0 && (calls_nz | calls_t0)) {
 		atomicAdd(P.counters + DSB_CNT_N_BIT0, (unsigned long long)calls_nz);
@@ -190,48 +229,44 @@ __global__ void __launch_bounds__(128) k_islands(const __grid_constant__ IslandP
 }
 
 // ------------------------------------------------------------------------------------------------ K2
-struct ScratchLayout { uint64_t anc, anc_tmp, chain, chain_tmp, sms, sms_tmp, cand, sort_key[2], sort_idx[2], score_v, sc_hash, sp_set, sp_gen, lane_mem, seed_rec, chunk_next, total; };
-static ScratchLayout scratch_layout(uint32_t max_anchors, uint32_t max_matches, uint32_t max_len)
+struct ScratchLayout { uint64_t anc_tmp, chain, chain_tmp, sms, sms_tmp, cand, sort_key[2], sort_idx[2], score_v, sc_hash, total; };
+static ScratchLayout scratch_layout(uint32_t max_anchors, uint32_t max_matches)
 {
 	ScratchLayout L; uint64_t o = 0;
 	auto take = [&](uint64_t bytes) { uint64_t at = o; o += (bytes + 127) & ~127ull; return at; };
-	L.anc = take((uint64_t)max_anchors * sizeof(DevAnchor)); L.anc_tmp = take((uint64_t)max_anchors * sizeof(DevAnchor));
+	L.anc_tmp = take((uint64_t)max_anchors * sizeof(DevAnchor));
 	L.chain = take((uint64_t)max_anchors * sizeof(DevChain)); L.chain_tmp = take((uint64_t)max_anchors * sizeof(DevChain));
 	L.sms = take((uint64_t)max_matches * sizeof(DevSms));
 	L.score_v = take(1024 * sizeof(int));
 	L.sc_hash = take((256 + 2 * 400 + 8) * sizeof(ScHash));
 	L.sms_tmp = take((uint64_t)max_matches * sizeof(DevSms)); L.cand = take((uint64_t)CAND_CAP * sizeof(uint2));
 	for (int s = 0; s < 2; s++) { L.sort_key[s] = take((uint64_t)max_matches * 8); L.sort_idx[s] = take((uint64_t)max_matches * 4); }
-	L.sp_set = take(32 * (SP_SMALL + SP_TAB) * 8);
-	L.sp_gen = take(32 * 4);
-	L.lane_mem = take(32 * 512 * sizeof(MemRst));
-	L.seed_rec = take((std::max<uint64_t>(2 * (uint64_t)max_len / 3, GROUP_SEEDS) + 16) * sizeof(SeedRec));   // island seeds of both strands of a read / of a group
-	L.chunk_next = take(((uint64_t)max_anchors / ANCHOR_CHUNK + 8) * 4);
 	L.total = o;
 	return L;
 }
 
 struct ClassifyLaunch { ClassifyParams P; ScratchLayout L; };
 
-// Persistent phase kernels: every warp pulls read ids from a work list (first seeding pass: all reads, longest first; later
-// phases: the lists the chain kernel fills) and runs one phase of classify_seq for that read in its own scratch.
-__device__ __forceinline__ void warp_setup(const ClassifyLaunch &A, ReadState &S, uint8_t *smem_raw)
+// Persistent phase kernels: every warp pulls read ids from a work list (chaining after the fast pass: all reads, longest first;
+// later phases: the lists the chain kernel fills) and runs one phase of classify_seq for that read in its own scratch.
+__device__ __forceinline__ void scratch_setup(const ClassifyLaunch &A, ReadState &S, uint32_t slot)
 {
-	const int warp = threadIdx.x >> 5;
-	const uint32_t gw = blockIdx.x * CLASSIFY_WARPS_PER_BLOCK + warp;
+	uint8_t *base = A.P.scratch + (uint64_t)slot * A.P.scratch_stride;
 	S.ix = &A.P.ix;
-	S.sm = (WarpSmem *)smem_raw + warp;
-	uint8_t *base = A.P.scratch + (uint64_t)gw * A.P.scratch_stride;
-	S.ws.anc = (DevAnchor *)(base + A.L.anc); S.ws.anc_tmp = (DevAnchor *)(base + A.L.anc_tmp);
+	S.ws.anc = nullptr; S.ws.anc_tmp = (DevAnchor *)(base + A.L.anc_tmp);
 	S.ws.chain = (DevChain *)(base + A.L.chain); S.ws.chain_tmp = (DevChain *)(base + A.L.chain_tmp);
 	S.ws.sms = (DevSms *)(base + A.L.sms); S.ws.score_v = (int *)(base + A.L.score_v);
 	S.ws.sc_hash = (ScHash *)(base + A.L.sc_hash);
-	S.ws.sp_set = (uint64_t *)(base + A.L.sp_set); S.ws.sp_gen = (uint32_t *)(base + A.L.sp_gen); S.ws.lane_mem = (MemRst *)(base + A.L.lane_mem);
-	S.ws.seed_rec = (SeedRec *)(base + A.L.seed_rec); S.ws.chunk_next = (uint32_t *)(base + A.L.chunk_next);
 	S.ws.sms_tmp = (DevSms *)(base + A.L.sms_tmp); S.ws.cand = (uint2 *)(base + A.L.cand);
 	for (int s = 0; s < 2; s++) { S.ws.sort_key[s] = (uint64_t *)(base + A.L.sort_key[s]); S.ws.sort_idx[s] = (uint32_t *)(base + A.L.sort_idx[s]); }
 	S.max_anchors = A.P.max_anchors; S.max_matches = A.P.max_matches;
 	S.team = nullptr; S.mt = nullptr; S.l_read = 0;
+}
+__device__ __forceinline__ void warp_setup(const ClassifyLaunch &A, ReadState &S, uint8_t *smem_raw)
+{
+	const int warp = threadIdx.x >> 5;
+	S.sm = (WarpSmem *)smem_raw + warp;
+	scratch_setup(A, S, blockIdx.x * CLASSIFY_WARPS_PER_BLOCK + warp);
 }
 // next read of the launch's work list, or 0xffffffff; list < 0: all reads in `order`
 __device__ __forceinline__ uint32_t next_read(const ClassifyParams &P, int list, int cursor)
@@ -247,64 +282,18 @@ __device__ __forceinline__ uint32_t next_read(const ClassifyParams &P, int list,
 #ifndef CLASSIFY_WARPS_PER_SM
 #define CLASSIFY_WARPS_PER_SM 16          // resident classify warps per SM the phase kernels are compiled for (register budget 65536 / (32 * this))
 #endif
-#ifndef SEED_REG_WARPS
-#define SEED_REG_WARPS CLASSIFY_WARPS_PER_SM    // warps per SM the register budget of k_seed / k_chain is cut for (>= the launched number: launches of several contexts can then share an SM)
+#ifndef SEED_WARPS_PER_SM
+#define SEED_WARPS_PER_SM 16              // resident warps per SM of k_seed (register budget; 8 KB of shared memory per warp for the visited-row sets)
 #endif
-#define SEED_MIN_BLOCKS (SEED_REG_WARPS / CLASSIFY_WARPS_PER_BLOCK)
 #define SCORE_MIN_BLOCKS (CLASSIFY_WARPS_PER_SM / CLASSIFY_WARPS_PER_BLOCK)
-__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SEED_MIN_BLOCKS) k_seed(const __grid_constant__ ClassifyLaunch A, int pass, int list, int cursor)
+// lane per island seed over the flat task list of the pass (dsb_seed.cuh)
+__global__ void __launch_bounds__(SEED_WARPS_PER_BLOCK * 32, SEED_WARPS_PER_SM / SEED_WARPS_PER_BLOCK) k_seed(const __grid_constant__ SeedPassParams P)
 {
-	extern __shared__ __align__(16) uint8_t smem_raw[];
-	ReadState S;
-	warp_setup(A, S, smem_raw);
-	DevAnchor *scratch_anc = S.ws.anc;
-	WarpSmem *sm = S.sm;
-	if (list >= 0) {
-		// the work lists are in no particular order: take the long reads of the list first (their seeding is the tail of the pass)
-		for (int sweep = 0; sweep < 2; sweep++)
-			for (uint32_t r; (r = next_read(A.P, list, cursor + 12 * sweep)) != 0xffffffffu;) {
-				const bool is_long = (A.P.read_off[r + 1] - A.P.read_off[r]) > 12000;
-				if (is_long != (sweep == 0)) continue;
-				__syncwarp();
-				if (lane_id() == 0) { sm->grp_read[0] = r; sm->grp_n = 1; }
-				phase_seed(A.P, S, pass, scratch_anc);
-			}
-		return;
-	}
-	// first pass over all reads in `order` (longest first): the long ones SEED_GROUP at a time -- as one group of jobs while
-	// their island seeds stay below GROUP_SEEDS, else in smaller groups -- the short tail 32 reads per warp
-	for (;;) {
-		uint32_t i0 = 0;
-		if (lane_id() == 0) i0 = atomicAdd(A.P.ctl + CTL_CURSOR + cursor, (uint32_t)SEED_GROUP);
-		i0 = __shfl_sync(DSB_FULL, i0, 0);
-		if (i0 >= A.P.n_long) break;
-		const uint32_t cnt = min((uint32_t)SEED_GROUP, A.P.n_long - i0);
-		for (uint32_t q = 0; q < cnt;) {
-			uint32_t g = 0, tot = 0;
-			__syncwarp();
-			while (q + g < cnt) {
-				const uint32_t r = A.P.order[i0 + q + g];
-				const uint32_t ns = A.P.n_seeds[0][r] + A.P.n_seeds[1][r];
-				if (g > 0 && tot + ns > GROUP_SEEDS) break;
-				if (lane_id() == 0) sm->grp_read[g] = r;
-				g++; tot += ns;
-			}
-			if (lane_id() == 0) sm->grp_n = g;
-			phase_seed(A.P, S, pass, scratch_anc);
-			q += g;
-		}
-	}
-	const uint32_t n_short = A.P.n_reads - A.P.n_long;
-	for (;;) {
-		uint32_t i0 = 0;
-		if (lane_id() == 0) i0 = atomicAdd(A.P.ctl + CTL_CURSOR + 11, 32u);
-		i0 = __shfl_sync(DSB_FULL, i0, 0);
-		if (i0 >= n_short) break;
-		phase_seed_group(A.P, S, A.P.n_long + i0, min(32u, n_short - i0), scratch_anc);
-	}
+	__shared__ uint32_t s_vis1[SEED_WARPS_PER_BLOCK][VIS1_SLOTS][32];
+	seed_warp_loop(P, s_vis1[threadIdx.x >> 5]);
 }
 
-__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SEED_MIN_BLOCKS) k_chain(const __grid_constant__ ClassifyLaunch A, int pass, int list, int cursor)
+__global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SCORE_MIN_BLOCKS) k_chain(const __grid_constant__ ClassifyLaunch A, int pass, int list, int cursor)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	ReadState S;
@@ -328,7 +317,6 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SCORE_MIN_BLOCK
 
 // Reads with many anchors (repeats) carry the long tail of a batch: their sparse DP looks back over thousands of matches.
 // They get a whole CTA each: warp 0 runs phase_score, the other warps serve its DP look-backs (dp_team_helper_loop).
-// Runs on a second stream next to k_score.
 __global__ void __launch_bounds__(TEAM_WARPS * 32) k_score_heavy(const __grid_constant__ ClassifyLaunch A, int list, int cursor, uint32_t slot0)
 {
 	__shared__ __align__(16) WarpSmem wsm;
@@ -337,17 +325,8 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) k_score_heavy(const __grid_co
 	const int warp = threadIdx.x >> 5;
 	if (warp == 0) {
 		ReadState S;
-		S.ix = &A.P.ix; S.sm = &wsm; S.team = &team;
-		uint8_t *base = A.P.scratch + (uint64_t)(slot0 + blockIdx.x) * A.P.scratch_stride;       // scratch slots of their own
-		S.ws.anc = (DevAnchor *)(base + A.L.anc); S.ws.anc_tmp = (DevAnchor *)(base + A.L.anc_tmp);
-		S.ws.chain = (DevChain *)(base + A.L.chain); S.ws.chain_tmp = (DevChain *)(base + A.L.chain_tmp);
-		S.ws.sms = (DevSms *)(base + A.L.sms); S.ws.score_v = (int *)(base + A.L.score_v);
-		S.ws.sc_hash = (ScHash *)(base + A.L.sc_hash);
-		S.ws.sp_set = (uint64_t *)(base + A.L.sp_set); S.ws.sp_gen = (uint32_t *)(base + A.L.sp_gen); S.ws.lane_mem = (MemRst *)(base + A.L.lane_mem);
-		S.ws.seed_rec = (SeedRec *)(base + A.L.seed_rec); S.ws.chunk_next = (uint32_t *)(base + A.L.chunk_next);
-		S.ws.sms_tmp = (DevSms *)(base + A.L.sms_tmp); S.ws.cand = (uint2 *)(base + A.L.cand);
-		for (int s = 0; s < 2; s++) { S.ws.sort_key[s] = (uint64_t *)(base + A.L.sort_key[s]); S.ws.sort_idx[s] = (uint32_t *)(base + A.L.sort_idx[s]); }
-		S.max_anchors = A.P.max_anchors; S.max_matches = A.P.max_matches; S.mt = &msm; S.l_read = 0;
+		scratch_setup(A, S, slot0 + blockIdx.x);             // scratch slots of their own
+		S.sm = &wsm; S.team = &team; S.mt = &msm;
 		for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_score(A.P, S, r);
 		if (lane_id() == 0) team.cmd = -1;
 		__syncthreads();                                 // releases the helpers
@@ -453,7 +432,7 @@ extern "C" void dsb_opts_default(dsb_opts *o)
 {
 	if (!o) return;
 	o->l_min_match = 170; o->min_score = 64;               // cly_mt.c:486
-	o->max_anchors = 16384; o->max_matches = 16384; o->max_read_len = 1u << 20; o->warps_per_sm = CLASSIFY_WARPS_PER_SM;
+	o->max_anchors = 16384; o->max_matches = 16384; o->max_read_len = 1u << 20; o->warps_per_sm = CLASSIFY_WARPS_PER_SM; o->pool_scale_pct = 100;
 }
 
 extern "C" int dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out)
@@ -464,20 +443,19 @@ extern "C" int dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out)
 	dsb_ctx *c = new dsb_ctx();
 	c->ix = ix;
 	if (o) c->opts = *o; else dsb_opts_default(&c->opts);
-	if (c->opts.max_anchors < 32 * SHORT_LANE_ANCHORS) c->opts.max_anchors = 32 * SHORT_LANE_ANCHORS;   // the lane-per-read path cuts the buffer in 32
+	if (c->opts.max_anchors < 1024) c->opts.max_anchors = 1024;
 	if (c->opts.max_matches < 1024) c->opts.max_matches = 1024;
 	if (c->opts.warps_per_sm < CLASSIFY_WARPS_PER_BLOCK) c->opts.warps_per_sm = CLASSIFY_WARPS_PER_BLOCK;
 	if (c->opts.warps_per_sm > 32) c->opts.warps_per_sm = 32;
-	c->stream = nullptr; c->stream2 = nullptr; c->ev_fork = nullptr; c->ev_join = nullptr; c->h_pin = nullptr; c->h_pin_cap = 0; c->ran = false; c->launches = 0;
-	c->n_reads = 0; c->m_bin_read = 0; c->scratch_zeroed_stride = 0; c->scratch_stride = 0; c->rec_len = 0; c->hits_cap = 0;
+	c->stream = nullptr; c->h_pin = nullptr; c->h_pin_cap = 0; c->ran = false; c->launches = 0;
+	c->n_reads = 0; c->m_bin_read = 0; c->scratch_stride = 0; c->hits_cap = 0; c->task_cap = 0; c->n_chunks = 0; c->max_read_l_in = 0; c->retries = 0;
+	for (int k = 0; k < 5; k++) c->grow[k] = 0;
 	cudaDeviceProp prop;
 	DSB_CUDA(cudaGetDeviceProperties(&prop, ix->device));
 	c->n_sm = prop.multiProcessorCount;
 	c->n_warps = c->n_sm * (int)(c->opts.warps_per_sm / CLASSIFY_WARPS_PER_BLOCK) * CLASSIFY_WARPS_PER_BLOCK;
+	c->seed_blocks = c->n_sm * (SEED_WARPS_PER_SM / SEED_WARPS_PER_BLOCK);
 	DSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-	DSB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-	DSB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-	DSB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 	for (int i = 0; i < DSB_N_EV; i++) DSB_CUDA(cudaEventCreate(&c->ev[i]));
 	int rc = ensure(c->counters, DSB_CNT_COUNT * 8);
 	if (rc != DSB_OK) { dsb_ctx_free(c); return rc; }
@@ -492,13 +470,12 @@ extern "C" void dsb_ctx_free(dsb_ctx *c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = {&c->seqs, &c->read_off, &c->bin_off, &c->bits_off, &c->seed_off, &c->tiles, &c->bin, &c->bits, &c->seeds[0], &c->seeds[1],
 	                  &c->n_seeds[0], &c->n_seeds[1], &c->total_score[0], &c->total_score[1], &c->scratch, &c->rr, &c->hits, &c->counters, &c->prof, &c->work, &c->anc_pool, &c->chain_pool,
-	                  &c->lists[0], &c->lists[1], &c->lists[2], &c->lists[3], &c->lists[4], &c->ctl, &c->order, &c->hdr7};
+	                  &c->lists[0], &c->lists[1], &c->lists[2], &c->lists[3], &c->ctl, &c->order, &c->hdr7,
+	                  &c->pk, &c->tasks[0], &c->tasks[1], &c->recs, &c->chunks, &c->lane_mem, &c->vis2, &c->vis1_full, &c->vis_gen,
+	                  &c->task_first[0], &c->task_first[1], &c->task_cnt[0], &c->task_cnt[1]};
 	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
 	if (c->h_pin) cudaFreeHost(c->h_pin);
 	for (int i = 0; i < DSB_N_EV; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-	if (c->ev_join) cudaEventDestroy(c->ev_join);
-	if (c->stream2) cudaStreamDestroy(c->stream2);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -567,8 +544,6 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 		for (uint32_t l = max_len + 1; l-- > 0;) { const uint32_t n_l = first[l]; first[l] = run; run += n_l; }   // first[l] = reads longer than l
 		for (uint32_t r = 0; r < n_reads; r++) h_order[first[(uint32_t)(offs[r + 1] - offs[r])]++] = r;
 	}
-	c->n_long = 0;
-	for (uint32_t r = 0; r < n_reads; r++) if (offs[r + 1] - offs[r] > SHORT_READ_MAX) c->n_long++;
 	// policy P3: the capacity of the reference's bin_read buffer (BUFF_REALLOC, utils.h:117-122) in input order decides the
 	// chunk-header byte an alignment that runs 7 bases off the start of a read compares with
 	uint8_t *h_hdr7 = (uint8_t *)(h_order + n_reads);
@@ -605,35 +580,56 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 	return DSB_OK;
 }
 
+// zero-initialised grow-only buffer (the visited-row tables and their generation counters start at zero)
+static int ensure_zeroed(DevBuf &b, size_t bytes, cudaStream_t st)
+{
+	if (bytes <= b.cap) return DSB_OK;
+	int rc = ensure(b, bytes);
+	if (rc != DSB_OK) return rc;
+	DSB_CUDA(cudaMemsetAsync(b.p, 0, b.cap, st));
+	return DSB_OK;
+}
+
 extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 {
 	if (!c) return DSB_E_ARG;
 	DSB_CUDA(cudaSetDevice(c->ix->device));
 	cudaStream_t st = c->stream;
 	c->launches = 0;
+	c->max_read_l_in = max_read_l_in;
 	const uint32_t n = c->n_reads;
 	if (n == 0) { c->ran = true; return DSB_OK; }
-	// classify scratch: the per-seed records are sized by the longest read seen
-	if (c->max_len + 64 > c->rec_len || c->scratch_stride == 0) c->rec_len = std::max(c->rec_len, c->max_len + 64);
-	const ScratchLayout L = scratch_layout(c->opts.max_anchors, c->opts.max_matches, c->rec_len);
+	const ScratchLayout L = scratch_layout(c->opts.max_anchors, c->opts.max_matches);
 	c->scratch_stride = L.total;
 	int rc;
-	{
-		const void *before = c->scratch.p;
-		if ((rc = ensure(c->scratch, (size_t)L.total * (c->n_warps + HEAVY_BLOCKS))) != DSB_OK) return rc;
-		// the visited-row hash sets (and their generation counters) must start zeroed; a changed layout moves them
-		if (c->scratch.p != before || L.total != c->scratch_zeroed_stride) { DSB_CUDA(cudaMemsetAsync(c->scratch.p, 0, c->scratch.cap, st)); c->scratch_zeroed_stride = L.total; }
-	}
+	if ((rc = ensure(c->scratch, (size_t)L.total * (c->n_warps + HEAVY_BLOCKS))) != DSB_OK) return rc;
+	// Pools between the phase kernels, sized from the batch; a kernel that runs out of one sets its bit in ctl[CTL_OVERFLOW] and
+	// dsb_batch_download doubles that pool and runs the batch again (grow[] keeps the factor for the batches that follow).
+	const uint64_t sc = c->opts.pool_scale_pct ? c->opts.pool_scale_pct : 100;
+	auto pool = [&](uint64_t base, int k) { return std::min<uint64_t>(((base * sc / 100) << c->grow[k]) + 1024, 0xfffffff0ull); };
+	const uint64_t task_cap = pool(c->n_bases / 32 + 4ull * n, 0), n_chunks = pool(c->n_bases / 32 + 8ull * n, 1);
+	const uint64_t anc_cap = pool(c->n_bases / 8 + 64ull * n + (1u << 16), 2), chain_cap = pool(c->n_bases / 32 + 16ull * n + (1u << 14), 3);
 	// hits: the pre-filter chains of a read use 2 slots each (second half = merge-sort scratch)
-	const uint64_t hits_cap = std::max<uint64_t>(4096, (uint64_t)n * 24);
+	const uint64_t hits_cap = pool(std::max<uint64_t>(4096, (uint64_t)n * 24), 4);
 	if ((rc = ensure(c->hits, hits_cap * sizeof(dsb_hit))) != DSB_OK) return rc;
 	if ((rc = ensure(c->prof, (size_t)n * 32)) != DSB_OK) return rc;
-	// state between the phase kernels: per-read records, anchor / chain pools (bump-allocated per read), work lists
-	const uint64_t anc_cap = c->n_bases / 8 + 64ull * n + (1u << 16), chain_cap = c->n_bases / 32 + 16ull * n + (1u << 14);
 	if ((rc = ensure(c->work, (size_t)n * sizeof(ReadWork))) || (rc = ensure(c->anc_pool, anc_cap * sizeof(DevAnchor))) ||
 	    (rc = ensure(c->chain_pool, chain_cap * sizeof(DevChain))) || (rc = ensure(c->ctl, CTL_WORDS * 4)))
 		return rc;
 	for (int l = 0; l < N_LISTS; l++) if ((rc = ensure(c->lists[l], (size_t)n * 4)) != DSB_OK) return rc;
+	// seeding: packed strands, task lists, per-task records, staging chunks, per-lane memory of the persistent k_seed grid
+	const uint64_t seed_lanes = (uint64_t)c->seed_blocks * SEED_WARPS_PER_BLOCK * 32;
+	const bool big_rows = c->ix->dev.n_lines * 128 >= (1ull << 32);
+	if ((rc = ensure(c->pk, (c->bits_words / N_BITVEC + 4) * 8)) || (rc = ensure(c->tasks[0], task_cap * sizeof(SeedTaskRef))) ||
+	    (rc = ensure(c->tasks[1], task_cap * sizeof(SeedTaskRef))) || (rc = ensure(c->recs, task_cap * sizeof(SeedRec))) ||
+	    (rc = ensure(c->chunks, n_chunks * 64)) || (rc = ensure(c->lane_mem, seed_lanes * SEED_MEM_SLOTS * sizeof(MemRst))) ||
+	    (rc = ensure_zeroed(c->vis2, seed_lanes * VIS2_SLOTS * 8, st)) || (rc = ensure_zeroed(c->vis_gen, seed_lanes * 4, st)) ||
+	    (rc = ensure(c->vis1_full, big_rows ? seed_lanes * VIS1_SLOTS * 8 : 64)))
+		return rc;
+	for (int s = 0; s < 2; s++) if ((rc = ensure(c->task_first[s], (size_t)n * 4)) || (rc = ensure(c->task_cnt[s], (size_t)n * 4))) return rc;
+	c->task_cap = (uint32_t)(std::min<uint64_t>(c->tasks[0].cap, c->tasks[1].cap) / sizeof(SeedTaskRef));
+	c->task_cap = (uint32_t)std::min<uint64_t>(c->task_cap, c->recs.cap / sizeof(SeedRec));
+	c->n_chunks = (uint32_t)std::min<uint64_t>(c->chunks.cap / 64, 0xfffffff0u);
 	DSB_CUDA(cudaMemsetAsync(c->ctl.p, 0, CTL_WORDS * 4, st));
 	DSB_CUDA(cudaMemsetAsync(c->prof.p, 0, (size_t)n * 32, st));
 	c->hits_cap = c->hits.cap / sizeof(dsb_hit);
@@ -645,6 +641,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		ProbeParams P;
 		P.ix = c->ix->dev; P.seqs = (const char *)c->seqs.p; P.read_off = (const uint64_t *)c->read_off.p; P.bin_off = (const uint64_t *)c->bin_off.p;
 		P.bits_off = (const uint64_t *)c->bits_off.p; P.tiles = (const uint2 *)c->tiles.p; P.hdr7 = (const uint8_t *)c->hdr7.p; P.bin = (uint8_t *)c->bin.p; P.bits = (uint32_t *)c->bits.p;
+		P.pk = (uint64_t *)c->pk.p;
 		k_encode_probe<<<c->n_tiles, PROBE_THREADS, 0, st>>>(P);
 		c->launches++;
 	}
@@ -655,6 +652,8 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		P.seed_off = (const uint32_t *)c->seed_off.p; P.bits = (const uint32_t *)c->bits.p;
 		for (int s = 0; s < 2; s++) { P.seeds[s] = (dsb_seed *)c->seeds[s].p; P.n_seeds[s] = (uint32_t *)c->n_seeds[s].p; P.total_score[s] = (uint32_t *)c->total_score[s].p; }
 		P.counters = cnt;
+		P.tasks = (SeedTaskRef *)c->tasks[PASS_FAST & 1].p; P.task_cap = c->task_cap; P.ctl = (uint32_t *)c->ctl.p;
+		for (int s = 0; s < 2; s++) { P.task_first[s] = (uint32_t *)c->task_first[s].p; P.task_cnt[s] = (uint32_t *)c->task_cnt[s].p; }
 		k_islands<<<(2 * n + 127) / 128, 128, 0, st>>>(P);
 		c->launches++;
 	}
@@ -665,7 +664,9 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		P.ix = c->ix->dev; P.n_reads = n; P.read_off = (const uint64_t *)c->read_off.p; P.bin_off = (const uint64_t *)c->bin_off.p; P.bin = (const uint8_t *)c->bin.p;
 		P.seed_off = (const uint32_t *)c->seed_off.p;
 		for (int s = 0; s < 2; s++) { P.seeds[s] = (const dsb_seed *)c->seeds[s].p; P.n_seeds[s] = (const uint32_t *)c->n_seeds[s].p; P.total_score[s] = (const uint32_t *)c->total_score[s].p; }
-		P.order = (const uint32_t *)c->order.p; P.n_long = c->n_long; P.prof = (uint32_t *)c->prof.p;
+		P.order = (const uint32_t *)c->order.p; P.prof = (uint32_t *)c->prof.p;
+		for (int s = 0; s < 2; s++) { P.tasks[s] = (SeedTaskRef *)c->tasks[s].p; P.recs[s] = (SeedRec *)c->recs.p; P.task_first[s] = (uint32_t *)c->task_first[s].p; P.task_cnt[s] = (uint32_t *)c->task_cnt[s].p; }
+		P.task_cap = c->task_cap; P.chunks = (const uint4 *)c->chunks.p;
 		P.work = (ReadWork *)c->work.p;
 		P.anc_pool = (DevAnchor *)c->anc_pool.p; P.anc_pool_cap = (uint32_t)std::min<uint64_t>(c->anc_pool.cap / sizeof(DevAnchor), 0xfffffff0u);
 		P.chain_pool = (DevChain *)c->chain_pool.p; P.chain_pool_cap = (uint32_t)std::min<uint64_t>(c->chain_pool.cap / sizeof(DevChain), 0xfffffff0u);
@@ -676,23 +677,28 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		P.rr = (dsb_read_result *)c->rr.p; P.hits = (dsb_hit *)c->hits.p; P.hits_cap = c->hits_cap; P.hits_cursor = cnt + DSB_CNT_HITS_CURSOR;
 		P.counters = cnt;
 		A.L = L;
+		SeedPassParams SP;
+		SP.E.ix = c->ix->dev; SP.E.pk = (const uint64_t *)c->pk.p; SP.E.read_off = P.read_off; SP.E.bits_off = (const uint64_t *)c->bits_off.p; SP.E.seed_off = P.seed_off;
+		SP.E.seeds[0] = P.seeds[0]; SP.E.seeds[1] = P.seeds[1]; SP.E.recs = (SeedRec *)c->recs.p; SP.E.chunks = (uint4 *)c->chunks.p; SP.E.n_chunks = c->n_chunks;
+		SP.E.big_rows = big_rows ? 1 : 0;
+		SP.ctl = P.ctl; SP.task_cap = c->task_cap;
+		SP.lane_mem = (MemRst *)c->lane_mem.p; SP.vis2 = (uint64_t *)c->vis2.p; SP.vis1_full = (uint64_t *)c->vis1_full.p; SP.vis_gen = (uint32_t *)c->vis_gen.p;
+		auto seed = [&](int pass) { SP.pass = pass; SP.E.slow = pass != PASS_FAST; SP.E.tasks = (const SeedTaskRef *)c->tasks[pass & 1].p; k_seed<<<c->seed_blocks, SEED_WARPS_PER_BLOCK * 32, 0, st>>>(SP); };
 		const int blocks = c->n_warps / CLASSIFY_WARPS_PER_BLOCK, threads = CLASSIFY_WARPS_PER_BLOCK * 32;
 		const size_t smem = CLASSIFY_WARPS_PER_BLOCK * sizeof(WarpSmem);
 		// classify_seq's control flow (cly.c:3098-3131) as a sequence of phase kernels over work lists
-		k_seed <<<blocks, threads, smem, st>>>(A, PASS_FAST, -1, 0);
-		k_seed <<<blocks, threads, smem, st>>>(A, PASS_FAST, LIST_SEED_REDO, 10);    // short reads whose lane buffer overflowed
-		DSB_CUDA(cudaEventRecord(c->ev[3], st));
+		seed(PASS_FAST);                                                        DSB_CUDA(cudaEventRecord(c->ev[3], st));
 		k_chain<<<blocks, threads, smem, st>>>(A, PASS_FAST, -1, 1);            DSB_CUDA(cudaEventRecord(c->ev[4], st));
-		k_seed <<<blocks, threads, smem, st>>>(A, PASS_SLOW0, LIST_SLOW0, 2);   DSB_CUDA(cudaEventRecord(c->ev[5], st));
+		seed(PASS_SLOW0);                                                       DSB_CUDA(cudaEventRecord(c->ev[5], st));
 		k_chain<<<blocks, threads, smem, st>>>(A, PASS_SLOW0, LIST_SLOW0, 3);   DSB_CUDA(cudaEventRecord(c->ev[6], st));
-		k_seed <<<blocks, threads, smem, st>>>(A, PASS_SLOW1, LIST_SLOW1, 4);   DSB_CUDA(cudaEventRecord(c->ev[7], st));
+		seed(PASS_SLOW1);                                                       DSB_CUDA(cudaEventRecord(c->ev[7], st));
 		k_chain<<<blocks, threads, smem, st>>>(A, PASS_SLOW1, LIST_SLOW1, 5);   DSB_CUDA(cudaEventRecord(c->ev[8], st));
 		// scoring: a warp per read; the few reads that give up there (ERR_DEFER) then get a CTA each
 		k_score<<<blocks, threads, smem + CLASSIFY_WARPS_PER_BLOCK * sizeof(MatchSmem), st>>>(A, LIST_SCORE, 6);
 		DSB_CUDA(cudaEventRecord(c->ev[9], st));
 		k_score_heavy<<<HEAVY_BLOCKS, TEAM_WARPS * 32, 0, st>>>(A, LIST_SCORE_HEAVY, 7, (uint32_t)c->n_warps);
 		DSB_CUDA(cudaEventRecord(c->ev[10], st));
-		c->launches += 9;
+		c->launches += 8;
 	}
 	{
 		FinalizeParams P;
@@ -716,20 +722,36 @@ extern "C" int dsb_batch_sync(dsb_ctx *c)
 	return DSB_OK;
 }
 
+#define DSB_MAX_RETRIES 6
 extern "C" int dsb_batch_download(dsb_ctx *c, int32_t *max_read_l_out, dsb_read_result *rr, dsb_hit *hits, uint64_t hits_cap, uint64_t *n_hits_out)
 {
 	if (!c || !c->ran) { dsb_set_error("dsb_batch_download: no batch has been run"); return DSB_E_ARG; }
 	DSB_CUDA(cudaSetDevice(c->ix->device));
 	if (n_hits_out) *n_hits_out = 0;
+	if (max_read_l_out) *max_read_l_out = c->max_read_l_in;
 	if (c->n_reads == 0) return DSB_OK;
 	cudaStream_t st = c->stream;
 	unsigned long long h_cnt[DSB_CNT_COUNT];
-	DSB_CUDA(cudaMemcpyAsync(h_cnt, c->counters.p, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+	c->retries = 0;
+	for (;;) {
+		uint32_t ovf = 0;
+		DSB_CUDA(cudaMemcpyAsync(h_cnt, c->counters.p, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+		DSB_CUDA(cudaMemcpyAsync(&ovf, (uint32_t *)c->ctl.p + CTL_OVERFLOW, 4, cudaMemcpyDeviceToHost, st));
+		DSB_CUDA(cudaStreamSynchronize(st));
+		if (ovf & OVF_STUCK) { dsb_set_error("seeding did not terminate (malformed index?)"); return DSB_E_CUDA; }
+		if (!ovf || c->retries >= DSB_MAX_RETRIES) break;
+		// a pool between the phase kernels overflowed (a batch far richer in seeds / anchors / chains than the sizing assumes):
+		// double the pools concerned and run the batch again -- its inputs are still resident
+		for (int k = 0; k < 5; k++) if (ovf & (1u << k)) c->grow[k]++;
+		c->retries++;
+		int rc = dsb_batch_run(c, c->max_read_l_in);
+		if (rc != DSB_OK) return rc;
+	}
 	if (rr) DSB_CUDA(cudaMemcpyAsync(rr, c->rr.p, (size_t)c->n_reads * sizeof(dsb_read_result), cudaMemcpyDeviceToHost, st));
 	DSB_CUDA(cudaStreamSynchronize(st));
 	const uint64_t used = std::min<uint64_t>(h_cnt[DSB_CNT_HITS_CURSOR], c->hits_cap);
 	if (n_hits_out) *n_hits_out = used;
-	if (max_read_l_out) *max_read_l_out = (int32_t)h_cnt[DSB_CNT_MAX_READ_L];
+	if (max_read_l_out) *max_read_l_out = std::max<int32_t>((int32_t)h_cnt[DSB_CNT_MAX_READ_L], c->max_read_l_in);
 	if (hits && used) {
 		if (used > hits_cap) { dsb_set_error("hits array too small: %llu needed, %llu given", (unsigned long long)used, (unsigned long long)hits_cap); return DSB_E_CAPACITY; }
 		DSB_CUDA(cudaMemcpyAsync(hits, c->hits.p, used * sizeof(dsb_hit), cudaMemcpyDeviceToHost, st));
@@ -742,15 +764,16 @@ extern "C" int dsb_batch_download(dsb_ctx *c, int32_t *max_read_l_out, dsb_read_
 	return DSB_OK;
 }
 
+extern "C" int dsb_batch_retries(dsb_ctx *c) { return c ? c->retries : 0; }
+
 extern "C" int dsb_classify_batch(dsb_ctx *c, const char *seqs, const uint64_t *offs, uint32_t n_reads, int32_t max_read_l_in, int32_t *max_read_l_out,
                                   dsb_read_result *rr, dsb_hit *hits, uint64_t hits_cap, uint64_t *n_hits_out)
 {
 	int rc;
+	if (max_read_l_out) *max_read_l_out = max_read_l_in;
 	if ((rc = dsb_batch_upload(c, seqs, offs, n_reads)) != DSB_OK) return rc;
 	if ((rc = dsb_batch_run(c, max_read_l_in)) != DSB_OK) return rc;
-	rc = dsb_batch_download(c, max_read_l_out, rr, hits, hits_cap, n_hits_out);
-	if (max_read_l_out && (rc == DSB_OK || rc == DSB_E_CAPACITY)) *max_read_l_out = std::max(*max_read_l_out, max_read_l_in);
-	return rc;
+	return dsb_batch_download(c, max_read_l_out, rr, hits, hits_cap, n_hits_out);
 }
 
 extern "C" int dsb_batch_get_seeds(dsb_ctx *c, uint32_t read, int strand, dsb_seed *out, uint32_t cap, uint32_t *n_out, uint32_t *total_score)

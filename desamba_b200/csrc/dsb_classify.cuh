@@ -1,23 +1,16 @@
-// dsb_classify.cuh -- the per-read classifier (seeding by FM-index backward search, anchor chaining, 9-mer sparse-DP
-// scoring) as warp-per-read device code.  Behaviour follows the reference function by function (citations inline);
-// structure is this project's own: anchors/chains are index-linked arrays in per-warp HBM scratch, the visited-row
-// set / flank frame / reference window live in shared memory, the read's 9-mer index is a warp-built CSR table.
+// dsb_classify.cuh -- the warp-per-read phases of the classifier (anchor chaining, 9-mer sparse-DP scoring) and the per-read
+// state between the phase kernels.  Behaviour follows the reference function by function (citations inline); structure is
+// this project's own: anchors/chains are index-linked arrays in HBM pools, the reference window and the hash table of its
+// scanned 9-mers live in shared memory, the read range is streamed through that table.  Seeding is in dsb_seedcore.h /
+// dsb_seed.cuh (lane per island seed over a flat task list).
 #pragma once
 #include "dsb_device.cuh"
 #include <climits>
 #include "../../include/desamba_b200.h"
 
-#define L_PRE_IDX 13
-#define PRE_IDX_MASK 0x3FFFFFFu
-#define SA_MASK 0x7
-#define SA_OFF 3
-#define MIN_UNI_L 35
-#define LV_L 12
 #define S_A_KEMR_L 9
 #define OVER_SEARCH_M2 50
 #define MIN_SCORE_MEM 12
-#define NO_SA 0xFFFFFFFFFFFFFFFFull
-#define SP_SET_CAP 500
 
 struct DevAnchor {              // Anchor (cly.h:44-61), only the fields read after map_seed
 	uint32_t ref_ID, ref_offset, index_in_read;
@@ -32,37 +25,10 @@ struct DevChain {               // chain_item (cly.h:69-89)
 	uint8_t  direction, with_top_anchor, primary, pri_index;
 };
 struct DevSms { uint32_t t_pos, q_pos, len, score; };   // spd_match (cly.h:127-133)
-struct MemRst { int match_len; int sa_sp_l; uint64_t sp, sa_sp; int read_offset; int pad; };   // MEM_rst (cly.c:619-627)
 struct ScHash { uint16_t next; uint16_t seed_ID; uint16_t s_or_e; uint16_t pad; };   // seed_con_hash (cly.h:120-125)
 
-// a seeding job = one strand pass of one read (fast_classify / slow_classify over its island seeds); a warp runs the jobs of
-// up to SEED_GROUP reads at once.  Measured (gpurun_out/bench_vg*.json): groups of 4 / 8 reads take exactly as long as the
-// reads one after the other -- lanes on different seeds are in different code most of the time and a warp has ONE
-// scoreboard, so their latencies do not overlap -- and the coarser work units lengthen the tail of the launch
-// (fast pass 11.5 -> 19.6 -> 27.3 ms).  Hence 1: both strand passes of one read form the set of jobs.
-#ifndef SEED_GROUP
-#define SEED_GROUP 1
-#endif
-#define MAX_SEED_JOBS (2 * SEED_GROUP)
-#ifndef GROUP_SEEDS
-#define GROUP_SEEDS 384
-#endif
-//                              seeds (both strands) of the reads of a group: more and the next read starts a group of its own
-struct SeedJob {
-	const dsb_seed *seed_v; const uint8_t *bin_read;
-	uint32_t l_seed_v, read_len, direction;
-	uint32_t base;              // index of the job's first seed in the combined numbering of the group
-	uint32_t anc_end;           // anchors of the group up to and including this job
-	uint32_t pad;
-};
 struct WarpSmem {               // per-warp shared memory
 	uint8_t  refwin[2176];      // ref[2000] of sdp_middle_M2 / ref[1000] of sdp_right/left_M2 (+ over-read slack)
-	uint32_t next_seed;         // seed_pass: work counter of the lanes
-	uint32_t chunk_cursor;      // seed_pass: next free chunk of the anchor staging pool
-	uint32_t grp_n;             // reads of the current seeding group
-	uint32_t pad;
-	uint32_t grp_read[SEED_GROUP], grp_job0[SEED_GROUP + 4];   // read ids, first job of each read (+ end)
-	SeedJob  job[MAX_SEED_JOBS];
 };
 // per-warp shared memory of the scoring kernels: hash table of the 9-mers of the scanned TARGET positions of one sdp_match
 #define TT_SLOTS 1024           // >= 2 x the scanned positions of a window (t_len < 2000 -> at most 497)
@@ -72,13 +38,9 @@ struct MatchSmem {
 	uint32_t bloom[512];        // one hash bit per scanned 9-mer (16 bits per table slot): the streaming loop tests this first
 	uint32_t n_cand, n_tmp, pad[2];
 };
-#define FR_A 8
-#define FR_B 21
-#define FR_C 34
 
-struct SeedRec;
-struct WarpScratch {            // per-warp HBM scratch
-	DevAnchor *anc, *anc_tmp;   // anc_tmp: staging pool of seed_pass, then merge-sort scratch of chain_insert_M3
+struct WarpScratch {            // per-warp HBM scratch of the chaining / scoring kernels
+	DevAnchor *anc, *anc_tmp;   // anc: the read's anchors (in the anchor pool); anc_tmp: merge-sort scratch of chain_insert_M3
 	DevChain  *chain, *chain_tmp;
 	DevSms    *sms;
 	int       *score_v;         // 1024
@@ -87,11 +49,6 @@ struct WarpScratch {            // per-warp HBM scratch
 	uint2     *cand;            // sdp_match: (scanned target index, read position) pairs with equal 9-mers (CAND_CAP)
 	uint64_t  *sort_key[2];     // sdp_match: order keys of sms_tmp + merge-sort ping-pong (max_matches each)
 	uint32_t  *sort_idx[2];     // merge-sort permutation ping-pong (max_matches each)
-	uint64_t  *sp_set;          // 32 lanes x (SP_SMALL + SP_TAB) slots of the visited-row hash sets, interleaved (zeroed when the scratch is allocated)
-	uint32_t  *sp_gen;          // 32 generation counters of those sets
-	MemRst    *lane_mem;        // 32 lanes x 512
-	SeedRec   *seed_rec;        // one per island seed of a strand
-	uint32_t  *chunk_next;      // max_anchors / ANCHOR_CHUNK links
 };
 
 // per-read state that lives in HBM between the phase kernels
@@ -100,16 +57,17 @@ struct ReadWork {
 	uint32_t chain_off, n_chain;  // chains kept by resolve_tree, in the chain pool
 	uint16_t error; uint8_t fast_classify, pad;
 };
-enum { LIST_SLOW0 = 0, LIST_SLOW1 = 1, LIST_SCORE = 2, LIST_SCORE_HEAVY = 3, LIST_SEED_REDO = 4, N_LISTS = 5 };
+enum { LIST_SLOW0 = 0, LIST_SLOW1 = 1, LIST_SCORE = 2, LIST_SCORE_HEAVY = 3, N_LISTS = 4 };
 // HEAVY: a read whose sparse DP collects more than DEFER_SMS matches in one extension (repeats) gives up in k_score and is
 // re-scored from its (untouched) pool chains by k_score_heavy, a whole CTA per read
 #define DEFER_SMS 1024
 #define ERR_DEFER 7
 enum { PASS_FAST = 0, PASS_SLOW0 = 1, PASS_SLOW1 = 2 };
-// control block (u32): [0..4] list lengths, [5] anchor pool cursor, [6] chain pool cursor, [8..19] work cursors of the launches
-enum { CTL_LIST_N = 0, CTL_ANC_CURSOR = 5, CTL_CHAIN_CURSOR = 6, CTL_CURSOR = 8, CTL_WORDS = 32 };
-#define SHORT_READ_MAX 600          // reads up to this length are seeded one LANE per read in the fast pass
-#define SHORT_LANE_ANCHORS 256      // their lane-private anchor buffer; a read that needs more is redone warp-per-read
+// control block (u32): [0..3] list lengths, [5] anchor pool cursor, [6] chain pool cursor, [7] pools that overflowed (OVF_*),
+// [8..31] work cursors of the launches, [32..34] seed tasks of the three seeding passes, [36..38] their fetch cursors,
+// [40..42] staging-chunk cursors of the passes
+enum { CTL_LIST_N = 0, CTL_ANC_CURSOR = 5, CTL_CHAIN_CURSOR = 6, CTL_OVERFLOW = 7, CTL_CURSOR = 8, CTL_TASK_N = 32, CTL_TASK_CURSOR = 36, CTL_CHUNK_CURSOR = 40, CTL_WORDS = 48 };
+enum { OVF_TASKS = 1, OVF_CHUNKS = 2, OVF_ANCHORS = 4, OVF_CHAINS = 8, OVF_HITS = 16, OVF_STUCK = 1u << 30 };
 
 struct ClassifyParams {
 	DevIndex ix;
@@ -121,9 +79,13 @@ struct ClassifyParams {
 	const dsb_seed *seeds[2];   // [0] forward strand, [1] reverse strand
 	const uint32_t *n_seeds[2];
 	const uint32_t *total_score[2];
-	const uint32_t *order;      // read ids, longest first (work order of the first seeding pass)
-	uint32_t n_long;            // the first n_long entries of `order` are longer than SHORT_READ_MAX
-	uint32_t *prof;             // per read: 8 x u32 phase times in units of 1024 cycles (fast, chain, slow, sdp_match [part of the next three], middle, right, left, total)
+	const uint32_t *order;      // read ids, longest first (work order of the chaining pass over all reads)
+	uint32_t *prof;             // per read: 8 x u32 phase times in units of 1024 cycles (-, chain, -, sdp_match [part of the next three], middle, right, left, total)
+	// seeding: task lists / per-seed records of the passes (ping-pong: fast and slow 1 use [0], slow 0 uses [1]), staging chunks,
+	// the tasks of a (strand, read) in the current pass
+	SeedTaskRef *tasks[2]; SeedRec *recs[2]; uint32_t task_cap;
+	const uint4 *chunks;
+	uint32_t *task_first[2], *task_cnt[2];
 	// state between the phase kernels
 	ReadWork *work;
 	DevAnchor *anc_pool; uint32_t anc_pool_cap;
@@ -1222,206 +1184,68 @@ __device__ __forceinline__ void write_empty_result(const ClassifyParams &P, uint
 	}
 }
 
-// One seeding pass (fast / slow strand 0 / slow strand 1) of the reads S.sm->grp_read[0 .. grp_n): all their strand passes
-// run as one set of jobs (seed_pass); more than one read only in the fast pass.  A group that runs into a capacity is
-// taken apart again: its reads go to the redo list and are seeded one by one.
-__device__ __noinline__ void phase_seed(const ClassifyParams &P, ReadState &S, int pass, DevAnchor *scratch_anc)
-{
-	const long long t0 = clock64();
-	WarpSmem *sm = S.sm;
-	const int lane = lane_id();
-	__syncwarp();
-	const int g = (int)sm->grp_n;
-	read_begin(S);
-	S.ws.anc = scratch_anc;
-	ReadWork w;
-	w.anc_off = w.n_anc = w.chain_off = w.n_chain = 0; w.error = 0; w.fast_classify = 1; w.pad = 0;
-	// jobs
-	int n_jobs = 0; uint32_t base = 0;
-	for (int q = 0; q < g; q++) {
-		const uint32_t r = sm->grp_read[q];
-		const uint32_t read_len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
-		__syncwarp();
-		if (lane == 0) sm->grp_job0[q] = (uint32_t)n_jobs;
-		if (read_len < MIN_READ_LEN) continue;                         // cly.c:3089: untouched (unmapped) result, written below
-		SearchDir sd[2];
-		const bool both_direction = setup_dirs(P, r, read_len, sd);
-		const int d0 = (pass == PASS_SLOW1) ? 1 : 0, d1 = (pass == PASS_FAST && both_direction) ? 1 : d0;
-		for (int d = d0; d <= d1; d++) {
-			if (lane == 0) {
-				SeedJob J; J.seed_v = sd[d].seed_v; J.bin_read = sd[d].bin_read; J.l_seed_v = sd[d].l_seed_v; J.read_len = read_len;
-				J.direction = sd[d].direction; J.base = base; J.anc_end = 0; J.pad = 0;
-				sm->job[n_jobs] = J;
-			}
-			base += sd[d].l_seed_v; n_jobs++;
-		}
-	}
-	__syncwarp();
-	if (lane == 0) sm->grp_job0[g] = (uint32_t)n_jobs;
-	__syncwarp();
-	if (pass != PASS_FAST) {                                           // (one read)
-		w = P.work[sm->grp_read[0]];
-		w.fast_classify = 0;
-		if (pass == PASS_SLOW1) {                                      // the third pass appends to the (re-ordered) anchors of the second (cly.c:3121-3125)
-			const uint64_t *src = (const uint64_t *)(P.anc_pool + w.anc_off); uint64_t *dst = (uint64_t *)scratch_anc;
-			for (uint32_t i = lane; i < w.n_anc * 3; i += 32) dst[i] = src[i];
-			__syncwarp();
-			S.n_anc = w.n_anc;
-		}
-	}
-	if (n_jobs) { PH_BEGIN(); seed_pass(S, n_jobs, pass != PASS_FAST); PH_END(S, pass == PASS_FAST ? 0 : 2); }
-	if (S.error && g > 1) {                                            // take the group apart
-		if (lane == 0) for (int q = 0; q < g; q++) { const uint32_t i = atomicAdd(P.ctl + CTL_LIST_N + LIST_SEED_REDO, 1u); P.list[LIST_SEED_REDO][i] = sm->grp_read[q]; }
-		__syncwarp();
-		return;
-	}
-	// move the anchors of every read to its own region of the pool
-	for (int q = 0; q < g; q++) {
-		const uint32_t r = sm->grp_read[q];
-		const uint32_t read_len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
-		const int j0 = (int)sm->grp_job0[q], j1 = (int)sm->grp_job0[q + 1];
-		if (j0 == j1) {                                                // too short (fast pass only)
-			if (lane == 0) P.work[r] = w;
-			write_empty_result(P, r, read_len, 0, 1, 0);
-			continue;
-		}
-		const uint32_t a0 = (g == 1) ? 0u : ((j0 > 0) ? sm->job[j0 - 1].anc_end : 0u);
-		const uint32_t a1 = (g == 1) ? S.n_anc : sm->job[j1 - 1].anc_end;
-		const uint32_t n = S.error ? 0u : a1 - a0;
-		uint32_t off = 0; int err = S.error;
-		if (n) {
-			if (lane == 0) off = atomicAdd(P.ctl + CTL_ANC_CURSOR, n);
-			off = __shfl_sync(DSB_FULL, off, 0);
-			if ((uint64_t)off + n > P.anc_pool_cap) err = 1;
-			else {
-				const uint64_t *src = (const uint64_t *)(scratch_anc + a0); uint64_t *dst = (uint64_t *)(P.anc_pool + off);
-				for (uint32_t i = lane; i < n * 3; i += 32) dst[i] = src[i];
-			}
-		}
-		ReadWork wr = w;
-		wr.anc_off = off; wr.n_anc = err ? ((g == 1) ? S.n_anc : 0u) : n; wr.error = (uint16_t)err;
-		if (lane == 0) P.work[r] = wr;
-		if (P.prof && lane == 0) { const uint32_t dt = (uint32_t)(((clock64() - t0) / g) >> 10); P.prof[(uint64_t)r * 8 + (pass == PASS_FAST ? 0 : 2)] += dt; P.prof[(uint64_t)r * 8 + 7] += dt; }
-	}
-	if (lane == 0) {
-		unsigned long long *C = P.counters;
-		atomicAdd(C + DSB_CNT_N_PREFIX, (unsigned long long)S.c_prefix);
-		atomicAdd(C + DSB_CNT_N_OCC, (unsigned long long)S.c_occ);
-		atomicAdd(C + DSB_CNT_N_LOCATE, (unsigned long long)S.c_locate);
-		atomicAdd(C + DSB_CNT_N_GETREF, (unsigned long long)S.c_getref);
-		atomicAdd(C + DSB_CNT_N_GETREF_BYTES, (unsigned long long)S.c_getref_bytes);
-	}
-	__syncwarp();
-}
-
-// Fast pass for SHORT reads (<= SHORT_READ_MAX bp: a handful of island seeds each), one LANE per READ: lane l runs
-// fast_classify of read order[i0 + l] start to end -- seeds in order, so the "> 512 skips the next seed" rule is applied as
-// the reference writes it (cly.c:1530-1531) -- with the same lane-private search code as seed_pass.  No warp collective
-// is used between the first and the last line of the per-lane part.
-__device__ void phase_seed_group(const ClassifyParams &P, ReadState &S, uint32_t i0, uint32_t count, DevAnchor *scratch_anc)
-{
-	const long long t0 = clock64();
-	const int lane = lane_id();
-	const bool act = (uint32_t)lane < count;
-	uint32_t c_prefix = 0, c_occ = 0, c_locate = 0, c_getref = 0, c_getref_bytes = 0;
-	uint32_t r = 0, read_len = 0;
-	ReadWork w;
-	w.anc_off = w.n_anc = w.chain_off = w.n_chain = 0; w.error = 0; w.fast_classify = 1; w.pad = 0;
-	SearchDir sd[2];
-	LaneCtx L;
-	L.ix = S.ix; L.sp_set = S.ws.sp_set + lane; L.sp_l = 0; L.sp_gen = S.ws.sp_gen[lane]; L.mem = S.ws.lane_mem + lane * 512;
-	L.pool = nullptr; L.chunk_next = nullptr; L.chunk_cursor = nullptr; L.n_chunks = 0; L.first_chunk = L.cur_chunk = 0;
-	L.lin = scratch_anc + (uint32_t)lane * SHORT_LANE_ANCHORS; L.lin_cap = SHORT_LANE_ANCHORS;
-	L.n_out = 0; L.top_score = 35; L.error = 0;
-	L.c_prefix = L.c_occ = L.c_locate = L.c_getref = L.c_getref_bytes = 0;
-	// lane state: strand pass d, next seed k of it, the running seed task
-	int n_dir = 0, d = 0; uint32_t k = 0, seed_start = 0;
-	SeedTask T; T.stage = 2;
-	bool busy = false, running = false;
-	SeedInfo s_i = {nullptr, 0, 0};
-	if (act) {
-		r = P.order[i0 + lane];
-		read_len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
-		if (read_len < MIN_READ_LEN) {                                 // cly.c:3089: untouched (unmapped) result
-			dsb_read_result out;
-			out.hit_off = 0; out.n_hit = 0; out.n_anchor = 0; out.fast_classify = 1; out.entered_final = 0; out.error = 0; out.read_len = read_len;
-			P.rr[r] = out; P.work[r] = w;
-		} else {
-			n_dir = setup_dirs(P, r, read_len, sd) ? 2 : 1;
-			s_i.bin_read = sd[0].bin_read; s_i.read_L = read_len; s_i.direction = sd[0].direction;
-			busy = true;
-		}
-	}
-	for (;;) {
-		// a busy lane without a running seed advances to its next top seed (or finishes its read)
-		while (busy && !running) {
-			if (k >= sd[d].l_seed_v) {
-				d++; k = 0;
-				if (d >= n_dir) { busy = false; break; }
-				s_i.bin_read = sd[d].bin_read; s_i.direction = sd[d].direction;
-				continue;
-			}
-			const dsb_seed sv = sd[d].seed_v[k];
-			if (sv.top == 0) { k++; continue; }
-			sp_set_clear_t(L); L.top_score = 35; seed_start = L.n_out;
-			seed_task_begin(T, sv, false, L.ix->l_ek);
-			running = true;
-		}
-		if (__all_sync(DSB_FULL, !busy)) break;
-		if (running) {
-			if (T.stage != 2) fast_seed_step(L, T, s_i);
-			if (L.error) { busy = false; running = false; }
-			else if (T.stage == 2) {
-				for (uint32_t a = seed_start; a < L.n_out; a++) L.lin[a].useless = (L.lin[a].score < L.top_score) ? 1 : 0;      // cly.c:1536-1542
-				k += T.flag512 ? 2 : 1;                                  // "> 512": c_sv++ skips the next seed (cly.c:1530-1531)
-				running = false;
-			}
-		}
-		__syncwarp();
-	}
-	S.ws.sp_gen[lane] = L.sp_gen;
-	if (act && read_len >= MIN_READ_LEN) {
-		if (L.error == 6) {                                            // too many anchors for the lane buffer: redo warp-per-read
-			const uint32_t i = atomicAdd(P.ctl + CTL_LIST_N + LIST_SEED_REDO, 1u);
-			P.list[LIST_SEED_REDO][i] = r;
-		} else {
-			uint32_t off = 0;
-			if (!L.error && L.n_out) {
-				off = atomicAdd(P.ctl + CTL_ANC_CURSOR, L.n_out);
-				if ((uint64_t)off + L.n_out > P.anc_pool_cap) L.error = 1;
-				else for (uint32_t a = 0; a < L.n_out; a++) P.anc_pool[off + a] = L.lin[a];
-			}
-			w.anc_off = off; w.n_anc = L.n_out; w.error = (uint16_t)L.error;
-			P.work[r] = w;
-			c_prefix = L.c_prefix; c_occ = L.c_occ; c_locate = L.c_locate; c_getref = L.c_getref; c_getref_bytes = L.c_getref_bytes;
-		}
-	}
-	__syncwarp();
-	c_prefix = __reduce_add_sync(DSB_FULL, c_prefix); c_occ = __reduce_add_sync(DSB_FULL, c_occ); c_locate = __reduce_add_sync(DSB_FULL, c_locate);
-	c_getref = __reduce_add_sync(DSB_FULL, c_getref); c_getref_bytes = __reduce_add_sync(DSB_FULL, c_getref_bytes);
-	if (lane == 0) {
-		unsigned long long *C = P.counters;
-		atomicAdd(C + DSB_CNT_N_PREFIX, (unsigned long long)c_prefix);
-		atomicAdd(C + DSB_CNT_N_OCC, (unsigned long long)c_occ);
-		atomicAdd(C + DSB_CNT_N_LOCATE, (unsigned long long)c_locate);
-		atomicAdd(C + DSB_CNT_N_GETREF, (unsigned long long)c_getref);
-		atomicAdd(C + DSB_CNT_N_GETREF_BYTES, (unsigned long long)c_getref_bytes);
-	}
-	if (act && P.prof) { const uint32_t dt = (uint32_t)((clock64() - t0) >> 10); P.prof[(uint64_t)r * 8 + 0] += dt; P.prof[(uint64_t)r * 8 + 7] += dt; }
-	__syncwarp();
-}
-
+// Chaining phase of one read after a seeding pass: first the anchors of the pass are gathered from the per-seed staging lists
+// into the read's anchor vector (gather_strand, dsb_seed.cuh: the order in which fast_classify / slow_classify push them),
+// then resolve_tree and the decisions of classify_seq (cly.c:3098-3127); a read that goes on to a slow pass gets its seed
+// tasks appended to that pass's list.
 __device__ void phase_chain(const ClassifyParams &P, ReadState &S, uint32_t r, int pass)
 {
 	const long long t0 = clock64();
+	const int lane = lane_id();
 	const uint32_t read_len = (uint32_t)(P.read_off[r + 1] - P.read_off[r]);
-	if (read_len < MIN_READ_LEN) return;
+	ReadWork w;
+	w.anc_off = w.n_anc = w.chain_off = w.n_chain = 0; w.error = 0; w.fast_classify = 1; w.pad = 0;
+	if (read_len < MIN_READ_LEN) {                                     // cly.c:3089: untouched (unmapped) result
+		if (pass == PASS_FAST) { if (lane == 0) P.work[r] = w; write_empty_result(P, r, read_len, 0, 1, 0); }
+		return;
+	}
 	read_begin(S);
-	ReadWork w = P.work[r];
+	if (pass != PASS_FAST) { w = P.work[r]; w.fast_classify = 0; }     // slow_classify: results->fast_classify = false (cly.c:1610)
 	if (w.error) { write_empty_result(P, r, read_len, w.n_anc, w.fast_classify, w.error); return; }
 	SearchDir sd[2];
 	const bool both_direction = setup_dirs(P, r, read_len, sd);
 	const int super_repeat = 0;                                        // always 0 in the reference (cly.c:849-888,1545)
+	{	// gather: fast = strand pass 0 (+ 1 if both_direction), slow 0 = strand pass 0 from scratch (cly.c:3116), slow 1 = strand
+		// pass 1 appended to the (re-ordered) anchors of slow 0 (cly.c:3121-3125)
+		const int d0 = (pass == PASS_SLOW1) ? 1 : 0, d1 = (pass == PASS_FAST && both_direction) ? 1 : d0;
+		const uint32_t n_old = (pass == PASS_SLOW1) ? w.n_anc : 0u;
+		GatherSum G; G.n_anchor = n_old; G.c_prefix = G.c_occ = G.c_locate = G.c_getref = G.c_getref_bytes = 0; G.error = 0;
+		for (int d = d0; d <= d1; d++) gather_strand(P, r, sd[d].direction == DSB_FORWARD ? 0u : 1u, pass, nullptr, G, false);
+		const uint32_t total = G.n_anchor;
+		int err = __reduce_max_sync(DSB_FULL, G.error);
+		uint32_t off = 0;
+		if (total && !err) {
+			if (lane == 0) off = atomicAdd(P.ctl + CTL_ANC_CURSOR, total);
+			off = __shfl_sync(DSB_FULL, off, 0);
+			if ((uint64_t)off + total > P.anc_pool_cap) { err = 1; if (lane == 0) atomicOr(P.ctl + CTL_OVERFLOW, OVF_ANCHORS); }
+			else if (total > S.max_anchors) err = 1;
+		}
+		if (err) {
+			w.n_anc = total; w.error = (uint16_t)err;
+			if (lane == 0) P.work[r] = w;
+			write_empty_result(P, r, read_len, total, w.fast_classify, err);
+			return;
+		}
+		DevAnchor *dst = P.anc_pool + off;
+		if (n_old) {
+			const uint64_t *src = (const uint64_t *)(P.anc_pool + w.anc_off); uint64_t *d64 = (uint64_t *)dst;
+			for (uint32_t i = lane; i < n_old * 3; i += 32) d64[i] = src[i];
+		}
+		GatherSum G2 = G; G2.n_anchor = n_old;
+		for (int d = d0; d <= d1; d++) gather_strand(P, r, sd[d].direction == DSB_FORWARD ? 0u : 1u, pass, dst, G2, true);
+		__syncwarp();
+		w.anc_off = off; w.n_anc = total;
+		const uint32_t c_prefix = __reduce_add_sync(DSB_FULL, G.c_prefix), c_occ = __reduce_add_sync(DSB_FULL, G.c_occ), c_locate = __reduce_add_sync(DSB_FULL, G.c_locate);
+		const uint32_t c_getref = __reduce_add_sync(DSB_FULL, G.c_getref), c_getref_bytes = __reduce_add_sync(DSB_FULL, G.c_getref_bytes);
+		if (lane == 0) {
+			unsigned long long *C = P.counters;
+			atomicAdd(C + DSB_CNT_N_PREFIX, (unsigned long long)c_prefix);
+			atomicAdd(C + DSB_CNT_N_OCC, (unsigned long long)c_occ);
+			atomicAdd(C + DSB_CNT_N_LOCATE, (unsigned long long)c_locate);
+			atomicAdd(C + DSB_CNT_N_GETREF, (unsigned long long)c_getref);
+			atomicAdd(C + DSB_CNT_N_GETREF_BYTES, (unsigned long long)c_getref_bytes);
+		}
+	}
 	S.ws.anc = P.anc_pool + w.anc_off; S.n_anc = w.n_anc;
 	{ PH_BEGIN(); resolve_tree(S); PH_END(S, 1); }
 	int next;                                                           // -1: finished without hits
@@ -1439,14 +1263,22 @@ __device__ void phase_chain(const ClassifyParams &P, ReadState &S, uint32_t r, i
 		next = S.n_hit ? LIST_SCORE : -1;
 	if (next == LIST_SCORE) {
 		uint32_t off = 0;
-		if (lane_id() == 0) off = atomicAdd(P.ctl + CTL_CHAIN_CURSOR, S.n_hit);
+		if (lane == 0) off = atomicAdd(P.ctl + CTL_CHAIN_CURSOR, S.n_hit);
 		off = __shfl_sync(DSB_FULL, off, 0);
-		if ((uint64_t)off + S.n_hit > P.chain_pool_cap) { write_empty_result(P, r, read_len, w.n_anc, w.fast_classify, 1); read_end(P, S, r, t0); return; }
+		if ((uint64_t)off + S.n_hit > P.chain_pool_cap) {
+			if (lane == 0) atomicOr(P.ctl + CTL_OVERFLOW, OVF_CHAINS);
+			write_empty_result(P, r, read_len, w.n_anc, w.fast_classify, 1); read_end(P, S, r, t0); return;
+		}
 		const uint32_t *src = (const uint32_t *)S.ws.chain; uint32_t *dst = (uint32_t *)(P.chain_pool + off);
-		for (uint32_t i = lane_id(); i < S.n_hit * (uint32_t)(sizeof(DevChain) / 4); i += 32) dst[i] = src[i];
+		for (uint32_t i = lane; i < S.n_hit * (uint32_t)(sizeof(DevChain) / 4); i += 32) dst[i] = src[i];
 		w.chain_off = off; w.n_chain = S.n_hit;
-		if (lane_id() == 0) P.work[r] = w;
+	} else if (next == LIST_SLOW0 || next == LIST_SLOW1) {
+		const int d = (next == LIST_SLOW0) ? 0 : 1;
+		if (!slow_tasks_append(P, r, sd[d].direction == DSB_FORWARD ? 0u : 1u, next == LIST_SLOW0 ? PASS_SLOW0 : PASS_SLOW1)) {
+			write_empty_result(P, r, read_len, w.n_anc, 0, 1); read_end(P, S, r, t0); return;
+		}
 	}
+	if (lane == 0) P.work[r] = w;
 	if (next >= 0) list_push(P, next, r);
 	else write_empty_result(P, r, read_len, w.n_anc, w.fast_classify, 0);
 	read_end(P, S, r, t0);
@@ -1481,7 +1313,7 @@ __device__ void phase_score(const ClassifyParams &P, ReadState &S, uint32_t r)
 	if (S.n_hit) {
 		if (lane_id() == 0) off = atomicAdd(P.hits_cursor, (unsigned long long)(2 * S.n_hit));
 		off = __shfl_sync(DSB_FULL, off, 0);
-		if (off + 2ull * S.n_hit > P.hits_cap) { out.error = 4; out.entered_final = 0; S.n_hit = 0; }
+		if (off + 2ull * S.n_hit > P.hits_cap) { out.error = 4; out.entered_final = 0; S.n_hit = 0; if (lane_id() == 0) atomicOr(P.ctl + CTL_OVERFLOW, OVF_HITS); }
 	}
 	out.hit_off = off; out.n_hit = S.n_hit;
 	for (uint32_t i = lane_id(); i < S.n_hit; i += 32) {

@@ -32,20 +32,25 @@ struct DevBuf {                         // grow-only device buffer
 struct dsb_ctx {
 	dsb_index *ix;
 	dsb_opts opts;
-	cudaStream_t stream, stream2;       // stream2: k_score_heavy next to k_score
-	cudaEvent_t ev_fork, ev_join;
+	cudaStream_t stream;
 	int n_sm, n_warps;                  // resident classify warps = n_sm * warps_per_sm
+	int seed_blocks;                    // grid of k_seed (persistent, SEED_WARPS_PER_SM warps per SM)
 	// batch inputs (device)
 	DevBuf seqs, read_off, bin_off, bits_off, seed_off, tiles, bin, bits, seeds[2], n_seeds[2], total_score[2];
 	// classify scratch + outputs
-	DevBuf scratch, rr, hits, counters, prof, work, anc_pool, chain_pool, lists[5], ctl, order, hdr7;
-	uint64_t scratch_stride, scratch_zeroed_stride; uint32_t rec_len;   /* rec_len: longest read seen (+64), sizes the per-seed records */
+	DevBuf scratch, rr, hits, counters, prof, work, anc_pool, chain_pool, lists[4], ctl, order, hdr7;
+	// seeding: packed forward strands, task lists (ping-pong), per-task records, staging chunks, per-lane memory of k_seed
+	DevBuf pk, tasks[2], recs, chunks, lane_mem, vis2, vis1_full, vis_gen, task_first[2], task_cnt[2];
+	uint32_t task_cap, n_chunks;
+	uint32_t grow[5];                   // pool growth (x 2^k) after overflows: tasks, chunks, anchors, chains, hits
+	int32_t max_read_l_in;              // of the last dsb_batch_run (re-runs after a pool overflow, dsb_batch_download)
+	int retries;                        // re-runs of the last batch
+	uint64_t scratch_stride;
 	uint64_t hits_cap;
 	// pinned staging
 	void *h_pin; size_t h_pin_cap;
 	// batch state
 	uint32_t m_bin_read;                // capacity of the reference's bin_read buffer after the batches seen so far (policy P3)
-	uint32_t n_long;                    // reads longer than SHORT_READ_MAX (prefix of the length-sorted order)
 	uint32_t n_reads, n_tiles; uint64_t n_bases, bits_words, seed_slots, bin_bytes; uint32_t max_len;
 	std::vector<uint64_t> h_off;        // host copies of the per-read offset tables
 	std::vector<uint64_t> h_bits_off;

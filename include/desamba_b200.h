@@ -37,6 +37,9 @@ typedef struct {
 	uint32_t max_matches;        /* per-extension 9-mer match capacity (spd_match_set), default 16384 */
 	uint32_t max_read_len;       /* longest read accepted in a batch, default 1<<20 */
 	uint32_t warps_per_sm;       /* resident classify warps per SM (scratch is per warp), default 16 */
+	uint32_t pool_scale_pct;     /* initial size of the per-batch pools (seed tasks, staging, anchors, chains, hits) in % of the
+	                                built-in sizing from the batch's bases and reads, default 100; a pool that still overflows is
+	                                doubled and the batch re-run inside dsb_batch_download (dsb_batch_retries) */
 } dsb_opts;
 
 /* one result line of cly_r.hit (chain_item, cly.h:69-89): exactly the fields the writers read
@@ -113,6 +116,8 @@ uint32_t dsb_ctx_bin_capacity(dsb_ctx *ctx);
 int dsb_batch_run(dsb_ctx *ctx, int32_t max_read_l_in);
 int dsb_batch_download(dsb_ctx *ctx, int32_t *max_read_l_out, dsb_read_result *rr, dsb_hit *hits, uint64_t hits_cap, uint64_t *n_hits_out);
 int dsb_batch_sync(dsb_ctx *ctx);
+/* re-runs of the last batch after a pool overflow (0 in the normal case) */
+int dsb_batch_retries(dsb_ctx *ctx);
 
 /* introspection for tests / profiling (valid after dsb_batch_run + dsb_batch_sync) */
 int dsb_batch_get_seeds(dsb_ctx *ctx, uint32_t read, int strand /*0 fwd,1 rev*/, dsb_seed *out, uint32_t cap, uint32_t *n_out, uint32_t *total_score);

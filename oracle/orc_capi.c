@@ -109,3 +109,37 @@ uint64_t orc_capi_classify_mt(void *h_, const char *seqs, const uint64_t *offs, 
 	for (int t = 0; t < n_threads; t++) { pthread_join(th[t], NULL); tot += job[t].n_hits; }
 	return tot;
 }
+
+/* anchors of ONE seeding pass of one read, for the anchor-level parity test of the seeding engine:
+ * dir = index into search_dir after the swap of getIsland (cly.c:1261-1266), slow = 0 fast_classify (cly.c:1476-1546) /
+ * 1 slow_classify (cly.c:1548-1611).  out[]: {ref_ID, ref_offset, index_in_read, mtch_len | score << 16, direction | useless << 8}.
+ * *strand_out = 0 forward / 1 reverse strand of that search direction; counters[5] = prefix look-ups, occ, locates,
+ * get_ref calls, get_ref bytes of the pass. */
+typedef struct { uint32_t ref_ID, ref_offset, index_in_read, len_score, dir_useless; } capi_anchor;
+int orc_capi_seed_pass(void *h_, const char *seq, uint32_t L, int dir, int slow, capi_anchor *out, uint32_t cap, int *strand_out, int *both_out, uint64_t *counters)
+{
+	capi_handle *h = (capi_handle *)h_;
+	if (L < MIN_READ_LEN) return 0;
+	orc_buff *buff = orc_buff_new();
+	orc_result res; memset(&res, 0, sizeof res);
+	search_dir_t sd[2];
+	get_island(&h->ix, seq, L, buff, &res, sd);
+	if (strand_out) *strand_out = (sd[dir].direction == FORWARD) ? 0 : 1;
+	if (both_out) *both_out = ((sd[0].total_score - sd[1].total_score) <= (sd[0].total_score >> 3)) ? 1 : 0;
+	orc_counters before = orc_cnt;
+	res.n_anc = 0;
+	if (slow) slow_classify(&h->ix, sd + dir, L, &res); else fast_classify(&h->ix, sd + dir, L, &res);
+	if (counters) {
+		counters[0] = orc_cnt.n_prefix - before.n_prefix; counters[1] = orc_cnt.n_occ - before.n_occ; counters[2] = orc_cnt.n_locate - before.n_locate;
+		counters[3] = orc_cnt.n_getref - before.n_getref; counters[4] = orc_cnt.n_getref_bytes - before.n_getref_bytes;
+	}
+	int n = (int)res.n_anc;
+	for (int i = 0; i < n && (uint32_t)i < cap; i++) {
+		const orc_anchor *a = res.anc + i;
+		out[i].ref_ID = a->ref_ID; out[i].ref_offset = a->ref_offset; out[i].index_in_read = a->index_in_read;
+		out[i].len_score = (uint32_t)a->mtch_len | ((uint32_t)(uint16_t)a->score << 16);
+		out[i].dir_useless = (uint32_t)a->direction | ((uint32_t)a->anchor_useless << 8);
+	}
+	orc_result_free(&res); orc_buff_free(buff);
+	return n;
+}
