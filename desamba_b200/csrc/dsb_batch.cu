@@ -290,7 +290,8 @@ __device__ __forceinline__ uint32_t next_read(const ClassifyParams &P, int list,
 __global__ void __launch_bounds__(SEED_WARPS_PER_BLOCK * 32, SEED_WARPS_PER_SM / SEED_WARPS_PER_BLOCK) k_seed(const __grid_constant__ SeedPassParams P)
 {
 	__shared__ uint32_t s_vis1[SEED_WARPS_PER_BLOCK][VIS1_SLOTS][32];
-	seed_warp_loop(P, s_vis1[threadIdx.x >> 5]);
+	__shared__ uint64_t s_lvs[SEED_WARPS_PER_BLOCK][4][32];
+	seed_warp_loop(P, s_vis1[threadIdx.x >> 5], s_lvs[threadIdx.x >> 5]);
 }
 
 __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SCORE_MIN_BLOCKS) k_chain(const __grid_constant__ ClassifyLaunch A, int pass, int list, int cursor)
@@ -682,6 +683,8 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		SP.E.seeds[0] = P.seeds[0]; SP.E.seeds[1] = P.seeds[1]; SP.E.recs = (SeedRec *)c->recs.p; SP.E.chunks = (uint4 *)c->chunks.p; SP.E.n_chunks = c->n_chunks;
 		SP.E.big_rows = big_rows ? 1 : 0;
 		SP.ctl = P.ctl; SP.task_cap = c->task_cap;
+		SP.policy = SC_POLICY; SP.fetch_min = SC_FETCH_MIN;
+		if (const char *e = getenv("DSB_SEED_POLICY")) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 0 && b >= 1) { SP.policy = a; SP.fetch_min = b; } }   // developer knob (profiles/)
 		SP.lane_mem = (MemRst *)c->lane_mem.p; SP.vis2 = (uint64_t *)c->vis2.p; SP.vis1_full = (uint64_t *)c->vis1_full.p; SP.vis_gen = (uint32_t *)c->vis_gen.p;
 		auto seed = [&](int pass) { SP.pass = pass; SP.E.slow = pass != PASS_FAST; SP.E.tasks = (const SeedTaskRef *)c->tasks[pass & 1].p; k_seed<<<c->seed_blocks, SEED_WARPS_PER_BLOCK * 32, 0, st>>>(SP); };
 		const int blocks = c->n_warps / CLASSIFY_WARPS_PER_BLOCK, threads = CLASSIFY_WARPS_PER_BLOCK * 32;

@@ -14,6 +14,7 @@ struct SeedPassParams {
 	uint32_t *ctl;                 // control block of the batch (CTL_*)
 	int pass;                      // PASS_FAST / PASS_SLOW0 / PASS_SLOW1
 	uint32_t task_cap;
+	int policy, fetch_min;         // of the state vote (pick_state)
 	// per resident lane of the kernel (grid * block threads)
 	MemRst *lane_mem; uint64_t *vis2, *vis1_full; uint32_t *vis_gen;
 };
@@ -22,13 +23,14 @@ struct SeedPassParams {
 #define SEED_WARPS_PER_BLOCK 4
 #endif
 
-__device__ __forceinline__ void seed_warp_loop(const SeedPassParams &P, uint32_t (*s_vis1)[32])
+__device__ __forceinline__ void seed_warp_loop(const SeedPassParams &P, uint32_t (*s_vis1)[32], uint64_t (*s_lvs)[32])
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t glane = (blockIdx.x * blockDim.x) + threadIdx.x;
 	const SeedEnv &E = P.E;
 	LaneMem M;
 	M.vis1 = (uint32_t)__cvta_generic_to_shared(&s_vis1[0][lane]);
+	M.lvs = (uint32_t)__cvta_generic_to_shared(&s_lvs[0][lane]);
 	M.vis1_full = P.vis1_full + (E.big_rows ? (uint64_t)glane * VIS1_SLOTS : 0);
 	M.vis2 = P.vis2 + (uint64_t)glane * VIS2_SLOTS;
 	M.mem = P.lane_mem + (uint64_t)glane * SEED_MEM_SLOTS;
@@ -45,7 +47,7 @@ __device__ __forceinline__ void seed_warp_loop(const SeedPassParams &P, uint32_t
 		#pragma unroll
 		for (int s = 0; s < ST_DEAD; s++) cnt[s] = __popc(__ballot_sync(DSB_FULL, L.st == (uint32_t)s));
 		cnt[ST_DEAD] = 0;
-		const int sel = pick_state(cnt);
+		const int sel = pick_state(cnt, P.policy, P.fetch_min);
 		if (sel == ST_DEAD) break;
 		if (sel == ST_FETCH) {
 			const uint32_t fm = __ballot_sync(DSB_FULL, L.st == ST_FETCH);
@@ -61,7 +63,8 @@ __device__ __forceinline__ void seed_warp_loop(const SeedPassParams &P, uint32_t
 				case ST_CTRL: h_ctrl(E, L, M); break;
 				case ST_OCC: h_occ(E, L, M); break;
 				case ST_LOCATE: h_locate(E, L); break;
-				case ST_FLANK: h_flank(E, L); break;
+				case ST_FLANK: h_flank(E, L, M); break;
+				case ST_LV: h_lv(E, L, M); break;
 				default: h_rp(E, L); break;
 			}
 		}
@@ -82,7 +85,7 @@ __device__ __forceinline__ void seed_warp_loop(const SeedPassParams &P, uint32_t
 				bool ok = true;
 				if (need) {
 					const uint32_t c = base + __popc(nm & lt);
-					if (c >= E.n_chunks) { ok = false; atomicOr(P.ctl + CTL_OVERFLOW, OVF_CHUNKS); L.error = 1; map_done(E, L, 0); }
+					if (c >= E.n_chunks) { ok = false; atomicOr(P.ctl + CTL_OVERFLOW, OVF_CHUNKS); L.error = 1; map_done(L, 0); }
 					else {
 						E.chunks[(uint64_t)c * 4 + 3] = make_uint4(SC_NO_CHUNK, 0, 0, 0);
 						if (L.n_out == 0) L.first_chunk = c; else E.chunks[(uint64_t)L.cur_chunk * 4 + 3].x = c;
@@ -92,7 +95,7 @@ __device__ __forceinline__ void seed_warp_loop(const SeedPassParams &P, uint32_t
 				if (ok) {
 					E.chunks[(uint64_t)L.cur_chunk * 4 + (L.n_out % STAGE_PER_CHUNK)] = push_make(E, L);
 					L.n_out++;
-					rp_next(E, L);
+					rp_next(L);
 				}
 			}
 		}

@@ -10,7 +10,7 @@
 //     OCC    one FM-index step (one backward-extension step with 2 occ, or one LF step of a single-row search or of a
 //            locate walk)                  LOCATE  SA sample -> unitig -> first reference position
 //     FLANK  fetch reference + read windows, exact-match extension, Landau-Vishkin on 2-bit packed registers
-//     RP     next reference position of the unitig (anchor push / per-reference re-extension)
+//     LV     one row of the Landau-Vishkin      RP     next reference position of the unitig (anchor push / per-reference re-extension)
 // Each turn the warp votes for one state and only the lanes in that state run its handler, all executing the same
 // instructions, all their loads in flight together.  Nothing in a handler is warp-cooperative: the handlers are plain
 // per-lane functions, compiled for the device (k_seed, dsb_seed.cuh) and -- unchanged -- for the host, where
@@ -162,10 +162,15 @@ struct LaneMem {
 	uint64_t *vis1_full;           // full rows of the tier-1 slots (only touched when big_rows)
 	uint64_t *vis2;
 	MemRst *mem;
+#if defined(__CUDACC__)
+	uint32_t lvs;                  // shared-memory address of the lane's Landau-Vishkin state (4 x u64, word k at + 256 k bytes)
+#else
+	uint64_t *lvs;
+#endif
 };
 
-enum { ST_FETCH = 0, ST_CTRL, ST_OCC, ST_LOCATE, ST_FLANK, ST_RP, ST_DEAD, SC_N_STATES };
-enum { CK_KMER = 0, CK_MAP, CK_FIN };                      // kinds of CTRL step
+enum { ST_FETCH = 0, ST_CTRL, ST_OCC, ST_LOCATE, ST_FLANK, ST_LV, ST_RP, ST_DEAD, SC_N_STATES };
+enum { CK_KMER = 0, CK_MAP, CK_FIN, CK_ROWS, CK_MAPDONE }; // kinds of CTRL step
 enum { OK_EXT = 0, OK_SINGLE, OK_WALK1, OK_WALK2 };        // kinds of OCC step
 enum { FK_PRE = 0, FK_SUF, FK_NEWL, FK_NEWR };             // kinds of FLANK step
 enum { AL_PRE = 0, AL_SUF };                               // what follows a locate
@@ -194,11 +199,9 @@ struct SeedLane {
 	int32_t  fl_q; uint64_t fl_t; uint32_t fl_max, fl_ext;
 	uint32_t c_r_p, r_p_e, rp_ref, ext_l; uint64_t rp_global;
 	uint32_t am_mtch_len; int32_t am_score; uint32_t am_ll, am_le, am_rl, am_re, rsl, rsr;
-	uint32_t push;
-	int32_t  error;
+	uint32_t push, row_res, lv_st;
+	int32_t  ret, error;
 };
-#define b_p sp
-#define t_off ep
 
 // ---------------------------------------------------------------- windows on the read strands and on the reference
 SC_HD uint64_t fwd_win(const uint64_t *rd, int64_t p)              // 32 bases of the forward strand from position p (>= -32)
@@ -477,22 +480,39 @@ SC_HD int32_t lv_frames(uint32_t ref_pre_arr, uint32_t ref_arr, uint64_t eq, int
 // ---------------------------------------------------------------- small helpers of the state machine
 SC_HD void count_getref(SeedLane &L, uint32_t len) { L.c_getref++; L.c_getref_bytes += (len + 3) >> 2; }
 SC_HD void go(SeedLane &L, uint32_t st, uint32_t kind) { L.st = st; L.kind = kind; }
+// map_seed returns `score` (cly.c:938): the seed's schedule goes on in CTRL
+SC_HD void map_done(SeedLane &L, int32_t score) { L.ret = score; go(L, ST_CTRL, CK_MAPDONE); }
 
-// map_seed returned `score` (cly.c:938): the seed's schedule goes on (cly.c:1519-1533 / 1599-1600)
-SC_HD void map_done(const SeedEnv &E, SeedLane &L, int32_t score)
+// one window call site each for the read and for the reference: 32 bases of the lane's strand from position p, rightwards
+// (p, p+1, ...) or leftwards (p, p-1, ...).  Reverse strand: base p = 3 - forward[len-1-p] (cly.c:1258-1259).
+SC_HD uint64_t strand_window(const SeedEnv &E, const SeedLane &L, int64_t p, uint32_t left)
 {
-	L.i_mem++;
-	if (L.error) { go(L, ST_CTRL, CK_FIN); return; }
-	if (E.slow) { go(L, ST_CTRL, (L.i_mem < L.n_found) ? CK_MAP : CK_FIN); return; }
-	L.max_score = SC_MAX(score, L.max_score);
-	if (L.i_mem < L.n_found) { go(L, ST_CTRL, CK_MAP); return; }
-	if (L.max_score > 35) L.j -= 7;
-	if (L.max_score > 256) {
-		if (L.max_score > 512) L.flag512 = 1;              // "skip next and break": the gather drops the next seed (cly.c:1530-1531)
-		go(L, ST_CTRL, CK_FIN);
-		return;
-	}
-	go(L, ST_CTRL, CK_KMER);
+	const uint64_t *rd = E.pk + L.pkw;
+	const uint32_t rev = L.strand ^ left;
+	const int64_t base = L.strand ? (int64_t)L.read_len - 1 - p : p;
+	uint64_t w = fwd_win(rd, rev ? base - 31 : base);
+	if (rev) w = sc_rev2(w);
+	return L.strand ? ~w : w;
+}
+SC_HDN uint64_t ref_win_slow(const DevIndex &ix, uint64_t o)
+{
+	uint64_t v = 0;
+	for (int k = 0; k < 32; k++) v = (v << 2) | ref_base_at(ix, o + k);
+	return v;
+}
+// get_ref (cly.c:435-466) forward from o, or backward from o (positions below 0 read as base 0: the reference wraps around there)
+SC_HD uint64_t ref_window(const DevIndex &ix, uint64_t o, uint32_t left)
+{
+	const uint64_t s = left ? (o >= 31 ? o - 31 : 0) : o;
+	const uint64_t wi = s >> 5;
+	uint64_t w;
+	if ((wi + 2) * 8 <= ix.ref_bin_n + 1024) {
+		const uint64_t *p = (const uint64_t *)ix.ref_bin + wi;
+		w = sc_funnel(sc_bswap64(sc_ld64(p)), sc_bswap64(sc_ld64(p + 1)), 2u * (uint32_t)(s & 31));
+	} else
+		w = ref_win_slow(ix, s);
+	if (left) { w = sc_rev2(w); if (o < 31) w <<= 2 * (31 - (uint32_t)o); }
+	return w;
 }
 
 // a MEM result of the running search (cly.c:1429-1431 / 1441-1443): fast mode keeps the <= 2 of the search in arrival order,
@@ -508,40 +528,6 @@ SC_HD void mem_keep(const SeedEnv &E, SeedLane &L, const LaneMem &M, const MemRs
 	while (p > 0 && M.mem[p - 1].match_len < r.match_len) { M.mem[p] = M.mem[p - 1]; p--; }
 	M.mem[p] = r;
 	if (n < SEED_MEM_SLOTS) L.n_found = n + 1;
-}
-
-// the search is over (bwt_MEM_search returned): cly.c:1510-1517 / 1582-1591
-SC_HD void search_done(const SeedEnv &E, SeedLane &L, uint32_t n_rst)
-{
-	if (E.slow) { L.j -= 2; go(L, ST_CTRL, CK_KMER); return; }
-	if (n_rst == 0) { L.j -= 2; go(L, ST_CTRL, CK_KMER); return; }
-	L.j -= 3;
-	L.i_mem = 0; L.max_score = 0;
-	go(L, ST_CTRL, CK_MAP);
-}
-
-// next row of the interval the backward extension ended with (cly.c:1425-1446): every row not seen before starts a
-// single-row search from the same read position
-SC_HD void rows_advance(const SeedEnv &E, SeedLane &L, const LaneMem &M)
-{
-	while (L.rows_left) {
-		const uint64_t c_sp = L.row_next++;
-		L.rows_left--;
-		if (vis_insert(E, L, M, c_sp) == 0) continue;
-		const int32_t max_single = SC_MAX(0, L.si - L.ext_ml);
-		if (0 >= max_single) {                             // bwt_single_search leaves at once (cly.c:1356)
-			const int32_t total = L.ext_ml + 1;
-			if (total >= (E.slow ? SC_MIN(19, E.ix.l_ek + 1) : 20)) {
-				MemRst r; r.match_len = total; r.sa_sp_l = 0; r.sp = c_sp; r.sa_sp = NO_SA; r.read_offset = L.si - total; r.pad = 0;
-				mem_keep(E, L, M, r);
-			}
-			continue;
-		}
-		L.sp = c_sp; L.ep = NO_SA; L.sa_l = 0; L.ml = 0; L.pos = L.pos_ext;
-		go(L, ST_OCC, OK_SINGLE);
-		return;
-	}
-	search_done(E, L, L.n_found);
 }
 
 // ---------------------------------------------------------------- FETCH: a lane takes task t
@@ -563,26 +549,62 @@ SC_HD void task_begin(const SeedEnv &E, SeedLane &L, const LaneMem &M, uint32_t 
 	go(L, ST_CTRL, CK_KMER);
 }
 
-// ---------------------------------------------------------------- CTRL
+// ---------------------------------------------------------------- CTRL: everything between the memory-bound steps of a seed
+// (the kinds run top to bottom, so one turn can pass through several of them)
 SC_HD void h_ctrl(const SeedEnv &E, SeedLane &L, const LaneMem &M)
 {
 	const DevIndex &ix = E.ix;
-	if (L.kind == CK_KMER) {
-		const int l_ek = ix.l_ek;
-		const bool more = E.slow ? (L.j >= 1) : (L.j >= 21 - l_ek);          // cly.c:1500 / 1570
-		if (more) {
-			// one k-mer of the island: prefix-table interval of its last 13 bases, then backward extension (cly.c:1502-1509, 1399-1401)
-			const int32_t si = (int32_t)L.s_off + L.j + l_ek - 1;
-			const uint64_t pre_v = strand_win(E, L, (int64_t)si - 12) >> 38;
-			L.sp = sc_ld64(ix.prefix + pre_v); L.ep = sc_ld64(ix.prefix + pre_v + 1);
-			L.c_pl++;
-			L.si = si; L.pos = si - L_PRE_IDX; L.ml = L_PRE_IDX;
-			if (!E.slow) L.n_found = 0;
-			go(L, ST_OCC, OK_EXT);
+	const int l_min = E.slow ? SC_MIN(19, ix.l_ek + 1) : 20;
+	if (L.kind == CK_MAPDONE) {
+		// map_seed returned L.ret: cly.c:1519-1533 (fast) / 1599-1600 (slow)
+		L.i_mem++;
+		if (L.error) L.kind = CK_FIN;
+		else if (E.slow) L.kind = (L.i_mem < L.n_found) ? CK_MAP : CK_FIN;
+		else {
+			L.max_score = SC_MAX(L.ret, L.max_score);
+			if (L.i_mem < L.n_found) L.kind = CK_MAP;
+			else {
+				if (L.max_score > 35) L.j -= 7;
+				if (L.max_score > 256) {
+					if (L.max_score > 512) L.flag512 = 1;          // "skip next and break": the gather drops the next seed (cly.c:1530-1531)
+					L.kind = CK_FIN;
+				} else L.kind = CK_KMER;
+			}
+		}
+	}
+	if (L.kind == CK_ROWS) {
+		// the rows of the interval the backward extension ended with (cly.c:1425-1446): every row not seen before starts a
+		// single-row search from the same read position; L.row_res: a single-row search has just ended (1) / was aborted (0)
+		uint32_t pending = L.row_res;
+		L.row_res = 0;
+		for (;;) {
+			if (pending) {
+				const int32_t total = L.ml + L.ext_ml + 1;
+				if (total >= l_min) {
+					MemRst r; r.match_len = total; r.sa_sp_l = L.sa_l; r.sp = L.sp; r.sa_sp = L.ep; r.read_offset = L.si - total; r.pad = 0;
+					mem_keep(E, L, M, r);
+				}
+				pending = 0;
+			}
+			if (!L.rows_left) break;
+			const uint64_t c_sp = L.row_next++;
+			L.rows_left--;
+			if (vis_insert(E, L, M, c_sp) == 0) continue;
+			L.sp = c_sp; L.ep = NO_SA; L.sa_l = 0; L.ml = 0; L.pos = L.pos_ext;
+			if (L.si - L.ext_ml <= 0) { pending = 1; continue; }            // bwt_single_search leaves at once (cly.c:1356)
+			go(L, ST_OCC, OK_SINGLE);
 			return;
 		}
-		if (E.slow && L.n_found > 0) { L.i_mem = 0; L.kind = CK_MAP; }        // cly.c:1592-1600
-		else L.kind = CK_FIN;
+		// bwt_MEM_search returned: cly.c:1510-1517 / 1582-1591
+		if (E.slow || L.n_found == 0) { L.j -= 2; L.kind = CK_KMER; }
+		else { L.j -= 3; L.i_mem = 0; L.max_score = 0; L.kind = CK_MAP; }
+	}
+	if (L.kind == CK_KMER) {
+		const bool more = E.slow ? (L.j >= 1) : (L.j >= 21 - ix.l_ek);     // cly.c:1500 / 1570
+		if (!more) {
+			if (E.slow && L.n_found > 0) { L.i_mem = 0; L.kind = CK_MAP; }  // cly.c:1592-1600
+			else L.kind = CK_FIN;
+		}
 	}
 	if (L.kind == CK_FIN) {
 		SeedRec rec;
@@ -592,28 +614,40 @@ SC_HD void h_ctrl(const SeedEnv &E, SeedLane &L, const LaneMem &M)
 		go(L, ST_FETCH, 0);
 		return;
 	}
-	// CK_MAP: map_seed of MEM result i_mem (cly.c:706-733)
-	const MemRst m = M.mem[L.i_mem];
-	L.b_p = m.sp; L.q_off = m.read_offset; L.l_m = (uint32_t)m.match_len;
+	// CK_KMER: one k-mer of the island -- prefix-table interval of its last 13 bases, then backward extension (cly.c:1502-1509,
+	// 1399-1401).  CK_MAP: map_seed of MEM result i_mem (cly.c:706-733).  Both start with a window of the read.
+	const bool is_map = L.kind == CK_MAP;
+	MemRst m; m.sp = 0; m.sa_sp = NO_SA; m.match_len = 0; m.sa_sp_l = 0; m.read_offset = 0;
+	if (is_map) m = M.mem[L.i_mem];
+	const int32_t si = (int32_t)L.s_off + L.j + ix.l_ek - 1;
+	const uint64_t w = strand_window(E, L, is_map ? (int64_t)m.read_offset : (int64_t)si - 12, is_map ? 1u : 0u);
+	if (!is_map) {
+		const uint64_t pre_v = w >> 38;
+		L.sp = sc_ld64(ix.prefix + pre_v); L.ep = sc_ld64(ix.prefix + pre_v + 1);
+		L.c_pl++;
+		L.si = si; L.pos = si - L_PRE_IDX; L.ml = L_PRE_IDX;
+		if (!E.slow) L.n_found = 0;
+		go(L, ST_OCC, OK_EXT);
+		return;
+	}
+	L.sp = m.sp; L.q_off = m.read_offset; L.l_m = (uint32_t)m.match_len;      // (b_p lives in L.sp)
 	L.uni = -1; L.s_l = 0; L.s = 0; L.max_s = 0;
 	L.A = L.B = L.C = 0;                                       // the frame starts zeroed (trivial-auto-var-init, oracle policy P1)
 	L.l_pre = (uint32_t)SC_MIN(L.q_off + 1, LV_L);
 	L.l_suf = L.d_suf = L.d_pre = 0; L.u_off = 0; L.uni_len = 0;
-	if (L.l_pre) L.A = frame_merge(0, strand_win_left(E, L, L.q_off), L.l_pre);
+	L.A = frame_merge(0, w, L.l_pre);
 	if (m.sa_sp != NO_SA) { L.loc_row = m.sa_sp; L.loc_l = m.sa_sp_l; L.after_loc = AL_PRE; go(L, ST_LOCATE, 0); }
-	else if ((L.b_p & SA_MASK) == 0) { L.loc_row = L.b_p; L.loc_l = 0; L.after_loc = AL_PRE; go(L, ST_LOCATE, 0); }
+	else if ((L.sp & SA_MASK) == 0) { L.loc_row = L.sp; L.loc_l = 0; L.after_loc = AL_PRE; go(L, ST_LOCATE, 0); }
 	else go(L, ST_OCC, OK_WALK1);
 }
 
-// ---------------------------------------------------------------- OCC
+// ---------------------------------------------------------------- OCC: one FM-index step
 SC_HD void h_occ(const SeedEnv &E, SeedLane &L, const LaneMem &M)
 {
 	const DevIndex &ix = E.ix;
 	const uint32_t kind = L.kind;
 	const uint64_t rowA = L.sp;
 	const uint4 *lineA = (const uint4 *)(ix.occ + (rowA >> 7) * 128);
-	const uint4 hA0 = sc_ld128(lineA), hA1 = sc_ld128(lineA + 1);
-	const uint64_t hA4 = sc_ld64((const uint64_t *)lineA + 4);
 	const uint4 pA0 = sc_ld128(lineA + 3), pA1 = sc_ld128(lineA + 4), pA2 = sc_ld128(lineA + 5);
 	uint32_t c = 0;
 	if (kind <= OK_SINGLE) c = strand_base(E, L, L.pos);
@@ -626,19 +660,9 @@ SC_HD void h_occ(const SeedEnv &E, SeedLane &L, const LaneMem &M)
 	const int inA = (int)(rowA & 127);
 	uint32_t cA = c;
 	if (kind != OK_EXT) cA = plane_symbol(pA0, pA1, pA2, inA);
-	uint64_t lfA;                                              // LF(rowA) for symbol cA
-	if (cA == 5) lfA = ix.dollar_pos + ix.rank[5];             // bwt.c:54-55
-	else {
-		uint64_t base;
-		switch (cA) {
-			case 0: base = (uint64_t)hA0.x | ((uint64_t)hA0.y << 32); break;
-			case 1: base = (uint64_t)hA0.z | ((uint64_t)hA0.w << 32); break;
-			case 2: base = (uint64_t)hA1.x | ((uint64_t)hA1.y << 32); break;
-			case 3: base = (uint64_t)hA1.z | ((uint64_t)hA1.w << 32); break;
-			default: base = hA4; break;
-		}
-		lfA = ix.rank[cA] + base + plane_count(pA0, pA1, pA2, inA, cA);
-	}
+	// LF(rowA) for symbol cA; '$' (5) goes to DOLLOR_POS (bwt.c:54-55).  The count word of the symbol is a second access to the line just fetched.
+	uint64_t lfA = ix.dollar_pos + ix.rank[5];
+	if (cA != 5) lfA = ix.rank[cA] + sc_ld64((const uint64_t *)lineA + cA) + plane_count(pA0, pA1, pA2, inA, cA);
 	if (kind == OK_EXT) {
 		// one step of the backward extension of bwt_MEM_search (cly.c:1403-1422)
 		const uint64_t new_sp = lfA;
@@ -646,41 +670,31 @@ SC_HD void h_occ(const SeedEnv &E, SeedLane &L, const LaneMem &M)
 		L.c_occ += 2;
 		L.pos--;
 		const int l_min = E.slow ? SC_MIN(19, ix.l_ek + 1) : 20, max_rst = E.slow ? 8 : 2;
-		bool brk = false;
+		bool brk = false, none = false;
 		if (L.ml >= l_min - 1) {
 			if (new_sp + max_rst >= new_ep) brk = true;
-			else if (L.ml >= L.si) { search_done(E, L, 0); return; }
+			else if (L.ml >= L.si) none = true;                    // longer than what is left of the read: no result
 		}
-		if (!brk && new_sp + 1 >= new_ep) brk = true;
-		if (!brk) { L.ml++; L.sp = new_sp; L.ep = new_ep; return; }
-		if (new_sp >= new_ep) { search_done(E, L, 0); return; }
-		L.row_next = new_sp; L.rows_left = (uint32_t)(new_ep - new_sp);
+		if (!brk && !none && new_sp + 1 >= new_ep) brk = true;
+		if (!brk && !none) { L.ml++; L.sp = new_sp; L.ep = new_ep; return; }
+		L.row_res = 0; L.row_next = new_sp;
+		L.rows_left = (none || new_sp >= new_ep) ? 0u : (uint32_t)(new_ep - new_sp);
 		L.ext_ml = L.ml; L.pos_ext = L.pos;
-		rows_advance(E, L, M);
+		go(L, ST_CTRL, CK_ROWS);
 		return;
 	}
 	L.c_occ++;
 	if (kind == OK_SINGLE) {
 		// one step of bwt_single_search (cly.c:1354-1382); L.ep = last sampled row, L.sa_l = steps since
-		uint64_t sa_sp = L.ep; int32_t sa_l = L.sa_l;
-		if ((rowA & SA_MASK) == 0) { sa_sp = rowA; sa_l = 0; } else sa_l--;
-		L.ep = sa_sp; L.sa_l = sa_l;
-		bool done = false, aborted = false;
-		if (cA != c) done = true;
+		if ((rowA & SA_MASK) == 0) { L.ep = rowA; L.sa_l = 0; } else L.sa_l--;
+		uint32_t res = 2;                                          // 2: goes on, 1: ended (result), 0: aborted (row seen before)
+		if (cA != c) res = 1;
 		else {
 			L.ml++; L.pos--;
-			if (vis_insert(E, L, M, lfA) == 0) aborted = true;
-			else { L.sp = lfA; if (L.ml >= SC_MAX(0, L.si - L.ext_ml)) done = true; }
+			if (vis_insert(E, L, M, lfA) == 0) res = 0;
+			else { L.sp = lfA; if (L.ml >= L.si - L.ext_ml) res = 1; }
 		}
-		if (!done && !aborted) return;
-		if (done) {
-			const int32_t total = L.ml + L.ext_ml + 1;
-			if (total >= (E.slow ? SC_MIN(19, ix.l_ek + 1) : 20)) {
-				MemRst r; r.match_len = total; r.sa_sp_l = L.sa_l; r.sp = L.sp; r.sa_sp = L.ep; r.read_offset = L.si - total; r.pad = 0;
-				mem_keep(E, L, M, r);
-			}
-		}
-		rows_advance(E, L, M);
+		if (res != 2) { L.row_res = res; go(L, ST_CTRL, CK_ROWS); }
 		return;
 	}
 	if (kind == OK_WALK1) {
@@ -691,28 +705,22 @@ SC_HD void h_occ(const SeedEnv &E, SeedLane &L, const LaneMem &M)
 			if (cA == 5) L.B = (L.B & ~0x3Fu) | FR_POISON | (uint32_t)L.s_l;
 			else L.B |= cA << (30 - 2 * L.s_l);
 			L.s_l++;
-			L.b_p = lfA;
-			if ((uint32_t)L.s_l >= L.l_pre || (L.b_p & SA_MASK) == 0) end = true;
+			L.sp = lfA;
+			if ((uint32_t)L.s_l >= L.l_pre || (L.sp & SA_MASK) == 0) end = true;
 		}
 		if (!end) return;
-		if ((L.b_p & SA_MASK) == 0) { L.loc_row = L.b_p; L.loc_l = L.s_l; L.after_loc = AL_PRE; go(L, ST_LOCATE, 0); }
+		if ((L.sp & SA_MASK) == 0) { L.loc_row = L.sp; L.loc_l = L.s_l; L.after_loc = AL_PRE; go(L, ST_LOCATE, 0); }
 		else { L.l_pre = (uint32_t)L.s_l; go(L, ST_FLANK, FK_PRE); }
 		return;
 	}
 	// OK_WALK2: on to the next sampled row once the left flank has passed (cly.c:782-788)
-	L.b_p = lfA; L.s_l++;
-	if (L.s_l > (1 << 20)) { L.error = 5; map_done(E, L, 0); return; }   // cannot happen on a well-formed index; never hang the GPU
-	if ((L.b_p & SA_MASK) == 0) { L.loc_row = L.b_p; L.loc_l = L.s_l; L.after_loc = AL_SUF; go(L, ST_LOCATE, 0); }
+	L.sp = lfA; L.s_l++;
+	if (L.s_l > (1 << 20)) { L.error = 5; map_done(L, 0); return; }   // cannot happen on a well-formed index; never hang the GPU
+	if ((L.sp & SA_MASK) == 0) { L.loc_row = L.sp; L.loc_l = L.s_l; L.after_loc = AL_SUF; go(L, ST_LOCATE, 0); }
 }
 
 // ---------------------------------------------------------------- right flank of map_seed (cly.c:796-835)
-SC_HD void rp_begin(const SeedEnv &E, SeedLane &L);
-SC_HD void suf_done(const SeedEnv &E, SeedLane &L)
-{
-	if ((L.s <= 20 && L.l_suf == LV_L) || !(L.s > 0)) { map_done(E, L, 0); return; }     // cly.c:831-835, 842
-	rp_begin(E, L);
-}
-SC_HD void suf_begin(const SeedEnv &E, SeedLane &L)
+SC_HD void suf_begin(SeedLane &L)
 {
 	const int32_t q_off_r = L.q_off + (int32_t)L.l_m + 1;
 	const uint32_t l_max_suf = SC_MIN(L.uni_len - L.u_off - L.l_m, L.read_len - (uint32_t)q_off_r);
@@ -722,8 +730,8 @@ SC_HD void suf_begin(const SeedEnv &E, SeedLane &L)
 		go(L, ST_FLANK, FK_SUF);
 		return;
 	}
-	L.l_suf = L.d_suf = 0;
-	suf_done(E, L);
+	L.l_suf = L.d_suf = 0;                                     // cly.c:828-829; the test of cly.c:831 needs l_suf == 12
+	if (!(L.s > 0)) map_done(L, 0); else go(L, ST_RP, 1);
 }
 
 // ---------------------------------------------------------------- LOCATE (get_uni, cly.c:471-496)
@@ -742,138 +750,61 @@ SC_HD void h_locate(const SeedEnv &E, SeedLane &L)
 			ul = sc_ld2(ix.uni + u);
 		}
 	const uint64_t rp = sc_ld64(ix.ref_pos + ul.x);
-	L.t_off = (rp & 0xFFFFFFFFFFull) + uni_offset;               // (b_p is not needed any more: t_off shares its register pair)
+	L.ep = (rp & 0xFFFFFFFFFFull) + uni_offset;                  // t_off lives in L.ep
 	L.u_off = uni_offset; L.uni = (int32_t)u; L.uni_len = ul.y;
-	if (ul.y < MIN_UNI_L) { map_done(E, L, 0); return; }       // cly.c:767 / 791
+	if (ul.y < MIN_UNI_L) { map_done(L, 0); return; }          // cly.c:767 / 791
 	if (L.after_loc == AL_PRE) { L.l_pre = SC_MIN(L.l_pre, L.u_off); go(L, ST_FLANK, FK_PRE); }
-	else suf_begin(E, L);
+	else suf_begin(L);
 }
 
-// ---------------------------------------------------------------- FLANK
-SC_HD void rp_next(const SeedEnv &E, SeedLane &L)
+// ---------------------------------------------------------------- RP: the reference positions of the unitig (cly.c:840-937)
+SC_HD void rp_next(SeedLane &L)
 {
 	L.c_r_p++;
-	if (L.c_r_p >= L.r_p_e) map_done(E, L, L.max_s); else go(L, ST_RP, 0);
-}
-SC_HD void newr_begin(SeedLane &L)
-{   // get_new_ed(..., is_FWD = false), cly.c:656-662
-	L.B = 0; L.C = 0;
-	const int32_t q2 = L.q_off + (int32_t)L.l_m + 1;
-	const uint32_t max_len = L.read_len - (uint32_t)q2;
-	L.fl_q = q2; L.fl_t = L.rp_global + L.u_off + L.l_m; L.fl_max = max_len; L.fl_ext = 0;
-	count_getref(L, SC_MIN(12u, max_len));
-	L.kind = FK_NEWR;
-}
-SC_HD void newl_begin(SeedLane &L)
-{   // get_new_ed(..., is_FWD = true), cly.c:645-662
-	L.B = 0; L.C = 0;
-	const int32_t qo = SC_MAX(L.q_off, 0);
-	L.fl_q = qo; L.fl_t = L.rp_global + L.u_off - 1; L.fl_max = (uint32_t)qo; L.fl_ext = 0;
-	count_getref(L, SC_MIN(12u, (uint32_t)qo));
-	L.kind = FK_NEWL;
+	if (L.c_r_p >= L.r_p_e) map_done(L, L.max_s); else go(L, ST_RP, 0);
 }
 SC_HD void rp_score(const SeedEnv &E, SeedLane &L)
 {   // cly.c:914-920
 	L.am_score = (int16_t)(Q_MEM_at(E.ix, L.am_mtch_len) + Q_LV_at(E.ix, L.am_le, L.am_ll) + Q_LV_at(E.ix, L.am_re, L.am_rl));
-	if (L.am_score < 20) rp_next(E, L); else L.push = 1;
+	if (L.am_score < 20) rp_next(L); else L.push = 1;
 }
-
-SC_HD void h_flank(const SeedEnv &E, SeedLane &L)
-{
-	const DevIndex &ix = E.ix;
-	const uint32_t fk = L.kind;
-	if (fk == FK_PRE) {
-		// left flank of map_seed (cly.c:764-779): the reference bases left of the match when the unitig is known, else what the walk collected
-		if (L.uni >= 0) {
-			int64_t o = (int64_t)L.t_off - 1; if (o < 0) o = 0;
-			L.B = frame_merge(L.B, ref_win_left(ix, (uint64_t)o), L.l_pre);
-			count_getref(L, L.l_pre);
-		}
-		L.d_pre = (uint32_t)lv_frames(L.A, L.B, frame_ext(0, L.A), (int32_t)L.l_pre, true, L.B);
-		L.s = Q_MEM_at(ix, L.l_m) + Q_LV_at(ix, L.d_pre, L.l_pre);
-		if (L.s < 12 && L.l_pre == LV_L && L.uni < 0) { map_done(E, L, 0); return; }
-		if (L.uni < 0) {
-			if ((L.b_p & SA_MASK) == 0) { L.loc_row = L.b_p; L.loc_l = L.s_l; L.after_loc = AL_SUF; go(L, ST_LOCATE, 0); }
-			else go(L, ST_OCC, OK_WALK2);
-			return;
-		}
-		suf_begin(E, L);
-		return;
-	}
-	// exact-match extension in strides of <= 12 (cly.c:806-823 / 663-689), then Landau-Vishkin on what follows
-	const bool right = (fk != FK_NEWL);
-	uint64_t qfull, qw, rw; int cap;
+SC_HD void new_ed_begin(SeedLane &L, uint32_t right)
+{   // get_new_ed (cly.c:629-662): q_buff / t_buff take the t_pre / t_suf slots of the frame and start zeroed (oracle policy P2)
+	L.B = 0; L.C = 0; L.fl_ext = 0;
 	if (right) {
-		qfull = strand_win(E, L, (int64_t)L.fl_q - 5);               // 5 bases in front of the cursor: what negative indices of the query read
-		qw = qfull << 10; cap = 27;
-		const uint64_t t = (fk == FK_SUF) ? (L.t_off + L.l_m) : L.fl_t;
-		rw = ref_win(ix, t);
+		const int32_t q2 = L.q_off + (int32_t)L.l_m + 1;
+		L.fl_q = q2; L.fl_t = L.rp_global + L.u_off + L.l_m; L.fl_max = L.read_len - (uint32_t)q2;
 	} else {
-		qfull = 0;
-		qw = strand_win_left(E, L, L.fl_q); cap = 32;
-		int64_t o = (int64_t)L.fl_t; if (o < 0) o = 0;
-		rw = ref_win_left(ix, (uint64_t)o);
+		const int32_t qo = SC_MAX(L.q_off, 0);
+		L.fl_q = qo; L.fl_t = L.rp_global + L.u_off - 1; L.fl_max = (uint32_t)qo;
 	}
-	int d = 0; uint32_t len;
-	for (;;) {
-		len = SC_MIN(L.fl_max, 12u);
-		if (fk == FK_NEWL) L.B = frame_merge(L.B, qw << (2 * d), len);
-		if (d + 12 > cap) {                                        // the windows are used up: fetch again at the new cursors
-			if (right) L.fl_q += d; else L.fl_q -= d;
-			if (fk != FK_SUF) { if (right) L.fl_t += d; else L.fl_t -= d; }
-			return;
-		}
-		const uint32_t mtc = SC_MIN((uint32_t)sc_common(rw << (2 * d), qw << (2 * d)), len);
-		if (mtc == 0) break;
-		if (fk == FK_SUF) L.l_m += mtc; else L.fl_ext += mtc;
-		L.fl_max -= mtc;
-		d += (int)mtc;
-		count_getref(L, SC_MIN(L.fl_max, 12u));
-	}
-	L.C = frame_merge(L.C, rw << (2 * d), len);
-	int32_t ed;
-	if (right) ed = lv_frames(L.B, L.C, qfull << (2 * d), (int32_t)len, false, L.B);
-	else ed = lv_frames(L.B, L.C, frame_ext(frame_tail(L.A), L.B), (int32_t)len, false, L.B);
-	if (fk == FK_SUF) {
-		L.l_suf = len; L.d_suf = (uint32_t)ed;
-		L.s = Q_MEM_at(ix, L.l_m) + Q_LV_at(ix, L.d_pre, L.l_pre) + Q_LV_at(ix, L.d_suf, L.l_suf);
-		suf_done(E, L);
-		return;
-	}
-	if (fk == FK_NEWL) {
-		L.am_ll = len & 0xff; L.am_le = (uint32_t)ed & 0xff; L.ext_l = L.fl_ext;
-		L.am_mtch_len = (L.l_m + L.ext_l) & 0xffff;
-		if (L.rsr) { newr_begin(L); return; }
-		rp_score(E, L);
-		return;
-	}
-	L.am_rl = len & 0xff; L.am_re = (uint32_t)ed & 0xff;
-	L.am_mtch_len = (L.am_mtch_len + L.fl_ext) & 0xffff;
-	rp_score(E, L);
-}
-
-// ---------------------------------------------------------------- RP: the reference positions of the unitig (cly.c:840-937)
-SC_HD void rp_begin(const SeedEnv &E, SeedLane &L)
-{
-	const DevIndex &ix = E.ix;
-	L.am_mtch_len = L.l_m & 0xffff; L.am_score = (int16_t)L.s;
-	L.am_ll = L.l_pre & 0xff; L.am_le = L.d_pre & 0xff; L.am_rl = L.l_suf & 0xff; L.am_re = L.d_suf & 0xff;
-	const uint32_t r_p_s = sc_ld2(ix.uni + L.uni).x, r_p_e = sc_ld2(ix.uni + L.uni + 1).x;
-	L.rsl = (L.l_pre < LV_L || L.d_pre == 0) ? 1 : 0;          // an edit distance of 0: the extension is not over
-	L.rsr = (L.l_suf < LV_L || L.d_suf == 0) ? 1 : 0;
-	const int64_t n = (int64_t)r_p_e - (int64_t)r_p_s;
-	if (n > 50 && !(n < 1000)) { map_done(E, L, 50); return; }
-	L.c_r_p = r_p_s; L.r_p_e = r_p_e;
-	if (r_p_s >= r_p_e) { map_done(E, L, L.max_s); return; }
-	go(L, ST_RP, 0);
+	count_getref(L, SC_MIN(12u, L.fl_max));
+	go(L, ST_FLANK, right ? FK_NEWR : FK_NEWL);
 }
 SC_HD void h_rp(const SeedEnv &E, SeedLane &L)
 {
-	const uint64_t rp = sc_ld64(E.ix.ref_pos + L.c_r_p);
+	const DevIndex &ix = E.ix;
+	if (L.kind == 1) {
+		// first turn of a map_seed that passed both flanks (cly.c:840-888)
+		L.am_mtch_len = L.l_m & 0xffff; L.am_score = (int16_t)L.s;
+		L.am_ll = L.l_pre & 0xff; L.am_le = L.d_pre & 0xff; L.am_rl = L.l_suf & 0xff; L.am_re = L.d_suf & 0xff;
+		const uint32_t r_p_s = sc_ld2(ix.uni + L.uni).x, r_p_e = sc_ld2(ix.uni + L.uni + 1).x;
+		L.rsl = (L.l_pre < LV_L || L.d_pre == 0) ? 1 : 0;      // an edit distance of 0: the extension is not over
+		L.rsr = (L.l_suf < LV_L || L.d_suf == 0) ? 1 : 0;
+		const int64_t n = (int64_t)r_p_e - (int64_t)r_p_s;
+		if (n > 50 && !(n < 1000)) { map_done(L, 50); return; }
+		L.c_r_p = r_p_s; L.r_p_e = r_p_e;
+		if (r_p_s >= r_p_e) { map_done(L, L.max_s); return; }
+		L.kind = 0;
+	}
+	const uint64_t rp = sc_ld64(ix.ref_pos + L.c_r_p);
 	L.rp_global = rp & 0xFFFFFFFFFFull; L.rp_ref = (uint32_t)((rp >> 40) & 0x7FFFFF);
 	L.ext_l = 0;
-	if (L.rsl) { newl_begin(L); L.st = ST_FLANK; return; }
-	if (L.rsr) { L.am_mtch_len = L.l_m & 0xffff; newr_begin(L); L.st = ST_FLANK; return; }
+	if (L.rsl | L.rsr) {
+		if (!L.rsl) L.am_mtch_len = L.l_m & 0xffff;
+		new_ed_begin(L, L.rsl ? 0u : 1u);
+		return;
+	}
 	L.push = 1;
 }
 // the pending anchor of a lane, after the collective part of the push gave it a staging slot
@@ -895,45 +826,206 @@ SC_HD uint4 push_make(const SeedEnv &E, SeedLane &L)
 	return a;
 }
 
+// ---------------------------------------------------------------- what follows the Landau-Vishkin of a flank
+SC_HD void flank_done(const SeedEnv &E, SeedLane &L, uint32_t len, int32_t ed)
+{
+	const DevIndex &ix = E.ix;
+	const uint32_t fk = L.kind;
+	if (fk == FK_PRE) {
+		// cly.c:773-795
+		L.d_pre = (uint32_t)ed;
+		L.s = Q_MEM_at(ix, L.l_m) + Q_LV_at(ix, L.d_pre, L.l_pre);
+		if (L.s < 12 && L.l_pre == LV_L && L.uni < 0) { map_done(L, 0); return; }
+		if (L.uni < 0) {
+			if ((L.sp & SA_MASK) == 0) { L.loc_row = L.sp; L.loc_l = L.s_l; L.after_loc = AL_SUF; go(L, ST_LOCATE, 0); }
+			else go(L, ST_OCC, OK_WALK2);
+			return;
+		}
+		suf_begin(L);
+		return;
+	}
+	if (fk == FK_SUF) {
+		// cly.c:826-842
+		L.l_suf = len; L.d_suf = (uint32_t)ed;
+		L.s = Q_MEM_at(ix, L.l_m) + Q_LV_at(ix, L.d_pre, L.l_pre) + Q_LV_at(ix, L.d_suf, L.l_suf);
+		if ((L.s <= 20 && L.l_suf == LV_L) || !(L.s > 0)) { map_done(L, 0); return; }
+		go(L, ST_RP, 1);
+		return;
+	}
+	if (fk == FK_NEWL) {
+		L.am_ll = len & 0xff; L.am_le = (uint32_t)ed & 0xff; L.ext_l = L.fl_ext;
+		L.am_mtch_len = (L.l_m + L.ext_l) & 0xffff;
+		if (L.rsr) { new_ed_begin(L, 1); return; }
+		rp_score(E, L);
+		return;
+	}
+	L.am_rl = len & 0xff; L.am_re = (uint32_t)ed & 0xff;
+	L.am_mtch_len = (L.am_mtch_len + L.fl_ext) & 0xffff;
+	rp_score(E, L);
+}
+
+// ---------------------------------------------------------------- FLANK: windows, exact-match extension, start of the Landau-Vishkin
+// Landau-Vishkin state of a lane between its row turns: the two extended strings and the mn / ed rows, in shared memory
+SC_HD uint64_t lvs_ld(const LaneMem &M, uint32_t k)
+{
+#if SC_DEVICE
+	uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(M.lvs + 256u * k) : "memory"); return v;
+#elif defined(__CUDACC__)
+	return 0 * M.lvs * k;
+#else
+	return M.lvs[k];
+#endif
+}
+SC_HD void lvs_st(const LaneMem &M, uint32_t k, uint64_t v)
+{
+#if SC_DEVICE
+	asm volatile("st.shared.u64 [%0], %1;" :: "r"(M.lvs + 256u * k), "l"(v) : "memory");
+#elif defined(__CUDACC__)
+	(void)M; (void)k; (void)v;
+#else
+	M.lvs[k] = v;
+#endif
+}
+
+SC_HD void h_flank(const SeedEnv &E, SeedLane &L, const LaneMem &M)
+{
+	const DevIndex &ix = E.ix;
+	const uint32_t fk = L.kind;
+	const bool pre = fk == FK_PRE;
+	const uint32_t left = (fk == FK_PRE || fk == FK_NEWL) ? 1u : 0u;
+	// the reference window (get_ref, cly.c:435-466: a negative offset is clamped to 0) and the read window
+	uint64_t t;
+	if (pre) { const int64_t o = (int64_t)L.ep - 1; t = o < 0 ? 0 : (uint64_t)o; }
+	else if (fk == FK_SUF) t = L.ep + L.l_m;
+	else { const int64_t o = (int64_t)L.fl_t; t = o < 0 ? 0 : (uint64_t)o; }
+	uint64_t rw = 0, qraw = 0;
+	if (!pre || L.uni >= 0) rw = ref_window(ix, t, left);
+	if (!pre) qraw = strand_window(E, L, left ? (int64_t)L.fl_q : (int64_t)L.fl_q - 5, left);   // rightwards: 5 bases in front of the cursor, what negative indices of the query read
+	uint64_t er, eq; uint32_t len;
+	if (pre) {
+		// left flank of map_seed (cly.c:764-772): the reference bases left of the match when the unitig is known, else what the walk collected
+		if (L.uni >= 0) { L.B = frame_merge(L.B, rw, L.l_pre); count_getref(L, L.l_pre); }
+		len = L.l_pre;
+		er = frame_ext(frame_tail(L.A), L.B); eq = frame_ext(0, L.A);
+	} else {
+		// exact-match extension in strides of <= 12 (cly.c:806-823 / 663-689), then Landau-Vishkin on what follows
+		const uint64_t qw = left ? qraw : (qraw << 10);
+		const int cap = left ? 32 : 27;
+		int d = 0;
+		for (;;) {
+			len = SC_MIN(L.fl_max, 12u);
+			if (fk == FK_NEWL) L.B = frame_merge(L.B, qw << (2 * d), len);
+			if (d + 12 > cap) {                                        // the windows are used up: fetch again at the new cursors
+				if (left) { L.fl_q -= d; L.fl_t -= d; } else { L.fl_q += d; L.fl_t += d; }
+				return;
+			}
+			const uint32_t mtc = SC_MIN((uint32_t)sc_common(rw << (2 * d), qw << (2 * d)), len);
+			if (mtc == 0) break;
+			if (fk == FK_SUF) L.l_m += mtc; else L.fl_ext += mtc;
+			L.fl_max -= mtc;
+			d += (int)mtc;
+			count_getref(L, SC_MIN(L.fl_max, 12u));
+		}
+		L.C = frame_merge(L.C, rw << (2 * d), len);
+		er = frame_ext(frame_tail(L.B), L.C);
+		eq = left ? frame_ext(frame_tail(L.A), L.B) : (qraw << (2 * d));
+	}
+	if (L.B & FR_POISON) {                                         // t_pre holds '$' (a walk off the start of unitig 0): the byte statement
+		uint8_t r[18], q[18];
+		for (int k = 0; k < 18; k++) { r[k] = (uint8_t)((er >> (62 - 2 * k)) & 3); q[k] = (uint8_t)((eq >> (62 - 2 * k)) & 3); }
+		const uint32_t pe = L.B & 15;
+		if (pre) r[5 + pe] = 5; else if (pe >= 8 && pe <= 12) r[pe - 8] = 5;
+		flank_done(E, L, len, lv_bytes(r, q, (int32_t)len));
+		return;
+	}
+	lvs_st(M, 0, er); lvs_st(M, 1, eq); lvs_st(M, 2, 1ull << 44); lvs_st(M, 3, 0x054321012345ull);
+	L.lv_st = (len << 8) | (len << 16);                            // row 0, best_score = len
+	L.st = ST_LV;
+}
+
+// ---------------------------------------------------------------- LV: one row of the Landau-Vishkin (lv_extd, cly.c:544-607)
+// Lanes in different rows run together: row i visits the diagonals j = -i .. 4, so the turn walks j = -4 .. 4 and a lane joins
+// at its -i.  With j a compile-time constant the 4-bit fields of the mn / ed rows sit at fixed positions.
+SC_HD void h_lv(const SeedEnv &E, SeedLane &L, const LaneMem &M)
+{
+	const uint64_t er = lvs_ld(M, 0), eq = lvs_ld(M, 1);
+	uint64_t MN = lvs_ld(M, 2), ED = lvs_ld(M, 3);
+	int i = (int)(L.lv_st & 15), best_score = (int)((L.lv_st >> 8) & 0xff);
+	const int len = (int)((L.lv_st >> 16) & 0xff);
+	int prev_mn = -1, cur_mn = i - 1, next_mn = lv_get(MN, -i + 1) - 1;
+	int prev_ed = i + 1, cur_ed = i, next_ed = lv_get(ED, -i + 1);
+	bool fin = false;
+	#pragma unroll
+	for (int j = -4; j <= 4; j++) {
+		if (!fin && j >= -i) {
+			int m, e;
+			if (cur_mn + j < len - 1) {
+				int best = cur_mn + 1 - cur_ed;
+				m = cur_mn + 1; e = cur_ed + 1;
+				if (best < next_mn + 1 - next_ed) { m = next_mn + 1; e = next_ed + 1; best = next_mn - next_ed; }
+				if (best < prev_mn - prev_ed) { m = prev_mn + 1; e = prev_ed + 1; }
+			} else {
+				int best = cur_mn - cur_ed;
+				m = cur_mn; e = cur_ed + 1;
+				if (best < prev_mn - prev_ed) { m = prev_mn; e = prev_ed + 1; best = prev_mn - prev_ed; }
+				if (best < next_mn + 1 - next_ed) { m = next_mn + 1; e = next_ed + 1; }
+			}
+			ED = lv_set(ED, j, e);
+			int mn_j = SC_MIN(m, len);
+			mn_j = SC_MIN(mn_j, len - j);
+			{	// in-line match along diagonal j: reference index mn_j + j against query index mn_j, up to the sentinels
+				const int a = mn_j + j;
+				int run = sc_common(er << (2 * (a + 5)), eq << (2 * (mn_j + 5)));
+				run = SC_MIN(run, SC_MIN(len - a, len - mn_j));
+				mn_j += run;
+			}
+			MN = lv_set(MN, j, mn_j + 1);
+			if (mn_j == len || mn_j + j == len) {
+				best_score = SC_MIN(e - 1, best_score);
+				if (j <= i + 1) fin = true;
+			}
+			prev_mn = cur_mn; cur_mn = next_mn; next_mn = lv_get(MN, j + 2) - 1;
+			prev_ed = cur_ed; cur_ed = next_ed; next_ed = lv_get(ED, j + 2);
+		}
+	}
+	if (!fin && ++i > 4) fin = true;
+	if (fin) { L.st = ST_FLANK; flank_done(E, L, (uint32_t)len, best_score); return; }
+	lvs_st(M, 2, MN); lvs_st(M, 3, ED);
+	L.lv_st = (uint32_t)i | ((uint32_t)best_score << 8) | ((uint32_t)len << 16);
+}
+
 // ---------------------------------------------------------------- which state runs this turn
 // cnt[s] = lanes in state s.  The most populated state runs; a state with few lanes waits as long as a fuller one exists,
 // so parked lanes pile up until their state is worth a turn.  Free lanes (FETCH) are refilled as soon as there are
 // SC_FETCH_MIN of them, or when nothing else is left to do.
 #ifndef SC_FETCH_MIN
-#define SC_FETCH_MIN 6
+#define SC_FETCH_MIN 3
 #endif
-#ifdef SC_POLICY_VAR
-static int sc_policy = 2, sc_fetch_min = SC_FETCH_MIN;
+#ifndef SC_POLICY
+#define SC_POLICY 3
 #endif
-SC_HD int pick_state(const int *cnt)
+SC_HD int pick_state(const int *cnt, int policy, int fetch_min)
 {
-#ifdef SC_POLICY_VAR
-	const int policy = sc_policy, fetch_min = sc_fetch_min;
-#else
-	const int policy = 2, fetch_min = SC_FETCH_MIN;
-#endif
-	if (policy == 0 && cnt[ST_FETCH] > 0) return ST_FETCH;
-	if (policy == 2 && cnt[ST_FETCH] >= fetch_min) return ST_FETCH;
 	if (policy >= 3) {
-		// light states (a few dozen instructions) run as soon as `fetch_min` lanes wait in them: their lanes come back to the
-		// heavy states (OCC, FLANK) quickly, which then run fuller; FLANK, the most expensive, waits for policy - 2 lanes or for OCC to drain
-		const int flank_min = policy - 2;
+		// light states (a few dozen instructions: FETCH, CTRL, LOCATE, RP) run as soon as fetch_min lanes wait in one of them -- their
+		// lanes are back in the heavy states (OCC, FLANK, LV) the sooner, which then run fuller; otherwise the fullest heavy state
 		int bl = ST_DEAD, nl = 0;
-		if (cnt[ST_FETCH] > nl) { nl = cnt[ST_FETCH]; bl = ST_FETCH; }
 		if (cnt[ST_CTRL] > nl) { nl = cnt[ST_CTRL]; bl = ST_CTRL; }
+		if (cnt[ST_FETCH] > nl) { nl = cnt[ST_FETCH]; bl = ST_FETCH; }
 		if (cnt[ST_LOCATE] > nl) { nl = cnt[ST_LOCATE]; bl = ST_LOCATE; }
 		if (cnt[ST_RP] > nl) { nl = cnt[ST_RP]; bl = ST_RP; }
 		if (nl >= fetch_min) return bl;
-		const int o = cnt[ST_OCC], f = cnt[ST_FLANK];
-		if (f >= flank_min && f >= o) return ST_FLANK;
-		if (o > 0) return ST_OCC;
-		if (f > 0) return ST_FLANK;
+		int bh = ST_DEAD, nh = 0;
+		if (cnt[ST_OCC] > nh) { nh = cnt[ST_OCC]; bh = ST_OCC; }
+		if (cnt[ST_LV] > nh) { nh = cnt[ST_LV]; bh = ST_LV; }
+		if (cnt[ST_FLANK] > nh) { nh = cnt[ST_FLANK]; bh = ST_FLANK; }
+		if (nh >= nl && nh > 0) return bh;
 		return bl;
 	}
+	if (cnt[ST_FETCH] >= fetch_min) return ST_FETCH;
 	int best = ST_DEAD, n = 0;
-	for (int s = (policy == 1) ? ST_FETCH : ST_CTRL; s < ST_DEAD; s++) if (cnt[s] > n) { n = cnt[s]; best = s; }
+	#pragma unroll
+	for (int s = ST_CTRL; s < ST_DEAD; s++) if (cnt[s] > n) { n = cnt[s]; best = s; }
 	if (best == ST_DEAD && cnt[ST_FETCH] > 0) return ST_FETCH;
 	return best;
 }
-#undef b_p
-#undef t_off

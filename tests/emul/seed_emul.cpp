@@ -3,7 +3,6 @@
 // with the same state vote as the kernel.  tests/test_seed_engine.py compares the anchors of every seed with the oracle
 // (fast_classify / slow_classify), checks the packed Landau-Vishkin against its plain byte statement, and reads the
 // lanes-per-turn statistics the scheduling policy is tuned with.  Nothing of the product links or loads this.
-#define SC_POLICY_VAR 1
 #include "../../desamba_b200/csrc/dsb_seedcore.h"
 #include <vector_functions.h>
 #include <cstdio>
@@ -14,6 +13,8 @@
 #include <vector>
 
 namespace {
+
+int sc_policy = SC_POLICY, sc_fetch_min = SC_FETCH_MIN;
 
 struct HostIndex {
 	DevIndex dev;
@@ -68,6 +69,7 @@ struct Stats { uint64_t turns[SC_N_STATES], lanes[SC_N_STATES]; };
 struct Warp {
 	SeedLane L[32];
 	uint32_t vis1[32][VIS1_SLOTS];
+	uint64_t lvs[32][4];
 	std::vector<uint64_t> vis1_full, vis2;
 	std::vector<MemRst> mem;
 	bool dead;
@@ -145,6 +147,7 @@ void *emul_open(const char *dir)
 void emul_close(void *h) { delete (HostIndex *)h; }
 int emul_l_ek(void *h) { return ((HostIndex *)h)->dev.l_ek; }
 void emul_set_policy(int policy, int fetch_min) { sc_policy = policy; sc_fetch_min = fetch_min; }
+int emul_n_states(void) { return SC_N_STATES; }
 
 // One seeding pass over a task list.  seqs/offs: ASCII reads; seeds0/seeds1 + seed_off: the island seeds of the two strands
 // (from the oracle); tasks: the seeds to run.  Outputs: recs[n_tasks]; the staged anchors of task t at anc[anc_off[t] ..
@@ -199,19 +202,20 @@ int64_t emul_seed_pass(void *h_, const char *seqs, const uint64_t *offs, uint32_
 			if (w.dead) continue;
 			int cnt[SC_N_STATES] = {0};
 			for (int l = 0; l < 32; l++) cnt[w.L[l].st]++;
-			const int sel = pick_state(cnt);
+			const int sel = pick_state(cnt, sc_policy, sc_fetch_min);
 			if (sel == ST_DEAD) { w.dead = true; n_dead++; continue; }
 			S.turns[sel]++; S.lanes[sel] += cnt[sel];
 			for (int l = 0; l < 32; l++) {
 				SeedLane &L = w.L[l];
 				if ((int)L.st != sel) continue;
-				LaneMem M; M.vis1 = w.vis1[l]; M.vis1_full = w.vis1_full.data() + l * VIS1_SLOTS; M.vis2 = w.vis2.data() + l * VIS2_SLOTS; M.mem = w.mem.data() + l * SEED_MEM_SLOTS;
+				LaneMem M; M.vis1 = w.vis1[l]; M.lvs = w.lvs[l]; M.vis1_full = w.vis1_full.data() + l * VIS1_SLOTS; M.vis2 = w.vis2.data() + l * VIS2_SLOTS; M.mem = w.mem.data() + l * SEED_MEM_SLOTS;
 				switch (sel) {
 					case ST_FETCH: { const uint32_t t = task_cursor++; if (t < n_tasks) task_begin(E, L, M, t); else L.st = ST_DEAD; break; }
 					case ST_CTRL: h_ctrl(E, L, M); break;
 					case ST_OCC: h_occ(E, L, M); break;
 					case ST_LOCATE: h_locate(E, L); break;
-					case ST_FLANK: h_flank(E, L); break;
+					case ST_FLANK: h_flank(E, L, M); break;
+					case ST_LV: h_lv(E, L, M); break;
 					case ST_RP: h_rp(E, L); break;
 				}
 			}
@@ -223,14 +227,14 @@ int64_t emul_seed_pass(void *h_, const char *seqs, const uint64_t *offs, uint32_
 				const uint32_t slot = L.n_out % STAGE_PER_CHUNK;
 				if (slot == 0) {
 					const uint32_t c = chunk_cursor++;
-					if (c >= E.n_chunks) { overflow = true; L.error = 1; map_done(E, L, 0); continue; }
+					if (c >= E.n_chunks) { overflow = true; L.error = 1; map_done(L, 0); continue; }
 					E.chunks[c * 4 + 3] = make_uint4(SC_NO_CHUNK, 0, 0, 0);
 					if (L.n_out == 0) L.first_chunk = c; else E.chunks[L.cur_chunk * 4 + 3].x = c;
 					L.cur_chunk = c;
 				}
 				E.chunks[L.cur_chunk * 4 + slot] = push_make(E, L);
 				L.n_out++;
-				rp_next(E, L);
+				rp_next(L);
 			}
 		}
 	}

@@ -15,7 +15,7 @@ TASK_DTYPE = np.dtype([("read", "<u4"), ("sk", "<u4")])
 REC_DTYPE = np.dtype([("first_chunk", "<u4"), ("count", "<u4"), ("top_score", "<i4"), ("flag512", "<u4"), ("c_occ", "<u4"),
                       ("c_getref", "<u4"), ("c_getref_bytes", "<u4"), ("c_pl", "<u4")])
 STAGED_DTYPE = np.dtype([("ref_ID", "<u4"), ("ref_offset", "<u4"), ("index_in_read", "<u4"), ("len_score", "<u4")])
-STATES = ["FETCH", "CTRL", "OCC", "LOCATE", "FLANK", "RP", "DEAD"]
+STATES = ["FETCH", "CTRL", "OCC", "LOCATE", "FLANK", "LV", "RP", "DEAD"]
 
 
 def build():
