@@ -43,11 +43,8 @@ __device__ __forceinline__ void seed_warp_loop(const SeedPassParams &P, uint32_t
 	const uint32_t lt = (1u << lane) - 1;
 	for (uint32_t turn = 0;; turn++) {
 		if (turn > (1u << 26)) { if (lane == 0) atomicOr(P.ctl + CTL_OVERFLOW, OVF_STUCK); break; }     // never hang the GPU on a malformed index
-		int cnt[SC_N_STATES];
-		#pragma unroll
-		for (int s = 0; s < ST_DEAD; s++) cnt[s] = __popc(__ballot_sync(DSB_FULL, L.st == (uint32_t)s));
-		cnt[ST_DEAD] = 0;
-		const int sel = pick_state(cnt, P.policy, P.fetch_min);
+		const int k = __popc(__match_any_sync(DSB_FULL, L.st));
+		const int sel = (int)vote_state(__reduce_max_sync(DSB_FULL, vote_key(L.st, k, P.policy, P.fetch_min)));
 		if (sel == ST_DEAD) break;
 		if (sel == ST_FETCH) {
 			const uint32_t fm = __ballot_sync(DSB_FULL, L.st == ST_FETCH);

@@ -314,13 +314,15 @@ SC_HD void vis1_st(const LaneMem &M, uint32_t i, uint32_t v)
 	M.vis1[i] = v;
 #endif
 }
+SC_HDN void vis2_zero(uint64_t *vis2)                     // (cold: once per 16 M seeds of a lane)
+{
+	#pragma unroll 1
+	for (int i = 0; i < VIS2_SLOTS; i++) vis2[i] = 0;
+}
 SC_HD void vis_clear(SeedLane &L, const LaneMem &M)
 {
 	L.vis_mask = 0; L.sp_l = 0;
-	if (++L.vis_gen >= (1u << 24)) {
-		for (int i = 0; i < VIS2_SLOTS; i++) M.vis2[i] = 0;
-		L.vis_gen = 1;
-	}
+	if (++L.vis_gen >= (1u << 24)) { vis2_zero(M.vis2); L.vis_gen = 1; }
 }
 SC_HD int vis_insert(const SeedEnv &E, SeedLane &L, const LaneMem &M, uint64_t row)
 {
@@ -407,14 +409,17 @@ SC_HDN int32_t lv_bytes(const uint8_t *ref, const uint8_t *query, int32_t len)
 {
 	int32_t mn_d[12], ed_d[12];
 	int32_t *mn = mn_d + 5, *ed = ed_d + 5;
+	#pragma unroll 1
 	for (int i = -5; i <= 5; i++) { mn[i] = -1; ed[i] = (i > 0) ? (i) : (-i); }
 	mn[6] = 0; ed[6] = 0;
 	int32_t best_score = len;
 	#define SC_R(idx) (((idx) == len) ? (uint32_t)'#' : (uint32_t)ref[(idx) + 5])
 	#define SC_Q(idx) (((idx) == len) ? (uint32_t)'$' : (uint32_t)query[(idx) + 5])
+	#pragma unroll 1
 	for (int i = 0; i <= 4; i++) {
 		int32_t prev_mn = -1, cur_mn = (i - 1), next_mn = mn[-i + 1];
 		int32_t prev_ed = i + 1, cur_ed = i, next_ed = ed[-i + 1];
+		#pragma unroll 1
 		for (int j = -i; j <= 4; j++) {
 			int32_t m, e;
 			if (cur_mn + j < len - 1) {
@@ -663,40 +668,44 @@ SC_HD void h_occ(const SeedEnv &E, SeedLane &L, const LaneMem &M)
 	// LF(rowA) for symbol cA; '$' (5) goes to DOLLOR_POS (bwt.c:54-55).  The count word of the symbol is a second access to the line just fetched.
 	uint64_t lfA = ix.dollar_pos + ix.rank[5];
 	if (cA != 5) lfA = ix.rank[cA] + sc_ld64((const uint64_t *)lineA + cA) + plane_count(pA0, pA1, pA2, inA, cA);
-	if (kind == OK_EXT) {
-		// one step of the backward extension of bwt_MEM_search (cly.c:1403-1422)
-		const uint64_t new_sp = lfA;
-		const uint64_t new_ep = ix.rank[c] + cntB + plane_count(pB0, pB1, pB2, (int)(L.ep & 127), c);
-		L.c_occ += 2;
-		L.pos--;
-		const int l_min = E.slow ? SC_MIN(19, ix.l_ek + 1) : 20, max_rst = E.slow ? 8 : 2;
-		bool brk = false, none = false;
-		if (L.ml >= l_min - 1) {
-			if (new_sp + max_rst >= new_ep) brk = true;
-			else if (L.ml >= L.si) none = true;                    // longer than what is left of the read: no result
+	if (kind <= OK_SINGLE) {
+		uint64_t ins = lfA; bool do_ins = false, first_row = false;
+		if (kind == OK_EXT) {
+			// one step of the backward extension of bwt_MEM_search (cly.c:1403-1422)
+			const uint64_t new_sp = lfA;
+			const uint64_t new_ep = ix.rank[c] + cntB + plane_count(pB0, pB1, pB2, (int)(L.ep & 127), c);
+			L.c_occ += 2;
+			L.pos--;
+			const int l_min = E.slow ? SC_MIN(19, ix.l_ek + 1) : 20, max_rst = E.slow ? 8 : 2;
+			bool brk = false, none = false;
+			if (L.ml >= l_min - 1) {
+				if (new_sp + max_rst >= new_ep) brk = true;
+				else if (L.ml >= L.si) none = true;                // longer than what is left of the read: no result
+			}
+			if (!brk && !none && new_sp + 1 >= new_ep) brk = true;
+			if (!brk && !none) { L.ml++; L.sp = new_sp; L.ep = new_ep; return; }
+			// the rows [new_sp, new_ep) go through single-row searches (cly.c:1425-1446): the first one starts right here
+			L.ext_ml = L.ml; L.pos_ext = L.pos; L.row_res = 0;
+			if (none || new_sp >= new_ep) { L.rows_left = 0; go(L, ST_CTRL, CK_ROWS); return; }
+			L.row_next = new_sp + 1; L.rows_left = (uint32_t)(new_ep - new_sp) - 1;
+			do_ins = true; first_row = true;
+		} else {
+			// one step of bwt_single_search (cly.c:1354-1382); L.ep = last sampled row, L.sa_l = steps since
+			L.c_occ++;
+			if ((rowA & SA_MASK) == 0) { L.ep = rowA; L.sa_l = 0; } else L.sa_l--;
+			if (cA != c) { L.row_res = 1; go(L, ST_CTRL, CK_ROWS); return; }
+			L.ml++; L.pos--;
+			do_ins = true;
 		}
-		if (!brk && !none && new_sp + 1 >= new_ep) brk = true;
-		if (!brk && !none) { L.ml++; L.sp = new_sp; L.ep = new_ep; return; }
-		L.row_res = 0; L.row_next = new_sp;
-		L.rows_left = (none || new_sp >= new_ep) ? 0u : (uint32_t)(new_ep - new_sp);
-		L.ext_ml = L.ml; L.pos_ext = L.pos;
-		go(L, ST_CTRL, CK_ROWS);
+		if (do_ins) {
+			if (vis_insert(E, L, M, ins) == 0) { L.row_res = 0; go(L, ST_CTRL, CK_ROWS); return; }   // row seen before: this single-row search is dropped
+			L.sp = ins;
+			if (first_row) { L.ep = NO_SA; L.sa_l = 0; L.ml = 0; L.pos = L.pos_ext; L.kind = OK_SINGLE; }
+			if (L.ml >= L.si - L.ext_ml) { L.row_res = 1; go(L, ST_CTRL, CK_ROWS); }            // cly.c:1356: the read is used up
+		}
 		return;
 	}
 	L.c_occ++;
-	if (kind == OK_SINGLE) {
-		// one step of bwt_single_search (cly.c:1354-1382); L.ep = last sampled row, L.sa_l = steps since
-		if ((rowA & SA_MASK) == 0) { L.ep = rowA; L.sa_l = 0; } else L.sa_l--;
-		uint32_t res = 2;                                          // 2: goes on, 1: ended (result), 0: aborted (row seen before)
-		if (cA != c) res = 1;
-		else {
-			L.ml++; L.pos--;
-			if (vis_insert(E, L, M, lfA) == 0) res = 0;
-			else { L.sp = lfA; if (L.ml >= L.si - L.ext_ml) res = 1; }
-		}
-		if (res != 2) { L.row_res = res; go(L, ST_CTRL, CK_ROWS); }
-		return;
-	}
 	if (kind == OK_WALK1) {
 		// locate walk of map_seed while the left flank is collected (cly.c:741-757)
 		bool end = false;
@@ -944,8 +953,7 @@ SC_HD void h_flank(const SeedEnv &E, SeedLane &L, const LaneMem &M)
 }
 
 // ---------------------------------------------------------------- LV: one row of the Landau-Vishkin (lv_extd, cly.c:544-607)
-// Lanes in different rows run together: row i visits the diagonals j = -i .. 4, so the turn walks j = -4 .. 4 and a lane joins
-// at its -i.  With j a compile-time constant the 4-bit fields of the mn / ed rows sit at fixed positions.
+// Lanes in different rows run together (row i visits the diagonals j = -i .. 4).
 SC_HD void h_lv(const SeedEnv &E, SeedLane &L, const LaneMem &M)
 {
 	const uint64_t er = lvs_ld(M, 0), eq = lvs_ld(M, 1);
@@ -955,38 +963,36 @@ SC_HD void h_lv(const SeedEnv &E, SeedLane &L, const LaneMem &M)
 	int prev_mn = -1, cur_mn = i - 1, next_mn = lv_get(MN, -i + 1) - 1;
 	int prev_ed = i + 1, cur_ed = i, next_ed = lv_get(ED, -i + 1);
 	bool fin = false;
-	#pragma unroll
-	for (int j = -4; j <= 4; j++) {
-		if (!fin && j >= -i) {
-			int m, e;
-			if (cur_mn + j < len - 1) {
-				int best = cur_mn + 1 - cur_ed;
-				m = cur_mn + 1; e = cur_ed + 1;
-				if (best < next_mn + 1 - next_ed) { m = next_mn + 1; e = next_ed + 1; best = next_mn - next_ed; }
-				if (best < prev_mn - prev_ed) { m = prev_mn + 1; e = prev_ed + 1; }
-			} else {
-				int best = cur_mn - cur_ed;
-				m = cur_mn; e = cur_ed + 1;
-				if (best < prev_mn - prev_ed) { m = prev_mn; e = prev_ed + 1; best = prev_mn - prev_ed; }
-				if (best < next_mn + 1 - next_ed) { m = next_mn + 1; e = next_ed + 1; }
-			}
-			ED = lv_set(ED, j, e);
-			int mn_j = SC_MIN(m, len);
-			mn_j = SC_MIN(mn_j, len - j);
-			{	// in-line match along diagonal j: reference index mn_j + j against query index mn_j, up to the sentinels
-				const int a = mn_j + j;
-				int run = sc_common(er << (2 * (a + 5)), eq << (2 * (mn_j + 5)));
-				run = SC_MIN(run, SC_MIN(len - a, len - mn_j));
-				mn_j += run;
-			}
-			MN = lv_set(MN, j, mn_j + 1);
-			if (mn_j == len || mn_j + j == len) {
-				best_score = SC_MIN(e - 1, best_score);
-				if (j <= i + 1) fin = true;
-			}
-			prev_mn = cur_mn; cur_mn = next_mn; next_mn = lv_get(MN, j + 2) - 1;
-			prev_ed = cur_ed; cur_ed = next_ed; next_ed = lv_get(ED, j + 2);
+	#pragma unroll 1
+	for (int j = -i; j <= 4 && !fin; j++) {
+		int m, e;
+		if (cur_mn + j < len - 1) {
+			int best = cur_mn + 1 - cur_ed;
+			m = cur_mn + 1; e = cur_ed + 1;
+			if (best < next_mn + 1 - next_ed) { m = next_mn + 1; e = next_ed + 1; best = next_mn - next_ed; }
+			if (best < prev_mn - prev_ed) { m = prev_mn + 1; e = prev_ed + 1; }
+		} else {
+			int best = cur_mn - cur_ed;
+			m = cur_mn; e = cur_ed + 1;
+			if (best < prev_mn - prev_ed) { m = prev_mn; e = prev_ed + 1; best = prev_mn - prev_ed; }
+			if (best < next_mn + 1 - next_ed) { m = next_mn + 1; e = next_ed + 1; }
 		}
+		ED = lv_set(ED, j, e);
+		int mn_j = SC_MIN(m, len);
+		mn_j = SC_MIN(mn_j, len - j);
+		{	// in-line match along diagonal j: reference index mn_j + j against query index mn_j, up to the sentinels
+			const int a = mn_j + j;
+			int run = sc_common(er << (2 * (a + 5)), eq << (2 * (mn_j + 5)));
+			run = SC_MIN(run, SC_MIN(len - a, len - mn_j));
+			mn_j += run;
+		}
+		MN = lv_set(MN, j, mn_j + 1);
+		if (mn_j == len || mn_j + j == len) {
+			best_score = SC_MIN(e - 1, best_score);
+			if (j <= i + 1) fin = true;
+		}
+		prev_mn = cur_mn; cur_mn = next_mn; next_mn = lv_get(MN, j + 2) - 1;
+		prev_ed = cur_ed; cur_ed = next_ed; next_ed = lv_get(ED, j + 2);
 	}
 	if (!fin && ++i > 4) fin = true;
 	if (fin) { L.st = ST_FLANK; flank_done(E, L, (uint32_t)len, best_score); return; }
@@ -995,37 +1001,22 @@ SC_HD void h_lv(const SeedEnv &E, SeedLane &L, const LaneMem &M)
 }
 
 // ---------------------------------------------------------------- which state runs this turn
-// cnt[s] = lanes in state s.  The most populated state runs; a state with few lanes waits as long as a fuller one exists,
-// so parked lanes pile up until their state is worth a turn.  Free lanes (FETCH) are refilled as soon as there are
-// SC_FETCH_MIN of them, or when nothing else is left to do.
+// Every lane computes a key from its state and the number of lanes k sharing it; the state of the largest key runs.  The
+// fullest state wins, so a state with few lanes waits while a fuller one exists and parked lanes pile up until their state is
+// worth a turn.  Free lanes (FETCH) are refilled as soon as fetch_min of them wait, or when nothing else is left to do.
+// policy 3: the light states (a few dozen instructions: CTRL, LOCATE, RP) also go first once fetch_min lanes wait in them.
 #ifndef SC_FETCH_MIN
-#define SC_FETCH_MIN 3
+#define SC_FETCH_MIN 4
 #endif
 #ifndef SC_POLICY
-#define SC_POLICY 3
+#define SC_POLICY 2
 #endif
-SC_HD int pick_state(const int *cnt, int policy, int fetch_min)
+SC_HD uint32_t vote_key(uint32_t st, int k, int policy, int fetch_min)
 {
-	if (policy >= 3) {
-		// light states (a few dozen instructions: FETCH, CTRL, LOCATE, RP) run as soon as fetch_min lanes wait in one of them -- their
-		// lanes are back in the heavy states (OCC, FLANK, LV) the sooner, which then run fuller; otherwise the fullest heavy state
-		int bl = ST_DEAD, nl = 0;
-		if (cnt[ST_CTRL] > nl) { nl = cnt[ST_CTRL]; bl = ST_CTRL; }
-		if (cnt[ST_FETCH] > nl) { nl = cnt[ST_FETCH]; bl = ST_FETCH; }
-		if (cnt[ST_LOCATE] > nl) { nl = cnt[ST_LOCATE]; bl = ST_LOCATE; }
-		if (cnt[ST_RP] > nl) { nl = cnt[ST_RP]; bl = ST_RP; }
-		if (nl >= fetch_min) return bl;
-		int bh = ST_DEAD, nh = 0;
-		if (cnt[ST_OCC] > nh) { nh = cnt[ST_OCC]; bh = ST_OCC; }
-		if (cnt[ST_LV] > nh) { nh = cnt[ST_LV]; bh = ST_LV; }
-		if (cnt[ST_FLANK] > nh) { nh = cnt[ST_FLANK]; bh = ST_FLANK; }
-		if (nh >= nl && nh > 0) return bh;
-		return bl;
-	}
-	if (cnt[ST_FETCH] >= fetch_min) return ST_FETCH;
-	int best = ST_DEAD, n = 0;
-	#pragma unroll
-	for (int s = ST_CTRL; s < ST_DEAD; s++) if (cnt[s] > n) { n = cnt[s]; best = s; }
-	if (best == ST_DEAD && cnt[ST_FETCH] > 0) return ST_FETCH;
-	return best;
+	if (st == ST_DEAD) return 0;
+	uint32_t prio = (uint32_t)k;                                   // 1..32
+	if (st == ST_FETCH) prio = (k >= fetch_min) ? 100u : 0u;
+	else if (policy >= 3 && (st == ST_CTRL || st == ST_LOCATE || st == ST_RP) && k >= fetch_min) prio = 64u + (uint32_t)k;
+	return (prio << 3) | (7u - st) | 0x800u;
 }
+SC_HD uint32_t vote_state(uint32_t best_key) { return best_key ? 7u - (best_key & 7u) : (uint32_t)ST_DEAD; }

@@ -202,7 +202,9 @@ int64_t emul_seed_pass(void *h_, const char *seqs, const uint64_t *offs, uint32_
 			if (w.dead) continue;
 			int cnt[SC_N_STATES] = {0};
 			for (int l = 0; l < 32; l++) cnt[w.L[l].st]++;
-			const int sel = pick_state(cnt, sc_policy, sc_fetch_min);
+			uint32_t best = 0;
+			for (int l = 0; l < 32; l++) { const uint32_t key = vote_key(w.L[l].st, cnt[w.L[l].st], sc_policy, sc_fetch_min); if (key > best) best = key; }
+			const int sel = (int)vote_state(best);
 			if (sel == ST_DEAD) { w.dead = true; n_dead++; continue; }
 			S.turns[sel]++; S.lanes[sel] += cnt[sel];
 			for (int l = 0; l < 32; l++) {
