@@ -62,6 +62,8 @@ _sig("dsb_batch_kernel_ms", C.c_int, _vp, C.POINTER(C.c_float * 11), C.c_int)
 _sig("dsb_ctx_mark", C.c_int, _vp, C.c_int)
 _sig("dsb_ctx_elapsed_ms", C.c_int, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_float))
 _sig("dsb_batch_launches", C.c_int, _vp)
+_sig("dsb_batch_retries", C.c_int, _vp)
+_sig("dsb_index_clone", C.c_int, _vp, C.c_int, C.POINTER(_vp))
 _sig("dsb_batch_counters", C.c_int, _vp, C.POINTER(C.c_uint64 * 16))
 _sig("dsb_batch_profile", C.c_int, _vp, _vp)
 _sig("dsb_ctx_set_bin_capacity", C.c_int, _vp, C.c_uint32)
@@ -92,9 +94,12 @@ def _check(rc, where):
 class Index:
     """The on-disk deSAMBA index resident in one GPU's HBM (load_idx, idx.c:1103-1160)."""
 
-    def __init__(self, index_dir, device=0):
+    def __init__(self, index_dir, device=0, _clone_of=None):
         self._h = _vp()
-        _check(lib.dsb_index_load(os.fsencode(index_dir), device, C.byref(self._h)), "dsb_index_load")
+        if _clone_of is None:
+            _check(lib.dsb_index_load(os.fsencode(index_dir), device, C.byref(self._h)), "dsb_index_load")
+        else:
+            _check(lib.dsb_index_clone(_clone_of._h, device, C.byref(self._h)), "dsb_index_clone")
         self.device = device
         n = lib.dsb_index_n_ref(self._h)
         ri = lib.dsb_index_ref_info(self._h)
@@ -102,6 +107,10 @@ class Index:
         self.ref_len = [ri[i].seq_l for i in range(n)]
         self.hbm_bytes = lib.dsb_index_hbm_bytes(self._h)
         self.l_ek = lib.dsb_index_l_ek(self._h)
+
+    def clone(self, device):
+        """the same index on another GPU, copied device to device (dsb_index_clone)"""
+        return Index(None, device, _clone_of=self)
 
     def close(self):
         if self._h:

@@ -9,15 +9,18 @@
  *   writer (main)   formats the result records of each batch in input order (output_results, cly_mt.c:350-365)
  * The index is replicated per GPU, reads are sharded by batch, nothing is exchanged between GPUs.
  * Extra options: -g INT GPUs to use [all visible], -c INT contexts (batches in flight) per GPU [3], -B INT reads per batch
- * [262144], -M INT Mbases per batch [512], -P INT helper threads of the FASTQ reader [8 on >= 16 cores; 0 = serial reader].
+ * [262144], -M INT Mbases per batch [512], -P INT helper threads of the FASTQ reader [8 on >= 16 cores; 0 = serial reader],
+ * -A / -m INT per-read anchor / match capacity, -L INT longest read accepted, -p INT pool sizing in % (dsb_opts).
  * -t is accepted and ignored (the thread pool it sized no longer exists).
  *
  * Classify_buff_pool.max_read_l (cly.c:2958) is the reference's only cross-read state; with -t 1 it is the running maximum
  * in input order.  It only matters through the test `max_read_l < 510`, so a batch needs its predecessors' value only
- * when it holds a read < 510 bp while an unfinished earlier batch holds one >= 510 bp; only then does a GPU wait.
+ * when it holds a read < 510 bp while an unfinished earlier batch holds one >= 510 bp; only then does a GPU wait
+ * (batch_order.h: the value handed to a batch is built from batches before it in input order only).
  */
 #define _GNU_SOURCE
 #include "desamba_b200.h"
+#include "batch_order.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -37,10 +40,11 @@ typedef struct {
 	uint32_t batch_reads; uint64_t batch_bases;
 	FILE *out;
 	int n_parse_threads;                    /* helper threads of the FASTQ reader (0: serial reader only) */
+	uint32_t max_anchors, max_matches, max_read_len, pool_scale_pct;   /* 0: library default (dsb_opts) */
 } opts_t;
 
 /* ---------------------------------------------------------------- batches */
-enum { SLOT_FREE = 0, SLOT_READY, SLOT_BUSY, SLOT_DONE };
+enum { SLOT_FREE = BO_FREE, SLOT_READY = BO_READY, SLOT_BUSY = BO_BUSY, SLOT_DONE = BO_DONE };
 typedef struct {
 	int state; int rc;
 	uint64_t seq_no;
@@ -61,7 +65,9 @@ typedef struct {
 	int n_slots; slot_t *slot;
 	pthread_mutex_t mu; pthread_cond_t cv;
 	uint64_t n_filled, n_claimed, n_written; int eof;
-	int32_t known_max;                      /* max_read_l over finished batches */
+	bo_slot *bo;                            /* per slot: what batch_order.h needs (kept under mu) */
+	uint64_t done_upto; int32_t prefix_max; /* every batch below done_upto is finished; max_read_l after them */
+	uint64_t n_capacity_reads;              /* reads that exceeded a per-read capacity: written as unclassified, with a warning */
 	int error; char errmsg[600];
 	int n_files; char **files;
 	uint64_t total_sequences;
@@ -72,6 +78,20 @@ typedef struct {
 
 typedef struct { shared_t *sh; int gpu; dsb_index *ix; dsb_ctx *ctx; } worker_t;
 static double now_s(void);
+
+/* the x-alloc convention of the reference (utils.c:112-134): out of memory ends the run with a message */
+static void *xrealloc(void *p, size_t n)
+{
+	void *q = realloc(p, n ? n : 1);
+	if (!q) { fprintf(stderr, "[deSAMBA-b200] out of memory (%zu bytes)\n", n); exit(1); }
+	return q;
+}
+static void *xcalloc(size_t n, size_t sz)
+{
+	void *q = calloc(n ? n : 1, sz);
+	if (!q) { fprintf(stderr, "[deSAMBA-b200] out of memory (%zu x %zu bytes)\n", n, sz); exit(1); }
+	return q;
+}
 
 static void fail(shared_t *sh, const char *what, int rc)
 {
@@ -113,11 +133,11 @@ static int slot_add(shared_t *sh, slot_t *b, const char *name, size_t n_name, co
 	if (b->n_reads == 0) b->offs[0] = 0;
 	memcpy(b->seqs + b->n_bases, seq, L);
 	if (o->fmt == FMT_SAM_FULL) {
-		if (b->n_bases + L + 1 > b->m_quals) { b->m_quals = (b->n_bases + L + 1) * 2; b->quals = realloc(b->quals, b->m_quals); }
+		if (b->n_bases + L + 1 > b->m_quals) { b->m_quals = (b->n_bases + L + 1) * 2; b->quals = xrealloc(b->quals, b->m_quals); }
 		if (n_qual == L) memcpy(b->quals + b->n_bases, qual, L); else memset(b->quals + b->n_bases, '*', L);
 	}
-	if ((size_t)b->n_reads + 1 > b->m_name_off) { b->m_name_off = ((size_t)b->n_reads + 1) * 2; b->name_off = realloc(b->name_off, b->m_name_off * 4); }
-	if (b->n_names + n_name + 1 > b->m_names) { b->m_names = (b->n_names + n_name + 1) * 2; b->names = realloc(b->names, b->m_names); }
+	if ((size_t)b->n_reads + 1 > b->m_name_off) { b->m_name_off = ((size_t)b->n_reads + 1) * 2; b->name_off = xrealloc(b->name_off, b->m_name_off * 4); }
+	if (b->n_names + n_name + 1 > b->m_names) { b->m_names = (b->n_names + n_name + 1) * 2; b->names = xrealloc(b->names, b->m_names); }
 	b->name_off[b->n_reads] = (uint32_t)b->n_names;
 	memcpy(b->names + b->n_names, name, n_name); b->names[b->n_names + n_name] = 0; b->n_names += n_name + 1;
 	b->n_bases += L; b->n_reads++; b->offs[b->n_reads] = b->n_bases;
@@ -148,9 +168,9 @@ static int slot_add_block(shared_t *sh, slot_t *b, const char *map, const fq_rec
 	const size_t n = i1 - i0;
 	if (grow_pinned((void **)&b->seqs, &b->m_seqs, b->n_bases + bases + 16, b->n_bases, o->batch_bases + ((size_t)4 << 20)) ||
 	    grow_pinned((void **)&b->offs, &b->m_offs, ((size_t)b->n_reads + n + 2) * 8, ((size_t)b->n_reads + 1) * 8, ((size_t)o->batch_reads + 2) * 8)) return -1;
-	if (o->fmt == FMT_SAM_FULL && b->n_bases + bases + 1 > b->m_quals) { b->m_quals = (b->n_bases + bases + 1) * 2; b->quals = realloc(b->quals, b->m_quals); }
-	if ((size_t)b->n_reads + n > b->m_name_off) { b->m_name_off = ((size_t)b->n_reads + n) * 2; b->name_off = realloc(b->name_off, b->m_name_off * 4); }
-	if (b->n_names + names > b->m_names) { b->m_names = (b->n_names + names) * 2; b->names = realloc(b->names, b->m_names); }
+	if (o->fmt == FMT_SAM_FULL && b->n_bases + bases + 1 > b->m_quals) { b->m_quals = (b->n_bases + bases + 1) * 2; b->quals = xrealloc(b->quals, b->m_quals); }
+	if ((size_t)b->n_reads + n > b->m_name_off) { b->m_name_off = ((size_t)b->n_reads + n) * 2; b->name_off = xrealloc(b->name_off, b->m_name_off * 4); }
+	if (b->n_names + names > b->m_names) { b->m_names = (b->n_names + names) * 2; b->names = xrealloc(b->names, b->m_names); }
 	if (b->n_reads == 0) b->offs[0] = 0;
 	const uint32_t first = b->n_reads;
 	for (size_t i = i0; i < i1; i++) {
@@ -184,7 +204,7 @@ static int slot_add_block(shared_t *sh, slot_t *b, const char *map, const fq_rec
 static void *reader_main(void *arg)
 {
 	shared_t *sh = (shared_t *)arg; opts_t *o = sh->o;
-	stream_t st; memset(&st, 0, sizeof st); st.buf = malloc(SBUF);
+	stream_t st; memset(&st, 0, sizeof st); st.buf = xrealloc(NULL, SBUF);
 	rec_t rec; memset(&rec, 0, sizeof rec);
 	int file_i = 0, stream_open = 0, pending = 0;      /* pending: rec holds a record not yet stored */
 	uint32_t m_bin_read = 0;                           /* running BUFF_REALLOC capacity over all reads, in input order */
@@ -276,7 +296,12 @@ static void *reader_main(void *arg)
 		}
 		sh->t_reader_work += now_s() - tw1;
 		pthread_mutex_lock(&sh->mu);
-		if (b->n_reads) { b->seq_no = sh->n_filled; b->state = SLOT_READY; sh->n_filled++; sh->total_sequences += b->n_reads; }
+		if (b->n_reads) {
+			b->seq_no = sh->n_filled; b->state = SLOT_READY;
+			bo_slot *q = &sh->bo[sh->n_filled % sh->n_slots];
+			q->state = BO_READY; q->has_long = b->has_long; q->has_short = b->has_short; q->max_out = 0; q->seq_no = b->seq_no;
+			sh->n_filled++; sh->total_sequences += b->n_reads;
+		}
 		if (end_of_input) sh->eof = 1;
 		pthread_cond_broadcast(&sh->cv);
 		pthread_mutex_unlock(&sh->mu);
@@ -299,35 +324,40 @@ static void *worker_main(void *arg)
 		if (sh->error || sh->n_claimed == sh->n_filled) { pthread_mutex_unlock(&sh->mu); break; }
 		const uint64_t my = sh->n_claimed++;
 		slot_t *b = &sh->slot[my % sh->n_slots];
-		b->state = SLOT_BUSY;
-		/* the only cross-batch dependency (see the header comment) */
-		if (sh->known_max < 510 && b->has_short) {
-			for (;;) {
-				int earlier_long = 0;
-				for (uint64_t k = sh->n_written; k < my; k++) { slot_t *e = &sh->slot[k % sh->n_slots]; if (e->state == SLOT_BUSY && e->has_long) earlier_long = 1; }
-				if (!earlier_long || sh->known_max >= 510 || sh->error) break;
-				pthread_cond_wait(&sh->cv, &sh->mu);
-			}
-		}
-		const int32_t max_in = sh->known_max;
+		b->state = SLOT_BUSY; sh->bo[my % sh->n_slots].state = BO_BUSY;
+		/* the only cross-batch dependency (batch_order.h) */
+		int32_t max_in = 0;
+		const double tw0 = now_s();
+		while (!sh->error && !bo_may_start(sh->bo, sh->n_slots, my, sh->done_upto, sh->prefix_max, &max_in)) pthread_cond_wait(&sh->cv, &sh->mu);
+		sh->t_worker_wait += now_s() - tw0;
+		if (sh->error) { pthread_mutex_unlock(&sh->mu); break; }
 		pthread_mutex_unlock(&sh->mu);
 
-		if ((size_t)b->n_reads > b->m_rr) { b->m_rr = (size_t)b->n_reads * 2; b->rr = realloc(b->rr, b->m_rr * sizeof *b->rr); }
+		if ((size_t)b->n_reads > b->m_rr) { b->m_rr = (size_t)b->n_reads * 2; b->rr = xrealloc(b->rr, b->m_rr * sizeof *b->rr); }
 		size_t want = (size_t)b->n_reads * 24 + 4096;
 		int32_t max_out = max_in; int rc;
 		const double tc0 = now_s();
 		for (;;) {
-			if (want > b->m_hits) { b->m_hits = want; free(b->hits); b->hits = malloc(b->m_hits * sizeof *b->hits); }
+			if (want > b->m_hits) { b->m_hits = want; free(b->hits); b->hits = xrealloc(NULL, b->m_hits * sizeof *b->hits); }
 			dsb_ctx_set_bin_capacity(w->ctx, b->m_bin_read_in);
 			rc = dsb_classify_batch(w->ctx, b->seqs, b->offs, b->n_reads, max_in, &max_out, b->rr, b->hits, b->m_hits, &b->n_hits);
 			if (rc == DSB_E_CAPACITY && b->n_hits > b->m_hits) { want = b->n_hits; continue; }
 			break;
 		}
+		uint64_t n_cap = 0;
+		if (rc == DSB_E_CAPACITY) {
+			/* single reads beyond a per-read capacity (-A / -m): they carry dsb_read_result.error and no hits; the run goes on and
+			 * they are written as unclassified (the reference grows its vectors without bound instead) */
+			for (uint32_t r = 0; r < b->n_reads; r++) if (b->rr[r].error) { n_cap++; b->rr[r].n_hit = 0; }
+			rc = DSB_OK;
+		}
 		if (rc != DSB_OK) { fail(sh, "dsb_classify_batch", rc); break; }
 		pthread_mutex_lock(&sh->mu);
 		sh->t_worker_call += now_s() - tc0;
-		if (max_out > sh->known_max) sh->known_max = max_out;
+		sh->n_capacity_reads += n_cap;
 		b->state = SLOT_DONE; b->rc = rc;
+		sh->bo[my % sh->n_slots].max_out = max_out; sh->bo[my % sh->n_slots].state = BO_DONE;
+		bo_finished(sh->bo, sh->n_slots, sh->n_claimed, &sh->done_upto, &sh->prefix_max);
 		pthread_cond_broadcast(&sh->cv);
 		pthread_mutex_unlock(&sh->mu);
 	}
@@ -336,7 +366,7 @@ static void *worker_main(void *arg)
 
 /* ---------------------------------------------------------------- writers (cly_mt.c:60-344) */
 typedef struct { char *s; size_t n, m; } obuf_t;
-static inline void ob_need(obuf_t *b, size_t add) { if (b->n + add > b->m) { b->m = (b->n + add) * 2 + 4096; b->s = realloc(b->s, b->m); } }
+static inline void ob_need(obuf_t *b, size_t add) { if (b->n + add > b->m) { b->m = (b->n + add) * 2 + 4096; b->s = xrealloc(b->s, b->m); } }
 static const char PRI_STR[3][4] = {"PRI", "SEC", "SUP"};
 
 static void put_hit(obuf_t *ob, const dsb_hit *c, const dsb_ref_info *ri, int rst_cnt)      /* print_hit, cly_mt.c:60-105 */
@@ -406,7 +436,8 @@ static void usage(void)
 	fprintf(stderr, "    -l, INT         minimum matching length, ignored for NGS reads [170]\n    -r, INT         max Output number of secondary alignments[5]\n");
 	fprintf(stderr, "    -o, FILE        output results into file [stdout]\n    -s, INT         MIN score[64]\n");
 	fprintf(stderr, "    -f, STR         output format, one of: SAM (default), SAM_FULL, DES, DES_FULL\n");
-	fprintf(stderr, "    -g, INT         number of GPUs [all visible]\n    -c, INT         batches in flight per GPU [3]\n    -B, INT         reads per batch [262144]\n    -M, INT         Mbases per batch [512]\n    -P, INT         FASTQ reader threads [8 on >= 16 cores; 0: serial]\n\n");
+	fprintf(stderr, "    -g, INT         number of GPUs [all visible]\n    -c, INT         batches in flight per GPU [3]\n    -B, INT         reads per batch [262144]\n    -M, INT         Mbases per batch [512]\n    -P, INT         FASTQ reader threads [8 on >= 16 cores; 0: serial]\n");
+	fprintf(stderr, "    -A, INT         anchors kept per read [16384]\n    -m, INT         9-mer matches kept per extension [16384]\n    -L, INT         longest read accepted [1048576]\n    -p, INT         size of the per-batch device pools in %% of the built-in sizing [100]\n\n");
 }
 
 typedef struct { const opts_t *o; const dsb_ref_info *ri; slot_t *b; uint32_t r0, r1; obuf_t ob; } fmt_job_t;
@@ -425,9 +456,9 @@ static double cpu_s(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); return 
 
 static int classify_main(int argc, char **argv)
 {
-	opts_t o = {170, 4, 5, FMT_SAM, 64, 0, 3, 262144, 512ull << 20, stdout, -1};
+	opts_t o = {170, 4, 5, FMT_SAM, 64, 0, 3, 262144, 512ull << 20, stdout, -1, 0, 0, 0, 0};
 	int c;
-	while ((c = getopt(argc, argv, "ht:l:r:f:o:s:g:B:M:c:P:")) >= 0) {
+	while ((c = getopt(argc, argv, "ht:l:r:f:o:s:g:B:M:c:P:A:m:L:p:")) >= 0) {
 		if (c == 'h') { usage(); return 0; }
 		else if (c == 't') o.n_threads = atoi(optarg);
 		else if (c == 'l') o.l_min_match = atoi(optarg);
@@ -437,6 +468,10 @@ static int classify_main(int argc, char **argv)
 		else if (c == 'g') o.n_gpus = atoi(optarg);
 		else if (c == 'P') o.n_parse_threads = atoi(optarg);
 		else if (c == 'c') o.ctx_per_gpu = atoi(optarg);
+		else if (c == 'A') o.max_anchors = (uint32_t)atol(optarg);
+		else if (c == 'm') o.max_matches = (uint32_t)atol(optarg);
+		else if (c == 'L') o.max_read_len = (uint32_t)atol(optarg);
+		else if (c == 'p') o.pool_scale_pct = (uint32_t)atol(optarg);
 		else if (c == 'B') o.batch_reads = (uint32_t)atol(optarg);
 		else if (c == 'M') o.batch_bases = (uint64_t)atol(optarg) << 20;
 		else if (c == 'f') {
@@ -460,32 +495,41 @@ static int classify_main(int argc, char **argv)
 	#define STAMP(what) do { if (verbose) fprintf(stderr, "[deSAMBA-b200] %-34s at %7.3f s\n", what, now_s() - t_start); } while (0)
 	/* the reader starts at once: the first batches are parsed into pinned memory while the index is loaded into HBM */
 	shared_t sh; memset(&sh, 0, sizeof sh);
-	sh.o = &o; sh.n_slots = 2 * ((o.n_gpus > 0 ? o.n_gpus : 8) * o.ctx_per_gpu) + 2; sh.slot = calloc(sh.n_slots, sizeof(slot_t));
+	sh.o = &o; sh.n_slots = 2 * ((o.n_gpus > 0 ? o.n_gpus : 8) * o.ctx_per_gpu) + 2; sh.slot = xcalloc(sh.n_slots, sizeof(slot_t)); sh.bo = xcalloc(sh.n_slots, sizeof(bo_slot));
 	sh.max_ahead = 3;
 	pthread_mutex_init(&sh.mu, NULL); pthread_cond_init(&sh.cv, NULL);
 	sh.n_files = argc - optind; sh.files = argv + optind;
 	pthread_t rd;
 	pthread_create(&rd, NULL, reader_main, &sh);
+	/* load_idx runs ONCE (idx.c:1103): the index is read, uploaded and re-cut on GPU 0; the other GPUs get device-to-device copies */
+	#define BAIL(...) do { fprintf(stderr, __VA_ARGS__); pthread_mutex_lock(&sh.mu); if (!sh.error) sh.error = -1; pthread_cond_broadcast(&sh.cv); pthread_mutex_unlock(&sh.mu); pthread_join(rd, NULL); return 1; } while (0)
 	dsb_index *gix[64];
 	int n_gpus = 0;
+	double t_load0 = 0, t_clone = 0;
 	for (int g = 0; g < (o.n_gpus > 0 ? o.n_gpus : 64); g++) {
 		dsb_index *ix = NULL;
-		int rc = dsb_index_load(index_dir, g, &ix);
+		const double tl = now_s();
+		int rc = (g == 0 || getenv("DSB_NO_CLONE")) ? dsb_index_load(index_dir, g, &ix) : dsb_index_clone(gix[0], g, &ix);
 		if (rc != DSB_OK) {
-			if (g == 0 || o.n_gpus > 0) { fprintf(stderr, "\n[deSAMBA-b200] cannot load index on GPU %d: %s\n", g, dsb_last_error()); return 1; }
+			if (g == 0 || o.n_gpus > 0) BAIL("\n[deSAMBA-b200] cannot load index on GPU %d: %s\n", g, dsb_last_error());
 			break;                                       /* ran out of visible devices */
 		}
+		if (g == 0) t_load0 = now_s() - tl; else t_clone += now_s() - tl;
 		gix[g] = ix; n_gpus++;
 	}
 	STAMP("index resident in HBM");
 	/* several contexts (streams) per GPU: the expensive tail reads of one batch overlap the next batch */
 	const int n_workers = n_gpus * o.ctx_per_gpu;
-	worker_t *w = calloc(n_workers, sizeof *w);
+	worker_t *w = xcalloc(n_workers, sizeof *w);
 	dsb_opts dop; dsb_opts_default(&dop);
 	dop.l_min_match = o.l_min_match; dop.min_score = o.min_score;
+	if (o.max_anchors) dop.max_anchors = o.max_anchors;
+	if (o.max_matches) dop.max_matches = o.max_matches;
+	if (o.max_read_len) dop.max_read_len = o.max_read_len;
+	if (o.pool_scale_pct) dop.pool_scale_pct = o.pool_scale_pct;
 	for (int k = 0; k < n_workers; k++) {
 		w[k].gpu = k % n_gpus; w[k].ix = gix[k % n_gpus];
-		if (dsb_ctx_create(w[k].ix, &dop, &w[k].ctx) != DSB_OK) { fprintf(stderr, "\n[deSAMBA-b200] %s\n", dsb_last_error()); return 1; }
+		if (dsb_ctx_create(w[k].ix, &dop, &w[k].ctx) != DSB_OK) BAIL("\n[deSAMBA-b200] %s\n", dsb_last_error());
 	}
 	STAMP("contexts created");
 	const dsb_ref_info *ri = dsb_index_ref_info(w[0].ix);
@@ -497,7 +541,7 @@ static int classify_main(int argc, char **argv)
 	if (sh.max_ahead > sh.n_slots) sh.max_ahead = sh.n_slots;
 	pthread_cond_broadcast(&sh.cv);
 	pthread_mutex_unlock(&sh.mu);
-	pthread_t *th = calloc(n_workers, sizeof *th);
+	pthread_t *th = xcalloc(n_workers, sizeof *th);
 	for (int k = 0; k < n_workers; k++) { w[k].sh = &sh; pthread_create(&th[k], NULL, worker_main, &w[k]); }
 
 	/* the text of a batch is formatted by helper threads (contiguous shares of the batch's reads, written in order) */
@@ -551,7 +595,8 @@ static int classify_main(int argc, char **argv)
 	const double sec = now_s() - t0;
 	fprintf(stderr, "%ld sequences processed in %.3fs (%.1f Kseq/m).\n", (long)sh.total_sequences, sec, sh.total_sequences / 1.0e3 / (sec / 60));   /* report_stats, cly_mt.c:439-446 */
 	fprintf(stderr, "Classify CPU: %.3f sec\n", cpu_s() - c0);
-	fprintf(stderr, "GPUs: %d (%d contexts each)\n", n_gpus, o.ctx_per_gpu);
+	fprintf(stderr, "GPUs: %d (%d contexts each); index: %.3f s load on GPU 0 + %.3f s device-to-device copies\n", n_gpus, o.ctx_per_gpu, t_load0, t_clone);
+	if (sh.n_capacity_reads) fprintf(stderr, "[deSAMBA-b200] warning: %llu read(s) exceeded a per-read capacity and were written as unclassified (raise -A / -m)\n", (unsigned long long)sh.n_capacity_reads);
 	for (int k = 0; k < n_workers; k++) dsb_ctx_free(w[k].ctx);
 	for (int g = 0; g < n_gpus; g++) dsb_index_free(gix[g]);
 	STAMP("device memory released");

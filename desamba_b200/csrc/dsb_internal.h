@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <vector>
 #include <string>
+#include <utility>
 
 void dsb_set_error(const char *fmt, ...);
 #define DSB_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -13,7 +14,7 @@ void dsb_set_error(const char *fmt, ...);
 struct dsb_index {
 	int device;
 	DevIndex dev;                       // device pointers + scalars, passed to kernels by value
-	std::vector<void *> allocs;         // every cudaMalloc of this index
+	std::vector<std::pair<void *, size_t>> allocs;   // every cudaMalloc of this index (pointer, bytes)
 	uint64_t hbm_bytes;
 	std::vector<dsb_ref_info> ref_info; // host copy of .ref_i for the writers
 	uint64_t ref_bin_n;                 // bytes of .ref_b (L_REF = 4 * this, cly_mt.c:527)

@@ -81,6 +81,9 @@ const char *dsb_version(void);
 /* load_idx + load_bwt (idx.c:1103-1160, bwt.c:68-104): reads <dir>/deSAMBA.{bwt,sa,exki,exk0,exk1,unv,ref_b,ref_i,ref_p}
  * (.acg is not needed on the GPU) and uploads to `device`. */
 int  dsb_index_load(const char *dir, int device, dsb_index **out);
+/* the same index on another GPU of the box, copied device to device from a loaded one (peer copy over NVLink / NVSwitch):
+ * a multi-GPU run reads, uploads and re-cuts the index once */
+int  dsb_index_clone(const dsb_index *src, int device, dsb_index **out);
 void dsb_index_free(dsb_index *ix);
 uint64_t dsb_index_n_ref(const dsb_index *ix);
 const dsb_ref_info *dsb_index_ref_info(const dsb_index *ix);          /* host copy of .ref_i */

@@ -40,3 +40,20 @@ for s in syn_long10 syn_short1; do
 done
 md5sum "$R"/sets/*.fq "$R/demo/ERR1050068.fastq" "$FA" "$SYN/syn.fa" | sed "s#$R/##" > "$G/inputs.md5"
 ls -la "$G"
+# l_ek = 17..20 (hash masks of 31..37 bits): the same synthetic index with its exist-k-mer tables re-written for a larger size
+# class (oracle/rebuild_exk.c: the index builder's own rule, idx.c:998-1031; class 27 reproduces the builder's tables byte for
+# byte), classified by the unmodified reference.  EK_CLASSES="28 30 32 34" (table bytes = 2^class each; 34 needs 32 GB of RAM + disk)
+EKW=${EKW:-/tmp/dsb_ek}; mkdir -p "$EKW"
+[ -x "$HERE/rebuild_exk" ] || gcc -O2 -w -o "$HERE/rebuild_exk" "$HERE/rebuild_exk.c"
+"$HERE/rebuild_exk" "$SYN/idx" "$EKW/c27" 27 2>/dev/null && cmp "$EKW/c27/deSAMBA.exk0" "$SYN/idx/deSAMBA.exk0" && cmp "$EKW/c27/deSAMBA.exk1" "$SYN/idx/deSAMBA.exk1"
+rm -rf "$EKW/c27"
+for c in ${EK_CLASSES:-28 30 32}; do
+  case $c in 28) ek=17;; 30) ek=18;; 32) ek=19;; 34) ek=20;; *) echo "class $c?"; exit 1;; esac
+  "$HERE/rebuild_exk" "$SYN/idx" "$EKW/c$c" $c
+  for s in syn_long10 syn_short1; do
+    [ $c -ge 32 ] && [ $s = syn_long10 ] && continue
+    "$R/deSAMBA_zero" classify -t 1 -f DES_FULL "$EKW/c$c" "$R/sets/$s.fq" -o "$G/$s.ek$ek.DES_FULL" 2>/dev/null; gzip -9nf "$G/$s.ek$ek.DES_FULL"
+  done
+  rm -rf "$EKW/c$c"
+done
+ls -la "$G"

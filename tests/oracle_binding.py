@@ -54,6 +54,43 @@ def ensure_syn_index():
     return SYN_IDX
 
 
+EK_CLASSES = {17: 28, 18: 30, 19: 32, 20: 34}      # l_ek -> log2 of the exist-k-mer table size in bytes (idx.c:966-996)
+
+
+def ensure_ek_index(l_ek):
+    """the synthetic multi-strain index with its exist-k-mer tables re-written for the size class of `l_ek` (oracle/rebuild_exk.c:
+    the index builder's own rule applied to the unitigs recovered from the index; the unmodified reference made the goldens
+    tests/golden/*.ek<l_ek>.* on exactly these files).  Tables of 2 x 2^28 .. 2 x 2^34 bytes: built on first use in shared
+    memory / a temporary directory, never shipped."""
+    src = ensure_syn_index()
+    exe = os.path.join(ORACLE_DIR, "rebuild_exk")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(exe + ".c"):
+        subprocess.run(["gcc", "-O2", "-w", "-o", exe, exe + ".c"], check=True)
+    lg = EK_CLASSES[l_ek]
+    need = 2 * (1 << lg) + (1 << 20)
+    base = None
+    for cand in (os.environ.get("DSB_EK_DIR"), "/dev/shm", "/tmp"):
+        if cand and os.path.isdir(cand):
+            st = os.statvfs(cand)
+            if st.f_bavail * st.f_frsize > need + (2 << 30):
+                base = cand
+                break
+    if base is None:
+        raise FileNotFoundError(f"no room for an l_ek {l_ek} index ({need >> 20} MiB)")
+    dst = os.path.join(base, "dsb_ek", f"c{lg}")
+    if not (os.path.exists(os.path.join(dst, "deSAMBA.exk1")) and os.path.getsize(os.path.join(dst, "deSAMBA.exk1")) == (1 << lg)):
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        subprocess.run([exe, src, dst, str(lg)], check=True, capture_output=True)
+    return dst
+
+
+def drop_ek_index(l_ek):
+    import shutil
+    for cand in (os.environ.get("DSB_EK_DIR"), "/dev/shm", "/tmp"):
+        if cand:
+            shutil.rmtree(os.path.join(cand, "dsb_ek", f"c{EK_CLASSES[l_ek]}"), ignore_errors=True)
+
+
 _lib = None
 
 

@@ -136,6 +136,43 @@ def test_second_index_multi_strain(gpu, ob, name, spec):
     assert out == gzip.open(os.path.join(GOLD, f"{name}.DES_FULL.gz")).read()
 
 
+@pytest.mark.parametrize("l_ek", [17, 18, 19, 20])
+def test_larger_exist_kmer_table_classes(gpu, ob, l_ek):
+    # l_ek = 17..20 with hash masks of 31..37 bits (set_ekmer_par, idx.c:966-982; the classes a 0.3 .. 40 Gbp reference gets):
+    # tables of 2 x 256 MiB .. 2 x 16 GiB (no L2 summary above 256 MiB), single_base_max 13..16.  Records and every algorithmic
+    # counter against the oracle, driver text against the unmodified reference's output on the same index files.
+    dsb, _, _ = gpu
+    try:
+        idx = ob.ensure_ek_index(l_ek)
+    except FileNotFoundError as e:
+        pytest.skip(str(e))
+    try:
+        orc = ob.Oracle(idx)
+        ix2 = dsb.Index(idx, 0)
+        ctx2 = dsb.Context(ix2)
+        assert ix2.l_ek == l_ek
+        try:
+            for name, spec in (("syn_long10", ("long", 400, 0.10, 20261025)), ("syn_short1", ("short", 4000, 0.01, 20261026))):
+                path = ob.sim_set(name, *spec, fasta=ob.SYN_FA)
+                names, seqs, _ = ob.read_fastq(path)
+                cat, offs = ob.pack(seqs)
+                orc.counters(reset=True)
+                rr_o, hits_o, mx_o = orc.classify(cat, offs)
+                cnt_o = orc.counters()
+                res = ctx2.classify(cat, offs)
+                _assert_same(ob, res, rr_o, hits_o, names)
+                cnt_g = ctx2.counters()
+                assert {k: cnt_g[k] for k in CNT} == {k: cnt_o[k] for k in CNT}
+                gold = os.path.join(GOLD, f"{name}.ek{l_ek}.DES_FULL.gz")
+                if os.path.exists(gold):
+                    assert _run_driver(["-f", "DES_FULL", "-B", "1000", idx, path]) == gzip.open(gold).read()
+        finally:
+            ctx2.close(); ix2.close(); orc.close()
+    finally:
+        if l_ek >= 18:
+            ob.drop_ek_index(l_ek)
+
+
 def test_edge_cases(gpu, ob, oracle):
     dsb, ix, ctx = gpu
     _, demo, _ = ob.read_fastq(ob.DEMO_FQ, 40)
@@ -275,25 +312,86 @@ def test_sample_of_large_batch_against_oracle(gpu, ob, oracle):
     path = ob.sim_set("short1_50k", "short", 50000, 0.01, 20261031)
     names, seqs, _ = ob.read_fastq(path)
     res = ctx.classify(*ob.pack(seqs))
-    idx = list(range(0, len(seqs), 25))
+    idx = list(range(len(seqs)))                                     # every read (a few seconds of the oracle)
     rr_o, hits_o, _ = oracle.classify(*ob.pack([seqs[i] for i in idx]))
     for k, i in enumerate(idx):
         assert res.read_hits(i).tobytes() == hits_o[int(rr_o["hit_off"][k]):int(rr_o["hit_off"][k]) + int(rr_o["n_hit"][k])].tobytes(), i
         assert int(res.rr["n_anchor"][i]) == int(rr_o["n_anchor"][k])
 
 
-def test_capacity_is_reported_not_fatal(gpu, ob):
+def test_capacity_is_reported_not_fatal(gpu, ob, oracle, demo_index, tmp_path):
+    # a read built from 50 simulated reads has > 2500 anchors (test_very_long_reads_many_anchors): with max_anchors = 1024 it
+    # must come back with dsb_read_result.error = 1 and DSB_E_CAPACITY, its neighbours of the batch untouched; the driver
+    # (-A 1024) writes it as unclassified, warns, and finishes the run
     dsb, ix, _ = gpu
-    small = dsb.Context(ix, max_anchors=1024, max_matches=1024)
-    _, seqs, _ = ob.read_fastq(_set_path(ob, "long10"), 300)
-    big = max(seqs, key=len)
+    _, seqs, _ = ob.read_fastq(_set_path(ob, "long10"), 120)
+    reads = [seqs[0], b"".join(seqs[20:70]), seqs[1], seqs[2]]
+    cat, offs = ob.pack(reads)
+    rr_o, hits_o, _ = oracle.classify(cat, offs)
+    assert int(rr_o["n_anchor"][1]) > 2500
+    small = dsb.Context(ix, max_anchors=1024)
     try:
-        res = small.classify(*ob.pack([big * 3]))
-        assert not res.rr["error"].any()
-    except dsb.DsbError as e:
+        with pytest.raises(dsb.DsbError) as ei:
+            small.classify(cat, offs)
+        e = ei.value
         assert e.code == -5 and "capacity" in str(e)
+        res = e.result
+        assert res.rr["error"].tolist() == [0, 1, 0, 0] and int(res.rr["n_hit"][1]) == 0
+        for i in (0, 2, 3):
+            assert res.read_hits(i).tobytes() == hits_o[int(rr_o["hit_off"][i]):int(rr_o["hit_off"][i]) + int(rr_o["n_hit"][i])].tobytes()
     finally:
         small.close()
+    fq = tmp_path / "cap.fq"
+    fq.write_bytes(b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(reads)))
+    r = subprocess.run([DRIVER, "classify", "-A", "1024", "-f", "DES", demo_index, str(fq)], capture_output=True)
+    assert r.returncode == 0 and b"exceeded a per-read capacity" in r.stderr
+    heads = [l.split(b"\t") for l in r.stdout.split(b"\n") if l.startswith(b"r")]
+    assert [h[1] for h in heads] == [b"CLASSIFY" if int(rr_o["n_hit"][i]) and i != 1 else b"UNCLASSIFY" for i in range(4)]
+
+
+def test_pool_overflow_grows_and_reruns(gpu, ob, oracle):
+    # the per-batch device pools (seed tasks, staging chunks, anchors, chains, hits) are sized from the batch; a batch richer than
+    # the sizing assumes must not fail: the pools are doubled and the batch is run again inside the call (dsb_batch_retries)
+    dsb, ix, _ = gpu
+    _, seqs, _ = ob.read_fastq(_set_path(ob, "long10"), 300)
+    cat, offs = ob.pack(seqs)
+    rr_o, hits_o, _ = oracle.classify(cat, offs)
+    tiny = dsb.Context(ix, pool_scale_pct=1)
+    try:
+        res = tiny.classify(cat, offs)
+        assert tiny.retries() >= 1
+        _assert_same(ob, res, rr_o, hits_o)
+        res = tiny.classify(cat, offs)                   # the grown pools are kept
+        assert tiny.retries() == 0
+        _assert_same(ob, res, rr_o, hits_o)
+    finally:
+        tiny.close()
+
+
+def test_driver_two_gpus_small_batches(gpu, ob, demo_index):
+    # -g 2 (index loaded once and copied device to device, batches dealt to 2 x 3 contexts, records merged in input order,
+    # max_read_l carried across GPUs): the mixed set in batches of 97 reads against the unmodified reference's text
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU on this box")
+    for fmt in ("SAM", "DES_FULL"):
+        out = _run_driver(["-g", "2", "-B", "97", "-f", fmt, demo_index, _set_path(ob, "mixed")])
+        assert out == gzip.open(os.path.join(GOLD, f"mixed.{fmt}.gz")).read()
+
+
+def test_index_clone_equals_load(gpu, ob, oracle):
+    # dsb_index_clone (the copy the driver gives to GPUs 1..N-1): same results as the loaded index (here onto the same device)
+    dsb, ix, _ = gpu
+    clone = ix.clone(0)
+    ctx2 = dsb.Context(clone)
+    try:
+        assert clone.l_ek == ix.l_ek and clone.hbm_bytes == ix.hbm_bytes
+        _, seqs, _ = ob.read_fastq(_set_path(ob, "long30"), 60)
+        cat, offs = ob.pack(seqs)
+        rr_o, hits_o, _ = oracle.classify(cat, offs)
+        _assert_same(ob, ctx2.classify(cat, offs), rr_o, hits_o)
+    finally:
+        ctx2.close(); clone.close()
 
 
 def test_gather_microbenchmark(gpu):

@@ -63,6 +63,34 @@ def test_second_index_multi_strain(ob, name, spec):
     assert out == gold and gold.count(b" SEC ") > 1000
 
 
+@pytest.mark.parametrize("l_ek,name", [(17, "syn_long10"), (17, "syn_short1"), (18, "syn_short1")])
+def test_larger_exist_kmer_table_classes(ob, l_ek, name):
+    # l_ek = 17 / 31-bit hash mask and l_ek = 18 / 33-bit mask (set_ekmer_par, idx.c:966-982): the reference picks them for
+    # references of 0.3 / 1.3 Gbp and more; here the small multi-strain index carries tables of that class (oracle/rebuild_exk.c)
+    try:
+        idx = ob.ensure_ek_index(l_ek)
+    except FileNotFoundError as e:
+        pytest.skip(str(e))
+    spec = ("long", 400, 0.10, 20261025) if name == "syn_long10" else ("short", 4000, 0.01, 20261026)
+    path = ob.sim_set(name, *spec, fasta=ob.SYN_FA)
+    out = _orc_cli(ob, ["-f", "DES_FULL", idx, path])
+    gold = gzip.open(os.path.join(GOLD, f"{name}.ek{l_ek}.DES_FULL.gz")).read()
+    assert out == gold
+    assert gold != gzip.open(os.path.join(GOLD, f"{name}.DES_FULL.gz")).read()      # the class changes the result: the path is exercised
+    if l_ek == 18:
+        ob.drop_ek_index(18)                                                        # 2 GiB of shared memory
+
+
+def test_rebuilt_tables_of_the_original_class_are_the_builders(ob, tmp_path):
+    # the table rule of oracle/rebuild_exk.c is the index builder's: for the class the builder chose it reproduces its files
+    idx = ob.ensure_syn_index()
+    exe = os.path.join(ob.ORACLE_DIR, "rebuild_exk")
+    subprocess.run(["gcc", "-O2", "-w", "-o", exe, exe + ".c"], check=True)
+    subprocess.run([exe, idx, str(tmp_path / "c27"), "27"], check=True, capture_output=True)
+    for f in ("deSAMBA.exk0", "deSAMBA.exk1", "deSAMBA.exki"):
+        assert open(tmp_path / "c27" / f, "rb").read() == open(os.path.join(idx, f), "rb").read(), f
+
+
 def test_options_l_s_r(ob, demo_index):
     path = ob.sim_set("long10", *SETS["long10"])
     out = _orc_cli(ob, ["-l", "100", "-s", "40", "-r", "2", demo_index, path])

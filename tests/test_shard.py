@@ -33,7 +33,7 @@ def test_needs_predecessors():
     assert not shard.needs_predecessors(0, True, False)
 
 
-def _worker(rank, world_size, port, q):
+def _worker(rank, world_size, port, q, use_gpu=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size), LOCAL_RANK=str(rank))
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import torch.distributed as dist
@@ -41,11 +41,19 @@ def _worker(rank, world_size, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world_size)
     names, seqs, _ = ob.read_fastq(ob.DEMO_FQ, 60)
     batches = shard.split_batches([len(s) for s in seqs], 8, 10**9)
-    orc = ob.Oracle()
+    if use_gpu:                                   # the real thing: one process per GPU, the index replicated (both ranks share GPU 0 on a 1-GPU box)
+        import torch
+        import desamba_b200 as dsb
+        ix = dsb.Index(ob.ensure_demo_index(), rank % torch.cuda.device_count())
+        eng = dsb.Context(ix)
+        classify = lambda cat, offs: (lambda r: (r.rr, r.hits))(eng.classify(cat, offs, 10**6))
+    else:                                         # CPU box: the oracle stands in for the GPU, the host logic is what is tested
+        orc = ob.Oracle()
+        classify = lambda cat, offs: orc.classify(cat, offs, max_read_l_in=10**6)[:2]
     mine = []
     for b in shard.deal(len(batches), world_size, rank):
         lo, hi = batches[b]
-        rr, hits, _ = orc.classify(*ob.pack(seqs[lo:hi]), max_read_l_in=10**6)       # long-read state: batches are independent
+        rr, hits = classify(*ob.pack(seqs[lo:hi]))                                   # long-read state: batches are independent
         mine.append((b, (rr.tobytes(), hits.tobytes())))
     t = shard.dist_max(float(rank + 1))
     n = shard.dist_sum(float(sum(batches[b][1] - batches[b][0] for b in shard.deal(len(batches), world_size, rank))))
@@ -57,12 +65,21 @@ def _worker(rank, world_size, port, q):
     dist.destroy_process_group()
 
 
+@pytest.mark.gpu
+def test_world_size_2_on_the_gpu(ob, oracle, demo_index):
+    _run_world_size_2(ob, oracle, True)
+
+
 def test_world_size_2_gloo(ob, oracle, demo_index):
+    _run_world_size_2(ob, oracle, False)
+
+
+def _run_world_size_2(ob, oracle, use_gpu):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 1000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + os.getpid() % 1000 + (500 if use_gpu else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, use_gpu)) for r in range(2)]
     for p in procs: p.start()
     t, n, merged = q.get(timeout=300)
     for p in procs: p.join(timeout=60)
@@ -73,5 +90,5 @@ def test_world_size_2_gloo(ob, oracle, demo_index):
     # per-read records of the sharded run, in input order, equal the single-process run
     got_hits = b"".join(h for _, h in merged)
     assert got_hits == hits.tobytes()
-    got_n = np.concatenate([np.frombuffer(r, dtype=ob.RR_DTYPE)["n_hit"] for r, _ in merged])
-    assert got_n.tolist() == rr["n_hit"].tolist()
+    got_rr = np.concatenate([np.frombuffer(r, dtype=ob.RR_DTYPE) for r, _ in merged])
+    assert got_rr["n_hit"].tolist() == rr["n_hit"].tolist() and got_rr["n_anchor"].tolist() == rr["n_anchor"].tolist()
