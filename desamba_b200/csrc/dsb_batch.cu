@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(SEED_WARPS_PER_BLOCK * 32, SEED_WARPS_PER_SM /
 {
 	__shared__ uint32_t s_vis1[SEED_WARPS_PER_BLOCK][VIS1_SLOTS][32];
 	__shared__ uint64_t s_lvs[SEED_WARPS_PER_BLOCK][4][32];
+	if (P.ctl[CTL_OVERFLOW]) return;                      // a pool of an earlier kernel overflowed: the batch is run again with larger pools (dsb_batch_download)
 	seed_warp_loop(P, s_vis1[threadIdx.x >> 5], s_lvs[threadIdx.x >> 5]);
 }
 
@@ -298,6 +299,7 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SCORE_MIN_BLOCK
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	ReadState S;
+	if (A.P.ctl[CTL_OVERFLOW]) return;
 	warp_setup(A, S, smem_raw);
 	for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_chain(A.P, S, r, pass);
 }
@@ -306,6 +308,7 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SCORE_MIN_BLOCK
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	ReadState S;
+	if (A.P.ctl[CTL_OVERFLOW]) return;
 	warp_setup(A, S, smem_raw);
 	S.mt = (MatchSmem *)(smem_raw + CLASSIFY_WARPS_PER_BLOCK * sizeof(WarpSmem)) + (threadIdx.x >> 5);
 	// the list is in no particular order: reads with many anchors or many bases (the expensive ones) are scored first
@@ -324,6 +327,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) k_score_heavy(const __grid_co
 	__shared__ __align__(16) MatchSmem msm;
 	__shared__ DpTeam team;
 	const int warp = threadIdx.x >> 5;
+	if (A.P.ctl[CTL_OVERFLOW]) return;                    // (uniform over the CTA)
 	if (warp == 0) {
 		ReadState S;
 		scratch_setup(A, S, slot0 + blockIdx.x);             // scratch slots of their own
@@ -341,6 +345,7 @@ struct FinalizeParams {
 	int filter_min_length, filter_min_score, filter_min_score_LV3;
 	dsb_read_result *rr; dsb_hit *hits;
 	const unsigned long long *counters;
+	const uint32_t *ctl;
 };
 
 struct HitCmpByMEMScore {           // chain_cmp_by_MEM_score (cly.c:54-64): asymmetric on ties, as written
@@ -358,7 +363,7 @@ struct HitCmpByMEMScore {           // chain_cmp_by_MEM_score (cly.c:54-64): asy
 __global__ void __launch_bounds__(128) k_finalize(const __grid_constant__ FinalizeParams P)
 {
 	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-	if (r >= P.n_reads) return;
+	if (r >= P.n_reads || P.ctl[CTL_OVERFLOW]) return;
 	dsb_read_result rr = P.rr[r];
 	uint32_t n = rr.n_hit;
 	if (n == 0) return;
@@ -608,7 +613,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 	// dsb_batch_download doubles that pool and runs the batch again (grow[] keeps the factor for the batches that follow).
 	const uint64_t sc = c->opts.pool_scale_pct ? c->opts.pool_scale_pct : 100;
 	auto pool = [&](uint64_t base, int k) { return std::min<uint64_t>(((base * sc / 100) << c->grow[k]) + 1024, 0xfffffff0ull); };
-	const uint64_t task_cap = pool(c->n_bases / 32 + 4ull * n, 0), n_chunks = pool(c->n_bases / 32 + 8ull * n, 1);
+	const uint64_t task_cap = pool(c->n_bases / 32 + 4ull * n, 0), n_chunks = pool(c->n_bases / 16 + 16ull * n, 1);
 	const uint64_t anc_cap = pool(c->n_bases / 8 + 64ull * n + (1u << 16), 2), chain_cap = pool(c->n_bases / 32 + 16ull * n + (1u << 14), 3);
 	// hits: the pre-filter chains of a read use 2 slots each (second half = merge-sort scratch)
 	const uint64_t hits_cap = pool(std::max<uint64_t>(4096, (uint64_t)n * 24), 4);
@@ -707,7 +712,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		FinalizeParams P;
 		P.n_reads = n; P.max_read_l_in = max_read_l_in;
 		P.filter_min_length = c->opts.l_min_match; P.filter_min_score = c->opts.min_score; P.filter_min_score_LV3 = c->opts.min_score + 10;   // cly_mt.c:521-523
-		P.rr = (dsb_read_result *)c->rr.p; P.hits = (dsb_hit *)c->hits.p; P.counters = cnt;
+		P.rr = (dsb_read_result *)c->rr.p; P.hits = (dsb_hit *)c->hits.p; P.counters = cnt; P.ctl = (const uint32_t *)c->ctl.p;
 		k_finalize<<<(n + 127) / 128, 128, 0, st>>>(P);
 		c->launches++;
 	}
@@ -725,7 +730,7 @@ extern "C" int dsb_batch_sync(dsb_ctx *c)
 	return DSB_OK;
 }
 
-#define DSB_MAX_RETRIES 6
+#define DSB_MAX_RETRIES 8
 extern "C" int dsb_batch_download(dsb_ctx *c, int32_t *max_read_l_out, dsb_read_result *rr, dsb_hit *hits, uint64_t hits_cap, uint64_t *n_hits_out)
 {
 	if (!c || !c->ran) { dsb_set_error("dsb_batch_download: no batch has been run"); return DSB_E_ARG; }
@@ -749,6 +754,11 @@ extern "C" int dsb_batch_download(dsb_ctx *c, int32_t *max_read_l_out, dsb_read_
 		c->retries++;
 		int rc = dsb_batch_run(c, c->max_read_l_in);
 		if (rc != DSB_OK) return rc;
+	}
+	{
+		uint32_t ovf = 0;
+		DSB_CUDA(cudaMemcpy(&ovf, (uint32_t *)c->ctl.p + CTL_OVERFLOW, 4, cudaMemcpyDeviceToHost));
+		if (ovf) { dsb_set_error("device pools still too small after %d doublings (overflow mask 0x%x): split the batch", c->retries, ovf); return DSB_E_NOMEM; }
 	}
 	if (rr) DSB_CUDA(cudaMemcpyAsync(rr, c->rr.p, (size_t)c->n_reads * sizeof(dsb_read_result), cudaMemcpyDeviceToHost, st));
 	DSB_CUDA(cudaStreamSynchronize(st));

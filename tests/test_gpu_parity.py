@@ -356,7 +356,7 @@ def test_pool_overflow_grows_and_reruns(gpu, ob, oracle):
     _, seqs, _ = ob.read_fastq(_set_path(ob, "long10"), 300)
     cat, offs = ob.pack(seqs)
     rr_o, hits_o, _ = oracle.classify(cat, offs)
-    tiny = dsb.Context(ix, pool_scale_pct=1)
+    tiny = dsb.Context(ix, pool_scale_pct=3)
     try:
         res = tiny.classify(cat, offs)
         assert tiny.retries() >= 1
