@@ -8,7 +8,7 @@
  *   one thread/GPU  dsb_classify_batch on its own context; batches are dealt in input order
  *   writer (main)   formats the result records of each batch in input order (output_results, cly_mt.c:350-365)
  * The index is replicated per GPU, reads are sharded by batch, nothing is exchanged between GPUs.
- * Extra options: -g INT GPUs to use [all visible], -c INT contexts (batches in flight) per GPU [3], -B INT reads per batch
+ * Extra options: -g INT GPUs to use [all visible], -c INT contexts (batches in flight) per GPU [up to 6, as HBM allows], -B INT reads per batch
  * [262144], -M INT Mbases per batch [512], -P INT helper threads of the FASTQ reader [8 on >= 16 cores; 0 = serial reader],
  * -A / -m INT per-read anchor / match capacity, -L INT longest read accepted, -p INT pool sizing in % (dsb_opts).
  * -t is accepted and ignored (the thread pool it sized no longer exists).
@@ -107,7 +107,7 @@ static void fail(shared_t *sh, const char *what, int rc)
 /* The batch buffers are ordinary (huge-page) memory by default: cudaHostAlloc costs ~1 s per GB on an 8-GPU box (19 allocations
  * = 6.9 s for a 4 GB input, more than reading, classifying and writing it), and the H2D copy of a batch from pageable memory
  * was not slower in the driver (3 contexts per GPU overlap it).  DSB_PINNED=1 pins them (long multi-GPU runs). */
-static double g_t_pinned = 0; static int g_n_pinned = 0; static int g_pageable = 1;
+static double g_t_pinned = 0; static int g_n_pinned = 0; static int g_pageable = 1, g_register = 0;
 static int grow_pinned(void **p, size_t *m, size_t need, size_t keep, size_t full)
 {
 	if (need <= *m) return 0;
@@ -116,9 +116,12 @@ static int grow_pinned(void **p, size_t *m, size_t need, size_t keep, size_t ful
 	while (need > nm) nm *= 2;
 	if ((nm > full || nm >= ((size_t)128 << 20)) && need <= full) nm = full;       /* a batch of long reads will fill up: no more copies */
 	void *np = NULL;
-	if (g_pageable) { if (posix_memalign(&np, (size_t)2 << 20, nm)) return -1; madvise(np, nm, MADV_HUGEPAGE); }
-	else if (dsb_host_alloc(nm, &np) != DSB_OK) return -1;
-	if (*p) { memcpy(np, *p, keep); if (g_pageable) free(*p); else dsb_host_free(*p); }
+	if (g_pageable) {
+		if (posix_memalign(&np, (size_t)2 << 20, nm)) return -1;
+		madvise(np, nm, MADV_HUGEPAGE);
+		if (g_register && nm >= ((size_t)8 << 20) && dsb_host_register(np, nm) != DSB_OK) g_register = 0;   /* DSB_REGISTER=1: page-lock the huge pages */
+	} else if (dsb_host_alloc(nm, &np) != DSB_OK) return -1;
+	if (*p) { memcpy(np, *p, keep); if (g_pageable) { if (g_register) dsb_host_unregister(*p); free(*p); } else dsb_host_free(*p); }
 	*p = np; *m = nm;
 	g_t_pinned += now_s() - t0; g_n_pinned++;
 	return 0;
@@ -456,7 +459,7 @@ static double cpu_s(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); return 
 
 static int classify_main(int argc, char **argv)
 {
-	opts_t o = {170, 4, 5, FMT_SAM, 64, 0, 3, 262144, 512ull << 20, stdout, -1, 0, 0, 0, 0};
+	opts_t o = {170, 4, 5, FMT_SAM, 64, 0, 0, 262144, 512ull << 20, stdout, -1, 0, 0, 0, 0};
 	int c;
 	while ((c = getopt(argc, argv, "ht:l:r:f:o:s:g:B:M:c:P:A:m:L:p:")) >= 0) {
 		if (c == 'h') { usage(); return 0; }
@@ -485,12 +488,14 @@ static int classify_main(int argc, char **argv)
 	const char *index_dir = argv[optind++];
 	if (o.n_gpus <= 0) { const char *e = getenv("DSB_GPUS"); o.n_gpus = e ? atoi(e) : 0; }
 	fprintf(stderr, "loading index\t");
-	if (o.ctx_per_gpu < 1) o.ctx_per_gpu = 1;
+	const int auto_ctx = o.ctx_per_gpu < 1;                 /* as many as HBM allows, up to 6 (decided once the index is resident) */
+	if (auto_ctx) o.ctx_per_gpu = 6;
 	if (o.ctx_per_gpu > 8) o.ctx_per_gpu = 8;
-	if (o.n_parse_threads < 0) { long nc = sysconf(_SC_NPROCESSORS_ONLN); o.n_parse_threads = nc >= 16 ? 8 : nc >= 8 ? 4 : nc >= 4 ? 2 : 1; }
+	if (o.n_parse_threads < 0) { long nc = sysconf(_SC_NPROCESSORS_ONLN); o.n_parse_threads = nc >= 16 ? (nc - 4 > 24 ? 24 : (int)nc - 4) : nc >= 8 ? 4 : nc >= 4 ? 2 : 1; }
 	if (o.n_parse_threads > 64) o.n_parse_threads = 64;
 	const int verbose = getenv("DSB_VERBOSE") != NULL;
 	g_pageable = getenv("DSB_PINNED") == NULL;
+	g_register = getenv("DSB_REGISTER") != NULL;
 	const double t_start = now_s();
 	#define STAMP(what) do { if (verbose) fprintf(stderr, "[deSAMBA-b200] %-34s at %7.3f s\n", what, now_s() - t_start); } while (0)
 	/* the reader starts at once: the first batches are parsed into pinned memory while the index is loaded into HBM */
@@ -518,19 +523,35 @@ static int classify_main(int argc, char **argv)
 		gix[g] = ix; n_gpus++;
 	}
 	STAMP("index resident in HBM");
-	/* several contexts (streams) per GPU: the expensive tail reads of one batch overlap the next batch */
-	const int n_workers = n_gpus * o.ctx_per_gpu;
-	worker_t *w = xcalloc(n_workers, sizeof *w);
+	/* several contexts (streams) per GPU: the expensive tail reads of one batch overlap the next batch.  Every device buffer of a
+	 * context is allocated at its final size now (no cudaMalloc while batches are in flight); without -c, contexts are added
+	 * while a quarter of the HBM stays free for the pools that may still grow */
 	dsb_opts dop; dsb_opts_default(&dop);
 	dop.l_min_match = o.l_min_match; dop.min_score = o.min_score;
 	if (o.max_anchors) dop.max_anchors = o.max_anchors;
 	if (o.max_matches) dop.max_matches = o.max_matches;
 	if (o.max_read_len) dop.max_read_len = o.max_read_len;
 	if (o.pool_scale_pct) dop.pool_scale_pct = o.pool_scale_pct;
-	for (int k = 0; k < n_workers; k++) {
-		w[k].gpu = k % n_gpus; w[k].ix = gix[k % n_gpus];
-		if (dsb_ctx_create(w[k].ix, &dop, &w[k].ctx) != DSB_OK) BAIL("\n[deSAMBA-b200] %s\n", dsb_last_error());
+	worker_t *w = xcalloc((size_t)n_gpus * o.ctx_per_gpu, sizeof *w);
+	int n_workers = 0, ctx_made = 0;
+	for (int k = 0; k < o.ctx_per_gpu; k++) {               /* round k: one more context on every GPU */
+		int ok = 1;
+		for (int g = 0; g < n_gpus && ok; g++) {
+			uint64_t fr = 0, tot = 0;
+			if (auto_ctx && k >= 2 && dsb_device_memory(g, &fr, &tot) == DSB_OK && fr < tot / 4) { ok = 0; break; }
+			worker_t *x = &w[n_workers];
+			x->gpu = g; x->ix = gix[g];
+			if (dsb_ctx_create(x->ix, &dop, &x->ctx) != DSB_OK) BAIL("\n[deSAMBA-b200] %s\n", dsb_last_error());
+			if (!getenv("DSB_NO_RESERVE") && dsb_ctx_reserve(x->ctx, o.batch_reads, o.batch_bases + ((uint64_t)4 << 20)) != DSB_OK) {
+				if (k == 0) BAIL("\n[deSAMBA-b200] %s\n", dsb_last_error());
+				dsb_ctx_free(x->ctx); x->ctx = NULL; ok = 0; break;   /* HBM is full: the contexts made so far do the work */
+			}
+			n_workers++;
+		}
+		if (!ok) { while (n_workers > (k) * n_gpus) { n_workers--; dsb_ctx_free(w[n_workers].ctx); } break; }
+		ctx_made = k + 1;
 	}
+	o.ctx_per_gpu = ctx_made;
 	STAMP("contexts created");
 	const dsb_ref_info *ri = dsb_index_ref_info(w[0].ix);
 	const double t0 = now_s(), c0 = cpu_s();

@@ -453,7 +453,7 @@ extern "C" int dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out)
 	if (c->opts.max_matches < 1024) c->opts.max_matches = 1024;
 	if (c->opts.warps_per_sm < CLASSIFY_WARPS_PER_BLOCK) c->opts.warps_per_sm = CLASSIFY_WARPS_PER_BLOCK;
 	if (c->opts.warps_per_sm > 32) c->opts.warps_per_sm = 32;
-	c->stream = nullptr; c->h_pin = nullptr; c->h_pin_cap = 0; c->ran = false; c->launches = 0;
+	c->stream = nullptr; c->h_pin = nullptr; c->h_pin_cap = 0; c->ran = false; c->launches = 0; c->h_stage = nullptr; c->ev_stage[0] = c->ev_stage[1] = nullptr;
 	c->n_reads = 0; c->m_bin_read = 0; c->scratch_stride = 0; c->hits_cap = 0; c->task_cap = 0; c->n_chunks = 0; c->max_read_l_in = 0; c->retries = 0;
 	for (int k = 0; k < 5; k++) c->grow[k] = 0;
 	cudaDeviceProp prop;
@@ -481,6 +481,7 @@ extern "C" void dsb_ctx_free(dsb_ctx *c)
 	                  &c->task_first[0], &c->task_first[1], &c->task_cnt[0], &c->task_cnt[1]};
 	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
 	if (c->h_pin) cudaFreeHost(c->h_pin);
+	if (c->h_stage) { cudaFreeHost(c->h_stage); for (int k = 0; k < 2; k++) if (c->ev_stage[k]) cudaEventDestroy(c->ev_stage[k]); }
 	for (int i = 0; i < DSB_N_EV; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -498,6 +499,106 @@ extern "C" int dsb_host_alloc(size_t bytes, void **out)
 	return DSB_OK;
 }
 extern "C" void dsb_host_free(void *p) { if (p) cudaFreeHost(p); }
+// page-lock memory the caller allocated itself (huge pages: far fewer pages to pin than cudaHostAlloc's 4 KB pages)
+extern "C" int dsb_host_register(void *p, size_t bytes)
+{
+	if (!p || !bytes) return DSB_E_ARG;
+	DSB_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+	return DSB_OK;
+}
+extern "C" void dsb_host_unregister(void *p) { if (p) cudaHostUnregister(p); }
+extern "C" int dsb_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes)
+{
+	DSB_CUDA(cudaSetDevice(device));
+	size_t f = 0, t = 0;
+	DSB_CUDA(cudaMemGetInfo(&f, &t));
+	if (free_bytes) *free_bytes = f;
+	if (total_bytes) *total_bytes = t;
+	return DSB_OK;
+}
+
+// device buffers of the upload step for a batch of n_reads reads / n_bases bases (grow-only)
+static int reserve_upload(dsb_ctx *c, uint64_t n_reads, uint64_t n_bases, uint64_t n_tiles, uint64_t bo, uint64_t wo, uint64_t so)
+{
+	const size_t tbl_bytes = (size_t)(n_reads + 1) * 8;
+	int rc;
+	if ((rc = ensure(c->seqs, n_bases + 16)) || (rc = ensure(c->read_off, tbl_bytes)) || (rc = ensure(c->bin_off, tbl_bytes)) ||
+	    (rc = ensure(c->bits_off, tbl_bytes)) || (rc = ensure(c->seed_off, (size_t)(n_reads + 1) * 4)) || (rc = ensure(c->tiles, n_tiles * 8 + 8)) ||
+	    (rc = ensure(c->bin, bo + 64)) || (rc = ensure(c->bits, wo * 4 + 64)) ||
+	    (rc = ensure(c->seeds[0], so * sizeof(dsb_seed) + 64)) || (rc = ensure(c->seeds[1], so * sizeof(dsb_seed) + 64)) ||
+	    (rc = ensure(c->n_seeds[0], (size_t)n_reads * 4)) || (rc = ensure(c->n_seeds[1], (size_t)n_reads * 4)) ||
+	    (rc = ensure(c->total_score[0], (size_t)n_reads * 4)) || (rc = ensure(c->total_score[1], (size_t)n_reads * 4)) ||
+	    (rc = ensure(c->rr, (size_t)n_reads * sizeof(dsb_read_result))) || (rc = ensure(c->order, (size_t)n_reads * 4)) || (rc = ensure(c->hdr7, (size_t)n_reads + 16)))
+		return rc;
+	return DSB_OK;
+}
+static int ensure_zeroed(DevBuf &b, size_t bytes, cudaStream_t st);
+static ScratchLayout scratch_layout(uint32_t max_anchors, uint32_t max_matches);
+// device buffers of the run step: scratch of the warp-per-read kernels, pools between the phase kernels, seeding memory
+static int reserve_run(dsb_ctx *c, uint64_t n, uint64_t n_bases, uint64_t bits_words)
+{
+	cudaStream_t st = c->stream;
+	const ScratchLayout L = scratch_layout(c->opts.max_anchors, c->opts.max_matches);
+	c->scratch_stride = L.total;
+	int rc;
+	if ((rc = ensure(c->scratch, (size_t)L.total * (c->n_warps + HEAVY_BLOCKS))) != DSB_OK) return rc;
+	// Pools between the phase kernels, sized from the batch; a kernel that runs out of one sets its bit in ctl[CTL_OVERFLOW] and
+	// dsb_batch_download doubles that pool and runs the batch again (grow[] keeps the factor for the batches that follow).
+	const uint64_t sc = c->opts.pool_scale_pct ? c->opts.pool_scale_pct : 100;
+	auto pool = [&](uint64_t base, int k) { return std::min<uint64_t>(((base * sc / 100) << c->grow[k]) + 1024, 0xfffffff0ull); };
+	const uint64_t task_cap = pool(n_bases / 32 + 4ull * n, 0), n_chunks = pool(n_bases / 16 + 16ull * n, 1);
+	const uint64_t anc_cap = pool(n_bases / 8 + 64ull * n + (1u << 16), 2), chain_cap = pool(n_bases / 32 + 16ull * n + (1u << 14), 3);
+	// hits: the pre-filter chains of a read use 2 slots each (second half = merge-sort scratch)
+	const uint64_t hits_cap = pool(std::max<uint64_t>(4096, (uint64_t)n * 24), 4);
+	if ((rc = ensure(c->hits, hits_cap * sizeof(dsb_hit))) != DSB_OK) return rc;
+	if ((rc = ensure(c->prof, (size_t)n * 32)) != DSB_OK) return rc;
+	if ((rc = ensure(c->work, (size_t)n * sizeof(ReadWork))) || (rc = ensure(c->anc_pool, anc_cap * sizeof(DevAnchor))) ||
+	    (rc = ensure(c->chain_pool, chain_cap * sizeof(DevChain))) || (rc = ensure(c->ctl, CTL_WORDS * 4)))
+		return rc;
+	for (int l = 0; l < N_LISTS; l++) if ((rc = ensure(c->lists[l], (size_t)n * 4)) != DSB_OK) return rc;
+	// seeding: packed strands, task lists, per-task records, staging chunks, per-lane memory of the persistent k_seed grid
+	const uint64_t seed_lanes = (uint64_t)c->seed_blocks * SEED_WARPS_PER_BLOCK * 32;
+	const bool big_rows = c->ix->dev.n_lines * 128 >= (1ull << 32);
+	if ((rc = ensure(c->pk, (bits_words / N_BITVEC + 4) * 8)) || (rc = ensure(c->tasks[0], task_cap * sizeof(SeedTaskRef))) ||
+	    (rc = ensure(c->tasks[1], task_cap * sizeof(SeedTaskRef))) || (rc = ensure(c->recs, task_cap * sizeof(SeedRec))) ||
+	    (rc = ensure(c->chunks, n_chunks * 64)) || (rc = ensure(c->lane_mem, seed_lanes * SEED_MEM_SLOTS * sizeof(MemRst))) ||
+	    (rc = ensure_zeroed(c->vis2, seed_lanes * VIS2_SLOTS * 8, st)) || (rc = ensure_zeroed(c->vis_gen, seed_lanes * 4, st)) ||
+	    (rc = ensure(c->vis1_full, big_rows ? seed_lanes * VIS1_SLOTS * 8 : 64)))
+		return rc;
+	for (int s = 0; s < 2; s++) if ((rc = ensure(c->task_first[s], (size_t)n * 4)) || (rc = ensure(c->task_cnt[s], (size_t)n * 4))) return rc;
+	c->task_cap = (uint32_t)(std::min<uint64_t>(c->tasks[0].cap, c->tasks[1].cap) / sizeof(SeedTaskRef));
+	c->task_cap = (uint32_t)std::min<uint64_t>(c->task_cap, c->recs.cap / sizeof(SeedRec));
+	c->n_chunks = (uint32_t)std::min<uint64_t>(c->chunks.cap / 64, 0xfffffff0u);
+	c->hits_cap = c->hits.cap / sizeof(dsb_hit);
+	return DSB_OK;
+}
+
+// All device buffers of a context for batches of up to max_reads reads and max_bases bases, allocated now (the driver calls this
+// before its timed interval: no cudaMalloc while batches are in flight); also sizes the pinned staging of the offset tables.
+extern "C" int dsb_ctx_reserve(dsb_ctx *c, uint32_t max_reads, uint64_t max_bases)
+{
+	if (!c || max_reads == 0) { dsb_set_error("dsb_ctx_reserve: bad argument"); return DSB_E_ARG; }
+	DSB_CUDA(cudaSetDevice(c->ix->device));
+	const uint64_t n = max_reads, nb = max_bases;
+	const uint64_t n_tiles = nb / PROBE_TILE + n, bo = 2 * nb + (2 * DSB_GUARD + 16) * n, wo = (uint64_t)N_BITVEC * (nb / 32 + 2 * n), so = nb / 2 + 2 * n;
+	if (so >= 0xffffffffull) { dsb_set_error("dsb_ctx_reserve: batch limit too large (seed slots overflow 32 bits)"); return DSB_E_ARG; }
+	int rc;
+	if ((rc = reserve_upload(c, n, nb, n_tiles, bo, wo, so)) != DSB_OK) return rc;
+	if ((rc = reserve_run(c, n, nb, wo)) != DSB_OK) return rc;
+	const size_t pin_need = (size_t)(n + 1) * 8 * 4 + n_tiles * 8 + n + 64;
+	if (pin_need > c->h_pin_cap) {
+		if (c->h_pin) cudaFreeHost(c->h_pin);
+		c->h_pin = nullptr; c->h_pin_cap = 0;
+		DSB_CUDA(cudaHostAlloc(&c->h_pin, pin_need, cudaHostAllocDefault));
+		c->h_pin_cap = pin_need;
+	}
+	if (!c->h_stage) {
+		DSB_CUDA(cudaHostAlloc(&c->h_stage, 2 * (size_t)DSB_STAGE_BYTES, cudaHostAllocDefault));
+		for (int k = 0; k < 2; k++) DSB_CUDA(cudaEventCreateWithFlags(&c->ev_stage[k], cudaEventDisableTiming));
+	}
+	DSB_CUDA(cudaStreamSynchronize(c->stream));
+	return DSB_OK;
+}
 
 extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *offs, uint32_t n_reads)
 {
@@ -566,16 +667,31 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 	c->h_seed_off.assign(h_seed_off, h_seed_off + n_reads + 1);
 	c->h_off.assign(offs, offs + n_reads + 1);
 	int rc;
-	if ((rc = ensure(c->seqs, n_bases + 16)) || (rc = ensure(c->read_off, tbl_bytes)) || (rc = ensure(c->bin_off, tbl_bytes)) ||
-	    (rc = ensure(c->bits_off, tbl_bytes)) || (rc = ensure(c->seed_off, (size_t)(n_reads + 1) * 4)) || (rc = ensure(c->tiles, n_tiles * 8 + 8)) ||
-	    (rc = ensure(c->bin, bo + 64)) || (rc = ensure(c->bits, wo * 4 + 64)) ||
-	    (rc = ensure(c->seeds[0], so * sizeof(dsb_seed) + 64)) || (rc = ensure(c->seeds[1], so * sizeof(dsb_seed) + 64)) ||
-	    (rc = ensure(c->n_seeds[0], (size_t)n_reads * 4)) || (rc = ensure(c->n_seeds[1], (size_t)n_reads * 4)) ||
-	    (rc = ensure(c->total_score[0], (size_t)n_reads * 4)) || (rc = ensure(c->total_score[1], (size_t)n_reads * 4)) ||
-	    (rc = ensure(c->rr, (size_t)n_reads * sizeof(dsb_read_result))) || (rc = ensure(c->order, (size_t)n_reads * 4)) || (rc = ensure(c->hdr7, (size_t)n_reads + 16)))
-		return rc;
+	if ((rc = reserve_upload(c, n_reads, n_bases, n_tiles, bo, wo, so)) != DSB_OK) return rc;
 	cudaStream_t st = c->stream;
-	DSB_CUDA(cudaMemcpyAsync(c->seqs.p, seqs, n_bases, cudaMemcpyHostToDevice, st));
+	{	// the reads: straight from the caller's buffer when it is page-locked, else through the context's pinned staging ring (the
+		// runtime's own path for pageable memory serialises the copies of all contexts of a process)
+		cudaPointerAttributes pa;
+		const bool pinned = cudaPointerGetAttributes(&pa, seqs) == cudaSuccess && (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged);
+		(void)cudaGetLastError();
+		if (pinned || n_bases < (1u << 20)) DSB_CUDA(cudaMemcpyAsync(c->seqs.p, seqs, n_bases, cudaMemcpyHostToDevice, st));
+		else {
+			if (!c->h_stage) {
+				DSB_CUDA(cudaHostAlloc(&c->h_stage, 2 * (size_t)DSB_STAGE_BYTES, cudaHostAllocDefault));
+				for (int k = 0; k < 2; k++) DSB_CUDA(cudaEventCreateWithFlags(&c->ev_stage[k], cudaEventDisableTiming));
+			}
+			uint64_t off = 0;
+			for (int k = 0; off < n_bases; k ^= 1) {
+				const size_t nb = (size_t)std::min<uint64_t>(DSB_STAGE_BYTES, n_bases - off);
+				char *stg = (char *)c->h_stage + (size_t)k * DSB_STAGE_BYTES;
+				DSB_CUDA(cudaEventSynchronize(c->ev_stage[k]));            // the copy that last used this half has landed
+				memcpy(stg, seqs + off, nb);
+				DSB_CUDA(cudaMemcpyAsync((char *)c->seqs.p + off, stg, nb, cudaMemcpyHostToDevice, st));
+				DSB_CUDA(cudaEventRecord(c->ev_stage[k], st));
+				off += nb;
+			}
+		}
+	}
 	DSB_CUDA(cudaMemcpyAsync(c->read_off.p, offs, tbl_bytes, cudaMemcpyHostToDevice, st));
 	DSB_CUDA(cudaMemcpyAsync(c->bin_off.p, h_bin_off, tbl_bytes, cudaMemcpyHostToDevice, st));
 	DSB_CUDA(cudaMemcpyAsync(c->bits_off.p, h_bits_off, tbl_bytes, cudaMemcpyHostToDevice, st));
@@ -606,39 +722,11 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 	const uint32_t n = c->n_reads;
 	if (n == 0) { c->ran = true; return DSB_OK; }
 	const ScratchLayout L = scratch_layout(c->opts.max_anchors, c->opts.max_matches);
-	c->scratch_stride = L.total;
 	int rc;
-	if ((rc = ensure(c->scratch, (size_t)L.total * (c->n_warps + HEAVY_BLOCKS))) != DSB_OK) return rc;
-	// Pools between the phase kernels, sized from the batch; a kernel that runs out of one sets its bit in ctl[CTL_OVERFLOW] and
-	// dsb_batch_download doubles that pool and runs the batch again (grow[] keeps the factor for the batches that follow).
-	const uint64_t sc = c->opts.pool_scale_pct ? c->opts.pool_scale_pct : 100;
-	auto pool = [&](uint64_t base, int k) { return std::min<uint64_t>(((base * sc / 100) << c->grow[k]) + 1024, 0xfffffff0ull); };
-	const uint64_t task_cap = pool(c->n_bases / 32 + 4ull * n, 0), n_chunks = pool(c->n_bases / 16 + 16ull * n, 1);
-	const uint64_t anc_cap = pool(c->n_bases / 8 + 64ull * n + (1u << 16), 2), chain_cap = pool(c->n_bases / 32 + 16ull * n + (1u << 14), 3);
-	// hits: the pre-filter chains of a read use 2 slots each (second half = merge-sort scratch)
-	const uint64_t hits_cap = pool(std::max<uint64_t>(4096, (uint64_t)n * 24), 4);
-	if ((rc = ensure(c->hits, hits_cap * sizeof(dsb_hit))) != DSB_OK) return rc;
-	if ((rc = ensure(c->prof, (size_t)n * 32)) != DSB_OK) return rc;
-	if ((rc = ensure(c->work, (size_t)n * sizeof(ReadWork))) || (rc = ensure(c->anc_pool, anc_cap * sizeof(DevAnchor))) ||
-	    (rc = ensure(c->chain_pool, chain_cap * sizeof(DevChain))) || (rc = ensure(c->ctl, CTL_WORDS * 4)))
-		return rc;
-	for (int l = 0; l < N_LISTS; l++) if ((rc = ensure(c->lists[l], (size_t)n * 4)) != DSB_OK) return rc;
-	// seeding: packed strands, task lists, per-task records, staging chunks, per-lane memory of the persistent k_seed grid
-	const uint64_t seed_lanes = (uint64_t)c->seed_blocks * SEED_WARPS_PER_BLOCK * 32;
+	if ((rc = reserve_run(c, n, c->n_bases, c->bits_words)) != DSB_OK) return rc;
 	const bool big_rows = c->ix->dev.n_lines * 128 >= (1ull << 32);
-	if ((rc = ensure(c->pk, (c->bits_words / N_BITVEC + 4) * 8)) || (rc = ensure(c->tasks[0], task_cap * sizeof(SeedTaskRef))) ||
-	    (rc = ensure(c->tasks[1], task_cap * sizeof(SeedTaskRef))) || (rc = ensure(c->recs, task_cap * sizeof(SeedRec))) ||
-	    (rc = ensure(c->chunks, n_chunks * 64)) || (rc = ensure(c->lane_mem, seed_lanes * SEED_MEM_SLOTS * sizeof(MemRst))) ||
-	    (rc = ensure_zeroed(c->vis2, seed_lanes * VIS2_SLOTS * 8, st)) || (rc = ensure_zeroed(c->vis_gen, seed_lanes * 4, st)) ||
-	    (rc = ensure(c->vis1_full, big_rows ? seed_lanes * VIS1_SLOTS * 8 : 64)))
-		return rc;
-	for (int s = 0; s < 2; s++) if ((rc = ensure(c->task_first[s], (size_t)n * 4)) || (rc = ensure(c->task_cnt[s], (size_t)n * 4))) return rc;
-	c->task_cap = (uint32_t)(std::min<uint64_t>(c->tasks[0].cap, c->tasks[1].cap) / sizeof(SeedTaskRef));
-	c->task_cap = (uint32_t)std::min<uint64_t>(c->task_cap, c->recs.cap / sizeof(SeedRec));
-	c->n_chunks = (uint32_t)std::min<uint64_t>(c->chunks.cap / 64, 0xfffffff0u);
 	DSB_CUDA(cudaMemsetAsync(c->ctl.p, 0, CTL_WORDS * 4, st));
 	DSB_CUDA(cudaMemsetAsync(c->prof.p, 0, (size_t)n * 32, st));
-	c->hits_cap = c->hits.cap / sizeof(dsb_hit);
 	unsigned long long *cnt = (unsigned long long *)c->counters.p;
 	DSB_CUDA(cudaMemsetAsync(cnt, 0, DSB_CNT_COUNT * 8, st));
 	DSB_CUDA(cudaMemsetAsync(cnt + DSB_CNT_FIRST_LONG, 0xff, 8, st));

@@ -27,6 +27,7 @@ struct DevBuf {                         // grow-only device buffer
 	DevBuf() : p(nullptr), cap(0) {}
 };
 
+#define DSB_STAGE_BYTES (16u << 20)
 #define DSB_N_KERNELS 11               // timed kernel groups of one dsb_batch_run
 #define DSB_N_EV (DSB_N_KERNELS + 3)   // kernel boundaries + 2 user marks
 
@@ -48,8 +49,9 @@ struct dsb_ctx {
 	int retries;                        // re-runs of the last batch
 	uint64_t scratch_stride;
 	uint64_t hits_cap;
-	// pinned staging
+	// pinned staging: per-read tables of the upload; ring of two chunks for reads that arrive in pageable memory
 	void *h_pin; size_t h_pin_cap;
+	void *h_stage; cudaEvent_t ev_stage[2];
 	// batch state
 	uint32_t m_bin_read;                // capacity of the reference's bin_read buffer after the batches seen so far (policy P3)
 	uint32_t n_reads, n_tiles; uint64_t n_bases, bits_words, seed_slots, bin_bytes; uint32_t max_len;

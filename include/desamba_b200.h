@@ -93,6 +93,9 @@ int  dsb_index_l_ek(const dsb_index *ix);
 void dsb_opts_default(dsb_opts *o);
 int  dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out);
 void dsb_ctx_free(dsb_ctx *ctx);
+/* allocate every device buffer of the context now for batches of up to max_reads reads / max_bases bases (they grow on demand
+ * otherwise -- a cudaMalloc in the middle of a run stalls every stream of the GPU) */
+int  dsb_ctx_reserve(dsb_ctx *ctx, uint32_t max_reads, uint64_t max_bases);
 
 /*
  * One batch = the reads of one kt_for call (cly_mt.c:389).  seqs: concatenated read bases (ASCII, no separators),
@@ -150,6 +153,11 @@ int dsb_batch_profile(dsb_ctx *ctx, uint32_t *out);
 /* pinned host memory for the caller's batch buffers (the driver batches reads into these; cly_mt.c:42-56 equivalent) */
 int  dsb_host_alloc(size_t bytes, void **out);
 void dsb_host_free(void *p);
+/* page-lock / release memory the caller allocated itself (e.g. huge-page batch buffers of the driver) */
+int  dsb_host_register(void *p, size_t bytes);
+void dsb_host_unregister(void *p);
+/* free / total HBM of a device in bytes */
+int  dsb_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes);
 
 /* HBM random-gather microbenchmark (roofline denominator): n_gathers random reads of `bytes_each`
  * (1..128, power of two) from a table of table_bytes; returns sector-granular GB/s in *gbs and elapsed ms. */
