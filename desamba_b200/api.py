@@ -63,6 +63,7 @@ _sig("dsb_ctx_mark", C.c_int, _vp, C.c_int)
 _sig("dsb_ctx_elapsed_ms", C.c_int, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_float))
 _sig("dsb_batch_launches", C.c_int, _vp)
 _sig("dsb_batch_retries", C.c_int, _vp)
+_sig("dsb_batch_work", C.c_int, _vp, C.POINTER(C.c_uint32 * 12))
 _sig("dsb_index_clone", C.c_int, _vp, C.c_int, C.POINTER(_vp))
 _sig("dsb_batch_counters", C.c_int, _vp, C.POINTER(C.c_uint64 * 16))
 _sig("dsb_batch_profile", C.c_int, _vp, _vp)
@@ -199,6 +200,13 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def work(self):
+        """work-list sizes of the last run (dsb_batch_work)"""
+        out = (C.c_uint32 * 12)()
+        _check(lib.dsb_batch_work(self._h, C.byref(out)), "dsb_batch_work")
+        names = ["slow0_reads", "slow1_reads", "scored", "scored_heavy", "tasks_fast", "tasks_slow0", "tasks_slow1", "chunks_fast", "chunks_slow0", "chunks_slow1", "anchors", "chains"]
+        return dict(zip(names, list(out)))
 
     def retries(self):
         """re-runs of the last batch after a pool overflow (dsb_batch_retries)"""

@@ -461,6 +461,8 @@ extern "C" int dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out)
 	c->n_sm = prop.multiProcessorCount;
 	c->n_warps = c->n_sm * (int)(c->opts.warps_per_sm / CLASSIFY_WARPS_PER_BLOCK) * CLASSIFY_WARPS_PER_BLOCK;
 	c->seed_blocks = c->n_sm * (SEED_WARPS_PER_SM / SEED_WARPS_PER_BLOCK);
+	c->heavy_blocks = HEAVY_BLOCKS;
+	if (const char *e = getenv("DSB_HEAVY_BLOCKS")) { const int v = atoi(e); if (v >= 1 && v <= 1024) c->heavy_blocks = v; }   // developer knob
 	DSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (int i = 0; i < DSB_N_EV; i++) DSB_CUDA(cudaEventCreate(&c->ev[i]));
 	int rc = ensure(c->counters, DSB_CNT_COUNT * 8);
@@ -541,7 +543,7 @@ static int reserve_run(dsb_ctx *c, uint64_t n, uint64_t n_bases, uint64_t bits_w
 	const ScratchLayout L = scratch_layout(c->opts.max_anchors, c->opts.max_matches);
 	c->scratch_stride = L.total;
 	int rc;
-	if ((rc = ensure(c->scratch, (size_t)L.total * (c->n_warps + HEAVY_BLOCKS))) != DSB_OK) return rc;
+	if ((rc = ensure(c->scratch, (size_t)L.total * (c->n_warps + c->heavy_blocks))) != DSB_OK) return rc;
 	// Pools between the phase kernels, sized from the batch; a kernel that runs out of one sets its bit in ctl[CTL_OVERFLOW] and
 	// dsb_batch_download doubles that pool and runs the batch again (grow[] keeps the factor for the batches that follow).
 	const uint64_t sc = c->opts.pool_scale_pct ? c->opts.pool_scale_pct : 100;
@@ -792,7 +794,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 		// scoring: a warp per read; the few reads that give up there (ERR_DEFER) then get a CTA each
 		k_score<<<blocks, threads, smem + CLASSIFY_WARPS_PER_BLOCK * sizeof(MatchSmem), st>>>(A, LIST_SCORE, 6);
 		DSB_CUDA(cudaEventRecord(c->ev[9], st));
-		k_score_heavy<<<HEAVY_BLOCKS, TEAM_WARPS * 32, 0, st>>>(A, LIST_SCORE_HEAVY, 7, (uint32_t)c->n_warps);
+		k_score_heavy<<<c->heavy_blocks, TEAM_WARPS * 32, 0, st>>>(A, LIST_SCORE_HEAVY, 7, (uint32_t)c->n_warps);
 		DSB_CUDA(cudaEventRecord(c->ev[10], st));
 		c->launches += 8;
 	}
@@ -930,6 +932,21 @@ extern "C" int dsb_batch_profile(dsb_ctx *c, uint32_t *out)
 }
 
 extern "C" int dsb_batch_launches(dsb_ctx *c) { return c ? c->launches : 0; }
+
+// work-list sizes of the last run: [0] slow pass 0, [1] slow pass 1, [2] scored (warp), [3] scored again (CTA per read), [4..6] seed
+// tasks of the fast / slow 0 / slow 1 pass, [7..9] staging chunks of the passes, [10] anchors, [11] chains kept
+extern "C" int dsb_batch_work(dsb_ctx *c, uint32_t out[12])
+{
+	if (!c || !c->ran || !out) return DSB_E_ARG;
+	DSB_CUDA(cudaSetDevice(c->ix->device));
+	DSB_CUDA(cudaStreamSynchronize(c->stream));
+	uint32_t h[CTL_WORDS];
+	DSB_CUDA(cudaMemcpy(h, c->ctl.p, sizeof h, cudaMemcpyDeviceToHost));
+	for (int i = 0; i < 4; i++) out[i] = h[CTL_LIST_N + i];
+	for (int i = 0; i < 3; i++) { out[4 + i] = h[CTL_TASK_N + i]; out[7 + i] = h[CTL_CHUNK_CURSOR + i]; }
+	out[10] = h[CTL_ANC_CURSOR]; out[11] = h[CTL_CHAIN_CURSOR];
+	return DSB_OK;
+}
 
 extern "C" int dsb_batch_counters(dsb_ctx *c, uint64_t out[16])
 {

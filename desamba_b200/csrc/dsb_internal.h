@@ -37,6 +37,7 @@ struct dsb_ctx {
 	cudaStream_t stream;
 	int n_sm, n_warps;                  // resident classify warps = n_sm * warps_per_sm
 	int seed_blocks;                    // grid of k_seed (persistent, SEED_WARPS_PER_SM warps per SM)
+	int heavy_blocks;                   // CTAs of k_score_heavy
 	// batch inputs (device)
 	DevBuf seqs, read_off, bin_off, bits_off, seed_off, tiles, bin, bits, seeds[2], n_seeds[2], total_score[2];
 	// classify scratch + outputs

@@ -135,6 +135,10 @@ int dsb_batch_kernel_ms(dsb_ctx *ctx, float *ms, int cap);
  * context's stream; dsb_ctx_elapsed_ms waits for b's mark and returns b.mark_b - a.mark_a in ms */
 int dsb_ctx_mark(dsb_ctx *ctx, int which);
 int dsb_ctx_elapsed_ms(dsb_ctx *a, int mark_a, dsb_ctx *b, int mark_b, float *ms);
+/* work-list sizes of the last run: [0] reads in slow pass 0, [1] in slow pass 1, [2] scored (warp per read), [3] scored again by a CTA
+ * each (repeat-rich), [4..6] seed tasks of the fast / slow 0 / slow 1 pass, [7..9] staging chunks of the passes, [10] anchors,
+ * [11] chains handed to scoring */
+int dsb_batch_work(dsb_ctx *ctx, uint32_t out[12]);
 /* number of kernel launches issued by the last dsb_batch_run */
 int dsb_batch_launches(dsb_ctx *ctx);
 /* CUDA stream handle (cudaStream_t) the context launches on */

@@ -46,7 +46,10 @@ def _worker(rank, world_size, port, q, use_gpu=False):
         import desamba_b200 as dsb
         ix = dsb.Index(ob.ensure_demo_index(), rank % torch.cuda.device_count())
         eng = dsb.Context(ix)
-        classify = lambda cat, offs: (lambda r: (r.rr, r.hits))(eng.classify(cat, offs, 10**6))
+        def classify(cat, offs):
+            r = eng.classify(cat, offs, 10**6)                  # the hit array of the library has merge-sort scratch between the reads: compact it
+            hits = np.concatenate([r.read_hits(i) for i in range(len(r.rr))]) if len(r.rr) else r.hits[:0]
+            return r.rr, hits
     else:                                         # CPU box: the oracle stands in for the GPU, the host logic is what is tested
         orc = ob.Oracle()
         classify = lambda cat, offs: orc.classify(cat, offs, max_read_l_in=10**6)[:2]
