@@ -865,7 +865,7 @@ __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8
 				if (!(total_ref_len < 2000)) { S.error = 3; return 0; }         // xassert(total_ref_len < 2000) aborts the reference (cly.c:2473)
 				refwin_zero(S, 2128);
 				const uint64_t ref_offset = pre_refoffset + t_offset + pre_mch;
-				CNT_GETREF(S, total_ref_len); get_ref_coop(ix, S.sm->refwin, ref_offset, total_ref_len, true);
+				CNT_GETREF(S, total_ref_len); get_ref_coop(ix, S.sm->refwin, ref_offset, total_ref_len);
 				sdp_match(S, pa.index_in_read + pre_mch - 8, ca.index_in_read - 1, q_str, S.sm->refwin, total_ref_len, pre_refoffset + pre_mch, true);
 				if (S.error) return 0;
 				if (!S.team && S.n_sms > DEFER_SMS) { S.error = ERR_DEFER; return 0; }
@@ -922,7 +922,7 @@ __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, int
 				max_search_ref = (uint32_t)(t_length - c_t_offset);
 			max_search_ref = DSB_MIN(600, max_search_ref);
 			__syncwarp();
-			CNT_GETREF(S, max_search_ref + OVER_SEARCH_M2); get_ref_coop(ix, S.sm->refwin, c_t_offset + t_offset_global, max_search_ref + OVER_SEARCH_M2, true);
+			CNT_GETREF(S, max_search_ref + OVER_SEARCH_M2); get_ref_coop(ix, S.sm->refwin, c_t_offset + t_offset_global, max_search_ref + OVER_SEARCH_M2);
 			int search_q_ed = (int)sms[max_sms_id].q_pos + 1000;
 			search_q_ed = DSB_MIN(search_q_ed, l_read);
 			const int search_q_st = DSB_MAX(search_q_ed - 2000, ch.q_st - 8);
@@ -1009,9 +1009,9 @@ __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, int 
 			max_search_ref = DSB_MIN(600, max_search_ref);
 			__syncwarp();
 			if (t_offset_global == 0 && c_t_offset < OVER_SEARCH_M2 + max_search_ref)
-				{ CNT_GETREF(S, max_search_ref); get_ref_coop(ix, S.sm->refwin, (int64_t)(c_t_offset + t_offset_global - max_search_ref), max_search_ref, true); }
+				{ CNT_GETREF(S, max_search_ref); get_ref_coop(ix, S.sm->refwin, (int64_t)(c_t_offset + t_offset_global - max_search_ref), max_search_ref); }
 			else
-				{ CNT_GETREF(S, max_search_ref + OVER_SEARCH_M2); get_ref_coop(ix, S.sm->refwin, (int64_t)(c_t_offset + t_offset_global - max_search_ref - OVER_SEARCH_M2), max_search_ref + OVER_SEARCH_M2, true); }
+				{ CNT_GETREF(S, max_search_ref + OVER_SEARCH_M2); get_ref_coop(ix, S.sm->refwin, (int64_t)(c_t_offset + t_offset_global - max_search_ref - OVER_SEARCH_M2), max_search_ref + OVER_SEARCH_M2); }
 			int search_q_st = (int)sms[max_sms_id].q_pos - 1000;
 			search_q_st = DSB_MAX(search_q_st, 0);
 			const int search_q_ed = DSB_MIN(search_q_st + 2000, ch.q_st - 1);
