@@ -47,35 +47,16 @@ __device__ __forceinline__ uint64_t dsb_hash64_2(uint64_t key)
 }
 
 // get_ref (cly.c:435-466), forward: unpack `length` bases of the packed reference from position `off` into out[0 .. length)
-// (one byte per base; out is 16-byte aligned shared memory).  Cooperative: a lane takes 16 bases at a time -- two aligned words
-// of the packed reference, a funnel shift, four byte-spreads, one 16-byte store.  Bytes behind `length` are never written:
-// the window keeps what it held there (zero-initialised, then earlier loads of the same call: oracle policy P1).
-static __device__ __noinline__ void get_ref_coop(const DevIndex &ix, uint8_t *out, int64_t off, int32_t length)
+// (one byte per base).  Cooperative: lane k writes out[k], out[k+32], ...; bytes behind `length` are never written: the window
+// keeps what it held there (zero-initialised, then earlier loads of the same call: oracle policy P1).
+// (A variant that unpacked 16 bases per lane from two aligned words executed 5x fewer instructions and made k_score 10 % SLOWER,
+// twice: the byte loop's 64 independent loads per lane are all in flight at once; profiles/README.md.)
+__device__ __forceinline__ void get_ref_coop(const DevIndex &ix, uint8_t *out, int64_t off, int32_t length)
 {
 	if (off < 0) off = 0;
 	if (length < 0) length = 0;
 	const uint64_t o = (uint64_t)off;
-	const uint32_t n = (uint32_t)length;
-	for (uint32_t g = lane_id(); 16 * g < n; g += 32) {
-		const uint64_t p = o + 16ull * g;
-		const uint64_t wa = (p >> 4) << 2;                             // byte address of the aligned word that holds base p
-		const uint32_t left = n - 16 * g;
-		if (wa + 8 <= ix.ref_bin_n + 1024) {
-			const uint32_t *wp = (const uint32_t *)(ix.ref_bin + wa);
-			const uint32_t w0 = __byte_perm(__ldg(wp), 0, 0x0123), w1 = __byte_perm(__ldg(wp + 1), 0, 0x0123);   // first base of a word in its top bits
-			const uint32_t v = __funnelshift_l(w1, w0, 2 * (uint32_t)(p & 15));
-			uint32_t q[4];
-			#pragma unroll
-			for (int k = 0; k < 4; k++) {
-				const uint32_t x = (v >> (24 - 8 * k)) & 0xff;              // 4 bases, first in bits 7-6
-				const uint32_t y = (x >> 4) | ((x & 0xf) << 16);
-				q[k] = ((y >> 2) & 0x00030003u) | ((y << 8) & 0x03000300u);  // one byte per base, first base in the low byte
-			}
-			if (left >= 16) *(uint4 *)(out + 16 * g) = make_uint4(q[0], q[1], q[2], q[3]);
-			else for (uint32_t k = 0; k < left; k++) out[16 * g + k] = (uint8_t)(q[k >> 2] >> (8 * (k & 3)));
-		} else
-			for (uint32_t k = 0; k < 16 && k < left; k++) out[16 * g + k] = (uint8_t)ref_base_at(ix, p + k);
-	}
+	for (uint32_t k = lane_id(); k < (uint32_t)length; k += 32) out[k] = (uint8_t)ref_base_at(ix, o + k);
 	__syncwarp();
 }
 
