@@ -202,8 +202,12 @@ static int slot_add_block(shared_t *sh, slot_t *b, const char *map, const fq_rec
 	return 0;
 }
 
-#define FQ_BLOCK ((uint64_t)256 << 20)     /* bytes of a plain FASTQ file indexed at a time */
+static uint64_t g_fq_block = (uint64_t)256 << 20;   /* bytes of a plain FASTQ file indexed at a time (DSB_FQ_BLOCK_MB: tests use small blocks) */
+#define FQ_BLOCK g_fq_block
 #define FQ_MARGIN ((uint64_t)16 << 20)     /* read beyond the block: the records that start in it must be complete */
+/* the next block of the file is read into the other buffer while the records of the current one are copied into batches */
+typedef struct { int fd, n_thr, rc, active; uint64_t pos, len; char *buf; pthread_t th; } prefetch_t;
+static void *prefetch_main(void *a) { prefetch_t *p = (prefetch_t *)a; p->rc = fq_read_block(p->fd, p->pos, p->len, p->buf, p->n_thr); return NULL; }
 static void *reader_main(void *arg)
 {
 	shared_t *sh = (shared_t *)arg; opts_t *o = sh->o;
@@ -214,7 +218,8 @@ static void *reader_main(void *arg)
 	long plen = 0;
 	/* plain 4-line FASTQ: read and indexed a block at a time by the helper threads (fastq_reader.h) */
 	const char *map = NULL; uint64_t map_size = 0, map_pos = 0;           /* map = blockbuf - (offset of the block): file offsets index it */
-	char *blockbuf = NULL;
+	char *blockbuf = NULL, *blockbuf2[2] = {NULL, NULL}; int cur_buf = 0;
+	prefetch_t pf; memset(&pf, 0, sizeof pf);
 	fq_list_t lists[64]; memset(lists, 0, sizeof lists);
 	fq_rec_t *recs = NULL; size_t m_recs = 0, n_recs = 0, i_rec = 0;
 	const int n_thr = o->n_parse_threads;
@@ -244,11 +249,24 @@ static void *reader_main(void *arg)
 					uint64_t next = map_pos;
 					const uint64_t len = (map_size - map_pos < FQ_BLOCK + FQ_MARGIN) ? map_size - map_pos : FQ_BLOCK + FQ_MARGIN;
 					long n = -1;
-					if (fq_read_block(st.fd, map_pos, len, blockbuf, n_thr) == 0) {
+					int have = 0;
+					if (pf.active) {                    /* the block may have been read ahead */
+						pthread_join(pf.th, NULL); pf.active = 0;
+						if (pf.rc == 0 && pf.pos == map_pos && pf.len == len && pf.fd == st.fd) { cur_buf ^= 1; blockbuf = blockbuf2[cur_buf]; have = 1; }
+					}
+					if (have || fq_read_block(st.fd, map_pos, len, blockbuf, n_thr) == 0) {
 						map = blockbuf - map_pos;
 						n = fq_index_block(map, map_pos + len, map_pos + len == map_size, map_pos, map_pos + FQ_BLOCK, n_thr, lists, &recs, &m_recs, &next);
 					}
-					if (n >= 0) { n_recs = (size_t)n; i_rec = 0; map_pos = next; continue; }
+					if (n >= 0) {
+						n_recs = (size_t)n; i_rec = 0; map_pos = next;
+						if (next < map_size && blockbuf2[cur_buf ^ 1]) {   /* read ahead while this block's records go into batches */
+							pf.fd = st.fd; pf.n_thr = n_thr; pf.pos = next; pf.buf = blockbuf2[cur_buf ^ 1];
+							pf.len = (map_size - next < FQ_BLOCK + FQ_MARGIN) ? map_size - next : FQ_BLOCK + FQ_MARGIN;
+							if (pthread_create(&pf.th, NULL, prefetch_main, &pf) == 0) pf.active = 1;
+						}
+						continue;
+					}
 					/* not strict 4-line FASTQ from here on: the serial reader takes over at the start of the block */
 					map = NULL;
 					lseek(st.fd, (off_t)map_pos, SEEK_SET);
@@ -257,6 +275,7 @@ static void *reader_main(void *arg)
 					continue;
 				}
 				map = NULL; n_recs = i_rec = 0;
+				if (pf.active) { pthread_join(pf.th, NULL); pf.active = 0; }
 				close(st.fd); stream_open = 0; file_i++;
 				continue;
 			}
@@ -281,7 +300,8 @@ static void *reader_main(void *arg)
 					pthread_mutex_unlock(&sh->mu);
 					struct stat sb;
 					if (!st.fp && n_thr > 0 && got >= 1 && magic[0] == '@' && fstat(st.fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
-						if (!blockbuf) blockbuf = malloc(FQ_BLOCK + FQ_MARGIN + 16);
+						if (!blockbuf2[0]) { blockbuf2[0] = malloc(((uint64_t)256 << 20) + FQ_MARGIN + 16); blockbuf2[1] = malloc(((uint64_t)256 << 20) + FQ_MARGIN + 16); cur_buf = 0; }
+						blockbuf = blockbuf2[cur_buf];
 						if (blockbuf) {
 							map = blockbuf; map_size = (uint64_t)sb.st_size; map_pos = 0; n_recs = i_rec = 0;
 							continue;
@@ -310,7 +330,8 @@ static void *reader_main(void *arg)
 		pthread_mutex_unlock(&sh->mu);
 		if (end_of_input) break;
 	}
-	free(blockbuf);
+	if (pf.active) pthread_join(pf.th, NULL);
+	free(blockbuf2[0]); free(blockbuf2[1]);
 	for (int t = 0; t < 64; t++) free(lists[t].r);
 	free(recs);
 	free(st.buf); free(rec.name); free(rec.seq); free(rec.qual);
@@ -496,6 +517,7 @@ static int classify_main(int argc, char **argv)
 	const int verbose = getenv("DSB_VERBOSE") != NULL;
 	g_pageable = getenv("DSB_PINNED") == NULL;
 	g_register = getenv("DSB_REGISTER") != NULL;
+	if (getenv("DSB_FQ_BLOCK_MB") && atol(getenv("DSB_FQ_BLOCK_MB")) >= 1 && atol(getenv("DSB_FQ_BLOCK_MB")) <= 256) g_fq_block = (uint64_t)atol(getenv("DSB_FQ_BLOCK_MB")) << 20;
 	const double t_start = now_s();
 	#define STAMP(what) do { if (verbose) fprintf(stderr, "[deSAMBA-b200] %-34s at %7.3f s\n", what, now_s() - t_start); } while (0)
 	/* the reader starts at once: the first batches are parsed into pinned memory while the index is loaded into HBM */

@@ -99,6 +99,18 @@ def test_driver_reader_modes(gpu, ob, demo_index, tmp_path, extra):
         assert _run_driver(["-P", "4", demo_index, str(wrapped)]) == want
 
 
+def test_driver_reader_blocks_and_read_ahead(gpu, ob, demo_index):
+    # the parallel FASTQ reader works on blocks of the file (256 MB; 1 MB here) and reads the next block ahead while the records
+    # of the current one go into batches: same text as with the serial reader
+    path = _set_path(ob, "mixed")
+    want = _run_driver(["-f", "DES_FULL", "-P", "0", demo_index, path, path])          # the serial reader on the same two files
+    assert want.startswith(gzip.open(os.path.join(GOLD, "mixed.DES_FULL.gz")).read())
+    for extra in (["-P", "4"], ["-P", "7", "-B", "333"]):
+        r = subprocess.run([DRIVER, "classify", "-f", "DES_FULL"] + extra + [demo_index, path, path], capture_output=True, env=dict(os.environ, DSB_FQ_BLOCK_MB="1"))
+        assert r.returncode == 0, r.stderr.decode()[-1000:]
+        assert r.stdout == want
+
+
 def test_driver_options_and_gz_input(gpu, ob, demo_index, tmp_path):
     path = _set_path(ob, "long10")
     gz = tmp_path / "long10.fq.gz"
