@@ -512,7 +512,7 @@ static int classify_main(int argc, char **argv)
 	const int auto_ctx = o.ctx_per_gpu < 1;                 /* as many as HBM allows, up to 6 (decided once the index is resident) */
 	if (auto_ctx) o.ctx_per_gpu = 6;
 	if (o.ctx_per_gpu > 8) o.ctx_per_gpu = 8;
-	if (o.n_parse_threads < 0) { long nc = sysconf(_SC_NPROCESSORS_ONLN); o.n_parse_threads = nc >= 16 ? (nc - 4 > 24 ? 24 : (int)nc - 4) : nc >= 8 ? 4 : nc >= 4 ? 2 : 1; }
+	if (o.n_parse_threads < 0) { long nc = sysconf(_SC_NPROCESSORS_ONLN); o.n_parse_threads = nc >= 16 ? (nc - 4 > 48 ? 48 : (int)nc - 4) : nc >= 8 ? 4 : nc >= 4 ? 2 : 1; }
 	if (o.n_parse_threads > 64) o.n_parse_threads = 64;
 	const int verbose = getenv("DSB_VERBOSE") != NULL;
 	g_pageable = getenv("DSB_PINNED") == NULL;

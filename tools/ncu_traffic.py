@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """profiles/traffic.json from one ncu --set full capture of ALL launches of one bench step:
 dram__bytes_read.sum + dram__bytes_write.sum and gpu__time_duration.sum per kernel name, summed over the launches of that
-kernel in the step (k_seed = fast + redo + slow 0 + slow 1, k_chain = 3 launches).  usage: ncu_traffic.py x.ncu-rep out.json reads_per_step"""
+kernel in the step (k_seed = fast + slow 0 + slow 1, k_chain = 3 launches).  usage: ncu_traffic.py x.ncu-rep out.json reads_per_step [config key of bench.py: workload|index|reads]"""
 import csv, io, json, subprocess, sys
 
 rep, out, rps = sys.argv[1], sys.argv[2], int(sys.argv[3])
@@ -34,5 +34,6 @@ for r in rows[2:]:
 res["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum and gpu__time_duration.sum per kernel, summed over the launches of one bench step "
                 f"(ncu --set full --clock-control none, {rep.split('/')[-1]}), bench.py default workload")
 res["_reads_per_step"] = rps
+res["config"] = sys.argv[4] if len(sys.argv) > 4 else f"long|viral-gs|{rps}"
 json.dump(res, open(out, "w"), indent=1)
 print(json.dumps(res, indent=1))
