@@ -26,7 +26,9 @@ python tools/ncu_traffic.py $O/step_full.ncu-rep $O/traffic.json 65536 "long|vir
 python tools/ncu_kernels.py $O/step_full.ncu-rep $O/kernels_summary.txt > /dev/null 2>&1
 python -c "
 import json; t=json.load(open('$O/traffic.json')); print('DRAM per step:', '  '.join('%s %.2f GB (%.1f ms)' % (k, v['dram_bytes']/1e9, v['ncu_duration_ms']) for k, v in t.items() if isinstance(v, dict)))"
-for K in k_seed k_score k_chain k_encode_probe k_islands; do
+rm -f $O/step_full.ncu-rep                       # (55 MB; gpurun brings back at most 64 MiB: the summaries above are what is kept)
+for K in k_seed k_score k_chain; do
 	tools/gpu_ncu.sh $TAG/one $K 0 16384 > /dev/null 2>&1
+	[ $K = k_seed ] || rm -f $O/one_$K.ncu-rep
 done
-ls $O | head -40
+du -sh $O; ls $O | head -40
