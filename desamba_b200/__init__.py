@@ -6,5 +6,5 @@ ctypes binding over that ABI for the test-suite and ``bench.py``; it contains no
 ``desamba_b200.api`` fails loudly when the library has not been built.
 """
 from .api import (  # noqa: F401
-    Index, Context, BatchResult, DsbError, lib, lib_path, HIT_DTYPE, RR_DTYPE, SEED_DTYPE, KERNEL_NAMES, gather_bench,
+    Index, Context, BatchResult, DsbError, lib, lib_path, HIT_DTYPE, RR_DTYPE, SEED_DTYPE, KERNEL_NAMES, gather_bench, set_sync_mode,
 )

@@ -63,6 +63,9 @@ _sig("dsb_ctx_mark", C.c_int, _vp, C.c_int)
 _sig("dsb_ctx_elapsed_ms", C.c_int, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_float))
 _sig("dsb_batch_launches", C.c_int, _vp)
 _sig("dsb_batch_retries", C.c_int, _vp)
+_sig("dsb_batch_timeline", C.c_int, _vp, C.c_int, _vp, C.POINTER(C.c_float * 13), C.c_int)
+_sig("dsb_ctx_host_seconds", C.c_int, _vp, C.POINTER(C.c_double * 5), C.c_int)
+_sig("dsb_set_sync_mode", C.c_int, C.c_int)
 _sig("dsb_batch_work", C.c_int, _vp, C.POINTER(C.c_uint32 * 12))
 _sig("dsb_index_clone", C.c_int, _vp, C.c_int, C.POINTER(_vp))
 _sig("dsb_batch_counters", C.c_int, _vp, C.POINTER(C.c_uint64 * 16))
@@ -212,6 +215,18 @@ class Context:
         """re-runs of the last batch after a pool overflow (dsb_batch_retries)"""
         return int(lib.dsb_batch_retries(self._h))
 
+    def timeline(self, ref, ref_mark=0):
+        """ms from `ref`'s mark to: upload start, first kernel start, end of each of the 11 kernel groups (dsb_batch_timeline)"""
+        a = (C.c_float * 13)()
+        _check(lib.dsb_batch_timeline(ref._h, ref_mark, self._h, C.byref(a), 13), "dsb_batch_timeline")
+        return list(a)
+
+    def host_seconds(self):
+        """host seconds `classify` spent on this context so far (dsb_ctx_host_seconds): upload, launches, waiting + results; calls; re-runs"""
+        a = (C.c_double * 5)()
+        _check(lib.dsb_ctx_host_seconds(self._h, C.byref(a), 5), "dsb_ctx_host_seconds")
+        return dict(zip(("upload", "run", "download", "calls", "retries"), list(a)))
+
     # -- the end-to-end call with host buffers
     def classify(self, cat, offs, max_read_l_in=0, m_bin_read_in=0):
         """one batch; both cross-read states of the reference are given explicitly (0, 0 = first batch of a run)"""
@@ -322,6 +337,11 @@ class Context:
 
     def stream(self):
         return lib.dsb_ctx_stream(self._h)
+
+
+def set_sync_mode(blocking):
+    """host threads sleep (True) or let the CUDA runtime decide (False) while they wait for a batch; before the first Index"""
+    _check(lib.dsb_set_sync_mode(1 if blocking else 0), "dsb_set_sync_mode")
 
 
 def gather_bench(device=0, table_bytes=8 << 30, n_gathers=1 << 28, bytes_each=1):

@@ -72,7 +72,8 @@ typedef struct {
 	int n_files; char **files;
 	uint64_t total_sequences;
 	double t_reader_wait, t_reader_work, t_worker_call, t_worker_wait, t_writer_wait, t_writer_fmt;   /* DSB_VERBOSE: where the host time goes */
-	int max_ahead;                          /* batches the reader may be ahead of the writer (small until the GPUs are ready) */
+	double t_rd_read, t_rd_index, t_rd_copy;   /* parts of t_reader_work: block input (not hidden by the read-ahead), indexing, copies into the batch */
+	int max_ahead;                          /* batches the reader may be ahead of the writer */
 	int started; char early_msg[4096];      /* "Processing file" lines of the time before "Start classify" */
 } shared_t;
 
@@ -107,7 +108,7 @@ static void fail(shared_t *sh, const char *what, int rc)
 /* The batch buffers are ordinary (huge-page) memory by default: cudaHostAlloc costs ~1 s per GB on an 8-GPU box (19 allocations
  * = 6.9 s for a 4 GB input, more than reading, classifying and writing it), and the H2D copy of a batch from pageable memory
  * was not slower in the driver (3 contexts per GPU overlap it).  DSB_PINNED=1 pins them (long multi-GPU runs). */
-static double g_t_pinned = 0; static int g_n_pinned = 0; static int g_pageable = 1, g_register = 0;
+static double g_t_pinned = 0; static int g_n_pinned = 0; static int g_pageable = 1, g_register = 0, g_host_only = 0;
 static int grow_pinned(void **p, size_t *m, size_t need, size_t keep, size_t full)
 {
 	if (need <= *m) return 0;
@@ -205,9 +206,26 @@ static int slot_add_block(shared_t *sh, slot_t *b, const char *map, const fq_rec
 static uint64_t g_fq_block = (uint64_t)256 << 20;   /* bytes of a plain FASTQ file indexed at a time (DSB_FQ_BLOCK_MB: tests use small blocks) */
 #define FQ_BLOCK g_fq_block
 #define FQ_MARGIN ((uint64_t)16 << 20)     /* read beyond the block: the records that start in it must be complete */
-/* the next block of the file is read into the other buffer while the records of the current one are copied into batches */
-typedef struct { int fd, n_thr, rc, active; uint64_t pos, len; char *buf; pthread_t th; } prefetch_t;
-static void *prefetch_main(void *a) { prefetch_t *p = (prefetch_t *)a; p->rc = fq_read_block(p->fd, p->pos, p->len, p->buf, p->n_thr); return NULL; }
+/* Block input.  Default: pread by the helper threads into one of two reusable buffers, the next block by a read-ahead thread
+ * while the records of the current one are copied into batches.  DSB_FQ_MMAP=1 maps the block instead (MAP_POPULATE, one call
+ * for the whole block: no copy into a buffer of our own) -- measured no faster on tmpfs (host-only pipeline 1.91 s against
+ * 1.76 s for 32 GB of FASTQ), kept as an option for inputs in the page cache of a real file system. */
+static int g_fq_mmap = 0;
+typedef struct { const char *map; void *mbase; size_t mlen; int rc; } block_t;     /* map[file offset] for the offsets of the block */
+typedef struct { int fd, n_thr, active; uint64_t pos, len; char *buf; block_t blk; pthread_t th; } prefetch_t;
+static void block_get(int fd, uint64_t pos, uint64_t len, char *buf, int n_thr, block_t *o)
+{
+	o->map = NULL; o->mbase = NULL; o->mlen = 0; o->rc = -1;
+	if (g_fq_mmap) {
+		const uint64_t moff = pos & ~(uint64_t)4095;
+		const size_t mlen = (size_t)(pos + len - moff);
+		void *m = mmap(NULL, mlen, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, (off_t)moff);
+		if (m != MAP_FAILED) { o->mbase = m; o->mlen = mlen; o->map = (const char *)m - moff; o->rc = 0; return; }
+	}
+	if (buf && fq_read_block(fd, pos, len, buf, n_thr) == 0) { o->map = buf - pos; o->rc = 0; }
+}
+static void block_release(block_t *b) { if (b->mbase) munmap(b->mbase, b->mlen); b->mbase = NULL; b->map = NULL; b->mlen = 0; }
+static void *prefetch_main(void *a) { prefetch_t *p = (prefetch_t *)a; block_get(p->fd, p->pos, p->len, p->buf, p->n_thr, &p->blk); return NULL; }
 static void *reader_main(void *arg)
 {
 	shared_t *sh = (shared_t *)arg; opts_t *o = sh->o;
@@ -218,7 +236,9 @@ static void *reader_main(void *arg)
 	long plen = 0;
 	/* plain 4-line FASTQ: read and indexed a block at a time by the helper threads (fastq_reader.h) */
 	const char *map = NULL; uint64_t map_size = 0, map_pos = 0;           /* map = blockbuf - (offset of the block): file offsets index it */
-	char *blockbuf = NULL, *blockbuf2[2] = {NULL, NULL}; int cur_buf = 0;
+	char *blockbuf2[2] = {NULL, NULL}; int cur_buf = 0;      /* pread mode: two reusable buffers */
+	block_t cur; memset(&cur, 0, sizeof cur);
+	int par_file = 0;                                         /* the open file goes through the parallel indexer */
 	prefetch_t pf; memset(&pf, 0, sizeof pf);
 	fq_list_t lists[64]; memset(lists, 0, sizeof lists);
 	fq_rec_t *recs = NULL; size_t m_recs = 0, n_recs = 0, i_rec = 0;
@@ -236,46 +256,54 @@ static void *reader_main(void *arg)
 		b->n_reads = 0; b->n_bases = 0; b->n_names = 0; b->has_long = b->has_short = 0; b->m_bin_read_in = m_bin_read;
 		int end_of_input = 0;
 		while (b->n_reads < o->batch_reads && b->n_bases < o->batch_bases) {
-			if (map) {
+			if (par_file) {
 				if (i_rec < n_recs) {                   /* as many indexed records as the batch takes */
 					size_t e = i_rec; uint32_t nr = b->n_reads; uint64_t nb = b->n_bases;
 					while (e < n_recs && nr < o->batch_reads && nb < o->batch_bases) { nb += recs[e].n_seq; nr++; e++; }
+					const double tc0 = now_s();
 					if (slot_add_block(sh, b, map, recs, i_rec, e, n_thr)) { fail(sh, "pinned alloc", -4); end_of_input = 1; break; }
+					sh->t_rd_copy += now_s() - tc0;
 					for (size_t i = i_rec; i < e; i++) { const size_t L = recs[i].n_seq; if (L >= 40 && 2 * L > m_bin_read) m_bin_read = (uint32_t)(2 * L + 20); }
 					i_rec = e;
 					continue;
 				}
+				block_release(&cur); map = NULL;
 				if (map_pos < map_size) {               /* next block */
 					uint64_t next = map_pos;
 					const uint64_t len = (map_size - map_pos < FQ_BLOCK + FQ_MARGIN) ? map_size - map_pos : FQ_BLOCK + FQ_MARGIN;
 					long n = -1;
-					int have = 0;
+					const double tr0 = now_s(); double tr1 = tr0;
 					if (pf.active) {                    /* the block may have been read ahead */
 						pthread_join(pf.th, NULL); pf.active = 0;
-						if (pf.rc == 0 && pf.pos == map_pos && pf.len == len && pf.fd == st.fd) { cur_buf ^= 1; blockbuf = blockbuf2[cur_buf]; have = 1; }
+						if (pf.blk.rc == 0 && pf.pos == map_pos && pf.len == len && pf.fd == st.fd) { cur = pf.blk; if (!cur.mbase) cur_buf ^= 1; }
+						else block_release(&pf.blk);
+						memset(&pf.blk, 0, sizeof pf.blk);
 					}
-					if (have || fq_read_block(st.fd, map_pos, len, blockbuf, n_thr) == 0) {
-						map = blockbuf - map_pos;
+					if (!cur.map) block_get(st.fd, map_pos, len, blockbuf2[cur_buf], n_thr, &cur);
+					if (cur.map) {
+						map = cur.map; tr1 = now_s();
 						n = fq_index_block(map, map_pos + len, map_pos + len == map_size, map_pos, map_pos + FQ_BLOCK, n_thr, lists, &recs, &m_recs, &next);
 					}
+					sh->t_rd_read += tr1 - tr0; sh->t_rd_index += now_s() - tr1;
 					if (n >= 0) {
 						n_recs = (size_t)n; i_rec = 0; map_pos = next;
-						if (next < map_size && blockbuf2[cur_buf ^ 1]) {   /* read ahead while this block's records go into batches */
+						if (next < map_size) {             /* read ahead while this block's records go into batches */
 							pf.fd = st.fd; pf.n_thr = n_thr; pf.pos = next; pf.buf = blockbuf2[cur_buf ^ 1];
 							pf.len = (map_size - next < FQ_BLOCK + FQ_MARGIN) ? map_size - next : FQ_BLOCK + FQ_MARGIN;
+							memset(&pf.blk, 0, sizeof pf.blk);
 							if (pthread_create(&pf.th, NULL, prefetch_main, &pf) == 0) pf.active = 1;
 						}
 						continue;
 					}
 					/* not strict 4-line FASTQ from here on: the serial reader takes over at the start of the block */
-					map = NULL;
+					block_release(&cur); map = NULL; par_file = 0;
 					lseek(st.fd, (off_t)map_pos, SEEK_SET);
 					st.n = st.pos = st.eof = 0; st.last_char = 0;
 					n_recs = i_rec = 0;
 					continue;
 				}
-				map = NULL; n_recs = i_rec = 0;
-				if (pf.active) { pthread_join(pf.th, NULL); pf.active = 0; }
+				par_file = 0; n_recs = i_rec = 0;
+				if (pf.active) { pthread_join(pf.th, NULL); pf.active = 0; block_release(&pf.blk); }
 				close(st.fd); stream_open = 0; file_i++;
 				continue;
 			}
@@ -300,10 +328,9 @@ static void *reader_main(void *arg)
 					pthread_mutex_unlock(&sh->mu);
 					struct stat sb;
 					if (!st.fp && n_thr > 0 && got >= 1 && magic[0] == '@' && fstat(st.fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
-						if (!blockbuf2[0]) { blockbuf2[0] = malloc(((uint64_t)256 << 20) + FQ_MARGIN + 16); blockbuf2[1] = malloc(((uint64_t)256 << 20) + FQ_MARGIN + 16); cur_buf = 0; }
-						blockbuf = blockbuf2[cur_buf];
-						if (blockbuf) {
-							map = blockbuf; map_size = (uint64_t)sb.st_size; map_pos = 0; n_recs = i_rec = 0;
+						if (!g_fq_mmap && !blockbuf2[0]) { blockbuf2[0] = malloc(((uint64_t)256 << 20) + FQ_MARGIN + 16); blockbuf2[1] = malloc(((uint64_t)256 << 20) + FQ_MARGIN + 16); cur_buf = 0; }
+						if (g_fq_mmap || (blockbuf2[0] && blockbuf2[1])) {
+							par_file = 1; map = NULL; map_size = (uint64_t)sb.st_size; map_pos = 0; n_recs = i_rec = 0;
 							continue;
 						}
 					}
@@ -330,7 +357,8 @@ static void *reader_main(void *arg)
 		pthread_mutex_unlock(&sh->mu);
 		if (end_of_input) break;
 	}
-	if (pf.active) pthread_join(pf.th, NULL);
+	if (pf.active) { pthread_join(pf.th, NULL); block_release(&pf.blk); }
+	block_release(&cur);
 	free(blockbuf2[0]); free(blockbuf2[1]);
 	for (int t = 0; t < 64; t++) free(lists[t].r);
 	free(recs);
@@ -362,6 +390,7 @@ static void *worker_main(void *arg)
 		int32_t max_out = max_in; int rc;
 		const double tc0 = now_s();
 		for (;;) {
+			if (g_host_only) { memset(b->rr, 0, (size_t)b->n_reads * sizeof *b->rr); b->n_hits = 0; rc = DSB_OK; break; }   /* DSB_HOST_ONLY: the host pipeline's own ceiling */
 			if (want > b->m_hits) { b->m_hits = want; free(b->hits); b->hits = xrealloc(NULL, b->m_hits * sizeof *b->hits); }
 			dsb_ctx_set_bin_capacity(w->ctx, b->m_bin_read_in);
 			rc = dsb_classify_batch(w->ctx, b->seqs, b->offs, b->n_reads, max_in, &max_out, b->rr, b->hits, b->m_hits, &b->n_hits);
@@ -517,13 +546,19 @@ static int classify_main(int argc, char **argv)
 	const int verbose = getenv("DSB_VERBOSE") != NULL;
 	g_pageable = getenv("DSB_PINNED") == NULL;
 	g_register = getenv("DSB_REGISTER") != NULL;
+	if (getenv("DSB_FQ_MMAP")) g_fq_mmap = atoi(getenv("DSB_FQ_MMAP")) != 0;
+	g_host_only = getenv("DSB_HOST_ONLY") != NULL;     /* test / developer aid: reader + writer only -- no device is opened, every read is written as unclassified */
 	if (getenv("DSB_FQ_BLOCK_MB") && atol(getenv("DSB_FQ_BLOCK_MB")) >= 1 && atol(getenv("DSB_FQ_BLOCK_MB")) <= 256) g_fq_block = (uint64_t)atol(getenv("DSB_FQ_BLOCK_MB")) << 20;
+	if (getenv("DSB_FQ_BLOCK_KB") && atol(getenv("DSB_FQ_BLOCK_KB")) >= 1 && atol(getenv("DSB_FQ_BLOCK_KB")) <= (256 << 10)) g_fq_block = (uint64_t)atol(getenv("DSB_FQ_BLOCK_KB")) << 10;   /* tests */
 	const double t_start = now_s();
 	#define STAMP(what) do { if (verbose) fprintf(stderr, "[deSAMBA-b200] %-34s at %7.3f s\n", what, now_s() - t_start); } while (0)
 	/* the reader starts at once: the first batches are parsed into pinned memory while the index is loaded into HBM */
 	shared_t sh; memset(&sh, 0, sizeof sh);
 	sh.o = &o; sh.n_slots = 2 * ((o.n_gpus > 0 ? o.n_gpus : 8) * o.ctx_per_gpu) + 2; sh.slot = xcalloc(sh.n_slots, sizeof(slot_t)); sh.bo = xcalloc(sh.n_slots, sizeof(bo_slot));
-	sh.max_ahead = 3;
+	sh.max_ahead = getenv("DSB_READ_AHEAD") ? atoi(getenv("DSB_READ_AHEAD")) : 3;   /* batches filled while the index loads: few -- faulting fresh buffers in from a dozen threads slows the
+	                                                                                 * loader's and the contexts' device allocations (same mm lock) by more than it saves later (measured: 9.0 s wall against 4.5 s) */
+	if (sh.max_ahead < 1) sh.max_ahead = 1;
+	if (sh.max_ahead > sh.n_slots) sh.max_ahead = sh.n_slots;
 	pthread_mutex_init(&sh.mu, NULL); pthread_cond_init(&sh.cv, NULL);
 	sh.n_files = argc - optind; sh.files = argv + optind;
 	pthread_t rd;
@@ -532,8 +567,10 @@ static int classify_main(int argc, char **argv)
 	#define BAIL(...) do { fprintf(stderr, __VA_ARGS__); pthread_mutex_lock(&sh.mu); if (!sh.error) sh.error = -1; pthread_cond_broadcast(&sh.cv); pthread_mutex_unlock(&sh.mu); pthread_join(rd, NULL); return 1; } while (0)
 	dsb_index *gix[64];
 	int n_gpus = 0;
+	/* the worker threads sleep while their batch is on the GPU: up to 6 x 8 of them would otherwise spin on the reader's cores */
+	dsb_set_sync_mode(getenv("DSB_SPIN") == NULL);
 	double t_load0 = 0, t_clone = 0;
-	for (int g = 0; g < (o.n_gpus > 0 ? o.n_gpus : 64); g++) {
+	for (int g = 0; g < (o.n_gpus > 0 ? o.n_gpus : 64) && !g_host_only; g++) {
 		dsb_index *ix = NULL;
 		const double tl = now_s();
 		int rc = (g == 0 || getenv("DSB_NO_CLONE")) ? dsb_index_load(index_dir, g, &ix) : dsb_index_clone(gix[0], g, &ix);
@@ -554,9 +591,9 @@ static int classify_main(int argc, char **argv)
 	if (o.max_matches) dop.max_matches = o.max_matches;
 	if (o.max_read_len) dop.max_read_len = o.max_read_len;
 	if (o.pool_scale_pct) dop.pool_scale_pct = o.pool_scale_pct;
-	worker_t *w = xcalloc((size_t)n_gpus * o.ctx_per_gpu, sizeof *w);
+	worker_t *w = xcalloc((size_t)(n_gpus ? n_gpus : 1) * o.ctx_per_gpu, sizeof *w);
 	int n_workers = 0, ctx_made = 0;
-	for (int k = 0; k < o.ctx_per_gpu; k++) {               /* round k: one more context on every GPU */
+	for (int k = 0; k < o.ctx_per_gpu && !g_host_only; k++) {   /* round k: one more context on every GPU */
 		int ok = 1;
 		for (int g = 0; g < n_gpus && ok; g++) {
 			uint64_t fr = 0, tot = 0;
@@ -574,8 +611,9 @@ static int classify_main(int argc, char **argv)
 		ctx_made = k + 1;
 	}
 	o.ctx_per_gpu = ctx_made;
+	if (g_host_only) n_workers = 2;                         /* no device is opened at all: two threads hand the batches on with empty results */
 	STAMP("contexts created");
-	const dsb_ref_info *ri = dsb_index_ref_info(w[0].ix);
+	const dsb_ref_info *ri = g_host_only ? NULL : dsb_index_ref_info(w[0].ix);
 	const double t0 = now_s(), c0 = cpu_s();
 	fprintf(stderr, "Start classify\n");
 	pthread_mutex_lock(&sh.mu);
@@ -630,8 +668,13 @@ static int classify_main(int argc, char **argv)
 	for (int k = 0; k < n_workers; k++) pthread_join(th[k], NULL);
 	STAMP("last record written");
 	if (verbose) fprintf(stderr, "[deSAMBA-b200] batch buffers: %d allocations, %.3f s (%s)\n", g_n_pinned, g_t_pinned, g_pageable ? "pageable" : "pinned");
-	if (verbose) fprintf(stderr, "[deSAMBA-b200] host time: reader %.3f s work + %.3f s waiting for a free batch; GPU calls %.3f s (sum over %d worker threads); writer %.3f s formatting + %.3f s waiting\n",
-	                     sh.t_reader_work, sh.t_reader_wait, sh.t_worker_call, n_workers, sh.t_writer_fmt, sh.t_writer_wait);
+	if (verbose) fprintf(stderr, "[deSAMBA-b200] host time: reader %.3f s work (block input %.3f, indexing %.3f, copies %.3f) + %.3f s waiting for a free batch; GPU calls %.3f s (sum over %d worker threads); writer %.3f s formatting + %.3f s waiting\n",
+	                     sh.t_reader_work, sh.t_rd_read, sh.t_rd_index, sh.t_rd_copy, sh.t_reader_wait, sh.t_worker_call, n_workers, sh.t_writer_fmt, sh.t_writer_wait);
+	if (verbose && !g_host_only) {
+		double sum[5] = {0, 0, 0, 0, 0};
+		for (int k = 0; k < n_workers; k++) { double h[5] = {0, 0, 0, 0, 0}; dsb_ctx_host_seconds(w[k].ctx, h, 5); for (int i = 0; i < 5; i++) sum[i] += h[i]; }
+		fprintf(stderr, "[deSAMBA-b200] GPU calls: %.0f batches, upload %.3f s, launches %.3f s, waiting + results %.3f s (sums over the worker threads); %.0f pool-overflow re-runs\n", sum[3], sum[0], sum[1], sum[2], sum[4]);
+	}
 	fflush(o.out);
 	if (o.out != stdout) fclose(o.out);
 	if (sh.error) { fprintf(stderr, "[deSAMBA-b200] error %d: %s\n", sh.error, sh.errmsg); return 1; }
@@ -640,7 +683,7 @@ static int classify_main(int argc, char **argv)
 	fprintf(stderr, "Classify CPU: %.3f sec\n", cpu_s() - c0);
 	fprintf(stderr, "GPUs: %d (%d contexts each); index: %.3f s load on GPU 0 + %.3f s device-to-device copies\n", n_gpus, o.ctx_per_gpu, t_load0, t_clone);
 	if (sh.n_capacity_reads) fprintf(stderr, "[deSAMBA-b200] warning: %llu read(s) exceeded a per-read capacity and were written as unclassified (raise -A / -m)\n", (unsigned long long)sh.n_capacity_reads);
-	for (int k = 0; k < n_workers; k++) dsb_ctx_free(w[k].ctx);
+	for (int k = 0; k < n_workers; k++) if (w[k].ctx) dsb_ctx_free(w[k].ctx);
 	for (int g = 0; g < n_gpus; g++) dsb_index_free(gix[g]);
 	STAMP("device memory released");
 	return 0;

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
 
 #define PROBE_TILE 1024
 #define PROBE_THREADS 256
@@ -464,7 +465,7 @@ extern "C" int dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out)
 	c->heavy_blocks = HEAVY_BLOCKS;
 	if (const char *e = getenv("DSB_HEAVY_BLOCKS")) { const int v = atoi(e); if (v >= 1 && v <= 1024) c->heavy_blocks = v; }   // developer knob
 	DSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-	for (int i = 0; i < DSB_N_EV; i++) DSB_CUDA(cudaEventCreate(&c->ev[i]));
+	for (int i = 0; i < DSB_N_EV; i++) DSB_CUDA(cudaEventCreateWithFlags(&c->ev[i], dsb_blocking_sync() ? cudaEventBlockingSync : cudaEventDefault));
 	int rc = ensure(c->counters, DSB_CNT_COUNT * 8);
 	if (rc != DSB_OK) { dsb_ctx_free(c); return rc; }
 	*out = c;
@@ -596,7 +597,7 @@ extern "C" int dsb_ctx_reserve(dsb_ctx *c, uint32_t max_reads, uint64_t max_base
 	}
 	if (!c->h_stage) {
 		DSB_CUDA(cudaHostAlloc(&c->h_stage, 2 * (size_t)DSB_STAGE_BYTES, cudaHostAllocDefault));
-		for (int k = 0; k < 2; k++) DSB_CUDA(cudaEventCreateWithFlags(&c->ev_stage[k], cudaEventDisableTiming));
+		for (int k = 0; k < 2; k++) DSB_CUDA(cudaEventCreateWithFlags(&c->ev_stage[k], cudaEventDisableTiming | (dsb_blocking_sync() ? cudaEventBlockingSync : 0)));
 	}
 	DSB_CUDA(cudaStreamSynchronize(c->stream));
 	return DSB_OK;
@@ -613,6 +614,7 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 	if (offs[0] != 0) { dsb_set_error("dsb_batch_upload: offs[0] must be 0"); return DSB_E_ARG; }
 	// per-read layout tables (host): bin / bit-vector / seed-slot offsets and the probe tile list
 	const size_t tbl_bytes = (size_t)(n_reads + 1) * 8;
+	DSB_CUDA(cudaEventRecord(c->ev[DSB_N_KERNELS + 3], c->stream));             // the stream turns to this batch (dsb_batch_timeline)
 	uint64_t n_tiles = 0; uint32_t max_len = 0;
 	for (uint32_t r = 0; r < n_reads; r++) {
 		if (offs[r + 1] < offs[r] || offs[r + 1] - offs[r] > c->opts.max_read_len) { dsb_set_error("read %u: bad offsets or longer than max_read_len %u", r, c->opts.max_read_len); return DSB_E_ARG; }
@@ -680,7 +682,7 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 		else {
 			if (!c->h_stage) {
 				DSB_CUDA(cudaHostAlloc(&c->h_stage, 2 * (size_t)DSB_STAGE_BYTES, cudaHostAllocDefault));
-				for (int k = 0; k < 2; k++) DSB_CUDA(cudaEventCreateWithFlags(&c->ev_stage[k], cudaEventDisableTiming));
+				for (int k = 0; k < 2; k++) DSB_CUDA(cudaEventCreateWithFlags(&c->ev_stage[k], cudaEventDisableTiming | (dsb_blocking_sync() ? cudaEventBlockingSync : 0)));
 			}
 			uint64_t off = 0;
 			for (int k = 0; off < n_bases; k ^= 1) {
@@ -869,14 +871,30 @@ extern "C" int dsb_batch_download(dsb_ctx *c, int32_t *max_read_l_out, dsb_read_
 
 extern "C" int dsb_batch_retries(dsb_ctx *c) { return c ? c->retries : 0; }
 
+static double host_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 extern "C" int dsb_classify_batch(dsb_ctx *c, const char *seqs, const uint64_t *offs, uint32_t n_reads, int32_t max_read_l_in, int32_t *max_read_l_out,
                                   dsb_read_result *rr, dsb_hit *hits, uint64_t hits_cap, uint64_t *n_hits_out)
 {
 	int rc;
 	if (max_read_l_out) *max_read_l_out = max_read_l_in;
+	const double t0 = host_now();
 	if ((rc = dsb_batch_upload(c, seqs, offs, n_reads)) != DSB_OK) return rc;
+	const double t1 = host_now();
 	if ((rc = dsb_batch_run(c, max_read_l_in)) != DSB_OK) return rc;
-	return dsb_batch_download(c, max_read_l_out, rr, hits, hits_cap, n_hits_out);
+	const double t2 = host_now();
+	rc = dsb_batch_download(c, max_read_l_out, rr, hits, hits_cap, n_hits_out);
+	if (c) { c->host_s[0] += t1 - t0; c->host_s[1] += t2 - t1; c->host_s[2] += host_now() - t2; c->host_s[3] += 1; c->host_s[4] += c->retries; }
+	return rc;
+}
+
+// where the host time of dsb_classify_batch went on this context so far: seconds in upload (layout tables + copies of the reads
+// into the stream), run (kernel launches), download (waiting for the batch + result copies); calls; pool-overflow re-runs
+extern "C" int dsb_ctx_host_seconds(dsb_ctx *c, double *out, int cap)
+{
+	if (!c || !out) return DSB_E_ARG;
+	for (int i = 0; i < 5 && i < cap; i++) out[i] = c->host_s[i];
+	return DSB_OK;
 }
 
 extern "C" int dsb_batch_get_seeds(dsb_ctx *c, uint32_t read, int strand, dsb_seed *out, uint32_t cap, uint32_t *n_out, uint32_t *total_score)
@@ -919,6 +937,20 @@ extern "C" int dsb_ctx_elapsed_ms(dsb_ctx *a, int mark_a, dsb_ctx *b, int mark_b
 	DSB_CUDA(cudaSetDevice(a->ix->device));
 	DSB_CUDA(cudaEventSynchronize(b->ev[DSB_N_KERNELS + 1 + mark_b]));
 	DSB_CUDA(cudaEventElapsedTime(ms, a->ev[DSB_N_KERNELS + 1 + mark_a], b->ev[DSB_N_KERNELS + 1 + mark_b]));
+	return DSB_OK;
+}
+
+// Developer aid: where the batch last run on `c` sat on the device's time line -- ms from mark `ref_mark` of context `ref` to
+// t[0] the stream turning to the batch (start of the upload) and t[1 .. DSB_N_KERNELS + 1] the kernel boundaries (t[1] = reads
+// resident, first kernel starts; t[i + 1] = kernel group i done).
+extern "C" int dsb_batch_timeline(dsb_ctx *ref, int ref_mark, dsb_ctx *c, float *t, int cap)
+{
+	if (!ref || !c || !c->ran || !t || ref_mark < 0 || ref_mark > 1 || cap < DSB_N_KERNELS + 2) return DSB_E_ARG;
+	DSB_CUDA(cudaSetDevice(c->ix->device));
+	DSB_CUDA(cudaStreamSynchronize(c->stream));
+	const cudaEvent_t r = ref->ev[DSB_N_KERNELS + 1 + ref_mark];
+	DSB_CUDA(cudaEventElapsedTime(&t[0], r, c->ev[DSB_N_KERNELS + 3]));
+	for (int i = 0; i <= DSB_N_KERNELS; i++) DSB_CUDA(cudaEventElapsedTime(&t[1 + i], r, c->ev[i]));
 	return DSB_OK;
 }
 

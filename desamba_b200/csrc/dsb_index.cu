@@ -244,13 +244,25 @@ static int load_impl(dsb_index *ix, const char *dir, bool verbose)
 	return DSB_OK;
 }
 
+static int g_blocking_sync = 0;       // dsb_set_sync_mode
 static int open_device(int device)
 {
+
 	int n_dev = 0;
 	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { dsb_set_error("no CUDA device (there is no CPU fallback)"); return DSB_E_CUDA; }
 	if (device < 0 || device >= n_dev) { dsb_set_error("device %d out of range (%d devices)", device, n_dev); return DSB_E_ARG; }
 	DSB_CUDA(cudaSetDevice(device));
+	// host threads that wait for a batch sleep instead of spinning (dsb_set_sync_mode); CUDA 12 applies the flags to the current
+	// device whether or not its primary context exists already
+	if (g_blocking_sync && cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync) != cudaSuccess) (void)cudaGetLastError();
 	DSB_CUDA(cudaFree(0));
+	return DSB_OK;
+}
+
+int dsb_blocking_sync() { return g_blocking_sync; }
+extern "C" int dsb_set_sync_mode(int blocking)
+{
+	g_blocking_sync = blocking ? 1 : 0;
 	return DSB_OK;
 }
 

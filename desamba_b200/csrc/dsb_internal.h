@@ -8,6 +8,7 @@
 #include <utility>
 
 void dsb_set_error(const char *fmt, ...);
+int dsb_blocking_sync();                 // dsb_set_sync_mode (dsb_index.cu)
 #define DSB_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
 	dsb_set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return DSB_E_CUDA; } } while (0)
 
@@ -29,7 +30,7 @@ struct DevBuf {                         // grow-only device buffer
 
 #define DSB_STAGE_BYTES (16u << 20)
 #define DSB_N_KERNELS 11               // timed kernel groups of one dsb_batch_run
-#define DSB_N_EV (DSB_N_KERNELS + 3)   // kernel boundaries + 2 user marks
+#define DSB_N_EV (DSB_N_KERNELS + 4)   // kernel boundaries + 2 user marks + start of the upload
 
 struct dsb_ctx {
 	dsb_index *ix;
@@ -48,6 +49,7 @@ struct dsb_ctx {
 	uint32_t grow[5];                   // pool growth (x 2^k) after overflows: tasks, chunks, anchors, chains, hits
 	int32_t max_read_l_in;              // of the last dsb_batch_run (re-runs after a pool overflow, dsb_batch_download)
 	int retries;                        // re-runs of the last batch
+	double host_s[5] = {0, 0, 0, 0, 0};  // dsb_ctx_host_seconds
 	uint64_t scratch_stride;
 	uint64_t hits_cap;
 	// pinned staging: per-read tables of the upload; ring of two chunks for reads that arrive in pageable memory

@@ -135,6 +135,10 @@ int dsb_batch_kernel_ms(dsb_ctx *ctx, float *ms, int cap);
  * context's stream; dsb_ctx_elapsed_ms waits for b's mark and returns b.mark_b - a.mark_a in ms */
 int dsb_ctx_mark(dsb_ctx *ctx, int which);
 int dsb_ctx_elapsed_ms(dsb_ctx *a, int mark_a, dsb_ctx *b, int mark_b, float *ms);
+/* developer aid: where the batch last run on `ctx` sat on the device's time line, in ms from mark `ref_mark` of context `ref`:
+ * t[0] the stream turns to the batch (upload starts), t[1] reads resident / first kernel starts, t[2 .. 12] the 11 kernel groups
+ * of dsb_batch_kernel_ms done.  cap >= 13. */
+int dsb_batch_timeline(dsb_ctx *ref, int ref_mark, dsb_ctx *ctx, float *t, int cap);
 /* work-list sizes of the last run: [0] reads in slow pass 0, [1] in slow pass 1, [2] scored (warp per read), [3] scored again by a CTA
  * each (repeat-rich), [4..6] seed tasks of the fast / slow 0 / slow 1 pass, [7..9] staging chunks of the passes, [10] anchors,
  * [11] chains handed to scoring */
@@ -160,6 +164,14 @@ void dsb_host_free(void *p);
 /* page-lock / release memory the caller allocated itself (e.g. huge-page batch buffers of the driver) */
 int  dsb_host_register(void *p, size_t bytes);
 void dsb_host_unregister(void *p);
+/* Host seconds dsb_classify_batch has spent on this context so far: out[0] upload (per-read layout tables, copies of the reads
+ * into the stream), [1] run (kernel launches), [2] download (waiting for the batch, result copies), [3] calls, [4] re-runs
+ * after a pool overflow. */
+int  dsb_ctx_host_seconds(dsb_ctx *ctx, double *out, int cap);
+/* How host threads wait for the GPU: 0 (default) the CUDA runtime's choice (spins while there are more cores than contexts),
+ * 1 sleep until the stream is done.  With several contexts per GPU and one host thread each (the driver: up to 6 x 8 threads)
+ * spinning takes the cores the FASTQ reader needs.  Takes effect for devices opened afterwards (dsb_index_load / _clone). */
+int  dsb_set_sync_mode(int blocking);
 /* free / total HBM of a device in bytes */
 int  dsb_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes);
 

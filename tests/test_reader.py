@@ -91,3 +91,70 @@ def test_demo_and_simulated_sets(ob):
         want, _ = _dump("serial", path)
         got, rc = _dump("parallel", path, 1 << 18, 8)
         assert got == want and rc == 0
+
+
+# ---------------------------------------------------------------- the driver's whole host pipeline, without a GPU
+DRIVER = os.path.join(ROOT, "desamba_b200", "bin", "deSAMBA-b200")
+
+
+def _host_only(tmp_path, files, fmt, env=None, *opts):
+    """`deSAMBA-b200 classify` with DSB_HOST_ONLY=1: reader -> batches -> writer, no device opened, every read unclassified"""
+    out = str(tmp_path / "out.txt")
+    e = dict(os.environ, DSB_HOST_ONLY="1", **(env or {}))
+    r = subprocess.run([DRIVER, "classify", "-f", fmt, "-o", out] + [str(o) for o in opts] + ["no_index_needed"] + files, capture_output=True, env=e)
+    assert r.returncode == 0, r.stderr.decode()[-600:]
+    return open(out, "rb").read(), r.stderr.decode()
+
+
+def _records(rng, n, lo, hi, tag):
+    recs = []
+    for i in range(n):
+        L = int(rng.integers(lo, hi + 1))
+        recs.append((b"%s%d" % (tag, i), bytes(rng.choice(list(b"ACGTN"), L).tolist()), bytes(rng.choice(list(b"@+>I5#"), L).tolist())))
+    return recs
+
+
+def _fastq(recs, crlf=False, comment=False):
+    nl = b"\r\n" if crlf else b"\n"
+    return b"".join(b"@" + n + (b" a comment" if comment and i % 2 else b"") + nl + s + nl + b"+" + nl + q + nl for i, (n, s, q) in enumerate(recs))
+
+
+def test_driver_host_pipeline_hands_on_every_record_in_order(ob, tmp_path):
+    """several files (strict FASTQ through the parallel indexer, mapped or read; CRLF; gzip and a FASTA tail through the serial
+    reader), small blocks and small batches: the text holds every record once, in input order, with its bases and qualities"""
+    import gzip
+    rng = np.random.default_rng(11)
+    sets = [_records(rng, 300, 1, 6000, b"a"), _records(rng, 200, 50, 300, b"b"), _records(rng, 40, 20000, 60000, b"c"), _records(rng, 150, 1, 900, b"d")]
+    files = [str(tmp_path / f"f{i}.fq") for i in range(4)]
+    open(files[0], "wb").write(_fastq(sets[0]))
+    open(files[1], "wb").write(_fastq(sets[1], crlf=True, comment=True))
+    open(files[2], "wb").write(_fastq(sets[2]))
+    files[3] += ".gz"
+    with gzip.open(files[3], "wb") as f:
+        f.write(_fastq(sets[3]))
+    allrec = [r for s in sets for r in s]
+    want_full = b"".join(n + b"\t4\t*\t0\t0\t*\t*\t0\t0\t" + s + b"\t" + q + b"\t\n" for n, s, q in allrec)
+    want_des = b"".join(n + b"\tUNCLASSIFY\tSLOW\t%d\tn_rst:[0]\tn_anc:[0]\t\n\n" % len(s) for n, s, q in allrec)
+    for env, opts in (({}, ()), ({"DSB_FQ_BLOCK_KB": "64"}, ("-B", 37, "-P", 3)), ({"DSB_FQ_BLOCK_KB": "7", "DSB_FQ_MMAP": "0"}, ("-B", 1000, "-M", 1, "-P", 5)),
+                      ({"DSB_FQ_BLOCK_KB": "300"}, ("-B", 64, "-P", 0)), ({"DSB_FQ_BLOCK_MB": "1", "DSB_READ_AHEAD": "1"}, ("-B", 500, "-P", 8))):
+        got, err = _host_only(tmp_path, files, "SAM_FULL", env, *opts)
+        assert got == want_full, (env, opts)
+        assert "%d sequences processed" % len(allrec) in err
+    got, _ = _host_only(tmp_path, files, "DES", {"DSB_FQ_BLOCK_KB": "16"}, "-B", 100, "-P", 4)
+    assert got == want_des
+
+
+def test_driver_host_pipeline_falls_back_inside_a_file(ob, tmp_path):
+    """a file that stops being strict 4-line FASTQ after some blocks: the records before the break come from the indexer, the
+    rest (wrapped sequence lines) from the serial reader, nothing lost or doubled"""
+    rng = np.random.default_rng(12)
+    head = _records(rng, 400, 100, 400, b"h")
+    p = str(tmp_path / "mixed.fq")
+    wrapped = b"@w1\nACGT\nACGT\n+\nIIII\nIIII\n@w2\nAC\n+\nII\n"
+    open(p, "wb").write(_fastq(head) + wrapped + _fastq(_records(rng, 50, 10, 50, b"t")))
+    want, _ = _dump("serial", p)
+    want_des = b"".join(l.split(b"\t")[0] + b"\tUNCLASSIFY\tSLOW\t%d\tn_rst:[0]\tn_anc:[0]\t\n\n" % len(l.split(b"\t")[1]) for l in want.splitlines())
+    assert want_des.count(b"UNCLASSIFY") == 452
+    for env in ({"DSB_FQ_BLOCK_KB": "32"}, {"DSB_FQ_BLOCK_KB": "32", "DSB_FQ_MMAP": "0"}, {}):
+        got, _ = _host_only(tmp_path, [p, p], "DES", env, "-B", 90, "-P", 4)
+        assert got == want_des + want_des, env
