@@ -9,7 +9,7 @@
  *   writer (main)   formats the result records of each batch in input order (output_results, cly_mt.c:350-365)
  * The index is replicated per GPU, reads are sharded by batch, nothing is exchanged between GPUs.
  * Extra options: -g INT GPUs to use [all visible], -c INT contexts (batches in flight) per GPU [up to 6, as HBM allows], -B INT reads per batch
- * [262144], -M INT Mbases per batch [512], -P INT helper threads of the FASTQ reader [8 on >= 16 cores; 0 = serial reader],
+ * [262144], -M INT Mbases per batch [512], -P INT helper threads of the FASTQ reader [cores - 6, at most 48; 0 = serial reader],
  * -A / -m INT per-read anchor / match capacity, -L INT longest read accepted, -p INT pool sizing in % (dsb_opts).
  * -t is accepted and ignored (the thread pool it sized no longer exists).
  *
@@ -45,24 +45,44 @@ typedef struct {
 
 /* ---------------------------------------------------------------- batches */
 enum { SLOT_FREE = BO_FREE, SLOT_READY = BO_READY, SLOT_BUSY = BO_BUSY, SLOT_DONE = BO_DONE };
+/* the buffers of a batch travel as one set: a slot that starts to fill takes the set that was released LAST (its pages are
+ * resident and warm) -- rotating through all 2 x contexts x GPUs + 2 slots made nearly every batch of a run fault fresh memory in
+ * (measured on 8 GPUs: 98 slots, 120 batches, 4.5 of the reader's 6.8 s in the copies) */
+typedef struct {
+	char *seqs; size_t m_seqs;              /* ordinary (huge-page) memory, or pinned with DSB_PINNED=1 */
+	uint64_t *offs; size_t m_offs;          /* n_reads + 1 */
+	char *quals; size_t m_quals;            /* SAM_FULL only, same offsets as seqs */
+	char *names; size_t m_names;            /* NUL-terminated, concatenated */
+	uint32_t *name_off; size_t m_name_off;
+	dsb_read_result *rr; size_t m_rr;
+	dsb_hit *hits; size_t m_hits;
+} bufset_t;
 typedef struct {
 	int state; int rc;
 	uint64_t seq_no;
 	uint32_t n_reads; uint64_t n_bases;
-	char *seqs; size_t m_seqs;              /* pinned */
-	uint64_t *offs; size_t m_offs;          /* pinned, n_reads + 1 */
-	char *quals; size_t m_quals;            /* SAM_FULL only, same offsets as seqs */
-	char *names; size_t n_names, m_names;   /* NUL-terminated, concatenated */
-	uint32_t *name_off; size_t m_name_off;
+	union {
+		bufset_t B;
+		struct {
+			char *seqs; size_t m_seqs;
+			uint64_t *offs; size_t m_offs;
+			char *quals; size_t m_quals;
+			char *names; size_t m_names;
+			uint32_t *name_off; size_t m_name_off;
+			dsb_read_result *rr; size_t m_rr;
+			dsb_hit *hits; size_t m_hits;
+		};
+	};
+	size_t n_names;
 	int has_long, has_short;
 	uint32_t m_bin_read_in;                 /* capacity of the reference's bin_read buffer before this batch (dsb_ctx_set_bin_capacity) */
-	dsb_read_result *rr; size_t m_rr;
-	dsb_hit *hits; size_t m_hits; uint64_t n_hits;
+	uint64_t n_hits;
 } slot_t;
 
 typedef struct {
 	opts_t *o;
 	int n_slots; slot_t *slot;
+	bufset_t *free_set; int n_free_set;     /* released buffer sets, last in first out (under mu) */
 	pthread_mutex_t mu; pthread_cond_t cv;
 	uint64_t n_filled, n_claimed, n_written; int eof;
 	bo_slot *bo;                            /* per slot: what batch_order.h needs (kept under mu) */
@@ -253,6 +273,9 @@ static void *reader_main(void *arg)
 		if (err) break;
 		const double tw1 = now_s();
 		sh->t_reader_wait += tw1 - tw0;
+		pthread_mutex_lock(&sh->mu);
+		if (sh->n_free_set) b->B = sh->free_set[--sh->n_free_set]; else memset(&b->B, 0, sizeof b->B);
+		pthread_mutex_unlock(&sh->mu);
 		b->n_reads = 0; b->n_bases = 0; b->n_names = 0; b->has_long = b->has_short = 0; b->m_bin_read_in = m_bin_read;
 		int end_of_input = 0;
 		while (b->n_reads < o->batch_reads && b->n_bases < o->batch_bases) {
@@ -489,7 +512,7 @@ static void usage(void)
 	fprintf(stderr, "    -l, INT         minimum matching length, ignored for NGS reads [170]\n    -r, INT         max Output number of secondary alignments[5]\n");
 	fprintf(stderr, "    -o, FILE        output results into file [stdout]\n    -s, INT         MIN score[64]\n");
 	fprintf(stderr, "    -f, STR         output format, one of: SAM (default), SAM_FULL, DES, DES_FULL\n");
-	fprintf(stderr, "    -g, INT         number of GPUs [all visible]\n    -c, INT         batches in flight per GPU [3]\n    -B, INT         reads per batch [262144]\n    -M, INT         Mbases per batch [512]\n    -P, INT         FASTQ reader threads [8 on >= 16 cores; 0: serial]\n");
+	fprintf(stderr, "    -g, INT         number of GPUs [all visible]\n    -c, INT         batches in flight per GPU [3]\n    -B, INT         reads per batch [262144]\n    -M, INT         Mbases per batch [512]\n    -P, INT         FASTQ reader threads [cores - 6; 0: serial]\n");
 	fprintf(stderr, "    -A, INT         anchors kept per read [16384]\n    -m, INT         9-mer matches kept per extension [16384]\n    -L, INT         longest read accepted [1048576]\n    -p, INT         size of the per-batch device pools in %% of the built-in sizing [100]\n\n");
 }
 
@@ -541,7 +564,7 @@ static int classify_main(int argc, char **argv)
 	const int auto_ctx = o.ctx_per_gpu < 1;                 /* as many as HBM allows, up to 6 (decided once the index is resident) */
 	if (auto_ctx) o.ctx_per_gpu = 6;
 	if (o.ctx_per_gpu > 8) o.ctx_per_gpu = 8;
-	if (o.n_parse_threads < 0) { long nc = sysconf(_SC_NPROCESSORS_ONLN); o.n_parse_threads = nc >= 16 ? (nc - 4 > 48 ? 48 : (int)nc - 4) : nc >= 8 ? 4 : nc >= 4 ? 2 : 1; }
+	if (o.n_parse_threads < 0) { long nc = sysconf(_SC_NPROCESSORS_ONLN); o.n_parse_threads = nc >= 16 ? (nc - 6 > 48 ? 48 : (int)nc - 6) : nc >= 8 ? 4 : nc >= 4 ? 2 : 1;   /* the GPU worker threads stage pageable batches with 3 threads each: leave them cores */ }
 	if (o.n_parse_threads > 64) o.n_parse_threads = 64;
 	const int verbose = getenv("DSB_VERBOSE") != NULL;
 	g_pageable = getenv("DSB_PINNED") == NULL;
@@ -554,7 +577,7 @@ static int classify_main(int argc, char **argv)
 	#define STAMP(what) do { if (verbose) fprintf(stderr, "[deSAMBA-b200] %-34s at %7.3f s\n", what, now_s() - t_start); } while (0)
 	/* the reader starts at once: the first batches are parsed into pinned memory while the index is loaded into HBM */
 	shared_t sh; memset(&sh, 0, sizeof sh);
-	sh.o = &o; sh.n_slots = 2 * ((o.n_gpus > 0 ? o.n_gpus : 8) * o.ctx_per_gpu) + 2; sh.slot = xcalloc(sh.n_slots, sizeof(slot_t)); sh.bo = xcalloc(sh.n_slots, sizeof(bo_slot));
+	sh.o = &o; sh.n_slots = 2 * ((o.n_gpus > 0 ? o.n_gpus : 8) * o.ctx_per_gpu) + 2; sh.slot = xcalloc(sh.n_slots, sizeof(slot_t)); sh.bo = xcalloc(sh.n_slots, sizeof(bo_slot)); sh.free_set = xcalloc(sh.n_slots + 1, sizeof(bufset_t));
 	sh.max_ahead = getenv("DSB_READ_AHEAD") ? atoi(getenv("DSB_READ_AHEAD")) : 3;   /* batches filled while the index loads: few -- faulting fresh buffers in from a dozen threads slows the
 	                                                                                 * loader's and the contexts' device allocations (same mm lock) by more than it saves later (measured: 9.0 s wall against 4.5 s) */
 	if (sh.max_ahead < 1) sh.max_ahead = 1;
@@ -660,6 +683,7 @@ static int classify_main(int argc, char **argv)
 		}
 		sh.t_writer_fmt += now_s() - tq1;
 		pthread_mutex_lock(&sh.mu);
+		sh.free_set[sh.n_free_set++] = b->B; memset(&b->B, 0, sizeof b->B);
 		b->state = SLOT_FREE; sh.n_written++;
 		pthread_cond_broadcast(&sh.cv);
 		pthread_mutex_unlock(&sh.mu);

@@ -28,7 +28,8 @@ struct DevBuf {                         // grow-only device buffer
 	DevBuf() : p(nullptr), cap(0) {}
 };
 
-#define DSB_STAGE_BYTES (16u << 20)
+#define DSB_STAGE_BYTES (8u << 20)     // one piece of the staged (pageable) upload
+#define DSB_STAGE_THREADS 3            // host threads that stage a batch, two pieces of the ring each
 #define DSB_N_KERNELS 11               // timed kernel groups of one dsb_batch_run
 #define DSB_N_EV (DSB_N_KERNELS + 4)   // kernel boundaries + 2 user marks + start of the upload
 
@@ -54,7 +55,7 @@ struct dsb_ctx {
 	uint64_t hits_cap;
 	// pinned staging: per-read tables of the upload; ring of two chunks for reads that arrive in pageable memory
 	void *h_pin; size_t h_pin_cap;
-	void *h_stage; cudaEvent_t ev_stage[2];
+	void *h_stage; cudaEvent_t ev_stage[2 * DSB_STAGE_THREADS];
 	// batch state
 	uint32_t m_bin_read;                // capacity of the reference's bin_read buffer after the batches seen so far (policy P3)
 	uint32_t n_reads, n_tiles; uint64_t n_bases, bits_words, seed_slots, bin_bytes; uint32_t max_len;

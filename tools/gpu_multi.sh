@@ -24,7 +24,7 @@ for k in 1 2 4 8; do
 	FILES=$(for i in $(seq $((16 * k))); do echo -n "/dev/shm/dsb_step.fq "; done)
 	DSB_VERBOSE=1 desamba_b200/bin/deSAMBA-b200 classify -g $k -f SAM -o /dev/shm/dsb_out.sam $IDX $FILES 2> /tmp/drv.err
 	echo "== driver -g $k, $((16 * k)) step files ($((8 * k)) Gbases): $(grep -E 'sequences processed' /tmp/drv.err)"
-	grep -E "host time|GPUs:" /tmp/drv.err | sed 's/^/     /'
+	grep -E "host time|GPU calls:|GPUs:| at +[0-9.]+ s" /tmp/drv.err | sed 's/^/     /'
 	md5sum /dev/shm/dsb_out.sam | cut -c1-12
 done
 if [ $N -gt 1 ]; then

@@ -30,5 +30,4 @@ run() { # label env... -- args
 }
 run "default" X=1 --
 md5sum /dev/shm/dsb_out.sam | cut -c1-12
-run "spin" DSB_SPIN=1 --
-run "-P 6" X=1 -- -P 6
+for p in $PS; do run "-P $p" X=1 -- -P $p; done
