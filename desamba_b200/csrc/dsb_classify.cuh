@@ -587,25 +587,32 @@ __device__ __noinline__ void sdp_match(ReadState &S, uint32_t q_bg, uint32_t q_e
 	// target index, read position) pair with equal 9-mers.
 	const uintptr_t a_lo = (uintptr_t)(A.q_str + lo) & ~(uintptr_t)15;
 	const int64_t p_first = (int64_t)(a_lo - (uintptr_t)A.q_str);                  // read position of byte 0 of the first 16-byte chunk (<= lo)
+	// a short range (the gap between two anchors of a chain: a few hundred positions) would leave most lanes without a chunk
+	// while the others look up 16 positions one after the other: there `share` = 2 or 4 lanes split a chunk (they load the same
+	// 24 bytes -- one request) and a round covers 256 or 128 positions
+	const uint32_t n_span = (uint32_t)((int64_t)hi - p_first + 1);
+	const int share = n_span <= 128 ? 4 : n_span <= 256 ? 2 : 1, per_lane = 16 / share, j_first = (lane & (share - 1)) * per_lane;
+	const int64_t round = 512 / share;
+	const uint32_t j_mine = ((1u << per_lane) - 1) << j_first;
 	uint4 a = make_uint4(0, 0, 0, 0); uint2 b = make_uint2(0, 0);
-	{ const int64_t p0 = p_first + 16 * lane; if (p0 <= (int64_t)hi) { a = __ldg((const uint4 *)(A.q_str + p0)); b = __ldg((const uint2 *)(A.q_str + p0 + 16)); } }
-	for (int64_t pb = p_first; pb <= (int64_t)hi; pb += 512) {
-		const int64_t p0 = pb + 16 * lane;
+	{ const int64_t p0 = p_first + 16 * (lane / share); if (p0 <= (int64_t)hi) { a = __ldg((const uint4 *)(A.q_str + p0)); b = __ldg((const uint2 *)(A.q_str + p0 + 16)); } }
+	for (int64_t pb = p_first; pb <= (int64_t)hi; pb += round) {
+		const int64_t p0 = pb + 16 * (lane / share);
 		const uint4 ca = a; const uint2 cb = b;
-		{ const int64_t pn = p0 + 512; if (pn <= (int64_t)hi) { a = __ldg((const uint4 *)(A.q_str + pn)); b = __ldg((const uint2 *)(A.q_str + pn + 16)); } }
+		{ const int64_t pn = p0 + round; if (pn <= (int64_t)hi) { a = __ldg((const uint4 *)(A.q_str + pn)); b = __ldg((const uint2 *)(A.q_str + pn + 16)); } }
 		uint32_t maybe = 0;                                                        // bit j: the 9-mer at p0 + j passes the filter
 		uint64_t bits = 0;
 		if (p0 <= (int64_t)hi && p0 + 15 >= (int64_t)lo) {
 			bits = ((uint64_t)pack4(ca.x) << 40) | ((uint64_t)pack4(ca.y) << 32) | ((uint64_t)pack4(ca.z) << 24) |
 			       ((uint64_t)pack4(ca.w) << 16) | ((uint64_t)pack4(cb.x) << 8) | (uint64_t)pack4(cb.y);   // base t of the chunk at bits 47-2t, 46-2t
 			#pragma unroll 4
-			for (int j = 0; j < 16; j++) {
+			for (int j = j_first; j < j_first + per_lane; j++) {
 				const uint32_t kmer = (uint32_t)(bits >> (30 - 2 * j)) & 0x3ffffu;
 				const uint32_t f = tt_hash(kmer, fbits);
 				maybe |= ((lds_u32_ro(a_bloom + 4 * (f >> 5)) >> (f & 31)) & 1u) << j;
 			}
 			const int j_min = (int)DSB_MAX((int64_t)lo - p0, (int64_t)0), j_max = (int)DSB_MIN((int64_t)hi - p0, (int64_t)15);
-			maybe &= (0xffffu >> (15 - j_max)) & (0xffffu << j_min);
+			maybe &= (0xffffu >> (15 - j_max)) & (0xffffu << j_min) & j_mine;
 		}
 		while (__any_sync(DSB_FULL, maybe != 0)) {                                  // one position per lane and turn
 			if (lds_u32(a_ncand) + 32 * n_pos > CAND_CAP) sdp_flush_cand(S, A);     // room for every scanned position on every lane
@@ -730,8 +737,8 @@ struct DpTeam {
 	int kind; uint32_t first, nb;
 	const DevSms *sms;
 	DevSms item[32]; int stopped0[32];
-	int best[TEAM_WARPS][32]; int brk[TEAM_WARPS][32];
-	uint4 tile[TEAM_WARPS][32];       // predecessor tile of dp_range, one per warp
+	int best[2][TEAM_WARPS][32]; uint8_t brk[2][TEAM_WARPS][32];   // per round (ping-pong), tile and lane: best candidate, walk hit its break
+	uint4 tile[TEAM_WARPS][32];       // predecessor tile, one per warp
 };
 
 // phase (A) over the predecessors [lo, hi), walked downwards: best candidate per lane and whether the lane's walk hit its break.
@@ -767,16 +774,54 @@ __device__ __noinline__ void dp_range(const int KIND, const DevSms *sms, int lo,
 	__syncwarp();
 }
 
-__device__ __forceinline__ void dp_team_range(DpTeam *T, int w)
-{   // the share of warp w (0 = the range nearest to the block) of the posted job
+// Phase (A) of a posted job by the whole CTA.  The predecessors first-1 .. 0 are cut into tiles of 32, nearest first; in round
+// r warp w walks tile 32 r + w, then all warps combine the 32 tiles of the round IN ORDER (a lane's walk ends at its first
+// break, later tiles do not count) -- every warp computes the same, so all leave the loop together once every lane has
+// stopped.  (Round 1 gave each warp one contiguous 1/32 of the predecessors: the walks of a repeat-rich window end after a few
+// thousand of them, so the two or three nearest warps did all the work -- 82 % of the kernel's stall samples were the other
+// warps at the barrier.)  Returns the best candidate of the lane's match over the earlier blocks (INT_MIN: none).
+__device__ __forceinline__ int dp_team_range(DpTeam *T, int w)
+{
 	const int lane = lane_id();
-	const int first = (int)T->first, chunk = (first + TEAM_WARPS - 1) / TEAM_WARPS;
-	const int hi = first - w * chunk, lo = max(0, hi - chunk);
+	const int first = (int)T->first, n_tiles = (first + 31) >> 5, kind = T->kind;
+	const DevSms *sms = T->sms;
 	const DevSms my = T->item[lane];
-	int best = INT_MIN; bool brk = false;
-	const bool stopped = T->stopped0[lane] != 0;
-	if (hi > 0) dp_range(T->kind, T->sms, lo, hi, my, stopped, best, brk, smem_addr(T->tile[w]));
-	T->best[w][lane] = best; T->brk[w][lane] = brk ? 1 : 0;
+	bool stopped = T->stopped0[lane] != 0;
+	int best = INT_MIN;
+	const uint32_t a_buf = smem_addr(T->tile[w]);
+	int t = w;
+	uint4 cur = make_uint4(0, 0, 0, 0);
+	if (t < n_tiles && first - 1 - 32 * t - lane >= 0) cur = *(const uint4 *)(sms + first - 1 - 32 * t - lane);
+	for (int r = 0; 32 * r < n_tiles; r++, t += TEAM_WARPS) {
+		uint4 nxt = make_uint4(0, 0, 0, 0);                  // my tile of the next round is in flight while this one is walked
+		if (t + TEAM_WARPS < n_tiles && first - 1 - 32 * (t + TEAM_WARPS) - lane >= 0) nxt = *(const uint4 *)(sms + first - 1 - 32 * (t + TEAM_WARPS) - lane);
+		int tb = INT_MIN; bool tbrk = false;
+		if (t < n_tiles) {
+			asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a_buf + 16 * lane), "r"(cur.x), "r"(cur.y), "r"(cur.z), "r"(cur.w) : "memory");
+			__syncwarp();
+			const int n_here = min(32, first - 32 * t);
+			if (!stopped) {
+				#pragma unroll 2
+				for (int k = 0; k < n_here; k++) {
+					DevSms p;
+					asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(p.t_pos), "=r"(p.q_pos), "=r"(p.len), "=r"(p.score) : "r"(a_buf + 16 * k) : "memory");
+					bool pass, brk, has; int cand;
+					dp_eval(kind, my, p, pass, brk, has, cand);
+					if (brk) { tbrk = true; break; }
+					if (has) tb = DSB_MAX(tb, cand);
+				}
+			}
+			__syncwarp();
+		}
+		const int buf = r & 1;
+		T->best[buf][w][lane] = tb; T->brk[buf][w][lane] = tbrk ? 1 : 0;
+		__syncthreads();                                 // the tiles of the round are done
+		if (!stopped)
+			for (int ww = 0; ww < TEAM_WARPS; ww++) { best = DSB_MAX(best, T->best[buf][ww][lane]); if (T->brk[buf][ww][lane]) { stopped = true; break; } }
+		cur = nxt;
+		if (__all_sync(DSB_FULL, stopped)) break;        // (the same in every warp)
+	}
+	return best;
 }
 
 __device__ __forceinline__ void dp_team_helper_loop(DpTeam *T, int w)
@@ -784,8 +829,7 @@ __device__ __forceinline__ void dp_team_helper_loop(DpTeam *T, int w)
 	for (;;) {
 		__syncthreads();                                 // job posted
 		if (T->cmd < 0) break;
-		dp_team_range(T, w);
-		__syncthreads();                                 // results ready
+		(void)dp_team_range(T, w);
 	}
 }
 
@@ -815,10 +859,8 @@ __device__ __noinline__ int dp_block(const int KIND, const DevSms *sms, uint32_t
 		team->item[lane] = my; team->stopped0[lane] = stopped ? 1 : 0;
 		if (lane == 0) { team->kind = KIND; team->first = first; team->nb = nb; team->sms = sms; team->cmd = 1; }
 		__syncthreads();                                 // job posted: the helper warps wake up
-		dp_team_range(team, 0);
-		__syncthreads();                                 // results ready
-		if (!stopped)
-			for (int w = 0; w < TEAM_WARPS; w++) { best = DSB_MAX(best, team->best[w][lane]); if (team->brk[w][lane]) break; }
+		const int tb = dp_team_range(team, 0);
+		if (!stopped) best = DSB_MAX(best, tb);
 		__syncwarp();
 	} else {
 		bool brk = false;
