@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS_PER_BLOCK * 32, SCORE_MIN_BLOCK
 	for (int sweep = 0; sweep < 2; sweep++)
 		for (uint32_t r; (r = next_read(A.P, list, cursor + 12 * sweep)) != 0xffffffffu;) {
 			const bool is_big = A.P.work[r].n_anc > 200 || (A.P.read_off[r + 1] - A.P.read_off[r]) > 16000;
-			if (is_big == (sweep == 0)) phase_score(A.P, S, r);
+			if (is_big == (sweep == 0)) phase_score<false>(A.P, S, r);
 		}
 }
 
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) k_score_heavy(const __grid_co
 		ReadState S;
 		scratch_setup(A, S, slot0 + blockIdx.x);             // scratch slots of their own
 		S.sm = &wsm; S.team = &team; S.mt = &msm;
-		for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_score(A.P, S, r);
+		for (uint32_t r; (r = next_read(A.P, list, cursor)) != 0xffffffffu;) phase_score<true>(A.P, S, r);
 		if (lane_id() == 0) team.cmd = -1;
 		__syncthreads();                                 // releases the helpers
 	} else

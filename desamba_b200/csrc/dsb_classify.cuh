@@ -220,12 +220,14 @@ __device__ __noinline__ void warp_stable_sort_by_key(T *a, T *tmp, uint32_t n, u
 // element finds its place in the other run by binary search; the left run wins ties, so the order is stable).  key0 holds the
 // keys; key0/key1 and idx0/idx1 are ping-pong buffers of n entries.  Returns the index array: result[i] = index of the i-th
 // smallest key.
-template <uint32_t CHUNK>
-__device__ __noinline__ const uint32_t *warp_sort_perm(uint32_t n, uint64_t *key0, uint64_t *key1, uint32_t *idx0, uint32_t *idx1)
+// Warp `w_` of NW warps of a CTA work together when NW > 1 (k_score_heavy's team, all of them called with the same arguments):
+// chunks and elements are dealt round-robin, the passes are separated by CTA barriers.
+template <uint32_t CHUNK, int NW = 1>
+__device__ __noinline__ const uint32_t *warp_sort_perm(uint32_t n, uint64_t *key0, uint64_t *key1, uint32_t *idx0, uint32_t *idx1, int w_ = 0)
 {
-	const int lane = lane_id();
-	__syncwarp();
-	for (uint32_t c0 = 0; c0 < n; c0 += CHUNK) {                         // chunk sort: (key0, identity) -> (key1, idx1)
+	const int lane = lane_id(), w = NW > 1 ? w_ : 0, nw = NW;
+	if (nw > 1) __syncthreads(); else __syncwarp();
+	for (uint32_t c0 = (uint32_t)w * CHUNK; c0 < n; c0 += (uint32_t)nw * CHUNK) {     // chunk sort: (key0, identity) -> (key1, idx1)
 		const uint32_t cn = DSB_MIN((uint32_t)CHUNK, n - c0);
 		for (uint32_t i0 = 0; i0 < cn; i0 += 32) {
 			const uint32_t i = i0 + lane;
@@ -235,11 +237,11 @@ __device__ __noinline__ const uint32_t *warp_sort_perm(uint32_t n, uint64_t *key
 			if (i < cn) { key1[c0 + r] = ki; idx1[c0 + r] = c0 + i; }
 		}
 	}
-	__syncwarp();
+	if (nw > 1) __syncthreads(); else __syncwarp();
 	uint64_t *ks = key1, *kd = key0; uint32_t *is = idx1, *id = idx0;
-	for (uint32_t w = CHUNK; w < n; w <<= 1) {                           // merge runs of width w
-		for (uint32_t p = lane; p < n; p += 32) {
-			const uint32_t pair = p / (2 * w) * (2 * w), l0 = pair, l1 = DSB_MIN(pair + w, n), r1 = DSB_MIN(pair + 2 * w, n);
+	for (uint32_t wd = CHUNK; wd < n; wd <<= 1) {                        // merge runs of width wd
+		for (uint32_t p = (uint32_t)w * 32 + lane; p < n; p += (uint32_t)nw * 32) {
+			const uint32_t pair = p / (2 * wd) * (2 * wd), l0 = pair, l1 = DSB_MIN(pair + wd, n), r1 = DSB_MIN(pair + 2 * wd, n);
 			const uint64_t k = ks[p];
 			uint32_t dst;
 			if (p < l1) {                                                // left run: elements of the right run that are < k come first
@@ -253,7 +255,7 @@ __device__ __noinline__ const uint32_t *warp_sort_perm(uint32_t n, uint64_t *key
 			}
 			kd[dst] = k; id[dst] = is[p];
 		}
-		__syncwarp();
+		if (nw > 1) __syncthreads(); else __syncwarp();
 		uint64_t *tk = ks; ks = kd; kd = tk;
 		uint32_t *ti = is; is = id; id = ti;
 	}
@@ -461,6 +463,25 @@ __device__ __forceinline__ bool sms_push(ReadState &S, uint32_t t_pos, uint32_t 
 	return true;
 }
 
+struct SdpArgs { uint32_t q_bg, q_ed; const uint8_t *q_str, *t_str; uint32_t t_len, t_st; bool fwd; };
+struct FlushArgs { SdpArgs A; MatchSmem *M; const uint2 *cand; DevSms *sms_tmp; uint64_t *key; uint32_t n_sms, max_matches; };
+// Heavy reads (repeats: thousands of matches per window) are scored by k_score_heavy with a whole CTA: warp 0 runs the
+// read, the other warps only help with phase (A) below -- each takes a contiguous range of the earlier matches.
+#ifndef TEAM_WARPS
+#define TEAM_WARPS 32
+#endif
+#define TEAM_MIN_FIRST 128
+struct DpTeam {
+	int cmd;                          // 1: DP look-back posted, 2: sort posted, 3: candidate extension posted, < 0: exit
+	int kind; uint32_t first, nb;
+	uint32_t sort_n; uint64_t *sort_key[2]; uint32_t *sort_idx[2];
+	FlushArgs flush; uint32_t flush_n;
+	const DevSms *sms;
+	DevSms item[32]; int stopped0[32];
+	int best[2][TEAM_WARPS][32]; uint8_t brk[2][TEAM_WARPS][32];   // per round (ping-pong), tile and lane: best candidate, walk hit its break
+	uint4 tile[TEAM_WARPS][32];       // predecessor tile, one per warp
+};
+
 // ---------------------------------------------------------------- sdp_match (cly.c:2335-2440) without a per-read index
 // The reference hashes all 9-mers of the READ once (build_hash_table_M2, cly.c:2173-2224) and looks up every 4th 9-mer of a
 // reference window; only read positions inside [q_bg, q_ed] (<= 2000 wide) count.  A per-read index is ~100 KB of scattered
@@ -470,7 +491,6 @@ __device__ __forceinline__ bool sms_push(ReadState &S, uint32_t t_pos, uint32_t 
 // out of a 48-bit register.  Equal 9-mers give (target index, read position) candidates; each candidate then runs the
 // reference's own test + extension on a lane of its own (sdp_extend), and the surviving matches are put into the
 // reference's push order: target scan order, ascending read position (the order the hash chains are walked in).
-struct SdpArgs { uint32_t q_bg, q_ed; const uint8_t *q_str, *t_str; uint32_t t_len, t_st; bool fwd; };
 #define CAND_CAP (32 * 512 + 4096)
 // The per-warp shared structures are reached through pointers kept in ReadState, which the compiler can only treat as
 // generic addresses (LD.E / generic atomics); these wrappers keep the accesses in the shared window (LDS / STS / ATOMS).
@@ -513,31 +533,61 @@ __device__ __forceinline__ bool sdp_extend(const SdpArgs &A, uint32_t k, uint32_
 }
 
 // the collected candidates, 32 at a time: test + extension; a surviving match goes (unordered) into sms_tmp with its order
-// key (target index, read position of the 9-mer)
+// key (target index, read position of the 9-mer).  Warp `w` of `nw` (k_score_heavy's team) takes every nw-th group of 32.
+__device__ __noinline__ void flush_range(const FlushArgs &F, uint32_t nc, int w, int nw)
+{
+	const uint32_t a_ntmp = smem_addr(&F.M->n_tmp);
+	for (uint32_t c0 = (uint32_t)w * 32; c0 < nc; c0 += (uint32_t)nw * 32) {
+		const uint32_t c = c0 + lane_id();
+		if (c < nc) {
+			const uint2 cd = F.cand[c];
+			DevSms m; m.score = 0;
+			if (sdp_extend(F.A, cd.x, cd.y, m)) {
+				const uint32_t slot = atoms_add(a_ntmp, 1u);
+				if (F.n_sms + slot < F.max_matches) { F.sms_tmp[slot] = m; F.key[slot] = ((uint64_t)cd.x << 32) | cd.y; }
+			}
+		}
+	}
+}
+
+template <bool HEAVY>
 __device__ __noinline__ void sdp_flush_cand(ReadState &S, const SdpArgs &A)
 {
 	MatchSmem *M = S.mt;
 	__syncwarp();
-	const uint32_t a_ntmp = smem_addr(&M->n_tmp), a_ncand = smem_addr(&M->n_cand);
+	const uint32_t a_ncand = smem_addr(&M->n_cand);
 	const uint32_t nc = DSB_MIN(lds_u32(a_ncand), (uint32_t)CAND_CAP);
-	for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
-		const uint32_t c = c0 + lane_id();
-		if (c < nc) {
-			const uint2 cd = S.ws.cand[c];
-			DevSms m; m.score = 0;
-			if (sdp_extend(A, cd.x, cd.y, m)) {
-				const uint32_t slot = atoms_add(a_ntmp, 1u);
-				if (S.n_sms + slot < S.max_matches) { S.ws.sms_tmp[slot] = m; S.ws.sort_key[0][slot] = ((uint64_t)cd.x << 32) | cd.y; }
+	if (HEAVY && nc >= 1024) {                             // k_score_heavy: the whole CTA extends the candidates
+		DpTeam *T = S.team;
+		if (lane_id() == 0) {
+			FlushArgs F; F.A = A; F.M = M; F.cand = S.ws.cand; F.sms_tmp = S.ws.sms_tmp; F.key = S.ws.sort_key[0]; F.n_sms = S.n_sms; F.max_matches = S.max_matches;
+			T->flush = F; T->flush_n = nc; T->cmd = 3;
+		}
+		__syncthreads();                                   // job posted: the helper warps wake up
+		flush_range(T->flush, nc, 0, TEAM_WARPS);
+		__syncthreads();                                   // every candidate has been looked at
+	} else {
+		const uint32_t a_ntmp = smem_addr(&M->n_tmp);
+		for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
+			const uint32_t c = c0 + lane_id();
+			if (c < nc) {
+				const uint2 cd = S.ws.cand[c];
+				DevSms m; m.score = 0;
+				if (sdp_extend(A, cd.x, cd.y, m)) {
+					const uint32_t slot = atoms_add(a_ntmp, 1u);
+					if (S.n_sms + slot < S.max_matches) { S.ws.sms_tmp[slot] = m; S.ws.sort_key[0][slot] = ((uint64_t)cd.x << 32) | cd.y; }
+				}
 			}
 		}
+		__syncwarp();
 	}
-	__syncwarp();
 	if (lane_id() == 0) sts_u32(a_ncand, 0);
 	__syncwarp();
 }
 
 // Sorted permutation of n 64-bit keys by a warp, for large n: see warp_sort_perm above.
 
+template <bool HEAVY>
 __device__ __noinline__ void sdp_match(ReadState &S, uint32_t q_bg, uint32_t q_ed, const uint8_t *q_str, const uint8_t *t_str, uint32_t t_len,
                                        uint32_t t_st, bool isForward)
 {
@@ -615,7 +665,7 @@ __device__ __noinline__ void sdp_match(ReadState &S, uint32_t q_bg, uint32_t q_e
 			maybe &= (0xffffu >> (15 - j_max)) & (0xffffu << j_min) & j_mine;
 		}
 		while (__any_sync(DSB_FULL, maybe != 0)) {                                  // one position per lane and turn
-			if (lds_u32(a_ncand) + 32 * n_pos > CAND_CAP) sdp_flush_cand(S, A);     // room for every scanned position on every lane
+			if (lds_u32(a_ncand) + 32 * n_pos > CAND_CAP) sdp_flush_cand<HEAVY>(S, A);     // room for every scanned position on every lane
 			if (maybe) {
 				const int j = __ffs(maybe) - 1;
 				maybe &= maybe - 1;
@@ -628,7 +678,7 @@ __device__ __noinline__ void sdp_match(ReadState &S, uint32_t q_bg, uint32_t q_e
 		}
 	}
 	SDP_PT(1);
-	sdp_flush_cand(S, A);
+	sdp_flush_cand<HEAVY>(S, A);
 	SDP_PT(2);
 	// (3) order: target scan order, then ascending read position (unique keys), appended to the match array
 	const uint32_t total = lds_u32(smem_addr(&M->n_tmp));
@@ -646,7 +696,15 @@ __device__ __noinline__ void sdp_match(ReadState &S, uint32_t q_bg, uint32_t q_e
 				if (i < total) { const DevSms m = src[i]; dst[r].t_pos = m.t_pos; dst[r].q_pos = m.q_pos; dst[r].len = m.len; }
 			}
 		} else {
-			const uint32_t *perm = warp_sort_perm<128>(total, S.ws.sort_key[0], S.ws.sort_key[1], S.ws.sort_idx[0], S.ws.sort_idx[1]);
+			const uint32_t *perm;
+			if (HEAVY && total >= 1024) {                                              // k_score_heavy: the whole CTA orders the matches
+				DpTeam *T = S.team;
+				__syncwarp();
+				if (lane == 0) { T->sort_n = total; T->sort_key[0] = S.ws.sort_key[0]; T->sort_key[1] = S.ws.sort_key[1]; T->sort_idx[0] = S.ws.sort_idx[0]; T->sort_idx[1] = S.ws.sort_idx[1]; T->cmd = 2; }
+				__syncthreads();                                                       // job posted: the helper warps wake up
+				perm = warp_sort_perm<128, TEAM_WARPS>(total, S.ws.sort_key[0], S.ws.sort_key[1], S.ws.sort_idx[0], S.ws.sort_idx[1], 0);
+			} else
+				perm = warp_sort_perm<128>(total, S.ws.sort_key[0], S.ws.sort_key[1], S.ws.sort_idx[0], S.ws.sort_idx[1]);
 			for (uint32_t i = lane; i < total; i += 32) { const DevSms m = src[perm[i]]; dst[i].t_pos = m.t_pos; dst[i].q_pos = m.q_pos; dst[i].len = m.len; }
 		}
 		S.n_sms += total;
@@ -725,21 +783,6 @@ __device__ __forceinline__ void dp_eval(const int KIND, const DevSms &c, const D
 		has = true; cand = new_score;
 	}
 }
-
-// Heavy reads (repeats: thousands of matches per window) are scored by k_score_heavy with a whole CTA: warp 0 runs the
-// read, the other warps only help with phase (A) below -- each takes a contiguous range of the earlier matches.
-#ifndef TEAM_WARPS
-#define TEAM_WARPS 32
-#endif
-#define TEAM_MIN_FIRST 128
-struct DpTeam {
-	int cmd;                          // >= 0: job posted, < 0: exit
-	int kind; uint32_t first, nb;
-	const DevSms *sms;
-	DevSms item[32]; int stopped0[32];
-	int best[2][TEAM_WARPS][32]; uint8_t brk[2][TEAM_WARPS][32];   // per round (ping-pong), tile and lane: best candidate, walk hit its break
-	uint4 tile[TEAM_WARPS][32];       // predecessor tile, one per warp
-};
 
 // phase (A) over the predecessors [lo, hi), walked downwards: best candidate per lane and whether the lane's walk hit its break.
 // The predecessors are fetched 32 at a time (one coalesced 512-byte request, the next tile already in flight), parked in a
@@ -829,11 +872,14 @@ __device__ __forceinline__ void dp_team_helper_loop(DpTeam *T, int w)
 	for (;;) {
 		__syncthreads();                                 // job posted
 		if (T->cmd < 0) break;
-		(void)dp_team_range(T, w);
+		if (T->cmd == 3) { flush_range(T->flush, T->flush_n, w, TEAM_WARPS); __syncthreads(); }
+		else if (T->cmd == 2) (void)warp_sort_perm<128, TEAM_WARPS>(T->sort_n, T->sort_key[0], T->sort_key[1], T->sort_idx[0], T->sort_idx[1], w);
+		else (void)dp_team_range(T, w);
 	}
 }
 
 // scores of the matches [first, first + nb), nb <= 32; lane j holds match first+j in `my` and receives its score.
+template <bool HEAVY>
 __device__ __noinline__ int dp_block(const int KIND, const DevSms *sms, uint32_t first, uint32_t nb, DevSms my, DpTeam *team, uint32_t a_tile)
 {
 	const int lane = lane_id();
@@ -855,7 +901,7 @@ __device__ __noinline__ int dp_block(const int KIND, const DevSms *sms, uint32_t
 	// (A) predecessors in earlier blocks: all lanes walk first-1 .. 0 together, each with its own stop
 	int best = (int)my.len;
 	const bool stopped = !mine || stop_at >= 0;
-	if (team && first >= TEAM_MIN_FIRST) {
+	if (HEAVY && first >= TEAM_MIN_FIRST) {
 		team->item[lane] = my; team->stopped0[lane] = stopped ? 1 : 0;
 		if (lane == 0) { team->kind = KIND; team->first = first; team->nb = nb; team->sms = sms; team->cmd = 1; }
 		__syncthreads();                                 // job posted: the helper warps wake up
@@ -884,6 +930,7 @@ __device__ __noinline__ int dp_block(const int KIND, const DevSms *sms, uint32_t
 	}
 	return my_score;
 }
+template <bool HEAVY>
 __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8_t *q_str)
 {   // cly.c:2444-2530
 	const DevIndex &ix = *S.ix;
@@ -908,9 +955,9 @@ __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8
 				refwin_zero(S, 2128);
 				const uint64_t ref_offset = pre_refoffset + t_offset + pre_mch;
 				CNT_GETREF(S, total_ref_len); get_ref_coop(ix, S.sm->refwin, ref_offset, total_ref_len);
-				sdp_match(S, pa.index_in_read + pre_mch - 8, ca.index_in_read - 1, q_str, S.sm->refwin, total_ref_len, pre_refoffset + pre_mch, true);
+				sdp_match<HEAVY>(S, pa.index_in_read + pre_mch - 8, ca.index_in_read - 1, q_str, S.sm->refwin, total_ref_len, pre_refoffset + pre_mch, true);
 				if (S.error) return 0;
-				if (!S.team && S.n_sms > DEFER_SMS) { S.error = ERR_DEFER; return 0; }
+				if (!HEAVY && S.n_sms > DEFER_SMS) { S.error = ERR_DEFER; return 0; }
 			}
 			if (!sms_push(S, ca.ref_offset, ca.index_in_read, ca.mtch_len - S_A_KEMR_L + 1)) return 0;
 			if (S.n_sms > 1) {
@@ -919,7 +966,7 @@ __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8
 					const uint32_t nb = DSB_MIN(32u, S.n_sms - first);
 					DevSms my; my.t_pos = my.q_pos = my.len = my.score = 0;
 					if ((uint32_t)lane_id() < nb) my = load_sms(base + first + lane_id());
-					const int sc = dp_block(DP_MIDDLE, base, first, nb, my, S.team, smem_addr(S.mt->tslot));
+					const int sc = dp_block<HEAVY>(DP_MIDDLE, base, first, nb, my, S.team, smem_addr(S.mt->tslot));
 					if ((uint32_t)lane_id() < nb) base[first + lane_id()].score = sc;
 					__syncwarp();
 					score = DSB_MAX(warp_max(((uint32_t)lane_id() < nb) ? sc : INT_MIN), score);
@@ -932,6 +979,7 @@ __device__ __noinline__ int sdp_middle_M2(ReadState &S, int32_t c_a, const uint8
 	return score - 10000;
 }
 
+template <bool HEAVY>
 __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, int chain_ID, uint32_t l_read, int score_ori)
 {   // cly.c:2532-2677
 	const DevIndex &ix = *S.ix;
@@ -968,9 +1016,9 @@ __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, int
 			int search_q_ed = (int)sms[max_sms_id].q_pos + 1000;
 			search_q_ed = DSB_MIN(search_q_ed, l_read);
 			const int search_q_st = DSB_MAX(search_q_ed - 2000, ch.q_st - 8);
-			sdp_match(S, search_q_st, search_q_ed, q_str, S.sm->refwin, max_search_ref, c_t_offset, true);
+			sdp_match<HEAVY>(S, search_q_st, search_q_ed, q_str, S.sm->refwin, max_search_ref, c_t_offset, true);
 			if (S.error) return 0;
-			if (!S.team && S.n_sms > DEFER_SMS) { S.error = ERR_DEFER; return 0; }
+			if (!HEAVY && S.n_sms > DEFER_SMS) { S.error = ERR_DEFER; return 0; }
 			c_t_offset += max_search_ref - S_A_KEMR_L - 3;
 			if (S.n_sms == current_sms) break;
 			if (sms[current_sms].t_pos > sms[max_sms_id].t_pos + 1000) break;
@@ -979,7 +1027,7 @@ __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, int
 		const uint32_t first = current_sms, nb = DSB_MIN(32u, S.n_sms - current_sms);
 		DevSms my; my.t_pos = my.q_pos = my.len = my.score = 0;
 		if ((uint32_t)lane_id() < nb) my = load_sms(sms + first + lane_id());
-		const int my_score = dp_block(DP_RIGHT, sms, first, nb, my, S.team, smem_addr(S.mt->tslot));
+		const int my_score = dp_block<HEAVY>(DP_RIGHT, sms, first, nb, my, S.team, smem_addr(S.mt->tslot));
 		if ((uint32_t)lane_id() < nb) sms[first + lane_id()].score = my_score;
 		__syncwarp();
 		// combine_chain returns 0 at once when the bucket of the match's diagonal is empty (cly.c:1771)
@@ -992,7 +1040,7 @@ __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, int
 			const int max_score = __shfl_sync(DSB_FULL, my_score, j);
 			current_sms = first + j + 1;
 			if (((cm >> j) & 1) && combine_chain(S, chain_ID, c_sms.t_pos - c_sms.q_pos, 0, c_sms.q_pos, &combined) == 1) {
-				total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2(S, c_st[combined].cur, q_str);
+				total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2<HEAVY>(S, c_st[combined].cur, q_str);
 				if (S.error) return 0;
 				score_ori = total_max_score;
 				max_sms_id = 0;
@@ -1019,6 +1067,7 @@ __device__ __noinline__ int sdp_right_M2(ReadState &S, const uint8_t *q_str, int
 	return total_max_score - 10000;
 }
 
+template <bool HEAVY>
 __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, int chain_ID, int score_ori)
 {   // cly.c:2679-2819
 	const DevIndex &ix = *S.ix;
@@ -1057,9 +1106,9 @@ __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, int 
 			int search_q_st = (int)sms[max_sms_id].q_pos - 1000;
 			search_q_st = DSB_MAX(search_q_st, 0);
 			const int search_q_ed = DSB_MIN(search_q_st + 2000, ch.q_st - 1);
-			sdp_match(S, search_q_st, search_q_ed, q_str, S.sm->refwin + OVER_SEARCH_M2, max_search_ref, c_t_offset - max_search_ref, false);
+			sdp_match<HEAVY>(S, search_q_st, search_q_ed, q_str, S.sm->refwin + OVER_SEARCH_M2, max_search_ref, c_t_offset - max_search_ref, false);
 			if (S.error) return 0;
-			if (!S.team && S.n_sms > DEFER_SMS) { S.error = ERR_DEFER; return 0; }
+			if (!HEAVY && S.n_sms > DEFER_SMS) { S.error = ERR_DEFER; return 0; }
 			c_t_offset = c_t_offset - max_search_ref + S_A_KEMR_L + 3;
 			if (S.n_sms == current_sms) break;
 			if (sms[current_sms].t_pos + 1000 < sms[max_sms_id].t_pos) break;
@@ -1068,7 +1117,7 @@ __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, int 
 		const uint32_t first = current_sms, nb = DSB_MIN(32u, S.n_sms - current_sms);
 		DevSms my; my.t_pos = my.q_pos = my.len = my.score = 0;
 		if ((uint32_t)lane_id() < nb) my = load_sms(sms + first + lane_id());
-		const int my_score = dp_block(DP_LEFT, sms, first, nb, my, S.team, smem_addr(S.mt->tslot));
+		const int my_score = dp_block<HEAVY>(DP_LEFT, sms, first, nb, my, S.team, smem_addr(S.mt->tslot));
 		if ((uint32_t)lane_id() < nb) sms[first + lane_id()].score = my_score;
 		__syncwarp();
 		const bool need = (uint32_t)lane_id() < nb && my.len >= 8 && S.ws.sc_hash[(my.t_pos - my.q_pos) & 0xff].next != 0;
@@ -1080,7 +1129,7 @@ __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, int 
 			const int max_score = __shfl_sync(DSB_FULL, my_score, j);
 			current_sms = first + j + 1;
 			if (((cm >> j) & 1) && combine_chain(S, chain_ID, c_sms.t_pos - c_sms.q_pos, 1, c_sms.q_pos + c_sms.len, &combined) == 1) {
-				total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2(S, c_st[combined].cur, q_str);
+				total_max_score = DSB_MAX(score_ori, max_score) - c_sms.len + sdp_middle_M2<HEAVY>(S, c_st[combined].cur, q_str);
 				if (S.error) return 0;
 				score_ori = total_max_score;
 				max_sms_id = 0;
@@ -1108,6 +1157,7 @@ __device__ __noinline__ int sdp_left_M2(ReadState &S, const uint8_t *q_str, int 
 }
 
 // delete_small_score_rst up to (not including) the max_read_l-dependent filter (cly.c:2883-2957)
+template <bool HEAVY>
 __device__ __noinline__ void score_and_merge(ReadState &S, const SearchDir *search_dir, uint32_t l_read)
 {
 	if (S.n_hit == 0) return;
@@ -1125,11 +1175,11 @@ __device__ __noinline__ void score_and_merge(ReadState &S, const SearchDir *sear
 		if (C[i].sum_score == 0) continue;
 		const uint32_t dir = C[i].direction;
 		const SearchDir *c_sd = ((search_dir->direction == dir) ? 0 : 1) + search_dir;
-		int score; { PH_BEGIN(); score = sdp_middle_M2(S, C[i].cur, c_sd->bin_read); PH_END(S, 4); }
+		int score; { PH_BEGIN(); score = sdp_middle_M2<HEAVY>(S, C[i].cur, c_sd->bin_read); PH_END(S, 4); }
 		if (S.error) return;
-		{ PH_BEGIN(); score = sdp_right_M2(S, c_sd->bin_read, (int)i, l_read, score); PH_END(S, 5); }
+		{ PH_BEGIN(); score = sdp_right_M2<HEAVY>(S, c_sd->bin_read, (int)i, l_read, score); PH_END(S, 5); }
 		if (S.error) return;
-		{ PH_BEGIN(); score = sdp_left_M2(S, c_sd->bin_read, (int)i, score); PH_END(S, 6); }
+		{ PH_BEGIN(); score = sdp_left_M2<HEAVY>(S, c_sd->bin_read, (int)i, score); PH_END(S, 6); }
 		if (S.error) return;
 		C[i].sum_score = score;
 	}
@@ -1326,6 +1376,7 @@ __device__ void phase_chain(const ClassifyParams &P, ReadState &S, uint32_t r, i
 	read_end(P, S, r, t0);
 }
 
+template <bool HEAVY>
 __device__ void phase_score(const ClassifyParams &P, ReadState &S, uint32_t r)
 {
 	const long long t0 = clock64();
@@ -1343,7 +1394,7 @@ __device__ void phase_score(const ClassifyParams &P, ReadState &S, uint32_t r)
 	}
 	dsb_read_result out;
 	out.hit_off = 0; out.n_hit = 0; out.n_anchor = w.n_anc; out.fast_classify = w.fast_classify; out.entered_final = 1; out.error = 0; out.read_len = read_len;
-	score_and_merge(S, sd, read_len);
+	score_and_merge<HEAVY>(S, sd, read_len);
 	if (S.error == ERR_DEFER) {                          // too heavy for one warp: k_score_heavy starts over from the pool chains
 		list_push(P, LIST_SCORE_HEAVY, r);
 		read_end(P, S, r, t0);
