@@ -274,6 +274,19 @@ class Context:
         _check(lib.dsb_batch_upload(self._h, cat.ctypes.data, offs.ctypes.data, self.n_reads), "dsb_batch_upload")
         _check(lib.dsb_batch_sync(self._h), "dsb_batch_sync")
 
+    def upload_async(self, cat, offs, m_bin_read_in=0):
+        """dsb_batch_upload without waiting: may be called for the NEXT batch while the one run before is still on the GPU
+        (order per context: upload(k+1); download(k); run(k+1)); cat / offs must stay alive until the batch has been run"""
+        lib.dsb_ctx_set_bin_capacity(self._h, m_bin_read_in)
+        self.n_reads_next = len(offs) - 1
+        _check(lib.dsb_batch_upload(self._h, cat.ctypes.data, offs.ctypes.data, self.n_reads_next), "dsb_batch_upload")
+
+    def download_into(self, rr, hits):
+        """dsb_batch_download into caller-owned arrays; returns (n_hit_slots, max_read_l)"""
+        mx, used = C.c_int32(0), C.c_uint64(0)
+        _check(lib.dsb_batch_download(self._h, C.byref(mx), rr.ctypes.data, hits.ctypes.data, len(hits), C.byref(used)), "dsb_batch_download")
+        return used.value, mx.value
+
     def run(self, max_read_l_in=0):
         _check(lib.dsb_batch_run(self._h, max_read_l_in), "dsb_batch_run")
 

@@ -390,51 +390,87 @@ static void *reader_main(void *arg)
 }
 
 /* ---------------------------------------------------------------- GPU workers */
+/* One thread per context, one batch ahead: the reads of batch k + 1 are uploaded (dsb_batch_upload: a copy stream of its own) while
+ * the kernels of batch k run; then the results of k are fetched and k + 1 is started -- kt_pipeline's overlap of its read step
+ * with its classify step (cly_mt.c:369-398), per context. */
+static int worker_finish(worker_t *w, slot_t *b, uint64_t id, int32_t max_in)
+{
+	shared_t *sh = w->sh;
+	size_t want = (size_t)b->n_reads * 24 + 4096;
+	int32_t max_out = max_in; int rc;
+	for (;;) {
+		if (want > b->m_hits) { b->m_hits = want; free(b->hits); b->hits = xrealloc(NULL, b->m_hits * sizeof *b->hits); }
+		if (g_host_only) { memset(b->rr, 0, (size_t)b->n_reads * sizeof *b->rr); b->n_hits = 0; rc = DSB_OK; break; }   /* DSB_HOST_ONLY: the host pipeline's own ceiling */
+		rc = dsb_batch_download(w->ctx, &max_out, b->rr, b->hits, b->m_hits, &b->n_hits);
+		if (rc == DSB_E_CAPACITY && b->n_hits > b->m_hits) { want = b->n_hits; continue; }    /* more hits than the array holds: again with a larger one */
+		break;
+	}
+	uint64_t n_cap = 0;
+	if (rc == DSB_E_CAPACITY) {
+		/* single reads beyond a per-read capacity (-A / -m): they carry dsb_read_result.error and no hits; the run goes on and
+		 * they are written as unclassified (the reference grows its vectors without bound instead) */
+		for (uint32_t r = 0; r < b->n_reads; r++) if (b->rr[r].error) { n_cap++; b->rr[r].n_hit = 0; }
+		rc = DSB_OK;
+	}
+	if (rc != DSB_OK) { fail(sh, "dsb_batch_download", rc); return -1; }
+	pthread_mutex_lock(&sh->mu);
+	sh->n_capacity_reads += n_cap;
+	b->state = SLOT_DONE; b->rc = rc;
+	sh->bo[id % sh->n_slots].max_out = max_out; sh->bo[id % sh->n_slots].state = BO_DONE;
+	bo_finished(sh->bo, sh->n_slots, sh->n_claimed, &sh->done_upto, &sh->prefix_max);
+	pthread_cond_broadcast(&sh->cv);
+	pthread_mutex_unlock(&sh->mu);
+	return 0;
+}
+
 static void *worker_main(void *arg)
 {
 	worker_t *w = (worker_t *)arg; shared_t *sh = w->sh;
+	slot_t *cur = NULL; uint64_t cur_id = 0; int32_t cur_max_in = 0;     /* the batch on the GPU */
 	for (;;) {
+		/* the next batch, if there is one; wait for it only while this context has nothing on the GPU */
+		slot_t *nxt = NULL; uint64_t nxt_id = 0;
 		pthread_mutex_lock(&sh->mu);
-		while (!sh->error && sh->n_claimed == sh->n_filled && !sh->eof) pthread_cond_wait(&sh->cv, &sh->mu);
-		if (sh->error || sh->n_claimed == sh->n_filled) { pthread_mutex_unlock(&sh->mu); break; }
-		const uint64_t my = sh->n_claimed++;
-		slot_t *b = &sh->slot[my % sh->n_slots];
-		b->state = SLOT_BUSY; sh->bo[my % sh->n_slots].state = BO_BUSY;
-		/* the only cross-batch dependency (batch_order.h) */
-		int32_t max_in = 0;
-		const double tw0 = now_s();
-		while (!sh->error && !bo_may_start(sh->bo, sh->n_slots, my, sh->done_upto, sh->prefix_max, &max_in)) pthread_cond_wait(&sh->cv, &sh->mu);
-		sh->t_worker_wait += now_s() - tw0;
-		if (sh->error) { pthread_mutex_unlock(&sh->mu); break; }
+		while (!sh->error && sh->n_claimed == sh->n_filled && !sh->eof && !cur) pthread_cond_wait(&sh->cv, &sh->mu);
+		if (!sh->error && sh->n_claimed < sh->n_filled) {
+			nxt_id = sh->n_claimed++;
+			nxt = &sh->slot[nxt_id % sh->n_slots];
+			nxt->state = SLOT_BUSY; sh->bo[nxt_id % sh->n_slots].state = BO_BUSY;
+		}
+		const int err = sh->error;
 		pthread_mutex_unlock(&sh->mu);
-
-		if ((size_t)b->n_reads > b->m_rr) { b->m_rr = (size_t)b->n_reads * 2; b->rr = xrealloc(b->rr, b->m_rr * sizeof *b->rr); }
-		size_t want = (size_t)b->n_reads * 24 + 4096;
-		int32_t max_out = max_in; int rc;
+		if (err || (!nxt && !cur)) break;
 		const double tc0 = now_s();
-		for (;;) {
-			if (g_host_only) { memset(b->rr, 0, (size_t)b->n_reads * sizeof *b->rr); b->n_hits = 0; rc = DSB_OK; break; }   /* DSB_HOST_ONLY: the host pipeline's own ceiling */
-			if (want > b->m_hits) { b->m_hits = want; free(b->hits); b->hits = xrealloc(NULL, b->m_hits * sizeof *b->hits); }
-			dsb_ctx_set_bin_capacity(w->ctx, b->m_bin_read_in);
-			rc = dsb_classify_batch(w->ctx, b->seqs, b->offs, b->n_reads, max_in, &max_out, b->rr, b->hits, b->m_hits, &b->n_hits);
-			if (rc == DSB_E_CAPACITY && b->n_hits > b->m_hits) { want = b->n_hits; continue; }
-			break;
+		if (nxt) {
+			if ((size_t)nxt->n_reads > nxt->m_rr) { nxt->m_rr = (size_t)nxt->n_reads * 2; nxt->rr = xrealloc(nxt->rr, nxt->m_rr * sizeof *nxt->rr); }
+			if (!g_host_only) {
+				dsb_ctx_set_bin_capacity(w->ctx, nxt->m_bin_read_in);
+				const int rc = dsb_batch_upload(w->ctx, nxt->seqs, nxt->offs, nxt->n_reads);
+				if (rc != DSB_OK) { fail(sh, "dsb_batch_upload", rc); break; }
+			}
 		}
-		uint64_t n_cap = 0;
-		if (rc == DSB_E_CAPACITY) {
-			/* single reads beyond a per-read capacity (-A / -m): they carry dsb_read_result.error and no hits; the run goes on and
-			 * they are written as unclassified (the reference grows its vectors without bound instead) */
-			for (uint32_t r = 0; r < b->n_reads; r++) if (b->rr[r].error) { n_cap++; b->rr[r].n_hit = 0; }
-			rc = DSB_OK;
+		if (cur && worker_finish(w, cur, cur_id, cur_max_in)) break;
+		cur = NULL;
+		double t_dep = 0;
+		if (nxt) {
+			/* the only cross-batch dependency (batch_order.h) */
+			int32_t max_in = 0;
+			pthread_mutex_lock(&sh->mu);
+			const double tw0 = now_s();
+			while (!sh->error && !bo_may_start(sh->bo, sh->n_slots, nxt_id, sh->done_upto, sh->prefix_max, &max_in)) pthread_cond_wait(&sh->cv, &sh->mu);
+			t_dep = now_s() - tw0;
+			sh->t_worker_wait += t_dep;
+			const int err2 = sh->error;
+			pthread_mutex_unlock(&sh->mu);
+			if (err2) break;
+			if (!g_host_only) {
+				const int rc = dsb_batch_run(w->ctx, max_in);
+				if (rc != DSB_OK) { fail(sh, "dsb_batch_run", rc); break; }
+			}
+			cur = nxt; cur_id = nxt_id; cur_max_in = max_in;
 		}
-		if (rc != DSB_OK) { fail(sh, "dsb_classify_batch", rc); break; }
 		pthread_mutex_lock(&sh->mu);
-		sh->t_worker_call += now_s() - tc0;
-		sh->n_capacity_reads += n_cap;
-		b->state = SLOT_DONE; b->rc = rc;
-		sh->bo[my % sh->n_slots].max_out = max_out; sh->bo[my % sh->n_slots].state = BO_DONE;
-		bo_finished(sh->bo, sh->n_slots, sh->n_claimed, &sh->done_upto, &sh->prefix_max);
-		pthread_cond_broadcast(&sh->cv);
+		sh->t_worker_call += now_s() - tc0 - t_dep;
 		pthread_mutex_unlock(&sh->mu);
 	}
 	return NULL;

@@ -454,7 +454,7 @@ extern "C" int dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out)
 	if (c->opts.max_matches < 1024) c->opts.max_matches = 1024;
 	if (c->opts.warps_per_sm < CLASSIFY_WARPS_PER_BLOCK) c->opts.warps_per_sm = CLASSIFY_WARPS_PER_BLOCK;
 	if (c->opts.warps_per_sm > 32) c->opts.warps_per_sm = 32;
-	c->stream = nullptr; c->h_pin = nullptr; c->h_pin_cap = 0; c->ran = false; c->launches = 0; c->h_stage = nullptr; for (int k = 0; k < 2 * DSB_STAGE_THREADS; k++) c->ev_stage[k] = nullptr;
+	c->stream = nullptr; c->copy_stream = nullptr; c->ran = false; c->launches = 0; c->h_stage = nullptr; for (int k = 0; k < 2 * DSB_STAGE_THREADS; k++) c->ev_stage[k] = nullptr;
 	c->n_reads = 0; c->m_bin_read = 0; c->scratch_stride = 0; c->hits_cap = 0; c->task_cap = 0; c->n_chunks = 0; c->max_read_l_in = 0; c->retries = 0;
 	for (int k = 0; k < 5; k++) c->grow[k] = 0;
 	cudaDeviceProp prop;
@@ -465,6 +465,8 @@ extern "C" int dsb_ctx_create(dsb_index *ix, const dsb_opts *o, dsb_ctx **out)
 	c->heavy_blocks = HEAVY_BLOCKS;
 	if (const char *e = getenv("DSB_HEAVY_BLOCKS")) { const int v = atoi(e); if (v >= 1 && v <= 1024) c->heavy_blocks = v; }   // developer knob
 	DSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	DSB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	for (int k = 0; k < 2; k++) DSB_CUDA(cudaEventCreateWithFlags(&c->in[k].ev_up, cudaEventDisableTiming));
 	for (int i = 0; i < DSB_N_EV; i++) DSB_CUDA(cudaEventCreateWithFlags(&c->ev[i], dsb_blocking_sync() ? cudaEventBlockingSync : cudaEventDefault));
 	int rc = ensure(c->counters, DSB_CNT_COUNT * 8);
 	if (rc != DSB_OK) { dsb_ctx_free(c); return rc; }
@@ -476,16 +478,18 @@ extern "C" void dsb_ctx_free(dsb_ctx *c)
 {
 	if (!c) return;
 	cudaSetDevice(c->ix->device);
+	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
 	if (c->stream) cudaStreamSynchronize(c->stream);
-	DevBuf *bufs[] = {&c->seqs, &c->read_off, &c->bin_off, &c->bits_off, &c->seed_off, &c->tiles, &c->bin, &c->bits, &c->seeds[0], &c->seeds[1],
+	DevBuf *bufs[] = {&c->in[0].seqs, &c->in[1].seqs, &c->read_off, &c->bin_off, &c->bits_off, &c->seed_off, &c->tiles, &c->bin, &c->bits, &c->seeds[0], &c->seeds[1],
 	                  &c->n_seeds[0], &c->n_seeds[1], &c->total_score[0], &c->total_score[1], &c->scratch, &c->rr, &c->hits, &c->counters, &c->prof, &c->work, &c->anc_pool, &c->chain_pool,
 	                  &c->lists[0], &c->lists[1], &c->lists[2], &c->lists[3], &c->ctl, &c->order, &c->hdr7,
 	                  &c->pk, &c->tasks[0], &c->tasks[1], &c->recs, &c->chunks, &c->lane_mem, &c->vis2, &c->vis1_full, &c->vis_gen,
 	                  &c->task_first[0], &c->task_first[1], &c->task_cnt[0], &c->task_cnt[1]};
 	for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
-	if (c->h_pin) cudaFreeHost(c->h_pin);
+	for (int k = 0; k < 2; k++) { if (c->in[k].h_pin) cudaFreeHost(c->in[k].h_pin); if (c->in[k].ev_up) cudaEventDestroy(c->in[k].ev_up); }
 	if (c->h_stage) { cudaFreeHost(c->h_stage); for (int k = 0; k < 2 * DSB_STAGE_THREADS; k++) if (c->ev_stage[k]) cudaEventDestroy(c->ev_stage[k]); }
 	for (int i = 0; i < DSB_N_EV; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -521,11 +525,11 @@ extern "C" int dsb_device_memory(int device, uint64_t *free_bytes, uint64_t *tot
 }
 
 // device buffers of the upload step for a batch of n_reads reads / n_bases bases (grow-only)
-static int reserve_upload(dsb_ctx *c, uint64_t n_reads, uint64_t n_bases, uint64_t n_tiles, uint64_t bo, uint64_t wo, uint64_t so)
+static int reserve_upload(dsb_ctx *c, BatchIn &I, uint64_t n_reads, uint64_t n_bases, uint64_t n_tiles, uint64_t bo, uint64_t wo, uint64_t so)
 {
 	const size_t tbl_bytes = (size_t)(n_reads + 1) * 8;
 	int rc;
-	if ((rc = ensure(c->seqs, n_bases + 16)) || (rc = ensure(c->read_off, tbl_bytes)) || (rc = ensure(c->bin_off, tbl_bytes)) ||
+	if ((rc = ensure(I.seqs, n_bases + 16)) || (rc = ensure(c->read_off, tbl_bytes)) || (rc = ensure(c->bin_off, tbl_bytes)) ||
 	    (rc = ensure(c->bits_off, tbl_bytes)) || (rc = ensure(c->seed_off, (size_t)(n_reads + 1) * 4)) || (rc = ensure(c->tiles, n_tiles * 8 + 8)) ||
 	    (rc = ensure(c->bin, bo + 64)) || (rc = ensure(c->bits, wo * 4 + 64)) ||
 	    (rc = ensure(c->seeds[0], so * sizeof(dsb_seed) + 64)) || (rc = ensure(c->seeds[1], so * sizeof(dsb_seed) + 64)) ||
@@ -576,6 +580,17 @@ static int reserve_run(dsb_ctx *c, uint64_t n, uint64_t n_bases, uint64_t bits_w
 	return DSB_OK;
 }
 
+// pinned host memory of a batch's per-read tables (grow-only)
+static int pin_tables(BatchIn &I, size_t need)
+{
+	if (need <= I.h_pin_cap) return DSB_OK;
+	if (I.h_pin) cudaFreeHost(I.h_pin);
+	I.h_pin = nullptr; I.h_pin_cap = 0;
+	DSB_CUDA(cudaHostAlloc(&I.h_pin, need, cudaHostAllocDefault));
+	I.h_pin_cap = need;
+	return DSB_OK;
+}
+
 // the pinned ring of the staged upload: DSB_STAGE_THREADS x 2 pieces, an event per piece ("the copy out of it has landed")
 static int stage_ring(dsb_ctx *c)
 {
@@ -595,19 +610,16 @@ extern "C" int dsb_ctx_reserve(dsb_ctx *c, uint32_t max_reads, uint64_t max_base
 	const uint64_t n_tiles = nb / PROBE_TILE + n, bo = 2 * nb + (2 * DSB_GUARD + 16) * n, wo = (uint64_t)N_BITVEC * (nb / 32 + 2 * n), so = nb / 2 + 2 * n;
 	if (so >= 0xffffffffull) { dsb_set_error("dsb_ctx_reserve: batch limit too large (seed slots overflow 32 bits)"); return DSB_E_ARG; }
 	int rc;
-	if ((rc = reserve_upload(c, n, nb, n_tiles, bo, wo, so)) != DSB_OK) return rc;
+	for (int k = 0; k < 2; k++) if ((rc = reserve_upload(c, c->in[k], n, nb, n_tiles, bo, wo, so)) != DSB_OK) return rc;   // both input sets: the next batch is uploaded while one runs
 	if ((rc = reserve_run(c, n, nb, wo)) != DSB_OK) return rc;
 	const size_t pin_need = (size_t)(n + 1) * 8 * 4 + n_tiles * 8 + n + 64;
-	if (pin_need > c->h_pin_cap) {
-		if (c->h_pin) cudaFreeHost(c->h_pin);
-		c->h_pin = nullptr; c->h_pin_cap = 0;
-		DSB_CUDA(cudaHostAlloc(&c->h_pin, pin_need, cudaHostAllocDefault));
-		c->h_pin_cap = pin_need;
-	}
+	for (int k = 0; k < 2; k++) if ((rc = pin_tables(c->in[k], pin_need)) != DSB_OK) return rc;
 	if ((rc = stage_ring(c)) != DSB_OK) return rc;
 	DSB_CUDA(cudaStreamSynchronize(c->stream));
 	return DSB_OK;
 }
+
+static double host_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // counting gate per device for the staged (pageable) upload path
 #include <mutex>
@@ -628,18 +640,30 @@ struct StageGate {
 };
 std::mutex StageGate::mu; std::condition_variable StageGate::cv; int StageGate::busy[StageGate::MAX_DEV] = {0}; int StageGate::limit = -1;
 
+static int upload_impl(dsb_ctx *c, const char *seqs, const uint64_t *offs, uint32_t n_reads);
 extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *offs, uint32_t n_reads)
+{
+	const double t0 = host_now();
+	const int rc = upload_impl(c, seqs, offs, n_reads);
+	if (c) c->host_s[0] += host_now() - t0;
+	return rc;
+}
+static int upload_impl(dsb_ctx *c, const char *seqs, const uint64_t *offs, uint32_t n_reads)
 {
 	if (!c || (n_reads && (!seqs || !offs))) { dsb_set_error("dsb_batch_upload: null argument"); return DSB_E_ARG; }
 	DSB_CUDA(cudaSetDevice(c->ix->device));
-	c->ran = false;
-	c->n_reads = n_reads;
-	if (n_reads == 0) { c->n_tiles = 0; c->n_bases = 0; return DSB_OK; }
+	if (c->has_pending) { dsb_set_error("dsb_batch_upload: the batch uploaded before has not been run yet"); return DSB_E_ARG; }
+	// the input set the running batch does not use (or the same one again when nothing is in flight)
+	const int u = c->run_pending ? (c->cur ^ 1) : c->cur;
+	BatchIn &I = c->in[u];
+	if (!c->run_pending) c->ran = false;
+	I.n_reads = n_reads;
+	if (n_reads == 0) { I.n_tiles = 0; I.n_bases = 0; c->pend = u; c->has_pending = true; return DSB_OK; }
 	const uint64_t n_bases = offs[n_reads] - offs[0];
 	if (offs[0] != 0) { dsb_set_error("dsb_batch_upload: offs[0] must be 0"); return DSB_E_ARG; }
 	// per-read layout tables (host): bin / bit-vector / seed-slot offsets and the probe tile list
 	const size_t tbl_bytes = (size_t)(n_reads + 1) * 8;
-	DSB_CUDA(cudaEventRecord(c->ev[DSB_N_KERNELS + 3], c->stream));             // the stream turns to this batch (dsb_batch_timeline)
+	DSB_CUDA(cudaEventRecord(c->ev[DSB_N_KERNELS + 3], c->copy_stream));        // the copy stream turns to this batch (dsb_batch_timeline)
 	uint64_t n_tiles = 0; uint32_t max_len = 0;
 	for (uint32_t r = 0; r < n_reads; r++) {
 		if (offs[r + 1] < offs[r] || offs[r + 1] - offs[r] > c->opts.max_read_len) { dsb_set_error("read %u: bad offsets or longer than max_read_len %u", r, c->opts.max_read_len); return DSB_E_ARG; }
@@ -647,14 +671,12 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 		if (len >= 40) n_tiles += (len + PROBE_TILE - 1) / PROBE_TILE;
 		max_len = std::max(max_len, len);
 	}
-	const size_t pin_need = tbl_bytes * 3 + (size_t)(n_reads + 1) * 8 + n_tiles * 8 + n_reads + 64;
-	if (pin_need > c->h_pin_cap) {
-		if (c->h_pin) cudaFreeHost(c->h_pin);
-		c->h_pin = nullptr; c->h_pin_cap = 0;
-		DSB_CUDA(cudaHostAlloc(&c->h_pin, pin_need + pin_need / 4, cudaHostAllocDefault));
-		c->h_pin_cap = pin_need + pin_need / 4;
+	int rc;
+	{
+		const size_t pin_need = tbl_bytes * 3 + (size_t)(n_reads + 1) * 8 + n_tiles * 8 + n_reads + 64;
+		if (pin_need > I.h_pin_cap && (rc = pin_tables(I, pin_need + pin_need / 4)) != DSB_OK) return rc;
 	}
-	uint64_t *h_bin_off = (uint64_t *)c->h_pin, *h_bits_off = h_bin_off + n_reads + 1, *h_tiles64 = h_bits_off + n_reads + 1;
+	uint64_t *h_bin_off = (uint64_t *)I.h_pin, *h_bits_off = h_bin_off + n_reads + 1, *h_tiles64 = h_bits_off + n_reads + 1;
 	uint2 *h_tiles = (uint2 *)h_tiles64;
 	uint32_t *h_seed_off = (uint32_t *)(h_tiles64 + n_tiles);
 	uint64_t bo = 0, wo = 0, so = 0, ti = 0;
@@ -691,19 +713,18 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 		h_hdr7[r] = (uint8_t)((chunk >> 8) & 0xff);
 	}
 	if (so >= 0xffffffffull) { dsb_set_error("batch too large (seed slots overflow 32 bits): split the batch"); return DSB_E_ARG; }
-	c->n_tiles = (uint32_t)n_tiles; c->n_bases = n_bases; c->bits_words = wo; c->seed_slots = so; c->bin_bytes = bo; c->max_len = max_len;
-	c->h_bits_off.assign(h_bits_off, h_bits_off + n_reads + 1);
-	c->h_seed_off.assign(h_seed_off, h_seed_off + n_reads + 1);
-	c->h_off.assign(offs, offs + n_reads + 1);
-	int rc;
-	if ((rc = reserve_upload(c, n_reads, n_bases, n_tiles, bo, wo, so)) != DSB_OK) return rc;
-	cudaStream_t st = c->stream;
+	I.n_tiles = (uint32_t)n_tiles; I.n_bases = n_bases; I.bits_words = wo; I.seed_slots = so; I.bin_bytes = bo; I.max_len = max_len;
+	I.h_bits_off.assign(h_bits_off, h_bits_off + n_reads + 1);
+	I.h_seed_off.assign(h_seed_off, h_seed_off + n_reads + 1);
+	I.h_off.assign(offs, offs + n_reads + 1);
+	if ((rc = reserve_upload(c, I, n_reads, n_bases, n_tiles, bo, wo, so)) != DSB_OK) return rc;   // (a buffer that grows is freed first: cudaFree waits for the batch in flight)
+	cudaStream_t st = c->copy_stream;
 	{	// the reads: straight from the caller's buffer when it is page-locked, else through the context's pinned staging ring (the
 		// runtime's own path for pageable memory serialises the copies of all contexts of a process)
 		cudaPointerAttributes pa;
 		const bool pinned = cudaPointerGetAttributes(&pa, seqs) == cudaSuccess && (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged);
 		(void)cudaGetLastError();
-		if (pinned || n_bases < (1u << 20)) DSB_CUDA(cudaMemcpyAsync(c->seqs.p, seqs, n_bases, cudaMemcpyHostToDevice, st));
+		if (pinned || n_bases < (1u << 20)) DSB_CUDA(cudaMemcpyAsync(I.seqs.p, seqs, n_bases, cudaMemcpyHostToDevice, st));
 		else {
 			if ((rc = stage_ring(c)) != DSB_OK) return rc;
 			// At most DSB_STAGE_CONCURRENCY (3) contexts of a device stage a batch at a time, each with DSB_STAGE_THREADS host threads
@@ -725,7 +746,7 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 					char *stg = (char *)c->h_stage + (size_t)k * DSB_STAGE_BYTES;
 					if (cudaEventSynchronize(c->ev_stage[k]) != cudaSuccess) { trc[t] = DSB_E_CUDA; return; }   // the copy that last used this piece has landed
 					memcpy(stg, seqs + off, nb);
-					if (cudaMemcpyAsync((char *)c->seqs.p + off, stg, nb, cudaMemcpyHostToDevice, st) != cudaSuccess || cudaEventRecord(c->ev_stage[k], st) != cudaSuccess) { trc[t] = DSB_E_CUDA; return; }
+					if (cudaMemcpyAsync((char *)I.seqs.p + off, stg, nb, cudaMemcpyHostToDevice, st) != cudaSuccess || cudaEventRecord(c->ev_stage[k], st) != cudaSuccess) { trc[t] = DSB_E_CUDA; return; }
 				}
 			};
 			const int n_thr = (int)std::min<uint64_t>(DSB_STAGE_THREADS, n_pieces);
@@ -736,11 +757,25 @@ extern "C" int dsb_batch_upload(dsb_ctx *c, const char *seqs, const uint64_t *of
 			for (int t = 0; t < n_thr; t++) if (trc[t] != DSB_OK) { dsb_set_error("staged upload: %s", cudaGetErrorString(cudaGetLastError())); return trc[t]; }
 		}
 	}
-	DSB_CUDA(cudaMemcpyAsync(c->read_off.p, offs, tbl_bytes, cudaMemcpyHostToDevice, st));
+	DSB_CUDA(cudaEventRecord(I.ev_up, st));
+	c->pend = u; c->has_pending = true;
+	return DSB_OK;
+}
+
+// the per-read tables of in[u] -> device, on the compute stream (they are single-buffered: the batch before has finished there)
+static int upload_tables(dsb_ctx *c, BatchIn &I, cudaStream_t st)
+{
+	const uint32_t n_reads = I.n_reads;
+	const size_t tbl_bytes = (size_t)(n_reads + 1) * 8;
+	const uint64_t *h_bin_off = (const uint64_t *)I.h_pin, *h_bits_off = h_bin_off + n_reads + 1, *h_tiles64 = h_bits_off + n_reads + 1;
+	const uint32_t *h_seed_off = (const uint32_t *)(h_tiles64 + I.n_tiles);
+	const uint32_t *h_order = h_seed_off + n_reads + 1;
+	const uint8_t *h_hdr7 = (const uint8_t *)(h_order + n_reads);
+	DSB_CUDA(cudaMemcpyAsync(c->read_off.p, I.h_off.data(), tbl_bytes, cudaMemcpyHostToDevice, st));
 	DSB_CUDA(cudaMemcpyAsync(c->bin_off.p, h_bin_off, tbl_bytes, cudaMemcpyHostToDevice, st));
 	DSB_CUDA(cudaMemcpyAsync(c->bits_off.p, h_bits_off, tbl_bytes, cudaMemcpyHostToDevice, st));
 	DSB_CUDA(cudaMemcpyAsync(c->seed_off.p, h_seed_off, (size_t)(n_reads + 1) * 4, cudaMemcpyHostToDevice, st));
-	if (n_tiles) DSB_CUDA(cudaMemcpyAsync(c->tiles.p, h_tiles, n_tiles * 8, cudaMemcpyHostToDevice, st));
+	if (I.n_tiles) DSB_CUDA(cudaMemcpyAsync(c->tiles.p, h_tiles64, (size_t)I.n_tiles * 8, cudaMemcpyHostToDevice, st));
 	DSB_CUDA(cudaMemcpyAsync(c->order.p, h_order, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
 	DSB_CUDA(cudaMemcpyAsync(c->hdr7.p, h_hdr7, (size_t)n_reads, cudaMemcpyHostToDevice, st));
 	return DSB_OK;
@@ -756,18 +791,32 @@ static int ensure_zeroed(DevBuf &b, size_t bytes, cudaStream_t st)
 	return DSB_OK;
 }
 
+static int run_impl(dsb_ctx *c, int32_t max_read_l_in, bool rerun);
 extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
+{
+	const double t0 = host_now();
+	const int rc = run_impl(c, max_read_l_in, false);
+	if (c) c->host_s[1] += host_now() - t0;
+	return rc;
+}
+static int run_impl(dsb_ctx *c, int32_t max_read_l_in, bool rerun)
 {
 	if (!c) return DSB_E_ARG;
 	DSB_CUDA(cudaSetDevice(c->ix->device));
 	cudaStream_t st = c->stream;
 	c->launches = 0;
 	c->max_read_l_in = max_read_l_in;
+	// the batch uploaded last; without one, the current batch again (re-run after a pool overflow, repeated runs of a resident batch)
+	if (c->has_pending && !rerun) { c->cur = c->pend; c->has_pending = false; }   // (results of the batch before that nobody fetched are dropped)
+	BatchIn &I = c->in[c->cur];
+	c->n_reads = I.n_reads; c->n_tiles = I.n_tiles; c->n_bases = I.n_bases; c->bits_words = I.bits_words; c->seed_slots = I.seed_slots; c->bin_bytes = I.bin_bytes; c->max_len = I.max_len;
 	const uint32_t n = c->n_reads;
-	if (n == 0) { c->ran = true; return DSB_OK; }
+	if (n == 0) { c->ran = true; c->run_pending = true; return DSB_OK; }
 	const ScratchLayout L = scratch_layout(c->opts.max_anchors, c->opts.max_matches);
 	int rc;
 	if ((rc = reserve_run(c, n, c->n_bases, c->bits_words)) != DSB_OK) return rc;
+	DSB_CUDA(cudaStreamWaitEvent(st, I.ev_up, 0));                 // the reads are resident
+	if ((rc = upload_tables(c, I, st)) != DSB_OK) return rc;
 	const bool big_rows = c->ix->dev.n_lines * 128 >= (1ull << 32);
 	DSB_CUDA(cudaMemsetAsync(c->ctl.p, 0, CTL_WORDS * 4, st));
 	DSB_CUDA(cudaMemsetAsync(c->prof.p, 0, (size_t)n * 32, st));
@@ -777,7 +826,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 	DSB_CUDA(cudaEventRecord(c->ev[0], st));
 	if (c->n_tiles) {
 		ProbeParams P;
-		P.ix = c->ix->dev; P.seqs = (const char *)c->seqs.p; P.read_off = (const uint64_t *)c->read_off.p; P.bin_off = (const uint64_t *)c->bin_off.p;
+		P.ix = c->ix->dev; P.seqs = (const char *)I.seqs.p; P.read_off = (const uint64_t *)c->read_off.p; P.bin_off = (const uint64_t *)c->bin_off.p;
 		P.bits_off = (const uint64_t *)c->bits_off.p; P.tiles = (const uint2 *)c->tiles.p; P.hdr7 = (const uint8_t *)c->hdr7.p; P.bin = (uint8_t *)c->bin.p; P.bits = (uint32_t *)c->bits.p;
 		P.pk = (uint64_t *)c->pk.p;
 		k_encode_probe<<<c->n_tiles, PROBE_THREADS, 0, st>>>(P);
@@ -850,7 +899,7 @@ extern "C" int dsb_batch_run(dsb_ctx *c, int32_t max_read_l_in)
 	}
 	DSB_CUDA(cudaEventRecord(c->ev[11], st));
 	DSB_CUDA(cudaGetLastError());
-	c->ran = true;
+	c->ran = true; c->run_pending = true;
 	return DSB_OK;
 }
 
@@ -858,12 +907,21 @@ extern "C" int dsb_batch_sync(dsb_ctx *c)
 {
 	if (!c) return DSB_E_ARG;
 	DSB_CUDA(cudaSetDevice(c->ix->device));
+	DSB_CUDA(cudaStreamSynchronize(c->copy_stream));
 	DSB_CUDA(cudaStreamSynchronize(c->stream));
 	return DSB_OK;
 }
 
 #define DSB_MAX_RETRIES 8
+static int download_impl(dsb_ctx *c, int32_t *max_read_l_out, dsb_read_result *rr, dsb_hit *hits, uint64_t hits_cap, uint64_t *n_hits_out);
 extern "C" int dsb_batch_download(dsb_ctx *c, int32_t *max_read_l_out, dsb_read_result *rr, dsb_hit *hits, uint64_t hits_cap, uint64_t *n_hits_out)
+{
+	const double t0 = host_now();
+	const int rc = download_impl(c, max_read_l_out, rr, hits, hits_cap, n_hits_out);
+	if (c) { c->run_pending = false; c->host_s[2] += host_now() - t0; c->host_s[3] += 1; c->host_s[4] += c->retries; }   // (the results stay on the device until the next run)
+	return rc;
+}
+static int download_impl(dsb_ctx *c, int32_t *max_read_l_out, dsb_read_result *rr, dsb_hit *hits, uint64_t hits_cap, uint64_t *n_hits_out)
 {
 	if (!c || !c->ran) { dsb_set_error("dsb_batch_download: no batch has been run"); return DSB_E_ARG; }
 	DSB_CUDA(cudaSetDevice(c->ix->device));
@@ -884,7 +942,7 @@ extern "C" int dsb_batch_download(dsb_ctx *c, int32_t *max_read_l_out, dsb_read_
 		// double the pools concerned and run the batch again -- its inputs are still resident
 		for (int k = 0; k < 5; k++) if (ovf & (1u << k)) c->grow[k]++;
 		c->retries++;
-		int rc = dsb_batch_run(c, c->max_read_l_in);
+		int rc = run_impl(c, c->max_read_l_in, true);          // (the batch uploaded ahead, if any, keeps waiting)
 		if (rc != DSB_OK) return rc;
 	}
 	{
@@ -911,24 +969,17 @@ extern "C" int dsb_batch_download(dsb_ctx *c, int32_t *max_read_l_out, dsb_read_
 
 extern "C" int dsb_batch_retries(dsb_ctx *c) { return c ? c->retries : 0; }
 
-static double host_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-
 extern "C" int dsb_classify_batch(dsb_ctx *c, const char *seqs, const uint64_t *offs, uint32_t n_reads, int32_t max_read_l_in, int32_t *max_read_l_out,
                                   dsb_read_result *rr, dsb_hit *hits, uint64_t hits_cap, uint64_t *n_hits_out)
 {
 	int rc;
 	if (max_read_l_out) *max_read_l_out = max_read_l_in;
-	const double t0 = host_now();
 	if ((rc = dsb_batch_upload(c, seqs, offs, n_reads)) != DSB_OK) return rc;
-	const double t1 = host_now();
 	if ((rc = dsb_batch_run(c, max_read_l_in)) != DSB_OK) return rc;
-	const double t2 = host_now();
-	rc = dsb_batch_download(c, max_read_l_out, rr, hits, hits_cap, n_hits_out);
-	if (c) { c->host_s[0] += t1 - t0; c->host_s[1] += t2 - t1; c->host_s[2] += host_now() - t2; c->host_s[3] += 1; c->host_s[4] += c->retries; }
-	return rc;
+	return dsb_batch_download(c, max_read_l_out, rr, hits, hits_cap, n_hits_out);
 }
 
-// where the host time of dsb_classify_batch went on this context so far: seconds in upload (layout tables + copies of the reads
+// where the host time of the batch calls went on this context so far: seconds in upload (layout tables + copies of the reads
 // into the stream), run (kernel launches), download (waiting for the batch + result copies); calls; pool-overflow re-runs
 extern "C" int dsb_ctx_host_seconds(dsb_ctx *c, double *out, int cap)
 {
@@ -949,7 +1000,7 @@ extern "C" int dsb_batch_get_seeds(dsb_ctx *c, uint32_t read, int strand, dsb_se
 	if (total_score) *total_score = ts;
 	if (out && n) {
 		if (n > cap) return DSB_E_CAPACITY;
-		DSB_CUDA(cudaMemcpy(out, (dsb_seed *)c->seeds[strand].p + c->h_seed_off[read], (size_t)n * sizeof(dsb_seed), cudaMemcpyDeviceToHost));
+		DSB_CUDA(cudaMemcpy(out, (dsb_seed *)c->seeds[strand].p + c->in[c->cur].h_seed_off[read], (size_t)n * sizeof(dsb_seed), cudaMemcpyDeviceToHost));
 	}
 	return DSB_OK;
 }

@@ -33,15 +33,32 @@ struct DevBuf {                         // grow-only device buffer
 #define DSB_N_KERNELS 11               // timed kernel groups of one dsb_batch_run
 #define DSB_N_EV (DSB_N_KERNELS + 4)   // kernel boundaries + 2 user marks + start of the upload
 
+// One uploaded batch: its reads in HBM, the per-read layout tables (pinned host memory, copied to the device when the batch is
+// run) and its sizes.  A context has two, so that dsb_batch_upload of the NEXT batch may run -- on a stream of its own -- while
+// the kernels of the current one are still busy (include/desamba_b200.h).
+struct BatchIn {
+	DevBuf seqs;
+	void *h_pin = nullptr; size_t h_pin_cap = 0;
+	uint32_t n_reads = 0, n_tiles = 0, max_len = 0; uint64_t n_bases = 0, bits_words = 0, seed_slots = 0, bin_bytes = 0;
+	std::vector<uint64_t> h_off;        // host copies of the per-read offset tables
+	std::vector<uint64_t> h_bits_off;
+	std::vector<uint32_t> h_seed_off;
+	cudaEvent_t ev_up = nullptr;        // the reads have landed in `seqs`
+};
+
 struct dsb_ctx {
 	dsb_index *ix;
 	dsb_opts opts;
 	cudaStream_t stream;
+	cudaStream_t copy_stream;           // uploads of the reads
+	BatchIn in[2]; int cur = 0, pend = 0;
+	bool has_pending = false;           // in[pend] is uploaded and waits for dsb_batch_run
+	bool run_pending = false;           // in[cur] has been run and not yet downloaded
 	int n_sm, n_warps;                  // resident classify warps = n_sm * warps_per_sm
 	int seed_blocks;                    // grid of k_seed (persistent, SEED_WARPS_PER_SM warps per SM)
 	int heavy_blocks;                   // CTAs of k_score_heavy
 	// batch inputs (device)
-	DevBuf seqs, read_off, bin_off, bits_off, seed_off, tiles, bin, bits, seeds[2], n_seeds[2], total_score[2];
+	DevBuf read_off, bin_off, bits_off, seed_off, tiles, bin, bits, seeds[2], n_seeds[2], total_score[2];
 	// classify scratch + outputs
 	DevBuf scratch, rr, hits, counters, prof, work, anc_pool, chain_pool, lists[4], ctl, order, hdr7;
 	// seeding: packed forward strands, task lists (ping-pong), per-task records, staging chunks, per-lane memory of k_seed
@@ -53,15 +70,11 @@ struct dsb_ctx {
 	double host_s[5] = {0, 0, 0, 0, 0};  // dsb_ctx_host_seconds
 	uint64_t scratch_stride;
 	uint64_t hits_cap;
-	// pinned staging: per-read tables of the upload; ring of two chunks for reads that arrive in pageable memory
-	void *h_pin; size_t h_pin_cap;
+	// pinned ring for reads that arrive in pageable memory
 	void *h_stage; cudaEvent_t ev_stage[2 * DSB_STAGE_THREADS];
 	// batch state
 	uint32_t m_bin_read;                // capacity of the reference's bin_read buffer after the batches seen so far (policy P3)
-	uint32_t n_reads, n_tiles; uint64_t n_bases, bits_words, seed_slots, bin_bytes; uint32_t max_len;
-	std::vector<uint64_t> h_off;        // host copies of the per-read offset tables
-	std::vector<uint64_t> h_bits_off;
-	std::vector<uint32_t> h_seed_off;
+	uint32_t n_reads, n_tiles; uint64_t n_bases, bits_words, seed_slots, bin_bytes; uint32_t max_len;   // of the batch last run (in[cur])
 	std::vector<uint32_t> h_len_first;  // counting sort of the reads by length (work order)
 	cudaEvent_t ev[DSB_N_EV];
 	int launches;

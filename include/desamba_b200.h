@@ -107,6 +107,11 @@ int  dsb_ctx_reserve(dsb_ctx *ctx, uint32_t max_reads, uint64_t max_bases);
  *
  * dsb_classify_batch      = upload + run + download with HOST buffers (the end-to-end call).
  * dsb_batch_upload/run/download = the same three steps separately (run works on inputs resident in HBM).
+ * A context holds two input sets: dsb_batch_upload of the NEXT batch may be called while the batch run before is still on the
+ * GPU (after its dsb_batch_run, before its dsb_batch_download) -- its reads then travel on a copy stream of their own under the
+ * running kernels.  The order per context is  upload(k+1); download(k); run(k+1)  -- one batch ahead, never two; the
+ * results of batch k stay readable until run(k+1).  (kt_pipeline's step 0 reading the next batch while step 1 classifies,
+ * cly_mt.c:369-398.)
  */
 int dsb_classify_batch(dsb_ctx *ctx, const char *seqs, const uint64_t *offs, uint32_t n_reads,
                        int32_t max_read_l_in, int32_t *max_read_l_out,
