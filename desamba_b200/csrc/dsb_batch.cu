@@ -717,7 +717,9 @@ static int upload_impl(dsb_ctx *c, const char *seqs, const uint64_t *offs, uint3
 	I.h_bits_off.assign(h_bits_off, h_bits_off + n_reads + 1);
 	I.h_seed_off.assign(h_seed_off, h_seed_off + n_reads + 1);
 	I.h_off.assign(offs, offs + n_reads + 1);
-	if ((rc = reserve_upload(c, I, n_reads, n_bases, n_tiles, bo, wo, so)) != DSB_OK) return rc;   // (a buffer that grows is freed first: cudaFree waits for the batch in flight)
+	// only the reads' own buffer here: the tables and work buffers of the context may still hold the batch in flight and its
+	// results -- they are sized when this batch is run (run_impl)
+	if ((rc = ensure(I.seqs, n_bases + 16)) != DSB_OK) return rc;
 	cudaStream_t st = c->copy_stream;
 	{	// the reads: straight from the caller's buffer when it is page-locked, else through the context's pinned staging ring (the
 		// runtime's own path for pageable memory serialises the copies of all contexts of a process)
@@ -814,6 +816,7 @@ static int run_impl(dsb_ctx *c, int32_t max_read_l_in, bool rerun)
 	if (n == 0) { c->ran = true; c->run_pending = true; return DSB_OK; }
 	const ScratchLayout L = scratch_layout(c->opts.max_anchors, c->opts.max_matches);
 	int rc;
+	if ((rc = reserve_upload(c, I, n, I.n_bases, I.n_tiles, I.bin_bytes, I.bits_words, I.seed_slots)) != DSB_OK) return rc;
 	if ((rc = reserve_run(c, n, c->n_bases, c->bits_words)) != DSB_OK) return rc;
 	DSB_CUDA(cudaStreamWaitEvent(st, I.ev_up, 0));                 // the reads are resident
 	if ((rc = upload_tables(c, I, st)) != DSB_OK) return rc;

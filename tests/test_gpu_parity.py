@@ -410,3 +410,45 @@ def test_gather_microbenchmark(gpu):
     dsb, _, _ = gpu
     gbs, ms = dsb.gather_bench(0, 2 << 30, 1 << 26, 1)
     assert 100 < gbs < 20000 and ms > 0
+
+
+def test_next_batch_uploaded_while_the_current_one_runs(gpu, ob):
+    """dsb_batch_upload of batch k + 1 before dsb_batch_download of batch k (two input sets per context, copy stream): the
+    records equal those of the blocking call, batch after batch, also when a batch is run twice or comes empty"""
+    dsb, ix, ctx = gpu
+    sets = []
+    for name in ("long10", "short1", "long30"):
+        _, seqs, _ = ob.read_fastq(_set_path(ob, name))
+        cat, offs = ob.pack(seqs[:2000])
+        sets.append((np.ascontiguousarray(cat, dtype=np.uint8), np.ascontiguousarray(offs, dtype=np.uint64)))
+    want = [ctx.classify(cat, offs, 10**6) for cat, offs in sets]
+    c2 = dsb.Context(ix)
+    order = [0, 1, 2, 1, 0, 0, 2]
+    got = []
+    cur = None
+    for k in order + [None]:
+        if k is not None:
+            c2.upload_async(sets[k][0], sets[k][1])             # (while batch `cur` is still on the GPU)
+        if cur is not None:
+            n = len(sets[cur][1]) - 1
+            rr = np.zeros(n, dtype=dsb.RR_DTYPE); hits = np.zeros(24 * n + 4096, dtype=dsb.HIT_DTYPE)
+            used, _ = c2.download_into(rr, hits)
+            got.append((cur, rr, hits[:used]))
+        if k is not None:
+            c2.run(10**6)
+        cur = k
+    assert [g[0] for g in got] == order
+    for k, rr, hits in got:
+        assert ob.compare_results(rr, hits, want[k].rr, want[k].hits, None, max_report=3) == [], k
+    # the blocking call on the same context afterwards, and a second upload without a run in between is refused
+    res = c2.classify(sets[1][0], sets[1][1], 10**6)
+    assert ob.compare_results(res.rr, res.hits, want[1].rr, want[1].hits, None, max_report=3) == []
+    c2.upload_async(sets[0][0], sets[0][1])
+    with pytest.raises(dsb.DsbError):
+        c2.upload_async(sets[2][0], sets[2][1])
+    c2.run(10**6)
+    n = len(sets[0][1]) - 1
+    rr = np.zeros(n, dtype=dsb.RR_DTYPE); hits = np.zeros(24 * n + 4096, dtype=dsb.HIT_DTYPE)
+    used, _ = c2.download_into(rr, hits)
+    assert ob.compare_results(rr, hits[:used], want[0].rr, want[0].hits, None, max_report=3) == []
+    c2.close()
