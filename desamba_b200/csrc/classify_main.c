@@ -226,26 +226,52 @@ static int slot_add_block(shared_t *sh, slot_t *b, const char *map, const fq_rec
 static uint64_t g_fq_block = (uint64_t)256 << 20;   /* bytes of a plain FASTQ file indexed at a time (DSB_FQ_BLOCK_MB: tests use small blocks) */
 #define FQ_BLOCK g_fq_block
 #define FQ_MARGIN ((uint64_t)16 << 20)     /* read beyond the block: the records that start in it must be complete */
-/* Block input.  Default: pread by the helper threads into one of two reusable buffers, the next block by a read-ahead thread
- * while the records of the current one are copied into batches.  DSB_FQ_MMAP=1 maps the block instead (MAP_POPULATE, one call
- * for the whole block: no copy into a buffer of our own) -- measured no faster on tmpfs (host-only pipeline 1.91 s against
- * 1.76 s for 32 GB of FASTQ), kept as an option for inputs in the page cache of a real file system. */
-static int g_fq_mmap = 0;
+/* Block input.  Default: the block is MAPPED -- the page-cache / tmpfs pages themselves, no copy into a buffer of our own -- by
+ * the read-ahead thread while the records of the current block are copied into batches; the helper threads fill in its page
+ * tables, a share each (one thread populating alone was as slow as the copy it replaces), and the read-ahead thread also unmaps
+ * the block before.  Measured on the 16-core box, 32 GB of FASTQ in tmpfs: reader 1.78 s against 2.00 s with pread under GPU
+ * load, 1.45-1.49 s against 1.53-1.56 s alone.  DSB_FQ_MMAP=0 (or a failed mmap) reads the block with pread into one of two
+ * reusable buffers instead (an input file that is truncated while it is mapped ends the run with SIGBUS). */
+static int g_fq_mmap = 1;
 typedef struct { const char *map; void *mbase; size_t mlen; int rc; } block_t;     /* map[file offset] for the offsets of the block */
-typedef struct { int fd, n_thr, active; uint64_t pos, len; char *buf; block_t blk; pthread_t th; } prefetch_t;
+typedef struct { int fd, n_thr, active; uint64_t pos, len; char *buf; block_t blk, old; pthread_t th; } prefetch_t;   /* old: the block before, unmapped by the read-ahead thread */
+typedef struct { char *p; size_t len; } populate_job_t;
+static void *populate_thread(void *a)
+{
+	populate_job_t *j = (populate_job_t *)a;
+#ifdef MADV_POPULATE_READ
+	if (madvise(j->p, j->len, MADV_POPULATE_READ) == 0) return NULL;
+#endif
+	volatile char sink = 0;
+	for (size_t i = 0; i < j->len; i += 4096) sink += j->p[i];       /* older kernels: a read fault per page */
+	(void)sink;
+	return NULL;
+}
 static void block_get(int fd, uint64_t pos, uint64_t len, char *buf, int n_thr, block_t *o)
 {
 	o->map = NULL; o->mbase = NULL; o->mlen = 0; o->rc = -1;
 	if (g_fq_mmap) {
 		const uint64_t moff = pos & ~(uint64_t)4095;
 		const size_t mlen = (size_t)(pos + len - moff);
-		void *m = mmap(NULL, mlen, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, (off_t)moff);
-		if (m != MAP_FAILED) { o->mbase = m; o->mlen = mlen; o->map = (const char *)m - moff; o->rc = 0; return; }
+		void *m = mmap(NULL, mlen, PROT_READ, MAP_PRIVATE, fd, (off_t)moff);
+		if (m != MAP_FAILED) {
+			/* page tables of the block filled in by the helper threads, a share each (one thread populating alone was as slow as
+			 * the copy it replaces) */
+			populate_job_t job[64]; pthread_t th[64];
+			int n = n_thr < 1 ? 1 : n_thr > 64 ? 64 : n_thr;
+			const size_t span = ((mlen + n - 1) / n + 4095) & ~(size_t)4095;
+			int k = 0;
+			for (size_t at = 0; at < mlen && k < 64; at += span, k++) { job[k].p = (char *)m + at; job[k].len = at + span <= mlen ? span : mlen - at; }
+			for (int t = 1; t < k; t++) pthread_create(&th[t], NULL, populate_thread, &job[t]);
+			populate_thread(&job[0]);
+			for (int t = 1; t < k; t++) pthread_join(th[t], NULL);
+			o->mbase = m; o->mlen = mlen; o->map = (const char *)m - moff; o->rc = 0; return;
+		}
 	}
 	if (buf && fq_read_block(fd, pos, len, buf, n_thr) == 0) { o->map = buf - pos; o->rc = 0; }
 }
 static void block_release(block_t *b) { if (b->mbase) munmap(b->mbase, b->mlen); b->mbase = NULL; b->map = NULL; b->mlen = 0; }
-static void *prefetch_main(void *a) { prefetch_t *p = (prefetch_t *)a; block_get(p->fd, p->pos, p->len, p->buf, p->n_thr, &p->blk); return NULL; }
+static void *prefetch_main(void *a) { prefetch_t *p = (prefetch_t *)a; block_get(p->fd, p->pos, p->len, p->buf, p->n_thr, &p->blk); block_release(&p->old); return NULL; }
 static void *reader_main(void *arg)
 {
 	shared_t *sh = (shared_t *)arg; opts_t *o = sh->o;
@@ -257,7 +283,7 @@ static void *reader_main(void *arg)
 	/* plain 4-line FASTQ: read and indexed a block at a time by the helper threads (fastq_reader.h) */
 	const char *map = NULL; uint64_t map_size = 0, map_pos = 0;           /* map = blockbuf - (offset of the block): file offsets index it */
 	char *blockbuf2[2] = {NULL, NULL}; int cur_buf = 0;      /* pread mode: two reusable buffers */
-	block_t cur; memset(&cur, 0, sizeof cur);
+	block_t cur, stale; memset(&cur, 0, sizeof cur); memset(&stale, 0, sizeof stale);
 	int par_file = 0;                                         /* the open file goes through the parallel indexer */
 	prefetch_t pf; memset(&pf, 0, sizeof pf);
 	fq_list_t lists[64]; memset(lists, 0, sizeof lists);
@@ -290,7 +316,8 @@ static void *reader_main(void *arg)
 					i_rec = e;
 					continue;
 				}
-				block_release(&cur); map = NULL;
+				if (cur.mbase) { block_release(&stale); stale = cur; memset(&cur, 0, sizeof cur); } else block_release(&cur);   /* a mapping is unmapped by the next read-ahead */
+				map = NULL;
 				if (map_pos < map_size) {               /* next block */
 					uint64_t next = map_pos;
 					const uint64_t len = (map_size - map_pos < FQ_BLOCK + FQ_MARGIN) ? map_size - map_pos : FQ_BLOCK + FQ_MARGIN;
@@ -314,7 +341,8 @@ static void *reader_main(void *arg)
 							pf.fd = st.fd; pf.n_thr = n_thr; pf.pos = next; pf.buf = blockbuf2[cur_buf ^ 1];
 							pf.len = (map_size - next < FQ_BLOCK + FQ_MARGIN) ? map_size - next : FQ_BLOCK + FQ_MARGIN;
 							memset(&pf.blk, 0, sizeof pf.blk);
-							if (pthread_create(&pf.th, NULL, prefetch_main, &pf) == 0) pf.active = 1;
+							pf.old = stale; memset(&stale, 0, sizeof stale);
+							if (pthread_create(&pf.th, NULL, prefetch_main, &pf) == 0) pf.active = 1; else block_release(&pf.old);
 						}
 						continue;
 					}
@@ -381,7 +409,7 @@ static void *reader_main(void *arg)
 		if (end_of_input) break;
 	}
 	if (pf.active) { pthread_join(pf.th, NULL); block_release(&pf.blk); }
-	block_release(&cur);
+	block_release(&cur); block_release(&stale);
 	free(blockbuf2[0]); free(blockbuf2[1]);
 	for (int t = 0; t < 64; t++) free(lists[t].r);
 	free(recs);
