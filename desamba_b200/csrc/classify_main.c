@@ -127,7 +127,8 @@ static void fail(shared_t *sh, const char *what, int rc)
 /* batch buffers grow by doubling from 32 MB, and from 128 MB straight to `full` (the batch limit) */
 /* The batch buffers are ordinary (huge-page) memory by default: cudaHostAlloc costs ~1 s per GB on an 8-GPU box (19 allocations
  * = 6.9 s for a 4 GB input, more than reading, classifying and writing it), and the H2D copy of a batch from pageable memory
- * was not slower in the driver (3 contexts per GPU overlap it).  DSB_PINNED=1 pins them (long multi-GPU runs). */
+ * goes through the library's pinned staging ring (three threads per batch, the next batch while the current one runs).
+ * DSB_PINNED=1 pins them (long multi-GPU runs). */
 static double g_t_pinned = 0; static int g_n_pinned = 0; static int g_pageable = 1, g_register = 0, g_host_only = 0;
 static int grow_pinned(void **p, size_t *m, size_t need, size_t keep, size_t full)
 {
@@ -576,7 +577,7 @@ static void usage(void)
 	fprintf(stderr, "    -l, INT         minimum matching length, ignored for NGS reads [170]\n    -r, INT         max Output number of secondary alignments[5]\n");
 	fprintf(stderr, "    -o, FILE        output results into file [stdout]\n    -s, INT         MIN score[64]\n");
 	fprintf(stderr, "    -f, STR         output format, one of: SAM (default), SAM_FULL, DES, DES_FULL\n");
-	fprintf(stderr, "    -g, INT         number of GPUs [all visible]\n    -c, INT         batches in flight per GPU [3]\n    -B, INT         reads per batch [262144]\n    -M, INT         Mbases per batch [512]\n    -P, INT         FASTQ reader threads [cores - 6; 0: serial]\n");
+	fprintf(stderr, "    -g, INT         number of GPUs [all visible]\n    -c, INT         batches in flight per GPU [up to 6, as HBM allows]\n    -B, INT         reads per batch [262144]\n    -M, INT         Mbases per batch [512]\n    -P, INT         FASTQ reader threads [cores - 6; 0: serial]\n");
 	fprintf(stderr, "    -A, INT         anchors kept per read [16384]\n    -m, INT         9-mer matches kept per extension [16384]\n    -L, INT         longest read accepted [1048576]\n    -p, INT         size of the per-batch device pools in %% of the built-in sizing [100]\n\n");
 }
 
@@ -639,7 +640,7 @@ static int classify_main(int argc, char **argv)
 	if (getenv("DSB_FQ_BLOCK_KB") && atol(getenv("DSB_FQ_BLOCK_KB")) >= 1 && atol(getenv("DSB_FQ_BLOCK_KB")) <= (256 << 10)) g_fq_block = (uint64_t)atol(getenv("DSB_FQ_BLOCK_KB")) << 10;   /* tests */
 	const double t_start = now_s();
 	#define STAMP(what) do { if (verbose) fprintf(stderr, "[deSAMBA-b200] %-34s at %7.3f s\n", what, now_s() - t_start); } while (0)
-	/* the reader starts at once: the first batches are parsed into pinned memory while the index is loaded into HBM */
+	/* the reader starts at once: the first batches are parsed while the index is loaded into HBM */
 	shared_t sh; memset(&sh, 0, sizeof sh);
 	sh.o = &o; sh.n_slots = 2 * ((o.n_gpus > 0 ? o.n_gpus : 8) * o.ctx_per_gpu) + 2; sh.slot = xcalloc(sh.n_slots, sizeof(slot_t)); sh.bo = xcalloc(sh.n_slots, sizeof(bo_slot)); sh.free_set = xcalloc(sh.n_slots + 1, sizeof(bufset_t));
 	sh.max_ahead = getenv("DSB_READ_AHEAD") ? atoi(getenv("DSB_READ_AHEAD")) : 3;   /* batches filled while the index loads: few -- faulting fresh buffers in from a dozen threads slows the
