@@ -15,6 +15,9 @@
 #include <cstring>
 #include <algorithm>
 #include <chrono>
+#include <mutex>
+#include <condition_variable>
+#include <thread>
 
 #define PROBE_TILE 1024
 #define PROBE_THREADS 256
@@ -622,9 +625,6 @@ extern "C" int dsb_ctx_reserve(dsb_ctx *c, uint32_t max_reads, uint64_t max_base
 static double host_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // counting gate per device for the staged (pageable) upload path
-#include <mutex>
-#include <condition_variable>
-#include <thread>
 struct StageGate {
 	static constexpr int MAX_DEV = 64;
 	static std::mutex mu; static std::condition_variable cv; static int busy[MAX_DEV]; static int limit;
