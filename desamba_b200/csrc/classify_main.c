@@ -605,35 +605,13 @@ static void usage(void)
 	fprintf(stderr, "    -A, INT         anchors kept per read [16384]\n    -m, INT         9-mer matches kept per extension [16384]\n    -L, INT         longest read accepted [1048576]\n    -p, INT         size of the per-batch device pools in %% of the built-in sizing [100]\n\n");
 }
 
-/* A share of a batch's text: formatted by a helper thread, then -- when the output is a regular file -- written by the same
- * thread at its own offset (pwrite) as soon as all shares have announced their sizes; the text of 20 M short reads is 1.4 GB,
- * and one thread copying it into the page cache was a third of the writer's time. */
-typedef struct fmt_job {
-	const opts_t *o; const dsb_ref_info *ri; slot_t *b; uint32_t r0, r1; obuf_t ob;
-	struct fmt_job *all; int idx, n_jobs; int fd; off_t base;       /* fd < 0: the main thread writes the shares in order */
-	pthread_mutex_t *mu; pthread_cond_t *cv; int *n_sized; int rc;
-} fmt_job_t;
+typedef struct { const opts_t *o; const dsb_ref_info *ri; slot_t *b; uint32_t r0, r1; obuf_t ob; } fmt_job_t;
 static void *fmt_thread(void *a)
 {
 	fmt_job_t *j = (fmt_job_t *)a; slot_t *b = j->b;
-	j->ob.n = 0; j->rc = 0;
 	for (uint32_t r = j->r0; r < j->r1; r++) {
 		const uint32_t L = (uint32_t)(b->offs[r + 1] - b->offs[r]);
 		format_read(&j->ob, j->o, j->ri, b->rr + r, b->hits, b->names + b->name_off[r], b->seqs + b->offs[r], b->quals ? b->quals + b->offs[r] : NULL, L);
-	}
-	if (j->fd < 0) return NULL;
-	pthread_mutex_lock(j->mu);
-	(*j->n_sized)++;
-	pthread_cond_broadcast(j->cv);
-	while (*j->n_sized < j->n_jobs) pthread_cond_wait(j->cv, j->mu);
-	pthread_mutex_unlock(j->mu);
-	off_t at = j->base;
-	for (int t = 0; t < j->idx; t++) at += (off_t)j->all[t].ob.n;
-	size_t done = 0;
-	while (done < j->ob.n) {
-		const ssize_t w = pwrite(j->fd, j->ob.s + done, j->ob.n - done, at + (off_t)done);
-		if (w <= 0) { j->rc = -1; break; }
-		done += (size_t)w;
 	}
 	return NULL;
 }
@@ -762,12 +740,6 @@ static int classify_main(int argc, char **argv)
 	/* the text of a batch is formatted by helper threads (contiguous shares of the batch's reads, written in order) */
 	const int n_fmt = o.n_parse_threads > 1 ? (o.n_parse_threads > 16 ? 16 : o.n_parse_threads) : 1;
 	fmt_job_t fj[16]; memset(fj, 0, sizeof fj);
-	pthread_mutex_t fmt_mu; pthread_cond_t fmt_cv; pthread_mutex_init(&fmt_mu, NULL); pthread_cond_init(&fmt_cv, NULL);
-	int out_fd = -1;                                         /* >= 0: the output is a regular file, the shares of a batch's text are written in parallel */
-	{	/* (not for a file opened for appending: pwrite ignores its offset there) */
-		struct stat osb; const int fl = fcntl(fileno(o.out), F_GETFL);
-		if (!getenv("DSB_SERIAL_WRITE") && fstat(fileno(o.out), &osb) == 0 && S_ISREG(osb.st_mode) && fl >= 0 && !(fl & O_APPEND)) out_fd = fileno(o.out);
-	}
 	obuf_t ob = {0};
 	for (;;) {
 		const double tq0 = now_s();
@@ -781,24 +753,14 @@ static int classify_main(int argc, char **argv)
 		sh.t_writer_wait += tq1 - tq0;
 		if (n_fmt > 1 && b->n_reads >= 4096) {
 			pthread_t ft[16];
-			int n_sized = 0;
-			off_t base = -1;
-			if (out_fd >= 0) { fflush(o.out); base = ftello(o.out); }
 			for (int t = 0; t < n_fmt; t++) {
 				fj[t].o = &o; fj[t].ri = ri; fj[t].b = b; fj[t].ob.n = 0;
 				fj[t].r0 = (uint32_t)((uint64_t)b->n_reads * t / n_fmt); fj[t].r1 = (uint32_t)((uint64_t)b->n_reads * (t + 1) / n_fmt);
-				fj[t].all = fj; fj[t].idx = t; fj[t].n_jobs = n_fmt; fj[t].fd = base >= 0 ? out_fd : -1; fj[t].base = base;
-				fj[t].mu = &fmt_mu; fj[t].cv = &fmt_cv; fj[t].n_sized = &n_sized;
 			}
 			for (int t = 1; t < n_fmt; t++) pthread_create(&ft[t], NULL, fmt_thread, &fj[t]);
 			fmt_thread(&fj[0]);
 			for (int t = 1; t < n_fmt; t++) pthread_join(ft[t], NULL);
-			if (fj[0].fd >= 0) {                            /* the shares are in the file: move the stream behind them */
-				off_t total = 0; int bad = 0;
-				for (int t = 0; t < n_fmt; t++) { total += (off_t)fj[t].ob.n; bad |= fj[t].rc; }
-				if (bad || fseeko(o.out, base + total, SEEK_SET) != 0) fail(&sh, "writing the output", -2);
-			} else
-				for (int t = 0; t < n_fmt; t++) fwrite(fj[t].ob.s, 1, fj[t].ob.n, o.out);
+			for (int t = 0; t < n_fmt; t++) fwrite(fj[t].ob.s, 1, fj[t].ob.n, o.out);
 		} else {
 			ob.n = 0;
 			for (uint32_t r = 0; r < b->n_reads; r++) {

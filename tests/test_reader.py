@@ -160,28 +160,8 @@ def test_driver_host_pipeline_falls_back_inside_a_file(ob, tmp_path):
         assert got == want_des + want_des, env
 
 
-def test_driver_text_written_in_parallel_shares(ob, tmp_path):
-    """batches of >= 4096 reads are formatted by helper threads that write their shares of the text at their own offsets of a
-    regular output file; the file equals the serially written one, batch after batch, also after a small (serially written) batch"""
-    rng = np.random.default_rng(13)
-    recs = _records(rng, 23000, 30, 200, b"p")
-    p = str(tmp_path / "many.fq")
-    open(p, "wb").write(_fastq(recs))
-    want = b"".join(n + b"\t4\t*\t0\t0\t*\t*\t0\t0\t" + s + b"\t" + q + b"\t\n" for n, s, q in recs)
-    small = str(tmp_path / "few.fq")
-    open(small, "wb").write(_fastq(recs[:100]))
-    want_small = b"".join(n + b"\t4\t*\t0\t0\t*\t*\t0\t0\t" + s + b"\t" + q + b"\t\n" for n, s, q in recs[:100])
-    for env, opts in (({}, ("-B", 5000, "-P", 4)), ({"DSB_SERIAL_WRITE": "1"}, ("-B", 5000, "-P", 4)), ({}, ("-B", 9000, "-P", 16)), ({}, ("-B", 4096, "-P", 2))):
-        got, _ = _host_only(tmp_path, [small, p, small, p], "SAM_FULL", env, *opts)
-        assert got == want_small + want + want_small + want, (env, opts)
-    # to a pipe (not a regular file): the shares go out through the stream, in order
-    e = dict(os.environ, DSB_HOST_ONLY="1")
-    r = subprocess.run([DRIVER, "classify", "-f", "SAM_FULL", "-B", "5000", "-P", "4", "no_index_needed", p], capture_output=True, env=e)
-    assert r.returncode == 0 and r.stdout == want
-
-
 def test_driver_text_appended_to_a_file_stays_in_order(ob, tmp_path):
-    """stdout redirected with >> (O_APPEND): the parallel writer must not be used -- pwrite ignores its offset there"""
+    """stdout redirected with >> or > behind existing bytes of a regular file: the text lands behind them, in order"""
     rng = np.random.default_rng(14)
     recs = _records(rng, 12000, 30, 120, b"q")
     p = str(tmp_path / "app.fq")
@@ -194,10 +174,29 @@ def test_driver_text_appended_to_a_file_stays_in_order(ob, tmp_path):
                            env=dict(os.environ, DSB_HOST_ONLY="1"))
     assert r.returncode == 0, r.stderr.decode()[-300:]
     assert open(out, "rb").read() == b"header line\n" + want
-    # redirected with > at a non-zero offset of a regular file: shares land behind what is already there
+    # redirected with > at a non-zero offset of a regular file
     with open(out, "wb") as f:
         f.write(b"header line\n"); f.flush()
         r = subprocess.run([DRIVER, "classify", "-f", "SAM_FULL", "-B", "5000", "-P", "4", "no_index_needed", p], stdout=f, stderr=subprocess.PIPE,
                            env=dict(os.environ, DSB_HOST_ONLY="1"))
     assert r.returncode == 0
     assert open(out, "rb").read() == b"header line\n" + want
+
+
+def test_driver_text_of_large_batches_formatted_by_helper_threads(ob, tmp_path):
+    """batches of >= 4096 reads are formatted in shares by helper threads; the text is that of the serial writer, batch after
+    batch, to a file and to a pipe, also after a small (serially formatted) batch"""
+    rng = np.random.default_rng(13)
+    recs = _records(rng, 23000, 30, 200, b"p")
+    p = str(tmp_path / "many.fq")
+    open(p, "wb").write(_fastq(recs))
+    want = b"".join(n + b"\t4\t*\t0\t0\t*\t*\t0\t0\t" + s + b"\t" + q + b"\t\n" for n, s, q in recs)
+    small = str(tmp_path / "few.fq")
+    open(small, "wb").write(_fastq(recs[:100]))
+    want_small = b"".join(n + b"\t4\t*\t0\t0\t*\t*\t0\t0\t" + s + b"\t" + q + b"\t\n" for n, s, q in recs[:100])
+    for opts in (("-B", 5000, "-P", 4), ("-B", 9000, "-P", 16), ("-B", 4096, "-P", 2)):
+        got, _ = _host_only(tmp_path, [small, p, small, p], "SAM_FULL", {}, *opts)
+        assert got == want_small + want + want_small + want, opts
+    r = subprocess.run([DRIVER, "classify", "-f", "SAM_FULL", "-B", "5000", "-P", "4", "no_index_needed", p], capture_output=True,
+                       env=dict(os.environ, DSB_HOST_ONLY="1"))
+    assert r.returncode == 0 and r.stdout == want
