@@ -276,7 +276,14 @@ static void *prefetch_main(void *a) { prefetch_t *p = (prefetch_t *)a; block_get
 static void *reader_main(void *arg)
 {
 	shared_t *sh = (shared_t *)arg; opts_t *o = sh->o;
-	stream_t st; memset(&st, 0, sizeof st); st.buf = xrealloc(NULL, SBUF);
+	stream_t st; memset(&st, 0, sizeof st); st.buf = xrealloc(NULL, SBUF); st.own_buf = st.buf;
+	/* .gz files of the command line are inflated ahead by threads of their own (fastq_reader.h): the one being parsed and the
+	 * next GZ_AHEAD - 1 */
+	gzq_t **gzq = xcalloc(sh->n_files, sizeof *gzq);
+	int gz_next = 0;                                   /* files below gz_next have been looked at */
+	/* inflating a file takes ~4 x as long as parsing it: 8 in flight hide it (measured on 16 files: 2.1 s with one stream, 1.7 s
+	 * with 4 ahead, 0.5 - 0.65 s with 8); each queue holds at most 128 MB */
+	const int gz_ahead = getenv("DSB_GZ_AHEAD") ? atoi(getenv("DSB_GZ_AHEAD")) : (o->n_parse_threads > 0 ? 8 : 0);
 	rec_t rec; memset(&rec, 0, sizeof rec);
 	int file_i = 0, stream_open = 0, pending = 0;      /* pending: rec holds a record not yet stored */
 	uint32_t m_bin_read = 0;                           /* running BUFF_REALLOC capacity over all reads, in input order */
@@ -362,15 +369,28 @@ static void *reader_main(void *arg)
 			if (!pending) {
 				if (!stream_open) {
 					if (file_i >= sh->n_files) { end_of_input = 1; break; }
-					st.fp = NULL;
-					st.fd = open(sh->files[file_i], O_RDONLY);
-					if (st.fd < 0) { fprintf(stderr, "[xzopen] fail to open file '%s'\n", sh->files[file_i]); fail(sh, "open reads", -2); end_of_input = 1; break; }
+					/* start inflating the .gz files among this one and the next gz_ahead - 1 */
+					if (gz_next < file_i) gz_next = file_i;
+					for (; gz_ahead > 0 && gz_next < sh->n_files && gz_next < file_i + gz_ahead; gz_next++) {
+						const int fd2 = open(sh->files[gz_next], O_RDONLY);
+						if (fd2 < 0) continue;                 /* (reported when its turn comes) */
+						unsigned char mg[2] = {0, 0};
+						if (pread(fd2, mg, 2, 0) == 2 && mg[0] == 0x1f && mg[1] == 0x8b) gzq[gz_next] = gzq_start(fd2);
+						if (!gzq[gz_next]) close(fd2);
+					}
+					st.fp = NULL; st.q = NULL;
 					unsigned char magic[2] = {0, 0};
-					const int got = (int)pread(st.fd, magic, 2, 0);
-					if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
-						st.fp = gzdopen(st.fd, "r");
-						if (!st.fp) { fail(sh, "gzdopen", -2); end_of_input = 1; break; }
-						gzbuffer(st.fp, 1 << 20);
+					int got = 0;
+					if (gzq[file_i]) { st.q = gzq[file_i]; gzq[file_i] = NULL; st.fd = -1; magic[0] = 0x1f; magic[1] = 0x8b; got = 2; }
+					else {
+						st.fd = open(sh->files[file_i], O_RDONLY);
+						if (st.fd < 0) { fprintf(stderr, "[xzopen] fail to open file '%s'\n", sh->files[file_i]); fail(sh, "open reads", -2); end_of_input = 1; break; }
+						got = (int)pread(st.fd, magic, 2, 0);
+						if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+							st.fp = gzdopen(st.fd, "r");
+							if (!st.fp) { fail(sh, "gzdopen", -2); end_of_input = 1; break; }
+							gzbuffer(st.fp, 1 << 20);
+						}
 					}
 					st.need_qual = (o->fmt == FMT_SAM_FULL);
 					st.n = st.pos = st.eof = 0; st.last_char = 0; stream_open = 1;
@@ -379,7 +399,7 @@ static void *reader_main(void *arg)
 					else { const size_t l = strlen(sh->early_msg); snprintf(sh->early_msg + l, sizeof sh->early_msg - l, "Processing file: [%s].\n", sh->files[file_i]); }
 					pthread_mutex_unlock(&sh->mu);
 					struct stat sb;
-					if (!st.fp && n_thr > 0 && got >= 1 && magic[0] == '@' && fstat(st.fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+					if (!st.fp && !st.q && n_thr > 0 && got >= 1 && magic[0] == '@' && fstat(st.fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
 						if (!g_fq_mmap && !blockbuf2[0]) { blockbuf2[0] = malloc(((uint64_t)256 << 20) + FQ_MARGIN + 16); blockbuf2[1] = malloc(((uint64_t)256 << 20) + FQ_MARGIN + 16); cur_buf = 0; }
 						if (g_fq_mmap || (blockbuf2[0] && blockbuf2[1])) {
 							par_file = 1; map = NULL; map_size = (uint64_t)sb.st_size; map_pos = 0; n_recs = i_rec = 0;
@@ -388,7 +408,7 @@ static void *reader_main(void *arg)
 					}
 				}
 				plen = read_record(&st, &rec);
-				if (plen < 0) { if (st.fp) gzclose(st.fp); else close(st.fd); stream_open = 0; file_i++; continue; }   /* -1 end of file; -2 ends the file like the reference ends its run */
+				if (plen < 0) { if (st.q) st_release_queue(&st); else if (st.fp) gzclose(st.fp); else close(st.fd); stream_open = 0; file_i++; continue; }   /* -1 end of file; -2 ends the file like the reference ends its run */
 				pending = 1;
 			}
 			const size_t L = (size_t)plen;
@@ -414,7 +434,10 @@ static void *reader_main(void *arg)
 	free(blockbuf2[0]); free(blockbuf2[1]);
 	for (int t = 0; t < 64; t++) free(lists[t].r);
 	free(recs);
-	free(st.buf); free(rec.name); free(rec.seq); free(rec.qual);
+	st_release_queue(&st);
+	for (int i = 0; i < sh->n_files; i++) gzq_close(gzq[i]);
+	free(gzq);
+	free(st.own_buf); free(rec.name); free(rec.seq); free(rec.qual);
 	return NULL;
 }
 

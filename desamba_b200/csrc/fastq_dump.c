@@ -8,7 +8,7 @@
 
 static int dump_serial(int fd, uint64_t from)
 {
-	stream_t st; memset(&st, 0, sizeof st); st.buf = malloc(SBUF); st.fd = fd; st.need_qual = 1;
+	stream_t st; memset(&st, 0, sizeof st); st.buf = malloc(SBUF); st.own_buf = st.buf; st.fd = fd; st.need_qual = 1;
 	lseek(fd, (off_t)from, SEEK_SET);
 	rec_t rec; memset(&rec, 0, sizeof rec);
 	long L;

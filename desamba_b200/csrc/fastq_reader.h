@@ -19,16 +19,106 @@
 #include <pthread.h>
 #include <zlib.h>
 
+/* ---------------------------------------------------------------- .gz input inflated ahead of the parser
+ * A gzip stream cannot be inflated in parallel, but the files of a run can: each of the next few .gz files of the command line
+ * gets a thread that inflates it into a bounded queue of chunks, so the parser never waits for zlib on inputs that come as many
+ * files (a sequencer's output directory), and on a single file inflating at least overlaps parsing. */
+#define GZ_CHUNK (4 << 20)
+#define GZ_QUEUE_CAP ((size_t)128 << 20)         /* inflated bytes a file may be ahead of the parser */
+typedef struct gz_chunk { struct gz_chunk *next; int n; unsigned char data[GZ_CHUNK]; } gz_chunk_t;
+typedef struct {
+	int fd; gzFile fp; pthread_t th; int started, done, stop;
+	pthread_mutex_t mu; pthread_cond_t cv;
+	gz_chunk_t *head, *tail; size_t queued;
+} gzq_t;
+static __attribute__((unused)) void *gzq_main(void *a)
+{
+	gzq_t *q = (gzq_t *)a;
+	for (;;) {
+		pthread_mutex_lock(&q->mu);
+		while (q->queued >= GZ_QUEUE_CAP && !q->stop) pthread_cond_wait(&q->cv, &q->mu);
+		const int stop = q->stop;
+		pthread_mutex_unlock(&q->mu);
+		if (stop) break;
+		gz_chunk_t *c = (gz_chunk_t *)malloc(sizeof(gz_chunk_t));
+		if (!c) break;
+		c->next = NULL;
+		c->n = gzread(q->fp, c->data, GZ_CHUNK);
+		if (c->n <= 0) { free(c); break; }              /* end of the stream (or a damaged one: the file ends here, as with gzread in the parser) */
+		pthread_mutex_lock(&q->mu);
+		if (q->tail) q->tail->next = c; else q->head = c;
+		q->tail = c; q->queued += (size_t)c->n;
+		pthread_cond_broadcast(&q->cv);
+		pthread_mutex_unlock(&q->mu);
+	}
+	pthread_mutex_lock(&q->mu);
+	q->done = 1;
+	pthread_cond_broadcast(&q->cv);
+	pthread_mutex_unlock(&q->mu);
+	return NULL;
+}
+/* takes over fd (a gzip file positioned at its start); NULL if the thread cannot be started (fd stays open) */
+static __attribute__((unused)) gzq_t *gzq_start(int fd)
+{
+	gzq_t *q = (gzq_t *)calloc(1, sizeof(gzq_t));
+	if (!q) return NULL;
+	q->fd = fd; q->fp = gzdopen(fd, "r");
+	if (!q->fp) { free(q); return NULL; }
+	gzbuffer(q->fp, 1 << 20);
+	pthread_mutex_init(&q->mu, NULL); pthread_cond_init(&q->cv, NULL);
+	if (pthread_create(&q->th, NULL, gzq_main, q) != 0) { free(q); return NULL; }   /* (gzFile leaks its small state; the caller goes on with the fd) */
+	q->started = 1;
+	return q;
+}
+/* next chunk (blocking); NULL at the end of the stream */
+static __attribute__((unused)) gz_chunk_t *gzq_pop(gzq_t *q)
+{
+	pthread_mutex_lock(&q->mu);
+	while (!q->head && !q->done) pthread_cond_wait(&q->cv, &q->mu);
+	gz_chunk_t *c = q->head;
+	if (c) { q->head = c->next; if (!q->head) q->tail = NULL; q->queued -= (size_t)c->n; pthread_cond_broadcast(&q->cv); }
+	pthread_mutex_unlock(&q->mu);
+	return c;
+}
+static __attribute__((unused)) void gzq_close(gzq_t *q)
+{
+	if (!q) return;
+	pthread_mutex_lock(&q->mu); q->stop = 1; pthread_cond_broadcast(&q->cv); pthread_mutex_unlock(&q->mu);
+	pthread_join(q->th, NULL);
+	for (gz_chunk_t *c = q->head; c;) { gz_chunk_t *nx = c->next; free(c); c = nx; }
+	gzclose(q->fp);
+	pthread_mutex_destroy(&q->mu); pthread_cond_destroy(&q->cv);
+	free(q);
+}
+
 /* ---------------------------------------------------------------- serial reader (kseq_read semantics, utils.c:939-977) */
-typedef struct { gzFile fp; int fd; unsigned char *buf; int n, pos, eof; int last_char; int need_qual; } stream_t;
+typedef struct {
+	gzFile fp; int fd; unsigned char *buf; int n, pos, eof; int last_char; int need_qual;
+	gzq_t *q; gz_chunk_t *chunk; unsigned char *own_buf;      /* q: the stream comes from an inflating thread, buf points into its current chunk */
+} stream_t;
 #define SBUF (4 << 20)
 /* plain files are read with read(2) (zlib's transparent mode costs an extra copy of every byte); .gz through zlib */
 static inline int st_fill(stream_t *s)
 {
+	if (s->q) {
+		if (s->chunk) { free(s->chunk); s->chunk = NULL; }
+		s->chunk = gzq_pop(s->q);
+		s->pos = 0;
+		if (!s->chunk) { s->buf = s->own_buf; s->eof = 1; s->n = 0; return -1; }
+		s->buf = s->chunk->data; s->n = s->chunk->n;
+		return 0;
+	}
 	s->n = s->fp ? gzread(s->fp, s->buf, SBUF) : (int)read(s->fd, s->buf, SBUF);
 	s->pos = 0;
 	if (s->n <= 0) { s->eof = 1; s->n = 0; return -1; }
 	return 0;
+}
+/* a stream is detached from its inflating thread when its file is done */
+static inline void st_release_queue(stream_t *s)
+{
+	if (s->chunk) { free(s->chunk); s->chunk = NULL; }
+	if (s->q) { gzq_close(s->q); s->q = NULL; }
+	if (s->own_buf) s->buf = s->own_buf;
 }
 static inline int st_getc(stream_t *s)
 {

@@ -200,3 +200,39 @@ def test_driver_text_of_large_batches_formatted_by_helper_threads(ob, tmp_path):
     r = subprocess.run([DRIVER, "classify", "-f", "SAM_FULL", "-B", "5000", "-P", "4", "no_index_needed", p], capture_output=True,
                        env=dict(os.environ, DSB_HOST_ONLY="1"))
     assert r.returncode == 0 and r.stdout == want
+
+
+def test_gz_files_are_inflated_ahead_of_the_parser(ob, tmp_path):
+    """.gz inputs: the next few files of the command line are inflated by threads of their own into bounded queues; the text is
+    that of the one-stream reader (DSB_GZ_AHEAD=0), whatever the mix of plain and compressed files, chunk boundaries included"""
+    import gzip
+    rng = np.random.default_rng(15)
+    files, allrec = [], []
+    for i in range(9):
+        recs = _records(rng, 40 if i % 3 else 3000, 50, 3000 if i != 4 else 9000, b"g%d_" % i)
+        path = str(tmp_path / f"part{i}.fq")
+        if i in (2, 6):                                   # plain files between the compressed ones
+            open(path, "wb").write(_fastq(recs))
+        else:
+            path += ".gz"
+            with gzip.open(path, "wb", compresslevel=1) as f:
+                f.write(_fastq(recs, crlf=(i == 5)))
+        files.append(path); allrec += recs
+    empty = str(tmp_path / "empty.fq.gz")
+    with gzip.open(empty, "wb") as f:
+        pass
+    files.insert(3, empty)
+    want = b"".join(n + b"\t4\t*\t0\t0\t*\t*\t0\t0\t" + s + b"\t" + q + b"\t\n" for n, s, q in allrec)
+    assert sum(len(s) for _, s, _ in allrec) > 12 << 20          # several 4-MB chunks per large file
+    for env, opts in (({"DSB_GZ_AHEAD": "0"}, ("-B", 700)), ({}, ("-B", 700)), ({"DSB_GZ_AHEAD": "1"}, ("-B", 5000, "-P", 3)),
+                      ({"DSB_GZ_AHEAD": "3"}, ("-B", 97, "-P", 0)), ({"DSB_GZ_AHEAD": "16"}, ("-B", 100000, "-P", 8))):
+        got, err = _host_only(tmp_path, files, "SAM_FULL", env, *opts)
+        assert got == want, (env, opts)
+        assert "%d sequences processed" % len(allrec) in err
+    # a damaged stream ends its file where zlib gives up, like the one-stream reader; the files behind it are read
+    bad = str(tmp_path / "cut.fq.gz")
+    blob = open(files[0], "rb").read()
+    open(bad, "wb").write(blob[: len(blob) // 2])
+    a, _ = _host_only(tmp_path, [bad, files[1]], "DES", {"DSB_GZ_AHEAD": "0"}, "-B", 500)
+    b, _ = _host_only(tmp_path, [bad, files[1]], "DES", {}, "-B", 500)
+    assert a == b and a.count(b"UNCLASSIFY") > 40
