@@ -372,6 +372,8 @@ static void *reader_main(void *arg)
 					/* start inflating the .gz files among this one and the next gz_ahead - 1 */
 					if (gz_next < file_i) gz_next = file_i;
 					for (; gz_ahead > 0 && gz_next < sh->n_files && gz_next < file_i + gz_ahead; gz_next++) {
+						struct stat sb2;
+						if (stat(sh->files[gz_next], &sb2) != 0 || !S_ISREG(sb2.st_mode)) continue;   /* regular files only: opening a FIFO ahead of its turn could block */
 						const int fd2 = open(sh->files[gz_next], O_RDONLY);
 						if (fd2 < 0) continue;                 /* (reported when its turn comes) */
 						unsigned char mg[2] = {0, 0};
