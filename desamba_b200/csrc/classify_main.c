@@ -388,7 +388,8 @@ static void *reader_main(void *arg)
 						st.fd = open(sh->files[file_i], O_RDONLY);
 						if (st.fd < 0) { fprintf(stderr, "[xzopen] fail to open file '%s'\n", sh->files[file_i]); fail(sh, "open reads", -2); end_of_input = 1; break; }
 						got = (int)pread(st.fd, magic, 2, 0);
-						if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+						/* gzip by its magic; a pipe cannot be looked into without consuming it: zlib reads it, compressed or not */
+						if ((got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) || got < 0) {
 							st.fp = gzdopen(st.fd, "r");
 							if (!st.fp) { fail(sh, "gzdopen", -2); end_of_input = 1; break; }
 							gzbuffer(st.fp, 1 << 20);

@@ -236,3 +236,17 @@ def test_gz_files_are_inflated_ahead_of_the_parser(ob, tmp_path):
     a, _ = _host_only(tmp_path, [bad, files[1]], "DES", {"DSB_GZ_AHEAD": "0"}, "-B", 500)
     b, _ = _host_only(tmp_path, [bad, files[1]], "DES", {}, "-B", 500)
     assert a == b and a.count(b"UNCLASSIFY") > 40
+
+
+def test_reads_from_pipes_plain_or_gzip(ob, tmp_path):
+    """inputs that cannot be looked into without consuming them (stdin, process substitution) go through zlib, compressed or not
+    -- the reference reads everything with gzread (utils.c:835-977)"""
+    import gzip
+    rng = np.random.default_rng(16)
+    recs = _records(rng, 300, 40, 400, b"s")
+    plain = _fastq(recs)
+    want = b"".join(n + b"\tUNCLASSIFY\tSLOW\t%d\tn_rst:[0]\tn_anc:[0]\t\n\n" % len(s) for n, s, q in recs)
+    e = dict(os.environ, DSB_HOST_ONLY="1")
+    for blob in (plain, gzip.compress(plain, 1)):
+        r = subprocess.run([DRIVER, "classify", "-f", "DES", "no_index_needed", "/dev/stdin"], input=blob, capture_output=True, env=e)
+        assert r.returncode == 0 and r.stdout == want
