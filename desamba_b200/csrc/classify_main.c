@@ -77,6 +77,7 @@ typedef struct {
 	int has_long, has_short;
 	uint32_t m_bin_read_in;                 /* capacity of the reference's bin_read buffer before this batch (dsb_ctx_set_bin_capacity) */
 	uint64_t n_hits;
+	uint32_t *long_r, *long_l; uint32_t n_long, m_long;   /* reads longer than -L: (index in the batch, true length), ascending; they travel with no bases */
 } slot_t;
 
 typedef struct {
@@ -88,6 +89,7 @@ typedef struct {
 	bo_slot *bo;                            /* per slot: what batch_order.h needs (kept under mu) */
 	uint64_t done_upto; int32_t prefix_max; /* every batch below done_upto is finished; max_read_l after them */
 	uint64_t n_capacity_reads;              /* reads that exceeded a per-read capacity: written as unclassified, with a warning */
+	uint64_t n_long_reads;                  /* reads longer than -L: written as unclassified, with a warning */
 	int error; char errmsg[600];
 	int n_files; char **files;
 	uint64_t total_sequences;
@@ -147,6 +149,24 @@ static int grow_pinned(void **p, size_t *m, size_t need, size_t keep, size_t ful
 	*p = np; *m = nm;
 	g_t_pinned += now_s() - t0; g_n_pinned++;
 	return 0;
+}
+
+/* A read longer than the longest the contexts accept (-L, dsb_opts.max_read_len) does not end the run: it goes into its batch
+ * with no bases (the GPU sees an empty read), is written as unclassified with its true length, and is counted for a warning. */
+static uint32_t g_max_read_len = 1u << 20;
+static void slot_note_long(slot_t *b, uint32_t r, uint32_t L)
+{
+	if (b->n_long == b->m_long) { b->m_long = b->m_long ? b->m_long * 2 : 16; b->long_r = xrealloc(b->long_r, b->m_long * 4); b->long_l = xrealloc(b->long_l, b->m_long * 4); }
+	b->long_r[b->n_long] = r; b->long_l[b->n_long] = L; b->n_long++;
+}
+static inline uint32_t slot_true_len(const slot_t *b, uint32_t r, uint32_t L, int *is_long)
+{
+	*is_long = 0;
+	if (!b->n_long) return L;
+	uint32_t lo = 0, hi = b->n_long;
+	while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (b->long_r[mid] < r) lo = mid + 1; else hi = mid; }
+	if (lo < b->n_long && b->long_r[lo] == r) { *is_long = 1; return b->long_l[lo]; }
+	return L;
 }
 
 /* one record into the batch (serial path) */
@@ -296,6 +316,7 @@ static void *reader_main(void *arg)
 	prefetch_t pf; memset(&pf, 0, sizeof pf);
 	fq_list_t lists[64]; memset(lists, 0, sizeof lists);
 	fq_rec_t *recs = NULL; size_t m_recs = 0, n_recs = 0, i_rec = 0;
+	struct { size_t i; uint32_t len; } *long_rec = NULL; size_t n_long_rec = 0, m_long_rec = 0;   /* over-long records of the indexed block */
 	const int n_thr = o->n_parse_threads;
 	for (;;) {
 		const double tw0 = now_s();
@@ -310,17 +331,23 @@ static void *reader_main(void *arg)
 		pthread_mutex_lock(&sh->mu);
 		if (sh->n_free_set) b->B = sh->free_set[--sh->n_free_set]; else memset(&b->B, 0, sizeof b->B);
 		pthread_mutex_unlock(&sh->mu);
-		b->n_reads = 0; b->n_bases = 0; b->n_names = 0; b->has_long = b->has_short = 0; b->m_bin_read_in = m_bin_read;
+		b->n_reads = 0; b->n_bases = 0; b->n_names = 0; b->has_long = b->has_short = 0; b->m_bin_read_in = m_bin_read; b->n_long = 0;
 		int end_of_input = 0;
 		while (b->n_reads < o->batch_reads && b->n_bases < o->batch_bases) {
 			if (par_file) {
 				if (i_rec < n_recs) {                   /* as many indexed records as the batch takes */
 					size_t e = i_rec; uint32_t nr = b->n_reads; uint64_t nb = b->n_bases;
 					while (e < n_recs && nr < o->batch_reads && nb < o->batch_bases) { nb += recs[e].n_seq; nr++; e++; }
+					const uint32_t first_in_batch = b->n_reads;
 					const double tc0 = now_s();
 					if (slot_add_block(sh, b, map, recs, i_rec, e, n_thr)) { fail(sh, "pinned alloc", -4); end_of_input = 1; break; }
 					sh->t_rd_copy += now_s() - tc0;
 					for (size_t i = i_rec; i < e; i++) { const size_t L = recs[i].n_seq; if (L >= 40 && 2 * L > m_bin_read) m_bin_read = (uint32_t)(2 * L + 20); }
+					for (size_t k = 0; k < n_long_rec; k++)
+						if (long_rec[k].i >= i_rec && long_rec[k].i < e) {
+							slot_note_long(b, first_in_batch + (uint32_t)(long_rec[k].i - i_rec), long_rec[k].len);
+							if (2 * (uint64_t)long_rec[k].len > m_bin_read) m_bin_read = (uint32_t)(2 * (uint64_t)long_rec[k].len + 20);
+						}
 					i_rec = e;
 					continue;
 				}
@@ -345,6 +372,13 @@ static void *reader_main(void *arg)
 					sh->t_rd_read += tr1 - tr0; sh->t_rd_index += now_s() - tr1;
 					if (n >= 0) {
 						n_recs = (size_t)n; i_rec = 0; map_pos = next;
+						n_long_rec = 0;
+						for (size_t i = 0; i < n_recs; i++)
+							if (recs[i].n_seq > g_max_read_len) {
+								if (n_long_rec == m_long_rec) { m_long_rec = m_long_rec ? m_long_rec * 2 : 16; long_rec = xrealloc(long_rec, m_long_rec * sizeof *long_rec); }
+								long_rec[n_long_rec].i = i; long_rec[n_long_rec].len = recs[i].n_seq; n_long_rec++;
+								recs[i].n_seq = 0;
+							}
 						if (next < map_size) {             /* read ahead while this block's records go into batches */
 							pf.fd = st.fd; pf.n_thr = n_thr; pf.pos = next; pf.buf = blockbuf2[cur_buf ^ 1];
 							pf.len = (map_size - next < FQ_BLOCK + FQ_MARGIN) ? map_size - next : FQ_BLOCK + FQ_MARGIN;
@@ -414,7 +448,8 @@ static void *reader_main(void *arg)
 				if (plen < 0) { if (st.q) st_release_queue(&st); else if (st.fp) gzclose(st.fp); else close(st.fd); stream_open = 0; file_i++; continue; }   /* -1 end of file; -2 ends the file like the reference ends its run */
 				pending = 1;
 			}
-			const size_t L = (size_t)plen;
+			size_t L = (size_t)plen;
+			if (L > g_max_read_len) { slot_note_long(b, b->n_reads, (uint32_t)(L > 0xffffffffu ? 0xffffffffu : L)); if (2 * L > m_bin_read) m_bin_read = (uint32_t)(2 * L + 20); L = 0; rec.n_qual = 0; }
 			if (slot_add(sh, b, rec.name, rec.n_name, rec.seq, rec.qual, rec.n_qual, L)) { fail(sh, "pinned alloc", -4); end_of_input = 1; break; }
 			if (L >= 40 && 2 * L > m_bin_read) m_bin_read = (uint32_t)(2 * L + 20);
 			pending = 0;
@@ -436,7 +471,7 @@ static void *reader_main(void *arg)
 	block_release(&cur); block_release(&stale);
 	free(blockbuf2[0]); free(blockbuf2[1]);
 	for (int t = 0; t < 64; t++) free(lists[t].r);
-	free(recs);
+	free(recs); free(long_rec);
 	st_release_queue(&st);
 	for (int i = 0; i < sh->n_files; i++) gzq_close(gzq[i]);
 	free(gzq);
@@ -557,7 +592,7 @@ static void put_hit(obuf_t *ob, const dsb_hit *c, const dsb_ref_info *ri, int rs
 }
 
 static void format_read(obuf_t *ob, const opts_t *o, const dsb_ref_info *ri, const dsb_read_result *r, const dsb_hit *hits,
-                        const char *name, const char *seq, const char *qual, uint32_t L)
+                        const char *name, const char *seq, const char *qual, uint32_t L, int no_bases)
 {
 	const size_t ln = strlen(name);
 	const dsb_hit *c_s = hits + r->hit_off, *c_e = c_s + r->n_hit;
@@ -572,7 +607,7 @@ static void format_read(obuf_t *ob, const opts_t *o, const dsb_ref_info *ri, con
 		ob_need(ob, 2); ob->s[ob->n++] = '\n';
 		return;
 	}
-	const int full = o->fmt == FMT_SAM_FULL;                        /* output_one_result_sam, cly_mt.c:248-344 */
+	const int full = o->fmt == FMT_SAM_FULL && !no_bases;           /* output_one_result_sam, cly_mt.c:248-344 (a read longer than -L has no bases here: '*') */
 	const size_t lsq = full ? L : 1;
 	ob_need(ob, ln + 2 * lsq + 400);
 	char *p = ob->s + ob->n;
@@ -636,8 +671,8 @@ static void *fmt_thread(void *a)
 {
 	fmt_job_t *j = (fmt_job_t *)a; slot_t *b = j->b;
 	for (uint32_t r = j->r0; r < j->r1; r++) {
-		const uint32_t L = (uint32_t)(b->offs[r + 1] - b->offs[r]);
-		format_read(&j->ob, j->o, j->ri, b->rr + r, b->hits, b->names + b->name_off[r], b->seqs + b->offs[r], b->quals ? b->quals + b->offs[r] : NULL, L);
+		int lg; const uint32_t L = slot_true_len(b, r, (uint32_t)(b->offs[r + 1] - b->offs[r]), &lg);
+		format_read(&j->ob, j->o, j->ri, b->rr + r, b->hits, b->names + b->name_off[r], b->seqs + b->offs[r], b->quals ? b->quals + b->offs[r] : NULL, L, lg);
 	}
 	return NULL;
 }
@@ -688,6 +723,7 @@ static int classify_main(int argc, char **argv)
 	g_host_only = getenv("DSB_HOST_ONLY") != NULL;     /* test / developer aid: reader + writer only -- no device is opened, every read is written as unclassified */
 	if (getenv("DSB_FQ_BLOCK_MB") && atol(getenv("DSB_FQ_BLOCK_MB")) >= 1 && atol(getenv("DSB_FQ_BLOCK_MB")) <= 256) g_fq_block = (uint64_t)atol(getenv("DSB_FQ_BLOCK_MB")) << 20;
 	if (getenv("DSB_FQ_BLOCK_KB") && atol(getenv("DSB_FQ_BLOCK_KB")) >= 1 && atol(getenv("DSB_FQ_BLOCK_KB")) <= (256 << 10)) g_fq_block = (uint64_t)atol(getenv("DSB_FQ_BLOCK_KB")) << 10;   /* tests */
+	{ dsb_opts d0; dsb_opts_default(&d0); g_max_read_len = o.max_read_len ? o.max_read_len : d0.max_read_len; }
 	const double t_start = now_s();
 	#define STAMP(what) do { if (verbose) fprintf(stderr, "[deSAMBA-b200] %-34s at %7.3f s\n", what, now_s() - t_start); } while (0)
 	/* the reader starts at once: the first batches are parsed while the index is loaded into HBM */
@@ -790,13 +826,14 @@ static int classify_main(int argc, char **argv)
 		} else {
 			ob.n = 0;
 			for (uint32_t r = 0; r < b->n_reads; r++) {
-				const uint32_t L = (uint32_t)(b->offs[r + 1] - b->offs[r]);
-				format_read(&ob, &o, ri, b->rr + r, b->hits, b->names + b->name_off[r], b->seqs + b->offs[r], b->quals ? b->quals + b->offs[r] : NULL, L);
+				int lg; const uint32_t L = slot_true_len(b, r, (uint32_t)(b->offs[r + 1] - b->offs[r]), &lg);
+				format_read(&ob, &o, ri, b->rr + r, b->hits, b->names + b->name_off[r], b->seqs + b->offs[r], b->quals ? b->quals + b->offs[r] : NULL, L, lg);
 				if (ob.n > (8u << 20)) { fwrite(ob.s, 1, ob.n, o.out); ob.n = 0; }
 			}
 			fwrite(ob.s, 1, ob.n, o.out);
 		}
 		sh.t_writer_fmt += now_s() - tq1;
+		sh.n_long_reads += b->n_long;
 		pthread_mutex_lock(&sh.mu);
 		sh.free_set[sh.n_free_set++] = b->B; memset(&b->B, 0, sizeof b->B);
 		b->state = SLOT_FREE; sh.n_written++;
@@ -821,6 +858,7 @@ static int classify_main(int argc, char **argv)
 	fprintf(stderr, "%ld sequences processed in %.3fs (%.1f Kseq/m).\n", (long)sh.total_sequences, sec, sh.total_sequences / 1.0e3 / (sec / 60));   /* report_stats, cly_mt.c:439-446 */
 	fprintf(stderr, "Classify CPU: %.3f sec\n", cpu_s() - c0);
 	fprintf(stderr, "GPUs: %d (%d contexts each); index: %.3f s load on GPU 0 + %.3f s device-to-device copies\n", n_gpus, o.ctx_per_gpu, t_load0, t_clone);
+	if (sh.n_long_reads) fprintf(stderr, "[deSAMBA-b200] warning: %llu read(s) longer than %u bases were written as unclassified (raise -L)\n", (unsigned long long)sh.n_long_reads, g_max_read_len);
 	if (sh.n_capacity_reads) fprintf(stderr, "[deSAMBA-b200] warning: %llu read(s) exceeded a per-read capacity and were written as unclassified (raise -A / -m)\n", (unsigned long long)sh.n_capacity_reads);
 	/* Freeing tens of GB of device memory buffer by buffer took 0.2 - 3.8 s here; the process is over and the driver reclaims all
 	 * of it at once.  DSB_FREE_AT_EXIT=1 keeps the orderly teardown (leak checkers). */

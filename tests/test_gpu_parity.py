@@ -452,3 +452,29 @@ def test_next_batch_uploaded_while_the_current_one_runs(gpu, ob):
     used, _ = c2.download_into(rr, hits)
     assert ob.compare_results(rr, hits[:used], want[0].rr, want[0].hits, None, max_report=3) == []
     c2.close()
+
+
+def test_driver_reads_longer_than_the_limit_are_unclassified_not_fatal(gpu, ob, demo_index):
+    """-L below the longest read of the set: those reads come out unclassified with their true length, every other read as in
+    the run without the limit, and the run ends normally with a warning"""
+    path = _set_path(ob, "long10")
+    _, seqs, _ = ob.read_fastq(path)
+    lens = sorted(len(s) for s in seqs)
+    limit = lens[len(lens) * 2 // 3]
+    n_over = sum(1 for l in lens if l > limit)
+    assert 0 < n_over < len(lens)
+
+    def blocks(text):
+        return [b for b in text.split(b"\n\n") if b]
+    full = blocks(_run_driver(["-f", "DES", demo_index, path]))
+    r = subprocess.run([DRIVER, "classify", "-f", "DES", "-L", str(limit), "-B", "64", demo_index, path], capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-1000:]
+    assert ("%d read(s) longer than %d bases" % (n_over, limit)).encode() in r.stderr
+    cut = blocks(r.stdout)
+    assert len(full) == len(cut) == len(seqs)
+    for a, b, s in zip(full, cut, seqs):
+        if len(s) > limit:
+            name = a.split(b"\t", 1)[0]
+            assert b == name + b"\tUNCLASSIFY\tFAST\t%d\tn_rst:[0]\tn_anc:[0]\t" % len(s)      # (the record of a read classify_seq does not look at, like one below 40 bp)
+        else:
+            assert a == b

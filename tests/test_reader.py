@@ -250,3 +250,25 @@ def test_reads_from_pipes_plain_or_gzip(ob, tmp_path):
     for blob in (plain, gzip.compress(plain, 1)):
         r = subprocess.run([DRIVER, "classify", "-f", "DES", "no_index_needed", "/dev/stdin"], input=blob, capture_output=True, env=e)
         assert r.returncode == 0 and r.stdout == want
+
+
+def test_reads_longer_than_the_limit_do_not_end_the_run(ob, tmp_path):
+    """a read longer than -L travels without bases, is written as unclassified with its true length (no bases in SAM_FULL: '*')
+    and counted for a warning -- through the block indexer, the one-stream reader and gzip"""
+    import gzip
+    rng = np.random.default_rng(17)
+    recs = _records(rng, 700, 20, 900, b"L")
+    n_over = sum(1 for _, s, _ in recs if len(s) > 300)
+    assert 100 < n_over < 650
+    plain = str(tmp_path / "l.fq"); open(plain, "wb").write(_fastq(recs))
+    gz = str(tmp_path / "l.fq.gz"); open(gz, "wb").write(gzip.compress(_fastq(recs), 1))
+    want_des = b"".join(n + b"\tUNCLASSIFY\tSLOW\t%d\tn_rst:[0]\tn_anc:[0]\t\n\n" % len(s) for n, s, q in recs)
+    want_full = b"".join(n + b"\t4\t*\t0\t0\t*\t*\t0\t0\t" + ((s + b"\t" + q) if len(s) <= 300 else b"*\t*") + b"\t\n" for n, s, q in recs)
+    for files, env, opts in (([plain], {"DSB_FQ_BLOCK_KB": "64"}, ("-B", 90, "-P", 4)), ([plain], {}, ("-B", 5000, "-P", 0)), ([gz, plain], {}, ("-B", 64, "-P", 3))):
+        got, err = _host_only(tmp_path, files, "DES", env, "-L", 300, *opts)
+        assert got == want_des * len(files), (files, env, opts)
+        assert "%d read(s) longer than 300 bases" % (n_over * len(files)) in err
+        got, _ = _host_only(tmp_path, files, "SAM_FULL", env, "-L", 300, *opts)
+        assert got == want_full * len(files), (files, env, opts)
+    got, err = _host_only(tmp_path, [plain], "DES", {}, "-B", 200)        # the default limit is 1 Mbase: nothing is held back
+    assert got == want_des and "longer than" not in err
